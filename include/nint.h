@@ -1,0 +1,92 @@
+/* nint.h -- C ABI of the B200-native Smart-NINT ConvLSTM hot path (libnint.so, sm_100a).
+ *
+ * The reference (smhassanerfani/nasa-niswan) has no FFI layer: its boundary for this path is the
+ * Python class surface of model.py.  Each entry point below names the reference code it replaces
+ * (file:line into the upstream repository).  Plain pointers and sizes only; every pointer is a
+ * DEVICE pointer unless it says "host"; `stream` is a cudaStream_t passed as void*.
+ * All functions return 0 on success and a non-zero code on failure; nint_last_error() returns a
+ * thread-local description.  There is no CPU fallback: without a CUDA device every compute call
+ * fails.
+ *
+ * Tensors crossing the boundary keep the reference's layouts:
+ *   x      [B,T,C,H,W] fp32            (model.py:253-255)
+ *   h, c   [B,Hc,H,W]  fp32            (model.py:216-217, 258-262)
+ *   weight [4*Hc, C+Hc, k, k] fp32, bias [4*Hc]     (model.py:207-211; gate order i,f,g,o model.py:221)
+ *   head   weight [1,Hc_last,1,1], bias [1]         (model.py:251)
+ *   pred   [B,1,H,W] fp32 ; seq [B,T,H,W] fp32      (model.py:274 ; commented variant model.py:264,272)
+ */
+#ifndef NINT_H_
+#define NINT_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NINT_MAX_LAYERS 8
+#define NINT_DTYPE_BF16 0 /* bf16 operands, fp32 accumulation and cell state */
+#define NINT_DTYPE_TF32 1 /* tf32 operands (fp32 storage), fp32 accumulation */
+
+typedef struct nint_plan nint_plan;
+
+/* Geometry of one ConvLSTM (model.py:235-251: ConvLSTM(input_channels, hidden_channels[],
+ * kernel_size[], num_layers)) plus the batch/sequence shape of the calls it will serve. */
+typedef struct nint_config {
+  int32_t batch, seq_len, height, width; /* B, T, H, W of x (model.py:255) */
+  int32_t in_channels;                   /* C */
+  int32_t num_layers;                    /* L <= NINT_MAX_LAYERS */
+  int32_t hidden[NINT_MAX_LAYERS];       /* Hc_l: multiple of 16; multiple of 64 when > 64; <= 256 */
+  int32_t ksize[NINT_MAX_LAYERS];        /* odd (model.py:204: padding = k // 2) */
+  int32_t dtype;                         /* NINT_DTYPE_* */
+  int32_t training;                      /* 1: keep gates/c/h of every step for BPTT */
+  int32_t return_sequence;               /* 1: also apply the head at every t (model.py:264,272) */
+} nint_config;
+
+int nint_version(void);
+const char* nint_last_error(void);
+
+/* ---- plan life cycle (host-side object; owns no device memory) */
+int nint_plan_create(const nint_config* cfg, nint_plan** out);
+void nint_plan_destroy(nint_plan* plan);
+/* device workspace the caller must provide (torch allocates it): activations, saved gates/states,
+ * packed weights, gradient accumulators */
+size_t nint_plan_workspace_bytes(const nint_plan* plan);
+/* attaches the workspace (256-byte aligned device pointer), zero-fills it and encodes the TMA
+ * tensor maps */
+int nint_plan_bind(nint_plan* plan, void* workspace, size_t bytes, void* stream);
+
+/* ---- parameters: repack the fp32 OIHW masters (state_dict names layers.{l}.conv.weight/bias,
+ * conv.weight/bias; utils.py:27,39) into tensor-core operand panels.  Call after every
+ * optimizer step. */
+int nint_plan_set_weights(nint_plan* plan, int layer, const float* weight, const float* bias, void* stream);
+int nint_plan_set_head(nint_plan* plan, const float* weight, const float* bias, void* stream);
+
+/* ---- recurrent state.  model.py:258-262 starts every forward from zeros (the default);
+ * ConvLSTMCell.forward (model.py:216-217) takes an explicit (h, c). */
+int nint_plan_reset_state(nint_plan* plan, void* stream);
+int nint_plan_set_state(nint_plan* plan, int layer, const float* h, const float* c, void* stream);
+int nint_plan_get_state(nint_plan* plan, int layer, float* h, float* c, void* stream);
+
+/* ---- ConvLSTM.forward (model.py:253-274): T x L fused cell steps + head.
+ * pred [B,1,H,W]; seq [B,T,H,W] or NULL (requires return_sequence). */
+int nint_forward(nint_plan* plan, const float* x, float* pred, float* seq, void* stream);
+
+/* ---- BPTT of the last nint_forward (replaces autograd over model.py:216-274, train.py:109).
+ * dpred [B,1,H,W], dseq [B,T,H,W] or NULL.  grad_weight[l] / grad_bias[l] are host arrays of
+ * device pointers with the parameters' shapes; gradients are WRITTEN (not accumulated). */
+int nint_backward(nint_plan* plan, const float* dpred, const float* dseq, float* const* grad_weight,
+                  float* const* grad_bias, float* grad_head_weight, float* grad_head_bias, void* stream);
+
+/* ---- test hook: raw gate pre-activations of layer 0 at t = 0 without bias,
+ * out [B,H,W,4*Hc] fp32 in kernel column order (see nint_gate_column). */
+int nint_debug_raw_gates(nint_plan* plan, const float* x, float* out, void* stream);
+/* reference gate channel n = gate*Hc + c for kernel column q of a layer with Hc hidden channels */
+int nint_gate_column(int q, int hidden);
+/* pixel tile chosen for a grid (host-only helper, no device needed) */
+int nint_pick_tile(int height, int width, int* tile_w, int* tile_h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NINT_H_ */

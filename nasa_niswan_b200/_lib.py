@@ -1,0 +1,67 @@
+"""ctypes binding of libnint.so (include/nint.h).  No CPU fallback: a missing library or a
+machine without a B200 makes every compute call raise."""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libnint.so")
+MAX_LAYERS = 8
+DTYPE_BF16, DTYPE_TF32 = 0, 1
+EXPORTS = ["nint_version", "nint_last_error", "nint_plan_create", "nint_plan_destroy", "nint_plan_workspace_bytes",
+           "nint_plan_bind", "nint_plan_set_weights", "nint_plan_set_head", "nint_plan_reset_state",
+           "nint_plan_set_state", "nint_plan_get_state", "nint_forward", "nint_backward", "nint_debug_raw_gates",
+           "nint_gate_column", "nint_pick_tile"]
+
+
+class NintConfig(ctypes.Structure):
+    _fields_ = [("batch", ctypes.c_int32), ("seq_len", ctypes.c_int32), ("height", ctypes.c_int32),
+                ("width", ctypes.c_int32), ("in_channels", ctypes.c_int32), ("num_layers", ctypes.c_int32),
+                ("hidden", ctypes.c_int32 * MAX_LAYERS), ("ksize", ctypes.c_int32 * MAX_LAYERS),
+                ("dtype", ctypes.c_int32), ("training", ctypes.c_int32), ("return_sequence", ctypes.c_int32)]
+
+
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: build it with `python -m nasa_niswan_b200.build` "
+                           "(there is no CPU or PyTorch fallback for the ConvLSTM hot path)")
+    L = ctypes.CDLL(LIB_PATH)
+    vp, ci, fp = ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p  # device pointers travel as void*
+    L.nint_version.restype = ci
+    L.nint_last_error.restype = ctypes.c_char_p
+    L.nint_plan_create.argtypes = [ctypes.POINTER(NintConfig), ctypes.POINTER(vp)]
+    L.nint_plan_destroy.argtypes = [vp]
+    L.nint_plan_destroy.restype = None
+    L.nint_plan_workspace_bytes.argtypes = [vp]
+    L.nint_plan_workspace_bytes.restype = ctypes.c_size_t
+    L.nint_plan_bind.argtypes = [vp, vp, ctypes.c_size_t, vp]
+    L.nint_plan_set_weights.argtypes = [vp, ci, fp, fp, vp]
+    L.nint_plan_set_head.argtypes = [vp, fp, fp, vp]
+    L.nint_plan_reset_state.argtypes = [vp, vp]
+    L.nint_plan_set_state.argtypes = [vp, ci, fp, fp, vp]
+    L.nint_plan_get_state.argtypes = [vp, ci, fp, fp, vp]
+    L.nint_forward.argtypes = [vp, fp, fp, fp, vp]
+    L.nint_backward.argtypes = [vp, fp, fp, ctypes.POINTER(vp), ctypes.POINTER(vp), fp, fp, vp]
+    L.nint_debug_raw_gates.argtypes = [vp, fp, fp, vp]
+    L.nint_gate_column.argtypes = [ci, ci]
+    L.nint_pick_tile.argtypes = [ci, ci, ctypes.POINTER(ci), ctypes.POINTER(ci)]
+    for name in EXPORTS:
+        getattr(L, name)  # raises AttributeError if the library does not export what nint.h declares
+    _lib = L
+    return L
+
+
+def check(rc, what):
+    if rc != 0:
+        raise RuntimeError(f"{what}: {load().nint_last_error().decode()}")
+
+
+def pick_tile(height, width):
+    tw, th = ctypes.c_int(), ctypes.c_int()
+    check(load().nint_pick_tile(height, width, ctypes.byref(tw), ctypes.byref(th)), "nint_pick_tile")
+    return tw.value, th.value

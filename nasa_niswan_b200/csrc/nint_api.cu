@@ -1,0 +1,569 @@
+// C-ABI layer (include/nint.h): plan geometry, workspace carving, TMA tensor-map encoding and
+// the host-side step loops of ConvLSTM.forward (model.py:253-274) and its BPTT.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "../../include/nint.h"
+#include "nint_kernels.h"
+
+namespace {
+
+using namespace nint;
+enum : int { BF16 = 0, TF32 = 1 };
+
+thread_local char g_err[512] = "";
+int fail(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return 1;
+}
+#define CK(expr)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e__ = (expr);                                                                      \
+    if (e__ != cudaSuccess) return fail("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Layer {
+  int cin, hc, k, taps;
+  int cx_pad, hc_pad, chx, chh;  // padded channels / 64-byte chunks of the x and h segments
+  int hcb, n_blocks, n_tile;
+  int nslots_h, nslots_c;
+  // workspace pointers
+  uint8_t* Hs = nullptr;   // [nslots_h][B][H][W][hc_pad] E
+  float* Cs = nullptr;     // [nslots_c][B][H][W][hc]
+  uint8_t* G = nullptr;    // [T][B][H][W][4hc] E   (training)
+  float* dC = nullptr;     // [B][H][W][hc]         (training)
+  uint8_t *wx = nullptr, *wh = nullptr, *wdx = nullptr, *wdh = nullptr;
+  float *bias_q = nullptr, *dw_acc = nullptr, *db_acc = nullptr;
+  size_t dw_acc_bytes = 0;
+  int ncols = 0;
+  CUtensorMap tm_H, tm_G, tm_wx, tm_wh, tm_wdx, tm_wdh;
+  bool weights_set = false;
+};
+
+}  // namespace
+
+struct nint_plan {
+  nint_config cfg;
+  int L, B, T, H, W, dtype, esize, ce;
+  int tile_w, tile_h, tiles_x, tiles_y;
+  int num_sms = 148;
+  Layer layer[NINT_MAX_LAYERS];
+  size_t ws_bytes = 0;
+  uint8_t* ws = nullptr;
+  uint8_t* X = nullptr;  // [T][B][H][W][cx_pad0] E
+  CUtensorMap tm_X;
+  float *head_w = nullptr, *head_b = nullptr;
+  bool head_set = false;
+  bool zero_init = true;
+  bool fwd_done = false;
+  int final_slot_h = 0, final_slot_c = 0;
+};
+
+namespace {
+
+int pick_tile(int H, int W, int* tw_out, int* th_out) {
+  long best = -1;
+  int btw = 0, bth = 0;
+  for (int tw = 1; tw <= 128 && tw <= W + 0; ++tw) {
+    int th = 128 / tw;
+    if (th > H) th = H;
+    if (th < 1) continue;
+    const long tiles = static_cast<long>((W + tw - 1) / tw) * ((H + th - 1) / th);
+    // fewer tiles first; then wider rows (longer contiguous TMA runs)
+    if (best < 0 || tiles < best || (tiles == best && tw > btw)) {
+      best = tiles;
+      btw = tw;
+      bth = th;
+    }
+  }
+  *tw_out = btw;
+  *th_out = bth;
+  return 0;
+}
+
+int encode_act_map(CUtensorMap* m, int dtype, void* base, int C, int W, int H, int B, int slots, int ce, int tw,
+                   int th) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail("cuTensorMapEncodeTiled not available (no CUDA driver?)");
+  const cuuint64_t es = dtype == BF16 ? 2 : 4;
+  cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B, (cuuint64_t)slots};
+  cuuint64_t strides[4] = {C * es, (cuuint64_t)W * C * es, (cuuint64_t)H * W * C * es,
+                           (cuuint64_t)B * H * W * C * es};
+  cuuint32_t box[5] = {(cuuint32_t)ce, (cuuint32_t)tw, (cuuint32_t)th, 1, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, dtype == BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, base,
+                   dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(activation C=%d W=%d H=%d B=%d slots=%d) -> %d", C, W, H, B, slots, (int)r);
+  return 0;
+}
+
+int encode_w_map(CUtensorMap* m, int dtype, void* base, long long rows, int ce, int n_tile) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail("cuTensorMapEncodeTiled not available (no CUDA driver?)");
+  const cuuint64_t es = dtype == BF16 ? 2 : 4;
+  cuuint64_t dims[2] = {(cuuint64_t)ce, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {ce * es};
+  cuuint32_t box[2] = {(cuuint32_t)ce, (cuuint32_t)n_tile};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, dtype == BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base,
+                   dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(weights rows=%lld n_tile=%d) -> %d", rows, n_tile, (int)r);
+  return 0;
+}
+
+// UMMA instruction descriptor (kind::f16 / kind::tf32, fp32 accumulate); see nint_common.cuh
+uint32_t idesc_of(int dtype, int m, int n, int a_mn, int b_mn) {
+  const uint32_t fmt = dtype == BF16 ? 1u : 2u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(a_mn & 1) << 15) | ((uint32_t)(b_mn & 1) << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+size_t act_bytes(const nint_plan* p, int slots, int c) {
+  return static_cast<size_t>(slots) * p->B * p->H * p->W * c * p->esize;
+}
+
+// carve (or just measure, when base == nullptr) the workspace
+size_t carve(nint_plan* p, uint8_t* base) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) -> uint8_t* {
+    uint8_t* r = base ? base + off : nullptr;
+    off += align_up(bytes, 1024);
+    return r;
+  };
+  const bool tr = p->cfg.training != 0;
+  const size_t npix = static_cast<size_t>(p->B) * p->H * p->W;
+  p->X = take(act_bytes(p, p->T, p->layer[0].cx_pad));
+  for (int l = 0; l < p->L; ++l) {
+    Layer& y = p->layer[l];
+    y.Hs = take(act_bytes(p, y.nslots_h, y.hc_pad));
+    y.Cs = reinterpret_cast<float*>(take(static_cast<size_t>(y.nslots_c) * npix * y.hc * 4));
+    y.G = tr ? take(act_bytes(p, p->T, 4 * y.hc)) : nullptr;
+    y.dC = tr ? reinterpret_cast<float*>(take(npix * y.hc * 4)) : nullptr;
+    const size_t wrow = static_cast<size_t>(p->ce) * p->esize;  // 64 bytes
+    y.wx = take(static_cast<size_t>(y.n_blocks) * y.taps * y.chx * y.n_tile * wrow);
+    y.wh = take(static_cast<size_t>(y.n_blocks) * y.taps * y.chh * y.n_tile * wrow);
+    y.bias_q = reinterpret_cast<float*>(take(4 * y.hc * 4));
+    if (tr) {
+      const int nch = 4 * y.hc / p->ce;
+      y.wdx = l > 0 ? take(static_cast<size_t>(y.taps) * nch * y.cin * wrow) : nullptr;
+      y.wdh = take(static_cast<size_t>(y.taps) * nch * y.hc * wrow);
+      y.dw_acc_bytes = static_cast<size_t>(y.taps) * 4 * y.hc * y.ncols * 4;
+      y.dw_acc = reinterpret_cast<float*>(take(y.dw_acc_bytes));
+      y.db_acc = reinterpret_cast<float*>(take(4 * y.hc * 4));
+    }
+  }
+  p->head_w = reinterpret_cast<float*>(take(p->layer[p->L - 1].hc * 4));
+  p->head_b = reinterpret_cast<float*>(take(16));
+  return off;
+}
+
+inline uint8_t* slot_ptr(const nint_plan* p, uint8_t* base, int slot, int c) {
+  return base + act_bytes(p, 1, c) * slot;
+}
+inline float* cslot_ptr(const nint_plan* p, const Layer& y, int slot) {
+  return y.Cs + static_cast<size_t>(slot) * p->B * p->H * p->W * y.hc;
+}
+
+void fill_common(const nint_plan* p, const Layer& y, ConvGemmParams& g) {
+  memset(&g, 0, sizeof(g));
+  g.B = p->B; g.H = p->H; g.W = p->W;
+  g.tile_w = p->tile_w; g.tile_h = p->tile_h; g.tiles_x = p->tiles_x; g.tiles_y = p->tiles_y;
+  g.hc = y.hc; g.hc_pad = y.hc_pad; g.hcb = y.hcb;
+}
+
+// one fused cell step of layer l at time t (model.py:216-231)
+int cell_step(nint_plan* p, int l, int t, int epi, float* raw_out, cudaStream_t st) {
+  Layer& y = p->layer[l];
+  const bool tr = p->cfg.training != 0;
+  ConvGemmParams g;
+  fill_common(p, y, g);
+  g.n_tile = y.n_tile;
+  g.n_blocks = y.n_blocks;
+  g.idesc = idesc_of(p->dtype, 128, y.n_tile, 0, 0);
+  g.num_stages = conv_gemm_pick_stages(y.n_tile, y.hc);
+  const int in_slot_h = tr ? t : (t & 1);
+  const int out_slot_h = tr ? t + 1 : ((t + 1) & 1);
+  // segment 0: x_t (layer 0) or the h_t of the layer below (model.py:266,271)
+  int s = 0;
+  g.seg[s].tmap_act = l == 0 ? p->tm_X : p->layer[l - 1].tm_H;
+  g.seg[s].tmap_w = y.tm_wx;
+  g.seg[s].slot = l == 0 ? t : (tr ? t + 1 : ((t + 1) & 1));
+  g.seg[s].ksize = y.k;
+  g.seg[s].nchunks = y.chx;
+  ++s;
+  const bool have_state = !(t == 0 && p->zero_init);
+  if (have_state) {  // h_{t-1} == 0 contributes nothing: skip its K-segment
+    g.seg[s].tmap_act = y.tm_H;
+    g.seg[s].tmap_w = y.tm_wh;
+    g.seg[s].slot = in_slot_h;
+    g.seg[s].ksize = y.k;
+    g.seg[s].nchunks = y.chh;
+    ++s;
+  }
+  g.nseg = s;
+  g.bias_q = y.bias_q;
+  g.c_prev = have_state ? cslot_ptr(p, y, tr ? t : 0) : nullptr;
+  g.c_out = cslot_ptr(p, y, tr ? t + 1 : 0);
+  g.h_out = slot_ptr(p, y.Hs, out_slot_h, y.hc_pad);
+  g.gates_out = tr ? slot_ptr(p, y.G, t, 4 * y.hc) : nullptr;
+  g.raw_out = raw_out;
+  CK(launch_conv_gemm(epi, p->dtype, g, p->num_sms, st));
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int nint_version(void) { return 100; }
+const char* nint_last_error(void) { return g_err; }
+int nint_gate_column(int q, int hidden) { return q_to_n(q, hidden); }
+int nint_pick_tile(int height, int width, int* tile_w, int* tile_h) {
+  if (height < 1 || width < 1 || !tile_w || !tile_h) return fail("nint_pick_tile: bad arguments");
+  return pick_tile(height, width, tile_w, tile_h);
+}
+
+int nint_plan_create(const nint_config* cfg, nint_plan** out) {
+  if (!cfg || !out) return fail("nint_plan_create: null argument");
+  if (cfg->num_layers < 1 || cfg->num_layers > NINT_MAX_LAYERS)
+    return fail("num_layers must be in [1,%d], got %d", NINT_MAX_LAYERS, cfg->num_layers);
+  if (cfg->batch < 1 || cfg->seq_len < 1 || cfg->height < 1 || cfg->width < 1 || cfg->in_channels < 1)
+    return fail("batch/seq_len/height/width/in_channels must be positive");
+  if (cfg->dtype != BF16 && cfg->dtype != TF32) return fail("unknown dtype %d", cfg->dtype);
+  nint_plan* p = new (std::nothrow) nint_plan();
+  if (!p) return fail("out of host memory");
+  p->cfg = *cfg;
+  p->L = cfg->num_layers; p->B = cfg->batch; p->T = cfg->seq_len; p->H = cfg->height; p->W = cfg->width;
+  p->dtype = cfg->dtype;
+  p->esize = cfg->dtype == BF16 ? 2 : 4;
+  p->ce = 64 / p->esize;
+  pick_tile(p->H, p->W, &p->tile_w, &p->tile_h);
+  p->tiles_x = (p->W + p->tile_w - 1) / p->tile_w;
+  p->tiles_y = (p->H + p->tile_h - 1) / p->tile_h;
+  int cin = cfg->in_channels;
+  for (int l = 0; l < p->L; ++l) {
+    Layer& y = p->layer[l];
+    y.cin = cin; y.hc = cfg->hidden[l]; y.k = cfg->ksize[l]; y.taps = y.k * y.k;
+    if (y.hc < 16 || y.hc % 16 || y.hc > 256 || (y.hc > 64 && y.hc % 64)) {
+      delete p;
+      return fail("hidden_channels[%d] = %d unsupported (multiple of 16; multiple of 64 above 64; <= 256)", l, y.hc);
+    }
+    if (y.k < 1 || y.k % 2 == 0 || y.k > 15) {
+      delete p;
+      return fail("kernel_size[%d] = %d unsupported (odd, <= 15)", l, y.k);
+    }
+    if (l > 0 && cin > 256) { delete p; return fail("layer %d input channels %d > 256", l, cin); }
+    y.chx = (y.cin + p->ce - 1) / p->ce; y.cx_pad = y.chx * p->ce;
+    y.chh = (y.hc + p->ce - 1) / p->ce;  y.hc_pad = y.chh * p->ce;
+    y.hcb = hcb_of(y.hc); y.n_blocks = y.hc / y.hcb; y.n_tile = 4 * y.hcb;
+    y.nslots_h = cfg->training ? p->T + 1 : 2;
+    y.nslots_c = cfg->training ? p->T + 1 : 1;
+    y.ncols = (y.chx + y.chh) * p->ce;
+    if (cfg->training && y.ncols > 256) {
+      delete p;
+      return fail("layer %d: padded input+hidden channels %d > 256 not supported by wgrad", l, y.ncols);
+    }
+    cin = y.hc;
+  }
+  // (layer l >= 1 reads the h tensor of layer l-1 as its x segment: ceil(hc_{l-1}/ce) chunks on both sides)
+  p->ws_bytes = carve(p, nullptr);
+  *out = p;
+  return 0;
+}
+
+void nint_plan_destroy(nint_plan* plan) { delete plan; }
+
+size_t nint_plan_workspace_bytes(const nint_plan* plan) { return plan ? plan->ws_bytes : 0; }
+
+int nint_plan_bind(nint_plan* p, void* workspace, size_t bytes, void* stream) {
+  if (!p || !workspace) return fail("nint_plan_bind: null argument");
+  if (bytes < p->ws_bytes) return fail("workspace too small: %zu < %zu", bytes, p->ws_bytes);
+  if (reinterpret_cast<uintptr_t>(workspace) % 256) return fail("workspace must be 256-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int dev = 0, sms = 0, cc_major = 0;
+  CK(cudaGetDevice(&dev));
+  CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  CK(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (cc_major != 10) return fail("libnint needs an sm_100 device (Blackwell B200); found compute capability %d.x", cc_major);
+  p->num_sms = sms;
+  p->ws = static_cast<uint8_t*>(workspace);
+  carve(p, p->ws);
+  CK(cudaMemsetAsync(p->ws, 0, p->ws_bytes, st));
+  const int tw = p->tile_w, th = p->tile_h, ce = p->ce;
+  if (encode_act_map(&p->tm_X, p->dtype, p->X, p->layer[0].cx_pad, p->W, p->H, p->B, p->T, ce, tw, th)) return 1;
+  for (int l = 0; l < p->L; ++l) {
+    Layer& y = p->layer[l];
+    if (encode_act_map(&y.tm_H, p->dtype, y.Hs, y.hc_pad, p->W, p->H, p->B, y.nslots_h, ce, tw, th)) return 1;
+    if (encode_w_map(&y.tm_wx, p->dtype, y.wx, (long long)y.n_blocks * y.taps * y.chx * y.n_tile, ce, y.n_tile)) return 1;
+    if (encode_w_map(&y.tm_wh, p->dtype, y.wh, (long long)y.n_blocks * y.taps * y.chh * y.n_tile, ce, y.n_tile)) return 1;
+    if (p->cfg.training) {
+      const int nch = 4 * y.hc / ce;
+      if (encode_act_map(&y.tm_G, p->dtype, y.G, 4 * y.hc, p->W, p->H, p->B, p->T, ce, tw, th)) return 1;
+      if (encode_w_map(&y.tm_wdh, p->dtype, y.wdh, (long long)y.taps * nch * y.hc, ce, y.hc)) return 1;
+      if (l > 0 && encode_w_map(&y.tm_wdx, p->dtype, y.wdx, (long long)y.taps * nch * y.cin, ce, y.cin)) return 1;
+    }
+  }
+  p->zero_init = true;
+  p->fwd_done = false;
+  return 0;
+}
+
+int nint_plan_set_weights(nint_plan* p, int l, const float* weight, const float* bias, void* stream) {
+  if (!p || !p->ws) return fail("plan not bound");
+  if (l < 0 || l >= p->L) return fail("layer %d out of range", l);
+  if (!weight) return fail("null weight");
+  Layer& y = p->layer[l];
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CK(launch_pack_weights_fwd(p->dtype, weight, bias, y.wx, y.wh, y.bias_q, y.cin, y.hc, y.k, st));
+  if (p->cfg.training) CK(launch_pack_weights_bwd(p->dtype, weight, y.wdx, y.wdh, y.cin, y.hc, y.k, st));
+  y.weights_set = true;
+  return 0;
+}
+
+int nint_plan_set_head(nint_plan* p, const float* weight, const float* bias, void* stream) {
+  if (!p || !p->ws) return fail("plan not bound");
+  if (!weight || !bias) return fail("null head parameter");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CK(cudaMemcpyAsync(p->head_w, weight, p->layer[p->L - 1].hc * 4, cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemcpyAsync(p->head_b, bias, 4, cudaMemcpyDeviceToDevice, st));
+  p->head_set = true;
+  return 0;
+}
+
+int nint_plan_reset_state(nint_plan* p, void* stream) {
+  if (!p || !p->ws) return fail("plan not bound");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!p->zero_init) {
+    for (int l = 0; l < p->L; ++l) {
+      Layer& y = p->layer[l];
+      CK(cudaMemsetAsync(y.Hs, 0, act_bytes(p, 1, y.hc_pad), st));
+      CK(cudaMemsetAsync(y.Cs, 0, static_cast<size_t>(p->B) * p->H * p->W * y.hc * 4, st));
+    }
+  }
+  p->zero_init = true;
+  return 0;
+}
+
+int nint_plan_set_state(nint_plan* p, int l, const float* h, const float* c, void* stream) {
+  if (!p || !p->ws) return fail("plan not bound");
+  if (l < 0 || l >= p->L || !h || !c) return fail("nint_plan_set_state: bad arguments");
+  Layer& y = p->layer[l];
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (p->zero_init) {
+    // the other layers keep an explicit zero state in slot 0
+    for (int j = 0; j < p->L; ++j) {
+      Layer& z = p->layer[j];
+      CK(cudaMemsetAsync(z.Hs, 0, act_bytes(p, 1, z.hc_pad), st));
+      CK(cudaMemsetAsync(z.Cs, 0, static_cast<size_t>(p->B) * p->H * p->W * z.hc * 4, st));
+    }
+  }
+  CK(launch_pack_state(p->dtype, h, y.Hs, p->B, y.hc, p->H, p->W, y.hc_pad, st));
+  CK(launch_nchw_to_nhwc_f32(c, y.Cs, p->B, y.hc, p->H, p->W, st));
+  p->zero_init = false;
+  return 0;
+}
+
+int nint_plan_get_state(nint_plan* p, int l, float* h, float* c, void* stream) {
+  if (!p || !p->ws) return fail("plan not bound");
+  if (l < 0 || l >= p->L) return fail("layer %d out of range", l);
+  if (!p->fwd_done) return fail("nint_plan_get_state before nint_forward");
+  Layer& y = p->layer[l];
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (h) CK(launch_unpack_state(p->dtype, slot_ptr(p, y.Hs, p->final_slot_h, y.hc_pad), h, p->B, y.hc, p->H, p->W, y.hc_pad, st));
+  if (c) CK(launch_nhwc_to_nchw_f32(cslot_ptr(p, y, p->final_slot_c), c, p->B, y.hc, p->H, p->W, st));
+  return 0;
+}
+
+static int check_ready(nint_plan* p) {
+  if (!p || !p->ws) return fail("plan not bound");
+  for (int l = 0; l < p->L; ++l)
+    if (!p->layer[l].weights_set) return fail("weights of layer %d not set", l);
+  if (!p->head_set) return fail("head parameters not set");
+  return 0;
+}
+
+int nint_forward(nint_plan* p, const float* x, float* pred, float* seq, void* stream) {
+  if (check_ready(p)) return 1;
+  if (!x || !pred) return fail("nint_forward: null x / pred");
+  if (seq && !p->cfg.return_sequence) return fail("seq output requires return_sequence in the plan");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool tr = p->cfg.training != 0;
+  const long long HW = static_cast<long long>(p->H) * p->W;
+  CK(launch_pack_input(p->dtype, x, p->X, p->B, p->T, p->cfg.in_channels, p->H, p->W, p->layer[0].cx_pad, st));
+  const Layer& top = p->layer[p->L - 1];
+  for (int t = 0; t < p->T; ++t) {          // model.py:265
+    for (int l = 0; l < p->L; ++l)          // model.py:267
+      if (cell_step(p, l, t, EPI_FWD, nullptr, st)) return 1;
+    if (seq) {                              // model.py:272 (commented variant)
+      const int slot = tr ? t + 1 : ((t + 1) & 1);
+      CK(launch_head_fwd(p->dtype, slot_ptr(p, top.Hs, slot, top.hc_pad), p->head_w, p->head_b, seq + t * HW, HW,
+                         p->B, top.hc, top.hc_pad, p->T * HW, st));
+    }
+  }
+  p->final_slot_h = tr ? p->T : (p->T & 1);
+  p->final_slot_c = tr ? p->T : 0;
+  CK(launch_head_fwd(p->dtype, slot_ptr(p, top.Hs, p->final_slot_h, top.hc_pad), p->head_w, p->head_b, pred, HW, p->B,
+                     top.hc, top.hc_pad, HW, st));  // model.py:274
+  p->fwd_done = true;
+  return 0;
+}
+
+int nint_debug_raw_gates(nint_plan* p, const float* x, float* out, void* stream) {
+  if (check_ready(p)) return 1;
+  if (!x || !out) return fail("nint_debug_raw_gates: null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CK(launch_pack_input(p->dtype, x, p->X, p->B, p->T, p->cfg.in_channels, p->H, p->W, p->layer[0].cx_pad, st));
+  return cell_step(p, 0, 0, EPI_RAW, out, st);
+}
+
+int nint_backward(nint_plan* p, const float* dpred, const float* dseq, float* const* grad_weight,
+                  float* const* grad_bias, float* grad_head_weight, float* grad_head_bias, void* stream) {
+  if (check_ready(p)) return 1;
+  if (!p->cfg.training) return fail("nint_backward needs a training plan");
+  if (!p->fwd_done) return fail("nint_backward before nint_forward");
+  if (!dpred && !dseq) return fail("nint_backward: no upstream gradient");
+  if (dseq && !p->cfg.return_sequence) return fail("dseq requires return_sequence in the plan");
+  if (dseq && dpred) return fail("pass either dpred or dseq (fold dpred into dseq[:, T-1])");
+  if (!grad_weight || !grad_bias) return fail("nint_backward: null gradient tables");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long HW = static_cast<long long>(p->H) * p->W;
+  const int L = p->L, T = p->T;
+  const Layer& top = p->layer[L - 1];
+  // ---- head gradients (model.py:274): dw = sum dpred * h_T, db = sum dpred
+  if (grad_head_weight && grad_head_bias) {
+    CK(cudaMemsetAsync(grad_head_weight, 0, top.hc * 4, st));
+    CK(cudaMemsetAsync(grad_head_bias, 0, 4, st));
+    if (dpred)
+      CK(launch_head_bwd(p->dtype, slot_ptr(p, top.Hs, T, top.hc_pad), dpred, HW, grad_head_weight, grad_head_bias, HW,
+                         p->B, top.hc, top.hc_pad, st));
+    if (dseq)
+      for (int t = 0; t < T; ++t)
+        CK(launch_head_bwd(p->dtype, slot_ptr(p, top.Hs, t + 1, top.hc_pad), dseq + t * HW, T * HW, grad_head_weight,
+                           grad_head_bias, HW, p->B, top.hc, top.hc_pad, st));
+  }
+  // ---- BPTT: reverse time, top layer first.  The dgrad conv of step t+1 (and of the layer
+  // above at step t) accumulates dh_t in TMEM; its epilogue is the gate backward of step t and
+  // overwrites the saved gates with dgates in place.
+  for (int t = T - 1; t >= 0; --t) {
+    for (int l = L - 1; l >= 0; --l) {
+      Layer& y = p->layer[l];
+      ConvGemmParams g;
+      fill_common(p, y, g);
+      g.n_tile = y.hc;
+      g.n_blocks = 1;
+      g.idesc = idesc_of(p->dtype, 128, y.hc, 0, 0);
+      g.num_stages = conv_gemm_pick_stages(y.hc, y.hc);
+      int s = 0;
+      if (t < T - 1) {  // dh_t += dgates_{t+1} (*) flip(W_h)
+        g.seg[s].tmap_act = y.tm_G; g.seg[s].tmap_w = y.tm_wdh; g.seg[s].slot = t + 1;
+        g.seg[s].ksize = y.k; g.seg[s].nchunks = 4 * y.hc / p->ce;
+        ++s;
+      }
+      if (l < L - 1) {  // dh_t += dx of the layer above at the same t
+        Layer& up = p->layer[l + 1];
+        g.seg[s].tmap_act = up.tm_G; g.seg[s].tmap_w = up.tm_wdx; g.seg[s].slot = t;
+        g.seg[s].ksize = up.k; g.seg[s].nchunks = 4 * up.hc / p->ce;
+        ++s;
+      }
+      g.nseg = s;
+      g.gates_in = slot_ptr(p, y.G, t, 4 * y.hc);
+      g.dgates_out = slot_ptr(p, y.G, t, 4 * y.hc);
+      g.c_cur = cslot_ptr(p, y, t + 1);
+      g.c_prev_b = (t == 0 && p->zero_init) ? nullptr : cslot_ptr(p, y, t);
+      g.dc_in = (t == T - 1) ? nullptr : y.dC;
+      g.dc_out = y.dC;
+      if (l == L - 1) {
+        if (dseq) {
+          // per-step head gradient; dpred (last step) is folded in by the caller adding it to dseq[:, T-1]
+          g.head_dpred = dseq + t * HW;
+          g.head_dpred_bstride = T * HW;
+          g.head_w = p->head_w;
+        } else if (t == T - 1) {
+          g.head_dpred = dpred;
+          g.head_dpred_bstride = HW;
+          g.head_w = p->head_w;
+        }
+      }
+      CK(launch_conv_gemm(EPI_BWD, p->dtype, g, p->num_sms, st));
+    }
+  }
+  // ---- weight / bias gradients, batched over all T steps
+  for (int l = 0; l < L; ++l) {
+    Layer& y = p->layer[l];
+    CK(cudaMemsetAsync(y.dw_acc, 0, y.dw_acc_bytes, st));
+    CK(cudaMemsetAsync(y.db_acc, 0, 4 * y.hc * 4, st));
+    WgradParams w;
+    memset(&w, 0, sizeof(w));
+    w.tmap_dg = y.tm_G;
+    w.tmap_b[0] = l == 0 ? p->tm_X : p->layer[l - 1].tm_H;
+    w.tmap_b[1] = y.tm_H;
+    w.slot_b0[0] = l == 0 ? 0 : 1;
+    w.slot_b0[1] = 0;
+    w.nchunks_b[0] = y.chx;
+    w.nchunks_b[1] = y.chh;
+    w.T = T; w.B = p->B; w.H = p->H; w.W = p->W;
+    w.tile_w = p->tile_w; w.tile_h = p->tile_h; w.tiles_x = p->tiles_x; w.tiles_y = p->tiles_y;
+    w.ksize = y.k;
+    w.hc4 = 4 * y.hc;
+    w.m_blocks = (w.hc4 + 127) / 128;
+    w.ncols = y.ncols;
+    const int tpg = 512 / y.ncols;                      // taps per group
+    int g0 = (512 - p->ce) / y.ncols;                   // group 0 also holds the bias columns
+    if (g0 > tpg) g0 = tpg;
+    if (g0 < 1) return fail("wgrad: ncols %d leaves no room for the bias columns", y.ncols);
+    int ng = 0, tap = 0;
+    w.group_tap0[0] = 0;
+    while (tap < y.taps) {
+      const int n = ng == 0 ? g0 : tpg;
+      tap = tap + n > y.taps ? y.taps : tap + n;
+      if (ng + 1 > kMaxWgradGroups) return fail("wgrad: too many tap groups");
+      w.group_tap0[++ng] = tap;
+    }
+    w.n_groups = ng;
+    const long long total_tiles = static_cast<long long>(T) * p->B * p->tiles_x * p->tiles_y;
+    int splits = p->num_sms / (w.m_blocks * ng);
+    if (splits < 1) splits = 1;
+    if (splits > total_tiles) splits = static_cast<int>(total_tiles);
+    w.splits = splits;
+    wgrad_pick_buffers(p->dtype, y.chx + y.chh, &w.a_bufs, &w.b_stages);
+    if (w.b_stages < 1) return fail("wgrad: operand panels do not fit in shared memory");
+    w.idesc = idesc_of(p->dtype, 128, y.ncols, 1, 1);
+    w.idesc_bias = idesc_of(p->dtype, 128, p->ce, 1, 1);
+    w.dw_acc = y.dw_acc;
+    w.db_acc = y.db_acc;
+    CK(launch_wgrad(p->dtype, w, st));
+    if (grad_weight[l])
+      CK(launch_unpack_wgrad(y.dw_acc, y.db_acc, grad_weight[l], grad_bias[l], y.cin, y.hc, y.k, y.ncols, y.cx_pad, 0, st));
+  }
+  return 0;
+}
+
+}  // extern "C"

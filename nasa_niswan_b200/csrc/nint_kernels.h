@@ -1,0 +1,126 @@
+// Internal host/device interface between the C-ABI layer (nint_api.cu) and the kernels.
+//
+// Layout conventions shared by every kernel (DESIGN.md "Data layout in HBM"):
+//   * activations are channels-last, [slot][B][H][W][C_pad] of E (E = bf16, or fp32 holding
+//     tf32-rounded values), C_pad a multiple of one 64-byte chunk (32 bf16 / 16 tf32 elements);
+//   * a pixel tile is tile_w x tile_h <= 128 pixels of one image, row = ty * tile_w + tx;
+//   * the 4*hc gate channels of a layer are stored in "q-order": with hcb = min(hc, 64) and
+//     n_blocks = hc / hcb,  q = nb * 4*hcb + gate * hcb + cc  <->  reference channel
+//     n = gate * hc + nb * hcb + cc   (gate order i,f,g,o: model.py:221).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace nint {
+
+enum : int { EPI_FWD = 0, EPI_BWD = 1, EPI_RAW = 2 };
+
+// One K-segment of an implicit-GEMM convolution: an activation tensor read through a 5-D TMA
+// map (box = one chunk x tile_w x tile_h pixels; out-of-image pixels are zero-filled by TMA =
+// the conv's zero padding, model.py:204-211) and its packed weights read through a 2-D map
+// [(nb*taps + tap)*nchunks + chunk][n_tile rows][chunk elements].
+struct alignas(64) ConvSegment {
+  CUtensorMap tmap_act;
+  CUtensorMap tmap_w;
+  int slot;
+  int ksize;
+  int nchunks;
+  int reserved;
+};
+
+struct alignas(64) ConvGemmParams {
+  ConvSegment seg[2];
+  int nseg;
+  int B, H, W;
+  int tile_w, tile_h;
+  int tiles_x, tiles_y;
+  int n_tile;    // UMMA N (accumulator columns per item)
+  int n_blocks;  // N blocks per pixel tile (forward with hidden > 64)
+  int num_stages;
+  uint32_t idesc;
+  int hc, hc_pad;  // hidden channels of this layer / padded channel count of its h tensor
+  int hcb;         // min(hc, 64)
+  // ---- EPI_FWD: LSTM cell update (model.py:221-229)
+  const float* bias_q;  // [4*hc], q-order
+  const float* c_prev;  // [B,H,W,hc] fp32 or null (zero state)
+  float* c_out;         // [B,H,W,hc] fp32
+  void* h_out;          // [B,H,W,hc_pad] E
+  void* gates_out;      // [B,H,W,4*hc] E, q-order, or null (inference)
+  // ---- EPI_BWD: gate backward; accumulator = dh (absent when nseg == 0)
+  const void* gates_in;     // [B,H,W,4*hc] E (activated i,f,g,o of step t)
+  const float* c_cur;       // c_t
+  const float* c_prev_b;    // c_{t-1} or null (zero state)
+  const float* dc_in;       // dc_t or null
+  float* dc_out;            // dc_{t-1}
+  void* dgates_out;         // [B,H,W,4*hc] E (may alias gates_in)
+  const float* head_dpred;  // optional [B,H,W] (+ stride): dh += head_dpred * head_w[c]
+  long long head_dpred_bstride;  // elements between images of head_dpred
+  const float* head_w;      // [hc]
+  // ---- EPI_RAW: dump fp32 accumulators [B,H,W,n_blocks*n_tile] (debug / generic conv)
+  float* raw_out;
+};
+
+int conv_gemm_smem_bytes(int n_tile, int num_stages, int hc);
+int conv_gemm_pick_stages(int n_tile, int hc);
+cudaError_t launch_conv_gemm(int epi, int dtype, const ConvGemmParams& p, int num_sms, cudaStream_t stream);
+
+// ---- wgrad (nint_wgrad.cu):  dW[tap][q][col] += sum_pixels dgates[pix][q] * comb[pix + tap][col]
+constexpr int kMaxWgradGroups = 32;
+struct alignas(64) WgradParams {
+  CUtensorMap tmap_dg;    // dgates [T][B][H][W][4*hc]        (A, MN-major, M = q)
+  CUtensorMap tmap_b[2];  // x-part tensor, h-part tensor      (B, MN-major, N = channel)
+  int slot_b0[2];         // slot of step 0 for each b tensor
+  int nchunks_b[2];       // 64-byte chunks per b segment
+  int T, B, H, W;
+  int tile_w, tile_h, tiles_x, tiles_y;
+  int ksize;
+  int m_blocks;           // ceil(4*hc / 128)
+  int n_groups;
+  int group_tap0[kMaxWgradGroups + 1];  // taps [group_tap0[g], group_tap0[g+1]) belong to group g
+  int splits;             // split-K factor over pixel tiles
+  int ncols;              // accumulator columns per tap = (sum nchunks_b) * elements per chunk
+  int a_bufs, b_stages;
+  uint32_t idesc, idesc_bias;
+  int hc4;                // 4*hc
+  float* dw_acc;          // [taps][4*hc][ncols] fp32, atomically accumulated (pre-zeroed)
+  float* db_acc;          // [4*hc] fp32 (q-order) or null
+};
+int wgrad_smem_bytes(int dtype, int bpanels, int a_bufs, int b_stages);
+void wgrad_pick_buffers(int dtype, int bpanels, int* a_bufs, int* b_stages);
+cudaError_t launch_wgrad(int dtype, const WgradParams& p, cudaStream_t stream);
+
+// ---- pointwise / layout kernels (nint_pointwise.cu)
+// x [B,T,C,H,W] fp32 (model.py:255) -> X [T][B][H][W][c_pad] E (pad channels zero)
+cudaError_t launch_pack_input(int dtype, const float* x, void* X, int B, int T, int C, int H, int W, int c_pad,
+                              cudaStream_t s);
+// NCHW fp32 <-> NHWC E (state import / export for the cell API)
+cudaError_t launch_pack_state(int dtype, const float* src_nchw, void* dst_nhwc, int B, int C, int H, int W,
+                              int c_pad, cudaStream_t s);
+cudaError_t launch_unpack_state(int dtype, const void* src_nhwc, float* dst_nchw, int B, int C, int H, int W,
+                                int c_pad, cudaStream_t s);
+cudaError_t launch_nchw_to_nhwc_f32(const float* src, float* dst, int B, int C, int H, int W, cudaStream_t s);
+cudaError_t launch_nhwc_to_nchw_f32(const float* src, float* dst, int B, int C, int H, int W, cudaStream_t s);
+// OIHW fp32 master weights -> packed operand panels
+cudaError_t launch_pack_weights_fwd(int dtype, const float* w, const float* bias, void* wpack_x, void* wpack_h,
+                                    float* bias_q, int cin, int hc, int k, cudaStream_t s);
+cudaError_t launch_pack_weights_bwd(int dtype, const float* w, void* wpack_dx, void* wpack_dh, int cin, int hc,
+                                    int k, cudaStream_t s);
+// 1x1 head (model.py:251,274)
+cudaError_t launch_head_fwd(int dtype, const void* h, const float* w, const float* b, float* out, long long npix_per_img,
+                            int B, int hc, int hc_pad, long long out_bstride, cudaStream_t s);
+cudaError_t launch_head_bwd(int dtype, const void* h, const float* dpred, long long dpred_bstride, float* dw, float* db,
+                            long long npix_per_img, int B, int hc, int hc_pad, cudaStream_t s);
+// dw_acc [taps][4hc (q)][ncols] -> grad weight OIHW [4hc][cin+hc][k][k]; db_acc (q) -> grad bias
+cudaError_t launch_unpack_wgrad(const float* dw_acc, const float* db_acc, float* gw, float* gb, int cin, int hc,
+                                int k, int ncols, int cx_pad, int accumulate, cudaStream_t s);
+
+// q-order helpers (host + device)
+__host__ __device__ inline int hcb_of(int hc) { return hc < 64 ? hc : 64; }
+__host__ __device__ inline int q_to_n(int q, int hc) {
+  const int hcb = hcb_of(hc);
+  const int nb = q / (4 * hcb), r = q % (4 * hcb);
+  return (r / hcb) * hc + nb * hcb + (r % hcb);
+}
+
+}  // namespace nint

@@ -1,0 +1,403 @@
+// Memory-bound layout / pointwise kernels of the ConvLSTM path (sm_100a): input and state
+// repacking between the reference's NCHW fp32 tensors and the channels-last operand layout,
+// weight packing into UMMA panels, the 1x1 output head (model.py:251,274) and its backward,
+// and the unpacking of the wgrad accumulators into OIHW gradients.
+#include "nint_common.cuh"
+#include "nint_kernels.h"
+
+namespace nint {
+
+__device__ __forceinline__ float round_for(float v, __nv_bfloat16*) { return v; }
+__device__ __forceinline__ float round_for(float v, float*) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+template <typename E>
+__device__ __forceinline__ E to_elem(float v);
+template <>
+__device__ __forceinline__ __nv_bfloat16 to_elem<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <>
+__device__ __forceinline__ float to_elem<float>(float v) { return round_for(v, (float*)nullptr); }
+__device__ __forceinline__ float from_elem(__nv_bfloat16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ float from_elem(float v) { return v; }
+
+// ------------------------------------------------------------------------------------------
+// NCHW-like fp32 source -> channels-last E.  One thread per pixel: reads are coalesced across
+// the warp (consecutive pixels of one channel plane), writes are CP*sizeof(E) contiguous bytes
+// per thread, i.e. a warp writes one contiguous span.  src image stride / dst image index are
+// given by the caller through (src_img_stride, dst slot mapping).
+// ------------------------------------------------------------------------------------------
+template <typename E, int CP>
+__global__ void pack_cl_kernel(const float* __restrict__ src, E* __restrict__ dst, int C, long long HW,
+                               int n_outer, int n_inner, long long src_outer_stride, long long src_inner_stride,
+                               long long dst_outer_stride, long long dst_inner_stride) {
+  // image (o, i): src + o*src_outer_stride + i*src_inner_stride, [C][HW];  dst + o*dst_outer + i*dst_inner, [HW][CP]
+  const long long total = static_cast<long long>(n_outer) * n_inner * HW;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long pix = idx % HW;
+    const long long img = idx / HW;
+    const int i = static_cast<int>(img % n_inner);
+    const int o = static_cast<int>(img / n_inner);
+    const float* s = src + o * src_outer_stride + i * src_inner_stride + pix;
+    E* d = dst + o * dst_outer_stride + i * dst_inner_stride + pix * CP;
+    float v[CP];
+#pragma unroll
+    for (int c = 0; c < CP; ++c) v[c] = (c < C) ? round_for(__ldg(s + c * HW), (E*)nullptr) : 0.f;
+    store_elems<E, CP>(d, v);
+  }
+}
+
+template <typename E>
+static cudaError_t pack_cl(const float* src, E* dst, int C, int c_pad, long long HW, int n_outer, int n_inner,
+                           long long so, long long si, long long dso, long long dsi, cudaStream_t s) {
+  const long long total = static_cast<long long>(n_outer) * n_inner * HW;
+  const int threads = 256;
+  long long blocks = (total + threads - 1) / threads;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks <= 0) return cudaSuccess;
+  switch (c_pad) {
+    case 16: pack_cl_kernel<E, 16><<<blocks, threads, 0, s>>>(src, dst, C, HW, n_outer, n_inner, so, si, dso, dsi); break;
+    case 32: pack_cl_kernel<E, 32><<<blocks, threads, 0, s>>>(src, dst, C, HW, n_outer, n_inner, so, si, dso, dsi); break;
+    case 48: pack_cl_kernel<E, 48><<<blocks, threads, 0, s>>>(src, dst, C, HW, n_outer, n_inner, so, si, dso, dsi); break;
+    case 64: pack_cl_kernel<E, 64><<<blocks, threads, 0, s>>>(src, dst, C, HW, n_outer, n_inner, so, si, dso, dsi); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+// generic (any channel count) variant: one thread per (pixel, 16-channel group)
+template <typename E>
+__global__ void pack_cl_wide_kernel(const float* __restrict__ src, E* __restrict__ dst, int C, int c_pad,
+                                    long long HW, int n_outer, int n_inner, long long so, long long si,
+                                    long long dso, long long dsi) {
+  const int groups = c_pad / 16;
+  const long long total = static_cast<long long>(n_outer) * n_inner * groups * HW;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long pix = idx % HW;
+    long long r = idx / HW;
+    const int g = static_cast<int>(r % groups);
+    r /= groups;
+    const int i = static_cast<int>(r % n_inner);
+    const int o = static_cast<int>(r / n_inner);
+    const float* s = src + o * so + i * si + pix;
+    E* d = dst + o * dso + i * dsi + pix * c_pad + g * 16;
+    float v[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      const int ch = g * 16 + c;
+      v[c] = (ch < C) ? round_for(__ldg(s + ch * HW), (E*)nullptr) : 0.f;
+    }
+    store_elems<E, 16>(d, v);
+  }
+}
+
+template <typename E>
+static cudaError_t pack_any(const float* src, E* dst, int C, int c_pad, long long HW, int n_outer, int n_inner,
+                            long long so, long long si, long long dso, long long dsi, cudaStream_t s) {
+  if (c_pad % 16) return cudaErrorInvalidValue;
+  if (c_pad <= 64) return pack_cl<E>(src, dst, C, c_pad, HW, n_outer, n_inner, so, si, dso, dsi, s);
+  const long long total = static_cast<long long>(n_outer) * n_inner * (c_pad / 16) * HW;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks <= 0) return cudaSuccess;
+  pack_cl_wide_kernel<E><<<blocks, 256, 0, s>>>(src, dst, C, c_pad, HW, n_outer, n_inner, so, si, dso, dsi);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pack_input(int dtype, const float* x, void* X, int B, int T, int C, int H, int W, int c_pad,
+                              cudaStream_t s) {
+  // x[b][t] (model.py:266) -> X[t][b]: outer = b, inner = t
+  const long long HW = static_cast<long long>(H) * W;
+  const long long so = static_cast<long long>(T) * C * HW, si = C * HW;
+  const long long dso = HW * c_pad, dsi = static_cast<long long>(B) * HW * c_pad;
+  if (dtype == NINT_BF16)
+    return pack_any<__nv_bfloat16>(x, reinterpret_cast<__nv_bfloat16*>(X), C, c_pad, HW, B, T, so, si, dso, dsi, s);
+  return pack_any<float>(x, reinterpret_cast<float*>(X), C, c_pad, HW, B, T, so, si, dso, dsi, s);
+}
+
+cudaError_t launch_pack_state(int dtype, const float* src, void* dst, int B, int C, int H, int W, int c_pad,
+                              cudaStream_t s) {
+  const long long HW = static_cast<long long>(H) * W;
+  if (dtype == NINT_BF16)
+    return pack_any<__nv_bfloat16>(src, reinterpret_cast<__nv_bfloat16*>(dst), C, c_pad, HW, B, 1, C * HW, 0,
+                                   HW * c_pad, 0, s);
+  return pack_any<float>(src, reinterpret_cast<float*>(dst), C, c_pad, HW, B, 1, C * HW, 0, HW * c_pad, 0, s);
+}
+
+// channels-last E / fp32 -> NCHW fp32: tile transpose through shared memory (32 pixels x 32 channels)
+template <typename E>
+__global__ void unpack_cl_kernel(const E* __restrict__ src, float* __restrict__ dst, int C, int c_pad, long long HW) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const long long p0 = static_cast<long long>(blockIdx.x) * 32;
+  const int c0 = blockIdx.y * 32;
+  const E* s = src + static_cast<long long>(b) * HW * c_pad;
+  float* d = dst + static_cast<long long>(b) * C * HW;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const long long p = p0 + r;
+    const int c = c0 + threadIdx.x;
+    tile[r][threadIdx.x] = (p < HW && c < C) ? from_elem(s[p * c_pad + c]) : 0.f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int c = c0 + r;
+    const long long p = p0 + threadIdx.x;
+    if (c < C && p < HW) d[c * HW + p] = tile[threadIdx.x][r];
+  }
+}
+
+cudaError_t launch_unpack_state(int dtype, const void* src, float* dst, int B, int C, int H, int W, int c_pad,
+                                cudaStream_t s) {
+  const long long HW = static_cast<long long>(H) * W;
+  dim3 grid(static_cast<unsigned>((HW + 31) / 32), (C + 31) / 32, B), block(32, 8);
+  if (dtype == NINT_BF16)
+    unpack_cl_kernel<__nv_bfloat16><<<grid, block, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(src), dst, C, c_pad, HW);
+  else
+    unpack_cl_kernel<float><<<grid, block, 0, s>>>(reinterpret_cast<const float*>(src), dst, C, c_pad, HW);
+  return cudaGetLastError();
+}
+
+__global__ void nchw_to_nhwc_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, long long HW) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const long long p0 = static_cast<long long>(blockIdx.x) * 32;
+  const int c0 = blockIdx.y * 32;
+  const float* s = src + static_cast<long long>(b) * C * HW;
+  float* d = dst + static_cast<long long>(b) * C * HW;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int c = c0 + r;
+    const long long p = p0 + threadIdx.x;
+    tile[r][threadIdx.x] = (c < C && p < HW) ? s[c * HW + p] : 0.f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const long long p = p0 + r;
+    const int c = c0 + threadIdx.x;
+    if (p < HW && c < C) d[p * C + c] = tile[threadIdx.x][r];
+  }
+}
+cudaError_t launch_nchw_to_nhwc_f32(const float* src, float* dst, int B, int C, int H, int W, cudaStream_t s) {
+  const long long HW = static_cast<long long>(H) * W;
+  dim3 grid(static_cast<unsigned>((HW + 31) / 32), (C + 31) / 32, B), block(32, 8);
+  nchw_to_nhwc_f32_kernel<<<grid, block, 0, s>>>(src, dst, C, HW);
+  return cudaGetLastError();
+}
+cudaError_t launch_nhwc_to_nchw_f32(const float* src, float* dst, int B, int C, int H, int W, cudaStream_t s) {
+  return launch_unpack_state(NINT_TF32, src, dst, B, C, H, W, C, s);
+}
+
+// ------------------------------------------------------------------------------------------
+// weight packing.  Reference layout: W[n][c][dy][dx], n = gate*hc + channel, c over cat(x, h)
+// (model.py:207-211,219).  Packed panel row index = ((nb*taps + tap)*nchunks + chunk)*n_tile + col,
+// each row holds one chunk (CE elements) of K.
+// ------------------------------------------------------------------------------------------
+template <typename E>
+__global__ void pack_w_fwd_kernel(const float* __restrict__ w, const float* __restrict__ bias, E* __restrict__ wx,
+                                  E* __restrict__ wh, float* __restrict__ bias_q, int cin, int hc, int k) {
+  constexpr int CE = ElemTraits<E>::kPerChunk;
+  const int hcb = hcb_of(hc), n_blocks = hc / hcb, n_tile = 4 * hcb, taps = k * k;
+  const int ctot = cin + hc;
+  const int chx = (cin + CE - 1) / CE, chh = (hc + CE - 1) / CE;
+  const long long nx = static_cast<long long>(n_blocks) * taps * chx * n_tile * CE;
+  const long long nh = static_cast<long long>(n_blocks) * taps * chh * n_tile * CE;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < nx + nh;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const bool is_h = idx >= nx;
+    long long r = is_h ? idx - nx : idx;
+    const int nch = is_h ? chh : chx;
+    const int e = static_cast<int>(r % CE); r /= CE;
+    const int col = static_cast<int>(r % n_tile); r /= n_tile;
+    const int ch = static_cast<int>(r % nch); r /= nch;
+    const int tap = static_cast<int>(r % taps);
+    const int nb = static_cast<int>(r / taps);
+    const int n = (col / hcb) * hc + nb * hcb + (col % hcb);
+    const int cl = ch * CE + e;
+    const int climit = is_h ? hc : cin;
+    float v = 0.f;
+    if (cl < climit) v = w[(static_cast<long long>(n) * ctot + (is_h ? cin + cl : cl)) * taps + tap];
+    (is_h ? wh : wx)[is_h ? idx - nx : idx] = to_elem<E>(v);
+  }
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < 4 * hc; q += gridDim.x * blockDim.x)
+    bias_q[q] = bias ? bias[q_to_n(q, hc)] : 0.f;
+}
+
+// dgrad operands: K = q (4*hc), N = input channel, taps flipped (transposed convolution):
+//   wd[tap'][chunk][col][e] = W[n(q = chunk*CE + e)][c(col)][k-1-dy'][k-1-dx']
+template <typename E>
+__global__ void pack_w_bwd_kernel(const float* __restrict__ w, E* __restrict__ wdx, E* __restrict__ wdh, int cin,
+                                  int hc, int k) {
+  constexpr int CE = ElemTraits<E>::kPerChunk;
+  const int taps = k * k, ctot = cin + hc, nch = 4 * hc / CE;
+  const long long nx = wdx ? static_cast<long long>(taps) * nch * cin * CE : 0;
+  const long long nh = static_cast<long long>(taps) * nch * hc * CE;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < nx + nh;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const bool is_h = idx >= nx;
+    long long r = is_h ? idx - nx : idx;
+    const int ncol = is_h ? hc : cin;
+    const int e = static_cast<int>(r % CE); r /= CE;
+    const int col = static_cast<int>(r % ncol); r /= ncol;
+    const int ch = static_cast<int>(r % nch);
+    const int tap = static_cast<int>(r / nch);
+    const int n = q_to_n(ch * CE + e, hc);
+    const int c = is_h ? cin + col : col;
+    const float v = w[(static_cast<long long>(n) * ctot + c) * taps + (taps - 1 - tap)];
+    (is_h ? wdh : wdx)[is_h ? idx - nx : idx] = to_elem<E>(v);
+  }
+}
+
+cudaError_t launch_pack_weights_fwd(int dtype, const float* w, const float* bias, void* wx, void* wh, float* bias_q,
+                                    int cin, int hc, int k, cudaStream_t s) {
+  if (dtype == NINT_BF16)
+    pack_w_fwd_kernel<__nv_bfloat16><<<296, 256, 0, s>>>(w, bias, reinterpret_cast<__nv_bfloat16*>(wx),
+                                                         reinterpret_cast<__nv_bfloat16*>(wh), bias_q, cin, hc, k);
+  else
+    pack_w_fwd_kernel<float><<<296, 256, 0, s>>>(w, bias, reinterpret_cast<float*>(wx), reinterpret_cast<float*>(wh),
+                                                 bias_q, cin, hc, k);
+  return cudaGetLastError();
+}
+cudaError_t launch_pack_weights_bwd(int dtype, const float* w, void* wdx, void* wdh, int cin, int hc, int k,
+                                    cudaStream_t s) {
+  if (dtype == NINT_BF16)
+    pack_w_bwd_kernel<__nv_bfloat16><<<296, 256, 0, s>>>(w, reinterpret_cast<__nv_bfloat16*>(wdx),
+                                                         reinterpret_cast<__nv_bfloat16*>(wdh), cin, hc, k);
+  else
+    pack_w_bwd_kernel<float><<<296, 256, 0, s>>>(w, reinterpret_cast<float*>(wdx), reinterpret_cast<float*>(wdh), cin,
+                                                 hc, k);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// 1x1 head: pred[b][pix] = bias + sum_c h[b][pix][c] * w[c]    (model.py:274)
+// One thread per pixel, 16-byte loads; a pixel's channel vector (<= 512 B) stays in L1 between
+// the thread's consecutive loads, so DRAM traffic is the algorithmic hc_pad*sizeof(E) per pixel.
+// ------------------------------------------------------------------------------------------
+template <typename E>
+__global__ void head_fwd_kernel(const E* __restrict__ h, const float* __restrict__ w, const float* __restrict__ bias,
+                                float* __restrict__ out, long long npix, int B, int hc, int hc_pad,
+                                long long out_bstride) {
+  extern __shared__ float s_w[];
+  for (int i = threadIdx.x; i < hc_pad; i += blockDim.x) s_w[i] = i < hc ? w[i] : 0.f;
+  __syncthreads();
+  constexpr int V = 16 / sizeof(E);
+  const long long total = static_cast<long long>(B) * npix;
+  const float b0 = bias[0];
+  for (long long gp = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; gp < total;
+       gp += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const E* hp = h + gp * hc_pad;
+    float acc = b0;
+    for (int c0 = 0; c0 < hc_pad; c0 += V) {
+      float f[V];
+      load_elems<E, V>(hp + c0, f);
+#pragma unroll
+      for (int j = 0; j < V; ++j) acc = fmaf(f[j], s_w[c0 + j], acc);
+    }
+    const long long b = gp / npix;
+    out[b * out_bstride + (gp - b * npix)] = acc;
+  }
+}
+
+cudaError_t launch_head_fwd(int dtype, const void* h, const float* w, const float* b, float* out, long long npix,
+                            int B, int hc, int hc_pad, long long out_bstride, cudaStream_t s) {
+  const long long total = static_cast<long long>(B) * npix;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks <= 0) return cudaSuccess;
+  if (dtype == NINT_BF16)
+    head_fwd_kernel<__nv_bfloat16><<<blocks, 256, hc_pad * 4, s>>>(reinterpret_cast<const __nv_bfloat16*>(h), w, b, out,
+                                                                  npix, B, hc, hc_pad, out_bstride);
+  else
+    head_fwd_kernel<float><<<blocks, 256, hc_pad * 4, s>>>(reinterpret_cast<const float*>(h), w, b, out, npix, B, hc,
+                                                          hc_pad, out_bstride);
+  return cudaGetLastError();
+}
+
+// head backward: dw[c] = sum_pix dpred[pix] * h[pix][c], db = sum dpred   (dh is fused into the
+// gate-backward epilogue).  Thread = (pixel group, channel); block reduction + atomics.
+template <typename E>
+__global__ void head_bwd_kernel(const E* __restrict__ h, const float* __restrict__ dpred, long long dpred_bstride,
+                                float* __restrict__ dw, float* __restrict__ db, long long npix, int B, int hc,
+                                int hc_pad) {
+  // blockDim = (32 channel lanes, 8 pixel rows); each block strides over pixels
+  const long long total = static_cast<long long>(B) * npix;
+  const int cgroups = (hc + 31) / 32;
+  __shared__ float red[8][33];
+  for (int cg = 0; cg < cgroups; ++cg) {
+    const int c = cg * 32 + threadIdx.x;
+    float acc = 0.f, accb = 0.f;
+    for (long long p = blockIdx.x * static_cast<long long>(blockDim.y) + threadIdx.y; p < total;
+         p += static_cast<long long>(gridDim.x) * blockDim.y) {
+      const long long b = p / npix;
+      const float d = dpred[b * dpred_bstride + (p - b * npix)];
+      if (c < hc) acc = fmaf(d, from_elem(h[p * hc_pad + c]), acc);
+      accb += d;
+    }
+    red[threadIdx.y][threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.y == 0) {
+      float s = 0.f;
+      for (int r = 0; r < 8; ++r) s += red[r][threadIdx.x];
+      if (c < hc) atomicAdd(dw + c, s);
+    }
+    __syncthreads();
+    if (cg == 0) {
+      red[threadIdx.y][threadIdx.x] = (threadIdx.x == 0) ? accb : 0.f;
+      __syncthreads();
+      if (threadIdx.y == 0 && threadIdx.x == 0) {
+        float s = 0.f;
+        for (int r = 0; r < 8; ++r) s += red[r][0];
+        atomicAdd(db, s);
+      }
+      __syncthreads();
+    }
+  }
+}
+
+cudaError_t launch_head_bwd(int dtype, const void* h, const float* dpred, long long dpred_bstride, float* dw, float* db,
+                            long long npix, int B, int hc, int hc_pad, cudaStream_t s) {
+  dim3 block(32, 8);
+  const int grid = 148 * 4;
+  if (dtype == NINT_BF16)
+    head_bwd_kernel<__nv_bfloat16><<<grid, block, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(h), dpred, dpred_bstride,
+                                                         dw, db, npix, B, hc, hc_pad);
+  else
+    head_bwd_kernel<float><<<grid, block, 0, s>>>(reinterpret_cast<const float*>(h), dpred, dpred_bstride, dw, db, npix,
+                                                 B, hc, hc_pad);
+  return cudaGetLastError();
+}
+
+// dw_acc [taps][4hc (q)][ncols] -> grad W[n][c][dy][dx];  col(c) = c (x part) or cx_pad + (c - cin) (h part)
+__global__ void unpack_wgrad_kernel(const float* __restrict__ dw_acc, const float* __restrict__ db_acc,
+                                    float* __restrict__ gw, float* __restrict__ gb, int cin, int hc, int k, int ncols,
+                                    int cx_pad, int accumulate) {
+  const int taps = k * k, ctot = cin + hc, hc4 = 4 * hc;
+  const long long total = static_cast<long long>(hc4) * ctot * taps;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    // read-coalesced order: (tap, q, c)
+    const int c = static_cast<int>(idx % ctot);
+    long long r = idx / ctot;
+    const int q = static_cast<int>(r % hc4);
+    const int tap = static_cast<int>(r / hc4);
+    const int col = c < cin ? c : cx_pad + (c - cin);
+    const float v = dw_acc[(static_cast<long long>(tap) * hc4 + q) * ncols + col];
+    float* dst = gw + (static_cast<long long>(q_to_n(q, hc)) * ctot + c) * taps + tap;
+    *dst = accumulate ? *dst + v : v;
+  }
+  if (gb) {
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < hc4; q += gridDim.x * blockDim.x) {
+      float* dst = gb + q_to_n(q, hc);
+      *dst = accumulate ? *dst + db_acc[q] : db_acc[q];
+    }
+  }
+}
+cudaError_t launch_unpack_wgrad(const float* dw_acc, const float* db_acc, float* gw, float* gb, int cin, int hc, int k,
+                                int ncols, int cx_pad, int accumulate, cudaStream_t s) {
+  unpack_wgrad_kernel<<<296, 256, 0, s>>>(dw_acc, db_acc, gw, gb, cin, hc, k, ncols, cx_pad, accumulate);
+  return cudaGetLastError();
+}
+
+}  // namespace nint

@@ -1,0 +1,258 @@
+// Weight-gradient implicit GEMM on tcgen05 (sm_100a), batched over all T steps of BPTT.
+//
+//   dW[tap][q][col] += sum over (t, b, y, x)  dgates_t[b,y,x,q] * comb_t[b, y+dy-p, x+dx-p, col]
+//
+// which is what autograd's conv-weight backward computes for model.py:220 summed over the time
+// loop (model.py:265); db[q] = sum dgates.  GEMM view: M = q (128 per m-block), N = ncols
+// (x-part chunks then h-part chunks of the concatenated input), K = pixels.  Both operands are
+// read "MN-major": a shared-memory panel is [128 pixel rows][64 bytes of channels], exactly what
+// the channels-last TMA box delivers, so no transpose is ever materialised.
+//
+// One CTA owns (m-block, tap group, split): it keeps up to 512 fp32 accumulator columns in TMEM
+// (taps_in_group x ncols [+ one chunk of columns for the bias]) across ALL its pixel tiles and
+// flushes once at the end with fp32 atomics (split-K over pixel tiles and time).
+// The bias gradient is an extra MMA against a constant panel of ones (group 0 only).
+#include "nint_common.cuh"
+#include "nint_kernels.h"
+
+namespace nint {
+
+constexpr int kWgThreads = 256;
+constexpr int kWgCtrlBytes = 1024;
+constexpr int kWgMaxBufs = 8;
+
+static inline int mpanels_of(int dtype) { return dtype == NINT_BF16 ? 4 : 8; }
+
+int wgrad_smem_bytes(int dtype, int bpanels, int a_bufs, int b_stages) {
+  return 1024 + a_bufs * mpanels_of(dtype) * kPanelBytes + b_stages * bpanels * kPanelBytes + kPanelBytes +
+         kWgCtrlBytes;
+}
+void wgrad_pick_buffers(int dtype, int bpanels, int* a_bufs, int* b_stages) {
+  const int budget = 227 * 1024 - 1024 - kWgCtrlBytes - kPanelBytes;
+  const int a1 = mpanels_of(dtype) * kPanelBytes, b1 = bpanels * kPanelBytes;
+  int a = 2, b = (budget - a * a1) / b1;
+  if (b < 2) {
+    a = 1;
+    b = (budget - a1) / b1;
+  }
+  if (b > kWgMaxBufs) b = kWgMaxBufs;
+  *a_bufs = a;
+  *b_stages = b;
+}
+
+template <typename E>
+__global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_constant__ WgradParams p) {
+  constexpr int DT = ElemTraits<E>::kDtype;
+  constexpr int CE = ElemTraits<E>::kPerChunk;
+  constexpr int MPANELS = 128 / CE;            // A panels per m-block
+  constexpr int ROWS_PER_MMA = 32 / sizeof(E);  // UMMA K: 16 (bf16) / 8 (tf32) pixel rows
+  constexpr int KSTEPS = kTilePixels / ROWS_PER_MMA;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int bpanels = p.nchunks_b[0] + p.nchunks_b[1];
+  const int a_buf_bytes = MPANELS * kPanelBytes;
+  const int b_stage_bytes = bpanels * kPanelBytes;
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + p.a_bufs * a_buf_bytes;
+  uint8_t* sOnes = sB + p.b_stages * b_stage_bytes;
+  uint8_t* ctrl = sOnes + kPanelBytes;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(ctrl);
+  uint64_t* a_empty = a_full + kWgMaxBufs;
+  uint64_t* b_full = a_empty + kWgMaxBufs;
+  uint64_t* b_empty = b_full + kWgMaxBufs;
+  uint64_t* acc_full = b_empty + kWgMaxBufs;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ctrl + kWgCtrlBytes - 16);
+
+  // blockIdx -> (split, group, m-block); CTAs of one split share their pixel tiles through L2
+  const int mb = blockIdx.x % p.m_blocks;
+  const int grp = (blockIdx.x / p.m_blocks) % p.n_groups;
+  const int split = blockIdx.x / (p.m_blocks * p.n_groups);
+  const int tap_begin = p.group_tap0[grp];
+  const int ntaps = p.group_tap0[grp + 1] - tap_begin;
+  const bool do_bias = (grp == 0) && (p.db_acc != nullptr);
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+  const int total_tiles = p.T * p.B * tiles_per_img;
+  const int my_tiles = (total_tiles - split + p.splits - 1) / p.splits;  // split < splits <= total or 0 tiles
+  const uint32_t panel_tx = static_cast<uint32_t>(p.tile_w * p.tile_h * kChunkBytes);
+  const int pad = p.ksize >> 1;
+
+  // zero all operand panels once: rows >= tile_w*tile_h are never written by TMA and must not
+  // contribute to the pixel reduction; fill the ones panel.
+  {
+    uint4* z = reinterpret_cast<uint4*>(smem);
+    const int n16 = (p.a_bufs * a_buf_bytes + p.b_stages * b_stage_bytes) / 16;
+    for (int i = threadIdx.x; i < n16; i += kWgThreads) z[i] = make_uint4(0, 0, 0, 0);
+    uint32_t one;
+    if constexpr (DT == NINT_BF16) one = 0x3f803f80u; else one = 0x3f800000u;
+    uint4* o = reinterpret_cast<uint4*>(sOnes);
+    for (int i = threadIdx.x; i < kPanelBytes / 16; i += kWgThreads) o[i] = make_uint4(one, one, one, one);
+    fence_proxy_async_smem();
+  }
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&p.tmap_dg);
+    prefetch_tensormap(&p.tmap_b[0]);
+    if (p.nchunks_b[1] > 0) prefetch_tensormap(&p.tmap_b[1]);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kWgMaxBufs; ++s) {
+      mbar_init(&a_full[s], 1);
+      mbar_init(&a_empty[s], 1);
+      mbar_init(&b_full[s], 1);
+      mbar_init(&b_empty[s], 1);
+    }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int ab = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      for (int i = 0; i < my_tiles; ++i) {
+        int r = split + i * p.splits;
+        const int tx = r % p.tiles_x;
+        r /= p.tiles_x;
+        const int ty = r % p.tiles_y;
+        r /= p.tiles_y;
+        const int b = r % p.B;
+        const int t = r / p.B;
+        const int x0 = tx * p.tile_w, y0 = ty * p.tile_h;
+        mbar_wait(&a_empty[ab], aph ^ 1);
+        mbar_arrive_expect_tx(&a_full[ab], panel_tx * MPANELS);
+        for (int j = 0; j < MPANELS; ++j)
+          tma_load_5d(sA + ab * a_buf_bytes + j * kPanelBytes, &p.tmap_dg, &a_full[ab], mb * 128 + j * CE, x0, y0, b, t);
+        if (++ab == p.a_bufs) {
+          ab = 0;
+          aph ^= 1;
+        }
+        for (int ti = 0; ti < ntaps; ++ti) {
+          const int tap = tap_begin + ti;
+          const int dy = tap / p.ksize - pad, dx = tap % p.ksize - pad;
+          mbar_wait(&b_empty[bs], bph ^ 1);
+          mbar_arrive_expect_tx(&b_full[bs], panel_tx * bpanels);
+          uint8_t* dst = sB + bs * b_stage_bytes;
+          for (int j = 0; j < p.nchunks_b[0]; ++j, dst += kPanelBytes)
+            tma_load_5d(dst, &p.tmap_b[0], &b_full[bs], j * CE, x0 + dx, y0 + dy, b, p.slot_b0[0] + t);
+          for (int j = 0; j < p.nchunks_b[1]; ++j, dst += kPanelBytes)
+            tma_load_5d(dst, &p.tmap_b[1], &b_full[bs], j * CE, x0 + dx, y0 + dy, b, p.slot_b0[1] + t);
+          if (++bs == p.b_stages) {
+            bs = 0;
+            bph ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0 && my_tiles > 0) {
+      int ab = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      for (int i = 0; i < my_tiles; ++i) {
+        mbar_wait(&a_full[ab], aph);
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(sA + ab * a_buf_bytes);
+        for (int ti = 0; ti < ntaps; ++ti) {
+          mbar_wait(&b_full[bs], bph);
+          tc_fence_after();
+          const uint32_t b_base = smem_u32(sB + bs * b_stage_bytes);
+          const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(ti * p.ncols);
+#pragma unroll
+          for (int ks = 0; ks < KSTEPS; ++ks) {
+            const uint32_t off = ks * ROWS_PER_MMA * kChunkBytes;
+            const uint64_t adesc = make_smem_desc_sw64(a_base + off, kPanelBytes, 512);
+            const uint64_t bdesc = make_smem_desc_sw64(b_base + off, kPanelBytes, 512);
+            umma<DT>(d_tmem, adesc, bdesc, p.idesc, (i | ks) != 0 ? 1u : 0u);
+          }
+          umma_commit(&b_empty[bs]);
+          if (++bs == p.b_stages) {
+            bs = 0;
+            bph ^= 1;
+          }
+        }
+        if (do_bias) {
+          const uint32_t o_base = smem_u32(sOnes);
+          const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(ntaps * p.ncols);
+#pragma unroll
+          for (int ks = 0; ks < KSTEPS; ++ks) {
+            const uint32_t off = ks * ROWS_PER_MMA * kChunkBytes;
+            const uint64_t adesc = make_smem_desc_sw64(a_base + off, kPanelBytes, 512);
+            const uint64_t bdesc = make_smem_desc_sw64(o_base + off, kPanelBytes, 512);
+            umma<DT>(d_tmem, adesc, bdesc, p.idesc_bias, (i | ks) != 0 ? 1u : 0u);
+          }
+        }
+        umma_commit(&a_empty[ab]);
+        if (++ab == p.a_bufs) {
+          ab = 0;
+          aph ^= 1;
+        }
+      }
+      umma_commit(acc_full);
+    }
+  } else if (warp >= 4 && my_tiles > 0) {
+    // ------------------------------------------------------------------ epilogue: flush partial sums
+    const int quad = warp & 3;
+    const int q = mb * 128 + quad * 32 + lane;
+    const bool valid = q < p.hc4;
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    for (int ti = 0; ti < ntaps; ++ti) {
+      float* dst = p.dw_acc + (static_cast<long long>(tap_begin + ti) * p.hc4 + q) * p.ncols;
+      for (int c0 = 0; c0 < p.ncols; c0 += 16) {
+        float v[16];
+        tmem_ld16(taddr + ti * p.ncols + c0, v);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) atomicAdd(dst + c0 + j, v[j]);
+        }
+      }
+    }
+    if (do_bias) {
+      float v[16];
+      tmem_ld16(taddr + ntaps * p.ncols, v);
+      tmem_ld_wait();
+      if (valid) atomicAdd(p.db_acc + q, v[0]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+template <typename E>
+static cudaError_t launch_wg(const WgradParams& p, cudaStream_t stream) {
+  const int dtype = ElemTraits<E>::kDtype;
+  const int smem = wgrad_smem_bytes(dtype, p.nchunks_b[0] + p.nchunks_b[1], p.a_bufs, p.b_stages);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  const int grid = p.m_blocks * p.n_groups * p.splits;
+  if (grid <= 0) return cudaSuccess;
+  wgrad_kernel<E><<<grid, kWgThreads, smem, stream>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_wgrad(int dtype, const WgradParams& p, cudaStream_t stream) {
+  if (dtype == NINT_BF16) return launch_wg<__nv_bfloat16>(p, stream);
+  return launch_wg<float>(p, stream);
+}
+
+}  // namespace nint

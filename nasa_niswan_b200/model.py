@@ -1,0 +1,165 @@
+"""Drop-in replacements for the reference's `model.py` ConvLSTM classes (model.py:196-274).
+
+Same constructor signatures, parameter names/shapes (`layers.{l}.conv.weight|bias`,
+`conv.weight|bias`; checkpoint contract utils.py:27,39), default initialisation and forward
+contracts, so `train.py`, `utils.py` and the notebooks can `from model import ConvLSTM`
+unchanged.  The arithmetic runs in libnint.so (hand-written sm_100a kernels behind the C ABI of
+include/nint.h); there is no CPU or eager-PyTorch fallback.
+"""
+from collections import OrderedDict
+from typing import Sequence
+
+import torch
+import torch.nn as nn
+
+from .engine import Plan
+
+_MAX_CACHED_PLANS = 4
+
+
+class _PlanCache:
+    def __init__(self):
+        self._plans = OrderedDict()
+
+    def get(self, key, factory):
+        p = self._plans.get(key)
+        if p is None:
+            p = factory()
+            self._plans[key] = p
+            while len(self._plans) > _MAX_CACHED_PLANS:
+                self._plans.popitem(last=False)
+        else:
+            self._plans.move_to_end(key)
+        return p
+
+    def clear(self):
+        self._plans.clear()
+
+
+class _ConvLSTMFunction(torch.autograd.Function):
+    """forward = nint_forward (T x L fused cell steps + head); backward = nint_backward (BPTT)."""
+
+    @staticmethod
+    def forward(ctx, plan, x, *params):
+        pred, seq = plan.forward(x)
+        ctx.plan, ctx.generation = plan, plan.generation
+        if plan.return_sequence:
+            return pred, seq
+        return pred
+
+    @staticmethod
+    def backward(ctx, dpred, dseq=None):
+        plan = ctx.plan
+        if plan.generation != ctx.generation:
+            raise RuntimeError("the ConvLSTM workspace was overwritten by a later forward() with the same shape "
+                               "before backward() ran; run backward first (BPTT state lives in the plan workspace)")
+        if ctx.needs_input_grad[1]:
+            raise NotImplementedError("gradient w.r.t. the input x is not implemented (train.py never needs it)")
+        gw, gb, ghw, ghb = plan.backward(dpred, dseq)
+        grads = []
+        for l in range(plan.L):
+            grads += [gw[l], gb[l]]
+        grads += [ghw, ghb]
+        return (None, None, *grads)
+
+
+class ConvLSTMCell(nn.Module):
+    """model.py:196-231.  `forward(x, (h, c)) -> (h, c)`; one fused step on the GPU.
+    Standalone cell calls are forward-only (the trainable path is `ConvLSTM`)."""
+
+    def __init__(self, input_channels, hidden_channels, kernel_size, bias=True, precision="bf16"):
+        super().__init__()
+        self.input_channels = input_channels
+        self.hidden_channels = hidden_channels
+        self.kernel_size = kernel_size
+        self.padding = kernel_size // 2
+        self.bias = bias
+        self.precision = precision
+        # parameter container only (never called): same names, shapes and default init as the reference
+        self.conv = nn.Conv2d(in_channels=self.input_channels + self.hidden_channels,
+                              out_channels=4 * self.hidden_channels, kernel_size=self.kernel_size,
+                              padding=self.padding, bias=self.bias)
+        self._plans = _PlanCache()
+
+    def forward(self, x, hidden_state):
+        h, c = hidden_state
+        if torch.is_grad_enabled() and (x.requires_grad or h.requires_grad or c.requires_grad or
+                                        any(p.requires_grad for p in self.parameters())):
+            raise NotImplementedError("standalone ConvLSTMCell is forward-only; wrap the call in torch.no_grad() "
+                                      "or train through ConvLSTM")
+        B, _, H, W = x.shape
+        key = (B, H, W, self.precision, x.device)
+        plan = self._plans.get(key, lambda: self._make_plan(B, H, W, x.device))
+        plan.set_weights(0, self.conv.weight, self.conv.bias)
+        plan.set_state(0, h, c)
+        plan.forward(x.unsqueeze(1))
+        return plan.get_state(0)
+
+    def _make_plan(self, B, H, W, device):
+        plan = Plan(B, 1, H, W, self.input_channels, [self.hidden_channels], [self.kernel_size],
+                    precision=self.precision, training=False, device=device)
+        hw = torch.zeros(1, self.hidden_channels, 1, 1, device=device)
+        plan.set_head(hw, torch.zeros(1, device=device))
+        return plan
+
+
+class ConvLSTM(nn.Module):
+    """model.py:234-274.  `forward(x[B,T,C,H,W]) -> [B,1,H,W]` (head on the last layer's h at the
+    last step).  `return_sequence=True` restates the commented-out variant (model.py:264,272,274)
+    that test.ipynb:273 was run against: returns `(pred, hs[B,T,H,W])`.
+    `precision`: "bf16" (bf16 operands, fp32 accumulate/state) or "tf32"."""
+
+    def __init__(self, input_channels, hidden_channels: Sequence[int], kernel_size: Sequence[int], num_layers,
+                 precision: str = "bf16", return_sequence: bool = False):
+        super().__init__()
+        assert len(hidden_channels) == num_layers, "The length of hidden_channels should be equal to num_layers"
+        assert len(kernel_size) == num_layers, "The length of kernel_size should be equal to num_layers"
+        self.num_layers = num_layers
+        self.input_channels = input_channels
+        self.precision = precision
+        self.return_sequence = return_sequence
+        layers = []
+        for i in range(self.num_layers):
+            in_ch = input_channels if i == 0 else hidden_channels[i - 1]
+            layers.append(ConvLSTMCell(in_ch, hidden_channels[i], kernel_size[i], precision=precision))
+        self.layers = nn.ModuleList(layers)
+        self.conv = nn.Conv2d(hidden_channels[-1], 1, 1)
+        self._plans = _PlanCache()
+
+    def _params(self):
+        ps = []
+        for cell in self.layers:
+            ps += [cell.conv.weight, cell.conv.bias]
+        return ps + [self.conv.weight, self.conv.bias]
+
+    def plan_for(self, x, training):
+        B, T, C, H, W = x.size()
+        if C != self.input_channels:
+            raise ValueError(f"expected {self.input_channels} input channels, got {C}")
+        key = (B, T, H, W, bool(training), self.return_sequence, self.precision, x.device)
+        hidden = [c.hidden_channels for c in self.layers]
+        ks = [c.kernel_size for c in self.layers]
+        plan = self._plans.get(key, lambda: Plan(B, T, H, W, C, hidden, ks, precision=self.precision,
+                                                 training=training, return_sequence=self.return_sequence,
+                                                 device=x.device))
+        for l, cell in enumerate(self.layers):
+            plan.set_weights(l, cell.conv.weight, cell.conv.bias)
+        plan.set_head(self.conv.weight, self.conv.bias)
+        return plan
+
+    def forward(self, x):
+        if not x.is_cuda:
+            raise RuntimeError("ConvLSTM runs on CUDA (B200) only: there is no CPU fallback; move the module and "
+                               "its input to the GPU")
+        params = self._params()
+        training = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        plan = self.plan_for(x, training)
+        if training:
+            return _ConvLSTMFunction.apply(plan, x, *params)
+        pred, seq = plan.forward(x)
+        return (pred, seq) if self.return_sequence else pred
+
+    def release_workspaces(self):
+        self._plans.clear()
+        for cell in self.layers:
+            cell._plans.clear()
