@@ -78,6 +78,16 @@ int nint_forward(nint_plan* plan, const float* x, float* pred, float* seq, void*
 int nint_backward(nint_plan* plan, const float* dpred, const float* dseq, float* const* grad_weight,
                   float* const* grad_bias, float* grad_head_weight, float* grad_head_bias, void* stream);
 
+/* ---- measurement.  Kernel classes: 0 = fused gate-conv forward, 1 = dgrad + gate backward,
+ * 2 = wgrad, 3 = everything else (layout packing, head, gradient unpacking); -1 = all.
+ * nint_launch_count: kernels launched by this library in the calling process so far.
+ * nint_plan_profile(plan, 1) brackets every later launch of the plan with CUDA events on the
+ * launching stream; nint_plan_profile_read waits for them and returns, per class, the summed
+ * device time in ms and the launch count since the last read (arrays of 4). */
+long long nint_launch_count(int kernel_class);
+int nint_plan_profile(nint_plan* plan, int enable);
+int nint_plan_profile_read(nint_plan* plan, double* ms, long long* count);
+
 /* ---- test hook: raw gate pre-activations of layer 0 at t = 0 without bias,
  * out [B,H,W,4*Hc] fp32 in kernel column order (see nint_gate_column). */
 int nint_debug_raw_gates(nint_plan* plan, const float* x, float* out, void* stream);

@@ -48,6 +48,17 @@ EncodeTiledFn get_encode() {
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// kernel classes for the launch counter / CUDA-event profile
+enum : int { K_FWD = 0, K_BWD = 1, K_WGRAD = 2, K_OTHER = 3, K_NCLS = 4 };
+long long g_launches[K_NCLS] = {0, 0, 0, 0};
+
+struct Profile {
+  bool on = false;
+  std::vector<cudaEvent_t> pool;
+  std::vector<int> cls;  // class of pair i (events 2i, 2i+1)
+  size_t used = 0;       // pairs in flight
+};
+
 struct Layer {
   int cin, hc, k, taps;
   int cx_pad, hc_pad, chx, chh;  // padded channels / 64-byte chunks of the x and h segments
@@ -63,6 +74,7 @@ struct Layer {
   size_t dw_acc_bytes = 0;
   int ncols = 0;
   CUtensorMap tm_H, tm_G, tm_wx, tm_wh, tm_wdx, tm_wdh;
+  CUtensorMap tmw_H, tmw_G;  // wgrad views (32-channel boxes; differ from tm_* in tf32 mode only)
   bool weights_set = false;
 };
 
@@ -77,15 +89,44 @@ struct nint_plan {
   size_t ws_bytes = 0;
   uint8_t* ws = nullptr;
   uint8_t* X = nullptr;  // [T][B][H][W][cx_pad0] E
-  CUtensorMap tm_X;
+  CUtensorMap tm_X, tmw_X;
   float *head_w = nullptr, *head_b = nullptr;
   bool head_set = false;
   bool zero_init = true;
   bool fwd_done = false;
   int final_slot_h = 0, final_slot_c = 0;
+  Profile prof;
 };
 
 namespace {
+
+// every kernel launch of the library goes through here: counts it and, when the plan is being
+// profiled, brackets it with CUDA events on the launching stream
+template <typename F>
+int launch(nint_plan* p, int cls, cudaStream_t st, const char* what, F&& f) {
+  cudaEvent_t e1 = nullptr;
+  if (p && p->prof.on) {
+    Profile& pr = p->prof;
+    if (pr.pool.size() < 2 * (pr.used + 1)) {
+      cudaEvent_t a, b;
+      if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return fail("cudaEventCreate failed");
+      pr.pool.push_back(a);
+      pr.pool.push_back(b);
+    }
+    e1 = pr.pool[2 * pr.used + 1];
+    if (pr.cls.size() <= pr.used) pr.cls.resize(pr.used + 1);
+    pr.cls[pr.used] = cls;
+    cudaEventRecord(pr.pool[2 * pr.used], st);
+    ++pr.used;
+  }
+  cudaError_t e = f();
+  if (e1) cudaEventRecord(e1, st);
+  if (e != cudaSuccess) return fail("%s failed: %s", what, cudaGetErrorString(e));
+  ++g_launches[cls];
+  return 0;
+}
+#define LAUNCH(plan, cls, st, call) \
+  do { if (launch(plan, cls, st, #call, [&]() { return (call); })) return 1; } while (0)
 
 int pick_tile(int H, int W, int* tw_out, int* th_out) {
   long best = -1;
@@ -107,18 +148,21 @@ int pick_tile(int H, int W, int* tw_out, int* th_out) {
   return 0;
 }
 
+// wgrad = true: 32-channel box; tf32 then needs the 128B swizzle with 32-byte atoms (the MN-major tf32
+// UMMA layout), bf16 is the same 64-byte box either way.
 int encode_act_map(CUtensorMap* m, int dtype, void* base, int C, int W, int H, int B, int slots, int ce, int tw,
-                   int th) {
+                   int th, bool wgrad = false) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return fail("cuTensorMapEncodeTiled not available (no CUDA driver?)");
   const cuuint64_t es = dtype == BF16 ? 2 : 4;
   cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B, (cuuint64_t)slots};
   cuuint64_t strides[4] = {C * es, (cuuint64_t)W * C * es, (cuuint64_t)H * W * C * es,
                            (cuuint64_t)B * H * W * C * es};
-  cuuint32_t box[5] = {(cuuint32_t)ce, (cuuint32_t)tw, (cuuint32_t)th, 1, 1};
+  cuuint32_t box[5] = {(cuuint32_t)(wgrad ? 32 : ce), (cuuint32_t)tw, (cuuint32_t)th, 1, 1};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  const CUtensorMapSwizzle sw = (wgrad && dtype == TF32) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_64B;
   CUresult r = enc(m, dtype == BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, base,
-                   dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                   dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(activation C=%d W=%d H=%d B=%d slots=%d) -> %d", C, W, H, B, slots, (int)r);
   return 0;
@@ -235,7 +279,7 @@ int cell_step(nint_plan* p, int l, int t, int epi, float* raw_out, cudaStream_t 
   g.h_out = slot_ptr(p, y.Hs, out_slot_h, y.hc_pad);
   g.gates_out = tr ? slot_ptr(p, y.G, t, 4 * y.hc) : nullptr;
   g.raw_out = raw_out;
-  CK(launch_conv_gemm(epi, p->dtype, g, p->num_sms, st));
+  LAUNCH(p, (epi == EPI_FWD ? K_FWD : K_OTHER), st, launch_conv_gemm(epi, p->dtype, g, p->num_sms, st));
   return 0;
 }
 
@@ -249,6 +293,33 @@ int nint_gate_column(int q, int hidden) { return q_to_n(q, hidden); }
 int nint_pick_tile(int height, int width, int* tile_w, int* tile_h) {
   if (height < 1 || width < 1 || !tile_w || !tile_h) return fail("nint_pick_tile: bad arguments");
   return pick_tile(height, width, tile_w, tile_h);
+}
+
+long long nint_launch_count(int kernel_class) {
+  if (kernel_class < 0) return g_launches[0] + g_launches[1] + g_launches[2] + g_launches[3];
+  return kernel_class < K_NCLS ? g_launches[kernel_class] : 0;
+}
+
+int nint_plan_profile(nint_plan* p, int enable) {
+  if (!p) return fail("null plan");
+  p->prof.on = enable != 0;
+  p->prof.used = 0;
+  return 0;
+}
+
+int nint_plan_profile_read(nint_plan* p, double* ms, long long* count) {
+  if (!p || !ms || !count) return fail("nint_plan_profile_read: null argument");
+  Profile& pr = p->prof;
+  for (int c = 0; c < K_NCLS; ++c) ms[c] = 0.0, count[c] = 0;
+  for (size_t i = 0; i < pr.used; ++i) {
+    CK(cudaEventSynchronize(pr.pool[2 * i + 1]));
+    float t = 0.f;
+    CK(cudaEventElapsedTime(&t, pr.pool[2 * i], pr.pool[2 * i + 1]));
+    ms[pr.cls[i]] += t;
+    ++count[pr.cls[i]];
+  }
+  pr.used = 0;
+  return 0;
 }
 
 int nint_plan_create(const nint_config* cfg, nint_plan** out) {
@@ -281,12 +352,12 @@ int nint_plan_create(const nint_config* cfg, nint_plan** out) {
       return fail("kernel_size[%d] = %d unsupported (odd, <= 15)", l, y.k);
     }
     if (l > 0 && cin > 256) { delete p; return fail("layer %d input channels %d > 256", l, cin); }
-    y.chx = (y.cin + p->ce - 1) / p->ce; y.cx_pad = y.chx * p->ce;
-    y.chh = (y.hc + p->ce - 1) / p->ce;  y.hc_pad = y.chh * p->ce;
+    y.cx_pad = (y.cin + 31) / 32 * 32; y.chx = y.cx_pad / p->ce;   // channels padded to 32 in both dtypes
+    y.hc_pad = (y.hc + 31) / 32 * 32;  y.chh = y.hc_pad / p->ce;
     y.hcb = hcb_of(y.hc); y.n_blocks = y.hc / y.hcb; y.n_tile = 4 * y.hcb;
     y.nslots_h = cfg->training ? p->T + 1 : 2;
     y.nslots_c = cfg->training ? p->T + 1 : 1;
-    y.ncols = (y.chx + y.chh) * p->ce;
+    y.ncols = y.cx_pad + y.hc_pad;
     if (cfg->training && y.ncols > 256) {
       delete p;
       return fail("layer %d: padded input+hidden channels %d > 256 not supported by wgrad", l, y.ncols);
@@ -299,7 +370,11 @@ int nint_plan_create(const nint_config* cfg, nint_plan** out) {
   return 0;
 }
 
-void nint_plan_destroy(nint_plan* plan) { delete plan; }
+void nint_plan_destroy(nint_plan* plan) {
+  if (!plan) return;
+  for (cudaEvent_t e : plan->prof.pool) cudaEventDestroy(e);
+  delete plan;
+}
 
 size_t nint_plan_workspace_bytes(const nint_plan* plan) { return plan ? plan->ws_bytes : 0; }
 
@@ -319,6 +394,7 @@ int nint_plan_bind(nint_plan* p, void* workspace, size_t bytes, void* stream) {
   CK(cudaMemsetAsync(p->ws, 0, p->ws_bytes, st));
   const int tw = p->tile_w, th = p->tile_h, ce = p->ce;
   if (encode_act_map(&p->tm_X, p->dtype, p->X, p->layer[0].cx_pad, p->W, p->H, p->B, p->T, ce, tw, th)) return 1;
+  if (encode_act_map(&p->tmw_X, p->dtype, p->X, p->layer[0].cx_pad, p->W, p->H, p->B, p->T, ce, tw, th, true)) return 1;
   for (int l = 0; l < p->L; ++l) {
     Layer& y = p->layer[l];
     if (encode_act_map(&y.tm_H, p->dtype, y.Hs, y.hc_pad, p->W, p->H, p->B, y.nslots_h, ce, tw, th)) return 1;
@@ -327,6 +403,8 @@ int nint_plan_bind(nint_plan* p, void* workspace, size_t bytes, void* stream) {
     if (p->cfg.training) {
       const int nch = 4 * y.hc / ce;
       if (encode_act_map(&y.tm_G, p->dtype, y.G, 4 * y.hc, p->W, p->H, p->B, p->T, ce, tw, th)) return 1;
+      if (encode_act_map(&y.tmw_G, p->dtype, y.G, 4 * y.hc, p->W, p->H, p->B, p->T, ce, tw, th, true)) return 1;
+      if (encode_act_map(&y.tmw_H, p->dtype, y.Hs, y.hc_pad, p->W, p->H, p->B, y.nslots_h, ce, tw, th, true)) return 1;
       if (encode_w_map(&y.tm_wdh, p->dtype, y.wdh, (long long)y.taps * nch * y.hc, ce, y.hc)) return 1;
       if (l > 0 && encode_w_map(&y.tm_wdx, p->dtype, y.wdx, (long long)y.taps * nch * y.cin, ce, y.cin)) return 1;
     }
@@ -342,8 +420,8 @@ int nint_plan_set_weights(nint_plan* p, int l, const float* weight, const float*
   if (!weight) return fail("null weight");
   Layer& y = p->layer[l];
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  CK(launch_pack_weights_fwd(p->dtype, weight, bias, y.wx, y.wh, y.bias_q, y.cin, y.hc, y.k, st));
-  if (p->cfg.training) CK(launch_pack_weights_bwd(p->dtype, weight, y.wdx, y.wdh, y.cin, y.hc, y.k, st));
+  LAUNCH(p, K_OTHER, st, launch_pack_weights_fwd(p->dtype, weight, bias, y.wx, y.wh, y.bias_q, y.cin, y.hc, y.k, y.cx_pad, y.hc_pad, st));
+  if (p->cfg.training) LAUNCH(p, K_OTHER, st, launch_pack_weights_bwd(p->dtype, weight, y.wdx, y.wdh, y.cin, y.hc, y.k, st));
   y.weights_set = true;
   return 0;
 }
@@ -385,8 +463,8 @@ int nint_plan_set_state(nint_plan* p, int l, const float* h, const float* c, voi
       CK(cudaMemsetAsync(z.Cs, 0, static_cast<size_t>(p->B) * p->H * p->W * z.hc * 4, st));
     }
   }
-  CK(launch_pack_state(p->dtype, h, y.Hs, p->B, y.hc, p->H, p->W, y.hc_pad, st));
-  CK(launch_nchw_to_nhwc_f32(c, y.Cs, p->B, y.hc, p->H, p->W, st));
+  LAUNCH(p, K_OTHER, st, launch_pack_state(p->dtype, h, y.Hs, p->B, y.hc, p->H, p->W, y.hc_pad, st));
+  LAUNCH(p, K_OTHER, st, launch_nchw_to_nhwc_f32(c, y.Cs, p->B, y.hc, p->H, p->W, st));
   p->zero_init = false;
   return 0;
 }
@@ -397,8 +475,8 @@ int nint_plan_get_state(nint_plan* p, int l, float* h, float* c, void* stream) {
   if (!p->fwd_done) return fail("nint_plan_get_state before nint_forward");
   Layer& y = p->layer[l];
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (h) CK(launch_unpack_state(p->dtype, slot_ptr(p, y.Hs, p->final_slot_h, y.hc_pad), h, p->B, y.hc, p->H, p->W, y.hc_pad, st));
-  if (c) CK(launch_nhwc_to_nchw_f32(cslot_ptr(p, y, p->final_slot_c), c, p->B, y.hc, p->H, p->W, st));
+  if (h) LAUNCH(p, K_OTHER, st, launch_unpack_state(p->dtype, slot_ptr(p, y.Hs, p->final_slot_h, y.hc_pad), h, p->B, y.hc, p->H, p->W, y.hc_pad, st));
+  if (c) LAUNCH(p, K_OTHER, st, launch_nhwc_to_nchw_f32(cslot_ptr(p, y, p->final_slot_c), c, p->B, y.hc, p->H, p->W, st));
   return 0;
 }
 
@@ -417,20 +495,20 @@ int nint_forward(nint_plan* p, const float* x, float* pred, float* seq, void* st
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool tr = p->cfg.training != 0;
   const long long HW = static_cast<long long>(p->H) * p->W;
-  CK(launch_pack_input(p->dtype, x, p->X, p->B, p->T, p->cfg.in_channels, p->H, p->W, p->layer[0].cx_pad, st));
+  LAUNCH(p, K_OTHER, st, launch_pack_input(p->dtype, x, p->X, p->B, p->T, p->cfg.in_channels, p->H, p->W, p->layer[0].cx_pad, st));
   const Layer& top = p->layer[p->L - 1];
   for (int t = 0; t < p->T; ++t) {          // model.py:265
     for (int l = 0; l < p->L; ++l)          // model.py:267
       if (cell_step(p, l, t, EPI_FWD, nullptr, st)) return 1;
     if (seq) {                              // model.py:272 (commented variant)
       const int slot = tr ? t + 1 : ((t + 1) & 1);
-      CK(launch_head_fwd(p->dtype, slot_ptr(p, top.Hs, slot, top.hc_pad), p->head_w, p->head_b, seq + t * HW, HW,
+      LAUNCH(p, K_OTHER, st, launch_head_fwd(p->dtype, slot_ptr(p, top.Hs, slot, top.hc_pad), p->head_w, p->head_b, seq + t * HW, HW,
                          p->B, top.hc, top.hc_pad, p->T * HW, st));
     }
   }
   p->final_slot_h = tr ? p->T : (p->T & 1);
   p->final_slot_c = tr ? p->T : 0;
-  CK(launch_head_fwd(p->dtype, slot_ptr(p, top.Hs, p->final_slot_h, top.hc_pad), p->head_w, p->head_b, pred, HW, p->B,
+  LAUNCH(p, K_OTHER, st, launch_head_fwd(p->dtype, slot_ptr(p, top.Hs, p->final_slot_h, top.hc_pad), p->head_w, p->head_b, pred, HW, p->B,
                      top.hc, top.hc_pad, HW, st));  // model.py:274
   p->fwd_done = true;
   return 0;
@@ -440,7 +518,7 @@ int nint_debug_raw_gates(nint_plan* p, const float* x, float* out, void* stream)
   if (check_ready(p)) return 1;
   if (!x || !out) return fail("nint_debug_raw_gates: null argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  CK(launch_pack_input(p->dtype, x, p->X, p->B, p->T, p->cfg.in_channels, p->H, p->W, p->layer[0].cx_pad, st));
+  LAUNCH(p, K_OTHER, st, launch_pack_input(p->dtype, x, p->X, p->B, p->T, p->cfg.in_channels, p->H, p->W, p->layer[0].cx_pad, st));
   return cell_step(p, 0, 0, EPI_RAW, out, st);
 }
 
@@ -462,11 +540,11 @@ int nint_backward(nint_plan* p, const float* dpred, const float* dseq, float* co
     CK(cudaMemsetAsync(grad_head_weight, 0, top.hc * 4, st));
     CK(cudaMemsetAsync(grad_head_bias, 0, 4, st));
     if (dpred)
-      CK(launch_head_bwd(p->dtype, slot_ptr(p, top.Hs, T, top.hc_pad), dpred, HW, grad_head_weight, grad_head_bias, HW,
+      LAUNCH(p, K_OTHER, st, launch_head_bwd(p->dtype, slot_ptr(p, top.Hs, T, top.hc_pad), dpred, HW, grad_head_weight, grad_head_bias, HW,
                          p->B, top.hc, top.hc_pad, st));
     if (dseq)
       for (int t = 0; t < T; ++t)
-        CK(launch_head_bwd(p->dtype, slot_ptr(p, top.Hs, t + 1, top.hc_pad), dseq + t * HW, T * HW, grad_head_weight,
+        LAUNCH(p, K_OTHER, st, launch_head_bwd(p->dtype, slot_ptr(p, top.Hs, t + 1, top.hc_pad), dseq + t * HW, T * HW, grad_head_weight,
                            grad_head_bias, HW, p->B, top.hc, top.hc_pad, st));
   }
   // ---- BPTT: reverse time, top layer first.  The dgrad conv of step t+1 (and of the layer
@@ -512,7 +590,7 @@ int nint_backward(nint_plan* p, const float* dpred, const float* dseq, float* co
           g.head_w = p->head_w;
         }
       }
-      CK(launch_conv_gemm(EPI_BWD, p->dtype, g, p->num_sms, st));
+      LAUNCH(p, K_BWD, st, launch_conv_gemm(EPI_BWD, p->dtype, g, p->num_sms, st));
     }
   }
   // ---- weight / bias gradients, batched over all T steps
@@ -522,13 +600,13 @@ int nint_backward(nint_plan* p, const float* dpred, const float* dseq, float* co
     CK(cudaMemsetAsync(y.db_acc, 0, 4 * y.hc * 4, st));
     WgradParams w;
     memset(&w, 0, sizeof(w));
-    w.tmap_dg = y.tm_G;
-    w.tmap_b[0] = l == 0 ? p->tm_X : p->layer[l - 1].tm_H;
-    w.tmap_b[1] = y.tm_H;
+    w.tmap_dg = y.tmw_G;
+    w.tmap_b[0] = l == 0 ? p->tmw_X : p->layer[l - 1].tmw_H;
+    w.tmap_b[1] = y.tmw_H;
     w.slot_b0[0] = l == 0 ? 0 : 1;
     w.slot_b0[1] = 0;
-    w.nchunks_b[0] = y.chx;
-    w.nchunks_b[1] = y.chh;
+    w.nchunks_b[0] = y.cx_pad / 32;
+    w.nchunks_b[1] = y.hc_pad / 32;
     w.T = T; w.B = p->B; w.H = p->H; w.W = p->W;
     w.tile_w = p->tile_w; w.tile_h = p->tile_h; w.tiles_x = p->tiles_x; w.tiles_y = p->tiles_y;
     w.ksize = y.k;
@@ -536,7 +614,7 @@ int nint_backward(nint_plan* p, const float* dpred, const float* dseq, float* co
     w.m_blocks = (w.hc4 + 127) / 128;
     w.ncols = y.ncols;
     const int tpg = 512 / y.ncols;                      // taps per group
-    int g0 = (512 - p->ce) / y.ncols;                   // group 0 also holds the bias columns
+    int g0 = (512 - 32) / y.ncols;                      // group 0 also holds the 32 bias columns
     if (g0 > tpg) g0 = tpg;
     if (g0 < 1) return fail("wgrad: ncols %d leaves no room for the bias columns", y.ncols);
     int ng = 0, tap = 0;
@@ -553,15 +631,15 @@ int nint_backward(nint_plan* p, const float* dpred, const float* dseq, float* co
     if (splits < 1) splits = 1;
     if (splits > total_tiles) splits = static_cast<int>(total_tiles);
     w.splits = splits;
-    wgrad_pick_buffers(p->dtype, y.chx + y.chh, &w.a_bufs, &w.b_stages);
+    wgrad_pick_buffers(p->dtype, y.ncols / 32, &w.a_bufs, &w.b_stages);
     if (w.b_stages < 1) return fail("wgrad: operand panels do not fit in shared memory");
     w.idesc = idesc_of(p->dtype, 128, y.ncols, 1, 1);
-    w.idesc_bias = idesc_of(p->dtype, 128, p->ce, 1, 1);
+    w.idesc_bias = idesc_of(p->dtype, 128, 32, 1, 1);
     w.dw_acc = y.dw_acc;
     w.db_acc = y.db_acc;
-    CK(launch_wgrad(p->dtype, w, st));
+    LAUNCH(p, K_WGRAD, st, launch_wgrad(p->dtype, w, st));
     if (grad_weight[l])
-      CK(launch_unpack_wgrad(y.dw_acc, y.db_acc, grad_weight[l], grad_bias[l], y.cin, y.hc, y.k, y.ncols, y.cx_pad, 0, st));
+      LAUNCH(p, K_OTHER, st, launch_unpack_wgrad(y.dw_acc, y.db_acc, grad_weight[l], grad_bias[l], y.cin, y.hc, y.k, y.ncols, y.cx_pad, 0, st));
   }
   return 0;
 }

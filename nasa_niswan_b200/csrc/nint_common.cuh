@@ -163,15 +163,22 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 //                                  (ignored by the hardware for swizzled K-major; CUTLASS encodes 1).
 // MN-major operand (wgrad):        64-byte (one chunk) MN atoms LBO apart (one panel), 8-k groups SBO
 //                                  apart (512 B).
-__host__ __device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t smem_addr, uint32_t lbo_bytes,
-                                                                 uint32_t sbo_bytes) {
+// layout codes: 4 = SWIZZLE_64B, 1 = SWIZZLE_128B_BASE32B (128-byte rows swizzled in 32-byte units: the
+// only MN-major layout the hardware accepts for tf32 operands; TMA twin: SWIZZLE_128B_ATOM_32B).
+constexpr uint32_t kLayoutSw64 = 4, kLayoutSw128Base32 = 1;
+__host__ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes,
+                                                            uint32_t sbo_bytes, uint32_t layout) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3fff);
   d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3fff) << 16;
   d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3fff) << 32;
   d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>(4) << 61;
+  d |= static_cast<uint64_t>(layout) << 61;
   return d;
+}
+__host__ __device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t smem_addr, uint32_t lbo_bytes,
+                                                                 uint32_t sbo_bytes) {
+  return make_smem_desc(smem_addr, lbo_bytes, sbo_bytes, kLayoutSw64);
 }
 // Instruction descriptor for kind::f16 / kind::tf32 with fp32 accumulation.
 //   [4,6) D format (1 = f32)  [7,10) A format  [10,13) B format (bf16 = 1, tf32 = 2)
@@ -255,6 +262,13 @@ __device__ __forceinline__ void load_elems(const E* src, float* v) {
       v[i] = f.x; v[i + 1] = f.y; v[i + 2] = f.z; v[i + 3] = f.w;
     }
   }
+}
+
+// round-to-nearest tf32 (tcgen05 kind::tf32 truncates the low 13 mantissa bits of its operands)
+__device__ __forceinline__ float round_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
 }
 
 // activations.  FAST: one MUFU.TANH each (bf16 mode, error below bf16 rounding).

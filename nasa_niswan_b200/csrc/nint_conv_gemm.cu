@@ -227,12 +227,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
               const float cv = fmaf(cn[j], gf, gi * gg);
               cn[j] = cv;
               float hv = go * act_tanh<FAST>(cv);
-              if constexpr (DT == NINT_TF32) {
-                // h feeds the next step's tf32 MMA: round to nearest instead of the MMA's truncation
-                uint32_t r;
-                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(hv));
-                hv = __uint_as_float(r);
-              }
+              if constexpr (DT == NINT_TF32) hv = round_tf32(hv);  // h feeds the next step's tf32 MMA
               hn[j] = hv;
               a[0][j] = gi; a[1][j] = gf; a[2][j] = gg; a[3][j] = go;
             }
@@ -302,6 +297,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
               gf[j] = d_f * f_ * (1.f - f_);
               gg[j] = d_g * (1.f - g_ * g_);
               go[j] = d_o * o_ * (1.f - o_);
+              if constexpr (DT == NINT_TF32) {
+                // dgates are MMA operands of dgrad and wgrad: round to nearest tf32 (the MMA truncates)
+                gi[j] = round_tf32(gi[j]); gf[j] = round_tf32(gf[j]);
+                gg[j] = round_tf32(gg[j]); go[j] = round_tf32(go[j]);
+              }
             }
             store_elems<float, 16>(dcout + c0, dc);
             store_elems<E, 16>(dgo + qb, gi);

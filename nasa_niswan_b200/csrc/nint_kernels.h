@@ -2,7 +2,8 @@
 //
 // Layout conventions shared by every kernel (DESIGN.md "Data layout in HBM"):
 //   * activations are channels-last, [slot][B][H][W][C_pad] of E (E = bf16, or fp32 holding
-//     tf32-rounded values), C_pad a multiple of one 64-byte chunk (32 bf16 / 16 tf32 elements);
+//     tf32-rounded values), C_pad a multiple of 32 channels; the conv kernels walk K in 64-byte
+//     chunks (32 bf16 / 16 tf32 elements), wgrad in 32-channel panels;
 //   * a pixel tile is tile_w x tile_h <= 128 pixels of one image, row = ty * tile_w + tx;
 //   * the 4*hc gate channels of a layer are stored in "q-order": with hcb = min(hc, 64) and
 //     n_blocks = hc / hcb,  q = nb * 4*hcb + gate * hcb + cc  <->  reference channel
@@ -71,7 +72,7 @@ struct alignas(64) WgradParams {
   CUtensorMap tmap_dg;    // dgates [T][B][H][W][4*hc]        (A, MN-major, M = q)
   CUtensorMap tmap_b[2];  // x-part tensor, h-part tensor      (B, MN-major, N = channel)
   int slot_b0[2];         // slot of step 0 for each b tensor
-  int nchunks_b[2];       // 64-byte chunks per b segment
+  int nchunks_b[2];       // 32-channel panels per b segment
   int T, B, H, W;
   int tile_w, tile_h, tiles_x, tiles_y;
   int ksize;
@@ -79,7 +80,7 @@ struct alignas(64) WgradParams {
   int n_groups;
   int group_tap0[kMaxWgradGroups + 1];  // taps [group_tap0[g], group_tap0[g+1]) belong to group g
   int splits;             // split-K factor over pixel tiles
-  int ncols;              // accumulator columns per tap = (sum nchunks_b) * elements per chunk
+  int ncols;              // accumulator columns per tap = (sum nchunks_b) * 32
   int a_bufs, b_stages;
   uint32_t idesc, idesc_bias;
   int hc4;                // 4*hc
@@ -103,7 +104,7 @@ cudaError_t launch_nchw_to_nhwc_f32(const float* src, float* dst, int B, int C, 
 cudaError_t launch_nhwc_to_nchw_f32(const float* src, float* dst, int B, int C, int H, int W, cudaStream_t s);
 // OIHW fp32 master weights -> packed operand panels
 cudaError_t launch_pack_weights_fwd(int dtype, const float* w, const float* bias, void* wpack_x, void* wpack_h,
-                                    float* bias_q, int cin, int hc, int k, cudaStream_t s);
+                                    float* bias_q, int cin, int hc, int k, int cx_pad, int hc_pad, cudaStream_t s);
 cudaError_t launch_pack_weights_bwd(int dtype, const float* w, void* wpack_dx, void* wpack_dh, int cin, int hc,
                                     int k, cudaStream_t s);
 // 1x1 head (model.py:251,274)

@@ -5,8 +5,10 @@
 // which is what autograd's conv-weight backward computes for model.py:220 summed over the time
 // loop (model.py:265); db[q] = sum dgates.  GEMM view: M = q (128 per m-block), N = ncols
 // (x-part chunks then h-part chunks of the concatenated input), K = pixels.  Both operands are
-// read "MN-major": a shared-memory panel is [128 pixel rows][64 bytes of channels], exactly what
-// the channels-last TMA box delivers, so no transpose is ever materialised.
+// read "MN-major": a shared-memory panel is [128 pixel rows][32 channels] (64-byte rows with the
+// 64-byte swizzle for bf16; 128-byte rows with the 128B/32B-atom swizzle for tf32, the only
+// MN-major layout tcgen05 accepts for 32-bit operands), exactly what the channels-last TMA box
+// delivers, so no transpose is ever materialised.
 //
 // One CTA owns (m-block, tap group, split): it keeps up to 512 fp32 accumulator columns in TMEM
 // (taps_in_group x ncols [+ one chunk of columns for the bias]) across ALL its pixel tiles and
@@ -21,15 +23,18 @@ constexpr int kWgThreads = 256;
 constexpr int kWgCtrlBytes = 1024;
 constexpr int kWgMaxBufs = 8;
 
-static inline int mpanels_of(int dtype) { return dtype == NINT_BF16 ? 4 : 8; }
+constexpr int kWgPanelChannels = 32;  // channels per panel row, both dtypes
+constexpr int kWgMPanels = 128 / kWgPanelChannels;
+static inline int wg_panel_bytes(int dtype) { return kTilePixels * kWgPanelChannels * (dtype == NINT_BF16 ? 2 : 4); }
 
 int wgrad_smem_bytes(int dtype, int bpanels, int a_bufs, int b_stages) {
-  return 1024 + a_bufs * mpanels_of(dtype) * kPanelBytes + b_stages * bpanels * kPanelBytes + kPanelBytes +
-         kWgCtrlBytes;
+  const int pb = wg_panel_bytes(dtype);
+  return 1024 + a_bufs * kWgMPanels * pb + b_stages * bpanels * pb + pb + kWgCtrlBytes;
 }
 void wgrad_pick_buffers(int dtype, int bpanels, int* a_bufs, int* b_stages) {
-  const int budget = 227 * 1024 - 1024 - kWgCtrlBytes - kPanelBytes;
-  const int a1 = mpanels_of(dtype) * kPanelBytes, b1 = bpanels * kPanelBytes;
+  const int pb = wg_panel_bytes(dtype);
+  const int budget = 227 * 1024 - 1024 - kWgCtrlBytes - pb;
+  const int a1 = kWgMPanels * pb, b1 = bpanels * pb;
   int a = 2, b = (budget - a * a1) / b1;
   if (b < 2) {
     a = 1;
@@ -43,21 +48,25 @@ void wgrad_pick_buffers(int dtype, int bpanels, int* a_bufs, int* b_stages) {
 template <typename E>
 __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_constant__ WgradParams p) {
   constexpr int DT = ElemTraits<E>::kDtype;
-  constexpr int CE = ElemTraits<E>::kPerChunk;
-  constexpr int MPANELS = 128 / CE;            // A panels per m-block
+  constexpr int CE = kWgPanelChannels;          // channels per panel row
+  constexpr int ROWB = CE * sizeof(E);          // 64 (bf16) / 128 (tf32) bytes per pixel row
+  constexpr int PANEL = kTilePixels * ROWB;     // bytes per panel
+  constexpr uint32_t LAYOUT = (DT == NINT_BF16) ? kLayoutSw64 : kLayoutSw128Base32;
+  constexpr int MPANELS = kWgMPanels;           // A panels per m-block
   constexpr int ROWS_PER_MMA = 32 / sizeof(E);  // UMMA K: 16 (bf16) / 8 (tf32) pixel rows
   constexpr int KSTEPS = kTilePixels / ROWS_PER_MMA;
+  constexpr uint32_t SBO = 512;                 // 8 rows x 64 B (bf16) / 4 rows x 128 B (tf32)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int bpanels = p.nchunks_b[0] + p.nchunks_b[1];
-  const int a_buf_bytes = MPANELS * kPanelBytes;
-  const int b_stage_bytes = bpanels * kPanelBytes;
+  const int a_buf_bytes = MPANELS * PANEL;
+  const int b_stage_bytes = bpanels * PANEL;
   uint8_t* sA = smem;
   uint8_t* sB = sA + p.a_bufs * a_buf_bytes;
   uint8_t* sOnes = sB + p.b_stages * b_stage_bytes;
-  uint8_t* ctrl = sOnes + kPanelBytes;
+  uint8_t* ctrl = sOnes + PANEL;
   uint64_t* a_full = reinterpret_cast<uint64_t*>(ctrl);
   uint64_t* a_empty = a_full + kWgMaxBufs;
   uint64_t* b_full = a_empty + kWgMaxBufs;
@@ -75,7 +84,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
   const int tiles_per_img = p.tiles_x * p.tiles_y;
   const int total_tiles = p.T * p.B * tiles_per_img;
   const int my_tiles = (total_tiles - split + p.splits - 1) / p.splits;  // split < splits <= total or 0 tiles
-  const uint32_t panel_tx = static_cast<uint32_t>(p.tile_w * p.tile_h * kChunkBytes);
+  const uint32_t panel_tx = static_cast<uint32_t>(p.tile_w * p.tile_h * ROWB);
   const int pad = p.ksize >> 1;
 
   // zero all operand panels once: rows >= tile_w*tile_h are never written by TMA and must not
@@ -87,7 +96,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
     uint32_t one;
     if constexpr (DT == NINT_BF16) one = 0x3f803f80u; else one = 0x3f800000u;
     uint4* o = reinterpret_cast<uint4*>(sOnes);
-    for (int i = threadIdx.x; i < kPanelBytes / 16; i += kWgThreads) o[i] = make_uint4(one, one, one, one);
+    for (int i = threadIdx.x; i < PANEL / 16; i += kWgThreads) o[i] = make_uint4(one, one, one, one);
     fence_proxy_async_smem();
   }
   if (warp == 0 && lane == 0) {
@@ -131,7 +140,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
         mbar_wait(&a_empty[ab], aph ^ 1);
         mbar_arrive_expect_tx(&a_full[ab], panel_tx * MPANELS);
         for (int j = 0; j < MPANELS; ++j)
-          tma_load_5d(sA + ab * a_buf_bytes + j * kPanelBytes, &p.tmap_dg, &a_full[ab], mb * 128 + j * CE, x0, y0, b, t);
+          tma_load_5d(sA + ab * a_buf_bytes + j * PANEL, &p.tmap_dg, &a_full[ab], mb * 128 + j * CE, x0, y0, b, t);
         if (++ab == p.a_bufs) {
           ab = 0;
           aph ^= 1;
@@ -142,9 +151,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
           mbar_wait(&b_empty[bs], bph ^ 1);
           mbar_arrive_expect_tx(&b_full[bs], panel_tx * bpanels);
           uint8_t* dst = sB + bs * b_stage_bytes;
-          for (int j = 0; j < p.nchunks_b[0]; ++j, dst += kPanelBytes)
+          for (int j = 0; j < p.nchunks_b[0]; ++j, dst += PANEL)
             tma_load_5d(dst, &p.tmap_b[0], &b_full[bs], j * CE, x0 + dx, y0 + dy, b, p.slot_b0[0] + t);
-          for (int j = 0; j < p.nchunks_b[1]; ++j, dst += kPanelBytes)
+          for (int j = 0; j < p.nchunks_b[1]; ++j, dst += PANEL)
             tma_load_5d(dst, &p.tmap_b[1], &b_full[bs], j * CE, x0 + dx, y0 + dy, b, p.slot_b0[1] + t);
           if (++bs == p.b_stages) {
             bs = 0;
@@ -169,9 +178,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
           const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(ti * p.ncols);
 #pragma unroll
           for (int ks = 0; ks < KSTEPS; ++ks) {
-            const uint32_t off = ks * ROWS_PER_MMA * kChunkBytes;
-            const uint64_t adesc = make_smem_desc_sw64(a_base + off, kPanelBytes, 512);
-            const uint64_t bdesc = make_smem_desc_sw64(b_base + off, kPanelBytes, 512);
+            const uint32_t off = ks * ROWS_PER_MMA * ROWB;
+            const uint64_t adesc = make_smem_desc(a_base + off, PANEL, SBO, LAYOUT);
+            const uint64_t bdesc = make_smem_desc(b_base + off, PANEL, SBO, LAYOUT);
             umma<DT>(d_tmem, adesc, bdesc, p.idesc, (i | ks) != 0 ? 1u : 0u);
           }
           umma_commit(&b_empty[bs]);
@@ -185,9 +194,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
           const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(ntaps * p.ncols);
 #pragma unroll
           for (int ks = 0; ks < KSTEPS; ++ks) {
-            const uint32_t off = ks * ROWS_PER_MMA * kChunkBytes;
-            const uint64_t adesc = make_smem_desc_sw64(a_base + off, kPanelBytes, 512);
-            const uint64_t bdesc = make_smem_desc_sw64(o_base + off, kPanelBytes, 512);
+            const uint32_t off = ks * ROWS_PER_MMA * ROWB;
+            const uint64_t adesc = make_smem_desc(a_base + off, PANEL, SBO, LAYOUT);
+            const uint64_t bdesc = make_smem_desc(o_base + off, PANEL, SBO, LAYOUT);
             umma<DT>(d_tmem, adesc, bdesc, p.idesc_bias, (i | ks) != 0 ? 1u : 0u);
           }
         }

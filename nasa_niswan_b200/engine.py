@@ -146,6 +146,19 @@ class Plan:
                                           _stream()), "nint_backward")
         return gw, gb, ghw, ghb
 
+    # ---- measurement
+    KERNEL_CLASSES = ("gate_conv_fwd", "dgrad_gate_bwd", "wgrad", "other")
+
+    def profile(self, enable: bool):
+        _lib.check(self.lib.nint_plan_profile(self._h, int(enable)), "nint_plan_profile")
+
+    def profile_read(self):
+        """{class: (device ms, launches)} since the last read (waits for the recorded events)."""
+        ms = (ctypes.c_double * 4)()
+        n = (ctypes.c_longlong * 4)()
+        _lib.check(self.lib.nint_plan_profile_read(self._h, ms, n), "nint_plan_profile_read")
+        return {k: (ms[i], n[i]) for i, k in enumerate(self.KERNEL_CLASSES)}
+
     def debug_raw_gates(self, x: torch.Tensor) -> torch.Tensor:
         """Gate pre-activations (no bias) of layer 0 at t=0, returned as [B,4*Hc,H,W] in the
         reference's channel order (test hook for the implicit-GEMM machinery)."""

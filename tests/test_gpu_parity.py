@@ -1,0 +1,165 @@
+"""GPU (B200): parity of the CUDA path, called through the C ABI, against the CPU oracle and the
+reference-generated golden vectors.  Metric and thresholds: SURVEY.md section 8d -- max|a-b| / max|b|
+with b the fp32 oracle; <= 1e-3 in tf32 mode, <= 2e-2 in bf16 mode (north star)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import convlstm_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"tf32": 1e-3, "bf16": 2e-2}
+CASES = ["lstm_c21_h32_k3", "lstm_3layer_k533", "lstm_c8_h16_k5"]
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu():
+    if not torch.cuda.is_available():
+        pytest.fail("GPU tests need a CUDA device (no CPU fallback exists)")
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+
+def _load(golden_dir, name):
+    z = np.load(os.path.join(golden_dir, name + ".npz"))
+    meta = z["meta"].tolist()
+    B, T, cin, H, W, L = meta[:6]
+    hidden, ks = meta[6:6 + L], meta[6 + L:6 + 2 * L]
+    crop = z["crop"].tolist()
+    return z, dict(B=B, T=T, cin=cin, H=H, W=W, L=L, hidden=hidden, ks=ks, crop=None if crop[0] < 0 else tuple(crop))
+
+
+def _net(z, m, precision, **kw):
+    from nasa_niswan_b200 import ConvLSTM
+    net = ConvLSTM(m["cin"], m["hidden"], m["ks"], m["L"], precision=precision, **kw).cuda()
+    net.load_state_dict({k[6:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("param/")})
+    return net
+
+
+@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+@pytest.mark.parametrize("shape", [(1, 21, 64, 3, 7, 18), (2, 21, 64, 3, 20, 24), (3, 8, 16, 5, 11, 13),
+                                   (2, 21, 128, 3, 20, 24), (2, 5, 32, 5, 18, 22), (1, 21, 64, 3, 90, 144)])
+def test_gate_conv_matches_conv2d(precision, shape):
+    """the implicit GEMM alone (TMA zero-fill padding, two K segments, UMMA descriptors)"""
+    from nasa_niswan_b200 import Plan
+    B, C, hc, k, H, W = shape
+    torch.manual_seed(1)
+    x = torch.randn(B, 1, C, H, W, device="cuda")
+    w = torch.randn(4 * hc, C + hc, k, k, device="cuda") * 0.1
+    h0 = torch.randn(B, hc, H, W, device="cuda") * 0.5
+    plan = Plan(B, 1, H, W, C, [hc], [k], precision=precision)
+    plan.set_weights(0, w, None)
+    plan.set_head(torch.zeros(1, hc, 1, 1, device="cuda"), torch.zeros(1, device="cuda"))
+    plan.set_state(0, h0, torch.zeros_like(h0))
+    got = plan.debug_raw_gates(x)
+    ref = F.conv2d(torch.cat([x[:, 0], h0], 1).double().cpu(), w.double().cpu(), None, padding=k // 2)  # fp64 on the CPU
+    assert O.max_abs_normalised(got.cpu(), ref) < TOL[precision]
+
+
+@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+@pytest.mark.parametrize("name", CASES)
+def test_cell_step_matches_golden(golden_dir, name, precision):
+    """ConvLSTMCell.forward with non-zero state (model.py:216-231) against the reference's output"""
+    from nasa_niswan_b200 import ConvLSTMCell
+    z, m = _load(golden_dir, name)
+    cell = ConvLSTMCell(m["cin"], m["hidden"][0], m["ks"][0], precision=precision).cuda()
+    cell.conv.weight.data.copy_(torch.from_numpy(z["param/layers.0.conv.weight"]))
+    cell.conv.bias.data.copy_(torch.from_numpy(z["param/layers.0.conv.bias"]))
+    with torch.no_grad():
+        h1, c1 = cell(torch.from_numpy(z["cell/x"]).cuda(),
+                      (torch.from_numpy(z["cell/h0"]).cuda(), torch.from_numpy(z["cell/c0"]).cuda()))
+    assert O.max_abs_normalised(h1.cpu(), z["cell/h1"]) < TOL[precision]
+    assert O.max_abs_normalised(c1.cpu(), z["cell/c1"]) < TOL[precision]
+
+
+@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+@pytest.mark.parametrize("name", CASES)
+def test_forward_backward_matches_golden(golden_dir, name, precision):
+    """ConvLSTM forward + MSE+L1 loss + BPTT (train.py:96-109) against the reference's autograd"""
+    z, m = _load(golden_dir, name)
+    net = _net(z, m, precision)
+    x, y = torch.from_numpy(z["x"]).cuda(), torch.from_numpy(z["y"]).cuda()
+    with torch.no_grad():
+        pred_inf = net(x)                       # inference plan (2-slot ring, no saved gates)
+    pred = net(x)                               # training plan
+    assert pred.shape == (m["B"], 1, m["H"], m["W"])
+    assert O.max_abs_normalised(pred.detach().cpu(), z["pred"]) < TOL[precision]
+    assert torch.equal(pred_inf, pred.detach())
+    loss = O.training_loss(pred, y, m["crop"])
+    loss.backward()
+    assert abs(float(loss) - float(z["loss"])) < TOL[precision] * max(1.0, abs(float(z["loss"])))
+    for k, p in net.named_parameters():
+        assert p.grad is not None and p.grad.shape == p.shape
+        assert O.max_abs_normalised(p.grad.cpu(), z["grad/" + k]) < TOL[precision], k
+
+
+@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+def test_twelve_step_rollout_against_oracle(precision):
+    """north-star tolerance over a 12-step rollout on the 90x144 grid, 20 levels + emission channel"""
+    from nasa_niswan_b200 import ConvLSTM
+    torch.manual_seed(0)
+    B, T, C, H, W, hc = 2, 12, 21, 90, 144, 64
+    net = ConvLSTM(C, [hc], [3], 1, precision=precision)
+    params = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    net = net.cuda()
+    x, y = torch.randn(B, T, C, H, W), torch.randn(B, H, W)
+    pred = net(x.cuda())
+    loss = O.training_loss(pred, y.cuda())
+    loss.backward()
+    ref_pred, ref_loss, ref_grads = O.forward_backward(x, y, params, 1)
+    assert O.max_abs_normalised(pred.detach().cpu(), ref_pred) < TOL[precision]
+    for k, p in net.named_parameters():
+        assert O.max_abs_normalised(p.grad.cpu(), ref_grads[k]) < TOL[precision], k
+
+
+def test_return_sequence_variant(golden_dir):
+    """commented-out variant model.py:264,272,274: (pred, hs[B,T,H,W]); grads flow through every step"""
+    z, m = _load(golden_dir, CASES[0])
+    net = _net(z, m, "tf32", return_sequence=True)
+    x = torch.from_numpy(z["x"]).cuda()
+    pred, seq = net(x)
+    params = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+    ref_pred, ref_seq = O.convlstm_forward(torch.from_numpy(z["x"]), params, m["L"], return_sequence=True)
+    assert seq.shape == (m["B"], m["T"], m["H"], m["W"])
+    assert O.max_abs_normalised(seq.detach().cpu(), ref_seq) < 1e-3
+    assert torch.equal(seq[:, -1:].detach(), pred.detach())
+    wts = torch.linspace(0.5, 1.5, m["T"]).view(1, -1, 1, 1)
+    ((seq * wts.cuda()).sum() + pred.sum()).backward()
+    leaf = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    rp, rs = O.convlstm_forward(torch.from_numpy(z["x"]), leaf, m["L"], return_sequence=True)
+    ((rs * wts).sum() + rp.sum()).backward()
+    for k, p in net.named_parameters():
+        assert O.max_abs_normalised(p.grad.cpu(), leaf[k].grad) < 1e-3, k
+
+
+def test_linearity_of_backward_at_full_size():
+    """size-independent property at BASELINE cfg-2 geometry (B=32 is too slow for the oracle):
+    gradients are linear in the upstream gradient -- grad(2*L) == 2*grad(L) and the workspace is
+    reusable across steps (same input twice -> identical results)."""
+    from nasa_niswan_b200 import ConvLSTM
+    torch.manual_seed(0)
+    net = ConvLSTM(21, [64], [3], 1, precision="bf16").cuda()
+    x = torch.randn(8, 12, 21, 90, 144, device="cuda")
+    g = {}
+    for scale in (1.0, 2.0, 1.0):
+        net.zero_grad(set_to_none=True)
+        (net(x).square().mean() * scale).backward()
+        g.setdefault(scale, []).append([p.grad.clone() for p in net.parameters()])
+    for a, b in zip(g[1.0][0], g[2.0][0]):
+        assert O.max_abs_normalised((2 * a).cpu(), b.cpu()) < 1e-4
+    for a, b in zip(g[1.0][0], g[1.0][1]):
+        assert O.max_abs_normalised(a.cpu(), b.cpu()) < 1e-4   # fp32 atomics reorder sums only
+
+
+def test_stale_workspace_is_detected(golden_dir):
+    z, m = _load(golden_dir, CASES[0])
+    net = _net(z, m, "bf16")
+    x = torch.from_numpy(z["x"]).cuda()
+    p1 = net(x)
+    net(x)
+    with pytest.raises(RuntimeError, match="overwritten"):
+        p1.sum().backward()

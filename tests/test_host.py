@@ -1,0 +1,128 @@
+"""CPU: the C-ABI library loads and exports what include/nint.h declares; host-side geometry
+logic (tile choice, gate column order, plan validation, workspace accounting); the nn.Module
+surface matches the reference's state_dict contract.  No compute calls (no GPU here)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from nasa_niswan_b200 import ConvLSTM, ConvLSTMCell, _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "nint.h")).read()
+    declared = set(re.findall(r"\b(nint_[a-z_0-9]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in nint.h but not exported by libnint.so"
+    assert declared == set(_lib.EXPORTS)
+    assert lib.nint_version() >= 100
+
+
+def test_pick_tile():
+    # 90x144 (BASELINE grid): 18x7 = 126 of 128 MMA rows used, 8 x 13 tiles
+    assert _lib.pick_tile(90, 144) == (18, 7)
+    for H, W in [(90, 144), (100, 154), (180, 288), (11, 13), (20, 24), (1, 1), (3, 500)]:
+        tw, th = _lib.pick_tile(H, W)
+        assert 1 <= tw * th <= 128 and tw <= 256 and th <= 256
+        assert tw <= max(W, 1) and th <= max(H, 1)
+
+
+@pytest.mark.parametrize("hc", [16, 32, 64, 128, 256])
+def test_gate_column_is_a_permutation(hc):
+    lib = _lib.load()
+    cols = [lib.nint_gate_column(q, hc) for q in range(4 * hc)]
+    assert sorted(cols) == list(range(4 * hc))
+    hcb = min(hc, 64)
+    # inside one n-block the four gates of a channel sit hcb columns apart (model.py:221 order i,f,g,o)
+    for q in range(0, hcb):
+        n = [cols[q + g * hcb] for g in range(4)]
+        assert [v // hc for v in n] == [0, 1, 2, 3] and len({v % hc for v in n}) == 1
+
+
+def _cfg(**kw):
+    cfg = _lib.NintConfig()
+    d = dict(batch=2, seq_len=3, height=20, width=24, in_channels=21, num_layers=1, dtype=0, training=1,
+             return_sequence=0)
+    d.update(kw)
+    hidden, ksize = d.pop("hidden", [32]), d.pop("ksize", [3])
+    for k, v in d.items():
+        setattr(cfg, k, v)
+    for i, (h, k) in enumerate(zip(hidden, ksize)):
+        cfg.hidden[i], cfg.ksize[i] = h, k
+    return cfg
+
+
+def _create(cfg):
+    lib = _lib.load()
+    h = ctypes.c_void_p()
+    rc = lib.nint_plan_create(ctypes.byref(cfg), ctypes.byref(h))
+    return rc, h, lib
+
+
+def test_plan_validation_and_workspace_accounting():
+    rc, h, lib = _create(_cfg())
+    assert rc == 0
+    train_bytes = lib.nint_plan_workspace_bytes(h)
+    lib.nint_plan_destroy(h)
+    rc, h, lib = _create(_cfg(training=0))
+    infer_bytes = lib.nint_plan_workspace_bytes(h)
+    lib.nint_plan_destroy(h)
+    npix = 2 * 20 * 24
+    # training keeps T+1 h/c slots and T gate slots; inference a 2-slot h ring and one c slot
+    assert train_bytes > infer_bytes
+    assert train_bytes >= 3 * npix * 32 * 2 + 4 * npix * 32 * 2 + 4 * npix * 32 * 4 + 3 * npix * 128 * 2
+    assert infer_bytes >= 3 * npix * 32 * 2 + 2 * npix * 32 * 2 + npix * 32 * 4
+    for bad in [dict(hidden=[24]), dict(hidden=[96]), dict(ksize=[4]), dict(num_layers=0), dict(batch=0),
+                dict(dtype=7), dict(hidden=[512])]:
+        rc, h, lib = _create(_cfg(**bad))
+        assert rc != 0 and lib.nint_last_error(), bad
+
+
+def test_compute_without_binding_fails_loudly():
+    rc, h, lib = _create(_cfg())
+    assert rc == 0
+    assert lib.nint_forward(h, None, None, None, None) != 0
+    assert b"not bound" in lib.nint_last_error()
+    lib.nint_plan_destroy(h)
+
+
+def test_module_surface_matches_reference_contract(golden_dir):
+    # param-count known answer test.ipynb:4698-4699 and state_dict names (utils.py:27,39)
+    net = ConvLSTM(5, [64, 32, 16], [5, 3, 3], 3)
+    assert [p.numel() for p in net.parameters()] == [441600, 256, 110592, 128, 27648, 64, 16, 1]
+    z = np.load(os.path.join(golden_dir, "lstm_3layer_k533.npz"))
+    ref_sd = {k[6:]: z[k] for k in z.files if k.startswith("param/")}
+    net = ConvLSTM(5, [32, 16, 16], [5, 3, 3], 3)
+    sd = net.state_dict()
+    assert list(sd.keys()) == list(ref_sd.keys())
+    assert all(tuple(sd[k].shape) == ref_sd[k].shape for k in sd)
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in ref_sd.items()})     # strict load works
+    assert net.layers[0].hidden_channels == 32 and net.num_layers == 3
+    with pytest.raises(AssertionError):
+        ConvLSTM(5, [64, 32], [5, 3, 3], 3)                                       # model.py:237
+
+
+def test_default_init_matches_reference_rng_stream(golden_dir):
+    # same seed -> same parameters as the reference constructor (golden generated with seed 0)
+    z = np.load(os.path.join(golden_dir, "lstm_c21_h32_k3.npz"))
+    torch.manual_seed(0)
+    net = ConvLSTM(21, [32], [3], 1)
+    for k, v in net.state_dict().items():
+        assert np.array_equal(v.numpy(), z["param/" + k]), k
+
+
+def test_no_cpu_fallback():
+    net = ConvLSTM(3, [16], [3], 1)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        net(torch.zeros(1, 2, 3, 8, 8))
+    cell = ConvLSTMCell(3, 16, 3)
+    with pytest.raises((RuntimeError, NotImplementedError)):
+        with torch.no_grad():
+            cell(torch.zeros(1, 3, 8, 8), (torch.zeros(1, 16, 8, 8), torch.zeros(1, 16, 8, 8)))

@@ -1,0 +1,83 @@
+"""CPU, world_size 2 over gloo: the data-parallel host logic (batch sharding, flat gradient buffer,
+mean all-reduce, replicated Adam step) with a tiny stand-in module (the CUDA ConvLSTM cannot run here)."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from nasa_niswan_b200.parallel import FlatGradients, Trainer, shard_batch
+
+
+def test_shard_batch_partitions():
+    for gb, world in [(256, 8), (256, 2), (10, 4), (3, 4), (32, 1)]:
+        spans = [shard_batch(gb, r, world) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == gb
+        assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+        sizes = [b - a for a, b in spans]
+        assert max(sizes) - min(sizes) <= 1
+    assert [shard_batch(256, r, 8) for r in (0, 7)] == [(0, 32), (224, 256)]
+
+
+class _Tiny(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.conv = torch.nn.Conv2d(3, 1, 3, padding=1)
+
+    def forward(self, x):                      # [B,T,C,H,W] -> [B,1,H,W]
+        return self.conv(x[:, -1])
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(100 + rank)              # different init per rank: broadcast must fix it
+    model = _Tiny()
+    tr = Trainer(model, lr=1e-2)
+    torch.manual_seed(0)
+    X, Y = torch.randn(8, 2, 3, 6, 7), torch.randn(8, 6, 7)
+    a, b = shard_batch(8, rank, world)
+    for _ in range(3):
+        tr.step(X[a:b], Y[a:b])
+    flat = torch.cat([p.detach().flatten() for p in model.parameters()])
+    gathered = [torch.zeros_like(flat) for _ in range(world)]
+    dist.all_gather(gathered, flat)
+    if rank == 0:
+        torch.save({"params": gathered}, out)
+    dist.destroy_process_group()
+
+
+def test_two_rank_training_matches_single_process(tmp_path):
+    out = str(tmp_path / "dp.pt")
+    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    got = torch.load(out)["params"]
+    assert torch.allclose(got[0], got[1], atol=0, rtol=0)          # replicas stay identical
+    # single process on the whole batch = same math (mean of shard means, equal shard sizes)
+    torch.manual_seed(100)
+    model = _Tiny()
+    tr = Trainer(model, lr=1e-2)
+    torch.manual_seed(0)
+    X, Y = torch.randn(8, 2, 3, 6, 7), torch.randn(8, 6, 7)
+    for _ in range(3):
+        tr.step(X, Y)
+    ref = torch.cat([p.detach().flatten() for p in model.parameters()])
+    assert torch.allclose(got[0], ref, atol=1e-5)
+
+
+def test_flat_gradients_are_views():
+    m = _Tiny()
+    fg = FlatGradients(m.parameters())
+    m(torch.randn(2, 1, 3, 4, 4)).sum().backward()
+    assert fg.flat.abs().sum() > 0
+    assert all(p.grad.data_ptr() >= fg.flat.data_ptr() for p in m.parameters())
+    fg.zero()
+    assert all(float(p.grad.abs().sum()) == 0 for p in m.parameters())

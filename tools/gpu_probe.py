@@ -40,7 +40,8 @@ def stage_raw(precision, B, C, hc, k, H, W, with_state):
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     comb = torch.cat([x[:, 0], h0 if with_state else torch.zeros_like(h0)], 1)
-    ref = F.conv2d(comb, w, None, padding=k // 2)
+    ref = F.conv2d(comb.double().cpu(), w.double().cpu(), None, padding=k // 2)
+    got = got.cpu()
     e = _err(got, ref)
     print(f"raw[{precision} B{B} C{C} hc{hc} k{k} {H}x{W} state={with_state}] err={e:.3e}")
     if e > 2e-2:
