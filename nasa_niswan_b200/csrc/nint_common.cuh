@@ -225,41 +225,86 @@ __device__ __forceinline__ void unpack_bf16x2(uint32_t u, float& lo, float& hi) 
   hi = __uint_as_float(u & 0xffff0000u);
 }
 
-// store / load N (multiple of 8) consecutive elements as fp32 registers <-> E in global memory
+// 256-bit global accesses (sm_100: LDG/STG.256), 32-byte aligned
+__device__ __forceinline__ void ldg256(const void* p, uint32_t* r) {
+  asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void stg256(void* p, const uint32_t* r) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]),
+               "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+
+// store / load N consecutive elements as fp32 registers <-> E in global memory.  N*sizeof(E) must be a
+// multiple of 16 bytes; multiples of 32 bytes (32-byte aligned addresses) use 256-bit accesses.
 template <typename E, int N>
 __device__ __forceinline__ void store_elems(E* dst, const float* v) {
+  constexpr int BYTES = N * sizeof(E);
   if constexpr (sizeof(E) == 2) {
+    if constexpr (BYTES % 32 == 0) {
 #pragma unroll
-    for (int i = 0; i < N; i += 8) {
-      uint4 u;
-      u.x = pack_bf16x2(v[i + 0], v[i + 1]);
-      u.y = pack_bf16x2(v[i + 2], v[i + 3]);
-      u.z = pack_bf16x2(v[i + 4], v[i + 5]);
-      u.w = pack_bf16x2(v[i + 6], v[i + 7]);
-      *reinterpret_cast<uint4*>(dst + i) = u;
+      for (int i = 0; i < N; i += 16) {
+        uint32_t u[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) u[j] = pack_bf16x2(v[i + 2 * j], v[i + 2 * j + 1]);
+        stg256(dst + i, u);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < N; i += 8) {
+        uint4 u;
+        u.x = pack_bf16x2(v[i + 0], v[i + 1]);
+        u.y = pack_bf16x2(v[i + 2], v[i + 3]);
+        u.z = pack_bf16x2(v[i + 4], v[i + 5]);
+        u.w = pack_bf16x2(v[i + 6], v[i + 7]);
+        *reinterpret_cast<uint4*>(dst + i) = u;
+      }
     }
   } else {
+    if constexpr (BYTES % 32 == 0) {
 #pragma unroll
-    for (int i = 0; i < N; i += 4)
-      *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+      for (int i = 0; i < N; i += 8) stg256(dst + i, reinterpret_cast<const uint32_t*>(v + i));
+    } else {
+#pragma unroll
+      for (int i = 0; i < N; i += 4)
+        *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+    }
   }
 }
 template <typename E, int N>
 __device__ __forceinline__ void load_elems(const E* src, float* v) {
+  constexpr int BYTES = N * sizeof(E);
   if constexpr (sizeof(E) == 2) {
+    if constexpr (BYTES % 32 == 0) {
 #pragma unroll
-    for (int i = 0; i < N; i += 8) {
-      const uint4 u = *reinterpret_cast<const uint4*>(src + i);
-      unpack_bf16x2(u.x, v[i + 0], v[i + 1]);
-      unpack_bf16x2(u.y, v[i + 2], v[i + 3]);
-      unpack_bf16x2(u.z, v[i + 4], v[i + 5]);
-      unpack_bf16x2(u.w, v[i + 6], v[i + 7]);
+      for (int i = 0; i < N; i += 16) {
+        uint32_t u[8];
+        ldg256(src + i, u);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) unpack_bf16x2(u[j], v[i + 2 * j], v[i + 2 * j + 1]);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < N; i += 8) {
+        const uint4 u = *reinterpret_cast<const uint4*>(src + i);
+        unpack_bf16x2(u.x, v[i + 0], v[i + 1]);
+        unpack_bf16x2(u.y, v[i + 2], v[i + 3]);
+        unpack_bf16x2(u.z, v[i + 4], v[i + 5]);
+        unpack_bf16x2(u.w, v[i + 6], v[i + 7]);
+      }
     }
   } else {
+    if constexpr (BYTES % 32 == 0) {
 #pragma unroll
-    for (int i = 0; i < N; i += 4) {
-      const float4 f = *reinterpret_cast<const float4*>(src + i);
-      v[i] = f.x; v[i + 1] = f.y; v[i + 2] = f.z; v[i + 3] = f.w;
+      for (int i = 0; i < N; i += 8) ldg256(src + i, reinterpret_cast<uint32_t*>(v + i));
+    } else {
+#pragma unroll
+      for (int i = 0; i < N; i += 4) {
+        const float4 f = *reinterpret_cast<const float4*>(src + i);
+        v[i] = f.x; v[i + 1] = f.y; v[i + 2] = f.z; v[i + 3] = f.w;
+      }
     }
   }
 }

@@ -12,9 +12,10 @@
 // convolution's zero padding; weights come from pre-packed panels through a 2-D map.  Both land
 // in the 64-byte-swizzled K-major layout the UMMA descriptors expect.
 //
-// Warp roles (256 threads, 1 CTA/SM, persistent over work items):
+// Warp roles (384 threads, 1 CTA/SM, persistent over work items):
 //   warp 0  TMA producer (one lane)       warp 1  MMA issuer (one lane)
-//   warp 2  TMEM allocator                warps 4-7  epilogue (TMEM lane quadrant = warp % 4)
+//   warp 2  TMEM allocator                warps 4-11  epilogue (TMEM lane quadrant = warp % 4,
+//                                                     two warps per quadrant split the channels)
 // The accumulator is double buffered in TMEM (2 x 256 columns) so the epilogue of item i
 // overlaps the MMAs of item i+1.
 #include "nint_common.cuh"
@@ -22,7 +23,7 @@
 
 namespace nint {
 
-constexpr int kConvThreads = 256;
+constexpr int kConvThreads = 384;
 constexpr int kCtrlBytes = 1024;
 constexpr int kMaxStages = 12;
 
@@ -91,7 +92,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4);
+      mbar_init(&tempty_bar[s], 8);
     }
     fence_barrier_init();
   }
@@ -179,8 +180,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       }
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------------ epilogue
+    // ------------------------------------------------------------------ epilogue (8 warps)
+    // TMEM lane quadrant = warp % 4 (hardware rule); the two warps of a quadrant split the
+    // 16-channel groups between them (half = 0 / 1).
     const int quad = warp & 3;
+    const int half = (warp - 4) >> 2;
     const int row = quad * 32 + lane;
     const int ty = row / p.tile_w;
     const int tx = row - ty * p.tile_w;
@@ -194,10 +198,14 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       const bool valid = (ty < p.tile_h) && (y < p.H) && (x < p.W);
       const long long pix = (static_cast<long long>(c.b) * p.H + y) * p.W + x;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(abuf * 256);
-      if (p.nseg > 0) {
-        mbar_wait(&tfull_bar[abuf], aphase);
-        tc_fence_after();
-      }
+      bool waited = (p.nseg == 0);
+      auto wait_acc = [&]() {
+        if (!waited) {
+          mbar_wait(&tfull_bar[abuf], aphase);
+          tc_fence_after();
+          waited = true;
+        }
+      };
       if constexpr (EPI == EPI_FWD) {
         // model.py:221-229.  columns of this n-block: gate * hcb + cc
         const float* cprev = p.c_prev ? p.c_prev + pix * hc + c.nb * hcb : nullptr;
@@ -205,19 +213,21 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
         E* hout = reinterpret_cast<E*>(p.h_out) + pix * p.hc_pad + c.nb * hcb;
         E* gout = p.gates_out ? reinterpret_cast<E*>(p.gates_out) + pix * 4 * hc + c.nb * p.n_tile : nullptr;
         const float* bq = s_bias + c.nb * p.n_tile;
-        for (int cg = 0; cg < hcb; cg += 16) {
+        for (int cg = half * 16; cg < hcb; cg += 32) {
+          float cn[16];
+          if (cprev && valid) {   // issued before the accumulator wait: overlaps the MMA tail
+            load_elems<float, 16>(cprev + cg, cn);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) cn[j] = 0.f;
+          }
+          wait_acc();
           float a[4][16];
 #pragma unroll
           for (int g = 0; g < 4; ++g) tmem_ld16(taddr + g * hcb + cg, a[g]);
           tmem_ld_wait();
           if (valid) {
-            float cn[16], hn[16];
-            if (cprev) {
-              load_elems<float, 16>(cprev + cg, cn);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) cn[j] = 0.f;
-            }
+            float hn[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const float gi = act_sigmoid<FAST>(a[0][j] + bq[cg + j]);
@@ -239,6 +249,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
             }
           }
         }
+        wait_acc();   // warps without a channel group (hcb == 16) still take part in the handshake
       } else if constexpr (EPI == EPI_BWD) {
         // gate backward; accumulator column c = dh_t[c] from the dgrad conv
         const E* gin = reinterpret_cast<const E*>(p.gates_in) + pix * 4 * hc;
@@ -252,19 +263,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
           const long long hw = static_cast<long long>(p.H) * p.W;
           dpred = p.head_dpred[c.b * p.head_dpred_bstride + (pix - c.b * hw)];
         }
-        for (int c0 = 0; c0 < hc; c0 += 16) {
-          float dh[16];
-          if (p.nseg > 0) {
-            tmem_ld16(taddr + c0, dh);
-            tmem_ld_wait();
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) dh[j] = 0.f;
-          }
-          if (valid) {
-            const int nb = c0 / hcb, cc = c0 - nb * hcb;
-            const int qb = nb * 4 * hcb + cc;  // + gate * hcb
-            float gi[16], gf[16], gg[16], go[16], ct[16], cp[16], dc[16];
+        for (int c0 = half * 16; c0 < hc; c0 += 32) {
+          const int nb = c0 / hcb, cc = c0 - nb * hcb;
+          const int qb = nb * 4 * hcb + cc;  // + gate * hcb
+          float gi[16], gf[16], gg[16], go[16], ct[16], cp[16], dc[16], dh[16];
+          if (valid) {   // all global loads of the group in flight before the accumulator wait
             load_elems<E, 16>(gin + qb, gi);
             load_elems<E, 16>(gin + qb + hcb, gf);
             load_elems<E, 16>(gin + qb + 2 * hcb, gg);
@@ -282,6 +285,16 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
 #pragma unroll
               for (int j = 0; j < 16; ++j) dc[j] = 0.f;
             }
+          }
+          if (p.nseg > 0) {
+            wait_acc();
+            tmem_ld16(taddr + c0, dh);
+            tmem_ld_wait();
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) dh[j] = 0.f;
+          }
+          if (valid) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const float dhv = fmaf(dpred, s_headw[c0 + j], dh[j]);
@@ -310,9 +323,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
             store_elems<E, 16>(dgo + qb + 3 * hcb, go);
           }
         }
+        wait_acc();
       } else {
         float* ro = p.raw_out + pix * (p.n_blocks * p.n_tile) + c.nb * p.n_tile;
-        for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
+        wait_acc();
+        for (int c0 = half * 16; c0 < p.n_tile; c0 += 32) {
           float v[16];
           tmem_ld16(taddr + c0, v);
           tmem_ld_wait();

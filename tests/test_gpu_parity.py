@@ -98,22 +98,29 @@ def test_forward_backward_matches_golden(golden_dir, name, precision):
 
 
 @pytest.mark.parametrize("precision", ["tf32", "bf16"])
-def test_twelve_step_rollout_against_oracle(precision):
-    """north-star tolerance over a 12-step rollout on the 90x144 grid, 20 levels + emission channel"""
+@pytest.mark.parametrize("ksize", [3, 5])
+def test_twelve_step_rollout_against_oracle(precision, ksize):
+    """north-star tolerance over a 12-step rollout on the 90x144 grid, 20 levels + emission channel.
+    Forward: pred vs the oracle.  Backward: BPTT of the SAME upstream gradient -- d(MSE+L1)/dpred taken
+    at the oracle's prediction -- because L1Loss's sign(pred - y) is discontinuous: a 1e-4 difference in
+    pred flips the sign at a pixel or two and moves a weight gradient by ~2/sqrt(#pixels) ~ 1e-2, which
+    says nothing about the kernels (measured: tools/parity_report.py)."""
     from nasa_niswan_b200 import ConvLSTM
     torch.manual_seed(0)
     B, T, C, H, W, hc = 2, 12, 21, 90, 144, 64
-    net = ConvLSTM(C, [hc], [3], 1, precision=precision)
+    net = ConvLSTM(C, [hc], [ksize], 1, precision=precision)
     params = {k: v.detach().clone() for k, v in net.state_dict().items()}
     net = net.cuda()
     x, y = torch.randn(B, T, C, H, W), torch.randn(B, H, W)
+    leaf = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    ref_pred = O.convlstm_forward(x, leaf, 1)
+    dpred = torch.autograd.grad(O.training_loss(ref_pred, y), ref_pred, retain_graph=True)[0]
+    ref_pred.backward(dpred)
     pred = net(x.cuda())
-    loss = O.training_loss(pred, y.cuda())
-    loss.backward()
-    ref_pred, ref_loss, ref_grads = O.forward_backward(x, y, params, 1)
-    assert O.max_abs_normalised(pred.detach().cpu(), ref_pred) < TOL[precision]
+    assert O.max_abs_normalised(pred.detach().cpu(), ref_pred.detach()) < TOL[precision]
+    pred.backward(dpred.cuda())
     for k, p in net.named_parameters():
-        assert O.max_abs_normalised(p.grad.cpu(), ref_grads[k]) < TOL[precision], k
+        assert O.max_abs_normalised(p.grad.cpu(), leaf[k].grad) < TOL[precision], k
 
 
 def test_return_sequence_variant(golden_dir):
