@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -74,6 +75,7 @@ struct Layer {
   size_t dw_acc_bytes = 0;
   int ncols = 0;
   CUtensorMap tm_H, tm_G, tm_wx, tm_wh, tm_wdx, tm_wdh;
+  CUtensorMap tm_H_up;       // Hs[l] read as the x segment of layer l+1 (halo of k_{l+1})
   CUtensorMap tmw_H, tmw_G;  // wgrad views (32-channel boxes; differ from tm_* in tf32 mode only)
   bool weights_set = false;
 };
@@ -95,6 +97,10 @@ struct nint_plan {
   bool zero_init = true;
   bool fwd_done = false;
   int final_slot_h = 0, final_slot_c = 0;
+  int variant = 1;        // 0 = per-tap tiles (nint_conv_gemm.cu), 1 = halo tiles (nint_conv_halo.cu)
+  int cluster = 1;        // CTAs sharing weight stages (halo variant, layers with n_blocks == 1)
+  int base_offset_mode = 0;
+  int debug_flags = 0;
   Profile prof;
 };
 
@@ -151,7 +157,9 @@ int pick_tile(int H, int W, int* tw_out, int* th_out) {
 // wgrad = true: 32-channel box; tf32 then needs the 128B swizzle with 32-byte atoms (the MN-major tf32
 // UMMA layout), bf16 is the same 64-byte box either way.
 int encode_act_map(CUtensorMap* m, int dtype, void* base, int C, int W, int H, int B, int slots, int ce, int tw,
-                   int th, bool wgrad = false) {
+                   int th, bool wgrad = false, int halo = 0) {
+  tw += 2 * halo;
+  th += 2 * halo;
   EncodeTiledFn enc = get_encode();
   if (!enc) return fail("cuTensorMapEncodeTiled not available (no CUDA driver?)");
   const cuuint64_t es = dtype == BF16 ? 2 : 4;
@@ -238,6 +246,7 @@ inline float* cslot_ptr(const nint_plan* p, const Layer& y, int slot) {
 
 void fill_common(const nint_plan* p, const Layer& y, ConvGemmParams& g) {
   memset(&g, 0, sizeof(g));
+  g.debug_flags = p->debug_flags;
   g.B = p->B; g.H = p->H; g.W = p->W;
   g.tile_w = p->tile_w; g.tile_h = p->tile_h; g.tiles_x = p->tiles_x; g.tiles_y = p->tiles_y;
   g.hc = y.hc; g.hc_pad = y.hc_pad; g.hcb = y.hcb;
@@ -257,7 +266,7 @@ int cell_step(nint_plan* p, int l, int t, int epi, float* raw_out, cudaStream_t 
   const int out_slot_h = tr ? t + 1 : ((t + 1) & 1);
   // segment 0: x_t (layer 0) or the h_t of the layer below (model.py:266,271)
   int s = 0;
-  g.seg[s].tmap_act = l == 0 ? p->tm_X : p->layer[l - 1].tm_H;
+  g.seg[s].tmap_act = l == 0 ? p->tm_X : (p->variant == 1 ? p->layer[l - 1].tm_H_up : p->layer[l - 1].tm_H);
   g.seg[s].tmap_w = y.tm_wx;
   g.seg[s].slot = l == 0 ? t : (tr ? t + 1 : ((t + 1) & 1));
   g.seg[s].ksize = y.k;
@@ -279,7 +288,14 @@ int cell_step(nint_plan* p, int l, int t, int epi, float* raw_out, cudaStream_t 
   g.h_out = slot_ptr(p, y.Hs, out_slot_h, y.hc_pad);
   g.gates_out = tr ? slot_ptr(p, y.G, t, 4 * y.hc) : nullptr;
   g.raw_out = raw_out;
-  LAUNCH(p, (epi == EPI_FWD ? K_FWD : K_OTHER), st, launch_conv_gemm(epi, p->dtype, g, p->num_sms, st));
+  if (p->variant == 1) {
+    g.cluster = y.n_blocks == 1 ? p->cluster : 1;
+    g.base_offset_mode = p->base_offset_mode;
+    conv_halo_plan(g);
+    LAUNCH(p, (epi == EPI_FWD ? K_FWD : K_OTHER), st, launch_conv_halo(epi, p->dtype, g, p->num_sms, st));
+  } else {
+    LAUNCH(p, (epi == EPI_FWD ? K_FWD : K_OTHER), st, launch_conv_gemm(epi, p->dtype, g, p->num_sms, st));
+  }
   return 0;
 }
 
@@ -336,7 +352,23 @@ int nint_plan_create(const nint_config* cfg, nint_plan** out) {
   p->dtype = cfg->dtype;
   p->esize = cfg->dtype == BF16 ? 2 : 4;
   p->ce = 64 / p->esize;
-  pick_tile(p->H, p->W, &p->tile_w, &p->tile_h);
+  {  // debug / A-B knobs (documented in DESIGN.md): kernel variant, cluster size, descriptor base offset
+    const char* v = getenv("NINT_CONV_VARIANT");
+    p->variant = (v && !strcmp(v, "pertap")) ? 0 : 1;
+    const char* c = getenv("NINT_CLUSTER");
+    p->cluster = c ? atoi(c) : 2;
+    if (p->cluster != 1 && p->cluster != 2 && p->cluster != 4) p->cluster = 1;
+    const char* b = getenv("NINT_BASE_OFFSET");
+    p->base_offset_mode = b ? atoi(b) : 0;
+    const char* d = getenv("NINT_DEBUG_FLAGS");
+    p->debug_flags = d ? atoi(d) : 0;
+  }
+  if (p->variant == 1) {
+    p->tile_w = 8;
+    p->tile_h = 16;
+  } else {
+    pick_tile(p->H, p->W, &p->tile_w, &p->tile_h);
+  }
   p->tiles_x = (p->W + p->tile_w - 1) / p->tile_w;
   p->tiles_y = (p->H + p->tile_h - 1) / p->tile_h;
   int cin = cfg->in_channels;
@@ -393,20 +425,27 @@ int nint_plan_bind(nint_plan* p, void* workspace, size_t bytes, void* stream) {
   carve(p, p->ws);
   CK(cudaMemsetAsync(p->ws, 0, p->ws_bytes, st));
   const int tw = p->tile_w, th = p->tile_h, ce = p->ce;
-  if (encode_act_map(&p->tm_X, p->dtype, p->X, p->layer[0].cx_pad, p->W, p->H, p->B, p->T, ce, tw, th)) return 1;
+  const bool halo = p->variant == 1;
+  auto pad_of = [&](int l) { return halo ? p->layer[l].k / 2 : 0; };
+  auto cl_fwd = [&](int l) { return (halo && p->layer[l].n_blocks == 1) ? p->cluster : 1; };
+  auto cl_bwd = [&](int l) { return halo ? p->cluster : 1; };
+  if (encode_act_map(&p->tm_X, p->dtype, p->X, p->layer[0].cx_pad, p->W, p->H, p->B, p->T, ce, tw, th, false, pad_of(0))) return 1;
   if (encode_act_map(&p->tmw_X, p->dtype, p->X, p->layer[0].cx_pad, p->W, p->H, p->B, p->T, ce, tw, th, true)) return 1;
   for (int l = 0; l < p->L; ++l) {
     Layer& y = p->layer[l];
-    if (encode_act_map(&y.tm_H, p->dtype, y.Hs, y.hc_pad, p->W, p->H, p->B, y.nslots_h, ce, tw, th)) return 1;
-    if (encode_w_map(&y.tm_wx, p->dtype, y.wx, (long long)y.n_blocks * y.taps * y.chx * y.n_tile, ce, y.n_tile)) return 1;
-    if (encode_w_map(&y.tm_wh, p->dtype, y.wh, (long long)y.n_blocks * y.taps * y.chh * y.n_tile, ce, y.n_tile)) return 1;
+    if (encode_act_map(&y.tm_H, p->dtype, y.Hs, y.hc_pad, p->W, p->H, p->B, y.nslots_h, ce, tw, th, false, pad_of(l))) return 1;
+    if (l + 1 < p->L &&
+        encode_act_map(&y.tm_H_up, p->dtype, y.Hs, y.hc_pad, p->W, p->H, p->B, y.nslots_h, ce, tw, th, false, pad_of(l + 1))) return 1;
+    if (encode_w_map(&y.tm_wx, p->dtype, y.wx, (long long)y.n_blocks * y.taps * y.chx * y.n_tile, ce, y.n_tile / cl_fwd(l))) return 1;
+    if (encode_w_map(&y.tm_wh, p->dtype, y.wh, (long long)y.n_blocks * y.taps * y.chh * y.n_tile, ce, y.n_tile / cl_fwd(l))) return 1;
     if (p->cfg.training) {
       const int nch = 4 * y.hc / ce;
-      if (encode_act_map(&y.tm_G, p->dtype, y.G, 4 * y.hc, p->W, p->H, p->B, p->T, ce, tw, th)) return 1;
+      if (encode_act_map(&y.tm_G, p->dtype, y.G, 4 * y.hc, p->W, p->H, p->B, p->T, ce, tw, th, false, pad_of(l))) return 1;
       if (encode_act_map(&y.tmw_G, p->dtype, y.G, 4 * y.hc, p->W, p->H, p->B, p->T, ce, tw, th, true)) return 1;
       if (encode_act_map(&y.tmw_H, p->dtype, y.Hs, y.hc_pad, p->W, p->H, p->B, y.nslots_h, ce, tw, th, true)) return 1;
-      if (encode_w_map(&y.tm_wdh, p->dtype, y.wdh, (long long)y.taps * nch * y.hc, ce, y.hc)) return 1;
-      if (l > 0 && encode_w_map(&y.tm_wdx, p->dtype, y.wdx, (long long)y.taps * nch * y.cin, ce, y.cin)) return 1;
+      // dgrad launch of layer l consumes wdh_l (N = hc_l); wdx_l is consumed by the launch of layer l-1 (N = hc_{l-1})
+      if (encode_w_map(&y.tm_wdh, p->dtype, y.wdh, (long long)y.taps * nch * y.hc, ce, y.hc / cl_bwd(l))) return 1;
+      if (l > 0 && encode_w_map(&y.tm_wdx, p->dtype, y.wdx, (long long)y.taps * nch * y.cin, ce, y.cin / cl_bwd(l - 1))) return 1;
     }
   }
   p->zero_init = true;
@@ -590,7 +629,14 @@ int nint_backward(nint_plan* p, const float* dpred, const float* dseq, float* co
           g.head_w = p->head_w;
         }
       }
-      LAUNCH(p, K_BWD, st, launch_conv_gemm(EPI_BWD, p->dtype, g, p->num_sms, st));
+      if (p->variant == 1) {
+        g.cluster = p->cluster;
+        g.base_offset_mode = p->base_offset_mode;
+        conv_halo_plan(g);
+        LAUNCH(p, K_BWD, st, launch_conv_halo(EPI_BWD, p->dtype, g, p->num_sms, st));
+      } else {
+        LAUNCH(p, K_BWD, st, launch_conv_gemm(EPI_BWD, p->dtype, g, p->num_sms, st));
+      }
     }
   }
   // ---- weight / bias gradients, batched over all T steps

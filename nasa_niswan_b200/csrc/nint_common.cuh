@@ -26,6 +26,16 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// One lane of a fully converged warp.  Role loops run warp-uniform (all 32 lanes walk the same
+// control flow, so addresses / descriptors live in uniform registers) and only the instructions with
+// side effects are predicated on the elected lane; guarding the whole loop with `lane == 0` instead
+// costs ~100 cycles per tcgen05.mma in R2UR moves and dependent scalar chains (ncu, profiles/).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------------------------
 // mbarrier
 // ---------------------------------------------------------------------------------
@@ -225,6 +235,9 @@ __device__ __forceinline__ void unpack_bf16x2(uint32_t u, float& lo, float& hi) 
   hi = __uint_as_float(u & 0xffff0000u);
 }
 
+__device__ __forceinline__ void lds128(uint32_t saddr, float* v) {
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(saddr));
+}
 // 256-bit global accesses (sm_100: LDG/STG.256), 32-byte aligned
 __device__ __forceinline__ void ldg256(const void* p, uint32_t* r) {
   asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"

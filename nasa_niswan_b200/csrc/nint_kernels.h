@@ -20,7 +20,7 @@ enum : int { EPI_FWD = 0, EPI_BWD = 1, EPI_RAW = 2 };
 // One K-segment of an implicit-GEMM convolution: an activation tensor read through a 5-D TMA
 // map (box = one chunk x tile_w x tile_h pixels; out-of-image pixels are zero-filled by TMA =
 // the conv's zero padding, model.py:204-211) and its packed weights read through a 2-D map
-// [(nb*taps + tap)*nchunks + chunk][n_tile rows][chunk elements].
+// [(nb*nchunks + chunk)*taps + tap][n_tile rows][chunk elements].
 struct alignas(64) ConvSegment {
   CUtensorMap tmap_act;
   CUtensorMap tmap_w;
@@ -39,6 +39,10 @@ struct alignas(64) ConvGemmParams {
   int n_tile;    // UMMA N (accumulator columns per item)
   int n_blocks;  // N blocks per pixel tile (forward with hidden > 64)
   int num_stages;
+  // halo variant (nint_conv_halo.cu): activation buffers, cluster size, descriptor base-offset policy
+  int na_bufs, a_buf_bytes, cluster, base_offset_mode, taps_per_stage;
+  int group, a_halo_bytes;
+  int debug_flags;          // experiments: 1 = epilogue does no global memory ops / math, 2 = no MMA issue  // tiles per item group (side-by-side accumulators), bytes of one halo chunk
   uint32_t idesc;
   int hc, hc_pad;  // hidden channels of this layer / padded channel count of its h tensor
   int hcb;         // min(hc, 64)
@@ -65,6 +69,9 @@ struct alignas(64) ConvGemmParams {
 int conv_gemm_smem_bytes(int n_tile, int num_stages, int hc);
 int conv_gemm_pick_stages(int n_tile, int hc);
 cudaError_t launch_conv_gemm(int epi, int dtype, const ConvGemmParams& p, int num_sms, cudaStream_t stream);
+// halo variant: 8x16 pixel tiles, activation chunk + halo loaded once and re-read by every tap
+void conv_halo_plan(ConvGemmParams& p);  // fills na_bufs / a_buf_bytes / num_stages from nseg, seg[].ksize, n_tile, hc
+cudaError_t launch_conv_halo(int epi, int dtype, const ConvGemmParams& p, int num_sms, cudaStream_t stream);
 
 // ---- wgrad (nint_wgrad.cu):  dW[tap][q][col] += sum_pixels dgates[pix][q] * comb[pix + tap][col]
 constexpr int kMaxWgradGroups = 32;

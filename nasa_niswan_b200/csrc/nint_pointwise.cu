@@ -191,7 +191,7 @@ cudaError_t launch_nhwc_to_nchw_f32(const float* src, float* dst, int B, int C, 
 
 // ------------------------------------------------------------------------------------------
 // weight packing.  Reference layout: W[n][c][dy][dx], n = gate*hc + channel, c over cat(x, h)
-// (model.py:207-211,219).  Packed panel row index = ((nb*taps + tap)*nchunks + chunk)*n_tile + col,
+// (model.py:207-211,219).  Packed panel row index = ((nb*nchunks + chunk)*taps + tap)*n_tile + col,
 // each row holds one chunk (CE elements) of K.
 // ------------------------------------------------------------------------------------------
 template <typename E>
@@ -211,9 +211,9 @@ __global__ void pack_w_fwd_kernel(const float* __restrict__ w, const float* __re
     const int nch = is_h ? chh : chx;
     const int e = static_cast<int>(r % CE); r /= CE;
     const int col = static_cast<int>(r % n_tile); r /= n_tile;
-    const int ch = static_cast<int>(r % nch); r /= nch;
-    const int tap = static_cast<int>(r % taps);
-    const int nb = static_cast<int>(r / taps);
+    const int tap = static_cast<int>(r % taps); r /= taps;
+    const int ch = static_cast<int>(r % nch);
+    const int nb = static_cast<int>(r / nch);
     const int n = (col / hcb) * hc + nb * hcb + (col % hcb);
     const int cl = ch * CE + e;
     const int climit = is_h ? hc : cin;
@@ -226,7 +226,7 @@ __global__ void pack_w_fwd_kernel(const float* __restrict__ w, const float* __re
 }
 
 // dgrad operands: K = q (4*hc), N = input channel, taps flipped (transposed convolution):
-//   wd[tap'][chunk][col][e] = W[n(q = chunk*CE + e)][c(col)][k-1-dy'][k-1-dx']
+//   wd[chunk][tap'][col][e] = W[n(q = chunk*CE + e)][c(col)][k-1-dy'][k-1-dx']
 template <typename E>
 __global__ void pack_w_bwd_kernel(const float* __restrict__ w, E* __restrict__ wdx, E* __restrict__ wdh, int cin,
                                   int hc, int k) {
@@ -241,8 +241,8 @@ __global__ void pack_w_bwd_kernel(const float* __restrict__ w, E* __restrict__ w
     const int ncol = is_h ? hc : cin;
     const int e = static_cast<int>(r % CE); r /= CE;
     const int col = static_cast<int>(r % ncol); r /= ncol;
-    const int ch = static_cast<int>(r % nch);
-    const int tap = static_cast<int>(r / nch);
+    const int tap = static_cast<int>(r % taps);
+    const int ch = static_cast<int>(r / taps);
     const int n = q_to_n(ch * CE + e, hc);
     const int c = is_h ? cin + col : col;
     const float v = w[(static_cast<long long>(n) * ctot + c) * taps + (taps - 1 - tap)];

@@ -125,7 +125,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    {
+      const bool leader = elect_one();
       int ab = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
       for (int i = 0; i < my_tiles; ++i) {
@@ -138,9 +139,11 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
         const int t = r / p.B;
         const int x0 = tx * p.tile_w, y0 = ty * p.tile_h;
         mbar_wait(&a_empty[ab], aph ^ 1);
-        mbar_arrive_expect_tx(&a_full[ab], panel_tx * MPANELS);
-        for (int j = 0; j < MPANELS; ++j)
-          tma_load_5d(sA + ab * a_buf_bytes + j * PANEL, &p.tmap_dg, &a_full[ab], mb * 128 + j * CE, x0, y0, b, t);
+        if (leader) {
+          mbar_arrive_expect_tx(&a_full[ab], panel_tx * MPANELS);
+          for (int j = 0; j < MPANELS; ++j)
+            tma_load_5d(sA + ab * a_buf_bytes + j * PANEL, &p.tmap_dg, &a_full[ab], mb * 128 + j * CE, x0, y0, b, t);
+        }
         if (++ab == p.a_bufs) {
           ab = 0;
           aph ^= 1;
@@ -149,12 +152,14 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
           const int tap = tap_begin + ti;
           const int dy = tap / p.ksize - pad, dx = tap % p.ksize - pad;
           mbar_wait(&b_empty[bs], bph ^ 1);
-          mbar_arrive_expect_tx(&b_full[bs], panel_tx * bpanels);
-          uint8_t* dst = sB + bs * b_stage_bytes;
-          for (int j = 0; j < p.nchunks_b[0]; ++j, dst += PANEL)
-            tma_load_5d(dst, &p.tmap_b[0], &b_full[bs], j * CE, x0 + dx, y0 + dy, b, p.slot_b0[0] + t);
-          for (int j = 0; j < p.nchunks_b[1]; ++j, dst += PANEL)
-            tma_load_5d(dst, &p.tmap_b[1], &b_full[bs], j * CE, x0 + dx, y0 + dy, b, p.slot_b0[1] + t);
+          if (leader) {
+            mbar_arrive_expect_tx(&b_full[bs], panel_tx * bpanels);
+            uint8_t* dst = sB + bs * b_stage_bytes;
+            for (int j = 0; j < p.nchunks_b[0]; ++j, dst += PANEL)
+              tma_load_5d(dst, &p.tmap_b[0], &b_full[bs], j * CE, x0 + dx, y0 + dy, b, p.slot_b0[0] + t);
+            for (int j = 0; j < p.nchunks_b[1]; ++j, dst += PANEL)
+              tma_load_5d(dst, &p.tmap_b[1], &b_full[bs], j * CE, x0 + dx, y0 + dy, b, p.slot_b0[1] + t);
+          }
           if (++bs == p.b_stages) {
             bs = 0;
             bph ^= 1;
@@ -164,49 +169,48 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0 && my_tiles > 0) {
+    if (my_tiles > 0) {
+      const bool leader = elect_one();
       int ab = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
       for (int i = 0; i < my_tiles; ++i) {
         mbar_wait(&a_full[ab], aph);
         tc_fence_after();
-        const uint32_t a_base = smem_u32(sA + ab * a_buf_bytes);
+        const uint64_t adesc0 = make_smem_desc(smem_u32(sA + ab * a_buf_bytes), PANEL, SBO, LAYOUT);
         for (int ti = 0; ti < ntaps; ++ti) {
           mbar_wait(&b_full[bs], bph);
           tc_fence_after();
-          const uint32_t b_base = smem_u32(sB + bs * b_stage_bytes);
+          const uint64_t bdesc0 = make_smem_desc(smem_u32(sB + bs * b_stage_bytes), PANEL, SBO, LAYOUT);
           const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(ti * p.ncols);
+          if (leader) {
 #pragma unroll
-          for (int ks = 0; ks < KSTEPS; ++ks) {
-            const uint32_t off = ks * ROWS_PER_MMA * ROWB;
-            const uint64_t adesc = make_smem_desc(a_base + off, PANEL, SBO, LAYOUT);
-            const uint64_t bdesc = make_smem_desc(b_base + off, PANEL, SBO, LAYOUT);
-            umma<DT>(d_tmem, adesc, bdesc, p.idesc, (i | ks) != 0 ? 1u : 0u);
+            for (int ks = 0; ks < KSTEPS; ++ks) {
+              const uint64_t off = static_cast<uint64_t>((ks * ROWS_PER_MMA * ROWB) >> 4);
+              umma<DT>(d_tmem, adesc0 + off, bdesc0 + off, p.idesc, (i | ks) != 0 ? 1u : 0u);
+            }
+            umma_commit(&b_empty[bs]);
           }
-          umma_commit(&b_empty[bs]);
           if (++bs == p.b_stages) {
             bs = 0;
             bph ^= 1;
           }
         }
-        if (do_bias) {
-          const uint32_t o_base = smem_u32(sOnes);
+        if (do_bias && leader) {
+          const uint64_t odesc0 = make_smem_desc(smem_u32(sOnes), PANEL, SBO, LAYOUT);
           const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(ntaps * p.ncols);
 #pragma unroll
           for (int ks = 0; ks < KSTEPS; ++ks) {
-            const uint32_t off = ks * ROWS_PER_MMA * ROWB;
-            const uint64_t adesc = make_smem_desc(a_base + off, PANEL, SBO, LAYOUT);
-            const uint64_t bdesc = make_smem_desc(o_base + off, PANEL, SBO, LAYOUT);
-            umma<DT>(d_tmem, adesc, bdesc, p.idesc_bias, (i | ks) != 0 ? 1u : 0u);
+            const uint64_t off = static_cast<uint64_t>((ks * ROWS_PER_MMA * ROWB) >> 4);
+            umma<DT>(d_tmem, adesc0 + off, odesc0 + off, p.idesc_bias, (i | ks) != 0 ? 1u : 0u);
           }
         }
-        umma_commit(&a_empty[ab]);
+        if (leader) umma_commit(&a_empty[ab]);
         if (++ab == p.a_bufs) {
           ab = 0;
           aph ^= 1;
         }
       }
-      umma_commit(acc_full);
+      if (leader) umma_commit(acc_full);
     }
   } else if (warp >= 4 && my_tiles > 0) {
     // ------------------------------------------------------------------ epilogue: flush partial sums

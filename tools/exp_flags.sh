@@ -1,0 +1,9 @@
+#!/bin/bash
+for f in 0 1 2 3; do
+  echo "##### NINT_DEBUG_FLAGS=$f (1: no epilogue memory/math, 2: no MMA issue)"
+  NINT_DEBUG_FLAGS=$f python bench.py --steps 6 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | python -c "
+import json,sys
+d=json.loads(sys.stdin.read())
+for k,v in d['kernels'].items(): print('  ', k, v['avg_launch_us'])
+"
+done
