@@ -11,8 +11,8 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["nint_api.cu", "nint_conv_gemm.cu", "nint_conv_halo.cu", "nint_wgrad.cu", "nint_pointwise.cu"]
-HEADERS = ["nint_common.cuh", "nint_kernels.h", "nint_epilogue.cuh", os.path.join("..", "..", "include", "nint.h")]
+SOURCES = ["nint_api.cu", "nint_conv_halo.cu", "nint_wgrad.cu", "nint_pointwise.cu"]
+HEADERS = ["nint_common.cuh", "nint_kernels.h", "nint_epilogue.cuh", "nint_pair.cuh", os.path.join("..", "..", "include", "nint.h")]
 LIB = os.path.join(HERE, "libnint.so")
 
 

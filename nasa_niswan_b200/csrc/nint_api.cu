@@ -77,6 +77,8 @@ struct Layer {
   CUtensorMap tm_H, tm_G, tm_wx, tm_wh, tm_wdx, tm_wdh;
   CUtensorMap tm_H_up;       // Hs[l] read as the x segment of layer l+1 (halo of k_{l+1})
   CUtensorMap tmw_H, tmw_G;  // wgrad views (32-channel boxes; differ from tm_* in tf32 mode only)
+  CUtensorMap tmw_H_up;      // Hs[l] as the x part of layer l+1's wgrad (halo of k_{l+1})
+  CUtensorMap tme_C, tme_H, tme_G, tme_dC;  // epilogue I/O boxes (16 | 64 channels x 8 x 16 pixels; nint_epilogue.cuh)
   bool weights_set = false;
 };
 
@@ -97,8 +99,7 @@ struct nint_plan {
   bool zero_init = true;
   bool fwd_done = false;
   int final_slot_h = 0, final_slot_c = 0;
-  int variant = 1;        // 0 = per-tap tiles (nint_conv_gemm.cu), 1 = halo tiles (nint_conv_halo.cu)
-  int cluster = 1;        // CTAs sharing weight stages (halo variant, layers with n_blocks == 1)
+  int cluster = 2;        // 2: CTA pairs (tcgen05 cta_group::2) where the layer geometry allows, 1: single CTAs
   int base_offset_mode = 0;
   int debug_flags = 0;
   Profile prof;
@@ -134,23 +135,12 @@ int launch(nint_plan* p, int cls, cudaStream_t st, const char* what, F&& f) {
 #define LAUNCH(plan, cls, st, call) \
   do { if (launch(plan, cls, st, #call, [&]() { return (call); })) return 1; } while (0)
 
+// the kernels work on 8 x 16 pixel tiles (UMMA M = 128 rows; 8-pixel rows = one 512-byte swizzle atom of the
+// halo buffers); grids that are not multiples are handled by TMA's out-of-bounds fill / clipping
 int pick_tile(int H, int W, int* tw_out, int* th_out) {
-  long best = -1;
-  int btw = 0, bth = 0;
-  for (int tw = 1; tw <= 128 && tw <= W + 0; ++tw) {
-    int th = 128 / tw;
-    if (th > H) th = H;
-    if (th < 1) continue;
-    const long tiles = static_cast<long>((W + tw - 1) / tw) * ((H + th - 1) / th);
-    // fewer tiles first; then wider rows (longer contiguous TMA runs)
-    if (best < 0 || tiles < best || (tiles == best && tw > btw)) {
-      best = tiles;
-      btw = tw;
-      bth = th;
-    }
-  }
-  *tw_out = btw;
-  *th_out = bth;
+  (void)H; (void)W;
+  *tw_out = 8;
+  *th_out = 16;
   return 0;
 }
 
@@ -173,6 +163,30 @@ int encode_act_map(CUtensorMap* m, int dtype, void* base, int C, int W, int H, i
                    dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(activation C=%d W=%d H=%d B=%d slots=%d) -> %d", C, W, H, B, slots, (int)r);
+  return 0;
+}
+
+// epilogue I/O box: `box_c` channels x 8 x 16 pixels of a channels-last tensor with element size `es`;
+// the swizzle span equals the box row (32 / 64 / 128 bytes) so per-pixel 16-byte accesses are conflict free
+int encode_io_map(CUtensorMap* m, bool fp32, void* base, int C, int W, int H, int B, int slots, int box_c) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail("cuTensorMapEncodeTiled not available (no CUDA driver?)");
+  const cuuint64_t es = fp32 ? 4 : 2;
+  cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B, (cuuint64_t)slots};
+  cuuint64_t strides[4] = {C * es, (cuuint64_t)W * C * es, (cuuint64_t)H * W * C * es,
+                           (cuuint64_t)B * H * W * C * es};
+  cuuint32_t box[5] = {(cuuint32_t)box_c, 8, 16, 1, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  const int row_bytes = box_c * (int)es;
+  CUtensorMapSwizzle sw;
+  if (row_bytes == 32) sw = CU_TENSOR_MAP_SWIZZLE_32B;
+  else if (row_bytes == 64) sw = CU_TENSOR_MAP_SWIZZLE_64B;
+  else if (row_bytes == 128) sw = CU_TENSOR_MAP_SWIZZLE_128B;
+  else return fail("encode_io_map: unsupported box row of %d bytes", row_bytes);
+  CUresult r = enc(m, fp32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, dims, strides,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(io C=%d W=%d H=%d B=%d slots=%d box=%d) -> %d", C, W, H, B, slots, box_c, (int)r);
   return 0;
 }
 
@@ -252,6 +266,15 @@ void fill_common(const nint_plan* p, const Layer& y, ConvGemmParams& g) {
   g.hc = y.hc; g.hc_pad = y.hc_pad; g.hcb = y.hcb;
 }
 
+// CTA-pair mode (cluster of 2, tcgen05 cta_group::2; halo variant only): every CTA holds half of the N rows
+// of a weight stage, which must stay a whole number of 8-row swizzle atoms with N a multiple of 32
+int fwd_cluster(const nint_plan* p, int l) {
+  return p->layer[l].n_blocks == 1 ? p->cluster : 1;   // n_tile = 4*hcb: multiple of 64
+}
+int bwd_cluster(const nint_plan* p, int l) {
+  return p->layer[l].hc % 32 == 0 ? p->cluster : 1;    // n_tile = hc
+}
+
 // one fused cell step of layer l at time t (model.py:216-231)
 int cell_step(nint_plan* p, int l, int t, int epi, float* raw_out, cudaStream_t st) {
   Layer& y = p->layer[l];
@@ -260,13 +283,13 @@ int cell_step(nint_plan* p, int l, int t, int epi, float* raw_out, cudaStream_t 
   fill_common(p, y, g);
   g.n_tile = y.n_tile;
   g.n_blocks = y.n_blocks;
-  g.idesc = idesc_of(p->dtype, 128, y.n_tile, 0, 0);
-  g.num_stages = conv_gemm_pick_stages(y.n_tile, y.hc);
+  g.cluster = fwd_cluster(p, l);
+  g.idesc = idesc_of(p->dtype, 128 * g.cluster, y.n_tile, 0, 0);
   const int in_slot_h = tr ? t : (t & 1);
   const int out_slot_h = tr ? t + 1 : ((t + 1) & 1);
   // segment 0: x_t (layer 0) or the h_t of the layer below (model.py:266,271)
   int s = 0;
-  g.seg[s].tmap_act = l == 0 ? p->tm_X : (p->variant == 1 ? p->layer[l - 1].tm_H_up : p->layer[l - 1].tm_H);
+  g.seg[s].tmap_act = l == 0 ? p->tm_X : p->layer[l - 1].tm_H_up;
   g.seg[s].tmap_w = y.tm_wx;
   g.seg[s].slot = l == 0 ? t : (tr ? t + 1 : ((t + 1) & 1));
   g.seg[s].ksize = y.k;
@@ -283,19 +306,16 @@ int cell_step(nint_plan* p, int l, int t, int epi, float* raw_out, cudaStream_t 
   }
   g.nseg = s;
   g.bias_q = y.bias_q;
-  g.c_prev = have_state ? cslot_ptr(p, y, tr ? t : 0) : nullptr;
-  g.c_out = cslot_ptr(p, y, tr ? t + 1 : 0);
-  g.h_out = slot_ptr(p, y.Hs, out_slot_h, y.hc_pad);
-  g.gates_out = tr ? slot_ptr(p, y.G, t, 4 * y.hc) : nullptr;
+  // epilogue I/O (TMA boxes): c_{t-1} -> c_t (in place at inference), h_t, activated gates (training)
+  g.tm_c = y.tme_C; g.tm_h = y.tme_H; g.tm_g = y.tme_G; g.tm_dc = y.tme_dC;
+  g.slot_c_in = have_state ? (tr ? t : 0) : -1;
+  g.slot_c_out = tr ? t + 1 : 0;
+  g.slot_h_out = out_slot_h;
+  g.slot_g = (tr && epi == EPI_FWD) ? t : -1;
   g.raw_out = raw_out;
-  if (p->variant == 1) {
-    g.cluster = y.n_blocks == 1 ? p->cluster : 1;
-    g.base_offset_mode = p->base_offset_mode;
-    conv_halo_plan(g);
-    LAUNCH(p, (epi == EPI_FWD ? K_FWD : K_OTHER), st, launch_conv_halo(epi, p->dtype, g, p->num_sms, st));
-  } else {
-    LAUNCH(p, (epi == EPI_FWD ? K_FWD : K_OTHER), st, launch_conv_gemm(epi, p->dtype, g, p->num_sms, st));
-  }
+  g.base_offset_mode = p->base_offset_mode;
+  if (conv_halo_plan(epi, p->dtype, g)) return fail("layer %d: the conv kernel's shared-memory plan does not fit (hidden %d, k %d)", l, y.hc, y.k);
+  LAUNCH(p, (epi == EPI_FWD ? K_FWD : K_OTHER), st, launch_conv_halo(epi, p->dtype, g, p->num_sms, st));
   return 0;
 }
 
@@ -352,23 +372,16 @@ int nint_plan_create(const nint_config* cfg, nint_plan** out) {
   p->dtype = cfg->dtype;
   p->esize = cfg->dtype == BF16 ? 2 : 4;
   p->ce = 64 / p->esize;
-  {  // debug / A-B knobs (documented in DESIGN.md): kernel variant, cluster size, descriptor base offset
-    const char* v = getenv("NINT_CONV_VARIANT");
-    p->variant = (v && !strcmp(v, "pertap")) ? 0 : 1;
+  {  // debug / A-B knobs (documented in DESIGN.md): CTA pairs on/off, experiment flags
     const char* c = getenv("NINT_CLUSTER");
     p->cluster = c ? atoi(c) : 2;
-    if (p->cluster != 1 && p->cluster != 2 && p->cluster != 4) p->cluster = 1;
+    if (p->cluster != 1 && p->cluster != 2) p->cluster = 1;
     const char* b = getenv("NINT_BASE_OFFSET");
     p->base_offset_mode = b ? atoi(b) : 0;
     const char* d = getenv("NINT_DEBUG_FLAGS");
     p->debug_flags = d ? atoi(d) : 0;
   }
-  if (p->variant == 1) {
-    p->tile_w = 8;
-    p->tile_h = 16;
-  } else {
-    pick_tile(p->H, p->W, &p->tile_w, &p->tile_h);
-  }
+  pick_tile(p->H, p->W, &p->tile_w, &p->tile_h);
   p->tiles_x = (p->W + p->tile_w - 1) / p->tile_w;
   p->tiles_y = (p->H + p->tile_h - 1) / p->tile_h;
   int cin = cfg->in_channels;
@@ -425,24 +438,34 @@ int nint_plan_bind(nint_plan* p, void* workspace, size_t bytes, void* stream) {
   carve(p, p->ws);
   CK(cudaMemsetAsync(p->ws, 0, p->ws_bytes, st));
   const int tw = p->tile_w, th = p->tile_h, ce = p->ce;
-  const bool halo = p->variant == 1;
-  auto pad_of = [&](int l) { return halo ? p->layer[l].k / 2 : 0; };
-  auto cl_fwd = [&](int l) { return (halo && p->layer[l].n_blocks == 1) ? p->cluster : 1; };
-  auto cl_bwd = [&](int l) { return halo ? p->cluster : 1; };
+  auto pad_of = [&](int l) { return p->layer[l].k / 2; };
+  auto cl_fwd = [&](int l) { return fwd_cluster(p, l); };
+  auto cl_bwd = [&](int l) { return bwd_cluster(p, l); };
   if (encode_act_map(&p->tm_X, p->dtype, p->X, p->layer[0].cx_pad, p->W, p->H, p->B, p->T, ce, tw, th, false, pad_of(0))) return 1;
-  if (encode_act_map(&p->tmw_X, p->dtype, p->X, p->layer[0].cx_pad, p->W, p->H, p->B, p->T, ce, tw, th, true)) return 1;
+  if (encode_act_map(&p->tmw_X, p->dtype, p->X, p->layer[0].cx_pad, p->W, p->H, p->B, p->T, ce, tw, th, true, pad_of(0))) return 1;
   for (int l = 0; l < p->L; ++l) {
     Layer& y = p->layer[l];
     if (encode_act_map(&y.tm_H, p->dtype, y.Hs, y.hc_pad, p->W, p->H, p->B, y.nslots_h, ce, tw, th, false, pad_of(l))) return 1;
     if (l + 1 < p->L &&
         encode_act_map(&y.tm_H_up, p->dtype, y.Hs, y.hc_pad, p->W, p->H, p->B, y.nslots_h, ce, tw, th, false, pad_of(l + 1))) return 1;
+    if (encode_io_map(&y.tme_C, true, y.Cs, y.hc, p->W, p->H, p->B, y.nslots_c, 16)) return 1;
+    if (encode_io_map(&y.tme_H, p->dtype == TF32, y.Hs, y.hc_pad, p->W, p->H, p->B, y.nslots_h, 16)) return 1;
+    if (p->cfg.training) {
+      if (encode_io_map(&y.tme_G, p->dtype == TF32, y.G, 4 * y.hc, p->W, p->H, p->B, p->T, 128 / p->esize)) return 1;
+      if (encode_io_map(&y.tme_dC, true, y.dC, y.hc, p->W, p->H, p->B, 1, 16)) return 1;
+    } else {
+      y.tme_G = y.tme_C;   // never dereferenced (slot_g < 0), but the kernel parameter must be a valid map
+      y.tme_dC = y.tme_C;
+    }
     if (encode_w_map(&y.tm_wx, p->dtype, y.wx, (long long)y.n_blocks * y.taps * y.chx * y.n_tile, ce, y.n_tile / cl_fwd(l))) return 1;
     if (encode_w_map(&y.tm_wh, p->dtype, y.wh, (long long)y.n_blocks * y.taps * y.chh * y.n_tile, ce, y.n_tile / cl_fwd(l))) return 1;
     if (p->cfg.training) {
       const int nch = 4 * y.hc / ce;
       if (encode_act_map(&y.tm_G, p->dtype, y.G, 4 * y.hc, p->W, p->H, p->B, p->T, ce, tw, th, false, pad_of(l))) return 1;
       if (encode_act_map(&y.tmw_G, p->dtype, y.G, 4 * y.hc, p->W, p->H, p->B, p->T, ce, tw, th, true)) return 1;
-      if (encode_act_map(&y.tmw_H, p->dtype, y.Hs, y.hc_pad, p->W, p->H, p->B, y.nslots_h, ce, tw, th, true)) return 1;
+      if (encode_act_map(&y.tmw_H, p->dtype, y.Hs, y.hc_pad, p->W, p->H, p->B, y.nslots_h, ce, tw, th, true, pad_of(l))) return 1;
+      if (l + 1 < p->L &&
+          encode_act_map(&y.tmw_H_up, p->dtype, y.Hs, y.hc_pad, p->W, p->H, p->B, y.nslots_h, ce, tw, th, true, pad_of(l + 1))) return 1;
       // dgrad launch of layer l consumes wdh_l (N = hc_l); wdx_l is consumed by the launch of layer l-1 (N = hc_{l-1})
       if (encode_w_map(&y.tm_wdh, p->dtype, y.wdh, (long long)y.taps * nch * y.hc, ce, y.hc / cl_bwd(l))) return 1;
       if (l > 0 && encode_w_map(&y.tm_wdx, p->dtype, y.wdx, (long long)y.taps * nch * y.cin, ce, y.cin / cl_bwd(l - 1))) return 1;
@@ -596,8 +619,8 @@ int nint_backward(nint_plan* p, const float* dpred, const float* dseq, float* co
       fill_common(p, y, g);
       g.n_tile = y.hc;
       g.n_blocks = 1;
-      g.idesc = idesc_of(p->dtype, 128, y.hc, 0, 0);
-      g.num_stages = conv_gemm_pick_stages(y.hc, y.hc);
+      g.cluster = bwd_cluster(p, l);
+      g.idesc = idesc_of(p->dtype, 128 * g.cluster, y.hc, 0, 0);
       int s = 0;
       if (t < T - 1) {  // dh_t += dgates_{t+1} (*) flip(W_h)
         g.seg[s].tmap_act = y.tm_G; g.seg[s].tmap_w = y.tm_wdh; g.seg[s].slot = t + 1;
@@ -611,12 +634,13 @@ int nint_backward(nint_plan* p, const float* dpred, const float* dseq, float* co
         ++s;
       }
       g.nseg = s;
-      g.gates_in = slot_ptr(p, y.G, t, 4 * y.hc);
-      g.dgates_out = slot_ptr(p, y.G, t, 4 * y.hc);
-      g.c_cur = cslot_ptr(p, y, t + 1);
-      g.c_prev_b = (t == 0 && p->zero_init) ? nullptr : cslot_ptr(p, y, t);
-      g.dc_in = (t == T - 1) ? nullptr : y.dC;
-      g.dc_out = y.dC;
+      // epilogue I/O: gates_t -> dgates_t in place, c_t, c_{t-1}, running dc in place
+      g.tm_c = y.tme_C; g.tm_h = y.tme_H; g.tm_g = y.tme_G; g.tm_dc = y.tme_dC;
+      g.slot_g = t;
+      g.slot_c_cur = t + 1;
+      g.slot_c_prev = (t == 0 && p->zero_init) ? -1 : t;
+      g.has_dc_in = (t == T - 1) ? 0 : 1;
+      g.slot_c_in = g.slot_c_out = g.slot_h_out = -1;
       if (l == L - 1) {
         if (dseq) {
           // per-step head gradient; dpred (last step) is folded in by the caller adding it to dseq[:, T-1]
@@ -629,14 +653,9 @@ int nint_backward(nint_plan* p, const float* dpred, const float* dseq, float* co
           g.head_w = p->head_w;
         }
       }
-      if (p->variant == 1) {
-        g.cluster = p->cluster;
-        g.base_offset_mode = p->base_offset_mode;
-        conv_halo_plan(g);
-        LAUNCH(p, K_BWD, st, launch_conv_halo(EPI_BWD, p->dtype, g, p->num_sms, st));
-      } else {
-        LAUNCH(p, K_BWD, st, launch_conv_gemm(EPI_BWD, p->dtype, g, p->num_sms, st));
-      }
+      g.base_offset_mode = p->base_offset_mode;
+      if (conv_halo_plan(EPI_BWD, p->dtype, g)) return fail("layer %d: the dgrad kernel's shared-memory plan does not fit (hidden %d, k %d)", l, y.hc, y.k);
+      LAUNCH(p, K_BWD, st, launch_conv_halo(EPI_BWD, p->dtype, g, p->num_sms, st));
     }
   }
   // ---- weight / bias gradients, batched over all T steps
@@ -647,7 +666,10 @@ int nint_backward(nint_plan* p, const float* dpred, const float* dseq, float* co
     WgradParams w;
     memset(&w, 0, sizeof(w));
     w.tmap_dg = y.tmw_G;
-    w.tmap_b[0] = l == 0 ? p->tmw_X : p->layer[l - 1].tmw_H;
+    w.tmap_b[0] = l == 0 ? p->tmw_X : p->layer[l - 1].tmw_H_up;
+    w.halo = 1;
+    w.debug_flags = p->debug_flags;
+    w.b_panel_bytes = wgrad_b_panel_bytes(p->dtype, w.halo, y.k);
     w.tmap_b[1] = y.tmw_H;
     w.slot_b0[0] = l == 0 ? 0 : 1;
     w.slot_b0[1] = 0;
@@ -677,7 +699,7 @@ int nint_backward(nint_plan* p, const float* dpred, const float* dseq, float* co
     if (splits < 1) splits = 1;
     if (splits > total_tiles) splits = static_cast<int>(total_tiles);
     w.splits = splits;
-    wgrad_pick_buffers(p->dtype, y.ncols / 32, &w.a_bufs, &w.b_stages);
+    wgrad_pick_buffers(p->dtype, y.ncols / 32, w.b_panel_bytes, &w.a_bufs, &w.b_stages);
     if (w.b_stages < 1) return fail("wgrad: operand panels do not fit in shared memory");
     w.idesc = idesc_of(p->dtype, 128, y.ncols, 1, 1);
     w.idesc_bias = idesc_of(p->dtype, 128, 32, 1, 1);

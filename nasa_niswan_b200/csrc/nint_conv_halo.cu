@@ -6,16 +6,23 @@
 // For tap (dy, dx) the UMMA A operand is the same buffer seen through a shifted descriptor: start
 // address + (dy*(8+2p) + dx) * 64 bytes, 8-row groups (one tile row of 8 pixels) strided by
 // SBO = (8+2p) * 64 bytes.  TMA's SWIZZLE_64B and the UMMA SW64 layout both derive the 16-byte
-// chunk permutation from shared-memory address bits [7,9), so a row-shifted view stays consistent.
-// L2 -> SM traffic per tile drops from taps x 8 KiB to one (8+2p)(16+2p) x 64 B halo per chunk
-// (k=3: 72 -> 11.25 KiB): the dgrad conv (N = hc = 64) was bound by exactly this traffic.
+// chunk permutation from shared-memory address bits [7,9) (verified on hardware: the descriptor
+// base-offset field must stay 0), so a row-shifted view stays consistent.
 //
-// Optional thread-block cluster (2 or 4 CTAs, n_blocks == 1): the CTAs of a cluster walk different
-// pixel tiles in lockstep and share every weight stage -- CTA r loads rows [r*n_tile/S, (r+1)*n_tile/S)
-// and TMA-multicasts them to all S CTAs; a stage is recycled when the MMA warps of all S CTAs have
-// released it (tcgen05.commit multicast onto every CTA's "empty" barrier).
+// CTA pair (cluster of 2, tcgen05 cta_group::2): measured on B200 (tools/micro/mma_rate*.cu) a
+// single-CTA M=128 MMA costs 171 / 110 / 88 cycles at N = 256 / 128 / 64 -- a ~60-cycle fixed cost
+// per instruction -- while the pair MMA (M=256: 128 pixels from each CTA) runs at the nominal floor
+// (128 / 64 / 43 cycles for BOTH SMs).  In pair mode the two CTAs walk different pixel tiles in
+// lockstep; each loads its own halo tiles and HALF of every weight stage (rows [r*N/2, (r+1)*N/2)),
+// which also halves the weight bytes every SM has to ingest.  The leader CTA (rank 0) issues the MMAs;
+// "full" barriers live in the leader (both CTAs' TMA loads complete_tx on them), "empty"/accumulator
+// barriers are signalled in both CTAs by multicast tcgen05.commit.
 //
-// Warp roles as in nint_conv_gemm.cu (warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warps 4-11 epilogue).
+// Item groups: G consecutive tiles (G * n_tile <= 256 columns) are accumulated side by side in one
+// TMEM buffer and share every weight stage.
+//
+// Warp roles: warp 0 operand TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator + epilogue TMA stores,
+// warp 3 epilogue TMA loads, warps 4-11 epilogue math (nint_epilogue.cuh).
 #include "nint_epilogue.cuh"
 
 namespace nint {
@@ -34,36 +41,19 @@ static inline int halo_a_buf_bytes(const ConvGemmParams& p) {
   return (m + 1023) & ~1023;
 }
 
-int conv_halo_smem_bytes(int a_buf_bytes, int na, int n_tile, int nw, int ts, int hc) {
-  return 1024 + na * a_buf_bytes + nw * ts * n_tile * kChunkBytes + kHaloCtrlBytes + (4 * hc + hc) * 4;
+static int halo_operand_bytes(int a_buf_bytes, int na, int n_tile, int nw, int ts, int cluster) {
+  return (na * a_buf_bytes + nw * ts * (n_tile / cluster) * kChunkBytes + 1023) & ~1023;
+}
+int conv_halo_smem_bytes(const ConvGemmParams& p) {
+  return 1024 + halo_operand_bytes(p.a_buf_bytes, p.na_bufs, p.n_tile, p.num_stages, p.taps_per_stage, p.cluster) +
+         p.e_stages * p.e_stage_bytes + kHaloCtrlBytes + (4 * p.hc + p.hc) * 4;
 }
 
-// cluster helpers
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tma_load_2d_mcast(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0,
-                                                  int c1, uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster"
-      " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(smem_dst)),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit_mcast(uint64_t* bar, uint16_t mask) {
-  asm volatile(
-      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-          smem_u32(bar)),
-      "h"(mask)
-      : "memory");
+__device__ __forceinline__ int halo_operand_bytes_dev(int a_buf_bytes, int na, int stage_bytes, int nw) {
+  return (na * a_buf_bytes + nw * stage_bytes + 1023) & ~1023;
 }
 
-template <typename E, int EPI>
+template <typename E, int EPI, bool PAIR>
 __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid_constant__ ConvGemmParams p) {
   constexpr int DT = ElemTraits<E>::kDtype;
   constexpr int CE = ElemTraits<E>::kPerChunk;
@@ -71,28 +61,34 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  constexpr int S = PAIR ? 2 : 1;               // 1: single CTA, 2: CTA pair (cta_group::2)
+  constexpr bool pair = PAIR;
   const int NA = p.na_bufs, NW = p.num_stages, TS = p.taps_per_stage;
-  const int w_bytes = p.n_tile * kChunkBytes;   // one tap of one chunk
+  const int w_rows = p.n_tile / S;              // weight rows (of N) this CTA holds
+  const int w_bytes = w_rows * kChunkBytes;     // one tap of one chunk, this CTA's share
   const int stage_bytes = TS * w_bytes;         // a weight stage holds up to TS consecutive taps
   uint8_t* sA = smem;
   uint8_t* sW = sA + NA * p.a_buf_bytes;
-  uint8_t* ctrl = sW + NW * stage_bytes;
+  uint8_t* sE = smem + halo_operand_bytes_dev(p.a_buf_bytes, NA, stage_bytes, NW);   // epilogue I/O stages
+  uint8_t* ctrl = sE + p.e_stages * p.e_stage_bytes;
   uint64_t* a_full = reinterpret_cast<uint64_t*>(ctrl);
   uint64_t* a_empty = a_full + kHaloMaxA;
   uint64_t* w_full = a_empty + kHaloMaxA;
   uint64_t* w_empty = w_full + kHaloMaxW;
   uint64_t* tfull_bar = w_empty + kHaloMaxW;
   uint64_t* tempty_bar = tfull_bar + 2;
+  uint64_t* e_full = tempty_bar + 2;
+  uint64_t* e_empty = e_full + kEpiMaxStages;
+  uint64_t* st_ready = e_empty + kEpiMaxStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ctrl + kHaloCtrlBytes - 16);
   float* s_bias = reinterpret_cast<float*>(ctrl + kHaloCtrlBytes);
   float* s_headw = s_bias + 4 * p.hc;
 
-  const int S = p.cluster;
-  const uint32_t crank = S > 1 ? cluster_ctarank() : 0;
-  const uint16_t cmask = static_cast<uint16_t>((1u << S) - 1);
+  uint32_t crank = 0;
+  if constexpr (pair) crank = cluster_ctarank();
+  const bool lead_cta = crank == 0;
   // work unit of a CTA iteration = G consecutive tiles ("item group") accumulated side by side in one
-  // TMEM buffer (independent accumulators: back-to-back MMAs into ONE accumulator serialise on the
-  // ~190-cycle accumulate latency when N is small) and sharing every weight stage
+  // TMEM buffer and sharing every weight stage; the two CTAs of a pair take adjacent groups
   const int G = p.group;
   const int num_items = p.n_blocks * p.B * p.tiles_x * p.tiles_y;
   const int groups = (num_items + S * G - 1) / (S * G);
@@ -108,6 +104,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
       prefetch_tensormap(&p.seg[s].tmap_w);
     }
   }
+  if (warp == 3 && lane == 0 && EPI != EPI_RAW) {
+    prefetch_tensormap(&p.tm_c);
+    prefetch_tensormap(&p.tm_g);
+    prefetch_tensormap(EPI == EPI_FWD ? &p.tm_h : &p.tm_dc);
+  }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < NA; ++s) {
       mbar_init(&a_full[s], 1);
@@ -115,17 +116,26 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
     }
     for (int s = 0; s < NW; ++s) {
       mbar_init(&w_full[s], 1);
-      mbar_init(&w_empty[s], S);   // one release per CTA of the cluster
+      mbar_init(&w_empty[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 8);
+      mbar_init(&tempty_bar[s], 8 * S);   // the leader waits for the epilogue warps of both CTAs
+    }
+    for (int s = 0; s < kEpiMaxStages; ++s) {
+      mbar_init(&e_full[s], 1);
+      mbar_init(&e_empty[s], 1);
+      mbar_init(&st_ready[s], 8);         // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, kTmemCols);
-    tmem_relinquish();
+    if constexpr (pair) {
+      tmem_alloc_pair(tmem_slot, kTmemCols);
+    } else {
+      tmem_alloc(tmem_slot, kTmemCols);
+      tmem_relinquish();
+    }
   }
   if (EPI == EPI_FWD) {
     for (int i = threadIdx.x; i < 4 * p.hc; i += kConvThreads) s_bias[i] = p.bias_q ? p.bias_q[i] : 0.f;
@@ -135,19 +145,18 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
   }
   tc_fence_before();
   __syncthreads();
-  if (S > 1) cluster_sync_all();   // peers' barriers are initialised before anyone signals them
+  if constexpr (pair) cluster_sync_all();   // the peer's barriers are initialised before anyone signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
     if (p.nseg > 0) {
       const bool leader = elect_one();
       int ia = 0, iw = 0;
       uint32_t pa = 0, pw = 0;
-      const int w_rows = p.n_tile / S;   // rows of every weight stage this CTA fetches (and multicasts)
       for (int item = first_item; item < items_padded; item += item_stride) {
-        const ItemCoord c = decode_item(p, item);   // nb is shared by the group (G > 1 only when n_blocks == 1)
+        const ItemCoord c = decode_item(p, item);   // nb is shared by the group and the pair
         for (int s = 0; s < p.nseg; ++s) {
           const ConvSegment& sg = p.seg[s];
           const int pad = sg.ksize >> 1;
@@ -157,11 +166,17 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
           for (int ch = 0; ch < sg.nchunks; ++ch) {
             mbar_wait(&a_empty[ia], pa ^ 1);
             if (leader) {
-              mbar_arrive_expect_tx(&a_full[ia], a_bytes * G);
+              // "full" barriers live in the leader CTA and count the bytes of both CTAs' loads
+              if (lead_cta) mbar_arrive_expect_tx(&a_full[ia], a_bytes * G * S);
+              uint32_t bar = 0;
+              if constexpr (pair) bar = mapa_rank(smem_u32(&a_full[ia]), 0);
               for (int g = 0; g < G; ++g) {
                 const ItemCoord cg = decode_item(p, item + g);
-                tma_load_5d(sA + ia * p.a_buf_bytes + g * p.a_halo_bytes, &sg.tmap_act, &a_full[ia], ch * CE,
-                            cg.x0 - pad, cg.y0 - pad, cg.b, sg.slot);
+                uint8_t* dst = sA + ia * p.a_buf_bytes + g * p.a_halo_bytes;
+                if constexpr (pair)
+                  tma_load_5d_pair(dst, &sg.tmap_act, bar, ch * CE, cg.x0 - pad, cg.y0 - pad, cg.b, sg.slot);
+                else
+                  tma_load_5d(dst, &sg.tmap_act, &a_full[ia], ch * CE, cg.x0 - pad, cg.y0 - pad, cg.b, sg.slot);
               }
             }
             if (++ia == NA) {
@@ -171,16 +186,19 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
             for (int tap0 = 0; tap0 < taps; tap0 += TS) {
               const int nt = (taps - tap0) < TS ? (taps - tap0) : TS;   // taps in this weight stage
               mbar_wait(&w_empty[iw], pw ^ 1);
-              if (leader) mbar_arrive_expect_tx(&w_full[iw], static_cast<uint32_t>(nt * w_bytes));
-              uint8_t* dst = sW + iw * stage_bytes + static_cast<int>(crank) * w_rows * kChunkBytes;
-              for (int j = 0; j < nt; ++j, dst += w_bytes, wrow += p.n_tile) {
-                if (leader) {
-                  if (S > 1)
-                    tma_load_2d_mcast(dst, &sg.tmap_w, &w_full[iw], 0, wrow, cmask);
+              if (leader) {
+                if (lead_cta) mbar_arrive_expect_tx(&w_full[iw], static_cast<uint32_t>(nt * w_bytes * S));
+                uint32_t bar = 0;
+                if constexpr (pair) bar = mapa_rank(smem_u32(&w_full[iw]), 0);
+                uint8_t* dst = sW + iw * stage_bytes;
+                for (int j = 0; j < nt; ++j, dst += w_bytes) {
+                  if constexpr (pair)
+                    tma_load_2d_pair(dst, &sg.tmap_w, bar, 0, wrow + j * p.n_tile);
                   else
-                    tma_load_2d(dst, &sg.tmap_w, &w_full[iw], 0, wrow);
+                    tma_load_2d(dst, &sg.tmap_w, &w_full[iw], 0, wrow + j * p.n_tile);
                 }
               }
+              wrow += nt * p.n_tile;
               if (++iw == NW) {
                 iw = 0;
                 pw ^= 1;
@@ -191,8 +209,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (p.nseg > 0) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (p.nseg > 0 && lead_cta) {
       const bool leader = elect_one();
       int ia = 0, iw = 0;
       uint32_t pa = 0, pw = 0;
@@ -225,8 +243,13 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
                 uint64_t adesc = adesc0 + static_cast<uint64_t>((dy * hw + dx) * (kChunkBytes >> 4));
                 if (leader && !(p.debug_flags & 2)) {
                   for (int g = 0; g < G; ++g, adesc += static_cast<uint64_t>(p.a_halo_bytes >> 4)) {
-                    umma<DT>(d_tmem + g * p.n_tile, adesc, bdesc, p.idesc, accumulate);
-                    umma<DT>(d_tmem + g * p.n_tile, adesc + 2, bdesc + 2, p.idesc, 1u);
+                    if constexpr (pair) {
+                      umma_pair<DT>(d_tmem + g * p.n_tile, adesc, bdesc, p.idesc, accumulate);
+                      umma_pair<DT>(d_tmem + g * p.n_tile, adesc + 2, bdesc + 2, p.idesc, 1u);
+                    } else {
+                      umma<DT>(d_tmem + g * p.n_tile, adesc, bdesc, p.idesc, accumulate);
+                      umma<DT>(d_tmem + g * p.n_tile, adesc + 2, bdesc + 2, p.idesc, 1u);
+                    }
                   }
                 }
                 accumulate = 1;
@@ -236,65 +259,112 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
                 }
               }
               if (leader) {
-                if (S > 1)
-                  umma_commit_mcast(&w_empty[iw], cmask);
-                else
-                  umma_commit(&w_empty[iw]);
+                if constexpr (pair) umma_commit_pair(&w_empty[iw]); else umma_commit(&w_empty[iw]);
               }
               if (++iw == NW) {
                 iw = 0;
                 pw ^= 1;
               }
             }
-            if (leader) umma_commit(&a_empty[ia]);
+            if (leader) {
+              if constexpr (pair) umma_commit_pair(&a_empty[ia]); else umma_commit(&a_empty[ia]);
+            }
             if (++ia == NA) {
               ia = 0;
               pa ^= 1;
             }
           }
         }
-        if (leader) umma_commit(&tfull_bar[abuf]);
+        if (leader) {
+          if constexpr (pair) umma_commit_pair(&tfull_bar[abuf]); else umma_commit(&tfull_bar[abuf]);
+        }
         if (++abuf == 2) {
           abuf = 0;
           aphase ^= 1;
         }
       }
     }
-  } else if (warp >= 4) {
-    conv_epilogue_loop<E, EPI>(p, warp, lane, tmem_base, tfull_bar, tempty_bar, s_bias, s_headw, first_item,
-                               item_stride, items_padded, G);
+  } else if (warp == 2) {
+    // ------------------------------------------------------------------ epilogue TMA stores
+    if constexpr (EPI != EPI_RAW) epi_storer<E, EPI>(p, sE, st_ready, e_empty, first_item, item_stride, items_padded, G);
+  } else if (warp == 3) {
+    // ------------------------------------------------------------------ epilogue TMA loads
+    if constexpr (EPI != EPI_RAW) epi_loader<E, EPI>(p, sE, e_full, e_empty, first_item, item_stride, items_padded, G);
+  } else {
+    // ------------------------------------------------------------------ epilogue math (warps 4-11)
+    // the epilogue of either CTA releases the accumulator buffer on the LEADER's "tmem empty" barrier
+    uint32_t tempty_remote = 0;
+    if constexpr (pair) tempty_remote = mapa_rank(smem_u32(&tempty_bar[0]), 0);
+    if constexpr (EPI == EPI_RAW)
+      epi_raw(p, warp, lane, tmem_base, tfull_bar, tempty_bar, first_item, item_stride, items_padded, G, tempty_remote);
+    else
+      epi_math<E, EPI>(p, warp, lane, tmem_base, sE, e_full, st_ready, tfull_bar, tempty_bar, s_bias, s_headw,
+                       first_item, item_stride, items_padded, G, tempty_remote);
   }
   tc_fence_before();
   __syncthreads();
-  if (S > 1) cluster_sync_all();   // no CTA may exit while a peer can still multicast into it
+  if constexpr (pair) cluster_sync_all();   // no CTA may exit (or free TMEM) while its peer still uses the pair's resources
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if constexpr (pair) tmem_dealloc_pair(tmem_base, kTmemCols); else tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
-// smem plan: as many weight stages as fit after NA halo buffers
-void conv_halo_plan(ConvGemmParams& p) {
+// shared-memory plan: epilogue I/O stages, tiles per group, taps per weight stage, stage / halo-buffer counts
+int conv_halo_plan(int epi, int dtype, ConvGemmParams& p) {
+  const int esize = dtype == NINT_BF16 ? 2 : 4;
+  // ---- epilogue stage layout (nint_epilogue.cuh): [gates][c / c_t][c_{t-1}][dc] or [gates][c][h]
+  const int gate_bytes = kTilePixels * 64 * esize;
+  if (epi == EPI_FWD) {
+    const int g = p.slot_g >= 0 ? gate_bytes : 0;
+    p.e_off_c = g;
+    p.e_off_h = g + kEpiBoxBytes16;
+    p.e_off_c2 = p.e_off_dc = 0;
+    p.e_stage_bytes = (p.e_off_h + kTilePixels * 16 * esize + 1023) & ~1023;
+  } else if (epi == EPI_BWD) {
+    p.e_off_c = gate_bytes;
+    p.e_off_c2 = p.e_off_c + kEpiBoxBytes16;
+    p.e_off_dc = p.e_off_c2 + kEpiBoxBytes16;
+    p.e_off_h = 0;
+    p.e_stage_bytes = p.e_off_dc + kEpiBoxBytes16;
+  } else {
+    p.e_off_c = p.e_off_c2 = p.e_off_dc = p.e_off_h = 0;
+    p.e_stage_bytes = 0;
+  }
   p.a_halo_bytes = halo_a_buf_bytes(p);
   if (p.a_halo_bytes == 0) p.a_halo_bytes = 1024;
-  // tiles per item group: fill one 256-column accumulator buffer, at most 4
-  int G = 256 / p.n_tile;
-  if (G > 4) G = 4;
-  if (G < 1 || p.n_blocks != 1 || p.nseg == 0) G = 1;
-  p.group = G;
-  p.a_buf_bytes = G * p.a_halo_bytes;
-  const int budget = 227 * 1024 - 1024 - kHaloCtrlBytes - (4 * p.hc + p.hc) * 4;
-  const int w_bytes = p.n_tile * kChunkBytes;
-  // (a) the single MMA-issuing thread pays ~300 cycles per barrier round trip: group taps so that one
-  //     weight stage carries >= ~1.5k cycles of tensor work (2 MMAs of n_tile/2 cycles per tap);
-  // (b) a halo chunk takes ~1.5 us to arrive (180+ scattered 64-byte rows) but only taps*n_tile cycles
-  //     to consume: keep 3 weight stages and spend the rest of shared memory on halo buffers.
+  const int total = 227 * 1024 - 1024 - kHaloCtrlBytes - (4 * p.hc + p.hc) * 4 - 1024;
+  const int w_bytes = (p.n_tile / p.cluster) * kChunkBytes;
   int max_k = 1;
   for (int s = 0; s < p.nseg; ++s) if (p.seg[s].ksize > max_k) max_k = p.seg[s].ksize;
+  // tiles per item group: fill one 256-column accumulator buffer, at most 4 (2 for the memory-bound backward
+  // epilogue, whose stages need the shared memory more than the weight stages need the reuse)
+  int gmax = 256 / p.n_tile;
+  if (gmax > (epi == EPI_BWD ? 2 : 4)) gmax = (epi == EPI_BWD ? 2 : 4);
+  if (gmax < 1 || p.n_blocks != 1 || p.nseg == 0) gmax = 1;
+  // three epilogue stages keep loads, math and stores of consecutive channel groups overlapped; fall back
+  // to two when the operands would not get 2 halo buffers + 3 single-tap weight stages otherwise
+  const int ns_max = epi == EPI_RAW ? 0 : 3, ns_min = epi == EPI_RAW ? 0 : 2;
+  int NS = -1, G = 1;
+  for (int ns = ns_max; ns >= ns_min && NS < 0; --ns)
+    for (int g = gmax; g >= 1; --g)
+      if (total - ns * p.e_stage_bytes >= 2 * g * p.a_halo_bytes + 3 * w_bytes) {
+        NS = ns;
+        G = g;
+        break;
+      }
+  if (NS < 0) return 1;
+  p.e_stages = NS;
+  p.group = G;
+  p.a_buf_bytes = G * p.a_halo_bytes;
+  const int budget = total - NS * p.e_stage_bytes;
+  // every barrier round trip of the MMA-issuing thread costs a few hundred cycles: group taps so that
+  // one weight stage carries plenty of tensor work, keep >= 3 weight stages in flight and spend the rest
+  // of shared memory on halo buffers (a halo chunk is 180+ scattered 64-byte rows: ~1.5 us to arrive)
   int want = (1536 + p.n_tile - 1) / p.n_tile;
   if (want > max_k * max_k) want = max_k * max_k;
   int ts = 1;
-  for (int cand = want; cand >= 1; --cand) {   // largest group that leaves room for 3 stages + 3 halo buffers and divides every tap count
+  for (int cand = want; cand >= 1; --cand) {   // largest tap group that leaves room for 3 stages + 2 halo buffers and divides every tap count
     if (budget - 3 * cand * w_bytes < 2 * p.a_buf_bytes) continue;
     bool divides = true;
     for (int s = 0; s < p.nseg; ++s) divides = divides && ((p.seg[s].ksize * p.seg[s].ksize) % cand == 0);
@@ -302,25 +372,28 @@ void conv_halo_plan(ConvGemmParams& p) {
   }
   int nw = 3;
   int na = (budget - nw * ts * w_bytes) / p.a_buf_bytes;
-  if (na > kHaloMaxA) na = kHaloMaxA;
+  if (na > 6) na = 6;
   if (na < 1) na = 1;
   nw = (budget - na * p.a_buf_bytes) / (ts * w_bytes);
   if (nw > kHaloMaxW) nw = kHaloMaxW;
+  if (nw < 1) return 1;
   p.na_bufs = na;
   p.taps_per_stage = ts;
   p.num_stages = nw;
+  return 0;
 }
 
-template <typename E, int EPI>
+template <typename E, int EPI, bool PAIR>
 static cudaError_t launch_h(const ConvGemmParams& p, int num_sms, cudaStream_t stream) {
-  const int smem = conv_halo_smem_bytes(p.a_buf_bytes, p.na_bufs, p.n_tile, p.num_stages, p.taps_per_stage, p.hc);
+  const int smem = conv_halo_smem_bytes(p);
+  if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<E, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<E, EPI, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  const int S = p.cluster;
+  constexpr int S = PAIR ? 2 : 1;
   const int items = p.n_blocks * p.B * p.tiles_x * p.tiles_y;
   const int groups = (items + S * p.group - 1) / (S * p.group);
   int clusters = num_sms / S;
@@ -337,21 +410,26 @@ static cudaError_t launch_h(const ConvGemmParams& p, int num_sms, cudaStream_t s
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, conv_halo_kernel<E, EPI>, p);
+  cfg.numAttrs = PAIR ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, conv_halo_kernel<E, EPI, PAIR>, p);
+}
+
+template <typename E, bool PAIR>
+static cudaError_t launch_e(int epi, const ConvGemmParams& p, int num_sms, cudaStream_t stream) {
+  if (epi == EPI_FWD) return launch_h<E, EPI_FWD, PAIR>(p, num_sms, stream);
+  if (epi == EPI_BWD) return launch_h<E, EPI_BWD, PAIR>(p, num_sms, stream);
+  return launch_h<E, EPI_RAW, PAIR>(p, num_sms, stream);
 }
 
 cudaError_t launch_conv_halo(int epi, int dtype, const ConvGemmParams& p, int num_sms, cudaStream_t stream) {
   if (p.tile_w != 8 || p.tile_h != 16) return cudaErrorInvalidValue;
-  if (p.cluster < 1 || (p.n_tile % p.cluster) || (p.cluster > 1 && p.n_blocks != 1)) return cudaErrorInvalidValue;
-  if (dtype == NINT_BF16) {
-    if (epi == EPI_FWD) return launch_h<__nv_bfloat16, EPI_FWD>(p, num_sms, stream);
-    if (epi == EPI_BWD) return launch_h<__nv_bfloat16, EPI_BWD>(p, num_sms, stream);
-    return launch_h<__nv_bfloat16, EPI_RAW>(p, num_sms, stream);
-  }
-  if (epi == EPI_FWD) return launch_h<float, EPI_FWD>(p, num_sms, stream);
-  if (epi == EPI_BWD) return launch_h<float, EPI_BWD>(p, num_sms, stream);
-  return launch_h<float, EPI_RAW>(p, num_sms, stream);
+  if (p.cluster != 1 && p.cluster != 2) return cudaErrorInvalidValue;
+  if (p.cluster == 2 && ((p.n_tile % 32) || p.n_blocks != 1)) return cudaErrorInvalidValue;
+  if (epi != EPI_RAW && (p.e_stages < 2 || p.e_stages > kEpiMaxStages)) return cudaErrorInvalidValue;
+  if (dtype == NINT_BF16)
+    return p.cluster == 2 ? launch_e<__nv_bfloat16, true>(epi, p, num_sms, stream)
+                          : launch_e<__nv_bfloat16, false>(epi, p, num_sms, stream);
+  return p.cluster == 2 ? launch_e<float, true>(epi, p, num_sms, stream) : launch_e<float, false>(epi, p, num_sms, stream);
 }
 
 }  // namespace nint

@@ -1,12 +1,25 @@
-// Epilogue shared by the implicit-GEMM convolution kernels: TMEM accumulator -> fused ConvLSTM
-// pointwise math -> global memory.  Included by nint_conv_gemm.cu and nint_conv_halo.cu.
+// Epilogue of the implicit-GEMM gate convolution: TMEM accumulator -> fused ConvLSTM pointwise math, with
+// every global-memory operand of the pointwise math staged through shared memory by TMA.
+//
+// Why staged: with one thread per pixel (the TMEM lane layout) a warp-wide global access touches 32
+// different cache lines; ncu showed the direct version latency-bound on L1 miss tracking at ~35 % of HBM
+// bandwidth (profiles/r1b).  Here a loader warp prefetches, per (pixel tile, 16-channel group), the boxes
+// the math needs ([16 | 64 channels] x 8 x 16 pixels, swizzled so that the per-pixel 16-byte accesses of
+// the epilogue threads are bank-conflict free), the 8 epilogue warps compute in place, and a storer warp
+// writes the result boxes back with TMA stores.  TMA's out-of-image handling (zero fill on load, clipping
+// on store) replaces every bounds check.
+//
+//   loader (warp 3)  --e_full[s]-->  epilogue (warps 4-11)  --st_ready[s]-->  storer (warp 2)  --e_empty[s]--> loader
 #pragma once
 #include "nint_common.cuh"
 #include "nint_kernels.h"
+#include "nint_pair.cuh"
 
 namespace nint {
 
-constexpr int kConvThreads = 384;   // warps 0-3: producer / MMA / TMEM alloc / spare; warps 4-11: epilogue
+constexpr int kConvThreads = 384;   // warp 0 operand TMA, 1 MMA, 2 TMEM alloc + epilogue stores, 3 epilogue loads, 4-11 epilogue
+constexpr int kEpiMaxStages = 4;
+constexpr int kEpiBoxBytes16 = kTilePixels * 16 * 4;   // 16 fp32 channels x 128 pixels = 8 KiB
 
 struct ItemCoord {
   int nb, b, x0, y0;
@@ -24,197 +37,428 @@ __device__ __forceinline__ ItemCoord decode_item(const ConvGemmParams& p, int it
   return c;
 }
 
+// shared-memory address of 16-byte chunk `chunk` of pixel row `row` inside a TMA box with ROWB-byte rows
+// (ROWB = 32 / 64 / 128 <-> SWIZZLE_32B / 64B / 128B: address bits [4,4+n) ^= bits [7,7+n)); base 1024-aligned
+template <int ROWB>
+__device__ __forceinline__ uint32_t swz(uint32_t base, int row, int chunk) {
+  const uint32_t off = static_cast<uint32_t>(row * ROWB + chunk * 16);
+  constexpr uint32_t mask = ROWB / 16 - 1;
+  return base + (off ^ (((off >> 7) & mask) << 4));
+}
+__device__ __forceinline__ void sts128(uint32_t saddr, const float* v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+}
+__device__ __forceinline__ void lds128u(uint32_t saddr, uint32_t* v) {
+  asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(saddr));
+}
+__device__ __forceinline__ void sts128u(uint32_t saddr, const uint32_t* v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
+}
+// 8 consecutive fp32 columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+// 5-D TMA store shared -> global (bulk async-group completion)
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2,
+                                             int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
-// Runs on warps 4..11 of a CTA.  `tfull_bar` / `tempty_bar`: MMA <-> epilogue handshake of the two
-// TMEM accumulator buffers (tempty expects one arrive per epilogue warp = 8).
+// 8 channels of element type E at a swizzled row <-> 8 fp32 registers.  bf16: one 16-byte chunk of a row with
+// ROWB bytes; fp32: two chunks.  `ec` = index of the 8-channel slice inside the row.
+template <typename E, int ROWB>
+__device__ __forceinline__ void lds8(uint32_t base, int row, int ec, float* v) {
+  if constexpr (sizeof(E) == 2) {
+    uint32_t u[4];
+    lds128u(swz<ROWB>(base, row, ec), u);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) unpack_bf16x2(u[j], v[2 * j], v[2 * j + 1]);
+  } else {
+    lds128(swz<ROWB>(base, row, 2 * ec), v);
+    lds128(swz<ROWB>(base, row, 2 * ec + 1), v + 4);
+  }
+}
+template <typename E, int ROWB>
+__device__ __forceinline__ void sts8(uint32_t base, int row, int ec, const float* v) {
+  if constexpr (sizeof(E) == 2) {
+    uint32_t u[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) u[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+    sts128u(swz<ROWB>(base, row, ec), u);
+  } else {
+    sts128(swz<ROWB>(base, row, 2 * ec), v);
+    sts128(swz<ROWB>(base, row, 2 * ec + 1), v + 4);
+  }
+}
+
+// Geometry of one epilogue stage (one 16-channel group of one pixel tile), shared by the three roles.
+//   gates : 64 q-columns (4 gates x 16 channels, contiguous in q-order) of E -> 128-byte rows, 1 (bf16) or 2 (fp32) boxes
+//   fp32 state boxes (c, dc) : 16 channels -> 64-byte rows;   h : 16 channels of E -> 32- (bf16) or 64-byte rows
+template <typename E>
+struct EpiGeom {
+  static constexpr int kGateBoxes = (64 * sizeof(E)) / 128;           // 1 / 2
+  static constexpr int kGateBoxCols = 128 / sizeof(E);                // q columns per gates box: 64 / 32
+  static constexpr int kGateBoxBytes = kTilePixels * 128;             // 16 KiB
+  static constexpr int kGateBytes = kGateBoxes * kGateBoxBytes;
+  static constexpr int kHRowB = 16 * sizeof(E);                       // 32 / 64
+  static constexpr int kHBytes = kTilePixels * kHRowB;
+};
+
+// gate g (0..3 = i,f,g,o) of the 8-channel half `half` inside the staged gates box(es)
+template <typename E>
+__device__ __forceinline__ void lds_gate(uint32_t st, int row, int g, int half, float* v) {
+  if constexpr (sizeof(E) == 2) lds8<E, 128>(st, row, g * 2 + half, v);
+  else lds8<E, 128>(st + (g >> 1) * EpiGeom<E>::kGateBoxBytes, row, (g & 1) * 2 + half, v);
+}
+template <typename E>
+__device__ __forceinline__ void sts_gate(uint32_t st, int row, int g, int half, const float* v) {
+  if constexpr (sizeof(E) == 2) sts8<E, 128>(st, row, g * 2 + half, v);
+  else sts8<E, 128>(st + (g >> 1) * EpiGeom<E>::kGateBoxBytes, row, (g & 1) * 2 + half, v);
+}
+
+// first q-column of the 16-channel group containing hidden channel `ch` (multiple of 16)
+__device__ __forceinline__ int group_q0(int ch, int hcb) {
+  const int nb = ch / hcb, cc = ch - nb * hcb;
+  return nb * 4 * hcb + (cc >> 4) * 64;
+}
+
+template <int EPI>
+__device__ __forceinline__ int epi_groups(const ConvGemmParams& p) {
+  return (EPI == EPI_FWD ? p.hcb : p.hc) >> 4;
+}
+
+// ------------------------------------------------------------------------------------ loader (warp 3)
 template <typename E, int EPI>
-__device__ __forceinline__ void conv_epilogue_loop(const ConvGemmParams& p, int warp, int lane, uint32_t tmem_base,
-                                                   uint64_t* tfull_bar, uint64_t* tempty_bar, const float* s_bias,
-                                                   const float* s_headw, int first_item, int item_stride,
-                                                   int num_items_padded, int G = 1) {
+__device__ __forceinline__ void epi_loader(const ConvGemmParams& p, uint8_t* sE, uint64_t* e_full, uint64_t* e_empty,
+                                           int first_item, int item_stride, int items_padded, int G) {
+  using GE = EpiGeom<E>;
+  const bool leader = elect_one();
+  const int num_items = p.n_blocks * p.B * p.tiles_x * p.tiles_y;
+  const int ngroups = epi_groups<EPI>(p);
+  int s = 0;
+  uint32_t ph = 0;
+  for (int base = first_item; base < items_padded; base += item_stride) {
+    for (int gi = 0; gi < G; ++gi) {
+      const int item = base + gi;
+      if (item >= num_items) break;
+      const ItemCoord c = decode_item(p, item);
+      for (int grp = 0; grp < ngroups; ++grp) {
+        mbar_wait(&e_empty[s], ph ^ 1);
+        if (leader) {
+          uint8_t* st = sE + s * p.e_stage_bytes;
+          uint64_t* bar = &e_full[s];
+          if constexpr (EPI == EPI_FWD) {
+            if (p.slot_c_in >= 0) {
+              mbar_arrive_expect_tx(bar, kEpiBoxBytes16);
+              tma_load_5d(st + p.e_off_c, &p.tm_c, bar, c.nb * p.hcb + grp * 16, c.x0, c.y0, c.b, p.slot_c_in);
+            } else {
+              mbar_arrive(bar);   // zero state: nothing to read, the stage is only an output buffer
+            }
+          } else {
+            const uint32_t bytes = GE::kGateBytes + kEpiBoxBytes16 * (1 + (p.slot_c_prev >= 0) + (p.has_dc_in != 0));
+            mbar_arrive_expect_tx(bar, bytes);
+            const int q0 = group_q0(grp * 16, p.hcb);
+#pragma unroll
+            for (int bx = 0; bx < GE::kGateBoxes; ++bx)
+              tma_load_5d(st + bx * GE::kGateBoxBytes, &p.tm_g, bar, q0 + bx * GE::kGateBoxCols, c.x0, c.y0, c.b, p.slot_g);
+            tma_load_5d(st + p.e_off_c, &p.tm_c, bar, grp * 16, c.x0, c.y0, c.b, p.slot_c_cur);
+            if (p.slot_c_prev >= 0)
+              tma_load_5d(st + p.e_off_c2, &p.tm_c, bar, grp * 16, c.x0, c.y0, c.b, p.slot_c_prev);
+            if (p.has_dc_in) tma_load_5d(st + p.e_off_dc, &p.tm_dc, bar, grp * 16, c.x0, c.y0, c.b, 0);
+          }
+        }
+        if (++s == p.e_stages) {
+          s = 0;
+          ph ^= 1;
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ storer (warp 2)
+template <typename E, int EPI>
+__device__ __forceinline__ void epi_storer(const ConvGemmParams& p, uint8_t* sE, uint64_t* st_ready, uint64_t* e_empty,
+                                           int first_item, int item_stride, int items_padded, int G) {
+  using GE = EpiGeom<E>;
+  const bool leader = elect_one();
+  const int num_items = p.n_blocks * p.B * p.tiles_x * p.tiles_y;
+  const int ngroups = epi_groups<EPI>(p);
+  int s = 0;
+  uint32_t ph = 0;
+  for (int base = first_item; base < items_padded; base += item_stride) {
+    for (int gi = 0; gi < G; ++gi) {
+      const int item = base + gi;
+      if (item >= num_items) break;
+      const ItemCoord c = decode_item(p, item);
+      for (int grp = 0; grp < ngroups; ++grp) {
+        mbar_wait(&st_ready[s], ph);
+        if (leader) {
+          const uint8_t* st = sE + s * p.e_stage_bytes;
+          if (!(p.debug_flags & 1)) {
+            if constexpr (EPI == EPI_FWD) {
+              const int ch = c.nb * p.hcb + grp * 16;
+              tma_store_5d(&p.tm_c, st + p.e_off_c, ch, c.x0, c.y0, c.b, p.slot_c_out);
+              tma_store_5d(&p.tm_h, st + p.e_off_h, ch, c.x0, c.y0, c.b, p.slot_h_out);
+              if (p.slot_g >= 0) {
+                const int q0 = group_q0(ch, p.hcb);
+#pragma unroll
+                for (int bx = 0; bx < GE::kGateBoxes; ++bx)
+                  tma_store_5d(&p.tm_g, st + bx * GE::kGateBoxBytes, q0 + bx * GE::kGateBoxCols, c.x0, c.y0, c.b, p.slot_g);
+              }
+            } else {
+              const int q0 = group_q0(grp * 16, p.hcb);
+#pragma unroll
+              for (int bx = 0; bx < GE::kGateBoxes; ++bx)
+                tma_store_5d(&p.tm_g, st + bx * GE::kGateBoxBytes, q0 + bx * GE::kGateBoxCols, c.x0, c.y0, c.b, p.slot_g);
+              tma_store_5d(&p.tm_dc, st + p.e_off_dc, grp * 16, c.x0, c.y0, c.b, 0);
+            }
+            tma_store_commit();
+            tma_store_wait_read();   // the stage may be overwritten once TMA has read it
+          }
+          mbar_arrive(&e_empty[s]);
+        }
+        if (++s == p.e_stages) {
+          s = 0;
+          ph ^= 1;
+        }
+      }
+    }
+  }
+  if (leader) tma_store_wait_all();   // global writes complete before the CTA exits
+}
+
+// ------------------------------------------------------------------------------------ math (warps 4..11)
+// TMEM lane quadrant = warp % 4 (hardware rule); the two warps of a quadrant take the two 8-channel halves
+// of the 16-channel group.  `tempty_remote`: CTA-pair mode, shared::cluster address of the leader's tempty_bar[0].
+template <typename E, int EPI>
+__device__ __forceinline__ void epi_math(const ConvGemmParams& p, int warp, int lane, uint32_t tmem_base, uint8_t* sE,
+                                         uint64_t* e_full, uint64_t* st_ready, uint64_t* tfull_bar, uint64_t* tempty_bar,
+                                         const float* s_bias, const float* s_headw, int first_item, int item_stride,
+                                         int items_padded, int G, uint32_t tempty_remote) {
+  using GE = EpiGeom<E>;
   constexpr int DT = ElemTraits<E>::kDtype;
   constexpr bool FAST = (DT == NINT_BF16);
   const int num_items = p.n_blocks * p.B * p.tiles_x * p.tiles_y;
-  {
-    // ------------------------------------------------------------------ epilogue (8 warps)
-    // TMEM lane quadrant = warp % 4 (hardware rule); the two warps of a quadrant split the
-    // 16-channel groups between them (half = 0 / 1).
-    const int quad = warp & 3;
-    const int half = (warp - 4) >> 2;
-    const int row = quad * 32 + lane;
-    const int ty = row / p.tile_w;
-    const int tx = row - ty * p.tile_w;
-    const int hc = p.hc;
-    const int hcb = p.hcb;
-    int abuf = 0;
-    uint32_t aphase = 0;
-    // one accumulator buffer (256 TMEM columns) holds the G consecutive tiles of an item group
-    for (int base = first_item; base < num_items_padded; base += item_stride) {
-      bool waited = (p.nseg == 0);
-      auto wait_acc = [&]() {
+  const int ngroups = epi_groups<EPI>(p);
+  const int quad = warp & 3;
+  const int half = (warp - 4) >> 2;
+  const int row = quad * 32 + lane;
+  const bool skip = (p.debug_flags & 1) != 0;
+  int s = 0;
+  uint32_t ph = 0;
+  int abuf = 0;
+  uint32_t aphase = 0;
+  for (int base = first_item; base < items_padded; base += item_stride) {
+    bool waited = (p.nseg == 0);
+    for (int gi = 0; gi < G; ++gi) {
+      const int item = base + gi;
+      if (item >= num_items) break;
+      const ItemCoord c = decode_item(p, item);
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
+                             static_cast<uint32_t>(abuf * 256 + gi * p.n_tile);
+      float dpred = 0.f;
+      if constexpr (EPI == EPI_BWD) {
+        if (p.head_dpred) {
+          const int y = c.y0 + (row >> 3), x = c.x0 + (row & 7);
+          if (y < p.H && x < p.W)
+            dpred = p.head_dpred[c.b * p.head_dpred_bstride + static_cast<long long>(y) * p.W + x];
+        }
+      }
+      for (int grp = 0; grp < ngroups; ++grp) {
+        const uint32_t st = smem_u32(sE + s * p.e_stage_bytes);
+        mbar_wait(&e_full[s], ph);
         if (!waited) {
           mbar_wait(&tfull_bar[abuf], aphase);
           tc_fence_after();
           waited = true;
         }
-      };
-      for (int gi = 0; gi < G; ++gi) {
-      const int item = base + gi;
-      const ItemCoord c = decode_item(p, item);
-      const int y = c.y0 + ty, x = c.x0 + tx;
-      const bool valid = (item < num_items) && (ty < p.tile_h) && (y < p.H) && (x < p.W) && !(p.debug_flags & 1);
-      const long long pix = (static_cast<long long>(c.b) * p.H + y) * p.W + x;
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
-                             static_cast<uint32_t>(abuf * 256 + gi * p.n_tile);
-      if constexpr (EPI == EPI_FWD) {
-        // model.py:221-229.  columns of this n-block: gate * hcb + cc
-        const float* cprev = p.c_prev ? p.c_prev + pix * hc + c.nb * hcb : nullptr;
-        float* cout = p.c_out + pix * hc + c.nb * hcb;
-        E* hout = reinterpret_cast<E*>(p.h_out) + pix * p.hc_pad + c.nb * hcb;
-        E* gout = p.gates_out ? reinterpret_cast<E*>(p.gates_out) + pix * 4 * hc + c.nb * p.n_tile : nullptr;
-        const uint32_t bq = smem_u32(s_bias + c.nb * p.n_tile);
-        for (int cg = half * 16; cg < hcb; cg += 32) {
-          float cn[16];
-          if (cprev && valid) {   // issued before the accumulator wait: overlaps the MMA tail
-            load_elems<float, 16>(cprev + cg, cn);
+        if constexpr (EPI == EPI_FWD) {
+          // model.py:221-229.  accumulator columns of this group: grp*64 + gate*16 + channel
+          float a[4][8], cn[8], hn[8];
+#pragma unroll
+          for (int g = 0; g < 4; ++g) tmem_ld8(taddr + grp * 64 + g * 16 + half * 8, a[g]);
+          if (p.slot_c_in >= 0 && !skip) {
+            lds8<float, 64>(st + p.e_off_c, row, half, cn);
           } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) cn[j] = 0.f;
+            for (int j = 0; j < 8; ++j) cn[j] = 0.f;
           }
-          wait_acc();
-          float a[4][16];
-#pragma unroll
-          for (int g = 0; g < 4; ++g) tmem_ld16(taddr + g * hcb + cg, a[g]);
+          const uint32_t bq = smem_u32(s_bias + c.nb * p.n_tile + grp * 64 + half * 8);
           tmem_ld_wait();
-          if (valid) {
-            float hn[16];
+          if (!skip) {
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {   // bias: explicit 128-bit ld.shared (a generic pointer costs 64 LD.E)
-              float bias[16];
+            for (int g = 0; g < 4; ++g) {
+              float bias[8];
+              lds128(bq + g * 64, bias);
+              lds128(bq + g * 64 + 16, bias + 4);
 #pragma unroll
-              for (int j = 0; j < 16; j += 4) lds128(bq + (g * hcb + cg + j) * 4, &bias[j]);
-#pragma unroll
-              for (int j = 0; j < 16; ++j) a[g][j] += bias[j];
+              for (int j = 0; j < 8; ++j) a[g][j] += bias[j];
             }
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float gi = act_sigmoid<FAST>(a[0][j]);
+            for (int j = 0; j < 8; ++j) {
+              const float gi_ = act_sigmoid<FAST>(a[0][j]);
               const float gf = act_sigmoid<FAST>(a[1][j]);
               const float gg = act_tanh<FAST>(a[2][j]);
               const float go = act_sigmoid<FAST>(a[3][j]);
-              const float cv = fmaf(cn[j], gf, gi * gg);
+              const float cv = fmaf(cn[j], gf, gi_ * gg);
               cn[j] = cv;
               float hv = go * act_tanh<FAST>(cv);
               if constexpr (DT == NINT_TF32) hv = round_tf32(hv);  // h feeds the next step's tf32 MMA
               hn[j] = hv;
-              a[0][j] = gi; a[1][j] = gf; a[2][j] = gg; a[3][j] = go;
+              a[0][j] = gi_; a[1][j] = gf; a[2][j] = gg; a[3][j] = go;
             }
-            store_elems<float, 16>(cout + cg, cn);
-            store_elems<E, 16>(hout + cg, hn);
-            if (gout) {
+            sts8<float, 64>(st + p.e_off_c, row, half, cn);
+            sts8<E, GE::kHRowB>(st + p.e_off_h, row, half, hn);
+            if (p.slot_g >= 0) {
 #pragma unroll
-              for (int g = 0; g < 4; ++g) store_elems<E, 16>(gout + g * hcb + cg, a[g]);
-            }
-          }
-        }
-        wait_acc();   // warps without a channel group (hcb == 16) still take part in the handshake
-      } else if constexpr (EPI == EPI_BWD) {
-        // gate backward; accumulator column c = dh_t[c] from the dgrad conv
-        const E* gin = reinterpret_cast<const E*>(p.gates_in) + pix * 4 * hc;
-        E* dgo = reinterpret_cast<E*>(p.dgates_out) + pix * 4 * hc;
-        const float* ccur = p.c_cur + pix * hc;
-        const float* cprv = p.c_prev_b ? p.c_prev_b + pix * hc : nullptr;
-        const float* dcin = p.dc_in ? p.dc_in + pix * hc : nullptr;
-        float* dcout = p.dc_out + pix * hc;
-        float dpred = 0.f;
-        if (p.head_dpred && valid) {
-          const long long hw = static_cast<long long>(p.H) * p.W;
-          dpred = p.head_dpred[c.b * p.head_dpred_bstride + (pix - c.b * hw)];
-        }
-        for (int c0 = half * 16; c0 < hc; c0 += 32) {
-          const int nb = c0 / hcb, cc = c0 - nb * hcb;
-          const int qb = nb * 4 * hcb + cc;  // + gate * hcb
-          float gi[16], gf[16], gg[16], go[16], ct[16], cp[16], dc[16], dh[16];
-          if (valid) {   // all global loads of the group in flight before the accumulator wait
-            load_elems<E, 16>(gin + qb, gi);
-            load_elems<E, 16>(gin + qb + hcb, gf);
-            load_elems<E, 16>(gin + qb + 2 * hcb, gg);
-            load_elems<E, 16>(gin + qb + 3 * hcb, go);
-            load_elems<float, 16>(ccur + c0, ct);
-            if (cprv) {
-              load_elems<float, 16>(cprv + c0, cp);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) cp[j] = 0.f;
-            }
-            if (dcin) {
-              load_elems<float, 16>(dcin + c0, dc);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) dc[j] = 0.f;
+              for (int g = 0; g < 4; ++g) sts_gate<E>(st, row, g, half, a[g]);
             }
           }
-          float hw[16];
-#pragma unroll
-          for (int j = 0; j < 16; j += 4) lds128(smem_u32(s_headw + c0 + j), &hw[j]);
+        } else {
+          // gate backward; accumulator column c = dh_t[c] from the dgrad conv
+          float gi_[8], gf[8], gg[8], go[8], ct[8], cp[8], dc[8], dh[8];
+          const int c0 = grp * 16 + half * 8;
           if (p.nseg > 0) {
-            wait_acc();
-            tmem_ld16(taddr + c0, dh);
-            tmem_ld_wait();
+            tmem_ld8(taddr + c0, dh);
           } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) dh[j] = 0.f;
+            for (int j = 0; j < 8; ++j) dh[j] = 0.f;
           }
-          if (valid) {
+          if (!skip) {
+            lds_gate<E>(st, row, 0, half, gi_);
+            lds_gate<E>(st, row, 1, half, gf);
+            lds_gate<E>(st, row, 2, half, gg);
+            lds_gate<E>(st, row, 3, half, go);
+            lds8<float, 64>(st + p.e_off_c, row, half, ct);
+            if (p.slot_c_prev >= 0) {
+              lds8<float, 64>(st + p.e_off_c2, row, half, cp);
+            } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
+              for (int j = 0; j < 8; ++j) cp[j] = 0.f;
+            }
+            if (p.has_dc_in) {
+              lds8<float, 64>(st + p.e_off_dc, row, half, dc);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) dc[j] = 0.f;
+            }
+          }
+          float hw[8];
+          if (p.head_dpred) {
+            lds128(smem_u32(s_headw + c0), hw);
+            lds128(smem_u32(s_headw + c0 + 4), hw + 4);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) hw[j] = 0.f;
+          }
+          if (p.nseg > 0) tmem_ld_wait();
+          if (!skip) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
               const float dhv = fmaf(dpred, hw[j], dh[j]);
               const float tc = act_tanh<FAST>(ct[j]);
               const float d_o = dhv * tc;
               const float dcv = fmaf(dhv * go[j], 1.f - tc * tc, dc[j]);
               const float d_i = dcv * gg[j];
-              const float d_g = dcv * gi[j];
+              const float d_g = dcv * gi_[j];
               const float d_f = dcv * cp[j];
               dc[j] = dcv * gf[j];
-              const float i_ = gi[j], f_ = gf[j], g_ = gg[j], o_ = go[j];
-              gi[j] = d_i * i_ * (1.f - i_);
+              const float i_ = gi_[j], f_ = gf[j], g_ = gg[j], o_ = go[j];
+              gi_[j] = d_i * i_ * (1.f - i_);
               gf[j] = d_f * f_ * (1.f - f_);
               gg[j] = d_g * (1.f - g_ * g_);
               go[j] = d_o * o_ * (1.f - o_);
               if constexpr (DT == NINT_TF32) {
                 // dgates are MMA operands of dgrad and wgrad: round to nearest tf32 (the MMA truncates)
-                gi[j] = round_tf32(gi[j]); gf[j] = round_tf32(gf[j]);
+                gi_[j] = round_tf32(gi_[j]); gf[j] = round_tf32(gf[j]);
                 gg[j] = round_tf32(gg[j]); go[j] = round_tf32(go[j]);
               }
             }
-            store_elems<float, 16>(dcout + c0, dc);
-            store_elems<E, 16>(dgo + qb, gi);
-            store_elems<E, 16>(dgo + qb + hcb, gf);
-            store_elems<E, 16>(dgo + qb + 2 * hcb, gg);
-            store_elems<E, 16>(dgo + qb + 3 * hcb, go);
+            sts8<float, 64>(st + p.e_off_dc, row, half, dc);
+            sts_gate<E>(st, row, 0, half, gi_);
+            sts_gate<E>(st, row, 1, half, gf);
+            sts_gate<E>(st, row, 2, half, gg);
+            sts_gate<E>(st, row, 3, half, go);
           }
         }
-        wait_acc();
-      } else {
-        float* ro = p.raw_out + pix * (p.n_blocks * p.n_tile) + c.nb * p.n_tile;
-        wait_acc();
-        for (int c0 = half * 16; c0 < p.n_tile; c0 += 32) {
-          float v[16];
-          tmem_ld16(taddr + c0, v);
-          tmem_ld_wait();
-          if (valid) store_elems<float, 16>(ro + c0, v);
-        }
-      }
-      }  // tiles of the group
-      if (p.nseg > 0) {
-        tc_fence_before();
+        // results visible to the async proxy (TMA store), then hand the stage to the storer
+        fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[abuf]);
-        if (++abuf == 2) {
-          abuf = 0;
-          aphase ^= 1;
+        if (lane == 0) mbar_arrive(&st_ready[s]);
+        if (++s == p.e_stages) {
+          s = 0;
+          ph ^= 1;
         }
       }
+    }
+    if (p.nseg > 0) {
+      if (!waited) {   // a group made only of padding items: still take part in the accumulator handshake
+        mbar_wait(&tfull_bar[abuf], aphase);
+        tc_fence_after();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        // pair mode: the MMA issuer lives in the leader CTA and waits for the epilogue warps of both CTAs
+        if (tempty_remote) mbar_arrive_cluster(tempty_remote + abuf * 8); else mbar_arrive(&tempty_bar[abuf]);
+      }
+      if (++abuf == 2) {
+        abuf = 0;
+        aphase ^= 1;
+      }
+    }
+  }
+}
+
+// debug epilogue: dump the fp32 accumulators [B,H,W,n_blocks*n_tile] (nint_debug_raw_gates)
+__device__ __forceinline__ void epi_raw(const ConvGemmParams& p, int warp, int lane, uint32_t tmem_base,
+                                        uint64_t* tfull_bar, uint64_t* tempty_bar, int first_item, int item_stride,
+                                        int items_padded, int G, uint32_t tempty_remote) {
+  const int num_items = p.n_blocks * p.B * p.tiles_x * p.tiles_y;
+  const int quad = warp & 3;
+  const int half = (warp - 4) >> 2;
+  const int row = quad * 32 + lane;
+  int abuf = 0;
+  uint32_t aphase = 0;
+  for (int base = first_item; base < items_padded; base += item_stride) {
+    mbar_wait(&tfull_bar[abuf], aphase);
+    tc_fence_after();
+    for (int gi = 0; gi < G; ++gi) {
+      const int item = base + gi;
+      if (item >= num_items) break;
+      const ItemCoord c = decode_item(p, item);
+      const int y = c.y0 + (row >> 3), x = c.x0 + (row & 7);
+      const bool valid = y < p.H && x < p.W;
+      const long long pix = (static_cast<long long>(c.b) * p.H + y) * p.W + x;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
+                             static_cast<uint32_t>(abuf * 256 + gi * p.n_tile);
+      float* ro = p.raw_out + pix * (p.n_blocks * p.n_tile) + c.nb * p.n_tile;
+      for (int c0 = half * 16; c0 < p.n_tile; c0 += 32) {
+        float v[16];
+        tmem_ld16(taddr + c0, v);
+        tmem_ld_wait();
+        if (valid) store_elems<float, 16>(ro + c0, v);
+      }
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) {
+      if (tempty_remote) mbar_arrive_cluster(tempty_remote + abuf * 8); else mbar_arrive(&tempty_bar[abuf]);
+    }
+    if (++abuf == 2) {
+      abuf = 0;
+      aphase ^= 1;
     }
   }
 }

@@ -5,9 +5,11 @@
 //     tf32-rounded values), C_pad a multiple of 32 channels; the conv kernels walk K in 64-byte
 //     chunks (32 bf16 / 16 tf32 elements), wgrad in 32-channel panels;
 //   * a pixel tile is tile_w x tile_h <= 128 pixels of one image, row = ty * tile_w + tx;
-//   * the 4*hc gate channels of a layer are stored in "q-order": with hcb = min(hc, 64) and
-//     n_blocks = hc / hcb,  q = nb * 4*hcb + gate * hcb + cc  <->  reference channel
-//     n = gate * hc + nb * hcb + cc   (gate order i,f,g,o: model.py:221).
+//   * the 4*hc gate channels of a layer are stored in "q-order": with hcb = min(hc, 64), n_blocks = hc / hcb
+//     and cc = 16*grp + c16 the channel inside its n-block,
+//       q = nb * 4*hcb + grp * 64 + gate * 16 + c16  <->  reference channel n = gate * hc + nb * hcb + cc
+//     (gate order i,f,g,o: model.py:221): the four gates of a 16-channel group are 64 contiguous columns,
+//     i.e. one 128-byte (bf16) TMA box row per pixel for the epilogue and one tcgen05.ld-friendly span.
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -41,24 +43,21 @@ struct alignas(64) ConvGemmParams {
   int num_stages;
   // halo variant (nint_conv_halo.cu): activation buffers, cluster size, descriptor base-offset policy
   int na_bufs, a_buf_bytes, cluster, base_offset_mode, taps_per_stage;
-  int group, a_halo_bytes;
-  int debug_flags;          // experiments: 1 = epilogue does no global memory ops / math, 2 = no MMA issue  // tiles per item group (side-by-side accumulators), bytes of one halo chunk
+  int group, a_halo_bytes;  // tiles per item group (side-by-side accumulators), bytes of one halo chunk
+  int debug_flags;          // experiments: 1 = epilogue does no memory ops / math, 2 = no MMA issue
+  // ---- TMA-staged epilogue I/O (nint_epilogue.cuh): 5-D maps (channel, x, y, image, slot) of the layer's
+  // c history (fp32), h history (E), saved gates (E, q-order) and running dc (fp32); slot < 0 = absent
+  CUtensorMap tm_c, tm_h, tm_g, tm_dc;
+  int slot_c_in, slot_c_out, slot_h_out, slot_g;   // FWD: c_{t-1}, c_t, h_t, gates_t;  BWD: slot_g = gates_t / dgates_t
+  int slot_c_cur, slot_c_prev, has_dc_in;          // BWD: c_t, c_{t-1}, dc_t present
+  int e_stages, e_stage_bytes, e_off_c, e_off_c2, e_off_dc, e_off_h;
   uint32_t idesc;
   int hc, hc_pad;  // hidden channels of this layer / padded channel count of its h tensor
   int hcb;         // min(hc, 64)
   // ---- EPI_FWD: LSTM cell update (model.py:221-229)
   const float* bias_q;  // [4*hc], q-order
-  const float* c_prev;  // [B,H,W,hc] fp32 or null (zero state)
-  float* c_out;         // [B,H,W,hc] fp32
-  void* h_out;          // [B,H,W,hc_pad] E
-  void* gates_out;      // [B,H,W,4*hc] E, q-order, or null (inference)
-  // ---- EPI_BWD: gate backward; accumulator = dh (absent when nseg == 0)
-  const void* gates_in;     // [B,H,W,4*hc] E (activated i,f,g,o of step t)
-  const float* c_cur;       // c_t
-  const float* c_prev_b;    // c_{t-1} or null (zero state)
-  const float* dc_in;       // dc_t or null
-  float* dc_out;            // dc_{t-1}
-  void* dgates_out;         // [B,H,W,4*hc] E (may alias gates_in)
+  // ---- EPI_BWD: gate backward; accumulator = dh (absent when nseg == 0); dgates overwrite
+  // the saved gates in place
   const float* head_dpred;  // optional [B,H,W] (+ stride): dh += head_dpred * head_w[c]
   long long head_dpred_bstride;  // elements between images of head_dpred
   const float* head_w;      // [hc]
@@ -66,11 +65,11 @@ struct alignas(64) ConvGemmParams {
   float* raw_out;
 };
 
-int conv_gemm_smem_bytes(int n_tile, int num_stages, int hc);
-int conv_gemm_pick_stages(int n_tile, int hc);
-cudaError_t launch_conv_gemm(int epi, int dtype, const ConvGemmParams& p, int num_sms, cudaStream_t stream);
-// halo variant: 8x16 pixel tiles, activation chunk + halo loaded once and re-read by every tap
-void conv_halo_plan(ConvGemmParams& p);  // fills na_bufs / a_buf_bytes / num_stages from nseg, seg[].ksize, n_tile, hc
+// 8x16 pixel tiles, activation chunk + halo loaded once and re-read by every tap (nint_conv_halo.cu).
+// conv_halo_plan fills the shared-memory plan (epilogue stages, item group, halo buffers, weight stages)
+// from nseg, seg[].ksize, n_tile, hc, cluster, slot_*; non-zero = does not fit.
+int conv_halo_plan(int epi, int dtype, ConvGemmParams& p);
+int conv_halo_smem_bytes(const ConvGemmParams& p);
 cudaError_t launch_conv_halo(int epi, int dtype, const ConvGemmParams& p, int num_sms, cudaStream_t stream);
 
 // ---- wgrad (nint_wgrad.cu):  dW[tap][q][col] += sum_pixels dgates[pix][q] * comb[pix + tap][col]
@@ -89,13 +88,17 @@ struct alignas(64) WgradParams {
   int splits;             // split-K factor over pixel tiles
   int ncols;              // accumulator columns per tap = (sum nchunks_b) * 32
   int a_bufs, b_stages;
+  int halo;               // 1: 8x16 tiles, B panels hold the tile + k//2 halo and every tap re-reads them in place
+  int b_panel_bytes;      // bytes between consecutive B panels of a stage
+  int debug_flags;        // experiments: 2 = no MMA issue, 4 = issue every MMA twice
   uint32_t idesc, idesc_bias;
   int hc4;                // 4*hc
   float* dw_acc;          // [taps][4*hc][ncols] fp32, atomically accumulated (pre-zeroed)
   float* db_acc;          // [4*hc] fp32 (q-order) or null
 };
-int wgrad_smem_bytes(int dtype, int bpanels, int a_bufs, int b_stages);
-void wgrad_pick_buffers(int dtype, int bpanels, int* a_bufs, int* b_stages);
+int wgrad_b_panel_bytes(int dtype, int halo, int ksize);
+int wgrad_smem_bytes(int dtype, int bpanels, int a_bufs, int b_stages, int b_panel_bytes);
+void wgrad_pick_buffers(int dtype, int bpanels, int b_panel_bytes, int* a_bufs, int* b_stages);
 cudaError_t launch_wgrad(int dtype, const WgradParams& p, cudaStream_t stream);
 
 // ---- pointwise / layout kernels (nint_pointwise.cu)
@@ -128,7 +131,8 @@ __host__ __device__ inline int hcb_of(int hc) { return hc < 64 ? hc : 64; }
 __host__ __device__ inline int q_to_n(int q, int hc) {
   const int hcb = hcb_of(hc);
   const int nb = q / (4 * hcb), r = q % (4 * hcb);
-  return (r / hcb) * hc + nb * hcb + (r % hcb);
+  const int grp = r >> 6, gate = (r >> 4) & 3, c16 = r & 15;
+  return gate * hc + nb * hcb + grp * 16 + c16;
 }
 
 }  // namespace nint

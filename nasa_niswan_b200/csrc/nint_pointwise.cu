@@ -214,7 +214,7 @@ __global__ void pack_w_fwd_kernel(const float* __restrict__ w, const float* __re
     const int tap = static_cast<int>(r % taps); r /= taps;
     const int ch = static_cast<int>(r % nch);
     const int nb = static_cast<int>(r / nch);
-    const int n = (col / hcb) * hc + nb * hcb + (col % hcb);
+    const int n = q_to_n(nb * n_tile + col, hc);
     const int cl = ch * CE + e;
     const int climit = is_h ? hc : cin;
     float v = 0.f;

@@ -27,14 +27,20 @@ constexpr int kWgPanelChannels = 32;  // channels per panel row, both dtypes
 constexpr int kWgMPanels = 128 / kWgPanelChannels;
 static inline int wg_panel_bytes(int dtype) { return kTilePixels * kWgPanelChannels * (dtype == NINT_BF16 ? 2 : 4); }
 
-int wgrad_smem_bytes(int dtype, int bpanels, int a_bufs, int b_stages) {
-  const int pb = wg_panel_bytes(dtype);
-  return 1024 + a_bufs * kWgMPanels * pb + b_stages * bpanels * pb + pb + kWgCtrlBytes;
+// halo mode: a B panel holds the (8+2p) x (16+2p) halo of the 8x16 pixel tile instead of 128 rows
+int wgrad_b_panel_bytes(int dtype, int halo, int ksize) {
+  if (!halo) return wg_panel_bytes(dtype);
+  const int rows = (8 + (ksize & ~1)) * (16 + (ksize & ~1));
+  return (rows * kWgPanelChannels * (dtype == NINT_BF16 ? 2 : 4) + 1023) & ~1023;
 }
-void wgrad_pick_buffers(int dtype, int bpanels, int* a_bufs, int* b_stages) {
+int wgrad_smem_bytes(int dtype, int bpanels, int a_bufs, int b_stages, int b_panel_bytes) {
+  const int pb = wg_panel_bytes(dtype);
+  return 1024 + a_bufs * kWgMPanels * pb + b_stages * bpanels * b_panel_bytes + pb + kWgCtrlBytes;
+}
+void wgrad_pick_buffers(int dtype, int bpanels, int b_panel_bytes, int* a_bufs, int* b_stages) {
   const int pb = wg_panel_bytes(dtype);
   const int budget = 227 * 1024 - 1024 - kWgCtrlBytes - pb;
-  const int a1 = kWgMPanels * pb, b1 = bpanels * pb;
+  const int a1 = kWgMPanels * pb, b1 = bpanels * b_panel_bytes;
   int a = 2, b = (budget - a * a1) / b1;
   if (b < 2) {
     a = 1;
@@ -62,7 +68,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
   const int lane = threadIdx.x & 31;
   const int bpanels = p.nchunks_b[0] + p.nchunks_b[1];
   const int a_buf_bytes = MPANELS * PANEL;
-  const int b_stage_bytes = bpanels * PANEL;
+  const int b_stage_bytes = bpanels * p.b_panel_bytes;
+  const int hpitch = 8 + (p.ksize & ~1);                        // halo mode: pixels per halo row
+  const int hrows = hpitch * (16 + (p.ksize & ~1));
   uint8_t* sA = smem;
   uint8_t* sB = sA + p.a_bufs * a_buf_bytes;
   uint8_t* sOnes = sB + p.b_stages * b_stage_bytes;
@@ -148,6 +156,21 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
           ab = 0;
           aph ^= 1;
         }
+        if (p.halo) {   // one halo load serves every tap of the group
+          mbar_wait(&b_empty[bs], bph ^ 1);
+          if (leader) {
+            mbar_arrive_expect_tx(&b_full[bs], static_cast<uint32_t>(hrows * ROWB * bpanels));
+            uint8_t* dst = sB + bs * b_stage_bytes;
+            for (int j = 0; j < p.nchunks_b[0]; ++j, dst += p.b_panel_bytes)
+              tma_load_5d(dst, &p.tmap_b[0], &b_full[bs], j * CE, x0 - pad, y0 - pad, b, p.slot_b0[0] + t);
+            for (int j = 0; j < p.nchunks_b[1]; ++j, dst += p.b_panel_bytes)
+              tma_load_5d(dst, &p.tmap_b[1], &b_full[bs], j * CE, x0 - pad, y0 - pad, b, p.slot_b0[1] + t);
+          }
+          if (++bs == p.b_stages) {
+            bs = 0;
+            bph ^= 1;
+          }
+        } else
         for (int ti = 0; ti < ntaps; ++ti) {
           const int tap = tap_begin + ti;
           const int dy = tap / p.ksize - pad, dx = tap % p.ksize - pad;
@@ -177,6 +200,51 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
         mbar_wait(&a_full[ab], aph);
         tc_fence_after();
         const uint64_t adesc0 = make_smem_desc(smem_u32(sA + ab * a_buf_bytes), PANEL, SBO, LAYOUT);
+        if (p.halo) {
+          // k-step outer, tap inner: consecutive MMAs hit different accumulators (an accumulate chain
+          // into one accumulator serialises on the MMA latency), every tap reads the halo in place
+          // through a row-shifted MN-major descriptor.
+          mbar_wait(&b_full[bs], bph);
+          tc_fence_after();
+          // one K step = ROWS_PER_MMA pixels = 2 tile rows (bf16: 8-pixel groups one halo row apart) or
+          // 1 tile row (tf32: 4-pixel groups 512 bytes apart)
+          const uint32_t sbo_b = (DT == NINT_BF16) ? static_cast<uint32_t>(hpitch * ROWB) : 512u;
+          const uint64_t bdesc0 = make_smem_desc(smem_u32(sB + bs * b_stage_bytes), p.b_panel_bytes, sbo_b, LAYOUT);
+          if (leader) {
+            const int reps = (p.debug_flags & 2) ? 0 : ((p.debug_flags & 4) ? 2 : 1);
+            for (int rep = 0; rep < reps; ++rep)
+#pragma unroll 1
+            for (int ks = 0; ks < KSTEPS; ++ks) {
+              const uint64_t aoff = static_cast<uint64_t>((ks * ROWS_PER_MMA * ROWB) >> 4);
+              const int row0 = ks * ROWS_PER_MMA / 8;
+              const uint32_t acc = (i | ks) != 0 ? 1u : 0u;
+              int dy = tap_begin / p.ksize, dx = tap_begin % p.ksize;
+              for (int ti = 0; ti < ntaps; ++ti) {
+                const uint64_t boff = static_cast<uint64_t>((((row0 + dy) * hpitch + dx) * ROWB) >> 4);
+                umma<DT>(tmem_base + static_cast<uint32_t>(ti * p.ncols), adesc0 + aoff, bdesc0 + boff, p.idesc, acc);
+                if (++dx == p.ksize) {
+                  dx = 0;
+                  ++dy;
+                }
+              }
+              if (do_bias) {
+                const uint64_t odesc0 = make_smem_desc(smem_u32(sOnes), PANEL, SBO, LAYOUT);
+                umma<DT>(tmem_base + static_cast<uint32_t>(ntaps * p.ncols), adesc0 + aoff, odesc0 + aoff, p.idesc_bias, acc);
+              }
+            }
+            umma_commit(&b_empty[bs]);
+            umma_commit(&a_empty[ab]);
+          }
+          if (++bs == p.b_stages) {
+            bs = 0;
+            bph ^= 1;
+          }
+          if (++ab == p.a_bufs) {
+            ab = 0;
+            aph ^= 1;
+          }
+          continue;
+        }
         for (int ti = 0; ti < ntaps; ++ti) {
           mbar_wait(&b_full[bs], bph);
           tc_fence_after();
@@ -250,7 +318,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
 template <typename E>
 static cudaError_t launch_wg(const WgradParams& p, cudaStream_t stream) {
   const int dtype = ElemTraits<E>::kDtype;
-  const int smem = wgrad_smem_bytes(dtype, p.nchunks_b[0] + p.nchunks_b[1], p.a_bufs, p.b_stages);
+  const int smem = wgrad_smem_bytes(dtype, p.nchunks_b[0] + p.nchunks_b[1], p.a_bufs, p.b_stages, p.b_panel_bytes);
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(wgrad_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

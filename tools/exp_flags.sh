@@ -1,5 +1,5 @@
 #!/bin/bash
-for f in 0 1 2 3; do
+for f in ${FLAGS:-0 1 2 3}; do
   echo "##### NINT_DEBUG_FLAGS=$f (1: no epilogue memory/math, 2: no MMA issue)"
   NINT_DEBUG_FLAGS=$f python bench.py --steps 6 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | python -c "
 import json,sys
