@@ -74,7 +74,10 @@ struct Layer {
   float *bias_q = nullptr, *dw_acc = nullptr, *db_acc = nullptr;
   size_t dw_acc_bytes = 0;
   int ncols = 0;
-  CUtensorMap tm_H, tm_G, tm_wx, tm_wh, tm_wdx, tm_wdh;
+  CUtensorMap tm_H, tm_G;
+  // weight maps depend on the launch's shared-memory plan (taps per stage): encoded on first use, cached
+  struct WMap { int ts = 0, rows = 0; CUtensorMap map; };
+  std::vector<WMap> wmaps[4];   // 0: wx, 1: wh, 2: wdx, 3: wdh
   CUtensorMap tm_H_up;       // Hs[l] read as the x segment of layer l+1 (halo of k_{l+1})
   CUtensorMap tmw_H, tmw_G;  // wgrad views (32-channel boxes; differ from tm_* in tf32 mode only)
   CUtensorMap tmw_H_up;      // Hs[l] as the x part of layer l+1's wgrad (halo of k_{l+1})
@@ -190,18 +193,20 @@ int encode_io_map(CUtensorMap* m, bool fp32, void* base, int C, int W, int H, in
   return 0;
 }
 
-int encode_w_map(CUtensorMap* m, int dtype, void* base, long long rows, int ce, int n_tile) {
+// packed weight panels [chunk-tap index][n_tile rows][ce elements] seen as a 3-D tensor; a box is the `w_rows`
+// rows one CTA holds (all of N, or half in CTA-pair mode) of `ts` consecutive taps = one weight stage
+int encode_w_map(CUtensorMap* m, int dtype, void* base, long long chunk_taps, int ce, int n_tile, int w_rows, int ts) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return fail("cuTensorMapEncodeTiled not available (no CUDA driver?)");
   const cuuint64_t es = dtype == BF16 ? 2 : 4;
-  cuuint64_t dims[2] = {(cuuint64_t)ce, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {ce * es};
-  cuuint32_t box[2] = {(cuuint32_t)ce, (cuuint32_t)n_tile};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(m, dtype == BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base,
+  cuuint64_t dims[3] = {(cuuint64_t)ce, (cuuint64_t)n_tile, (cuuint64_t)chunk_taps};
+  cuuint64_t strides[2] = {ce * es, (cuuint64_t)n_tile * ce * es};
+  cuuint32_t box[3] = {(cuuint32_t)ce, (cuuint32_t)w_rows, (cuuint32_t)ts};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, dtype == BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base,
                    dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(weights rows=%lld n_tile=%d) -> %d", rows, n_tile, (int)r);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(weights chunk_taps=%lld n_tile=%d rows=%d ts=%d) -> %d", chunk_taps, n_tile, w_rows, ts, (int)r);
   return 0;
 }
 
@@ -269,10 +274,29 @@ void fill_common(const nint_plan* p, const Layer& y, ConvGemmParams& g) {
 // CTA-pair mode (cluster of 2, tcgen05 cta_group::2; halo variant only): every CTA holds half of the N rows
 // of a weight stage, which must stay a whole number of 8-row swizzle atoms with N a multiple of 32
 int fwd_cluster(const nint_plan* p, int l) {
-  return p->layer[l].n_blocks == 1 ? p->cluster : 1;   // n_tile = 4*hcb: multiple of 64
+  (void)l;
+  return p->cluster;   // n_tile = 4*hcb: multiple of 64
 }
 int bwd_cluster(const nint_plan* p, int l) {
   return p->layer[l].hc % 32 == 0 ? p->cluster : 1;    // n_tile = hc
+}
+
+// weight map of layer `y` for one K segment: which = 0 wx, 1 wh (forward, N = n_tile per n-block), 2 wdx, 3 wdh
+// (dgrad, N = n_tile input channels); `rows` = N rows per CTA, `ts` = taps per weight stage
+int get_w_map(nint_plan* p, Layer& y, int which, int n_tile, int rows, int ts, CUtensorMap* out) {
+  for (const Layer::WMap& w : y.wmaps[which])
+    if (w.ts == ts && w.rows == rows) { *out = w.map; return 0; }
+  void* base = which == 0 ? y.wx : which == 1 ? y.wh : which == 2 ? y.wdx : y.wdh;
+  long long chunk_taps;
+  if (which == 0) chunk_taps = (long long)y.n_blocks * y.chx * y.taps;
+  else if (which == 1) chunk_taps = (long long)y.n_blocks * y.chh * y.taps;
+  else chunk_taps = (long long)(4 * y.hc / p->ce) * y.taps;
+  Layer::WMap w;
+  w.ts = ts; w.rows = rows;
+  if (encode_w_map(&w.map, p->dtype, base, chunk_taps, p->ce, n_tile, rows, ts)) return 1;
+  y.wmaps[which].push_back(w);
+  *out = w.map;
+  return 0;
 }
 
 // one fused cell step of layer l at time t (model.py:216-231)
@@ -290,7 +314,7 @@ int cell_step(nint_plan* p, int l, int t, int epi, float* raw_out, cudaStream_t 
   // segment 0: x_t (layer 0) or the h_t of the layer below (model.py:266,271)
   int s = 0;
   g.seg[s].tmap_act = l == 0 ? p->tm_X : p->layer[l - 1].tm_H_up;
-  g.seg[s].tmap_w = y.tm_wx;
+  g.seg[s].wsel = 0;
   g.seg[s].slot = l == 0 ? t : (tr ? t + 1 : ((t + 1) & 1));
   g.seg[s].ksize = y.k;
   g.seg[s].nchunks = y.chx;
@@ -298,7 +322,7 @@ int cell_step(nint_plan* p, int l, int t, int epi, float* raw_out, cudaStream_t 
   const bool have_state = !(t == 0 && p->zero_init);
   if (have_state) {  // h_{t-1} == 0 contributes nothing: skip its K-segment
     g.seg[s].tmap_act = y.tm_H;
-    g.seg[s].tmap_w = y.tm_wh;
+    g.seg[s].wsel = 1;
     g.seg[s].slot = in_slot_h;
     g.seg[s].ksize = y.k;
     g.seg[s].nchunks = y.chh;
@@ -315,6 +339,8 @@ int cell_step(nint_plan* p, int l, int t, int epi, float* raw_out, cudaStream_t 
   g.raw_out = raw_out;
   g.base_offset_mode = p->base_offset_mode;
   if (conv_halo_plan(epi, p->dtype, g)) return fail("layer %d: the conv kernel's shared-memory plan does not fit (hidden %d, k %d)", l, y.hc, y.k);
+  for (int i = 0; i < g.nseg; ++i)
+    if (get_w_map(p, y, g.seg[i].wsel, g.n_tile, g.n_tile / g.cluster, g.taps_per_stage, &g.seg[i].tmap_w)) return 1;
   LAUNCH(p, (epi == EPI_FWD ? K_FWD : K_OTHER), st, launch_conv_halo(epi, p->dtype, g, p->num_sms, st));
   return 0;
 }
@@ -399,7 +425,18 @@ int nint_plan_create(const nint_config* cfg, nint_plan** out) {
     if (l > 0 && cin > 256) { delete p; return fail("layer %d input channels %d > 256", l, cin); }
     y.cx_pad = (y.cin + 31) / 32 * 32; y.chx = y.cx_pad / p->ce;   // channels padded to 32 in both dtypes
     y.hc_pad = (y.hc + 31) / 32 * 32;  y.chh = y.hc_pad / p->ce;
-    y.hcb = hcb_of(y.hc); y.n_blocks = y.hc / y.hcb; y.n_tile = 4 * y.hcb;
+    // forward N slice (n-block) = hcb hidden channels x 4 gates.  If the whole weight slice of an n-block
+    // fits in shared memory next to the halo buffers and epilogue stages (<= 112 KiB per CTA of a pair), the
+    // conv kernel keeps it resident and only activations stream: weight re-reads were ~55 % of the L2 -> SM
+    // traffic of the forward cell and L2 sector throughput was its bound (profiles/).
+    y.hcb = y.hc < 64 ? y.hc : 64;
+    if (cfg->dtype == BF16) {
+      for (int cand = y.hcb; cand >= 32; cand >>= 1) {
+        const long long w_cta = static_cast<long long>((y.cin + 31) / 32 + (y.hc + 31) / 32) * y.taps * (4 * cand / p->cluster) * 64;
+        if (y.hc % cand == 0 && w_cta <= 112 * 1024) { y.hcb = cand; break; }
+      }
+    }
+    y.n_blocks = y.hc / y.hcb; y.n_tile = 4 * y.hcb;
     y.nslots_h = cfg->training ? p->T + 1 : 2;
     y.nslots_c = cfg->training ? p->T + 1 : 1;
     y.ncols = y.cx_pad + y.hc_pad;
@@ -439,8 +476,6 @@ int nint_plan_bind(nint_plan* p, void* workspace, size_t bytes, void* stream) {
   CK(cudaMemsetAsync(p->ws, 0, p->ws_bytes, st));
   const int tw = p->tile_w, th = p->tile_h, ce = p->ce;
   auto pad_of = [&](int l) { return p->layer[l].k / 2; };
-  auto cl_fwd = [&](int l) { return fwd_cluster(p, l); };
-  auto cl_bwd = [&](int l) { return bwd_cluster(p, l); };
   if (encode_act_map(&p->tm_X, p->dtype, p->X, p->layer[0].cx_pad, p->W, p->H, p->B, p->T, ce, tw, th, false, pad_of(0))) return 1;
   if (encode_act_map(&p->tmw_X, p->dtype, p->X, p->layer[0].cx_pad, p->W, p->H, p->B, p->T, ce, tw, th, true, pad_of(0))) return 1;
   for (int l = 0; l < p->L; ++l) {
@@ -457,18 +492,13 @@ int nint_plan_bind(nint_plan* p, void* workspace, size_t bytes, void* stream) {
       y.tme_G = y.tme_C;   // never dereferenced (slot_g < 0), but the kernel parameter must be a valid map
       y.tme_dC = y.tme_C;
     }
-    if (encode_w_map(&y.tm_wx, p->dtype, y.wx, (long long)y.n_blocks * y.taps * y.chx * y.n_tile, ce, y.n_tile / cl_fwd(l))) return 1;
-    if (encode_w_map(&y.tm_wh, p->dtype, y.wh, (long long)y.n_blocks * y.taps * y.chh * y.n_tile, ce, y.n_tile / cl_fwd(l))) return 1;
+    for (auto& v : y.wmaps) v.clear();
     if (p->cfg.training) {
-      const int nch = 4 * y.hc / ce;
       if (encode_act_map(&y.tm_G, p->dtype, y.G, 4 * y.hc, p->W, p->H, p->B, p->T, ce, tw, th, false, pad_of(l))) return 1;
       if (encode_act_map(&y.tmw_G, p->dtype, y.G, 4 * y.hc, p->W, p->H, p->B, p->T, ce, tw, th, true)) return 1;
       if (encode_act_map(&y.tmw_H, p->dtype, y.Hs, y.hc_pad, p->W, p->H, p->B, y.nslots_h, ce, tw, th, true, pad_of(l))) return 1;
       if (l + 1 < p->L &&
           encode_act_map(&y.tmw_H_up, p->dtype, y.Hs, y.hc_pad, p->W, p->H, p->B, y.nslots_h, ce, tw, th, true, pad_of(l + 1))) return 1;
-      // dgrad launch of layer l consumes wdh_l (N = hc_l); wdx_l is consumed by the launch of layer l-1 (N = hc_{l-1})
-      if (encode_w_map(&y.tm_wdh, p->dtype, y.wdh, (long long)y.taps * nch * y.hc, ce, y.hc / cl_bwd(l))) return 1;
-      if (l > 0 && encode_w_map(&y.tm_wdx, p->dtype, y.wdx, (long long)y.taps * nch * y.cin, ce, y.cin / cl_bwd(l - 1))) return 1;
     }
   }
   p->zero_init = true;
@@ -482,7 +512,7 @@ int nint_plan_set_weights(nint_plan* p, int l, const float* weight, const float*
   if (!weight) return fail("null weight");
   Layer& y = p->layer[l];
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  LAUNCH(p, K_OTHER, st, launch_pack_weights_fwd(p->dtype, weight, bias, y.wx, y.wh, y.bias_q, y.cin, y.hc, y.k, y.cx_pad, y.hc_pad, st));
+  LAUNCH(p, K_OTHER, st, launch_pack_weights_fwd(p->dtype, weight, bias, y.wx, y.wh, y.bias_q, y.cin, y.hc, y.hcb, y.k, y.cx_pad, y.hc_pad, st));
   if (p->cfg.training) LAUNCH(p, K_OTHER, st, launch_pack_weights_bwd(p->dtype, weight, y.wdx, y.wdh, y.cin, y.hc, y.k, st));
   y.weights_set = true;
   return 0;
@@ -623,13 +653,13 @@ int nint_backward(nint_plan* p, const float* dpred, const float* dseq, float* co
       g.idesc = idesc_of(p->dtype, 128 * g.cluster, y.hc, 0, 0);
       int s = 0;
       if (t < T - 1) {  // dh_t += dgates_{t+1} (*) flip(W_h)
-        g.seg[s].tmap_act = y.tm_G; g.seg[s].tmap_w = y.tm_wdh; g.seg[s].slot = t + 1;
+        g.seg[s].tmap_act = y.tm_G; g.seg[s].wsel = 3; g.seg[s].slot = t + 1;
         g.seg[s].ksize = y.k; g.seg[s].nchunks = 4 * y.hc / p->ce;
         ++s;
       }
       if (l < L - 1) {  // dh_t += dx of the layer above at the same t
         Layer& up = p->layer[l + 1];
-        g.seg[s].tmap_act = up.tm_G; g.seg[s].tmap_w = up.tm_wdx; g.seg[s].slot = t;
+        g.seg[s].tmap_act = up.tm_G; g.seg[s].wsel = 2; g.seg[s].slot = t;
         g.seg[s].ksize = up.k; g.seg[s].nchunks = 4 * up.hc / p->ce;
         ++s;
       }
@@ -655,6 +685,10 @@ int nint_backward(nint_plan* p, const float* dpred, const float* dseq, float* co
       }
       g.base_offset_mode = p->base_offset_mode;
       if (conv_halo_plan(EPI_BWD, p->dtype, g)) return fail("layer %d: the dgrad kernel's shared-memory plan does not fit (hidden %d, k %d)", l, y.hc, y.k);
+      for (int i = 0; i < g.nseg; ++i) {
+        Layer& owner = g.seg[i].wsel == 2 ? p->layer[l + 1] : y;   // wdx belongs to the layer above
+        if (get_w_map(p, owner, g.seg[i].wsel, g.n_tile, g.n_tile / g.cluster, g.taps_per_stage, &g.seg[i].tmap_w)) return 1;
+      }
       LAUNCH(p, K_BWD, st, launch_conv_halo(EPI_BWD, p->dtype, g, p->num_sms, st));
     }
   }

@@ -30,6 +30,7 @@ namespace nint {
 constexpr int kHaloCtrlBytes = 1024;
 constexpr int kHaloMaxA = 12;
 constexpr int kHaloMaxW = 28;
+constexpr int kMaxAcc = 4;       // TMEM accumulator buffers (512 columns / acc_cols, at most 4)
 
 __host__ __device__ inline int halo_rows(int ksize) { return (8 + (ksize & ~1)) * (16 + (ksize & ~1)); }
 static inline int halo_a_buf_bytes(const ConvGemmParams& p) {
@@ -76,8 +77,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
   uint64_t* w_full = a_empty + kHaloMaxA;
   uint64_t* w_empty = w_full + kHaloMaxW;
   uint64_t* tfull_bar = w_empty + kHaloMaxW;
-  uint64_t* tempty_bar = tfull_bar + 2;
-  uint64_t* e_full = tempty_bar + 2;
+  uint64_t* tempty_bar = tfull_bar + kMaxAcc;
+  uint64_t* e_full = tempty_bar + kMaxAcc;
   uint64_t* e_empty = e_full + kEpiMaxStages;
   uint64_t* st_ready = e_empty + kEpiMaxStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ctrl + kHaloCtrlBytes - 16);
@@ -87,16 +88,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
   uint32_t crank = 0;
   if constexpr (pair) crank = cluster_ctarank();
   const bool lead_cta = crank == 0;
-  // work unit of a CTA iteration = G consecutive tiles ("item group") accumulated side by side in one
+  // work unit of a CTA iteration = G consecutive tiles ("tile group") accumulated side by side in one
   // TMEM buffer and sharing every weight stage; the two CTAs of a pair take adjacent groups
   const int G = p.group;
-  const int num_items = p.n_blocks * p.B * p.tiles_x * p.tiles_y;
-  const int groups = (num_items + S * G - 1) / (S * G);
-  const int clusters = gridDim.x / S;
-  const int cid = blockIdx.x / S;
-  const int first_item = (cid * S + static_cast<int>(crank)) * G;
-  const int item_stride = clusters * S * G;
-  const int items_padded = groups * S * G;
+  const TileWalk walk = make_walk(p, S, static_cast<int>(crank));
+  const bool resident = p.w_resident != 0;   // the whole weight slice of this n-block fits: load it once
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.nseg; ++s) {
@@ -118,7 +114,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
       mbar_init(&w_full[s], 1);
       mbar_init(&w_empty[s], 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < kMaxAcc; ++s) {
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], 8 * S);   // the leader waits for the epilogue warps of both CTAs
     }
@@ -150,19 +146,22 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer (both CTAs)
+    // ------------------------------------------------------------------ operand TMA producer (both CTAs)
     if (p.nseg > 0) {
       const bool leader = elect_one();
       int ia = 0, iw = 0;
       uint32_t pa = 0, pw = 0;
-      for (int item = first_item; item < items_padded; item += item_stride) {
-        const ItemCoord c = decode_item(p, item);   // nb is shared by the group and the pair
+      int es = 0;          // epilogue stage ring (forward: this warp also prefetches c_{t-1})
+      uint32_t eph = 0;
+      bool first = true;
+      for (int base = walk.first_tile; base < walk.tiles_padded; base += walk.tile_stride) {
         for (int s = 0; s < p.nseg; ++s) {
           const ConvSegment& sg = p.seg[s];
           const int pad = sg.ksize >> 1;
           const int taps = sg.ksize * sg.ksize;
           const uint32_t a_bytes = static_cast<uint32_t>(halo_rows(sg.ksize) * kChunkBytes);
-          int wrow = c.nb * taps * sg.nchunks * p.n_tile + static_cast<int>(crank) * w_rows;
+          // weights: 3-D map (element, row of the N tile, chunk-tap index); one box = this CTA's rows of TS taps
+          int wtap = (walk.nb * sg.nchunks) * taps;
           for (int ch = 0; ch < sg.nchunks; ++ch) {
             mbar_wait(&a_empty[ia], pa ^ 1);
             if (leader) {
@@ -171,7 +170,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
               uint32_t bar = 0;
               if constexpr (pair) bar = mapa_rank(smem_u32(&a_full[ia]), 0);
               for (int g = 0; g < G; ++g) {
-                const ItemCoord cg = decode_item(p, item + g);
+                const ItemCoord cg = decode_tile(p, base + g);
                 uint8_t* dst = sA + ia * p.a_buf_bytes + g * p.a_halo_bytes;
                 if constexpr (pair)
                   tma_load_5d_pair(dst, &sg.tmap_act, bar, ch * CE, cg.x0 - pad, cg.y0 - pad, cg.b, sg.slot);
@@ -183,29 +182,29 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
               ia = 0;
               pa ^= 1;
             }
-            for (int tap0 = 0; tap0 < taps; tap0 += TS) {
-              const int nt = (taps - tap0) < TS ? (taps - tap0) : TS;   // taps in this weight stage
-              mbar_wait(&w_empty[iw], pw ^ 1);
+            if (resident && !first) continue;   // weights already in shared memory
+            for (int tap0 = 0; tap0 < taps; tap0 += TS) {   // TS divides taps (conv_halo_plan)
+              if (!resident) mbar_wait(&w_empty[iw], pw ^ 1);
               if (leader) {
-                if (lead_cta) mbar_arrive_expect_tx(&w_full[iw], static_cast<uint32_t>(nt * w_bytes * S));
-                uint32_t bar = 0;
-                if constexpr (pair) bar = mapa_rank(smem_u32(&w_full[iw]), 0);
+                // every bulk-async instruction costs its issuing thread ~440 cycles whatever its size (measured,
+                // tools/micro/tma_rate.cu): a weight stage is ONE box, not one per tap
+                if (lead_cta) mbar_arrive_expect_tx(&w_full[iw], static_cast<uint32_t>(stage_bytes * S));
                 uint8_t* dst = sW + iw * stage_bytes;
-                for (int j = 0; j < nt; ++j, dst += w_bytes) {
-                  if constexpr (pair)
-                    tma_load_2d_pair(dst, &sg.tmap_w, bar, 0, wrow + j * p.n_tile);
-                  else
-                    tma_load_2d(dst, &sg.tmap_w, &w_full[iw], 0, wrow + j * p.n_tile);
-                }
+                if constexpr (pair)
+                  tma_load_3d_pair(dst, &sg.tmap_w, mapa_rank(smem_u32(&w_full[iw]), 0), 0, static_cast<int>(crank) * w_rows, wtap + tap0);
+                else
+                  tma_load_3d(dst, &sg.tmap_w, &w_full[iw], 0, 0, wtap + tap0);
               }
-              wrow += nt * p.n_tile;
               if (++iw == NW) {
                 iw = 0;
                 pw ^= 1;
               }
             }
+            wtap += taps;
           }
         }
+        if constexpr (EPI == EPI_FWD) epi_fwd_loads<E>(p, sE, e_full, e_empty, walk, base, leader, es, eph);
+        first = false;
       }
     }
   } else if (warp == 1) {
@@ -216,11 +215,13 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
       uint32_t pa = 0, pw = 0;
       int abuf = 0;
       uint32_t aphase = 0;
-      for (int item = first_item; item < items_padded; item += item_stride) {
+      bool first = true;
+      for (int base = walk.first_tile; base < walk.tiles_padded; base += walk.tile_stride) {
         mbar_wait(&tempty_bar[abuf], aphase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(abuf * 256);
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(abuf * p.acc_cols);
         uint32_t accumulate = 0;
+        if (resident) iw = 0;   // stage index = position inside the tile's K walk
         for (int s = 0; s < p.nseg; ++s) {
           const ConvSegment& sg = p.seg[s];
           const int ks = sg.ksize;
@@ -234,9 +235,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
             const int taps = ks * ks;
             int dy = 0, dx = 0;
             for (int tap0 = 0; tap0 < taps; tap0 += TS) {
-              const int nt = (taps - tap0) < TS ? (taps - tap0) : TS;
-              mbar_wait(&w_full[iw], pw);
-              tc_fence_after();
+              const int nt = TS;   // TS divides taps (conv_halo_plan)
+              if (!resident || first) {
+                mbar_wait(&w_full[iw], pw);
+                tc_fence_after();
+              }
               uint64_t bdesc = make_smem_desc_sw64(smem_u32(sW + iw * stage_bytes), 16, 512);
               for (int j = 0; j < nt; ++j, bdesc += static_cast<uint64_t>(w_bytes >> 4)) {
                 // tap (dy, dx): the halo buffer seen through a row-shifted descriptor
@@ -258,7 +261,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
                   ++dy;
                 }
               }
-              if (leader) {
+              if (leader && !resident) {
                 if constexpr (pair) umma_commit_pair(&w_empty[iw]); else umma_commit(&w_empty[iw]);
               }
               if (++iw == NW) {
@@ -278,28 +281,32 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
         if (leader) {
           if constexpr (pair) umma_commit_pair(&tfull_bar[abuf]); else umma_commit(&tfull_bar[abuf]);
         }
-        if (++abuf == 2) {
+        if (++abuf == p.n_acc) {
           abuf = 0;
           aphase ^= 1;
         }
+        first = false;
       }
     }
   } else if (warp == 2) {
     // ------------------------------------------------------------------ epilogue TMA stores
-    if constexpr (EPI != EPI_RAW) epi_storer<E, EPI>(p, sE, st_ready, e_empty, first_item, item_stride, items_padded, G);
+    // forward: warps 2 and 3 both store (alternate channel groups; 3 boxes per group), c_{t-1} is prefetched by
+    // warp 0.  backward: warp 2 stores (2 boxes per group), warp 3 loads (4 boxes per group).
+    if constexpr (EPI == EPI_FWD) epi_storer<E, EPI>(p, sE, st_ready, e_empty, walk, 0, 2);
+    if constexpr (EPI == EPI_BWD) epi_storer<E, EPI>(p, sE, st_ready, e_empty, walk, 0, 1);
   } else if (warp == 3) {
-    // ------------------------------------------------------------------ epilogue TMA loads
-    if constexpr (EPI != EPI_RAW) epi_loader<E, EPI>(p, sE, e_full, e_empty, first_item, item_stride, items_padded, G);
+    if constexpr (EPI == EPI_FWD) epi_storer<E, EPI>(p, sE, st_ready, e_empty, walk, 1, 2);
+    if constexpr (EPI == EPI_BWD) epi_loader<E, EPI>(p, sE, e_full, e_empty, walk);
   } else {
     // ------------------------------------------------------------------ epilogue math (warps 4-11)
     // the epilogue of either CTA releases the accumulator buffer on the LEADER's "tmem empty" barrier
     uint32_t tempty_remote = 0;
     if constexpr (pair) tempty_remote = mapa_rank(smem_u32(&tempty_bar[0]), 0);
     if constexpr (EPI == EPI_RAW)
-      epi_raw(p, warp, lane, tmem_base, tfull_bar, tempty_bar, first_item, item_stride, items_padded, G, tempty_remote);
+      epi_raw(p, warp, lane, tmem_base, tfull_bar, tempty_bar, walk, tempty_remote);
     else
-      epi_math<E, EPI>(p, warp, lane, tmem_base, sE, e_full, st_ready, tfull_bar, tempty_bar, s_bias, s_headw,
-                       first_item, item_stride, items_padded, G, tempty_remote);
+      epi_math<E, EPI>(p, warp, lane, tmem_base, sE, e_full, st_ready, tfull_bar, tempty_bar, s_bias, s_headw, walk,
+                       tempty_remote);
   }
   tc_fence_before();
   __syncthreads();
@@ -335,16 +342,44 @@ int conv_halo_plan(int epi, int dtype, ConvGemmParams& p) {
   if (p.a_halo_bytes == 0) p.a_halo_bytes = 1024;
   const int total = 227 * 1024 - 1024 - kHaloCtrlBytes - (4 * p.hc + p.hc) * 4 - 1024;
   const int w_bytes = (p.n_tile / p.cluster) * kChunkBytes;
+  const int ns_max = epi == EPI_RAW ? 0 : 3, ns_min = epi == EPI_RAW ? 0 : 2;
   int max_k = 1;
   for (int s = 0; s < p.nseg; ++s) if (p.seg[s].ksize > max_k) max_k = p.seg[s].ksize;
-  // tiles per item group: fill one 256-column accumulator buffer, at most 4 (2 for the memory-bound backward
+  // ---- plan A: weights resident.  One stage per (segment, chunk) holding all taps; needs >= 3 halo buffers.
+  if (p.nseg > 0) {
+    int n_st = 0, ts = p.seg[0].ksize * p.seg[0].ksize;
+    bool same_k = true;
+    for (int s = 0; s < p.nseg; ++s) {
+      n_st += p.seg[s].nchunks;
+      same_k = same_k && (p.seg[s].ksize * p.seg[s].ksize == ts);
+    }
+    const long long res_bytes = static_cast<long long>(n_st) * ts * w_bytes;
+    if (same_k && n_st <= kHaloMaxW) {
+      for (int ns = ns_max; ns >= ns_min; --ns) {
+        const long long rem = static_cast<long long>(total) - ns * p.e_stage_bytes - res_bytes;
+        if (rem < 3LL * p.a_halo_bytes) continue;
+        p.w_resident = 1;
+        p.e_stages = ns;
+        p.group = 1;
+        p.a_buf_bytes = p.a_halo_bytes;
+        p.na_bufs = static_cast<int>(rem / p.a_halo_bytes) > 6 ? 6 : static_cast<int>(rem / p.a_halo_bytes);
+        p.taps_per_stage = ts;
+        p.num_stages = n_st;
+        p.acc_cols = p.n_tile;
+        p.n_acc = 512 / p.acc_cols > kMaxAcc ? kMaxAcc : 512 / p.acc_cols;
+        return 0;
+      }
+    }
+  }
+  // ---- plan B: weights stream through a ring of stages.
+  p.w_resident = 0;
+  // tiles per group: fill one 256-column accumulator buffer, at most 4 (2 for the memory-bound backward
   // epilogue, whose stages need the shared memory more than the weight stages need the reuse)
   int gmax = 256 / p.n_tile;
   if (gmax > (epi == EPI_BWD ? 2 : 4)) gmax = (epi == EPI_BWD ? 2 : 4);
-  if (gmax < 1 || p.n_blocks != 1 || p.nseg == 0) gmax = 1;
+  if (gmax < 1 || p.nseg == 0) gmax = 1;
   // three epilogue stages keep loads, math and stores of consecutive channel groups overlapped; fall back
   // to two when the operands would not get 2 halo buffers + 3 single-tap weight stages otherwise
-  const int ns_max = epi == EPI_RAW ? 0 : 3, ns_min = epi == EPI_RAW ? 0 : 2;
   int NS = -1, G = 1;
   for (int ns = ns_max; ns >= ns_min && NS < 0; --ns)
     for (int g = gmax; g >= 1; --g)
@@ -357,6 +392,8 @@ int conv_halo_plan(int epi, int dtype, ConvGemmParams& p) {
   p.e_stages = NS;
   p.group = G;
   p.a_buf_bytes = G * p.a_halo_bytes;
+  p.acc_cols = G * p.n_tile;
+  p.n_acc = 512 / p.acc_cols > kMaxAcc ? kMaxAcc : 512 / p.acc_cols;
   const int budget = total - NS * p.e_stage_bytes;
   // every barrier round trip of the MMA-issuing thread costs a few hundred cycles: group taps so that
   // one weight stage carries plenty of tensor work, keep >= 3 weight stages in flight and spend the rest
@@ -394,13 +431,13 @@ static cudaError_t launch_h(const ConvGemmParams& p, int num_sms, cudaStream_t s
     configured = true;
   }
   constexpr int S = PAIR ? 2 : 1;
-  const int items = p.n_blocks * p.B * p.tiles_x * p.tiles_y;
-  const int groups = (items + S * p.group - 1) / (S * p.group);
-  int clusters = num_sms / S;
-  if (clusters > groups) clusters = groups;
-  if (clusters <= 0) return cudaSuccess;
+  const int tiles = p.B * p.tiles_x * p.tiles_y;
+  const int groups = (tiles + S * p.group - 1) / (S * p.group);
+  int cpn = num_sms / (S * p.n_blocks);   // clusters per n-block
+  if (cpn > groups) cpn = groups;
+  if (cpn <= 0) return cudaErrorInvalidConfiguration;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(clusters * S);
+  cfg.gridDim = dim3(cpn * p.n_blocks * S);
   cfg.blockDim = dim3(kConvThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
@@ -424,7 +461,8 @@ static cudaError_t launch_e(int epi, const ConvGemmParams& p, int num_sms, cudaS
 cudaError_t launch_conv_halo(int epi, int dtype, const ConvGemmParams& p, int num_sms, cudaStream_t stream) {
   if (p.tile_w != 8 || p.tile_h != 16) return cudaErrorInvalidValue;
   if (p.cluster != 1 && p.cluster != 2) return cudaErrorInvalidValue;
-  if (p.cluster == 2 && ((p.n_tile % 32) || p.n_blocks != 1)) return cudaErrorInvalidValue;
+  if (p.cluster == 2 && (p.n_tile % 32)) return cudaErrorInvalidValue;
+  if (p.n_acc < 1 || p.n_acc > kMaxAcc || p.n_acc * p.acc_cols > kTmemCols) return cudaErrorInvalidValue;
   if (epi != EPI_RAW && (p.e_stages < 2 || p.e_stages > kEpiMaxStages)) return cudaErrorInvalidValue;
   if (dtype == NINT_BF16)
     return p.cluster == 2 ? launch_e<__nv_bfloat16, true>(epi, p, num_sms, stream)

@@ -22,19 +22,37 @@ constexpr int kEpiMaxStages = 4;
 constexpr int kEpiBoxBytes16 = kTilePixels * 16 * 4;   // 16 fp32 channels x 128 pixels = 8 KiB
 
 struct ItemCoord {
-  int nb, b, x0, y0;
+  int b, x0, y0;
 };
-__device__ __forceinline__ ItemCoord decode_item(const ConvGemmParams& p, int item) {
+__device__ __forceinline__ ItemCoord decode_tile(const ConvGemmParams& p, int tile) {
   ItemCoord c;
-  c.nb = item % p.n_blocks;
-  int r = item / p.n_blocks;
-  const int tx = r % p.tiles_x;
-  r /= p.tiles_x;
+  const int tx = tile % p.tiles_x;
+  int r = tile / p.tiles_x;
   const int ty = r % p.tiles_y;
-  c.b = r / p.tiles_y;
+  c.b = r / p.tiles_y;   // >= B for the padding tiles of the last group: TMA zero-fills / clips them
   c.x0 = tx * p.tile_w;
   c.y0 = ty * p.tile_h;
   return c;
+}
+
+// Work distribution.  The grid is `cpn * n_blocks` clusters (S = 1 or 2 CTAs each).  A cluster owns ONE
+// n-block (N slice of the gate columns: its weights can stay resident in shared memory) and walks pixel-tile
+// groups; the CTAs of a pair take adjacent groups of G tiles.
+struct TileWalk {
+  int nb, first_tile, tile_stride, tiles_padded, num_tiles;
+};
+__device__ __forceinline__ TileWalk make_walk(const ConvGemmParams& p, int S, int crank) {
+  TileWalk w;
+  const int G = p.group;
+  w.num_tiles = p.B * p.tiles_x * p.tiles_y;
+  const int groups = (w.num_tiles + S * G - 1) / (S * G);
+  const int cpn = static_cast<int>(gridDim.x) / (S * p.n_blocks);
+  const int cid = static_cast<int>(blockIdx.x) / S;
+  w.nb = cid % p.n_blocks;
+  w.first_tile = ((cid / p.n_blocks) * S + crank) * G;
+  w.tile_stride = cpn * S * G;
+  w.tiles_padded = groups * S * G;
+  return w;
 }
 
 // shared-memory address of 16-byte chunk `chunk` of pixel row `row` inside a TMA box with ROWB-byte rows
@@ -127,31 +145,57 @@ __device__ __forceinline__ void sts_gate(uint32_t st, int row, int g, int half, 
 }
 
 // first q-column of the 16-channel group containing hidden channel `ch` (multiple of 16)
-__device__ __forceinline__ int group_q0(int ch, int hcb) {
-  const int nb = ch / hcb, cc = ch - nb * hcb;
-  return nb * 4 * hcb + (cc >> 4) * 64;
-}
+__device__ __forceinline__ int group_q0(int ch) { return (ch >> 4) * 64; }
 
 template <int EPI>
 __device__ __forceinline__ int epi_groups(const ConvGemmParams& p) {
   return (EPI == EPI_FWD ? p.hcb : p.hc) >> 4;
 }
 
-// ------------------------------------------------------------------------------------ loader (warp 3)
+// forward: the operand producer (warp 0) prefetches c_{t-1} of the tile group it has just issued the
+// activation loads for.  `s` / `ph`: epilogue stage ring position (carried across calls).
+template <typename E>
+__device__ __forceinline__ void epi_fwd_loads(const ConvGemmParams& p, uint8_t* sE, uint64_t* e_full, uint64_t* e_empty,
+                                              const TileWalk& w, int base, bool leader, int& s, uint32_t& ph) {
+  const int ngroups = p.hcb >> 4;
+  for (int gi = 0; gi < p.group; ++gi) {
+    const int tile = base + gi;
+    if (tile >= w.num_tiles) break;
+    const ItemCoord c = decode_tile(p, tile);
+    for (int grp = 0; grp < ngroups; ++grp) {
+      mbar_wait(&e_empty[s], ph ^ 1);
+      if (leader) {
+        if (p.slot_c_in >= 0) {
+          mbar_arrive_expect_tx(&e_full[s], kEpiBoxBytes16);
+          tma_load_5d(sE + s * p.e_stage_bytes + p.e_off_c, &p.tm_c, &e_full[s], w.nb * p.hcb + grp * 16, c.x0, c.y0, c.b,
+                      p.slot_c_in);
+        } else {
+          mbar_arrive(&e_full[s]);   // zero state: nothing to read, the stage is only an output buffer
+        }
+      }
+      if (++s == p.e_stages) {
+        s = 0;
+        ph ^= 1;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ loader (backward: warp 3)
 template <typename E, int EPI>
 __device__ __forceinline__ void epi_loader(const ConvGemmParams& p, uint8_t* sE, uint64_t* e_full, uint64_t* e_empty,
-                                           int first_item, int item_stride, int items_padded, int G) {
+                                           const TileWalk& w) {
   using GE = EpiGeom<E>;
   const bool leader = elect_one();
-  const int num_items = p.n_blocks * p.B * p.tiles_x * p.tiles_y;
+  const int G = p.group;
   const int ngroups = epi_groups<EPI>(p);
   int s = 0;
   uint32_t ph = 0;
-  for (int base = first_item; base < items_padded; base += item_stride) {
+  for (int base = w.first_tile; base < w.tiles_padded; base += w.tile_stride) {
     for (int gi = 0; gi < G; ++gi) {
-      const int item = base + gi;
-      if (item >= num_items) break;
-      const ItemCoord c = decode_item(p, item);
+      const int tile = base + gi;
+      if (tile >= w.num_tiles) break;
+      const ItemCoord c = decode_tile(p, tile);
       for (int grp = 0; grp < ngroups; ++grp) {
         mbar_wait(&e_empty[s], ph ^ 1);
         if (leader) {
@@ -160,14 +204,14 @@ __device__ __forceinline__ void epi_loader(const ConvGemmParams& p, uint8_t* sE,
           if constexpr (EPI == EPI_FWD) {
             if (p.slot_c_in >= 0) {
               mbar_arrive_expect_tx(bar, kEpiBoxBytes16);
-              tma_load_5d(st + p.e_off_c, &p.tm_c, bar, c.nb * p.hcb + grp * 16, c.x0, c.y0, c.b, p.slot_c_in);
+              tma_load_5d(st + p.e_off_c, &p.tm_c, bar, w.nb * p.hcb + grp * 16, c.x0, c.y0, c.b, p.slot_c_in);
             } else {
               mbar_arrive(bar);   // zero state: nothing to read, the stage is only an output buffer
             }
           } else {
             const uint32_t bytes = GE::kGateBytes + kEpiBoxBytes16 * (1 + (p.slot_c_prev >= 0) + (p.has_dc_in != 0));
             mbar_arrive_expect_tx(bar, bytes);
-            const int q0 = group_q0(grp * 16, p.hcb);
+            const int q0 = group_q0(grp * 16);
 #pragma unroll
             for (int bx = 0; bx < GE::kGateBoxes; ++bx)
               tma_load_5d(st + bx * GE::kGateBoxBytes, &p.tm_g, bar, q0 + bx * GE::kGateBoxCols, c.x0, c.y0, c.b, p.slot_g);
@@ -186,38 +230,40 @@ __device__ __forceinline__ void epi_loader(const ConvGemmParams& p, uint8_t* sE,
   }
 }
 
-// ------------------------------------------------------------------------------------ storer (warp 2)
+// ------------------------------------------------------------------------------------ storer
+// handles the channel groups whose running index n satisfies n % nwhich == which
 template <typename E, int EPI>
 __device__ __forceinline__ void epi_storer(const ConvGemmParams& p, uint8_t* sE, uint64_t* st_ready, uint64_t* e_empty,
-                                           int first_item, int item_stride, int items_padded, int G) {
+                                           const TileWalk& w, int which, int nwhich) {
   using GE = EpiGeom<E>;
   const bool leader = elect_one();
-  const int num_items = p.n_blocks * p.B * p.tiles_x * p.tiles_y;
+  const int G = p.group;
   const int ngroups = epi_groups<EPI>(p);
-  int s = 0;
+  int s = 0, n = 0;
   uint32_t ph = 0;
-  for (int base = first_item; base < items_padded; base += item_stride) {
+  for (int base = w.first_tile; base < w.tiles_padded; base += w.tile_stride) {
     for (int gi = 0; gi < G; ++gi) {
-      const int item = base + gi;
-      if (item >= num_items) break;
-      const ItemCoord c = decode_item(p, item);
-      for (int grp = 0; grp < ngroups; ++grp) {
-        mbar_wait(&st_ready[s], ph);
-        if (leader) {
+      const int tile = base + gi;
+      if (tile >= w.num_tiles) break;
+      const ItemCoord c = decode_tile(p, tile);
+      for (int grp = 0; grp < ngroups; ++grp, ++n) {
+        const bool mine = (nwhich == 1) || ((n % nwhich) == which);
+        if (mine) mbar_wait(&st_ready[s], ph);
+        if (mine && leader) {
           const uint8_t* st = sE + s * p.e_stage_bytes;
           if (!(p.debug_flags & 1)) {
             if constexpr (EPI == EPI_FWD) {
-              const int ch = c.nb * p.hcb + grp * 16;
+              const int ch = w.nb * p.hcb + grp * 16;
               tma_store_5d(&p.tm_c, st + p.e_off_c, ch, c.x0, c.y0, c.b, p.slot_c_out);
               tma_store_5d(&p.tm_h, st + p.e_off_h, ch, c.x0, c.y0, c.b, p.slot_h_out);
               if (p.slot_g >= 0) {
-                const int q0 = group_q0(ch, p.hcb);
+                const int q0 = group_q0(ch);
 #pragma unroll
                 for (int bx = 0; bx < GE::kGateBoxes; ++bx)
                   tma_store_5d(&p.tm_g, st + bx * GE::kGateBoxBytes, q0 + bx * GE::kGateBoxCols, c.x0, c.y0, c.b, p.slot_g);
               }
             } else {
-              const int q0 = group_q0(grp * 16, p.hcb);
+              const int q0 = group_q0(grp * 16);
 #pragma unroll
               for (int bx = 0; bx < GE::kGateBoxes; ++bx)
                 tma_store_5d(&p.tm_g, st + bx * GE::kGateBoxBytes, q0 + bx * GE::kGateBoxCols, c.x0, c.y0, c.b, p.slot_g);
@@ -244,12 +290,12 @@ __device__ __forceinline__ void epi_storer(const ConvGemmParams& p, uint8_t* sE,
 template <typename E, int EPI>
 __device__ __forceinline__ void epi_math(const ConvGemmParams& p, int warp, int lane, uint32_t tmem_base, uint8_t* sE,
                                          uint64_t* e_full, uint64_t* st_ready, uint64_t* tfull_bar, uint64_t* tempty_bar,
-                                         const float* s_bias, const float* s_headw, int first_item, int item_stride,
-                                         int items_padded, int G, uint32_t tempty_remote) {
+                                         const float* s_bias, const float* s_headw, const TileWalk& w,
+                                         uint32_t tempty_remote) {
   using GE = EpiGeom<E>;
   constexpr int DT = ElemTraits<E>::kDtype;
   constexpr bool FAST = (DT == NINT_BF16);
-  const int num_items = p.n_blocks * p.B * p.tiles_x * p.tiles_y;
+  const int G = p.group;
   const int ngroups = epi_groups<EPI>(p);
   const int quad = warp & 3;
   const int half = (warp - 4) >> 2;
@@ -259,14 +305,14 @@ __device__ __forceinline__ void epi_math(const ConvGemmParams& p, int warp, int 
   uint32_t ph = 0;
   int abuf = 0;
   uint32_t aphase = 0;
-  for (int base = first_item; base < items_padded; base += item_stride) {
+  for (int base = w.first_tile; base < w.tiles_padded; base += w.tile_stride) {
     bool waited = (p.nseg == 0);
     for (int gi = 0; gi < G; ++gi) {
-      const int item = base + gi;
-      if (item >= num_items) break;
-      const ItemCoord c = decode_item(p, item);
+      const int tile = base + gi;
+      if (tile >= w.num_tiles) break;
+      const ItemCoord c = decode_tile(p, tile);
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
-                             static_cast<uint32_t>(abuf * 256 + gi * p.n_tile);
+                             static_cast<uint32_t>(abuf * p.acc_cols + gi * p.n_tile);
       float dpred = 0.f;
       if constexpr (EPI == EPI_BWD) {
         if (p.head_dpred) {
@@ -294,7 +340,7 @@ __device__ __forceinline__ void epi_math(const ConvGemmParams& p, int warp, int 
 #pragma unroll
             for (int j = 0; j < 8; ++j) cn[j] = 0.f;
           }
-          const uint32_t bq = smem_u32(s_bias + c.nb * p.n_tile + grp * 64 + half * 8);
+          const uint32_t bq = smem_u32(s_bias + w.nb * p.n_tile + grp * 64 + half * 8);
           tmem_ld_wait();
           if (!skip) {
 #pragma unroll
@@ -413,7 +459,7 @@ __device__ __forceinline__ void epi_math(const ConvGemmParams& p, int warp, int 
         // pair mode: the MMA issuer lives in the leader CTA and waits for the epilogue warps of both CTAs
         if (tempty_remote) mbar_arrive_cluster(tempty_remote + abuf * 8); else mbar_arrive(&tempty_bar[abuf]);
       }
-      if (++abuf == 2) {
+      if (++abuf == p.n_acc) {
         abuf = 0;
         aphase ^= 1;
       }
@@ -423,27 +469,27 @@ __device__ __forceinline__ void epi_math(const ConvGemmParams& p, int warp, int 
 
 // debug epilogue: dump the fp32 accumulators [B,H,W,n_blocks*n_tile] (nint_debug_raw_gates)
 __device__ __forceinline__ void epi_raw(const ConvGemmParams& p, int warp, int lane, uint32_t tmem_base,
-                                        uint64_t* tfull_bar, uint64_t* tempty_bar, int first_item, int item_stride,
-                                        int items_padded, int G, uint32_t tempty_remote) {
-  const int num_items = p.n_blocks * p.B * p.tiles_x * p.tiles_y;
+                                        uint64_t* tfull_bar, uint64_t* tempty_bar, const TileWalk& w,
+                                        uint32_t tempty_remote) {
+  const int G = p.group;
   const int quad = warp & 3;
   const int half = (warp - 4) >> 2;
   const int row = quad * 32 + lane;
   int abuf = 0;
   uint32_t aphase = 0;
-  for (int base = first_item; base < items_padded; base += item_stride) {
+  for (int base = w.first_tile; base < w.tiles_padded; base += w.tile_stride) {
     mbar_wait(&tfull_bar[abuf], aphase);
     tc_fence_after();
     for (int gi = 0; gi < G; ++gi) {
-      const int item = base + gi;
-      if (item >= num_items) break;
-      const ItemCoord c = decode_item(p, item);
+      const int tile = base + gi;
+      if (tile >= w.num_tiles) break;
+      const ItemCoord c = decode_tile(p, tile);
       const int y = c.y0 + (row >> 3), x = c.x0 + (row & 7);
       const bool valid = y < p.H && x < p.W;
       const long long pix = (static_cast<long long>(c.b) * p.H + y) * p.W + x;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
-                             static_cast<uint32_t>(abuf * 256 + gi * p.n_tile);
-      float* ro = p.raw_out + pix * (p.n_blocks * p.n_tile) + c.nb * p.n_tile;
+                             static_cast<uint32_t>(abuf * p.acc_cols + gi * p.n_tile);
+      float* ro = p.raw_out + pix * (p.n_blocks * p.n_tile) + w.nb * p.n_tile;
       for (int c0 = half * 16; c0 < p.n_tile; c0 += 32) {
         float v[16];
         tmem_ld16(taddr + c0, v);
@@ -456,7 +502,7 @@ __device__ __forceinline__ void epi_raw(const ConvGemmParams& p, int warp, int l
     if (lane == 0) {
       if (tempty_remote) mbar_arrive_cluster(tempty_remote + abuf * 8); else mbar_arrive(&tempty_bar[abuf]);
     }
-    if (++abuf == 2) {
+    if (++abuf == p.n_acc) {
       abuf = 0;
       aphase ^= 1;
     }

@@ -5,11 +5,11 @@
 //     tf32-rounded values), C_pad a multiple of 32 channels; the conv kernels walk K in 64-byte
 //     chunks (32 bf16 / 16 tf32 elements), wgrad in 32-channel panels;
 //   * a pixel tile is tile_w x tile_h <= 128 pixels of one image, row = ty * tile_w + tx;
-//   * the 4*hc gate channels of a layer are stored in "q-order": with hcb = min(hc, 64), n_blocks = hc / hcb
-//     and cc = 16*grp + c16 the channel inside its n-block,
-//       q = nb * 4*hcb + grp * 64 + gate * 16 + c16  <->  reference channel n = gate * hc + nb * hcb + cc
+//   * the 4*hc gate channels of a layer are stored in "q-order": hidden channel c = 16*grp + c16,
+//       q = grp * 64 + gate * 16 + c16  <->  reference channel n = gate * hc + c
 //     (gate order i,f,g,o: model.py:221): the four gates of a 16-channel group are 64 contiguous columns,
-//     i.e. one 128-byte (bf16) TMA box row per pixel for the epilogue and one tcgen05.ld-friendly span.
+//     i.e. one 128-byte (bf16) TMA box row per pixel for the epilogue, and any multiple of 16 hidden
+//     channels is a contiguous N slice (n-block) of the forward GEMM.
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -21,15 +21,15 @@ enum : int { EPI_FWD = 0, EPI_BWD = 1, EPI_RAW = 2 };
 
 // One K-segment of an implicit-GEMM convolution: an activation tensor read through a 5-D TMA
 // map (box = one chunk x tile_w x tile_h pixels; out-of-image pixels are zero-filled by TMA =
-// the conv's zero padding, model.py:204-211) and its packed weights read through a 2-D map
-// [(nb*nchunks + chunk)*taps + tap][n_tile rows][chunk elements].
+// the conv's zero padding, model.py:204-211) and its packed weights read through a 3-D map
+// [(nb*nchunks + chunk)*taps + tap][n_tile rows][chunk elements] (box = this CTA's rows of one weight stage).
 struct alignas(64) ConvSegment {
   CUtensorMap tmap_act;
   CUtensorMap tmap_w;
   int slot;
   int ksize;
   int nchunks;
-  int reserved;
+  int wsel;   // host only: which packed weight tensor of the layer (nint_api.cu get_w_map)
 };
 
 struct alignas(64) ConvGemmParams {
@@ -38,12 +38,14 @@ struct alignas(64) ConvGemmParams {
   int B, H, W;
   int tile_w, tile_h;
   int tiles_x, tiles_y;
-  int n_tile;    // UMMA N (accumulator columns per item)
-  int n_blocks;  // N blocks per pixel tile (forward with hidden > 64)
+  int n_tile;    // UMMA N (accumulator columns per tile)
+  int n_blocks;  // N slices of the gate columns (forward: 4*hc / n_tile); a cluster owns one slice
   int num_stages;
   // halo variant (nint_conv_halo.cu): activation buffers, cluster size, descriptor base-offset policy
   int na_bufs, a_buf_bytes, cluster, base_offset_mode, taps_per_stage;
-  int group, a_halo_bytes;  // tiles per item group (side-by-side accumulators), bytes of one halo chunk
+  int group, a_halo_bytes;  // tiles per group (side-by-side accumulators), bytes of one halo chunk
+  int acc_cols, n_acc;      // TMEM columns of one accumulator buffer (group * n_tile), number of buffers (2 or 4)
+  int w_resident;           // 1: num_stages covers a tile's whole K walk; weights are loaded once per CTA
   int debug_flags;          // experiments: 1 = epilogue does no memory ops / math, 2 = no MMA issue
   // ---- TMA-staged epilogue I/O (nint_epilogue.cuh): 5-D maps (channel, x, y, image, slot) of the layer's
   // c history (fp32), h history (E), saved gates (E, q-order) and running dc (fp32); slot < 0 = absent
@@ -53,7 +55,7 @@ struct alignas(64) ConvGemmParams {
   int e_stages, e_stage_bytes, e_off_c, e_off_c2, e_off_dc, e_off_h;
   uint32_t idesc;
   int hc, hc_pad;  // hidden channels of this layer / padded channel count of its h tensor
-  int hcb;         // min(hc, 64)
+  int hcb;         // hidden channels per n-block (n_tile / 4)
   // ---- EPI_FWD: LSTM cell update (model.py:221-229)
   const float* bias_q;  // [4*hc], q-order
   // ---- EPI_BWD: gate backward; accumulator = dh (absent when nseg == 0); dgates overwrite
@@ -114,7 +116,7 @@ cudaError_t launch_nchw_to_nhwc_f32(const float* src, float* dst, int B, int C, 
 cudaError_t launch_nhwc_to_nchw_f32(const float* src, float* dst, int B, int C, int H, int W, cudaStream_t s);
 // OIHW fp32 master weights -> packed operand panels
 cudaError_t launch_pack_weights_fwd(int dtype, const float* w, const float* bias, void* wpack_x, void* wpack_h,
-                                    float* bias_q, int cin, int hc, int k, int cx_pad, int hc_pad, cudaStream_t s);
+                                    float* bias_q, int cin, int hc, int hcb, int k, int cx_pad, int hc_pad, cudaStream_t s);
 cudaError_t launch_pack_weights_bwd(int dtype, const float* w, void* wpack_dx, void* wpack_dh, int cin, int hc,
                                     int k, cudaStream_t s);
 // 1x1 head (model.py:251,274)
@@ -126,13 +128,7 @@ cudaError_t launch_head_bwd(int dtype, const void* h, const float* dpred, long l
 cudaError_t launch_unpack_wgrad(const float* dw_acc, const float* db_acc, float* gw, float* gb, int cin, int hc,
                                 int k, int ncols, int cx_pad, int accumulate, cudaStream_t s);
 
-// q-order helpers (host + device)
-__host__ __device__ inline int hcb_of(int hc) { return hc < 64 ? hc : 64; }
-__host__ __device__ inline int q_to_n(int q, int hc) {
-  const int hcb = hcb_of(hc);
-  const int nb = q / (4 * hcb), r = q % (4 * hcb);
-  const int grp = r >> 6, gate = (r >> 4) & 3, c16 = r & 15;
-  return gate * hc + nb * hcb + grp * 16 + c16;
-}
+// q-order helper (host + device)
+__host__ __device__ inline int q_to_n(int q, int hc) { return ((q >> 4) & 3) * hc + (q >> 6) * 16 + (q & 15); }
 
 }  // namespace nint

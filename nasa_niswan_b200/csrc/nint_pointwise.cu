@@ -196,10 +196,10 @@ cudaError_t launch_nhwc_to_nchw_f32(const float* src, float* dst, int B, int C, 
 // ------------------------------------------------------------------------------------------
 template <typename E>
 __global__ void pack_w_fwd_kernel(const float* __restrict__ w, const float* __restrict__ bias, E* __restrict__ wx,
-                                  E* __restrict__ wh, float* __restrict__ bias_q, int cin, int hc, int k, int cx_pad,
-                                  int hc_pad) {
+                                  E* __restrict__ wh, float* __restrict__ bias_q, int cin, int hc, int hcb, int k,
+                                  int cx_pad, int hc_pad) {
   constexpr int CE = ElemTraits<E>::kPerChunk;
-  const int hcb = hcb_of(hc), n_blocks = hc / hcb, n_tile = 4 * hcb, taps = k * k;
+  const int n_blocks = hc / hcb, n_tile = 4 * hcb, taps = k * k;
   const int ctot = cin + hc;
   const int chx = cx_pad / CE, chh = hc_pad / CE;
   const long long nx = static_cast<long long>(n_blocks) * taps * chx * n_tile * CE;
@@ -251,14 +251,14 @@ __global__ void pack_w_bwd_kernel(const float* __restrict__ w, E* __restrict__ w
 }
 
 cudaError_t launch_pack_weights_fwd(int dtype, const float* w, const float* bias, void* wx, void* wh, float* bias_q,
-                                    int cin, int hc, int k, int cx_pad, int hc_pad, cudaStream_t s) {
+                                    int cin, int hc, int hcb, int k, int cx_pad, int hc_pad, cudaStream_t s) {
   if (dtype == NINT_BF16)
     pack_w_fwd_kernel<__nv_bfloat16><<<296, 256, 0, s>>>(w, bias, reinterpret_cast<__nv_bfloat16*>(wx),
-                                                         reinterpret_cast<__nv_bfloat16*>(wh), bias_q, cin, hc, k,
+                                                         reinterpret_cast<__nv_bfloat16*>(wh), bias_q, cin, hc, hcb, k,
                                                          cx_pad, hc_pad);
   else
     pack_w_fwd_kernel<float><<<296, 256, 0, s>>>(w, bias, reinterpret_cast<float*>(wx), reinterpret_cast<float*>(wh),
-                                                 bias_q, cin, hc, k, cx_pad, hc_pad);
+                                                 bias_q, cin, hc, hcb, k, cx_pad, hc_pad);
   return cudaGetLastError();
 }
 cudaError_t launch_pack_weights_bwd(int dtype, const float* w, void* wdx, void* wdh, int cin, int hc, int k,

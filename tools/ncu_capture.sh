@@ -14,10 +14,10 @@ ncu --metrics gpu__time_duration.sum --clock-control none -s 100 -c 120 --csv \
 echo "launch list rc=$?"
 fi
 # full captures: forward conv at t>=1 (launch 73 = 3 warm-up steps * 24 conv launches + t=1), a backward conv, wgrad
-ncu --set full --clock-control none --import-source on -k 'regex:^conv_(gemm|halo)_kernel' -s 73 -c 1 \
+ncu --set full --clock-control none --import-source on -k 'regex:conv_halo_kernel' -s 73 -c 1 \
     -o gpurun_out/prof_fwd_$TAG -f $CMD > gpurun_out/ncu_fwd_$TAG.log 2>&1
 echo "fwd capture rc=$?"
-ncu --set full --clock-control none --import-source on -k 'regex:^conv_(gemm|halo)_kernel' -s 86 -c 1 \
+ncu --set full --clock-control none --import-source on -k 'regex:conv_halo_kernel' -s 86 -c 1 \
     -o gpurun_out/prof_bwd_$TAG -f $CMD > gpurun_out/ncu_bwd_$TAG.log 2>&1
 echo "bwd capture rc=$?"
 ncu --set full --clock-control none --import-source on -k 'regex:^wgrad_kernel' -s 3 -c 1 \
