@@ -91,6 +91,9 @@ int nint_plan_profile_read(nint_plan* plan, double* ms, long long* count);
 /* ---- test hook: raw gate pre-activations of layer 0 at t = 0 without bias,
  * out [B,H,W,4*Hc] fp32 in kernel column order (see nint_gate_column). */
 int nint_debug_raw_gates(nint_plan* plan, const float* x, float* out, void* stream);
+/* debug timeline: with NINT_DEBUG_FLAGS & 8, CTA 0 of every conv launch records clock64() stamps per warp role
+ * (8 roles x 1024 stamps; later launches overwrite earlier ones).  Copies them to `host`, optionally clears. */
+int nint_debug_read_trace(long long* host, int n, int clear);
 /* reference gate channel n = gate*Hc + c for kernel column q of a layer with Hc hidden channels */
 int nint_gate_column(int q, int hidden);
 /* pixel tile chosen for a grid (host-only helper, no device needed) */

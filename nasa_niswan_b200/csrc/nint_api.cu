@@ -606,6 +606,14 @@ int nint_forward(nint_plan* p, const float* x, float* pred, float* seq, void* st
   return 0;
 }
 
+int nint_debug_read_trace(long long* host, int n, int clear) {
+  if (!host || n < 0) return fail("nint_debug_read_trace: bad arguments");
+  CK(cudaDeviceSynchronize());
+  CK(read_trace(host, n));
+  if (clear) CK(clear_trace());
+  return 0;
+}
+
 int nint_debug_raw_gates(nint_plan* p, const float* x, float* out, void* stream) {
   if (check_ready(p)) return 1;
   if (!x || !out) return fail("nint_debug_raw_gates: null argument");

@@ -21,8 +21,8 @@
 // Item groups: G consecutive tiles (G * n_tile <= 256 columns) are accumulated side by side in one
 // TMEM buffer and share every weight stage.
 //
-// Warp roles: warp 0 operand TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator + epilogue TMA stores,
-// warp 3 epilogue TMA loads, warps 4-11 epilogue math (nint_epilogue.cuh).
+// Warp roles (16 warps): 0 / 7 activation TMA producers, 6 weight TMA producer, 1 MMA issuer, 2 / 3 epilogue TMA
+// stores (2 also allocates TMEM), 4 / 5 epilogue TMA loads, 8-15 epilogue math (nint_epilogue.cuh).
 #include "nint_epilogue.cuh"
 
 namespace nint {
@@ -39,7 +39,7 @@ static inline int halo_a_buf_bytes(const ConvGemmParams& p) {
     const int b = halo_rows(p.seg[s].ksize) * kChunkBytes;
     if (b > m) m = b;
   }
-  return (m + 1023) & ~1023;
+  return (m + 511) & ~511;   // SWIZZLE_64B atoms are 512 bytes: halo buffers only need that alignment
 }
 
 static int halo_operand_bytes(int a_buf_bytes, int na, int n_tile, int nw, int ts, int cluster) {
@@ -60,7 +60,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
   constexpr int CE = ElemTraits<E>::kPerChunk;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int warp = threadIdx.x >> 5;
+  // broadcast from lane 0: tells the compiler these are warp-uniform, so role loops and descriptor
+  // arithmetic live in uniform registers instead of per-thread registers + R2UR moves
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   constexpr int S = PAIR ? 2 : 1;               // 1: single CTA, 2: CTA pair (cta_group::2)
   constexpr bool pair = PAIR;
@@ -86,7 +88,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
   float* s_headw = s_bias + 4 * p.hc;
 
   uint32_t crank = 0;
-  if constexpr (pair) crank = cluster_ctarank();
+  if constexpr (pair) crank = __shfl_sync(0xffffffffu, cluster_ctarank(), 0);
   const bool lead_cta = crank == 0;
   // work unit of a CTA iteration = G consecutive tiles ("tile group") accumulated side by side in one
   // TMEM buffer and sharing every weight stage; the two CTAs of a pair take adjacent groups
@@ -143,27 +145,32 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
   __syncthreads();
   if constexpr (pair) cluster_sync_all();   // the peer's barriers are initialised before anyone signals them
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
-  if (warp == 0) {
-    // ------------------------------------------------------------------ operand TMA producer (both CTAs)
-    if (p.nseg > 0) {
-      const bool leader = elect_one();
-      int ia = 0, iw = 0;
-      uint32_t pa = 0, pw = 0;
-      int es = 0;          // epilogue stage ring (forward: this warp also prefetches c_{t-1})
-      uint32_t eph = 0;
-      bool first = true;
-      for (int base = walk.first_tile; base < walk.tiles_padded; base += walk.tile_stride) {
-        for (int s = 0; s < p.nseg; ++s) {
-          const ConvSegment& sg = p.seg[s];
-          const int pad = sg.ksize >> 1;
-          const int taps = sg.ksize * sg.ksize;
-          const uint32_t a_bytes = static_cast<uint32_t>(halo_rows(sg.ksize) * kChunkBytes);
-          // weights: 3-D map (element, row of the N tile, chunk-tap index); one box = this CTA's rows of TS taps
-          int wtap = (walk.nb * sg.nchunks) * taps;
-          for (int ch = 0; ch < sg.nchunks; ++ch) {
+  // ------------------------------------------------------------------ operand TMA producers (both CTAs)
+  // Every bulk-async instruction keeps its issuing warp busy for ~440-750 cycles whatever its size, and the
+  // cost is per warp, not per SM (tools/micro/tma_rate.cu): the loads are spread over several warps.
+  //   a_par / a_npar: this warp issues the activation chunks whose running index c satisfies c % a_npar == a_par
+  //   do_w: this warp issues the weight stages
+  auto produce = [&](bool do_a, int a_par, int a_npar, bool do_w) {
+    const bool leader = elect_one();
+    Tracer tr(p, do_w ? 5 : 0, leader && (do_w || a_par == 0));
+    int ia = 0, iw = 0, cc = 0;
+    uint32_t pa = 0, pw = 0;
+    bool first = true;
+    for (int base = walk.first_tile; base < walk.tiles_padded; base += walk.tile_stride) {
+      for (int s = 0; s < p.nseg; ++s) {
+        const ConvSegment& sg = p.seg[s];
+        const int pad = sg.ksize >> 1;
+        const int taps = sg.ksize * sg.ksize;
+        const uint32_t a_bytes = static_cast<uint32_t>(halo_rows(sg.ksize) * kChunkBytes);
+        // weights: 3-D map (element, row of the N tile, chunk-tap index); one box = this CTA's rows of TS taps
+        int wtap = (walk.nb * sg.nchunks) * taps;
+        for (int ch = 0; ch < sg.nchunks; ++ch, ++cc, wtap += taps) {
+          if (do_a && (a_npar == 1 || (cc % a_npar) == a_par)) {
+            tr.stamp();
             mbar_wait(&a_empty[ia], pa ^ 1);
+            tr.stamp();
             if (leader) {
               // "full" barriers live in the leader CTA and count the bytes of both CTAs' loads
               if (lead_cta) mbar_arrive_expect_tx(&a_full[ia], a_bytes * G * S);
@@ -178,126 +185,200 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
                   tma_load_5d(dst, &sg.tmap_act, &a_full[ia], ch * CE, cg.x0 - pad, cg.y0 - pad, cg.b, sg.slot);
               }
             }
-            if (++ia == NA) {
-              ia = 0;
-              pa ^= 1;
+            tr.stamp();
+          }
+          if (++ia == NA) {
+            ia = 0;
+            pa ^= 1;
+          }
+          if (!do_w || (resident && !first)) continue;   // resident weights are loaded once
+          for (int tap0 = 0; tap0 < taps; tap0 += TS) {   // TS divides taps (conv_halo_plan)
+            if (!resident) mbar_wait(&w_empty[iw], pw ^ 1);
+            if (leader) {
+              if (lead_cta) mbar_arrive_expect_tx(&w_full[iw], static_cast<uint32_t>(stage_bytes * S));
+              uint8_t* dst = sW + iw * stage_bytes;   // a weight stage is ONE box (all TS taps)
+              if constexpr (pair)
+                tma_load_3d_pair(dst, &sg.tmap_w, mapa_rank(smem_u32(&w_full[iw]), 0), 0, static_cast<int>(crank) * w_rows, wtap + tap0);
+              else
+                tma_load_3d(dst, &sg.tmap_w, &w_full[iw], 0, 0, wtap + tap0);
             }
-            if (resident && !first) continue;   // weights already in shared memory
-            for (int tap0 = 0; tap0 < taps; tap0 += TS) {   // TS divides taps (conv_halo_plan)
-              if (!resident) mbar_wait(&w_empty[iw], pw ^ 1);
-              if (leader) {
-                // every bulk-async instruction costs its issuing thread ~440 cycles whatever its size (measured,
-                // tools/micro/tma_rate.cu): a weight stage is ONE box, not one per tap
-                if (lead_cta) mbar_arrive_expect_tx(&w_full[iw], static_cast<uint32_t>(stage_bytes * S));
-                uint8_t* dst = sW + iw * stage_bytes;
-                if constexpr (pair)
-                  tma_load_3d_pair(dst, &sg.tmap_w, mapa_rank(smem_u32(&w_full[iw]), 0), 0, static_cast<int>(crank) * w_rows, wtap + tap0);
-                else
-                  tma_load_3d(dst, &sg.tmap_w, &w_full[iw], 0, 0, wtap + tap0);
-              }
-              if (++iw == NW) {
-                iw = 0;
-                pw ^= 1;
-              }
+            if (++iw == NW) {
+              iw = 0;
+              pw ^= 1;
             }
-            wtap += taps;
           }
         }
-        if constexpr (EPI == EPI_FWD) epi_fwd_loads<E>(p, sE, e_full, e_empty, walk, base, leader, es, eph);
-        first = false;
       }
+      first = false;
     }
+  };
+  // two activation producers when a tile needs many chunk loads (dgrad: K = 4*hc channels, G tiles per chunk)
+  const bool a_split = (EPI == EPI_BWD);
+
+  if (warp == 0) {
+    if (p.nseg > 0) produce(true, 0, a_split ? 2 : 1, false);
+  } else if (warp == 7) {
+    if (p.nseg > 0 && a_split) produce(true, 1, 2, false);
+  } else if (warp == 6) {
+    if (p.nseg > 0) produce(false, 0, 1, true);
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    // The loop body between two tcgen05.mma must stay a handful of uniform-datapath instructions: every kernel
+    // parameter it needs is hoisted into a local, descriptors advance by adds (timeline traces showed ~190
+    // cycles per MMA of pure issue overhead before, against 64-cycle MMAs).
     if (p.nseg > 0 && lead_cta) {
       const bool leader = elect_one();
+      Tracer tr(p, 1, leader);
+      const bool issue_any = !(p.debug_flags & 2);
+      const int n_acc = p.n_acc, acc_cols = p.acc_cols, nseg = p.nseg, a_buf_bytes = p.a_buf_bytes;
+      const uint32_t idesc = p.idesc;
+      const uint32_t n_tile = static_cast<uint32_t>(p.n_tile);
+      const uint64_t a_halo16 = static_cast<uint64_t>(p.a_halo_bytes >> 4);
+      const uint64_t w16 = static_cast<uint64_t>(w_bytes >> 4);
+      const uint32_t sA_addr = smem_u32(sA), sW_addr = smem_u32(sW);
+      // The K walk of all tiles is one flat sequence of activation chunks.  Barrier round trips cost ~100 cycles
+      // each and the tensor pipe's instruction queue is shallow, so the readiness of the NEXT chunk (and of the
+      // next tile's accumulator) is awaited before the current chunk's MMAs are issued: between the last MMA of
+      // one chunk and the first of the next there is only the tcgen05.commit.
+      int cbase = walk.first_tile, cs = 0, cch = 0;
+      bool valid = cbase < walk.tiles_padded;
       int ia = 0, iw = 0;
       uint32_t pa = 0, pw = 0;
       int abuf = 0;
       uint32_t aphase = 0;
       bool first = true;
-      for (int base = walk.first_tile; base < walk.tiles_padded; base += walk.tile_stride) {
+      // with fewer than 3 halo buffers the next chunk cannot be in flight while the current one is consumed:
+      // then each chunk is awaited just before its own MMAs
+      const bool lookahead = NA >= 3;
+      if (valid && lookahead) {
         mbar_wait(&tempty_bar[abuf], aphase ^ 1);
+        mbar_wait(&a_full[ia], pa);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(abuf * p.acc_cols);
-        uint32_t accumulate = 0;
-        if (resident) iw = 0;   // stage index = position inside the tile's K walk
-        for (int s = 0; s < p.nseg; ++s) {
-          const ConvSegment& sg = p.seg[s];
-          const int ks = sg.ksize;
-          const int hw = 8 + (ks & ~1);            // halo row pitch in pixels
-          const uint32_t sbo = static_cast<uint32_t>(hw * kChunkBytes);
-          for (int ch = 0; ch < sg.nchunks; ++ch) {
-            mbar_wait(&a_full[ia], pa);
-            tc_fence_after();
-            // descriptors advance by plain adds on the 16-byte-granular start-address field
-            const uint64_t adesc0 = make_smem_desc_sw64(smem_u32(sA + ia * p.a_buf_bytes), 16, sbo);
-            const int taps = ks * ks;
-            int dy = 0, dx = 0;
-            for (int tap0 = 0; tap0 < taps; tap0 += TS) {
-              const int nt = TS;   // TS divides taps (conv_halo_plan)
-              if (!resident || first) {
-                mbar_wait(&w_full[iw], pw);
-                tc_fence_after();
-              }
-              uint64_t bdesc = make_smem_desc_sw64(smem_u32(sW + iw * stage_bytes), 16, 512);
-              for (int j = 0; j < nt; ++j, bdesc += static_cast<uint64_t>(w_bytes >> 4)) {
-                // tap (dy, dx): the halo buffer seen through a row-shifted descriptor
-                uint64_t adesc = adesc0 + static_cast<uint64_t>((dy * hw + dx) * (kChunkBytes >> 4));
-                if (leader && !(p.debug_flags & 2)) {
-                  for (int g = 0; g < G; ++g, adesc += static_cast<uint64_t>(p.a_halo_bytes >> 4)) {
-                    if constexpr (pair) {
-                      umma_pair<DT>(d_tmem + g * p.n_tile, adesc, bdesc, p.idesc, accumulate);
-                      umma_pair<DT>(d_tmem + g * p.n_tile, adesc + 2, bdesc + 2, p.idesc, 1u);
-                    } else {
-                      umma<DT>(d_tmem + g * p.n_tile, adesc, bdesc, p.idesc, accumulate);
-                      umma<DT>(d_tmem + g * p.n_tile, adesc + 2, bdesc + 2, p.idesc, 1u);
-                    }
-                  }
-                }
-                accumulate = 1;
-                if (++dx == ks) {
-                  dx = 0;
-                  ++dy;
-                }
-              }
-              if (leader && !resident) {
-                if constexpr (pair) umma_commit_pair(&w_empty[iw]); else umma_commit(&w_empty[iw]);
-              }
-              if (++iw == NW) {
-                iw = 0;
-                pw ^= 1;
-              }
-            }
-            if (leader) {
-              if constexpr (pair) umma_commit_pair(&a_empty[ia]); else umma_commit(&a_empty[ia]);
-            }
-            if (++ia == NA) {
-              ia = 0;
-              pa ^= 1;
-            }
+      }
+      while (valid) {
+        // ---- successor of the current chunk
+        int nbase = cbase, ns = cs, nch = cch + 1;
+        if (nch == p.seg[cs].nchunks) {
+          nch = 0;
+          if (++ns == nseg) {
+            ns = 0;
+            nbase += walk.tile_stride;
           }
         }
-        if (leader) {
-          if constexpr (pair) umma_commit_pair(&tfull_bar[abuf]); else umma_commit(&tfull_bar[abuf]);
+        const bool nvalid = nbase < walk.tiles_padded;
+        const bool last_of_tile = nbase != cbase;
+        const int nia = (ia + 1 == NA) ? 0 : ia + 1;
+        const uint32_t npa = (ia + 1 == NA) ? pa ^ 1 : pa;
+        int nabuf = abuf;
+        uint32_t naphase = aphase;
+        if (last_of_tile && ++nabuf == n_acc) {
+          nabuf = 0;
+          naphase ^= 1;
         }
-        if (++abuf == p.n_acc) {
-          abuf = 0;
-          aphase ^= 1;
+        tr.stamp();
+        if (lookahead) {
+          if (nvalid) {
+            if (last_of_tile) mbar_wait(&tempty_bar[nabuf], naphase ^ 1);
+            mbar_wait(&a_full[nia], npa);
+            tc_fence_after();
+          }
+        } else {
+          if ((cs | cch) == 0) mbar_wait(&tempty_bar[abuf], aphase ^ 1);
+          mbar_wait(&a_full[ia], pa);
+          tc_fence_after();
         }
-        first = false;
+        tr.stamp();
+        // ---- issue the current chunk
+        const int ks = p.seg[cs].ksize;
+        const int hw = 8 + (ks & ~1);            // halo row pitch in pixels
+        const uint32_t sbo = static_cast<uint32_t>(hw * kChunkBytes);
+        const int taps = ks * ks;
+        const uint64_t row_skip = static_cast<uint64_t>((hw - ks) * (kChunkBytes >> 4));
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(abuf * acc_cols);
+        uint32_t accumulate = (cs | cch) != 0 ? 1u : 0u;
+        if (resident && (cs | cch) == 0) iw = 0;   // stage index = position inside the tile's K walk
+        // tap (dy, dx) = the halo buffer seen through a row-shifted descriptor: start address advances by one
+        // pixel (64 B) per tap and skips the rest of the halo row when dx wraps
+        uint64_t adesc = make_smem_desc_sw64(sA_addr + ia * a_buf_bytes, 16, sbo);
+        int dx = 0;
+        for (int tap0 = 0; tap0 < taps; tap0 += TS) {
+          if (!resident || first) {
+            mbar_wait(&w_full[iw], pw);
+            tc_fence_after();
+          }
+          const uint64_t bdesc = make_smem_desc_sw64(sW_addr + iw * stage_bytes, 16, 512);
+          if (leader && issue_any) {
+            // single-lane region: the tcgen05.mma stream of one weight stage.  Only the low descriptor words move.
+            uint32_t alo = static_cast<uint32_t>(adesc), blo = static_cast<uint32_t>(bdesc);
+            const uint32_t ahi = static_cast<uint32_t>(adesc >> 32), bhi = static_cast<uint32_t>(bdesc >> 32);
+            const uint32_t w16l = static_cast<uint32_t>(w16), skipl = static_cast<uint32_t>(row_skip);
+            int dxl = dx;
+            if (G == 1) {
+#pragma unroll 3
+              for (int j = 0; j < TS; ++j) {
+                umma_lohi<DT, pair>(d_tmem, alo, ahi, blo, bhi, idesc, accumulate);
+                umma_lohi<DT, pair>(d_tmem, alo + 2, ahi, blo + 2, bhi, idesc, 1u);
+                accumulate = 1;
+                blo += w16l;
+                alo += kChunkBytes >> 4;
+                if (++dxl == ks) {
+                  dxl = 0;
+                  alo += skipl;
+                }
+              }
+            } else {
+              const uint32_t halo16l = static_cast<uint32_t>(a_halo16);
+              for (int j = 0; j < TS; ++j) {
+                uint32_t a2 = alo;
+                uint32_t d = d_tmem;
+                for (int g = 0; g < G; ++g, a2 += halo16l, d += n_tile) {
+                  umma_lohi<DT, pair>(d, a2, ahi, blo, bhi, idesc, accumulate);
+                  umma_lohi<DT, pair>(d, a2 + 2, ahi, blo + 2, bhi, idesc, 1u);
+                }
+                accumulate = 1;
+                blo += w16l;
+                alo += kChunkBytes >> 4;
+                if (++dxl == ks) {
+                  dxl = 0;
+                  alo += skipl;
+                }
+              }
+            }
+          }
+          __syncwarp();
+          accumulate = 1;
+          if (!resident) umma_commit_elect<pair>(&w_empty[iw]);
+          if (++iw == NW) {
+            iw = 0;
+            pw ^= 1;
+          }
+          // advance the warp-uniform descriptor past this stage's TS taps
+          const int adv = dx + TS;
+          adesc += static_cast<uint64_t>(TS * (kChunkBytes >> 4)) + static_cast<uint64_t>(adv / ks) * row_skip;
+          dx = adv % ks;
+        }
+        umma_commit_elect<pair>(&a_empty[ia]);
+        if (last_of_tile) {
+          umma_commit_elect<pair>(&tfull_bar[abuf]);
+          first = false;
+        }
+        tr.stamp();
+        ia = nia; pa = npa; abuf = nabuf; aphase = naphase;
+        cbase = nbase; cs = ns; cch = nch;
+        valid = nvalid;
       }
     }
-  } else if (warp == 2) {
-    // ------------------------------------------------------------------ epilogue TMA stores
-    // forward: warps 2 and 3 both store (alternate channel groups; 3 boxes per group), c_{t-1} is prefetched by
-    // warp 0.  backward: warp 2 stores (2 boxes per group), warp 3 loads (4 boxes per group).
-    if constexpr (EPI == EPI_FWD) epi_storer<E, EPI>(p, sE, st_ready, e_empty, walk, 0, 2);
-    if constexpr (EPI == EPI_BWD) epi_storer<E, EPI>(p, sE, st_ready, e_empty, walk, 0, 1);
-  } else if (warp == 3) {
-    if constexpr (EPI == EPI_FWD) epi_storer<E, EPI>(p, sE, st_ready, e_empty, walk, 1, 2);
-    if constexpr (EPI == EPI_BWD) epi_loader<E, EPI>(p, sE, e_full, e_empty, walk);
-  } else {
+  } else if (warp == 2 || warp == 3) {
+    // ------------------------------------------------------------------ epilogue TMA stores (alternate channel groups)
+    if constexpr (EPI != EPI_RAW) epi_storer<E, EPI>(p, sE, st_ready, e_empty, walk, warp - 2, 2);
+  } else if (warp == 4 || warp == 5) {
+    // ------------------------------------------------------------------ epilogue TMA loads
+    // backward: 4 boxes per channel group, two loaders alternate groups; forward: one box per group, warp 4 only
+    if constexpr (EPI == EPI_BWD) epi_loader<E, EPI>(p, sE, e_full, e_empty, walk, warp - 4, 2);
+    if constexpr (EPI == EPI_FWD) {
+      if (warp == 4) epi_loader<E, EPI>(p, sE, e_full, e_empty, walk, 0, 1);
+    }
+  } else if (warp >= kConvIoWarps) {
     // ------------------------------------------------------------------ epilogue math (warps 4-11)
     // the epilogue of either CTA releases the accumulator buffer on the LEADER's "tmem empty" barrier
     uint32_t tempty_remote = 0;
@@ -468,6 +549,16 @@ cudaError_t launch_conv_halo(int epi, int dtype, const ConvGemmParams& p, int nu
     return p.cluster == 2 ? launch_e<__nv_bfloat16, true>(epi, p, num_sms, stream)
                           : launch_e<__nv_bfloat16, false>(epi, p, num_sms, stream);
   return p.cluster == 2 ? launch_e<float, true>(epi, p, num_sms, stream) : launch_e<float, false>(epi, p, num_sms, stream);
+}
+
+// debug: copy the timeline trace of CTA 0 (see Tracer) to the host
+cudaError_t read_trace(long long* host, int n) {
+  if (n > kTraceRoles * kTraceLen) n = kTraceRoles * kTraceLen;
+  return cudaMemcpyFromSymbol(host, g_trace, static_cast<size_t>(n) * sizeof(long long));
+}
+cudaError_t clear_trace() {
+  static long long zeros[kTraceRoles * kTraceLen] = {0};
+  return cudaMemcpyToSymbol(g_trace, zeros, sizeof(zeros));
 }
 
 }  // namespace nint

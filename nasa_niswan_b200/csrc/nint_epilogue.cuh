@@ -9,7 +9,7 @@
 // writes the result boxes back with TMA stores.  TMA's out-of-image handling (zero fill on load, clipping
 // on store) replaces every bounds check.
 //
-//   loader (warp 3)  --e_full[s]-->  epilogue (warps 4-11)  --st_ready[s]-->  storer (warp 2)  --e_empty[s]--> loader
+//   loader (warps 4/5) --e_full[s]--> math (warps 8-15) --st_ready[s]--> storer (warps 2/3) --e_empty[s]--> loader
 #pragma once
 #include "nint_common.cuh"
 #include "nint_kernels.h"
@@ -17,9 +17,26 @@
 
 namespace nint {
 
-constexpr int kConvThreads = 384;   // warp 0 operand TMA, 1 MMA, 2 TMEM alloc + epilogue stores, 3 epilogue loads, 4-11 epilogue
+constexpr int kConvIoWarps = 8;     // warps 0-7: TMA producers / loaders / storers and the MMA issuer (nint_conv_halo.cu)
+constexpr int kConvThreads = 512;   // warps 8-15: epilogue math
 constexpr int kEpiMaxStages = 4;
 constexpr int kEpiBoxBytes16 = kTilePixels * 16 * 4;   // 16 fp32 channels x 128 pixels = 8 KiB
+
+// ---- timeline trace (debug_flags & 8): CTA 0 records clock64() stamps per role into a global buffer that
+// tools/trace_report.py reads back through nint_debug_read_trace
+constexpr int kTraceRoles = 8, kTraceLen = 1024;
+__device__ long long g_trace[kTraceRoles * kTraceLen];
+struct Tracer {
+  long long* dst;
+  int n;
+  __device__ __forceinline__ Tracer(const ConvGemmParams& p, int role, bool on) {
+    dst = (on && (p.debug_flags & 8) && blockIdx.x == 0) ? g_trace + role * kTraceLen : nullptr;
+    n = 0;
+  }
+  __device__ __forceinline__ void stamp() {
+    if (dst && n < kTraceLen) dst[n++] = clock64();
+  }
+};
 
 struct ItemCoord {
   int b, x0, y0;
@@ -152,53 +169,29 @@ __device__ __forceinline__ int epi_groups(const ConvGemmParams& p) {
   return (EPI == EPI_FWD ? p.hcb : p.hc) >> 4;
 }
 
-// forward: the operand producer (warp 0) prefetches c_{t-1} of the tile group it has just issued the
-// activation loads for.  `s` / `ph`: epilogue stage ring position (carried across calls).
-template <typename E>
-__device__ __forceinline__ void epi_fwd_loads(const ConvGemmParams& p, uint8_t* sE, uint64_t* e_full, uint64_t* e_empty,
-                                              const TileWalk& w, int base, bool leader, int& s, uint32_t& ph) {
-  const int ngroups = p.hcb >> 4;
-  for (int gi = 0; gi < p.group; ++gi) {
-    const int tile = base + gi;
-    if (tile >= w.num_tiles) break;
-    const ItemCoord c = decode_tile(p, tile);
-    for (int grp = 0; grp < ngroups; ++grp) {
-      mbar_wait(&e_empty[s], ph ^ 1);
-      if (leader) {
-        if (p.slot_c_in >= 0) {
-          mbar_arrive_expect_tx(&e_full[s], kEpiBoxBytes16);
-          tma_load_5d(sE + s * p.e_stage_bytes + p.e_off_c, &p.tm_c, &e_full[s], w.nb * p.hcb + grp * 16, c.x0, c.y0, c.b,
-                      p.slot_c_in);
-        } else {
-          mbar_arrive(&e_full[s]);   // zero state: nothing to read, the stage is only an output buffer
-        }
-      }
-      if (++s == p.e_stages) {
-        s = 0;
-        ph ^= 1;
-      }
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------ loader (backward: warp 3)
+// ------------------------------------------------------------------------------------ loader
+// handles the channel groups whose running index n satisfies n % nwhich == which
 template <typename E, int EPI>
 __device__ __forceinline__ void epi_loader(const ConvGemmParams& p, uint8_t* sE, uint64_t* e_full, uint64_t* e_empty,
-                                           const TileWalk& w) {
+                                           const TileWalk& w, int which, int nwhich) {
   using GE = EpiGeom<E>;
   const bool leader = elect_one();
+  Tracer tr(p, 2, leader && which == 0);
   const int G = p.group;
   const int ngroups = epi_groups<EPI>(p);
-  int s = 0;
+  int s = 0, n = 0;
   uint32_t ph = 0;
   for (int base = w.first_tile; base < w.tiles_padded; base += w.tile_stride) {
     for (int gi = 0; gi < G; ++gi) {
       const int tile = base + gi;
       if (tile >= w.num_tiles) break;
       const ItemCoord c = decode_tile(p, tile);
-      for (int grp = 0; grp < ngroups; ++grp) {
-        mbar_wait(&e_empty[s], ph ^ 1);
-        if (leader) {
+      for (int grp = 0; grp < ngroups; ++grp, ++n) {
+        const bool mine = (nwhich == 1) || ((n % nwhich) == which);
+        if (mine) tr.stamp();
+        if (mine) mbar_wait(&e_empty[s], ph ^ 1);
+        if (mine) tr.stamp();
+        if (mine && leader) {
           uint8_t* st = sE + s * p.e_stage_bytes;
           uint64_t* bar = &e_full[s];
           if constexpr (EPI == EPI_FWD) {
@@ -221,6 +214,7 @@ __device__ __forceinline__ void epi_loader(const ConvGemmParams& p, uint8_t* sE,
             if (p.has_dc_in) tma_load_5d(st + p.e_off_dc, &p.tm_dc, bar, grp * 16, c.x0, c.y0, c.b, 0);
           }
         }
+        if (mine) tr.stamp();
         if (++s == p.e_stages) {
           s = 0;
           ph ^= 1;
@@ -237,6 +231,7 @@ __device__ __forceinline__ void epi_storer(const ConvGemmParams& p, uint8_t* sE,
                                            const TileWalk& w, int which, int nwhich) {
   using GE = EpiGeom<E>;
   const bool leader = elect_one();
+  Tracer tr(p, 3, leader && which == 0);
   const int G = p.group;
   const int ngroups = epi_groups<EPI>(p);
   int s = 0, n = 0;
@@ -248,7 +243,9 @@ __device__ __forceinline__ void epi_storer(const ConvGemmParams& p, uint8_t* sE,
       const ItemCoord c = decode_tile(p, tile);
       for (int grp = 0; grp < ngroups; ++grp, ++n) {
         const bool mine = (nwhich == 1) || ((n % nwhich) == which);
+        if (mine) tr.stamp();
         if (mine) mbar_wait(&st_ready[s], ph);
+        if (mine) tr.stamp();
         if (mine && leader) {
           const uint8_t* st = sE + s * p.e_stage_bytes;
           if (!(p.debug_flags & 1)) {
@@ -274,6 +271,7 @@ __device__ __forceinline__ void epi_storer(const ConvGemmParams& p, uint8_t* sE,
           }
           mbar_arrive(&e_empty[s]);
         }
+        if (mine) tr.stamp();
         if (++s == p.e_stages) {
           s = 0;
           ph ^= 1;
@@ -284,7 +282,7 @@ __device__ __forceinline__ void epi_storer(const ConvGemmParams& p, uint8_t* sE,
   if (leader) tma_store_wait_all();   // global writes complete before the CTA exits
 }
 
-// ------------------------------------------------------------------------------------ math (warps 4..11)
+// ------------------------------------------------------------------------------------ math (warps 8..15)
 // TMEM lane quadrant = warp % 4 (hardware rule); the two warps of a quadrant take the two 8-channel halves
 // of the 16-channel group.  `tempty_remote`: CTA-pair mode, shared::cluster address of the leader's tempty_bar[0].
 template <typename E, int EPI>
@@ -298,9 +296,10 @@ __device__ __forceinline__ void epi_math(const ConvGemmParams& p, int warp, int 
   const int G = p.group;
   const int ngroups = epi_groups<EPI>(p);
   const int quad = warp & 3;
-  const int half = (warp - 4) >> 2;
+  const int half = (warp - kConvIoWarps) >> 2;
   const int row = quad * 32 + lane;
   const bool skip = (p.debug_flags & 1) != 0;
+  Tracer tr(p, 4, warp == kConvIoWarps && lane == 0);
   int s = 0;
   uint32_t ph = 0;
   int abuf = 0;
@@ -323,12 +322,15 @@ __device__ __forceinline__ void epi_math(const ConvGemmParams& p, int warp, int 
       }
       for (int grp = 0; grp < ngroups; ++grp) {
         const uint32_t st = smem_u32(sE + s * p.e_stage_bytes);
+        tr.stamp();
         mbar_wait(&e_full[s], ph);
+        tr.stamp();
         if (!waited) {
           mbar_wait(&tfull_bar[abuf], aphase);
           tc_fence_after();
           waited = true;
         }
+        tr.stamp();
         if constexpr (EPI == EPI_FWD) {
           // model.py:221-229.  accumulator columns of this group: grp*64 + gate*16 + channel
           float a[4][8], cn[8], hn[8];
@@ -442,6 +444,7 @@ __device__ __forceinline__ void epi_math(const ConvGemmParams& p, int warp, int 
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&st_ready[s]);
+        tr.stamp();
         if (++s == p.e_stages) {
           s = 0;
           ph ^= 1;
@@ -473,7 +476,7 @@ __device__ __forceinline__ void epi_raw(const ConvGemmParams& p, int warp, int l
                                         uint32_t tempty_remote) {
   const int G = p.group;
   const int quad = warp & 3;
-  const int half = (warp - 4) >> 2;
+  const int half = (warp - kConvIoWarps) >> 2;
   const int row = quad * 32 + lane;
   int abuf = 0;
   uint32_t aphase = 0;

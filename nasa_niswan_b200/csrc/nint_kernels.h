@@ -73,6 +73,9 @@ struct alignas(64) ConvGemmParams {
 int conv_halo_plan(int epi, int dtype, ConvGemmParams& p);
 int conv_halo_smem_bytes(const ConvGemmParams& p);
 cudaError_t launch_conv_halo(int epi, int dtype, const ConvGemmParams& p, int num_sms, cudaStream_t stream);
+// debug timeline (debug_flags & 8): 8 roles x 1024 clock64 stamps written by CTA 0 of the last traced launch
+cudaError_t read_trace(long long* host, int n);
+cudaError_t clear_trace();
 
 // ---- wgrad (nint_wgrad.cu):  dW[tap][q][col] += sum_pixels dgates[pix][q] * comb[pix + tap][col]
 constexpr int kMaxWgradGroups = 32;

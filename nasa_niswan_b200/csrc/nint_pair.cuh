@@ -90,4 +90,76 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
       : "memory");
 }
 
+// tcgen05.mma with the two shared-memory descriptors passed as (low, high) 32-bit halves: along a K walk only the
+// low words (start-address field) change, so the issuing thread's per-MMA work is two 32-bit adds and two
+// register->uniform moves instead of 64-bit descriptor arithmetic (the issue loop must run faster than the
+// 64-cycle N=128 pair MMA or every barrier round trip shows up as tensor idle time).
+template <int DTYPE, bool PAIR>
+__device__ __forceinline__ void umma_lohi(uint32_t d_tmem, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi,
+                                          uint32_t idesc, uint32_t accumulate) {
+#define NINT_UMMA_LOHI(GROUP, KIND)                                                                         \
+  asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 ad, bd;\n\tsetp.ne.b32 p, %6, 0;\n\t"                       \
+               "mov.b64 ad, {%1, %2};\n\tmov.b64 bd, {%3, %4};\n\t"                                        \
+               "tcgen05.mma.cta_group::" GROUP ".kind::" KIND " [%0], ad, bd, %5, p;\n\t}" ::"r"(d_tmem),   \
+               "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(accumulate)                          \
+               : "memory")
+  if constexpr (DTYPE == NINT_BF16) {
+    if constexpr (PAIR) NINT_UMMA_LOHI("2", "f16"); else NINT_UMMA_LOHI("1", "f16");
+  } else {
+    if constexpr (PAIR) NINT_UMMA_LOHI("2", "tf32"); else NINT_UMMA_LOHI("1", "tf32");
+  }
+#undef NINT_UMMA_LOHI
+}
+
+// ---- "elected" variants: every lane of the (converged) warp executes the call, the instruction itself is
+// predicated on elect.sync inside the asm block.  The surrounding C++ then has no divergent branch, which lets
+// ptxas keep descriptors / addresses in uniform registers (a lane-predicated branch around tcgen05.mma cost ~8
+// R2UR moves and ~60 extra cycles per tap: timeline traces, tools/trace_report.py).
+template <int DTYPE, bool PAIR>
+__device__ __forceinline__ void umma_elect(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  if constexpr (DTYPE == NINT_BF16) {
+    if constexpr (PAIR)
+      asm volatile(
+          "{\n\t.reg .pred p, e;\n\telect.sync _|e, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+          "@e tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+          "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+          : "memory");
+    else
+      asm volatile(
+          "{\n\t.reg .pred p, e;\n\telect.sync _|e, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+          "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+          "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+          : "memory");
+  } else {
+    if constexpr (PAIR)
+      asm volatile(
+          "{\n\t.reg .pred p, e;\n\telect.sync _|e, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+          "@e tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+          "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+          : "memory");
+    else
+      asm volatile(
+          "{\n\t.reg .pred p, e;\n\telect.sync _|e, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+          "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+          "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+          : "memory");
+  }
+}
+template <bool PAIR>
+__device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
+  if constexpr (PAIR)
+    asm volatile(
+        "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}" ::"r"(
+            smem_u32(bar)),
+        "h"(static_cast<uint16_t>(3))
+        : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar))
+        : "memory");
+}
+
 }  // namespace nint

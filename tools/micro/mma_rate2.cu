@@ -35,6 +35,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) k(Cfg c, lon
     const uint32_t idesc = make_idesc(NINT_BF16, 256, c.n, c.a_mn, c.b_mn);
     const uint64_t a0 = make_smem_desc(smem_u32(smem), c.lbo, c.sbo_a, c.layout);
     const uint64_t b0 = make_smem_desc(smem_u32(smem + 64 * 1024), c.lbo, 512, c.layout);
+    if (leader && c.iters == 32) {
+      // queue-depth probe: clock after each of 32 back-to-back MMAs issued into an idle tensor pipe
+      long long ts[33];
+      ts[0] = clock64();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        umma2(tm + (j % c.nacc) * c.n, a0 + ((j & 7) * c.stride_a >> 4), b0 + 2 * (j & 1), idesc, 1u);
+        ts[j + 1] = clock64();
+      }
+      if (blockIdx.x == 0) for (int j = 0; j < 33; ++j) out[2 + j] = ts[j] - ts[0];
+    }
     long long t0 = clock64();
     if (leader) {
       for (int i = 0; i < c.iters; i += 8) {
@@ -59,7 +70,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) k(Cfg c, lon
 }
 
 int main() {
-  long long* out; cudaMalloc(&out, 16);
+  long long* out; cudaMalloc(&out, 40 * 8);
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   struct { const char* name; Cfg c; } tests[] = {
     {"2cta K-major N=256 (128/CTA) 2acc",   {256, 0, 0, 4, 2, 512, 16, 4096, 0, 32}},
@@ -69,6 +80,23 @@ int main() {
     {"2cta MN-major N=96 5acc",             {96, 1, 1, 4, 5, 512, 8192, 4096, 0, 1024}},
     {"2cta MN-major N=192 2acc",            {192, 1, 1, 4, 2, 512, 8192, 4096, 0, 1024}},
   };
+  {
+    Cfg q = {128, 0, 0, 4, 2, 512, 16, 32, 0, 32};
+    k<<<148, 128, 200 * 1024>>>(q, out);
+    cudaDeviceSynchronize();
+    long long h[40];
+    cudaMemcpy(h, out, 40 * 8, cudaMemcpyDeviceToHost);
+    printf("issue-return clock of 32 back-to-back pair MMAs (N=128, 64 cyc each):\n  ");
+    for (int j = 1; j <= 32; ++j) printf("%lld ", h[2 + j]);
+    printf("\n");
+    Cfg q2 = {256, 0, 0, 4, 2, 512, 16, 32, 0, 32};
+    k<<<148, 128, 200 * 1024>>>(q2, out);
+    cudaDeviceSynchronize();
+    cudaMemcpy(h, out, 40 * 8, cudaMemcpyDeviceToHost);
+    printf("same, N=256 (128 cyc each):\n  ");
+    for (int j = 1; j <= 32; ++j) printf("%lld ", h[2 + j]);
+    printf("\n");
+  }
   for (auto& t : tests) {
     k<<<148, 128, 200 * 1024>>>(t.c, out);
     cudaError_t e = cudaDeviceSynchronize();

@@ -29,12 +29,12 @@ __device__ __forceinline__ void tma_load_2d_(void* dst, const CUtensorMap* m, ui
 __device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(reinterpret_cast<uint64_t>(gdst)), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
 }
-__global__ void __launch_bounds__(128, 1) k(const __grid_constant__ CUtensorMap map, Cfg c, long long* out, const CUtensorMap* gmap, uint8_t* gbuf) {
+__global__ void __launch_bounds__(256, 1) k(const __grid_constant__ CUtensorMap map, Cfg c, long long* out, const CUtensorMap* gmap, uint8_t* gbuf) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ uint64_t bar_all[64];
+  __shared__ uint64_t bar_all[128];
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 64; ++i) mbar_init(&bar_all[i], 1);
+    for (int i = 0; i < 128; ++i) mbar_init(&bar_all[i], 1);
     fence_barrier_init();
   }
   __syncthreads();
@@ -129,15 +129,17 @@ int main() {
   struct T { const char* name; int C; int box_c; int bw, bh; int depth; int store; CUtensorMapSwizzle sw; int nwarps; int B; };
   const CUtensorMapSwizzle S32 = CU_TENSOR_MAP_SWIZZLE_32B, S64 = CU_TENSOR_MAP_SWIZZLE_64B, S128 = CU_TENSOR_MAP_SWIZZLE_128B, S0 = CU_TENSOR_MAP_SWIZZLE_NONE;
   T tests[] = {
-    {"burst tensor 4D 64B 10x18 x8 (param desc)", 64, 32, 10, 18, 8, 2, S64, 1, 32},
-    {"burst tensor 4D 64B 10x18 x8 (global desc)", 64, 32, 10, 18, 8, 5, S64, 1, 32},
-    {"burst tensor 2D 64B x128 rows x8", 64, 32, 1, 128, 8, 6, S64, 1, 32},
-    {"burst bulk-1D load 8KB x8", 64, 32, 8, 16, 8, 3, S64, 1, 32},
-    {"burst bulk-1D load 16KB x8", 64, 64, 8, 16, 8, 3, S128, 1, 32},
-    {"burst bulk-1D load 2KB x8", 64, 32, 8, 4, 8, 3, S64, 1, 32},
-    {"burst bulk-1D store 8KB x4", 64, 32, 8, 16, 4, 4, S64, 1, 32},
-    {"burst bulk-1D store 16KB x4", 64, 64, 8, 16, 4, 4, S128, 1, 32},
-    {"burst bulk-1D store 16KB x1", 64, 64, 8, 16, 1, 4, S128, 1, 32},
+    {"ring load 64B 8x16 d2 1w", 64, 32, 8, 16, 2, 0, S64, 1, 32},
+    {"ring load 64B 8x16 d2 2w", 64, 32, 8, 16, 2, 0, S64, 2, 32},
+    {"ring load 64B 8x16 d2 4w", 64, 32, 8, 16, 2, 0, S64, 4, 32},
+    {"ring load 64B 8x16 d2 6w", 64, 32, 8, 16, 2, 0, S64, 6, 32},
+    {"ring load 64B 8x16 d2 8w", 64, 32, 8, 16, 2, 0, S64, 8, 32},
+    {"ring load 128B 8x16 d2 4w", 64, 64, 8, 16, 2, 0, S128, 4, 32},
+    {"ring load 128B 8x16 d1 8w", 64, 64, 8, 16, 1, 0, S128, 8, 32},
+    {"store 64B 8x16 d2 1w", 64, 32, 8, 16, 2, 1, S64, 1, 32},
+    {"store 64B 8x16 d2 4w", 64, 32, 8, 16, 2, 1, S64, 4, 32},
+    {"store 64B 8x16 d2 8w", 64, 32, 8, 16, 2, 1, S64, 8, 32},
+    {"store 128B 8x16 d1 8w", 64, 64, 8, 16, 1, 1, S128, 8, 32},
   };
   for (auto& t : tests) {
     void* buf;
@@ -166,7 +168,7 @@ int main() {
     c.bw = t.bw; c.bh = t.bh; c.store = t.store; c.nwarps = t.nwarps;
     CUtensorMap* gm; cudaMalloc(&gm, sizeof(CUtensorMap)); cudaMemcpy(gm, &m, sizeof(CUtensorMap), cudaMemcpyHostToDevice);
     if (t.store >= 3 && t.store != 5) { c.tiles_x = 1; c.tiles_y = 1; c.B = (int)(bytes / c.box_bytes); if (t.store == 6) c.bh = t.bh; }
-    for (int rep = 0; rep < 2; ++rep) k<<<148, 128, 200 * 1024>>>(m, c, out, gm, (uint8_t*)buf);
+    for (int rep = 0; rep < 2; ++rep) k<<<148, 256, 200 * 1024>>>(m, c, out, gm, (uint8_t*)buf);
     cudaError_t e = cudaDeviceSynchronize();
     long long hh[2] = {0, 0};
     cudaMemcpy(hh, out, 16, cudaMemcpyDeviceToHost);
