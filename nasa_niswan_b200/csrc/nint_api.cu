@@ -81,6 +81,8 @@ struct Layer {
   CUtensorMap tm_H_up;       // Hs[l] read as the x segment of layer l+1 (halo of k_{l+1})
   CUtensorMap tmw_H, tmw_G;  // wgrad views (32-channel boxes; differ from tm_* in tf32 mode only)
   CUtensorMap tmw_H_up;      // Hs[l] as the x part of layer l+1's wgrad (halo of k_{l+1})
+  CUtensorMap tmp_G, tmp_H, tmp_H_up;        // CTA-pair wgrad views: 64-q dgates boxes (SWIZZLE_128B), 16-channel halo boxes (SWIZZLE_32B)
+  bool wgrad_pair = false;
   CUtensorMap tme_C, tme_H, tme_G, tme_dC;  // epilogue I/O boxes (16 | 64 channels x 8 x 16 pixels; nint_epilogue.cuh)
   bool weights_set = false;
 };
@@ -96,7 +98,7 @@ struct nint_plan {
   size_t ws_bytes = 0;
   uint8_t* ws = nullptr;
   uint8_t* X = nullptr;  // [T][B][H][W][cx_pad0] E
-  CUtensorMap tm_X, tmw_X;
+  CUtensorMap tm_X, tmw_X, tmp_X;
   float *head_w = nullptr, *head_b = nullptr;
   bool head_set = false;
   bool zero_init = true;
@@ -166,6 +168,24 @@ int encode_act_map(CUtensorMap* m, int dtype, void* base, int C, int W, int H, i
                    dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(activation C=%d W=%d H=%d B=%d slots=%d) -> %d", C, W, H, B, slots, (int)r);
+  return 0;
+}
+
+// general activation box: `box_c` channels x (tw + 2*halo) x (th + 2*halo) pixels with an explicit swizzle
+int encode_act_box(CUtensorMap* m, int dtype, void* base, int C, int W, int H, int B, int slots, int box_c, int tw,
+                   int th, int halo, CUtensorMapSwizzle sw) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail("cuTensorMapEncodeTiled not available (no CUDA driver?)");
+  const cuuint64_t es = dtype == BF16 ? 2 : 4;
+  cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B, (cuuint64_t)slots};
+  cuuint64_t strides[4] = {C * es, (cuuint64_t)W * C * es, (cuuint64_t)H * W * C * es,
+                           (cuuint64_t)B * H * W * C * es};
+  cuuint32_t box[5] = {(cuuint32_t)box_c, (cuuint32_t)(tw + 2 * halo), (cuuint32_t)(th + 2 * halo), 1, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, dtype == BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, base,
+                   dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(box C=%d box_c=%d halo=%d) -> %d", C, box_c, halo, (int)r);
   return 0;
 }
 
@@ -501,6 +521,21 @@ int nint_plan_bind(nint_plan* p, void* workspace, size_t bytes, void* stream) {
           encode_act_map(&y.tmw_H_up, p->dtype, y.Hs, y.hc_pad, p->W, p->H, p->B, y.nslots_h, ce, tw, th, true, pad_of(l + 1))) return 1;
     }
   }
+  if (p->cfg.training) {
+    for (int l = 0; l < p->L; ++l) {
+      Layer& y = p->layer[l];
+      y.wgrad_pair = p->cluster == 2 && wgrad_pair_supported(p->dtype, 4 * y.hc, y.ncols, y.k) != 0;
+      if (!y.wgrad_pair) continue;
+      if (encode_act_box(&y.tmp_G, p->dtype, y.G, 4 * y.hc, p->W, p->H, p->B, p->T, 64, tw, th, 0, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+      if (encode_act_box(&y.tmp_H, p->dtype, y.Hs, y.hc_pad, p->W, p->H, p->B, y.nslots_h, 16, tw, th, pad_of(l), CU_TENSOR_MAP_SWIZZLE_32B)) return 1;
+      if (l == 0) {
+        if (encode_act_box(&p->tmp_X, p->dtype, p->X, y.cx_pad, p->W, p->H, p->B, p->T, 16, tw, th, pad_of(0), CU_TENSOR_MAP_SWIZZLE_32B)) return 1;
+      } else {
+        Layer& dn = p->layer[l - 1];
+        if (encode_act_box(&dn.tmp_H_up, p->dtype, dn.Hs, dn.hc_pad, p->W, p->H, p->B, dn.nslots_h, 16, tw, th, pad_of(l), CU_TENSOR_MAP_SWIZZLE_32B)) return 1;
+      }
+    }
+  }
   p->zero_init = true;
   p->fwd_done = false;
   return 0;
@@ -721,7 +756,13 @@ int nint_backward(nint_plan* p, const float* dpred, const float* dseq, float* co
     w.tile_w = p->tile_w; w.tile_h = p->tile_h; w.tiles_x = p->tiles_x; w.tiles_y = p->tiles_y;
     w.ksize = y.k;
     w.hc4 = 4 * y.hc;
-    w.m_blocks = (w.hc4 + 127) / 128;
+    w.pair = y.wgrad_pair ? 1 : 0;
+    if (w.pair) {
+      w.tmap_dg = y.tmp_G;
+      w.tmap_b[0] = l == 0 ? p->tmp_X : p->layer[l - 1].tmp_H_up;
+      w.tmap_b[1] = y.tmp_H;
+    }
+    w.m_blocks = w.pair ? w.hc4 / 256 : (w.hc4 + 127) / 128;
     w.ncols = y.ncols;
     const int tpg = 512 / y.ncols;                      // taps per group
     int g0 = (512 - 32) / y.ncols;                      // group 0 also holds the 32 bias columns
@@ -737,14 +778,14 @@ int nint_backward(nint_plan* p, const float* dpred, const float* dseq, float* co
     }
     w.n_groups = ng;
     const long long total_tiles = static_cast<long long>(T) * p->B * p->tiles_x * p->tiles_y;
-    int splits = p->num_sms / (w.m_blocks * ng);
+    int splits = (w.pair ? p->num_sms / 2 : p->num_sms) / (w.m_blocks * ng);
     if (splits < 1) splits = 1;
     if (splits > total_tiles) splits = static_cast<int>(total_tiles);
     w.splits = splits;
     wgrad_pick_buffers(p->dtype, y.ncols / 32, w.b_panel_bytes, &w.a_bufs, &w.b_stages);
     if (w.b_stages < 1) return fail("wgrad: operand panels do not fit in shared memory");
-    w.idesc = idesc_of(p->dtype, 128, y.ncols, 1, 1);
-    w.idesc_bias = idesc_of(p->dtype, 128, 32, 1, 1);
+    w.idesc = idesc_of(p->dtype, w.pair ? 256 : 128, y.ncols, 1, 1);
+    w.idesc_bias = idesc_of(p->dtype, w.pair ? 256 : 128, 32, 1, 1);
     w.dw_acc = y.dw_acc;
     w.db_acc = y.db_acc;
     LAUNCH(p, K_WGRAD, st, launch_wgrad(p->dtype, w, st));

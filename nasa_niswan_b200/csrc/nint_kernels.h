@@ -96,6 +96,8 @@ struct alignas(64) WgradParams {
   int halo;               // 1: 8x16 tiles, B panels hold the tile + k//2 halo and every tap re-reads them in place
   int b_panel_bytes;      // bytes between consecutive B panels of a stage
   int debug_flags;        // experiments: 2 = no MMA issue, 4 = issue every MMA twice
+  int pair;               // 1: CTA-pair kernel (bf16, 4*hc % 256 == 0): m_blocks counts 256-q blocks, tmap_dg has 64-q
+                          // boxes (SWIZZLE_128B) and tmap_b 16-channel halo boxes (SWIZZLE_32B)
   uint32_t idesc, idesc_bias;
   int hc4;                // 4*hc
   float* dw_acc;          // [taps][4*hc][ncols] fp32, atomically accumulated (pre-zeroed)
@@ -104,6 +106,7 @@ struct alignas(64) WgradParams {
 int wgrad_b_panel_bytes(int dtype, int halo, int ksize);
 int wgrad_smem_bytes(int dtype, int bpanels, int a_bufs, int b_stages, int b_panel_bytes);
 void wgrad_pick_buffers(int dtype, int bpanels, int b_panel_bytes, int* a_bufs, int* b_stages);
+int wgrad_pair_supported(int dtype, int hc4, int ncols, int ksize);
 cudaError_t launch_wgrad(int dtype, const WgradParams& p, cudaStream_t stream);
 
 // ---- pointwise / layout kernels (nint_pointwise.cu)

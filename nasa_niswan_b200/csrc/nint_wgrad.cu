@@ -16,6 +16,7 @@
 // The bias gradient is an extra MMA against a constant panel of ones (group 0 only).
 #include "nint_common.cuh"
 #include "nint_kernels.h"
+#include "nint_pair.cuh"
 
 namespace nint {
 
@@ -315,6 +316,274 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// CTA-pair variant (bf16, 4*hc a multiple of 256): one tcgen05.mma.cta_group::2 covers M = 256 gate columns
+// (128 per CTA) at the tensor pipe's nominal rate; the single-CTA M=128 MMA above needs ~100 cycles for the
+// N=96 shape whose floor is 48 (tools/micro/mma_rate.cu).  Operands per pixel tile and CTA:
+//   A  dgates  [128 px][128 q]  as 2 panels of 64 q   (128-byte rows, SWIZZLE_128B, MN-major)
+//   B  comb    [halo px][N/2 channels] as 16-channel panels (32-byte rows, SWIZZLE_32B, MN-major): the pair MMA
+//      splits N between the CTAs, and N/2 = 48 is not a multiple of the 32-channel panel of the 64B swizzle
+// Warps: 0 A producer, 3 B producer (every bulk-async instruction occupies its issuing warp for ~450-750 cycles),
+// 1 MMA issuer (leader CTA), 2 TMEM allocator, 4-7 flush the accumulators with fp32 atomics.
+constexpr int kWgPairBStages = 4;
+constexpr int kWgPairABufs = 3;   // the issuer awaits tile i+1 before issuing tile i: needs i-1, i, i+1 resident
+constexpr int kWgPairAPanel = kTilePixels * 128;   // 64 q x 128 px bf16 = 16 KiB
+
+__host__ __device__ static inline int wgp_b_panel_bytes(int ksize) {
+  const int rows = (8 + (ksize & ~1)) * (16 + (ksize & ~1));
+  return (rows * 32 + 1023) & ~1023;
+}
+static inline int wgp_smem_bytes(int bp_cta, int ksize) {
+  return 1024 + kWgPairABufs * 2 * kWgPairAPanel + kWgPairBStages * bp_cta * wgp_b_panel_bytes(ksize) + 1024 + kWgCtrlBytes;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kWgThreads, 1)
+wgrad_pair_kernel(const __grid_constant__ WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const uint32_t crank = __shfl_sync(0xffffffffu, cluster_ctarank(), 0);
+  const bool lead_cta = crank == 0;
+  const int bp_all = (p.nchunks_b[0] + p.nchunks_b[1]) * 2;   // 16-channel panels of the concatenated input
+  const int bp_cta = bp_all / 2;                              // this CTA's half of N
+  const int bx16 = p.nchunks_b[0] * 2;                        // panels that come from the x tensor
+  const int b_panel = wgp_b_panel_bytes(p.ksize);
+  const int a_buf_bytes = 2 * kWgPairAPanel;
+  const int b_stage_bytes = bp_cta * b_panel;
+  const int hpitch = 8 + (p.ksize & ~1);
+  const int hrows = hpitch * (16 + (p.ksize & ~1));
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + kWgPairABufs * a_buf_bytes;
+  uint8_t* sOnes = sB + kWgPairBStages * b_stage_bytes;
+  uint8_t* ctrl = sOnes + 1024;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(ctrl);
+  uint64_t* a_empty = a_full + kWgMaxBufs;
+  uint64_t* b_full = a_empty + kWgMaxBufs;
+  uint64_t* b_empty = b_full + kWgMaxBufs;
+  uint64_t* acc_full = b_empty + kWgMaxBufs;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ctrl + kWgCtrlBytes - 16);
+
+  // cluster -> (split, tap group, m-block of 256 q)
+  const int cid = blockIdx.x >> 1;
+  const int mb = cid % p.m_blocks;
+  const int grp = (cid / p.m_blocks) % p.n_groups;
+  const int split = cid / (p.m_blocks * p.n_groups);
+  const int tap_begin = p.group_tap0[grp];
+  const int ntaps = p.group_tap0[grp + 1] - tap_begin;
+  const bool do_bias = (grp == 0) && (p.db_acc != nullptr);
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+  const int total_tiles = p.T * p.B * tiles_per_img;
+  const int my_tiles = (total_tiles - split + p.splits - 1) / p.splits;
+  const int pad = p.ksize >> 1;
+
+  {
+    // the tiles are always full 8 x 16 boxes (TMA zero-fills outside the image), so no operand row is ever stale;
+    // the ones panel feeds the bias-gradient MMA
+    uint4* o = reinterpret_cast<uint4*>(sOnes);
+    for (int i = threadIdx.x; i < 1024 / 16; i += kWgThreads) o[i] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
+    fence_proxy_async_smem();
+  }
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&p.tmap_dg);
+    prefetch_tensormap(&p.tmap_b[0]);
+    prefetch_tensormap(&p.tmap_b[1]);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kWgMaxBufs; ++s) {
+      mbar_init(&a_full[s], 1);
+      mbar_init(&a_empty[s], 1);
+      mbar_init(&b_full[s], 1);
+      mbar_init(&b_empty[s], 1);
+    }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_pair(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+
+  auto tile_coords = [&](int i, int& x0, int& y0, int& b, int& t) {
+    int r = split + i * p.splits;
+    const int tx = r % p.tiles_x;
+    r /= p.tiles_x;
+    const int ty = r % p.tiles_y;
+    r /= p.tiles_y;
+    b = r % p.B;
+    t = r / p.B;
+    x0 = tx * p.tile_w;
+    y0 = ty * p.tile_h;
+  };
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ A producer: this CTA's 128 gate columns
+    const bool leader = elect_one();
+    int ab = 0;
+    uint32_t aph = 0;
+    for (int i = 0; i < my_tiles; ++i) {
+      int x0, y0, b, t;
+      tile_coords(i, x0, y0, b, t);
+      mbar_wait(&a_empty[ab], aph ^ 1);
+      if (leader) {
+        if (lead_cta) mbar_arrive_expect_tx(&a_full[ab], static_cast<uint32_t>(2 * a_buf_bytes));
+        const uint32_t bar = mapa_rank(smem_u32(&a_full[ab]), 0);
+        const int q0 = mb * 256 + static_cast<int>(crank) * 128;
+        tma_load_5d_pair(sA + ab * a_buf_bytes, &p.tmap_dg, bar, q0, x0, y0, b, t);
+        tma_load_5d_pair(sA + ab * a_buf_bytes + kWgPairAPanel, &p.tmap_dg, bar, q0 + 64, x0, y0, b, t);
+      }
+      if (++ab == kWgPairABufs) {
+        ab = 0;
+        aph ^= 1;
+      }
+    }
+  } else if (warp == 3) {
+    // ------------------------------------------------------------------ B producer: this CTA's half of the channels
+    const bool leader = elect_one();
+    int bs = 0;
+    uint32_t bph = 0;
+    for (int i = 0; i < my_tiles; ++i) {
+      int x0, y0, b, t;
+      tile_coords(i, x0, y0, b, t);
+      mbar_wait(&b_empty[bs], bph ^ 1);
+      if (leader) {
+        if (lead_cta) mbar_arrive_expect_tx(&b_full[bs], static_cast<uint32_t>(2 * bp_cta * hrows * 32));
+        const uint32_t bar = mapa_rank(smem_u32(&b_full[bs]), 0);
+        uint8_t* dst = sB + bs * b_stage_bytes;
+        for (int j = 0; j < bp_cta; ++j, dst += b_panel) {
+          const int pj = static_cast<int>(crank) * bp_cta + j;   // 16-channel panel of the concatenated input
+          if (pj < bx16)
+            tma_load_5d_pair(dst, &p.tmap_b[0], bar, pj * 16, x0 - pad, y0 - pad, b, p.slot_b0[0] + t);
+          else
+            tma_load_5d_pair(dst, &p.tmap_b[1], bar, (pj - bx16) * 16, x0 - pad, y0 - pad, b, p.slot_b0[1] + t);
+        }
+      }
+      if (++bs == kWgPairBStages) {
+        bs = 0;
+        bph ^= 1;
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA)
+    if (my_tiles > 0 && lead_cta) {
+      const bool leader = elect_one();
+      const uint32_t idesc = p.idesc, idesc_bias = p.idesc_bias;
+      const uint32_t ncols = static_cast<uint32_t>(p.ncols);
+      const int ksize = p.ksize;
+      const bool issue_any = !(p.debug_flags & 2);
+      // MN-major descriptors.  A: 64-q atoms (128-byte rows, SWIZZLE_128B) one panel apart, 8-pixel groups 1 KiB apart.
+      // B: 16-channel atoms (32-byte rows, SWIZZLE_32B) one panel apart, 8-pixel groups one halo row apart.
+      const uint64_t adesc_base = make_smem_desc(0, kWgPairAPanel, 1024, 2);
+      const uint64_t bdesc_base = make_smem_desc(0, static_cast<uint32_t>(b_panel), static_cast<uint32_t>(hpitch * 32), 6);
+      const uint64_t odesc = make_smem_desc(smem_u32(sOnes), 512, 256, 6);
+      const uint32_t ahi = static_cast<uint32_t>(adesc_base >> 32), bhi = static_cast<uint32_t>(bdesc_base >> 32);
+      const uint32_t alo_base = static_cast<uint32_t>(adesc_base), blo_base = static_cast<uint32_t>(bdesc_base);
+      const uint32_t sA16 = smem_u32(sA) >> 4, sB16 = smem_u32(sB) >> 4;
+      const int dy0 = tap_begin / ksize, dx0 = tap_begin % ksize;
+      int ab = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      mbar_wait(&a_full[0], 0);
+      mbar_wait(&b_full[0], 0);
+      tc_fence_after();
+      for (int i = 0; i < my_tiles; ++i) {
+        // readiness of the next tile's operands is awaited before this tile's MMAs are issued (the tensor pipe's
+        // queue is deep but every barrier round trip costs the issuing thread ~100 cycles)
+        const int nab = (ab + 1 == kWgPairABufs) ? 0 : ab + 1;
+        const int nbs = (bs + 1 == kWgPairBStages) ? 0 : bs + 1;
+        const uint32_t naph = (ab + 1 == kWgPairABufs) ? aph ^ 1 : aph;
+        const uint32_t nbph = (bs + 1 == kWgPairBStages) ? bph ^ 1 : bph;
+        if (i + 1 < my_tiles) {
+          mbar_wait(&a_full[nab], naph);
+          mbar_wait(&b_full[nbs], nbph);
+          tc_fence_after();
+        }
+        if (leader && issue_any) {
+          const uint32_t a0 = alo_base + sA16 + static_cast<uint32_t>((ab * a_buf_bytes) >> 4);
+          const uint32_t b0 = blo_base + sB16 + static_cast<uint32_t>((bs * b_stage_bytes) >> 4);
+          uint32_t acc = i != 0 ? 1u : 0u;
+#pragma unroll 1
+          for (int ks = 0; ks < 8; ++ks) {
+            // K step = 16 pixels = 2 tile rows: A advances 16 x 128 B, B two halo rows
+            const uint32_t alo = a0 + static_cast<uint32_t>(ks * 128);
+            uint32_t blo = b0 + static_cast<uint32_t>((((2 * ks + dy0) * hpitch + dx0) * 32) >> 4);
+            uint32_t d = tmem_base;
+            int dx = dx0;
+            for (int ti = 0; ti < ntaps; ++ti) {
+              umma_lohi<NINT_BF16, true>(d, alo, ahi, blo, bhi, idesc, acc);
+              d += ncols;
+              blo += 2;
+              if (++dx == ksize) {
+                dx = 0;
+                blo += static_cast<uint32_t>(((hpitch - ksize) * 32) >> 4);
+              }
+            }
+            if (do_bias)
+              umma_lohi<NINT_BF16, true>(d, alo, ahi, static_cast<uint32_t>(odesc), static_cast<uint32_t>(odesc >> 32),
+                                         idesc_bias, acc);
+            acc = 1;
+          }
+        }
+        __syncwarp();
+        umma_commit_elect<true>(&b_empty[bs]);
+        umma_commit_elect<true>(&a_empty[ab]);
+        ab = nab; bs = nbs; aph = naph; bph = nbph;
+      }
+      umma_commit_elect<true>(acc_full);
+    }
+  } else if (warp >= 4 && my_tiles > 0) {
+    // ------------------------------------------------------------------ epilogue: flush this CTA's 128 gate columns
+    const int quad = warp & 3;
+    const int q = mb * 256 + static_cast<int>(crank) * 128 + quad * 32 + lane;
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    for (int ti = 0; ti < ntaps; ++ti) {
+      float* dst = p.dw_acc + (static_cast<long long>(tap_begin + ti) * p.hc4 + q) * p.ncols;
+      for (int c0 = 0; c0 < p.ncols; c0 += 16) {
+        float v[16];
+        tmem_ld16(taddr + ti * p.ncols + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) atomicAdd(dst + c0 + j, v[j]);
+      }
+    }
+    if (do_bias) {
+      float v[16];
+      tmem_ld16(taddr + ntaps * p.ncols, v);
+      tmem_ld_wait();
+      atomicAdd(p.db_acc + q, v[0]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, kTmemCols);
+  }
+}
+
+int wgrad_pair_supported(int dtype, int hc4, int ncols, int ksize) {
+  if (dtype != NINT_BF16 || (hc4 % 256) != 0 || (ncols % 32) != 0) return 0;
+  return wgp_smem_bytes(ncols / 32, ksize) <= 227 * 1024;
+}
+
+static cudaError_t launch_wg_pair(const WgradParams& p, cudaStream_t stream) {
+  const int smem = wgp_smem_bytes(p.nchunks_b[0] + p.nchunks_b[1], p.ksize);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  const int grid = 2 * p.m_blocks * p.n_groups * p.splits;
+  if (grid <= 0) return cudaSuccess;
+  wgrad_pair_kernel<<<grid, kWgThreads, smem, stream>>>(p);
+  return cudaGetLastError();
+}
+
 template <typename E>
 static cudaError_t launch_wg(const WgradParams& p, cudaStream_t stream) {
   const int dtype = ElemTraits<E>::kDtype;
@@ -332,6 +601,7 @@ static cudaError_t launch_wg(const WgradParams& p, cudaStream_t stream) {
 }
 
 cudaError_t launch_wgrad(int dtype, const WgradParams& p, cudaStream_t stream) {
+  if (p.pair) return launch_wg_pair(p, stream);
   if (dtype == NINT_BF16) return launch_wg<__nv_bfloat16>(p, stream);
   return launch_wg<float>(p, stream);
 }
