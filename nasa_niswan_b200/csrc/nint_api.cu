@@ -764,18 +764,24 @@ int nint_backward(nint_plan* p, const float* dpred, const float* dseq, float* co
     }
     w.m_blocks = w.pair ? w.hc4 / 256 : (w.hc4 + 127) / 128;
     w.ncols = y.ncols;
+    // tap groups: a CTA keeps (taps in group) x ncols accumulator columns in TMEM (512 available); the 32 bias
+    // columns go to whichever group is lightest (the last one when it has room, else the first)
     const int tpg = 512 / y.ncols;                      // taps per group
-    int g0 = (512 - 32) / y.ncols;                      // group 0 also holds the 32 bias columns
-    if (g0 > tpg) g0 = tpg;
-    if (g0 < 1) return fail("wgrad: ncols %d leaves no room for the bias columns", y.ncols);
+    if (tpg < 1) return fail("wgrad: ncols %d exceeds the accumulator", y.ncols);
     int ng = 0, tap = 0;
     w.group_tap0[0] = 0;
+    const int full_groups = y.taps / tpg, rest = y.taps % tpg;
+    const bool bias_last = rest > 0 && rest * y.ncols + 32 <= 512;   // a partial last group with room for the bias
+    const int g0 = bias_last ? tpg : ((512 - 32) / y.ncols < tpg ? (512 - 32) / y.ncols : tpg);
+    if (g0 < 1) return fail("wgrad: ncols %d leaves no room for the bias columns", y.ncols);
+    (void)full_groups;
     while (tap < y.taps) {
       const int n = ng == 0 ? g0 : tpg;
       tap = tap + n > y.taps ? y.taps : tap + n;
       if (ng + 1 > kMaxWgradGroups) return fail("wgrad: too many tap groups");
       w.group_tap0[++ng] = tap;
     }
+    w.bias_group = bias_last ? ng - 1 : 0;
     w.n_groups = ng;
     const long long total_tiles = static_cast<long long>(T) * p->B * p->tiles_x * p->tiles_y;
     int splits = (w.pair ? p->num_sms / 2 : p->num_sms) / (w.m_blocks * ng);

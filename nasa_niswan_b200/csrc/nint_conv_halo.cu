@@ -150,9 +150,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
   // ------------------------------------------------------------------ operand TMA producers (both CTAs)
   // Every bulk-async instruction keeps its issuing warp busy for ~440-750 cycles whatever its size, and the
   // cost is per warp, not per SM (tools/micro/tma_rate.cu): the loads are spread over several warps.
-  //   a_par / a_npar: this warp issues the activation chunks whose running index c satisfies c % a_npar == a_par
+  //   a_par / a_npar: this warp issues the activation chunks whose running index c satisfies c % a_npar == a_par,
+  //                   or, with by_tile (G == 2), the box of tile a_par of EVERY chunk (halves the time from a free
+  //                   halo buffer to its "full" barrier)
   //   do_w: this warp issues the weight stages
   auto produce = [&](bool do_a, int a_par, int a_npar, bool do_w) {
+    const bool by_tile = do_a && a_npar == 2 && G == 2;
     const bool leader = elect_one();
     Tracer tr(p, do_w ? 5 : 0, leader && (do_w || a_par == 0));
     int ia = 0, iw = 0, cc = 0;
@@ -167,16 +170,17 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
         // weights: 3-D map (element, row of the N tile, chunk-tap index); one box = this CTA's rows of TS taps
         int wtap = (walk.nb * sg.nchunks) * taps;
         for (int ch = 0; ch < sg.nchunks; ++ch, ++cc, wtap += taps) {
-          if (do_a && (a_npar == 1 || (cc % a_npar) == a_par)) {
+          if (do_a && (a_npar == 1 || by_tile || (cc % a_npar) == a_par)) {
             tr.stamp();
             mbar_wait(&a_empty[ia], pa ^ 1);
             tr.stamp();
             if (leader) {
               // "full" barriers live in the leader CTA and count the bytes of both CTAs' loads
-              if (lead_cta) mbar_arrive_expect_tx(&a_full[ia], a_bytes * G * S);
+              if (lead_cta && (!by_tile || a_par == 0)) mbar_arrive_expect_tx(&a_full[ia], a_bytes * G * S);
               uint32_t bar = 0;
               if constexpr (pair) bar = mapa_rank(smem_u32(&a_full[ia]), 0);
-              for (int g = 0; g < G; ++g) {
+              const int g_begin = by_tile ? a_par : 0, g_end = by_tile ? a_par + 1 : G;
+              for (int g = g_begin; g < g_end; ++g) {
                 const ItemCoord cg = decode_tile(p, base + g);
                 uint8_t* dst = sA + ia * p.a_buf_bytes + g * p.a_halo_bytes;
                 if constexpr (pair)
@@ -250,9 +254,14 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
       // with fewer than 3 halo buffers the next chunk cannot be in flight while the current one is consumed:
       // then each chunk is awaited just before its own MMAs
       const bool lookahead = NA >= 3;
+      // streaming weights with one stage per chunk: the next chunk's stage is awaited ahead as well
+      bool single_stage = true;
+      for (int s = 0; s < nseg; ++s) single_stage = single_stage && (TS == p.seg[s].ksize * p.seg[s].ksize);
+      const bool w_ahead = lookahead && !resident && NW >= 3 && single_stage;
       if (valid && lookahead) {
         mbar_wait(&tempty_bar[abuf], aphase ^ 1);
         mbar_wait(&a_full[ia], pa);
+        if (w_ahead) mbar_wait(&w_full[0], 0);
         tc_fence_after();
       }
       while (valid) {
@@ -280,6 +289,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
           if (nvalid) {
             if (last_of_tile) mbar_wait(&tempty_bar[nabuf], naphase ^ 1);
             mbar_wait(&a_full[nia], npa);
+            if (w_ahead) {
+              // the next chunk's single weight stage is the ring slot after the current one
+              const int niw = (iw + 1 == NW) ? 0 : iw + 1;
+              mbar_wait(&w_full[niw], (iw + 1 == NW) ? pw ^ 1 : pw);
+            }
             tc_fence_after();
           }
         } else {
@@ -302,7 +316,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
         uint64_t adesc = make_smem_desc_sw64(sA_addr + ia * a_buf_bytes, 16, sbo);
         int dx = 0;
         for (int tap0 = 0; tap0 < taps; tap0 += TS) {
-          if (!resident || first) {
+          if ((!resident || first) && !w_ahead) {
             mbar_wait(&w_full[iw], pw);
             tc_fence_after();
           }
@@ -318,6 +332,23 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
               for (int j = 0; j < TS; ++j) {
                 umma_lohi<DT, pair>(d_tmem, alo, ahi, blo, bhi, idesc, accumulate);
                 umma_lohi<DT, pair>(d_tmem, alo + 2, ahi, blo + 2, bhi, idesc, 1u);
+                accumulate = 1;
+                blo += w16l;
+                alo += kChunkBytes >> 4;
+                if (++dxl == ks) {
+                  dxl = 0;
+                  alo += skipl;
+                }
+              }
+            } else if (G == 2) {
+              const uint32_t halo16l = static_cast<uint32_t>(a_halo16);
+              const uint32_t d1 = d_tmem + n_tile;
+#pragma unroll 3
+              for (int j = 0; j < TS; ++j) {
+                umma_lohi<DT, pair>(d_tmem, alo, ahi, blo, bhi, idesc, accumulate);
+                umma_lohi<DT, pair>(d1, alo + halo16l, ahi, blo, bhi, idesc, accumulate);
+                umma_lohi<DT, pair>(d_tmem, alo + 2, ahi, blo + 2, bhi, idesc, 1u);
+                umma_lohi<DT, pair>(d1, alo + halo16l + 2, ahi, blo + 2, bhi, idesc, 1u);
                 accumulate = 1;
                 blo += w16l;
                 alo += kChunkBytes >> 4;
@@ -459,16 +490,29 @@ int conv_halo_plan(int epi, int dtype, ConvGemmParams& p) {
   int gmax = 256 / p.n_tile;
   if (gmax > (epi == EPI_BWD ? 2 : 4)) gmax = (epi == EPI_BWD ? 2 : 4);
   if (gmax < 1 || p.nseg == 0) gmax = 1;
-  // three epilogue stages keep loads, math and stores of consecutive channel groups overlapped; fall back
-  // to two when the operands would not get 2 halo buffers + 3 single-tap weight stages otherwise
-  int NS = -1, G = 1;
-  for (int ns = ns_max; ns >= ns_min && NS < 0; --ns)
-    for (int g = gmax; g >= 1; --g)
-      if (total - ns * p.e_stage_bytes >= 2 * g * p.a_halo_bytes + 3 * w_bytes) {
-        NS = ns;
-        G = g;
-        break;
-      }
+  // taps per weight stage: every barrier round trip of the MMA-issuing thread costs ~100 cycles and every TMA box
+  // ~450-750 cycles of its producer warp, so a stage should carry all taps of a chunk when it fits
+  int want = (1536 + p.n_tile - 1) / p.n_tile;
+  if (want > max_k * max_k) want = max_k * max_k;
+  auto divides_all = [&](int cand) {
+    for (int s = 0; s < p.nseg; ++s) if ((p.seg[s].ksize * p.seg[s].ksize) % cand) return false;
+    return true;
+  };
+  // preference order: >= 3 halo buffers (the MMA issuer waits one chunk ahead) with 3 weight stages of `want` taps,
+  // first with three epilogue stages then two; after that relax the tap count, then the group size, then the buffers
+  int NS = -1, G = 1, ts = 1, min_na = 3;
+  for (int pass = 0; pass < 2 && NS < 0; ++pass, min_na = 2)
+    for (int cand = want; cand >= 1 && NS < 0; --cand) {
+      if (!divides_all(cand)) continue;
+      for (int g = gmax; g >= 1 && NS < 0; --g)
+        for (int ns = ns_max; ns >= ns_min; --ns)
+          if (total - ns * p.e_stage_bytes >= min_na * g * p.a_halo_bytes + 3 * cand * w_bytes) {
+            NS = ns;
+            G = g;
+            ts = cand;
+            break;
+          }
+    }
   if (NS < 0) return 1;
   p.e_stages = NS;
   p.group = G;
@@ -476,18 +520,6 @@ int conv_halo_plan(int epi, int dtype, ConvGemmParams& p) {
   p.acc_cols = G * p.n_tile;
   p.n_acc = 512 / p.acc_cols > kMaxAcc ? kMaxAcc : 512 / p.acc_cols;
   const int budget = total - NS * p.e_stage_bytes;
-  // every barrier round trip of the MMA-issuing thread costs a few hundred cycles: group taps so that
-  // one weight stage carries plenty of tensor work, keep >= 3 weight stages in flight and spend the rest
-  // of shared memory on halo buffers (a halo chunk is 180+ scattered 64-byte rows: ~1.5 us to arrive)
-  int want = (1536 + p.n_tile - 1) / p.n_tile;
-  if (want > max_k * max_k) want = max_k * max_k;
-  int ts = 1;
-  for (int cand = want; cand >= 1; --cand) {   // largest tap group that leaves room for 3 stages + 2 halo buffers and divides every tap count
-    if (budget - 3 * cand * w_bytes < 2 * p.a_buf_bytes) continue;
-    bool divides = true;
-    for (int s = 0; s < p.nseg; ++s) divides = divides && ((p.seg[s].ksize * p.seg[s].ksize) % cand == 0);
-    if (divides) { ts = cand; break; }
-  }
   int nw = 3;
   int na = (budget - nw * ts * w_bytes) / p.a_buf_bytes;
   if (na > 6) na = 6;

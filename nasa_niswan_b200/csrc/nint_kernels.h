@@ -90,6 +90,7 @@ struct alignas(64) WgradParams {
   int m_blocks;           // ceil(4*hc / 128)
   int n_groups;
   int group_tap0[kMaxWgradGroups + 1];  // taps [group_tap0[g], group_tap0[g+1]) belong to group g
+  int bias_group;         // tap group whose CTAs also accumulate the bias gradient
   int splits;             // split-K factor over pixel tiles
   int ncols;              // accumulator columns per tap = (sum nchunks_b) * 32
   int a_bufs, b_stages;

@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
   const int split = blockIdx.x / (p.m_blocks * p.n_groups);
   const int tap_begin = p.group_tap0[grp];
   const int ntaps = p.group_tap0[grp + 1] - tap_begin;
-  const bool do_bias = (grp == 0) && (p.db_acc != nullptr);
+  const bool do_bias = (grp == p.bias_group) && (p.db_acc != nullptr);
   const int tiles_per_img = p.tiles_x * p.tiles_y;
   const int total_tiles = p.T * p.B * tiles_per_img;
   const int my_tiles = (total_tiles - split + p.splits - 1) / p.splits;  // split < splits <= total or 0 tiles
@@ -371,7 +371,7 @@ wgrad_pair_kernel(const __grid_constant__ WgradParams p) {
   const int split = cid / (p.m_blocks * p.n_groups);
   const int tap_begin = p.group_tap0[grp];
   const int ntaps = p.group_tap0[grp + 1] - tap_begin;
-  const bool do_bias = (grp == 0) && (p.db_acc != nullptr);
+  const bool do_bias = (grp == p.bias_group) && (p.db_acc != nullptr);
   const int tiles_per_img = p.tiles_x * p.tiles_y;
   const int total_tiles = p.T * p.B * tiles_per_img;
   const int my_tiles = (total_tiles - split + p.splits - 1) / p.splits;
@@ -439,9 +439,11 @@ wgrad_pair_kernel(const __grid_constant__ WgradParams p) {
         aph ^= 1;
       }
     }
-  } else if (warp == 3) {
-    // ------------------------------------------------------------------ B producer: this CTA's half of the channels
+  } else if (warp == 3 || warp == 2) {
+    // ------------------------------------------------------------------ B producers: this CTA's half of the channels
+    // (warp 3 takes the even panels, warp 2 the odd ones)
     const bool leader = elect_one();
+    const int jpar = warp == 3 ? 0 : 1;
     int bs = 0;
     uint32_t bph = 0;
     for (int i = 0; i < my_tiles; ++i) {
@@ -449,10 +451,10 @@ wgrad_pair_kernel(const __grid_constant__ WgradParams p) {
       tile_coords(i, x0, y0, b, t);
       mbar_wait(&b_empty[bs], bph ^ 1);
       if (leader) {
-        if (lead_cta) mbar_arrive_expect_tx(&b_full[bs], static_cast<uint32_t>(2 * bp_cta * hrows * 32));
+        if (lead_cta && jpar == 0) mbar_arrive_expect_tx(&b_full[bs], static_cast<uint32_t>(2 * bp_cta * hrows * 32));
         const uint32_t bar = mapa_rank(smem_u32(&b_full[bs]), 0);
-        uint8_t* dst = sB + bs * b_stage_bytes;
-        for (int j = 0; j < bp_cta; ++j, dst += b_panel) {
+        uint8_t* dst = sB + bs * b_stage_bytes + jpar * b_panel;
+        for (int j = jpar; j < bp_cta; j += 2, dst += 2 * b_panel) {
           const int pj = static_cast<int>(crank) * bp_cta + j;   // 16-channel panel of the concatenated input
           if (pj < bx16)
             tma_load_5d_pair(dst, &p.tmap_b[0], bar, pj * 16, x0 - pad, y0 - pad, b, p.slot_b0[0] + t);

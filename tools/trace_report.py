@@ -15,7 +15,7 @@ import torch  # noqa: E402
 from nasa_niswan_b200 import Plan, _lib  # noqa: E402
 
 which = sys.argv[1] if len(sys.argv) > 1 else "fwd"
-B, T, C, H, W, hc, k = 32, 2, 21, 90, 144, 64, 3
+B, T, C, H, W, hc, k = 32, 3, 21, 90, 144, 64, 3
 torch.manual_seed(0)
 plan = Plan(B, T, H, W, C, [hc], [k], precision="bf16", training=True)
 plan.set_weights(0, torch.randn(4 * hc, C + hc, k, k, device="cuda") * 0.05, torch.zeros(4 * hc, device="cuda"))
@@ -29,6 +29,7 @@ for _ in range(2):
     if which == "fwd":
         _lib.check(lib.nint_debug_read_trace(buf, N, 1), "trace")
 if which == "bwd":
+    _lib.check(lib.nint_debug_read_trace(buf, N, 1), "trace")   # drop the forward's stamps
     plan.backward(torch.randn_like(pred))  # last conv launch = dgrad step t = 0
     _lib.check(lib.nint_debug_read_trace(buf, N, 1), "trace")
 tr = [[v for v in buf[r * 1024:(r + 1) * 1024] if v] for r in range(8)]
