@@ -55,6 +55,46 @@ def training_loss(pred: torch.Tensor, y: torch.Tensor, crop: Optional[Tuple[int,
     return F.mse_loss(p, y) + F.l1_loss(p, y)
 
 
+class HostFeeder:
+    """Double-buffered host -> device input path: the pinned-memory copy of batch i+1 (train.py:92-93) runs on a
+    side stream while batch i trains.  `put` starts the copy and returns a handle, `get` makes the current stream
+    wait for it, `release` marks the device buffers reusable once the step that read them has been enqueued."""
+
+    def __init__(self, device, depth: int = 2):
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(self.device)
+        self.slots = [None] * depth
+        self.i = 0
+
+    def put(self, xh: torch.Tensor, yh: torch.Tensor):
+        k = self.i % len(self.slots)
+        self.i += 1
+        slot = self.slots[k]
+        if slot is None or slot["x"].shape != xh.shape or slot["y"].shape != yh.shape:
+            slot = {"x": torch.empty(xh.shape, dtype=xh.dtype, device=self.device),
+                    "y": torch.empty(yh.shape, dtype=yh.dtype, device=self.device),
+                    "ready": torch.cuda.Event(), "free": None}
+            self.slots[k] = slot
+        with torch.cuda.stream(self.stream):
+            if slot["free"] is not None:
+                self.stream.wait_event(slot["free"])      # the step that last read this slot has finished
+            slot["x"].copy_(xh, non_blocking=True)
+            slot["y"].copy_(yh, non_blocking=True)
+            slot["ready"].record(self.stream)
+        return slot
+
+    @staticmethod
+    def get(slot):
+        torch.cuda.current_stream().wait_event(slot["ready"])
+        return slot["x"], slot["y"]
+
+    @staticmethod
+    def release(slot):
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        slot["free"] = ev
+
+
 class Trainer:
     def __init__(self, model, lr: float = 1e-3, betas=(0.5, 0.999), crop=None, process_group=None):
         self.model, self.crop = model, crop

@@ -9,7 +9,7 @@ $CMD > gpurun_out/plain_$TAG.log 2>&1 || { echo "plain run failed"; tail -20 gpu
 tail -1 gpurun_out/plain_$TAG.log
 # launch list of the two timed steps (3 warm-up steps = 3*~33 launches skipped)
 if [ -z "${SKIP_LIST:-}" ]; then
-ncu --metrics gpu__time_duration.sum --clock-control none -s 100 -c 120 --csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -s 150 -c 130 --csv \
     --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_list_$TAG.log 2>&1
 echo "launch list rc=$?"
 fi
@@ -20,7 +20,7 @@ echo "fwd capture rc=$?"
 ncu --set full --clock-control none --import-source on -k 'regex:conv_halo_kernel' -s 86 -c 1 \
     -o gpurun_out/prof_bwd_$TAG -f $CMD > gpurun_out/ncu_bwd_$TAG.log 2>&1
 echo "bwd capture rc=$?"
-ncu --set full --clock-control none --import-source on -k 'regex:^wgrad_kernel' -s 3 -c 1 \
+ncu --set full --clock-control none --import-source on -k 'regex:wgrad_' -s 3 -c 1 \
     -o gpurun_out/prof_wgrad_$TAG -f $CMD > gpurun_out/ncu_wgrad_$TAG.log 2>&1
 echo "wgrad capture rc=$?"
 ls -la gpurun_out/
