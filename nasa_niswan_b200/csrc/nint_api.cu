@@ -107,6 +107,7 @@ struct nint_plan {
   int cluster = 2;        // 2: CTA pairs (tcgen05 cta_group::2) where the layer geometry allows, 1: single CTAs
   int base_offset_mode = 0;
   int debug_flags = 0;
+  int plan_g = 0, plan_ns = 0;   // NINT_PLAN_G / NINT_PLAN_NS: experiment knobs of the backward kernel's shared-memory plan
   Profile prof;
 };
 
@@ -286,6 +287,7 @@ inline float* cslot_ptr(const nint_plan* p, const Layer& y, int slot) {
 void fill_common(const nint_plan* p, const Layer& y, ConvGemmParams& g) {
   memset(&g, 0, sizeof(g));
   g.debug_flags = p->debug_flags;
+  g.plan_g = p->plan_g; g.plan_ns = p->plan_ns;
   g.B = p->B; g.H = p->H; g.W = p->W;
   g.tile_w = p->tile_w; g.tile_h = p->tile_h; g.tiles_x = p->tiles_x; g.tiles_y = p->tiles_y;
   g.hc = y.hc; g.hc_pad = y.hc_pad; g.hcb = y.hcb;
@@ -426,6 +428,10 @@ int nint_plan_create(const nint_config* cfg, nint_plan** out) {
     p->base_offset_mode = b ? atoi(b) : 0;
     const char* d = getenv("NINT_DEBUG_FLAGS");
     p->debug_flags = d ? atoi(d) : 0;
+    const char* pg = getenv("NINT_PLAN_G");
+    p->plan_g = pg ? atoi(pg) : 0;
+    const char* pn = getenv("NINT_PLAN_NS");
+    p->plan_ns = pn ? atoi(pn) : 0;
   }
   pick_tile(p->H, p->W, &p->tile_w, &p->tile_h);
   p->tiles_x = (p->W + p->tile_w - 1) / p->tile_w;

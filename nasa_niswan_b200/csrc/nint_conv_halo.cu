@@ -95,6 +95,17 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
   const int G = p.group;
   const TileWalk walk = make_walk(p, S, static_cast<int>(crank));
   const bool resident = p.w_resident != 0;   // the whole weight slice of this n-block fits: load it once
+  // forward, resident 3x3 weights: TWO warps issue MMAs (alternate chunks).  The issuing thread only runs a few MMAs
+  // ahead of the tensor pipe, so one issuer loses its ~500 cycles of per-chunk barrier work as tensor idle time;
+  // with two, one warp's waits and commits hide behind the other's MMA stream.
+  int chunks_per_tile = 0;
+  bool all_k3 = true;
+  for (int s = 0; s < p.nseg; ++s) {
+    chunks_per_tile += p.seg[s].nchunks;
+    all_k3 = all_k3 && p.seg[s].ksize == 3;
+  }
+  const bool dual = EPI == EPI_FWD && resident && G == 1 && all_k3 && TS == 9 && NA >= 4 && !(p.debug_flags & 32);
+  volatile uint32_t* mma_started = reinterpret_cast<volatile uint32_t*>(ctrl + kHaloCtrlBytes - 32);
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.nseg; ++s) {
@@ -116,8 +127,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
       mbar_init(&w_full[s], 1);
       mbar_init(&w_empty[s], 1);
     }
+    *mma_started = 0;
     for (int s = 0; s < kMaxAcc; ++s) {
-      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tfull_bar[s], (dual && chunks_per_tile >= 2) ? 2 : 1);   // one commit per issuing warp
       mbar_init(&tempty_bar[s], 8 * S);   // the leader waits for the epilogue warps of both CTAs
     }
     for (int s = 0; s < kEpiMaxStages; ++s) {
@@ -216,6 +228,63 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
       first = false;
     }
   };
+  // ------------------------------------------------------------------ dual MMA issuer (see `dual` above)
+  auto issue_dual = [&](int which) {
+    const bool leader = elect_one();
+    Tracer tr(p, 1, leader && which == 0);
+    const bool issue_any = !(p.debug_flags & 2);
+    const int n_acc = p.n_acc, acc_cols = p.acc_cols, a_buf_bytes = p.a_buf_bytes;
+    const uint32_t idesc = p.idesc;
+    const uint32_t w16l = static_cast<uint32_t>(w_bytes >> 4);
+    const uint32_t sA_addr = smem_u32(sA), sW_addr = smem_u32(sW);
+    const int ntiles = (walk.tiles_padded - walk.first_tile + walk.tile_stride - 1) / walk.tile_stride;
+    const int cpt = chunks_per_tile;
+    const int total = walk.first_tile < walk.tiles_padded ? ntiles * cpt : 0;
+    const uint64_t adesc0 = make_smem_desc_sw64(0, 16, 10 * kChunkBytes);   // 3x3: halo pitch 10 pixels
+    const uint64_t bdesc0 = make_smem_desc_sw64(0, 16, 512);
+    const uint32_t ahi = static_cast<uint32_t>(adesc0 >> 32), bhi = static_cast<uint32_t>(bdesc0 >> 32);
+    for (int c = which; c < total; c += 2) {
+      const int k = c / cpt, j = c - k * cpt;          // tile of this CTA, chunk inside the tile
+      const int ia = c % NA;
+      const uint32_t pa = static_cast<uint32_t>(c / NA) & 1u;
+      const int abuf = k % n_acc;
+      const uint32_t aphase = static_cast<uint32_t>(k / n_acc) & 1u;
+      tr.stamp();
+      if (j == 0) mbar_wait(&tempty_bar[abuf], aphase ^ 1);
+      mbar_wait(&a_full[ia], pa);
+      if (k == 0) mbar_wait(&w_full[j], 0);            // resident weights arrive during the first tile
+      // chunks enter the tensor pipe strictly in order (deterministic accumulation order, and the tile's first
+      // MMA with accumulate = 0 precedes the rest): wait until the other warp has issued all of chunk c-1
+      while (*mma_started < static_cast<uint32_t>(c)) { }
+      tc_fence_after();
+      tr.stamp();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(abuf * acc_cols);
+      if (leader && issue_any) {
+        const uint32_t alo = static_cast<uint32_t>(adesc0) + ((sA_addr + ia * a_buf_bytes) >> 4);
+        const uint32_t blo = static_cast<uint32_t>(bdesc0) + ((sW_addr + j * stage_bytes) >> 4);
+#pragma unroll 1
+        for (int dy = 0; dy < 3; ++dy) {
+          const uint32_t ar = alo + static_cast<uint32_t>(dy * 10 * (kChunkBytes >> 4));
+          const uint32_t br = blo + static_cast<uint32_t>(dy * 3) * w16l;
+#pragma unroll
+          for (int dxc = 0; dxc < 3; ++dxc) {
+            const uint32_t acc = (j | dy | dxc) == 0 ? 0u : 1u;
+            umma_lohi<DT, pair>(d_tmem, ar + 4 * dxc, ahi, br + dxc * w16l, bhi, idesc, acc);
+            umma_lohi<DT, pair>(d_tmem, ar + 4 * dxc + 2, ahi, br + dxc * w16l + 2, bhi, idesc, 1u);
+          }
+        }
+      }
+      if (leader) {
+        __threadfence_block();
+        *mma_started = static_cast<uint32_t>(c + 1);   // chunk c fully issued
+      }
+      __syncwarp();
+      umma_commit_elect<pair>(&a_empty[ia]);
+      if (c + 2 >= (k + 1) * cpt) umma_commit_elect<pair>(&tfull_bar[abuf]);   // this warp's last chunk of the tile
+      tr.stamp();
+    }
+  };
+
   // two activation producers when a tile needs many chunk loads (dgrad: K = 4*hc channels, G tiles per chunk)
   const bool a_split = (EPI == EPI_BWD);
 
@@ -230,7 +299,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
     // The loop body between two tcgen05.mma must stay a handful of uniform-datapath instructions: every kernel
     // parameter it needs is hoisted into a local, descriptors advance by adds (timeline traces showed ~190
     // cycles per MMA of pure issue overhead before, against 64-cycle MMAs).
-    if (p.nseg > 0 && lead_cta) {
+    if (p.nseg > 0 && lead_cta && dual) {
+      issue_dual(0);
+    } else if (p.nseg > 0 && lead_cta) {
       const bool leader = elect_one();
       Tracer tr(p, 1, leader);
       const bool issue_any = !(p.debug_flags & 2);
@@ -284,8 +355,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
           nabuf = 0;
           naphase ^= 1;
         }
+        // 3x3 single-stage chunks take these waits BETWEEN the tap rows of the MMA stream (fast path below): the
+        // issuing thread only runs a few MMAs ahead of the tensor pipe, so a 300-cycle block of waits between two
+        // chunks idles the pipe, while three ~100-cycle pieces hide behind the rows already issued
+        const bool fast = lookahead && issue_any && p.seg[cs].ksize == 3 && TS == 9 && G == 2 && (resident || w_ahead);
         tr.stamp();
-        if (lookahead) {
+        if (lookahead && !fast) {
           if (nvalid) {
             if (last_of_tile) mbar_wait(&tempty_bar[nabuf], naphase ^ 1);
             mbar_wait(&a_full[nia], npa);
@@ -315,6 +390,58 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
         // pixel (64 B) per tap and skips the rest of the halo row when dx wraps
         uint64_t adesc = make_smem_desc_sw64(sA_addr + ia * a_buf_bytes, 16, sbo);
         int dx = 0;
+        if (fast) {
+          if (resident && first) {
+            mbar_wait(&w_full[iw], pw);
+            tc_fence_after();
+          }
+          const uint64_t bdesc = make_smem_desc_sw64(sW_addr + iw * stage_bytes, 16, 512);
+          const uint32_t alo = static_cast<uint32_t>(adesc), blo = static_cast<uint32_t>(bdesc);
+          const uint32_t ahi = static_cast<uint32_t>(adesc >> 32), bhi = static_cast<uint32_t>(bdesc >> 32);
+          const uint32_t w16l = static_cast<uint32_t>(w16);
+          const uint32_t halo16l = static_cast<uint32_t>(a_halo16);
+          const uint32_t d1 = d_tmem + n_tile;
+          // one tap row: descriptor offsets inside a row are compile-time constants (one pixel = 64 B apart), rows
+          // are one halo pitch (10 pixels) apart
+          auto issue_row = [&](int dy) {
+            if (leader) {
+              const uint32_t ar = alo + static_cast<uint32_t>(dy * 10 * (kChunkBytes >> 4));
+              const uint32_t br = blo + static_cast<uint32_t>(dy * 3) * w16l;
+              if (G == 1) {
+#pragma unroll
+                for (int dxc = 0; dxc < 3; ++dxc) {
+                  const uint32_t acc = (dy | dxc) == 0 ? accumulate : 1u;
+                  umma_lohi<DT, pair>(d_tmem, ar + 4 * dxc, ahi, br + dxc * w16l, bhi, idesc, acc);
+                  umma_lohi<DT, pair>(d_tmem, ar + 4 * dxc + 2, ahi, br + dxc * w16l + 2, bhi, idesc, 1u);
+                }
+              } else {
+#pragma unroll
+                for (int dxc = 0; dxc < 3; ++dxc) {
+                  const uint32_t acc = (dy | dxc) == 0 ? accumulate : 1u;
+                  umma_lohi<DT, pair>(d_tmem, ar + 4 * dxc, ahi, br + dxc * w16l, bhi, idesc, acc);
+                  umma_lohi<DT, pair>(d1, ar + halo16l + 4 * dxc, ahi, br + dxc * w16l, bhi, idesc, acc);
+                  umma_lohi<DT, pair>(d_tmem, ar + 4 * dxc + 2, ahi, br + dxc * w16l + 2, bhi, idesc, 1u);
+                  umma_lohi<DT, pair>(d1, ar + halo16l + 4 * dxc + 2, ahi, br + dxc * w16l + 2, bhi, idesc, 1u);
+                }
+              }
+            }
+            __syncwarp();
+          };
+          issue_row(0);
+          if (nvalid && last_of_tile) mbar_wait(&tempty_bar[nabuf], naphase ^ 1);
+          issue_row(1);
+          if (nvalid) {
+            mbar_wait(&a_full[nia], npa);
+            if (w_ahead) mbar_wait(&w_full[(iw + 1 == NW) ? 0 : iw + 1], (iw + 1 == NW) ? pw ^ 1 : pw);
+            tc_fence_after();
+          }
+          issue_row(2);
+          if (!resident) umma_commit_elect<pair>(&w_empty[iw]);
+          if (++iw == NW) {
+            iw = 0;
+            pw ^= 1;
+          }
+        } else
         for (int tap0 = 0; tap0 < taps; tap0 += TS) {
           if ((!resident || first) && !w_ahead) {
             mbar_wait(&w_full[iw], pw);
@@ -327,7 +454,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
             const uint32_t ahi = static_cast<uint32_t>(adesc >> 32), bhi = static_cast<uint32_t>(bdesc >> 32);
             const uint32_t w16l = static_cast<uint32_t>(w16), skipl = static_cast<uint32_t>(row_skip);
             int dxl = dx;
-            if (G == 1) {
+            if (false) {
+            } else if (G == 1) {
 #pragma unroll 3
               for (int j = 0; j < TS; ++j) {
                 umma_lohi<DT, pair>(d_tmem, alo, ahi, blo, bhi, idesc, accumulate);
@@ -408,6 +536,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
     if constexpr (EPI == EPI_BWD) epi_loader<E, EPI>(p, sE, e_full, e_empty, walk, warp - 4, 2);
     if constexpr (EPI == EPI_FWD) {
       if (warp == 4) epi_loader<E, EPI>(p, sE, e_full, e_empty, walk, 0, 1);
+      if (warp == 5 && p.nseg > 0 && lead_cta && dual) issue_dual(1);   // second MMA issuer
     }
   } else if (warp >= kConvIoWarps) {
     // ------------------------------------------------------------------ epilogue math (warps 4-11)
@@ -501,11 +630,13 @@ int conv_halo_plan(int epi, int dtype, ConvGemmParams& p) {
   // preference order: >= 3 halo buffers (the MMA issuer waits one chunk ahead) with 3 weight stages of `want` taps,
   // first with three epilogue stages then two; after that relax the tap count, then the group size, then the buffers
   int NS = -1, G = 1, ts = 1, min_na = 3;
+  if (p.plan_g > 0 && p.plan_g < gmax) gmax = p.plan_g;               // experiment knobs (NINT_PLAN_G / NINT_PLAN_NS)
+  const int ns_hi = (p.plan_ns >= ns_min && p.plan_ns <= ns_max) ? p.plan_ns : ns_max;
   for (int pass = 0; pass < 2 && NS < 0; ++pass, min_na = 2)
     for (int cand = want; cand >= 1 && NS < 0; --cand) {
       if (!divides_all(cand)) continue;
       for (int g = gmax; g >= 1 && NS < 0; --g)
-        for (int ns = ns_max; ns >= ns_min; --ns)
+        for (int ns = ns_hi; ns >= ns_min; --ns)
           if (total - ns * p.e_stage_bytes >= min_na * g * p.a_halo_bytes + 3 * cand * w_bytes) {
             NS = ns;
             G = g;

@@ -45,6 +45,7 @@ struct alignas(64) ConvGemmParams {
   int na_bufs, a_buf_bytes, cluster, base_offset_mode, taps_per_stage;
   int group, a_halo_bytes;  // tiles per group (side-by-side accumulators), bytes of one halo chunk
   int acc_cols, n_acc;      // TMEM columns of one accumulator buffer (group * n_tile), number of buffers (2 or 4)
+  int plan_g, plan_ns;      // experiment knobs for conv_halo_plan: cap on tiles per group / epilogue stages (0 = auto)
   int w_resident;           // 1: num_stages covers a tile's whole K walk; weights are loaded once per CTA
   int debug_flags;          // experiments: 1 = epilogue does no memory ops / math, 2 = no MMA issue
   // ---- TMA-staged epilogue I/O (nint_epilogue.cuh): 5-D maps (channel, x, y, image, slot) of the layer's

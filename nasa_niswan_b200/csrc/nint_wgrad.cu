@@ -484,6 +484,13 @@ wgrad_pair_kernel(const __grid_constant__ WgradParams p) {
       const uint32_t alo_base = static_cast<uint32_t>(adesc_base), blo_base = static_cast<uint32_t>(bdesc_base);
       const uint32_t sA16 = smem_u32(sA) >> 4, sB16 = smem_u32(sB) >> 4;
       const int dy0 = tap_begin / ksize, dx0 = tap_begin % ksize;
+      const uint32_t krow16 = static_cast<uint32_t>((2 * hpitch * 32) >> 4);   // one K step = two halo rows
+      uint32_t tap_off[5];
+#pragma unroll
+      for (int ti = 0; ti < 5; ++ti) {
+        const int tp = tap_begin + (ti < ntaps ? ti : 0);
+        tap_off[ti] = static_cast<uint32_t>((((tp / ksize) * hpitch + tp % ksize) * 32) >> 4);
+      }
       int ab = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
       mbar_wait(&a_full[0], 0);
@@ -505,26 +512,45 @@ wgrad_pair_kernel(const __grid_constant__ WgradParams p) {
           const uint32_t a0 = alo_base + sA16 + static_cast<uint32_t>((ab * a_buf_bytes) >> 4);
           const uint32_t b0 = blo_base + sB16 + static_cast<uint32_t>((bs * b_stage_bytes) >> 4);
           uint32_t acc = i != 0 ? 1u : 0u;
-#pragma unroll 1
-          for (int ks = 0; ks < 8; ++ks) {
-            // K step = 16 pixels = 2 tile rows: A advances 16 x 128 B, B two halo rows
-            const uint32_t alo = a0 + static_cast<uint32_t>(ks * 128);
-            uint32_t blo = b0 + static_cast<uint32_t>((((2 * ks + dy0) * hpitch + dx0) * 32) >> 4);
-            uint32_t d = tmem_base;
-            int dx = dx0;
-            for (int ti = 0; ti < ntaps; ++ti) {
-              umma_lohi<NINT_BF16, true>(d, alo, ahi, blo, bhi, idesc, acc);
-              d += ncols;
-              blo += 2;
-              if (++dx == ksize) {
-                dx = 0;
-                blo += static_cast<uint32_t>(((hpitch - ksize) * 32) >> 4);
+          if (ntaps <= 5) {
+            // per-tap B offsets are loop invariants: the MMA stream is adds + tcgen05.mma only
+#pragma unroll 2
+            for (int ks = 0; ks < 8; ++ks) {
+              // K step = 16 pixels = 2 tile rows: A advances 16 x 128 B, B two halo rows
+              const uint32_t alo = a0 + static_cast<uint32_t>(ks * 128);
+              const uint32_t bk = b0 + static_cast<uint32_t>(ks) * krow16;
+              uint32_t d = tmem_base;
+#pragma unroll
+              for (int ti = 0; ti < 5; ++ti) {
+                if (ti < ntaps) umma_lohi<NINT_BF16, true>(d, alo, ahi, bk + tap_off[ti], bhi, idesc, acc);
+                d += ncols;
               }
+              if (do_bias)
+                umma_lohi<NINT_BF16, true>(tmem_base + static_cast<uint32_t>(ntaps) * ncols, alo, ahi,
+                                           static_cast<uint32_t>(odesc), static_cast<uint32_t>(odesc >> 32), idesc_bias, acc);
+              acc = 1;
             }
-            if (do_bias)
-              umma_lohi<NINT_BF16, true>(d, alo, ahi, static_cast<uint32_t>(odesc), static_cast<uint32_t>(odesc >> 32),
-                                         idesc_bias, acc);
-            acc = 1;
+          } else {
+#pragma unroll 1
+            for (int ks = 0; ks < 8; ++ks) {
+              const uint32_t alo = a0 + static_cast<uint32_t>(ks * 128);
+              uint32_t blo = b0 + static_cast<uint32_t>((((2 * ks + dy0) * hpitch + dx0) * 32) >> 4);
+              uint32_t d = tmem_base;
+              int dx = dx0;
+              for (int ti = 0; ti < ntaps; ++ti) {
+                umma_lohi<NINT_BF16, true>(d, alo, ahi, blo, bhi, idesc, acc);
+                d += ncols;
+                blo += 2;
+                if (++dx == ksize) {
+                  dx = 0;
+                  blo += static_cast<uint32_t>(((hpitch - ksize) * 32) >> 4);
+                }
+              }
+              if (do_bias)
+                umma_lohi<NINT_BF16, true>(d, alo, ahi, static_cast<uint32_t>(odesc), static_cast<uint32_t>(odesc >> 32),
+                                           idesc_bias, acc);
+              acc = 1;
+            }
           }
         }
         __syncwarp();

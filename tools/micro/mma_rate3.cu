@@ -59,7 +59,7 @@ int main() {
   long long* out; cudaMalloc(&out, 64 * 8);
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   const int iters = 2048;
-  for (int n : {64, 128, 256}) for (int nw : {1, 2, 4}) {
+  for (int n : {16, 32, 64, 128, 256}) for (int nw : {1, 2, 4}) {
     if (n * nw > 512) continue;
     k<<<148, 256, 200 * 1024>>>(n, nw, iters, out);
     cudaError_t e = cudaDeviceSynchronize();
