@@ -47,7 +47,7 @@ static int halo_operand_bytes(int a_buf_bytes, int na, int n_tile, int nw, int t
 }
 int conv_halo_smem_bytes(const ConvGemmParams& p) {
   return 1024 + halo_operand_bytes(p.a_buf_bytes, p.na_bufs, p.n_tile, p.num_stages, p.taps_per_stage, p.cluster) +
-         p.e_stages * p.e_stage_bytes + kHaloCtrlBytes + (4 * p.hc + p.hc) * 4;
+         p.e_stages * p.e_stage_bytes + p.c_ring * kEpiBoxBytes16 + kHaloCtrlBytes + (4 * p.hc + p.hc) * 4;
 }
 
 __device__ __forceinline__ int halo_operand_bytes_dev(int a_buf_bytes, int na, int stage_bytes, int nw) {
@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
   uint8_t* sA = smem;
   uint8_t* sW = sA + NA * p.a_buf_bytes;
   uint8_t* sE = smem + halo_operand_bytes_dev(p.a_buf_bytes, NA, stage_bytes, NW);   // epilogue I/O stages
-  uint8_t* ctrl = sE + p.e_stages * p.e_stage_bytes;
+  uint8_t* ctrl = sE + p.e_stages * p.e_stage_bytes + p.c_ring * kEpiBoxBytes16;
   uint64_t* a_full = reinterpret_cast<uint64_t*>(ctrl);
   uint64_t* a_empty = a_full + kHaloMaxA;
   uint64_t* w_full = a_empty + kHaloMaxA;
@@ -83,6 +83,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
   uint64_t* e_full = tempty_bar + kMaxAcc;
   uint64_t* e_empty = e_full + kEpiMaxStages;
   uint64_t* st_ready = e_empty + kEpiMaxStages;
+  uint64_t* hg_ready = st_ready + kEpiMaxStages;   // forward only: h + gates output stages
+  uint64_t* hg_empty = hg_ready + kEpiMaxStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ctrl + kHaloCtrlBytes - 16);
   float* s_bias = reinterpret_cast<float*>(ctrl + kHaloCtrlBytes);
   float* s_headw = s_bias + 4 * p.hc;
@@ -136,6 +138,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
       mbar_init(&e_full[s], 1);
       mbar_init(&e_empty[s], 1);
       mbar_init(&st_ready[s], 8);         // one arrive per epilogue warp
+      mbar_init(&hg_ready[s], 8);
+      mbar_init(&hg_empty[s], 1);
     }
     fence_barrier_init();
   }
@@ -528,14 +532,16 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
       }
     }
   } else if (warp == 2 || warp == 3) {
-    // ------------------------------------------------------------------ epilogue TMA stores (alternate channel groups)
-    if constexpr (EPI != EPI_RAW) epi_storer<E, EPI>(p, sE, st_ready, e_empty, walk, warp - 2, 2);
+    // ------------------------------------------------------------------ epilogue TMA stores
+    // backward: the two warps alternate channel groups; forward: warp 3 stores c, warp 2 stores h + gates
+    if constexpr (EPI == EPI_BWD) epi_storer<E, EPI>(p, sE, st_ready, e_empty, walk, warp - 2, 2);
+    if constexpr (EPI == EPI_FWD) fwd_storer<E>(p, sE, FwdEpiBars{e_full, e_empty, st_ready, hg_ready, hg_empty}, walk, warp == 3 ? 0 : 1);
   } else if (warp == 4 || warp == 5) {
     // ------------------------------------------------------------------ epilogue TMA loads
     // backward: 4 boxes per channel group, two loaders alternate groups; forward: one box per group, warp 4 only
     if constexpr (EPI == EPI_BWD) epi_loader<E, EPI>(p, sE, e_full, e_empty, walk, warp - 4, 2);
     if constexpr (EPI == EPI_FWD) {
-      if (warp == 4) epi_loader<E, EPI>(p, sE, e_full, e_empty, walk, 0, 1);
+      if (warp == 4) fwd_c_loader<E>(p, sE, FwdEpiBars{e_full, e_empty, st_ready, hg_ready, hg_empty}, walk);
       if (warp == 5 && p.nseg > 0 && lead_cta && dual) issue_dual(1);   // second MMA issuer
     }
   } else if (warp >= kConvIoWarps) {
@@ -545,6 +551,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
     if constexpr (pair) tempty_remote = mapa_rank(smem_u32(&tempty_bar[0]), 0);
     if constexpr (EPI == EPI_RAW)
       epi_raw(p, warp, lane, tmem_base, tfull_bar, tempty_bar, walk, tempty_remote);
+    else if constexpr (EPI == EPI_FWD)
+      fwd_math<E>(p, warp, lane, tmem_base, sE, FwdEpiBars{e_full, e_empty, st_ready, hg_ready, hg_empty}, tfull_bar,
+                  tempty_bar, s_bias, walk, tempty_remote);
     else
       epi_math<E, EPI>(p, warp, lane, tmem_base, sE, e_full, st_ready, tfull_bar, tempty_bar, s_bias, s_headw, walk,
                        tempty_remote);
@@ -563,12 +572,14 @@ int conv_halo_plan(int epi, int dtype, ConvGemmParams& p) {
   const int esize = dtype == NINT_BF16 ? 2 : 4;
   // ---- epilogue stage layout (nint_epilogue.cuh): [gates][c / c_t][c_{t-1}][dc] or [gates][c][h]
   const int gate_bytes = kTilePixels * 64 * esize;
+  p.c_ring = 0;
   if (epi == EPI_FWD) {
+    // forward: output stages [gates][h] plus a separate ring of c slots (nint_epilogue.cuh)
     const int g = p.slot_g >= 0 ? gate_bytes : 0;
-    p.e_off_c = g;
-    p.e_off_h = g + kEpiBoxBytes16;
-    p.e_off_c2 = p.e_off_dc = 0;
-    p.e_stage_bytes = (p.e_off_h + kTilePixels * 16 * esize + 1023) & ~1023;
+    p.e_off_h = g;
+    p.e_off_c = p.e_off_c2 = p.e_off_dc = 0;
+    p.e_stage_bytes = (g + kTilePixels * 16 * esize + 1023) & ~1023;
+    p.c_ring = 3;
   } else if (epi == EPI_BWD) {
     p.e_off_c = gate_bytes;
     p.e_off_c2 = p.e_off_c + kEpiBoxBytes16;
@@ -581,9 +592,9 @@ int conv_halo_plan(int epi, int dtype, ConvGemmParams& p) {
   }
   p.a_halo_bytes = halo_a_buf_bytes(p);
   if (p.a_halo_bytes == 0) p.a_halo_bytes = 1024;
-  const int total = 227 * 1024 - 1024 - kHaloCtrlBytes - (4 * p.hc + p.hc) * 4 - 1024;
+  const int total = 227 * 1024 - 1024 - kHaloCtrlBytes - (4 * p.hc + p.hc) * 4 - 1024 - p.c_ring * kEpiBoxBytes16;
   const int w_bytes = (p.n_tile / p.cluster) * kChunkBytes;
-  const int ns_max = epi == EPI_RAW ? 0 : 3, ns_min = epi == EPI_RAW ? 0 : 2;
+  const int ns_max = epi == EPI_RAW ? 0 : (epi == EPI_FWD ? 2 : 3), ns_min = epi == EPI_RAW ? 0 : 2;
   int max_k = 1;
   for (int s = 0; s < p.nseg; ++s) if (p.seg[s].ksize > max_k) max_k = p.seg[s].ksize;
   // ---- plan A: weights resident.  One stage per (segment, chunk) holding all taps; needs >= 3 halo buffers.

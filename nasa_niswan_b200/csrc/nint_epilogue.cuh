@@ -19,7 +19,7 @@ namespace nint {
 
 constexpr int kConvIoWarps = 8;     // warps 0-7: TMA producers / loaders / storers and the MMA issuer (nint_conv_halo.cu)
 constexpr int kConvThreads = 512;   // warps 8-15: epilogue math
-constexpr int kEpiMaxStages = 4;
+constexpr int kEpiMaxStages = 4;    // ring depth limit (epilogue stages / forward c slots)
 constexpr int kEpiBoxBytes16 = kTilePixels * 16 * 4;   // 16 fp32 channels x 128 pixels = 8 KiB
 
 // ---- timeline trace (debug_flags & 8): CTA 0 records clock64() stamps per role into a global buffer that
@@ -167,6 +167,222 @@ __device__ __forceinline__ int group_q0(int ch) { return (ch >> 4) * 64; }
 template <int EPI>
 __device__ __forceinline__ int epi_groups(const ConvGemmParams& p) {
   return (EPI == EPI_FWD ? p.hcb : p.hc) >> 4;
+}
+
+// ====================================================================================================
+// Forward epilogue plumbing: TWO rings instead of one stage per channel group.
+//   c ring  (p.c_ring slots x 8 KiB): c_{t-1} is prefetched into a slot (deep: hides the HBM latency of the only
+//           load the forward epilogue has), updated in place by the math warps and stored back from there;
+//   hg ring (p.e_stages x [gates 16 KiB | h 4 KiB]): outputs only.
+// With a single ring the 28 KiB stage was held for load latency + math + store (~5000 cycles) and only two fit
+// next to the resident weights; split, the c slots turn over in ~4000 cycles / 3 and the hg stages in ~2300 / 2.
+//   loader (warp 4) --c_full--> math (warps 8-15) --c_ready--> c storer (warp 3) --c_empty--> loader
+//                               math --hg_ready--> hg storer (warp 2) --hg_empty--> math
+// ====================================================================================================
+struct FwdEpiBars {
+  uint64_t *c_full, *c_empty, *c_ready, *hg_ready, *hg_empty;
+};
+__device__ __forceinline__ uint8_t* fwd_c_slot(const ConvGemmParams& p, uint8_t* sE, int s) { return sE + s * kEpiBoxBytes16; }
+__device__ __forceinline__ uint8_t* fwd_hg_stage(const ConvGemmParams& p, uint8_t* sE, int s) {
+  return sE + p.c_ring * kEpiBoxBytes16 + s * p.e_stage_bytes;
+}
+
+template <typename E>
+__device__ __forceinline__ void fwd_c_loader(const ConvGemmParams& p, uint8_t* sE, const FwdEpiBars& b, const TileWalk& w) {
+  const bool leader = elect_one();
+  Tracer tr(p, 2, leader);
+  const int G = p.group, ngroups = p.hcb >> 4;
+  int s = 0;
+  uint32_t ph = 0;
+  for (int base = w.first_tile; base < w.tiles_padded; base += w.tile_stride) {
+    for (int gi = 0; gi < G; ++gi) {
+      const int tile = base + gi;
+      if (tile >= w.num_tiles) break;
+      const ItemCoord c = decode_tile(p, tile);
+      for (int grp = 0; grp < ngroups; ++grp) {
+        tr.stamp();
+        mbar_wait(&b.c_empty[s], ph ^ 1);
+        tr.stamp();
+        if (leader) {
+          if (p.slot_c_in >= 0) {
+            mbar_arrive_expect_tx(&b.c_full[s], kEpiBoxBytes16);
+            tma_load_5d(fwd_c_slot(p, sE, s), &p.tm_c, &b.c_full[s], w.nb * p.hcb + grp * 16, c.x0, c.y0, c.b, p.slot_c_in);
+          } else {
+            mbar_arrive(&b.c_full[s]);   // zero state: nothing to read, the slot is only an output buffer
+          }
+        }
+        tr.stamp();
+        if (++s == p.c_ring) {
+          s = 0;
+          ph ^= 1;
+        }
+      }
+    }
+  }
+}
+
+// kind 0: c slots (warp 3), kind 1: h + gates stages (warp 2)
+template <typename E>
+__device__ __forceinline__ void fwd_storer(const ConvGemmParams& p, uint8_t* sE, const FwdEpiBars& b, const TileWalk& w, int kind) {
+  using GE = EpiGeom<E>;
+  const bool leader = elect_one();
+  Tracer tr(p, 3, leader && kind == 1);
+  const int G = p.group, ngroups = p.hcb >> 4;
+  const int ring = kind == 0 ? p.c_ring : p.e_stages;
+  uint64_t* ready = kind == 0 ? b.c_ready : b.hg_ready;
+  uint64_t* empty = kind == 0 ? b.c_empty : b.hg_empty;
+  int s = 0;
+  uint32_t ph = 0;
+  for (int base = w.first_tile; base < w.tiles_padded; base += w.tile_stride) {
+    for (int gi = 0; gi < G; ++gi) {
+      const int tile = base + gi;
+      if (tile >= w.num_tiles) break;
+      const ItemCoord c = decode_tile(p, tile);
+      for (int grp = 0; grp < ngroups; ++grp) {
+        tr.stamp();
+        mbar_wait(&ready[s], ph);
+        tr.stamp();
+        if (leader) {
+          if (!(p.debug_flags & 1)) {
+            const int ch = w.nb * p.hcb + grp * 16;
+            if (kind == 0) {
+              tma_store_5d(&p.tm_c, fwd_c_slot(p, sE, s), ch, c.x0, c.y0, c.b, p.slot_c_out);
+            } else {
+              const uint8_t* st = fwd_hg_stage(p, sE, s);
+              tma_store_5d(&p.tm_h, st + p.e_off_h, ch, c.x0, c.y0, c.b, p.slot_h_out);
+              if (p.slot_g >= 0) {
+                const int q0 = group_q0(ch);
+#pragma unroll
+                for (int bx = 0; bx < GE::kGateBoxes; ++bx)
+                  tma_store_5d(&p.tm_g, st + bx * GE::kGateBoxBytes, q0 + bx * GE::kGateBoxCols, c.x0, c.y0, c.b, p.slot_g);
+              }
+            }
+            tma_store_commit();
+            tma_store_wait_read();   // the buffer may be overwritten once TMA has read it
+          }
+          mbar_arrive(&empty[s]);
+        }
+        tr.stamp();
+        if (++s == ring) {
+          s = 0;
+          ph ^= 1;
+        }
+      }
+    }
+  }
+  if (leader) tma_store_wait_all();   // global writes complete before the CTA exits
+}
+
+template <typename E>
+__device__ __forceinline__ void fwd_math(const ConvGemmParams& p, int warp, int lane, uint32_t tmem_base, uint8_t* sE,
+                                         const FwdEpiBars& b, uint64_t* tfull_bar, uint64_t* tempty_bar,
+                                         const float* s_bias, const TileWalk& w, uint32_t tempty_remote) {
+  using GE = EpiGeom<E>;
+  constexpr int DT = ElemTraits<E>::kDtype;
+  constexpr bool FAST = (DT == NINT_BF16);
+  const int G = p.group, ngroups = p.hcb >> 4;
+  const int quad = warp & 3;
+  const int half = (warp - kConvIoWarps) >> 2;
+  const int row = quad * 32 + lane;
+  const bool skip = (p.debug_flags & 1) != 0;
+  Tracer tr(p, 4, warp == kConvIoWarps && lane == 0);
+  int cs = 0, hs = 0;
+  uint32_t cph = 0, hph = 0;
+  int abuf = 0;
+  uint32_t aphase = 0;
+  for (int base = w.first_tile; base < w.tiles_padded; base += w.tile_stride) {
+    bool waited = false;
+    for (int gi = 0; gi < G; ++gi) {
+      const int tile = base + gi;
+      if (tile >= w.num_tiles) break;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
+                             static_cast<uint32_t>(abuf * p.acc_cols + gi * p.n_tile);
+      for (int grp = 0; grp < ngroups; ++grp) {
+        const uint32_t cslot = smem_u32(fwd_c_slot(p, sE, cs));
+        const uint32_t st = smem_u32(fwd_hg_stage(p, sE, hs));
+        tr.stamp();
+        mbar_wait(&b.c_full[cs], cph);
+        mbar_wait(&b.hg_empty[hs], hph ^ 1);
+        tr.stamp();
+        if (!waited) {
+          mbar_wait(&tfull_bar[abuf], aphase);
+          tc_fence_after();
+          waited = true;
+        }
+        tr.stamp();
+        // model.py:221-229.  accumulator columns of this group: grp*64 + gate*16 + channel
+        float a[4][8], cn[8], hn[8];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) tmem_ld8(taddr + grp * 64 + g * 16 + half * 8, a[g]);
+        if (p.slot_c_in >= 0 && !skip) {
+          lds8<float, 64>(cslot, row, half, cn);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) cn[j] = 0.f;
+        }
+        const uint32_t bq = smem_u32(s_bias + w.nb * p.n_tile + grp * 64 + half * 8);
+        tmem_ld_wait();
+        if (!skip) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float bias[8];
+            lds128(bq + g * 64, bias);
+            lds128(bq + g * 64 + 16, bias + 4);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a[g][j] += bias[j];
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float gi_ = act_sigmoid<FAST>(a[0][j]);
+            const float gf = act_sigmoid<FAST>(a[1][j]);
+            const float gg = act_tanh<FAST>(a[2][j]);
+            const float go = act_sigmoid<FAST>(a[3][j]);
+            const float cv = fmaf(cn[j], gf, gi_ * gg);
+            cn[j] = cv;
+            float hv = go * act_tanh<FAST>(cv);
+            if constexpr (DT == NINT_TF32) hv = round_tf32(hv);  // h feeds the next step's tf32 MMA
+            hn[j] = hv;
+            a[0][j] = gi_; a[1][j] = gf; a[2][j] = gg; a[3][j] = go;
+          }
+          sts8<float, 64>(cslot, row, half, cn);
+          sts8<E, GE::kHRowB>(st + p.e_off_h, row, half, hn);
+          if (p.slot_g >= 0) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) sts_gate<E>(st, row, g, half, a[g]);
+          }
+        }
+        // results visible to the async proxy (TMA store), then hand both buffers to their storers
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&b.c_ready[cs]);
+          mbar_arrive(&b.hg_ready[hs]);
+        }
+        tr.stamp();
+        if (++cs == p.c_ring) {
+          cs = 0;
+          cph ^= 1;
+        }
+        if (++hs == p.e_stages) {
+          hs = 0;
+          hph ^= 1;
+        }
+      }
+    }
+    if (!waited) {   // a group made only of padding tiles: still take part in the accumulator handshake
+      mbar_wait(&tfull_bar[abuf], aphase);
+      tc_fence_after();
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) {
+      if (tempty_remote) mbar_arrive_cluster(tempty_remote + abuf * 8); else mbar_arrive(&tempty_bar[abuf]);
+    }
+    if (++abuf == p.n_acc) {
+      abuf = 0;
+      aphase ^= 1;
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------ loader

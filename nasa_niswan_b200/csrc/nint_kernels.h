@@ -54,6 +54,7 @@ struct alignas(64) ConvGemmParams {
   int slot_c_in, slot_c_out, slot_h_out, slot_g;   // FWD: c_{t-1}, c_t, h_t, gates_t;  BWD: slot_g = gates_t / dgates_t
   int slot_c_cur, slot_c_prev, has_dc_in;          // BWD: c_t, c_{t-1}, dc_t present
   int e_stages, e_stage_bytes, e_off_c, e_off_c2, e_off_dc, e_off_h;
+  int c_ring;               // forward: slots of the separate c_{t-1} -> c_t ring (0 for the backward kernel)
   uint32_t idesc;
   int hc, hc_pad;  // hidden channels of this layer / padded channel count of its h tensor
   int hcb;         // hidden channels per n-block (n_tile / 4)
