@@ -123,6 +123,49 @@ def test_twelve_step_rollout_against_oracle(precision, ksize):
         assert O.max_abs_normalised(p.grad.cpu(), leaf[k].grad) < TOL[precision], k
 
 
+@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+@pytest.mark.parametrize("cfg", [
+    # (B, T, C, H, W, hidden, ksize): geometries that exercise the other kernel plans
+    (2, 3, 21, 20, 24, [128], [3]),          # hidden > 64: several n-blocks per pixel tile, two 256-q wgrad blocks
+    (2, 3, 5, 17, 13, [64, 64], [3, 3]),     # stacked layers with no padding lane (cin = 64), ragged 17x13 grid
+    (3, 2, 21, 16, 40, [64], [5]),           # 5x5 taps: weights stream through stages (not resident), 25-tap wgrad groups
+    (1, 4, 9, 33, 9, [32, 16], [3, 5]),      # small hidden sizes (single-CTA wgrad), odd tile counts, mixed k
+], ids=["h128", "h64x2_ragged", "k5_stream", "h32_h16_mixed"])
+def test_plans_against_oracle(cfg, precision):
+    """forward + BPTT against the CPU oracle for geometries whose shared-memory plans differ from the BASELINE one"""
+    from nasa_niswan_b200 import ConvLSTM
+    B, T, C, H, W, hidden, ks = cfg
+    torch.manual_seed(3)
+    net = ConvLSTM(C, hidden, ks, len(hidden), precision=precision)
+    params = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    net = net.cuda()
+    x, y = torch.randn(B, T, C, H, W), torch.randn(B, H, W)
+    leaf = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    ref_pred = O.convlstm_forward(x, leaf, len(hidden))
+    dpred = torch.autograd.grad(O.training_loss(ref_pred, y), ref_pred, retain_graph=True)[0]
+    ref_pred.backward(dpred)
+    pred = net(x.cuda())
+    assert O.max_abs_normalised(pred.detach().cpu(), ref_pred.detach()) < TOL[precision]
+    pred.backward(dpred.cuda())
+    for k, p in net.named_parameters():
+        assert O.max_abs_normalised(p.grad.cpu(), leaf[k].grad) < TOL[precision], k
+
+
+def test_long_inference_rollout_keeps_state_resident():
+    """BASELINE cfg 4 in miniature: forward-only T = 40 rollout (2-slot h ring, c updated in place) vs the oracle"""
+    from nasa_niswan_b200 import ConvLSTM
+    torch.manual_seed(4)
+    B, T, C, H, W, hc = 2, 40, 21, 24, 32, 64
+    net = ConvLSTM(C, [hc], [3], 1, precision="tf32")
+    params = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    net = net.cuda()
+    x = torch.randn(B, T, C, H, W)
+    with torch.no_grad():
+        pred = net(x.cuda())
+    ref = O.convlstm_forward(x, params, 1)
+    assert O.max_abs_normalised(pred.cpu(), ref) < TOL["tf32"]
+
+
 def test_return_sequence_variant(golden_dir):
     """commented-out variant model.py:264,272,274: (pred, hs[B,T,H,W]); grads flow through every step"""
     z, m = _load(golden_dir, CASES[0])
