@@ -78,6 +78,18 @@ int nint_forward(nint_plan* plan, const float* x, float* pred, float* seq, void*
 int nint_backward(nint_plan* plan, const float* dpred, const float* dseq, float* const* grad_weight,
                   float* const* grad_bias, float* grad_head_weight, float* grad_head_bias, void* stream);
 
+/* ---- the rest of the training step (train.py:101-110), SURVEY.md section 8f rank 1.
+ * nint_loss_mse_l1: loss = MSELoss(y, p) + L1Loss(y, p) (train.py:74-75,105) with p = pred[:, 0, y0:y1, x0:x1]
+ * (train.py:102 crop; pass 0, H, 0, W for none); pred [B,1,H,W], y [B, y1-y0, x1-x0]; writes the scalar loss, and
+ * d loss / d pred into dpred [B,1,H,W] (zero outside the crop; NULL = value only).  stats: 5 floats of device
+ * scratch, left holding {sum (p-y)^2, sum |p-y|, sum y, sum y^2, -} (enough for an on-device R^2, train.py:114).
+ * nint_adam_step: torch.optim.Adam (train.py:71; no weight decay / amsgrad) over one flat fp32 buffer; `step` counts
+ * from 1; grads are multiplied by grad_scale first (1 / world_size after a sum all-reduce). */
+int nint_loss_mse_l1(const float* pred, const float* y, int batch, int height, int width, int crop_y0, int crop_y1,
+                     int crop_x0, int crop_x1, float* dpred, float* loss, float* stats, void* stream);
+int nint_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr,
+                   float beta1, float beta2, float eps, int step, float grad_scale, void* stream);
+
 /* ---- measurement.  Kernel classes: 0 = fused gate-conv forward, 1 = dgrad + gate backward,
  * 2 = wgrad, 3 = everything else (layout packing, head, gradient unpacking); -1 = all.
  * nint_launch_count: kernels launched by this library in the calling process so far.

@@ -647,6 +647,26 @@ int nint_forward(nint_plan* p, const float* x, float* pred, float* seq, void* st
   return 0;
 }
 
+int nint_loss_mse_l1(const float* pred, const float* y, int batch, int height, int width, int crop_y0, int crop_y1,
+                     int crop_x0, int crop_x1, float* dpred, float* loss, float* stats, void* stream) {
+  if (!pred || !y || !loss || !stats) return fail("nint_loss_mse_l1: null argument");
+  if (batch < 1 || height < 1 || width < 1) return fail("nint_loss_mse_l1: bad shape");
+  if (crop_y0 < 0 || crop_y1 > height || crop_y0 >= crop_y1 || crop_x0 < 0 || crop_x1 > width || crop_x0 >= crop_x1)
+    return fail("nint_loss_mse_l1: crop [%d:%d, %d:%d] outside %dx%d", crop_y0, crop_y1, crop_x0, crop_x1, height, width);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  LAUNCH(nullptr, K_OTHER, st, launch_loss_mse_l1(pred, y, dpred, stats, loss, batch, height, width, crop_y0, crop_y1, crop_x0, crop_x1, st));
+  return 0;
+}
+
+int nint_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr,
+                   float beta1, float beta2, float eps, int step, float grad_scale, void* stream) {
+  if (!params || !grads || !exp_avg || !exp_avg_sq) return fail("nint_adam_step: null argument");
+  if (n < 0 || step < 1) return fail("nint_adam_step: n >= 0 and step >= 1 required");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  LAUNCH(nullptr, K_OTHER, st, launch_adam(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step, grad_scale, st));
+  return 0;
+}
+
 int nint_debug_read_trace(long long* host, int n, int clear) {
   if (!host || n < 0) return fail("nint_debug_read_trace: bad arguments");
   CK(cudaDeviceSynchronize());

@@ -137,6 +137,13 @@ cudaError_t launch_head_bwd(int dtype, const void* h, const float* dpred, long l
 cudaError_t launch_unpack_wgrad(const float* dw_acc, const float* db_acc, float* gw, float* gb, int cin, int hc,
                                 int k, int ncols, int cx_pad, int accumulate, cudaStream_t s);
 
+// fused training loss MSE + L1 on the cropped prediction (value + gradient); stats = 5 floats of scratch
+cudaError_t launch_loss_mse_l1(const float* pred, const float* y, float* dpred, float* stats, float* loss, int B, int H,
+                               int W, int y0, int y1, int x0, int x1, cudaStream_t s);
+// Adam step over a flat fp32 parameter buffer
+cudaError_t launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                        float eps, int step, float grad_scale, cudaStream_t s);
+
 // q-order helper (host + device)
 __host__ __device__ inline int q_to_n(int q, int hc) { return ((q >> 4) & 3) * hc + (q >> 6) * 16 + (q & 15); }
 

@@ -318,50 +318,52 @@ cudaError_t launch_head_fwd(int dtype, const void* h, const float* w, const floa
 }
 
 // head backward: dw[c] = sum_pix dpred[pix] * h[pix][c], db = sum dpred   (dh is fused into the
-// gate-backward epilogue).  Thread = (pixel group, channel); block reduction + atomics.
+// gate-backward epilogue).
 template <typename E>
-__global__ void head_bwd_kernel(const E* __restrict__ h, const float* __restrict__ dpred, long long dpred_bstride,
-                                float* __restrict__ dw, float* __restrict__ db, long long npix, int B, int hc,
-                                int hc_pad) {
-  // blockDim = (32 channel lanes, 8 pixel rows); each block strides over pixels
+__global__ void __launch_bounds__(256) head_bwd_kernel(const E* __restrict__ h, const float* __restrict__ dpred,
+                                                       long long dpred_bstride, float* __restrict__ dw,
+                                                       float* __restrict__ db, long long npix, int B, int hc, int hc_pad) {
+  // one warp per pixel: lane l owns channels l, l+32, ... (a warp reads one contiguous row of h per pixel);
+  // partial sums stay in registers across the warp's pixels, then one block reduction + atomics
+  constexpr int KMAX = 8;   // hc_pad <= 256
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nk = hc_pad >> 5;
   const long long total = static_cast<long long>(B) * npix;
-  const int cgroups = (hc + 31) / 32;
-  __shared__ float red[8][33];
-  for (int cg = 0; cg < cgroups; ++cg) {
-    const int c = cg * 32 + threadIdx.x;
-    float acc = 0.f, accb = 0.f;
-    for (long long p = blockIdx.x * static_cast<long long>(blockDim.y) + threadIdx.y; p < total;
-         p += static_cast<long long>(gridDim.x) * blockDim.y) {
-      const long long b = p / npix;
-      const float d = dpred[b * dpred_bstride + (p - b * npix)];
-      if (c < hc) acc = fmaf(d, from_elem(h[p * hc_pad + c]), acc);
-      accb += d;
-    }
-    red[threadIdx.y][threadIdx.x] = acc;
-    __syncthreads();
-    if (threadIdx.y == 0) {
-      float s = 0.f;
-      for (int r = 0; r < 8; ++r) s += red[r][threadIdx.x];
-      if (c < hc) atomicAdd(dw + c, s);
-    }
-    __syncthreads();
-    if (cg == 0) {
-      red[threadIdx.y][threadIdx.x] = (threadIdx.x == 0) ? accb : 0.f;
-      __syncthreads();
-      if (threadIdx.y == 0 && threadIdx.x == 0) {
-        float s = 0.f;
-        for (int r = 0; r < 8; ++r) s += red[r][0];
-        atomicAdd(db, s);
-      }
-      __syncthreads();
-    }
+  const long long wstride = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
+  float acc[KMAX];
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) acc[k] = 0.f;
+  float accb = 0.f;
+  for (long long p = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + warp; p < total; p += wstride) {
+    const long long b = p / npix;
+    const float d = dpred[b * dpred_bstride + (p - b * npix)];
+    const E* row = h + p * hc_pad;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k)
+      if (k < nk) acc[k] = fmaf(d, from_elem(row[k * 32 + lane]), acc[k]);
+    accb += d;
+  }
+  __shared__ float red[8][KMAX * 32 + 1];
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) red[warp][k * 32 + lane] = acc[k];
+  if (lane == 0) red[warp][KMAX * 32] = accb;
+  __syncthreads();
+  for (int c = threadIdx.x; c < hc; c += blockDim.x) {
+    float s = 0.f;
+    for (int w = 0; w < 8; ++w) s += red[w][c];
+    atomicAdd(dw + c, s);
+  }
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int w = 0; w < 8; ++w) s += red[w][KMAX * 32];
+    atomicAdd(db, s);
   }
 }
 
 cudaError_t launch_head_bwd(int dtype, const void* h, const float* dpred, long long dpred_bstride, float* dw, float* db,
                             long long npix, int B, int hc, int hc_pad, cudaStream_t s) {
-  dim3 block(32, 8);
-  const int grid = 148 * 4;
+  const int block = 256;
+  const int grid = 148 * 8;
   if (dtype == NINT_BF16)
     head_bwd_kernel<__nv_bfloat16><<<grid, block, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(h), dpred, dpred_bstride,
                                                          dw, db, npix, B, hc, hc_pad);
@@ -399,6 +401,102 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ dw_acc, const floa
 cudaError_t launch_unpack_wgrad(const float* dw_acc, const float* db_acc, float* gw, float* gb, int cin, int hc, int k,
                                 int ncols, int cx_pad, int accumulate, cudaStream_t s) {
   unpack_wgrad_kernel<<<296, 256, 0, s>>>(dw_acc, db_acc, gw, gb, cin, hc, k, ncols, cx_pad, accumulate);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// training loss (train.py:74-75,102,105): MSELoss(y, p) + L1Loss(y, p), both 'mean', on the cropped prediction
+// pred[:, 0, y0:y1, x0:x1]; forward value and d loss / d pred in one pass.  stats = {sum (p-y)^2, sum |p-y|,
+// sum y, sum y^2, blocks done}: the last block to finish turns them into the scalar loss (the two extra sums
+// are what an on-device R^2, train.py:114, needs).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) loss_mse_l1_kernel(const float* __restrict__ pred, const float* __restrict__ y,
+                                                          float* __restrict__ dpred, float* __restrict__ stats,
+                                                          float* __restrict__ loss, int B, int H, int W, int y0, int y1,
+                                                          int x0, int x1) {
+  const int hc = y1 - y0, wc = x1 - x0;
+  const long long total = static_cast<long long>(B) * H * W;
+  const float inv_n = 1.0f / (static_cast<float>(B) * hc * wc);
+  float s2 = 0.f, s1 = 0.f, sy = 0.f, syy = 0.f;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int x = static_cast<int>(i % W);
+    const long long r = i / W;
+    const int yy = static_cast<int>(r % H);
+    const long long b = r / H;
+    float g = 0.f;
+    if (yy >= y0 && yy < y1 && x >= x0 && x < x1) {
+      const float t = y[(b * hc + (yy - y0)) * wc + (x - x0)];
+      const float d = pred[i] - t;
+      s2 = fmaf(d, d, s2);
+      s1 += fabsf(d);
+      sy += t;
+      syy = fmaf(t, t, syy);
+      g = (2.f * d + (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f))) * inv_n;
+    }
+    if (dpred) dpred[i] = g;
+  }
+  __shared__ float red[4][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    sy += __shfl_xor_sync(0xffffffffu, sy, o);
+    syy += __shfl_xor_sync(0xffffffffu, syy, o);
+  }
+  if (lane == 0) { red[0][warp] = s2; red[1][warp] = s1; red[2][warp] = sy; red[3][warp] = syy; }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    float s = 0.f;
+    for (int w = 0; w < 8; ++w) s += red[threadIdx.x][w];
+    atomicAdd(stats + threadIdx.x, s);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const float done = atomicAdd(stats + 4, 1.0f);
+    if (done == static_cast<float>(gridDim.x - 1)) {
+      __threadfence();
+      const volatile float* vs = stats;
+      *loss = (vs[0] + vs[1]) * inv_n;
+    }
+  }
+}
+cudaError_t launch_loss_mse_l1(const float* pred, const float* y, float* dpred, float* stats, float* loss, int B, int H,
+                               int W, int y0, int y1, int x0, int x1, cudaStream_t s) {
+  cudaError_t e = cudaMemsetAsync(stats, 0, 5 * sizeof(float), s);
+  if (e != cudaSuccess) return e;
+  loss_mse_l1_kernel<<<148, 256, 0, s>>>(pred, y, dpred, stats, loss, B, H, W, y0, y1, x0, x1);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// Adam over one flat parameter buffer (train.py:71 torch.optim.Adam(lr, betas): no weight decay, no amsgrad).
+// grad_scale folds the 1 / world_size of the data-parallel mean into the update.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                   float* __restrict__ v, long long n, float lr, float beta1, float beta2,
+                                                   float eps, float bc1, float bc2_sqrt, float grad_scale) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float gi = g[i] * grad_scale;
+    const float mi = fmaf(beta1, m[i], (1.f - beta1) * gi);
+    const float vi = fmaf(beta2, v[i], (1.f - beta2) * gi * gi);
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] -= (lr / bc1) * (mi / denom);
+  }
+}
+cudaError_t launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                        float eps, int step, float grad_scale, cudaStream_t s) {
+  const float bc1 = 1.f - powf(beta1, static_cast<float>(step));
+  const float bc2_sqrt = sqrtf(1.f - powf(beta2, static_cast<float>(step)));
+  int grid = static_cast<int>((n + 255) / 256);
+  if (grid > 148 * 8) grid = 148 * 8;
+  if (grid < 1) grid = 1;
+  adam_kernel<<<grid, 256, 0, s>>>(p, g, m, v, n, lr, beta1, beta2, eps, bc1, bc2_sqrt, grad_scale);
   return cudaGetLastError();
 }
 

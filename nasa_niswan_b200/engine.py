@@ -67,7 +67,10 @@ class Plan:
             self.lib.nint_plan_destroy(h)
 
     # ---- parameters
-    def set_weights(self, layer: int, weight: torch.Tensor, bias: Optional[torch.Tensor], force=False):
+    def set_weights(self, layer: int, weight: torch.Tensor, bias: Optional[torch.Tensor], force=True):
+        """Repacks the fp32 OIHW masters into operand panels (two small kernels).  Done on EVERY call by default:
+        tensor version counters are not a safe cache key -- torch's fused optimizers update parameters in place
+        without bumping them, and a stale panel cache silently trains / evaluates with old weights."""
         key = (weight.data_ptr(), weight._version, None if bias is None else (bias.data_ptr(), bias._version))
         if not force and self._weight_keys[layer] == key:
             return
@@ -81,7 +84,7 @@ class Plan:
         _lib.check(self.lib.nint_plan_set_weights(self._h, layer, _ptr(w), _ptr(b), _stream()), "nint_plan_set_weights")
         self._weight_keys[layer] = key
 
-    def set_head(self, weight: torch.Tensor, bias: torch.Tensor, force=False):
+    def set_head(self, weight: torch.Tensor, bias: torch.Tensor, force=True):
         key = (weight.data_ptr(), weight._version, bias.data_ptr(), bias._version)
         if not force and self._weight_keys[self.L] == key:
             return
@@ -120,8 +123,10 @@ class Plan:
         self.generation += 1
         return pred, seq
 
-    def backward(self, dpred: Optional[torch.Tensor], dseq: Optional[torch.Tensor] = None):
-        """Returns ([grad_weight_l], [grad_bias_l], grad_head_weight, grad_head_bias)."""
+    def backward(self, dpred: Optional[torch.Tensor], dseq: Optional[torch.Tensor] = None, out=None):
+        """Returns ([grad_weight_l], [grad_bias_l], grad_head_weight, grad_head_bias).  `out`: optional
+        (gw list, gb list, ghw, ghb) of preallocated contiguous fp32 tensors the gradients are written into
+        (e.g. views of one flat all-reduce buffer)."""
         if dseq is not None:
             dseq = dseq.detach().contiguous().clone() if dpred is not None else dseq.detach().contiguous()
             _check_dev(dseq, "dseq", (self.B, self.T, self.H, self.W))
@@ -133,13 +138,25 @@ class Plan:
             _check_dev(dpred, "dpred", (self.B, 1, self.H, self.W))
         gw: List[torch.Tensor] = []
         gb: List[torch.Tensor] = []
-        cin = self.C
-        for hc, k in zip(self.hidden, self.ksize):
-            gw.append(torch.empty((4 * hc, cin + hc, k, k), dtype=torch.float32, device=self.device))
-            gb.append(torch.empty((4 * hc,), dtype=torch.float32, device=self.device))
-            cin = hc
-        ghw = torch.empty((1, self.hidden[-1], 1, 1), dtype=torch.float32, device=self.device)
-        ghb = torch.empty((1,), dtype=torch.float32, device=self.device)
+        if out is not None:
+            gw, gb, ghw, ghb = out
+            cin = self.C
+            for l, (hc, k) in enumerate(zip(self.hidden, self.ksize)):
+                _check_dev(gw[l], "grad weight", (4 * hc, cin + hc, k, k))
+                _check_dev(gb[l], "grad bias", (4 * hc,))
+                cin = hc
+            _check_dev(ghw, "grad head weight", (1, self.hidden[-1], 1, 1))
+            _check_dev(ghb, "grad head bias", (1,))
+            if not all(t.is_contiguous() for t in [*gw, *gb, ghw, ghb]):
+                raise ValueError("gradient outputs must be contiguous")
+        else:
+            cin = self.C
+            for hc, k in zip(self.hidden, self.ksize):
+                gw.append(torch.empty((4 * hc, cin + hc, k, k), dtype=torch.float32, device=self.device))
+                gb.append(torch.empty((4 * hc,), dtype=torch.float32, device=self.device))
+                cin = hc
+            ghw = torch.empty((1, self.hidden[-1], 1, 1), dtype=torch.float32, device=self.device)
+            ghb = torch.empty((1,), dtype=torch.float32, device=self.device)
         arr_w = (ctypes.c_void_p * self.L)(*[t.data_ptr() for t in gw])
         arr_b = (ctypes.c_void_p * self.L)(*[t.data_ptr() for t in gb])
         _lib.check(self.lib.nint_backward(self._h, _ptr(dpred), _ptr(dseq), arr_w, arr_b, _ptr(ghw), _ptr(ghb),

@@ -95,12 +95,89 @@ class HostFeeder:
         slot["free"] = ev
 
 
+class NativeAdam:
+    """torch.optim.Adam(lr, betas) (train.py:71) as ONE kernel over flat buffers (nint_adam_step).  The parameters
+    are re-pointed at views of one flat fp32 buffer (names, shapes and values unchanged: `state_dict` is untouched);
+    `state_dict` / `load_state_dict` speak torch.optim.Adam's format so utils.py:23-50 checkpoints interoperate."""
+
+    def __init__(self, params, flat_grads: torch.Tensor, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+        from . import _lib
+        self.lib = _lib.load()
+        self.params = list(params)
+        self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
+        self.step_count = 0
+        n = sum(p.numel() for p in self.params)
+        dev = self.params[0].device
+        self.flat_params = torch.empty(n, dtype=torch.float32, device=dev)
+        off = 0
+        with torch.no_grad():
+            for p in self.params:
+                view = self.flat_params[off:off + p.numel()].view_as(p)
+                view.copy_(p.data)
+                p.data = view
+                off += p.numel()
+        self.flat_grads = flat_grads
+        self.exp_avg = torch.zeros_like(self.flat_params)
+        self.exp_avg_sq = torch.zeros_like(self.flat_params)
+        self.param_groups = [{"lr": self.lr, "betas": self.betas, "eps": self.eps}]   # what LR schedulers touch
+
+    def step(self, grad_scale: float = 1.0):
+        import ctypes
+        from . import _lib
+        self.step_count += 1
+        lr = float(self.param_groups[0]["lr"])
+        vp = lambda t: ctypes.c_void_p(t.data_ptr())
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        _lib.check(self.lib.nint_adam_step(vp(self.flat_params), vp(self.flat_grads), vp(self.exp_avg), vp(self.exp_avg_sq),
+                                           self.flat_params.numel(), lr, self.betas[0], self.betas[1], self.eps,
+                                           self.step_count, float(grad_scale), st), "nint_adam_step")
+        for p in self.params:      # modified in place behind torch's back: keep the version counters honest
+            torch.autograd.graph.increment_version(p)
+
+    def state_dict(self):
+        state, off = {}, 0
+        for i, p in enumerate(self.params):
+            n = p.numel()
+            state[i] = {"step": torch.tensor(float(self.step_count)),
+                        "exp_avg": self.exp_avg[off:off + n].view_as(p).clone(),
+                        "exp_avg_sq": self.exp_avg_sq[off:off + n].view_as(p).clone()}
+            off += n
+        group = {"lr": float(self.param_groups[0]["lr"]), "betas": self.betas, "eps": self.eps, "weight_decay": 0,
+                 "amsgrad": False, "params": list(range(len(self.params)))}
+        return {"state": state, "param_groups": [group]}
+
+    def load_state_dict(self, sd):
+        off = 0
+        for i, p in enumerate(self.params):
+            n = p.numel()
+            st = sd["state"].get(i)
+            if st is not None:
+                self.exp_avg[off:off + n].copy_(st["exp_avg"].reshape(-1))
+                self.exp_avg_sq[off:off + n].copy_(st["exp_avg_sq"].reshape(-1))
+                self.step_count = int(float(st["step"]))
+            off += n
+        g = sd["param_groups"][0]
+        self.param_groups[0]["lr"] = float(g["lr"])
+        self.betas, self.eps = (float(g["betas"][0]), float(g["betas"][1])), float(g["eps"])
+
+
 class Trainer:
-    def __init__(self, model, lr: float = 1e-3, betas=(0.5, 0.999), crop=None, process_group=None):
-        self.model, self.crop = model, crop
+    """`native=True` (default on CUDA): the whole step stays in libnint kernels -- forward, fused MSE+L1 loss with its
+    gradient (nint_loss_mse_l1), BPTT writing straight into the flat all-reduce buffer, one Adam kernel -- with no
+    autograd graph and ~25 fewer small launches per step.  `native=False` keeps torch's loss / autograd / fused Adam
+    around the same ConvLSTM kernels (identical numerics up to summation order)."""
+
+    def __init__(self, model, lr: float = 1e-3, betas=(0.5, 0.999), crop=None, process_group=None, native=None):
+        self.model, self.crop, self.group = model, crop, process_group
         self.grads = FlatGradients(model.parameters(), process_group)
-        fused = next(model.parameters()).is_cuda
-        self.optimizer = torch.optim.Adam(self.grads.params, lr=lr, betas=betas, fused=fused)   # train.py:71
+        on_cuda = next(model.parameters()).is_cuda
+        self.native = on_cuda if native is None else bool(native)
+        if self.native:
+            self.optimizer = NativeAdam(self.grads.params, self.grads.flat, lr=lr, betas=betas)
+            self._loss = torch.zeros(1, dtype=torch.float32, device=self.grads.flat.device)
+            self._stats = torch.zeros(8, dtype=torch.float32, device=self.grads.flat.device)
+        else:
+            self.optimizer = torch.optim.Adam(self.grads.params, lr=lr, betas=betas, fused=on_cuda)   # train.py:71
         self.broadcast_parameters(process_group)
 
     def broadcast_parameters(self, group=None):
@@ -108,8 +185,42 @@ class Trainer:
             for p in self.model.parameters():
                 dist.broadcast(p.data, src=0, group=group)
 
+    def _grad_views(self):
+        ps = self.grads.params            # layers.{l}.conv.weight, .bias, ..., conv.weight, conv.bias (model.parameters() order)
+        L = (len(ps) - 2) // 2
+        return [ps[2 * l].grad for l in range(L)], [ps[2 * l + 1].grad for l in range(L)], ps[-2].grad, ps[-1].grad
+
+    def _step_native(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        import ctypes
+        from . import _lib
+        model = self.model
+        if getattr(model, "return_sequence", False):
+            raise NotImplementedError("the native step trains on the last-step prediction (train.py:96-105)")
+        plan = model.plan_for(x, True)
+        pred, _ = plan.forward(x)                                   # train.py:96
+        B, _, H, W = pred.shape
+        y0, y1, x0, x1 = self.crop if self.crop is not None else (0, H, 0, W)
+        if tuple(y.shape) != (B, y1 - y0, x1 - x0):
+            raise ValueError(f"y has shape {tuple(y.shape)}, expected {(B, y1 - y0, x1 - x0)}")
+        dpred = torch.empty_like(pred)
+        vp = lambda t: ctypes.c_void_p(t.data_ptr())
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        loss = torch.empty(1, dtype=torch.float32, device=pred.device)
+        _lib.check(_lib.load().nint_loss_mse_l1(vp(pred), vp(y.contiguous()), B, H, W, y0, y1, x0, x1, vp(dpred), vp(loss),
+                                                vp(self._stats), st), "nint_loss_mse_l1")   # train.py:102,105
+        plan.backward(dpred, out=self._grad_views())                # train.py:109, written into the flat buffer
+        world = 1
+        if dist.is_available() and dist.is_initialized():
+            world = dist.get_world_size(self.group)
+            if world > 1:
+                dist.all_reduce(self.grads.flat, op=dist.ReduceOp.SUM, group=self.group)
+        self.optimizer.step(grad_scale=1.0 / world)                 # train.py:110 (mean over ranks folded in)
+        return loss[0]
+
     def step(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
         """One optimizer step on this rank's shard; returns the (un-synchronised) local loss tensor."""
+        if self.native:
+            return self._step_native(x, y)
         self.grads.zero()                                   # train.py:108
         pred = self.model(x)                                # train.py:96
         loss = training_loss(pred, y, self.crop)            # train.py:102,105

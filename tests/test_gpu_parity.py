@@ -213,3 +213,77 @@ def test_stale_workspace_is_detected(golden_dir):
     net(x)
     with pytest.raises(RuntimeError, match="overwritten"):
         p1.sum().backward()
+
+
+@pytest.mark.parametrize("crop", [None, (5, 95, 5, 149)])
+def test_fused_loss_matches_torch(crop):
+    """nint_loss_mse_l1 = MSELoss + L1Loss on the cropped prediction (train.py:74-75,102,105): value and gradient"""
+    import ctypes
+    from nasa_niswan_b200 import _lib
+    torch.manual_seed(5)
+    B, H, W = 4, 100, 154
+    y0, y1, x0, x1 = crop if crop else (0, H, 0, W)
+    pred = torch.randn(B, 1, H, W, device="cuda", requires_grad=True)
+    y = torch.randn(B, y1 - y0, x1 - x0, device="cuda")
+    ref = O.training_loss(pred, y, crop)
+    ref.backward()
+    dpred, loss, stats = torch.empty_like(pred), torch.empty(1, device="cuda"), torch.zeros(8, device="cuda")
+    vp = lambda t: ctypes.c_void_p(t.data_ptr())
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _lib.check(_lib.load().nint_loss_mse_l1(vp(pred.detach()), vp(y), B, H, W, y0, y1, x0, x1, vp(dpred), vp(loss), vp(stats), st),
+               "nint_loss_mse_l1")
+    assert abs(float(loss) - float(ref)) < 1e-5 * max(1.0, abs(float(ref)))
+    assert torch.allclose(dpred, pred.grad, rtol=1e-5, atol=1e-9)
+    # the two extra sums give R^2 (train.py:114) without leaving the device
+    r2 = 1.0 - float(stats[0]) / (float(stats[3]) - float(stats[2]) ** 2 / y.numel())
+    p = pred.detach()[:, 0, y0:y1, x0:x1]
+    r2_ref = 1.0 - float(((p - y) ** 2).sum()) / float(((y - y.mean()) ** 2).sum())
+    assert abs(r2 - r2_ref) < 1e-4
+
+
+def test_native_adam_matches_torch():
+    """nint_adam_step vs torch.optim.Adam(lr, betas=(0.5, 0.999)) (train.py:71) over several steps"""
+    from nasa_niswan_b200.parallel import NativeAdam
+    torch.manual_seed(6)
+    shapes = [(64, 10, 3, 3), (64,), (1, 16, 1, 1), (1,)]
+    ref_p = [torch.nn.Parameter(torch.randn(s, device="cuda")) for s in shapes]
+    our_p = [torch.nn.Parameter(p.detach().clone()) for p in ref_p]
+    flat_g = torch.zeros(sum(p.numel() for p in our_p), device="cuda")
+    ours = NativeAdam(our_p, flat_g, lr=1e-3, betas=(0.5, 0.999))
+    ref = torch.optim.Adam(ref_p, lr=1e-3, betas=(0.5, 0.999))
+    for step in range(5):
+        g = torch.randn_like(flat_g) * (10.0 ** (step - 2))
+        flat_g.copy_(g)
+        off = 0
+        for p in ref_p:
+            p.grad = g[off:off + p.numel()].view_as(p).clone()
+            off += p.numel()
+        versions = [p._version for p in our_p]
+        ours.step()
+        ref.step()
+        assert all(p._version > v for p, v in zip(our_p, versions))   # in-place update is visible to autograd
+    for a, b in zip(our_p, ref_p):
+        assert torch.allclose(a, b, rtol=2e-5, atol=1e-7)
+    sd = ours.state_dict()
+    assert torch.allclose(sd["state"][0]["exp_avg"], ref.state_dict()["state"][0]["exp_avg"], rtol=1e-5, atol=1e-8)
+
+
+def test_native_step_matches_autograd_step():
+    """Trainer(native=True) (fused loss, BPTT into the flat buffer, one Adam kernel) follows Trainer(native=False)"""
+    from nasa_niswan_b200 import ConvLSTM
+    from nasa_niswan_b200.parallel import Trainer
+    torch.manual_seed(7)
+    x = torch.randn(2, 4, 21, 30, 40, device="cuda")
+    y = torch.randn(2, 20, 30, device="cuda")
+    losses = {}
+    for native in (False, True):
+        torch.manual_seed(8)
+        net = ConvLSTM(21, [64], [3], 1, precision="tf32").cuda()
+        tr = Trainer(net, lr=1e-3, betas=(0.5, 0.999), crop=(5, 25, 5, 35), native=native)
+        losses[native] = [float(tr.step(x, y)) for _ in range(4)]
+        losses[("w", native)] = net.layers[0].conv.weight.detach().clone()
+    assert losses[True][0] == pytest.approx(losses[False][0], rel=1e-5)
+    assert losses[True] == pytest.approx(losses[False], rel=2e-3)
+    assert losses[True][-1] < losses[True][0] and losses[False][-1] < losses[False][0]   # both train (weights are
+    # repacked every forward: torch's fused Adam does not bump parameter versions)
+    assert O.max_abs_normalised(losses[("w", True)].cpu(), losses[("w", False)].cpu()) < 5e-3
