@@ -236,6 +236,29 @@ def main():
                                  "frac": round(flops[name] * K_ / (ms * 1e-3) / 1e12 / peak_tf, 4)}
         dominant = max(kernels, key=lambda n_: kernels[n_]["ms_per_step"])
         conv_ms = sum(v["ms_per_step"] for v in kernels.values())
+        # the fused dgrad + gate-backward kernel is HBM-bound: 2048 algorithmic bytes per pixel-step
+        # (gates r 512 + dgates w 512 + c_t 256 + c_{t-1} 256 + dc r/w 512, bf16 gates / fp32 state)
+        esz = 2 if args.precision == "bf16" else 4
+        bwd_bytes = B * H * W * (2 * 4 * HIDDEN * esz + 4 * HIDDEN * 4)
+        hbm_peak = peaks.get("hbm_gbs", 6550.0)
+        if "dgrad_gate_bwd" in kernels:
+            kb = kernels["dgrad_gate_bwd"]
+            kb["hbm_gbs"] = round(bwd_bytes / (kb["avg_launch_us"] * 1e-6) / 1e9, 1)
+            kb["hbm_frac"] = round(kb["hbm_gbs"] / hbm_peak, 4)
+        traffic = None
+        try:   # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(dominant)
+        except (OSError, ValueError):
+            pass
+        if dominant == "dgrad_gate_bwd":
+            roof = {"bound": "hbm", "kernel": dominant, "achieved": kernels[dominant]["hbm_gbs"], "peak": hbm_peak,
+                    "unit": "GB/s", "frac": kernels[dominant]["hbm_frac"], "traffic": traffic,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6550 GB/s (B200_PROFILING.md)",
+                    "bytes_per_launch": bwd_bytes}
+        else:
+            roof = {"bound": "tensor", "kernel": dominant, "achieved": kernels[dominant]["tflops"], "peak": peak_tf,
+                    "unit": "TFLOP/s", "frac": kernels[dominant]["frac"], "traffic": traffic, "peak_source": peak_src,
+                    "flops_per_launch": flops[dominant] / (kernels[dominant]["launches_per_step"])}
         total_tf = sum(flops.values()) / (conv_ms * 1e-3) / 1e12
         out = {
             "metric": "train samples/sec", "value": round(value, 2), "unit": "samples/s", "n_gpus": world,
@@ -251,9 +274,7 @@ def main():
                            "stream), loss read back every step"},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": dominant, "achieved": kernels[dominant]["tflops"], "peak": peak_tf,
-                         "unit": "TFLOP/s", "frac": kernels[dominant]["frac"], "traffic": None, "peak_source": peak_src,
-                         "flops_per_launch": flops[dominant] / (kernels[dominant]["launches_per_step"])},
+            "roofline": roof,
             "kernels": kernels,
             "gate_conv_fwd_bwd": {"tflops": round(total_tf, 1), "frac": round(total_tf / peak_tf, 4),
                                   "conv_ms_per_step": round(conv_ms, 3), "other_ms_per_step": round(ms_step - conv_ms, 3)},

@@ -10,7 +10,7 @@ DTYPE_BF16, DTYPE_TF32 = 0, 1
 EXPORTS = ["nint_version", "nint_last_error", "nint_plan_create", "nint_plan_destroy", "nint_plan_workspace_bytes",
            "nint_plan_bind", "nint_plan_set_weights", "nint_plan_set_head", "nint_plan_reset_state",
            "nint_plan_set_state", "nint_plan_get_state", "nint_forward", "nint_backward", "nint_debug_raw_gates",
-           "nint_gate_column", "nint_debug_read_trace", "nint_loss_mse_l1", "nint_adam_step", "nint_pick_tile", "nint_launch_count", "nint_plan_profile",
+           "nint_gate_column", "nint_debug_read_trace", "nint_loss_mse_l1", "nint_adam_step", "nint_fuse_inputs", "nint_pick_tile", "nint_launch_count", "nint_plan_profile",
            "nint_plan_profile_read"]
 
 
@@ -57,6 +57,7 @@ def load():
     L.nint_debug_read_trace.argtypes = [ctypes.POINTER(ctypes.c_longlong), ci, ci]
     L.nint_loss_mse_l1.argtypes = [fp, fp, ci, ci, ci, ci, ci, ci, ci, fp, fp, fp, vp]
     cf, cll = ctypes.c_float, ctypes.c_longlong
+    L.nint_fuse_inputs.argtypes = [fp, fp, fp, fp, cll, ci, ci, ci, ci, ci, ci, fp, vp]
     L.nint_adam_step.argtypes = [fp, fp, fp, fp, cll, cf, cf, cf, cf, ci, cf, vp]
     L.nint_pick_tile.argtypes = [ci, ci, ctypes.POINTER(ci), ctypes.POINTER(ci)]
     for name in EXPORTS:

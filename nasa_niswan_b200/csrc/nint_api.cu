@@ -647,6 +647,24 @@ int nint_forward(nint_plan* p, const float* x, float* pred, float* seq, void* st
   return 0;
 }
 
+int nint_fuse_inputs(const float* levels3d, const float* emis2d, const float* mean, const float* std, long long frames,
+                     int levels, int height, int width, int padded_height, int padded_width, int mode, float* out,
+                     void* stream) {
+  if ((!levels3d && levels > 0) || !emis2d || !mean || !std || !out) return fail("nint_fuse_inputs: null argument");
+  if (frames < 1 || levels < 0 || height < 1 || width < 1) return fail("nint_fuse_inputs: bad shape");
+  if (mode != 0 && mode != 1) return fail("nint_fuse_inputs: mode must be 0 (reflect) or 1 (reference RNN dataset)");
+  const int left = (padded_width - width) / 2, right = padded_width - width - left;
+  const int top = (padded_height - height) / 2, bot = padded_height - height - top;
+  if (padded_width < width || padded_height < height) return fail("nint_fuse_inputs: padded size smaller than the grid");
+  if (left > width || right > width)   // dataset.py:80
+    return fail("The requested padding size is larger than width size of the input image.");
+  if (top + 1 > height || bot + 1 > height)   // dataset.py:98
+    return fail("The requested padding size is larger than height size of the input image.");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  LAUNCH(nullptr, K_OTHER, st, launch_fuse_inputs(levels3d, emis2d, mean, std, out, frames, levels, height, width, padded_height, padded_width, mode, st));
+  return 0;
+}
+
 int nint_loss_mse_l1(const float* pred, const float* y, int batch, int height, int width, int crop_y0, int crop_y1,
                      int crop_x0, int crop_x1, float* dpred, float* loss, float* stats, void* stream) {
   if (!pred || !y || !loss || !stats) return fail("nint_loss_mse_l1: null argument");

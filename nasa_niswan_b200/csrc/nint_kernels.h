@@ -137,6 +137,9 @@ cudaError_t launch_head_bwd(int dtype, const void* h, const float* dpred, long l
 cudaError_t launch_unpack_wgrad(const float* dw_acc, const float* db_acc, float* gw, float* gb, int cin, int hc,
                                 int k, int ncols, int cx_pad, int accumulate, cudaStream_t s);
 
+// preprocessing fusion: stack levels + emission, z-score, cyclic-longitude / reflect-latitude halo
+cudaError_t launch_fuse_inputs(const float* lev, const float* emis, const float* mean, const float* stdv, float* out,
+                               long long N, int L, int H, int W, int Hp, int Wp, int mode, cudaStream_t s);
 // fused training loss MSE + L1 on the cropped prediction (value + gradient); stats = 5 floats of scratch
 cudaError_t launch_loss_mse_l1(const float* pred, const float* y, float* dpred, float* stats, float* loss, int B, int H,
                                int W, int y0, int y1, int x0, int x1, cudaStream_t s);

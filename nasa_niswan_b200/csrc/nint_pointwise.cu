@@ -405,6 +405,48 @@ cudaError_t launch_unpack_wgrad(const float* dw_acc, const float* db_acc, float*
 }
 
 // ------------------------------------------------------------------------------------------
+// preprocessing fusion (north-star item 4; dataset.py:520-537 stack + z-score, dataset.py:67-98 halo): stack the
+// first L levels of a 3-D forcing [N,L,H,W] with a 2-D emission field [N,H,W] as channel L, z-score per channel,
+// cyclic halo in longitude, reflect halo in latitude -> [N,L+1,Hp,Wp] fp32.  mode 1 reproduces the shipped RNN
+// dataset's quirk (np.fliplr on a (T,C,rows,W) slab flips CHANNELS: halo rows keep their order, channel order is
+// reversed; dataset.py:96).  One thread per output element, coalesced along longitude; HBM-bound.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fuse_inputs_kernel(const float* __restrict__ lev, const float* __restrict__ emis,
+                                                          const float* __restrict__ mean, const float* __restrict__ stdv,
+                                                          float* __restrict__ out, long long N, int L, int H, int W, int Hp,
+                                                          int Wp, int mode) {
+  const int C = L + 1;
+  const int left = (Wp - W) / 2, top = (Hp - H) / 2, bot = Hp - H - top;
+  const long long total = N * C * Hp * Wp;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int xp = static_cast<int>(i % Wp);
+    long long r = i / Wp;
+    const int yp = static_cast<int>(r % Hp);
+    r /= Hp;
+    const int c = static_cast<int>(r % C);
+    const long long n = r / C;
+    int xs = xp - left;                       // cyclic longitude (dataset.py:67-80)
+    if (xs < 0) xs += W;
+    if (xs >= W) xs -= W;
+    int ys = yp - top, cs = c;
+    if (ys < 0) {                             // upper halo: rows 1..top (dataset.py:82-98)
+      if (mode == 0) ys = top - yp; else { ys = 1 + yp; cs = C - 1 - c; }
+    } else if (ys >= H) {                     // lower halo: rows H-bot-1..H-2
+      const int j = ys - H;
+      if (mode == 0) ys = H - 2 - j; else { ys = H - bot - 1 + j; cs = C - 1 - c; }
+    }
+    const float v = cs < L ? lev[((n * L + cs) * H + ys) * W + xs] : emis[(n * H + ys) * W + xs];
+    out[i] = (v - mean[cs]) / stdv[cs];       // IEEE subtract / divide: bit-identical to the numpy float32 pipeline
+  }
+}
+cudaError_t launch_fuse_inputs(const float* lev, const float* emis, const float* mean, const float* stdv, float* out,
+                               long long N, int L, int H, int W, int Hp, int Wp, int mode, cudaStream_t s) {
+  fuse_inputs_kernel<<<148 * 8, 256, 0, s>>>(lev, emis, mean, stdv, out, N, L, H, W, Hp, Wp, mode);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
 // training loss (train.py:74-75,102,105): MSELoss(y, p) + L1Loss(y, p), both 'mean', on the cropped prediction
 // pred[:, 0, y0:y1, x0:x1]; forward value and d loss / d pred in one pass.  stats = {sum (p-y)^2, sum |p-y|,
 // sum y, sum y^2, blocks done}: the last block to finish turns them into the scalar loss (the two extra sums

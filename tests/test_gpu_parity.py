@@ -287,3 +287,28 @@ def test_native_step_matches_autograd_step():
     assert losses[True][-1] < losses[True][0] and losses[False][-1] < losses[False][0]   # both train (weights are
     # repacked every forward: torch's fused Adam does not bump parameter versions)
     assert O.max_abs_normalised(losses[("w", True)].cpu(), losses[("w", False)].cpu()) < 5e-3
+
+
+@pytest.mark.parametrize("mode", ["reflect", "reference_rnn"])
+@pytest.mark.parametrize("shape", [(3, 20, 90, 144, 100, 154), (2, 4, 12, 20, 22, 30), (1, 0, 9, 7, 9, 7)])
+def test_fuse_inputs_matches_oracle(shape, mode):
+    """preprocessing fusion kernel vs the oracle restatement of dataset.py:520-537 / 67-98: bit-exact (fp32 in, fp32 out)"""
+    from nasa_niswan_b200.preprocess import fuse_inputs
+    T, L, H, W, Hp, Wp = shape
+    rng = np.random.default_rng(9)
+    lev = rng.standard_normal((T, L, H, W)).astype(np.float32) * 7 + 3
+    em = np.abs(rng.standard_normal((T, H, W))).astype(np.float32) * 1e-9
+    mean = rng.standard_normal(L + 1).astype(np.float32)
+    std = (np.abs(rng.standard_normal(L + 1)) + 0.5).astype(np.float32)
+    std[-1] *= 1e-9
+    ref = O.fuse_inputs(lev, em, mean, std, (Hp, Wp), mode)
+    got = fuse_inputs(*(torch.from_numpy(a).cuda() for a in (lev, em, mean, std)), (Hp, Wp), mode)
+    assert got.shape == ref.shape
+    assert np.array_equal(got.cpu().numpy(), ref)
+
+
+def test_fuse_inputs_rejects_oversized_halo():
+    from nasa_niswan_b200.preprocess import fuse_inputs
+    z = torch.zeros(1, 1, 4, 4, device="cuda")
+    with pytest.raises(RuntimeError, match="larger than width"):
+        fuse_inputs(z, z[:, 0], torch.zeros(2, device="cuda"), torch.ones(2, device="cuda"), (4, 20))
