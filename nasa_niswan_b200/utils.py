@@ -1,0 +1,77 @@
+"""Checkpoint and validation helpers with the reference's contracts (utils.py:23-75), SURVEY.md section 8f rank 4.
+
+`save_checkpoint` / `load_checkpoint` keep the reference's file format -- a dict with `model_state_dict`,
+`optimizer_state_dict`, `learning_rate`, `epoch` -- so checkpoints move freely between the reference ConvLSTM and
+this one (same `state_dict` keys and shapes) and between `torch.optim.Adam` and `NativeAdam` (same optimizer
+`state_dict` layout).  `val_loop` is utils.py:52-75 without its per-batch device-to-host copies: R^2 is reduced on
+the GPU by the fused loss kernel and read back once per batch as five floats."""
+import ctypes
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+
+def save_checkpoint(model, optimizer, filename, learning_rate=None, epoch=None):
+    """utils.py:23-32"""
+    checkpoint = {
+        "model_state_dict": model.state_dict(),
+        "optimizer_state_dict": optimizer.state_dict(),
+        "learning_rate": learning_rate,
+        "epoch": epoch,
+    }
+    torch.save(checkpoint, filename)
+
+
+def load_checkpoint(checkpoint_file, model, optimizer=None, lr=None, map_location=None):
+    """utils.py:34-50 (the learning-rate override rules included)"""
+    checkpoint = torch.load(checkpoint_file, map_location=map_location, weights_only=False)
+    model.load_state_dict(checkpoint["model_state_dict"])
+    if optimizer is not None:
+        optimizer.load_state_dict(checkpoint["optimizer_state_dict"])
+        if lr is not None:
+            for param_group in optimizer.param_groups:
+                param_group["lr"] = lr
+        elif checkpoint["learning_rate"] is not None:
+            for param_group in optimizer.param_groups:
+                param_group["lr"] = checkpoint["learning_rate"]
+    return checkpoint
+
+
+def r2_from_stats(stats: torch.Tensor, n: int) -> float:
+    """sklearn.metrics.r2_score(y.flatten(), pred.flatten()) (train.py:114, utils.py:73) from the sums the fused loss
+    kernel leaves in its scratch: stats = {sum (p-y)^2, sum |p-y|, sum y, sum y^2, -}."""
+    s = stats[:4].double().cpu()
+    ss_res, sy, syy = float(s[0]), float(s[2]), float(s[3])
+    ss_tot = syy - sy * sy / n
+    return 1.0 - ss_res / ss_tot if ss_tot > 0 else float("nan")
+
+
+def r2_score_device(pred: torch.Tensor, y: torch.Tensor, crop: Optional[Tuple[int, int, int, int]] = None) -> float:
+    """R^2 of pred[:, 0, y0:y1, x0:x1] against y on the GPU (one kernel, 20 bytes read back)."""
+    if not pred.is_cuda:
+        raise RuntimeError("r2_score_device needs CUDA tensors (no CPU fallback)")
+    B, _, H, W = pred.shape
+    y0, y1, x0, x1 = crop if crop is not None else (0, H, 0, W)
+    stats = torch.zeros(8, dtype=torch.float32, device=pred.device)
+    loss = torch.empty(1, dtype=torch.float32, device=pred.device)
+    vp = lambda t: ctypes.c_void_p(t.data_ptr())
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _lib.check(_lib.load().nint_loss_mse_l1(vp(pred.detach().contiguous().float()), vp(y.contiguous().float()), B, H, W,
+                                            y0, y1, x0, x1, None, vp(loss), vp(stats), st), "nint_loss_mse_l1")
+    return r2_from_stats(stats, B * (y1 - y0) * (x1 - x0))
+
+
+def val_loop(dataloader, model, crop: Optional[Tuple[int, int, int, int]] = (5, 95, 5, 149)) -> float:
+    """utils.py:52-75 for the LSTM branch: mean over batches of R^2 on the cropped prediction."""
+    model.eval()
+    r2, n = 0.0, 0
+    with torch.no_grad():
+        for X, y in dataloader:
+            X, y = X.cuda(non_blocking=True), y.cuda(non_blocking=True)
+            out = model(X)
+            pred = out[0] if isinstance(out, tuple) else out
+            r2 += r2_score_device(pred, y, crop)
+            n += 1
+    return r2 / max(n, 1)

@@ -312,3 +312,45 @@ def test_fuse_inputs_rejects_oversized_halo():
     z = torch.zeros(1, 1, 4, 4, device="cuda")
     with pytest.raises(RuntimeError, match="larger than width"):
         fuse_inputs(z, z[:, 0], torch.zeros(2, device="cuda"), torch.ones(2, device="cuda"), (4, 20))
+
+
+def test_val_loop_r2_matches_sklearn():
+    """utils.py:52-75: mean per-batch sklearn r2_score on the cropped prediction, computed on the device here"""
+    from sklearn.metrics import r2_score
+    from nasa_niswan_b200 import ConvLSTM
+    from nasa_niswan_b200.utils import val_loop
+    torch.manual_seed(10)
+    net = ConvLSTM(5, [16], [3], 1, precision="tf32").cuda()
+    data = [(torch.randn(2, 3, 5, 100, 154), torch.randn(2, 90, 144)) for _ in range(2)]
+    got = val_loop(data, net)
+    ref = 0.0
+    with torch.no_grad():
+        for X, y in data:
+            pred = net(X.cuda())[:, :, 5:95, 5:149].squeeze()
+            ref += r2_score(y.numpy().flatten(), pred.cpu().numpy().flatten())
+    assert abs(got - ref / len(data)) < 1e-4
+
+
+def test_checkpoint_moves_between_native_and_torch_adam(tmp_path):
+    """optimizer_state_dict written by NativeAdam loads into torch.optim.Adam and back (utils.py:23-50)"""
+    from nasa_niswan_b200 import ConvLSTM
+    from nasa_niswan_b200.parallel import Trainer
+    from nasa_niswan_b200.utils import load_checkpoint, save_checkpoint
+    torch.manual_seed(11)
+    x, y = torch.randn(2, 2, 5, 20, 24, device="cuda"), torch.randn(2, 20, 24, device="cuda")
+    net = ConvLSTM(5, [16], [3], 1, precision="tf32").cuda()
+    tr = Trainer(net, lr=1e-3, betas=(0.5, 0.999), native=True)
+    tr.step(x, y)
+    f = str(tmp_path / "generator.pth.tar")
+    save_checkpoint(net, tr.optimizer, f, learning_rate=1e-3, epoch=1)
+    net2 = ConvLSTM(5, [16], [3], 1, precision="tf32").cuda()
+    opt2 = torch.optim.Adam(net2.parameters(), lr=1e-3, betas=(0.5, 0.999))
+    load_checkpoint(f, net2, opt2)
+    assert all(torch.equal(a, b) for a, b in zip(net.state_dict().values(), net2.state_dict().values()))
+    s0 = opt2.state_dict()["state"][0]
+    assert torch.allclose(s0["exp_avg"].cpu(), tr.optimizer.state_dict()["state"][0]["exp_avg"].cpu())
+    tr2 = Trainer(net2, lr=1e-3, betas=(0.5, 0.999), native=True)
+    load_checkpoint(f, net2, tr2.optimizer)
+    assert tr2.optimizer.step_count == 1
+    l1, l2 = float(tr.step(x, y)), float(tr2.step(x, y))
+    assert l1 == pytest.approx(l2, rel=1e-5)

@@ -126,3 +126,24 @@ def test_no_cpu_fallback():
     with pytest.raises((RuntimeError, NotImplementedError)):
         with torch.no_grad():
             cell(torch.zeros(1, 3, 8, 8), (torch.zeros(1, 16, 8, 8), torch.zeros(1, 16, 8, 8)))
+
+
+def test_checkpoint_format_matches_reference(tmp_path):
+    """utils.py:23-50: same dict keys, same lr override rules (CPU: any nn.Module + torch optimizer)"""
+    import torch
+    from nasa_niswan_b200.utils import load_checkpoint, save_checkpoint
+    net = torch.nn.Conv2d(3, 4, 3)
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3, betas=(0.5, 0.999))
+    net(torch.randn(1, 3, 8, 8)).sum().backward()
+    opt.step()
+    f = tmp_path / "generator.pth.tar"
+    save_checkpoint(net, opt, str(f), learning_rate=5e-4, epoch=10)
+    raw = torch.load(str(f), weights_only=False)
+    assert set(raw) == {"model_state_dict", "optimizer_state_dict", "learning_rate", "epoch"}
+    net2 = torch.nn.Conv2d(3, 4, 3)
+    opt2 = torch.optim.Adam(net2.parameters(), lr=1e-3, betas=(0.5, 0.999))
+    load_checkpoint(str(f), net2, opt2)
+    assert all(torch.equal(a, b) for a, b in zip(net.state_dict().values(), net2.state_dict().values()))
+    assert opt2.param_groups[0]["lr"] == 5e-4            # utils.py:47-49: the stored learning rate wins
+    load_checkpoint(str(f), net2, opt2, lr=1e-2)
+    assert opt2.param_groups[0]["lr"] == 1e-2            # utils.py:43-45: an explicit lr overrides it
