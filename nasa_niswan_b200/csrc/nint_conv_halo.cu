@@ -458,8 +458,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
             const uint32_t ahi = static_cast<uint32_t>(adesc >> 32), bhi = static_cast<uint32_t>(bdesc >> 32);
             const uint32_t w16l = static_cast<uint32_t>(w16), skipl = static_cast<uint32_t>(row_skip);
             int dxl = dx;
-            if (false) {
-            } else if (G == 1) {
+            if (G == 1) {
 #pragma unroll 3
               for (int j = 0; j < TS; ++j) {
                 umma_lohi<DT, pair>(d_tmem, alo, ahi, blo, bhi, idesc, accumulate);

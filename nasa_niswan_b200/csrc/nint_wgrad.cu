@@ -323,11 +323,13 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
 //   A  dgates  [128 px][128 q]  as 2 panels of 64 q   (128-byte rows, SWIZZLE_128B, MN-major)
 //   B  comb    [halo px][N/2 channels] as 16-channel panels (32-byte rows, SWIZZLE_32B, MN-major): the pair MMA
 //      splits N between the CTAs, and N/2 = 48 is not a multiple of the 32-channel panel of the 64B swizzle
-// Warps: 0 A producer, 3 B producer (every bulk-async instruction occupies its issuing warp for ~450-750 cycles),
-// 1 MMA issuer (leader CTA), 2 TMEM allocator, 4-7 flush the accumulators with fp32 atomics.
+// Warps: 0 A producer, 3 / 2 B producers (every bulk-async instruction occupies its issuing warp for ~450-750
+// cycles; 2 also allocates TMEM), 1 / 8 MMA issuers (leader CTA, alternate tiles), 4-7 flush the accumulators with
+// fp32 atomics.
 constexpr int kWgPairBStages = 4;
 constexpr int kWgPairABufs = 3;   // the issuer awaits tile i+1 before issuing tile i: needs i-1, i, i+1 resident
 constexpr int kWgPairAPanel = kTilePixels * 128;   // 64 q x 128 px bf16 = 16 KiB
+constexpr int kWgPairThreads = 288;                // 9 warps: warp 8 is the second MMA issuer
 
 __host__ __device__ static inline int wgp_b_panel_bytes(int ksize) {
   const int rows = (8 + (ksize & ~1)) * (16 + (ksize & ~1));
@@ -337,7 +339,7 @@ static inline int wgp_smem_bytes(int bp_cta, int ksize) {
   return 1024 + kWgPairABufs * 2 * kWgPairAPanel + kWgPairBStages * bp_cta * wgp_b_panel_bytes(ksize) + 1024 + kWgCtrlBytes;
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kWgThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kWgPairThreads, 1)
 wgrad_pair_kernel(const __grid_constant__ WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -363,6 +365,7 @@ wgrad_pair_kernel(const __grid_constant__ WgradParams p) {
   uint64_t* b_empty = b_full + kWgMaxBufs;
   uint64_t* acc_full = b_empty + kWgMaxBufs;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ctrl + kWgCtrlBytes - 16);
+  volatile uint32_t* mma_issued = reinterpret_cast<volatile uint32_t*>(ctrl + kWgCtrlBytes - 32);
 
   // cluster -> (split, tap group, m-block of 256 q)
   const int cid = blockIdx.x >> 1;
@@ -381,7 +384,7 @@ wgrad_pair_kernel(const __grid_constant__ WgradParams p) {
     // the tiles are always full 8 x 16 boxes (TMA zero-fills outside the image), so no operand row is ever stale;
     // the ones panel feeds the bias-gradient MMA
     uint4* o = reinterpret_cast<uint4*>(sOnes);
-    for (int i = threadIdx.x; i < 1024 / 16; i += kWgThreads) o[i] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
+    for (int i = threadIdx.x; i < 1024 / 16; i += kWgPairThreads) o[i] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
     fence_proxy_async_smem();
   }
   if (warp == 0 && lane == 0) {
@@ -396,7 +399,8 @@ wgrad_pair_kernel(const __grid_constant__ WgradParams p) {
       mbar_init(&b_full[s], 1);
       mbar_init(&b_empty[s], 1);
     }
-    mbar_init(acc_full, 1);
+    mbar_init(acc_full, my_tiles >= 2 ? 2 : 1);   // one final commit per issuing warp that had a tile
+    *mma_issued = 0;
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc_pair(tmem_slot, kTmemCols);
@@ -467,9 +471,13 @@ wgrad_pair_kernel(const __grid_constant__ WgradParams p) {
         bph ^= 1;
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (leader CTA)
+  } else if (warp == 1 || warp == 8) {
+    // ------------------------------------------------------------------ MMA issuers (leader CTA): two warps take
+    // alternate pixel tiles.  The issuing thread only runs a few MMAs ahead of the tensor pipe, so with one issuer
+    // the ~500 cycles of barrier work per tile were tensor idle time; with two, one warp's waits and commits hide
+    // behind the other's MMA stream.  Tiles enter the pipe strictly in order (`mma_issued`): deterministic sums.
     if (my_tiles > 0 && lead_cta) {
+      const int which = warp == 1 ? 0 : 1;
       const bool leader = elect_one();
       const uint32_t idesc = p.idesc, idesc_bias = p.idesc_bias;
       const uint32_t ncols = static_cast<uint32_t>(p.ncols);
@@ -491,27 +499,20 @@ wgrad_pair_kernel(const __grid_constant__ WgradParams p) {
         const int tp = tap_begin + (ti < ntaps ? ti : 0);
         tap_off[ti] = static_cast<uint32_t>((((tp / ksize) * hpitch + tp % ksize) * 32) >> 4);
       }
-      int ab = 0, bs = 0;
-      uint32_t aph = 0, bph = 0;
-      mbar_wait(&a_full[0], 0);
-      mbar_wait(&b_full[0], 0);
-      tc_fence_after();
-      for (int i = 0; i < my_tiles; ++i) {
-        // readiness of the next tile's operands is awaited before this tile's MMAs are issued (the tensor pipe's
-        // queue is deep but every barrier round trip costs the issuing thread ~100 cycles)
-        const int nab = (ab + 1 == kWgPairABufs) ? 0 : ab + 1;
-        const int nbs = (bs + 1 == kWgPairBStages) ? 0 : bs + 1;
-        const uint32_t naph = (ab + 1 == kWgPairABufs) ? aph ^ 1 : aph;
-        const uint32_t nbph = (bs + 1 == kWgPairBStages) ? bph ^ 1 : bph;
-        if (i + 1 < my_tiles) {
-          mbar_wait(&a_full[nab], naph);
-          mbar_wait(&b_full[nbs], nbph);
-          tc_fence_after();
-        }
+      int last_mine = -1;
+      for (int i = which; i < my_tiles; i += 2) {
+        const int ab = i % kWgPairABufs, bs = i % kWgPairBStages;
+        const uint32_t aph = static_cast<uint32_t>(i / kWgPairABufs) & 1u, bph = static_cast<uint32_t>(i / kWgPairBStages) & 1u;
+        mbar_wait(&a_full[ab], aph);
+        mbar_wait(&b_full[bs], bph);
+        while (*mma_issued < static_cast<uint32_t>(i)) { }   // the other warp has issued all of tile i-1
+        tc_fence_after();
         if (leader && issue_any) {
           const uint32_t a0 = alo_base + sA16 + static_cast<uint32_t>((ab * a_buf_bytes) >> 4);
           const uint32_t b0 = blo_base + sB16 + static_cast<uint32_t>((bs * b_stage_bytes) >> 4);
           uint32_t acc = i != 0 ? 1u : 0u;
+          const int reps = (p.debug_flags & 4) ? 2 : 1;   // experiment: issue every tile's MMA stream twice
+          for (int rep = 0; rep < reps; ++rep)
           if (ntaps <= 5) {
             // per-tap B offsets are loop invariants: the MMA stream is adds + tcgen05.mma only
 #pragma unroll 2
@@ -553,14 +554,18 @@ wgrad_pair_kernel(const __grid_constant__ WgradParams p) {
             }
           }
         }
+        if (leader) {
+          __threadfence_block();
+          *mma_issued = static_cast<uint32_t>(i + 1);
+        }
         __syncwarp();
         umma_commit_elect<true>(&b_empty[bs]);
         umma_commit_elect<true>(&a_empty[ab]);
-        ab = nab; bs = nbs; aph = naph; bph = nbph;
+        last_mine = i;
       }
-      umma_commit_elect<true>(acc_full);
+      if (last_mine >= 0) umma_commit_elect<true>(acc_full);
     }
-  } else if (warp >= 4 && my_tiles > 0) {
+  } else if (warp >= 4 && warp < 8 && my_tiles > 0) {
     // ------------------------------------------------------------------ epilogue: flush this CTA's 128 gate columns
     const int quad = warp & 3;
     const int q = mb * 256 + static_cast<int>(crank) * 128 + quad * 32 + lane;
@@ -608,7 +613,7 @@ static cudaError_t launch_wg_pair(const WgradParams& p, cudaStream_t stream) {
   }
   const int grid = 2 * p.m_blocks * p.n_groups * p.splits;
   if (grid <= 0) return cudaSuccess;
-  wgrad_pair_kernel<<<grid, kWgThreads, smem, stream>>>(p);
+  wgrad_pair_kernel<<<grid, kWgPairThreads, smem, stream>>>(p);
   return cudaGetLastError();
 }
 

@@ -20,7 +20,7 @@ echo "fwd capture rc=$?"
 ncu --set full --clock-control none --import-source on -k 'regex:conv_halo_kernel' -s 86 -c 1 \
     -o gpurun_out/prof_bwd_$TAG -f $CMD > gpurun_out/ncu_bwd_$TAG.log 2>&1
 echo "bwd capture rc=$?"
-ncu --set full --clock-control none --import-source on -k 'regex:wgrad_' -s 3 -c 1 \
+ncu --set full --clock-control none --import-source on -k 'regex:^wgrad_(pair_)?kernel' -s 3 -c 1 \
     -o gpurun_out/prof_wgrad_$TAG -f $CMD > gpurun_out/ncu_wgrad_$TAG.log 2>&1
 echo "wgrad capture rc=$?"
 ls -la gpurun_out/
