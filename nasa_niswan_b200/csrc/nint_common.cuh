@@ -55,14 +55,18 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// suspend-time hint: a waiting thread may sleep up to this long inside one try_wait (it is woken when the phase
+// completes), instead of re-polling: 14 of a CTA's 16 warps are waiting at any time and every poll costs issue slots
+// and power on a part that runs power-capped
+constexpr uint32_t kMbarSuspendNs = 20000;
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(kMbarSuspendNs)
       : "memory");
   return ok != 0;
 }
@@ -75,6 +79,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if ((++spins & 0x3ff) == 0 && clock64() - t0 > 4000000000LL) {
       printf("nint: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", (int)blockIdx.x,
              (int)threadIdx.x, smem_u32(bar), parity);
+      __trap();
+    }
+  }
+}
+
+// Bounded spin on a shared-memory progress counter (in-order hand-off between two MMA-issuing warps): like
+// mbar_wait, a protocol bug traps instead of hanging the GPU.
+__device__ __forceinline__ void spin_until_at_least(volatile uint32_t* counter, uint32_t value) {
+  if (*counter >= value) return;
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+  while (*counter < value) {
+    if ((++spins & 0x3ff) == 0 && clock64() - t0 > 4000000000LL) {
+      printf("nint: progress counter wait timed out (block %d thread %d want %u have %u)\n", (int)blockIdx.x,
+             (int)threadIdx.x, value, *counter);
       __trap();
     }
   }

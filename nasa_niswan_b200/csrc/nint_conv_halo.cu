@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
       if (k == 0) mbar_wait(&w_full[j], 0);            // resident weights arrive during the first tile
       // chunks enter the tensor pipe strictly in order (deterministic accumulation order, and the tile's first
       // MMA with accumulate = 0 precedes the rest): wait until the other warp has issued all of chunk c-1
-      while (*mma_started < static_cast<uint32_t>(c)) { }
+      spin_until_at_least(mma_started, static_cast<uint32_t>(c));
       tc_fence_after();
       tr.stamp();
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(abuf * acc_cols);

@@ -505,7 +505,7 @@ wgrad_pair_kernel(const __grid_constant__ WgradParams p) {
         const uint32_t aph = static_cast<uint32_t>(i / kWgPairABufs) & 1u, bph = static_cast<uint32_t>(i / kWgPairBStages) & 1u;
         mbar_wait(&a_full[ab], aph);
         mbar_wait(&b_full[bs], bph);
-        while (*mma_issued < static_cast<uint32_t>(i)) { }   // the other warp has issued all of tile i-1
+        spin_until_at_least(mma_issued, static_cast<uint32_t>(i));   // the other warp has issued all of tile i-1
         tc_fence_after();
         if (leader && issue_any) {
           const uint32_t a0 = alo_base + sA16 + static_cast<uint32_t>((ab * a_buf_bytes) >> 4);
