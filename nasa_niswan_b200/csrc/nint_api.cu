@@ -105,7 +105,6 @@ struct nint_plan {
   bool fwd_done = false;
   int final_slot_h = 0, final_slot_c = 0;
   int cluster = 2;        // 2: CTA pairs (tcgen05 cta_group::2) where the layer geometry allows, 1: single CTAs
-  int base_offset_mode = 0;
   int debug_flags = 0;
   int plan_g = 0, plan_ns = 0;   // NINT_PLAN_G / NINT_PLAN_NS: experiment knobs of the backward kernel's shared-memory plan
   Profile prof;
@@ -359,7 +358,6 @@ int cell_step(nint_plan* p, int l, int t, int epi, float* raw_out, cudaStream_t 
   g.slot_h_out = out_slot_h;
   g.slot_g = (tr && epi == EPI_FWD) ? t : -1;
   g.raw_out = raw_out;
-  g.base_offset_mode = p->base_offset_mode;
   if (conv_halo_plan(epi, p->dtype, g)) return fail("layer %d: the conv kernel's shared-memory plan does not fit (hidden %d, k %d)", l, y.hc, y.k);
   for (int i = 0; i < g.nseg; ++i)
     if (get_w_map(p, y, g.seg[i].wsel, g.n_tile, g.n_tile / g.cluster, g.taps_per_stage, &g.seg[i].tmap_w)) return 1;
@@ -424,8 +422,6 @@ int nint_plan_create(const nint_config* cfg, nint_plan** out) {
     const char* c = getenv("NINT_CLUSTER");
     p->cluster = c ? atoi(c) : 2;
     if (p->cluster != 1 && p->cluster != 2) p->cluster = 1;
-    const char* b = getenv("NINT_BASE_OFFSET");
-    p->base_offset_mode = b ? atoi(b) : 0;
     const char* d = getenv("NINT_DEBUG_FLAGS");
     p->debug_flags = d ? atoi(d) : 0;
     const char* pg = getenv("NINT_PLAN_G");
@@ -770,8 +766,7 @@ int nint_backward(nint_plan* p, const float* dpred, const float* dseq, float* co
           g.head_w = p->head_w;
         }
       }
-      g.base_offset_mode = p->base_offset_mode;
-      if (conv_halo_plan(EPI_BWD, p->dtype, g)) return fail("layer %d: the dgrad kernel's shared-memory plan does not fit (hidden %d, k %d)", l, y.hc, y.k);
+          if (conv_halo_plan(EPI_BWD, p->dtype, g)) return fail("layer %d: the dgrad kernel's shared-memory plan does not fit (hidden %d, k %d)", l, y.hc, y.k);
       for (int i = 0; i < g.nseg; ++i) {
         Layer& owner = g.seg[i].wsel == 2 ? p->layer[l + 1] : y;   // wdx belongs to the layer above
         if (get_w_map(p, owner, g.seg[i].wsel, g.n_tile, g.n_tile / g.cluster, g.taps_per_stage, &g.seg[i].tmap_w)) return 1;

@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
   };
 
   // two activation producers when a tile needs many chunk loads (dgrad: K = 4*hc channels, G tiles per chunk)
-  const bool a_split = (EPI == EPI_BWD);
+  const bool a_split = (EPI != EPI_RAW);   // one producer warp cannot issue a box per 1152-cycle chunk (timeline: 670 cycles per box + waits)
 
   if (warp == 0) {
     if (p.nseg > 0) produce(true, 0, a_split ? 2 : 1, false);
@@ -544,7 +544,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
       if (warp == 5 && p.nseg > 0 && lead_cta && dual) issue_dual(1);   // second MMA issuer
     }
   } else if (warp >= kConvIoWarps) {
-    // ------------------------------------------------------------------ epilogue math (warps 4-11)
+    // ------------------------------------------------------------------ epilogue math (warps 8-15)
     // the epilogue of either CTA releases the accumulator buffer on the LEADER's "tmem empty" barrier
     uint32_t tempty_remote = 0;
     if constexpr (pair) tempty_remote = mapa_rank(smem_u32(&tempty_bar[0]), 0);

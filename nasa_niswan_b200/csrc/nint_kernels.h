@@ -42,7 +42,7 @@ struct alignas(64) ConvGemmParams {
   int n_blocks;  // N slices of the gate columns (forward: 4*hc / n_tile); a cluster owns one slice
   int num_stages;
   // halo variant (nint_conv_halo.cu): activation buffers, cluster size, descriptor base-offset policy
-  int na_bufs, a_buf_bytes, cluster, base_offset_mode, taps_per_stage;
+  int na_bufs, a_buf_bytes, cluster, taps_per_stage;
   int group, a_halo_bytes;  // tiles per group (side-by-side accumulators), bytes of one halo chunk
   int acc_cols, n_acc;      // TMEM columns of one accumulator buffer (group * n_tile), number of buffers (2 or 4)
   int plan_g, plan_ns;      // experiment knobs for conv_halo_plan: cap on tiles per group / epilogue stages (0 = auto)

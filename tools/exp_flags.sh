@@ -1,6 +1,6 @@
 #!/bin/bash
 for f in ${FLAGS:-0 1 2 3}; do
-  echo "##### NINT_DEBUG_FLAGS=$f (1: no epilogue memory/math, 2: no MMA issue)"
+  echo "##### NINT_DEBUG_FLAGS=$f (1: no epilogue math/stores, 2: no MMA issue, 4: wgrad MMA stream twice, 8: timeline trace, 32: single MMA issuer)"
   NINT_DEBUG_FLAGS=$f python bench.py --steps 6 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | python -c "
 import json,sys
 d=json.loads(sys.stdin.read())
