@@ -453,10 +453,18 @@ int nint_plan_create(const nint_config* cfg, nint_plan** out) {
     // traffic of the forward cell and L2 sector throughput was its bound (profiles/).
     y.hcb = y.hc < 64 ? y.hc : 64;
     if (cfg->dtype == BF16) {
-      for (int cand = y.hcb; cand >= 32; cand >>= 1) {
+      bool fits = false;
+      for (int cand = y.hcb; cand >= 32 && !fits; cand >>= 1) {
         const long long w_cta = static_cast<long long>((y.cin + 31) / 32 + (y.hc + 31) / 32) * y.taps * (4 * cand / p->cluster) * 64;
-        if (y.hc % cand == 0 && w_cta <= 112 * 1024) { y.hcb = cand; break; }
+        if (y.hc % cand == 0 && w_cta <= 112 * 1024) { y.hcb = cand; fits = true; }
       }
+      // weights that have to stream (5x5 taps, wide layers): N = 128 with two pixel tiles sharing every weight stage
+      // moves half the weight bytes per tile of N = 256 (measured: 5x5 forward 645 -> 328 us, cfg 5 352 -> 314 ms)
+      if (!fits && y.hc >= 32 && y.hc % 32 == 0) y.hcb = 32;
+    }
+    if (const char* e = getenv("NINT_HCB")) {   // experiment knob: force the forward n-block width (16 / 32 / 64)
+      const int v = atoi(e);
+      if (v >= 16 && v <= 64 && (v & (v - 1)) == 0 && y.hc % v == 0) y.hcb = v;
     }
     y.n_blocks = y.hc / y.hcb; y.n_tile = 4 * y.hcb;
     y.nslots_h = cfg->training ? p->T + 1 : 2;
