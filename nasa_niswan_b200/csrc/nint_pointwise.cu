@@ -328,16 +328,18 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const E* __restrict__ h, 
   constexpr int KMAX = 8;   // hc_pad <= 256
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nk = hc_pad >> 5;
-  const long long total = static_cast<long long>(B) * npix;
-  const long long wstride = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
+  // blockIdx.y = image, blockIdx.x strides over that image's pixels: no division in the loop
+  const int b = blockIdx.y;
+  const float* dp = dpred + b * dpred_bstride;
+  const E* hb = h + static_cast<long long>(b) * npix * hc_pad;
+  const int wstride = gridDim.x * (blockDim.x >> 5);
   float acc[KMAX];
 #pragma unroll
   for (int k = 0; k < KMAX; ++k) acc[k] = 0.f;
   float accb = 0.f;
-  for (long long p = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + warp; p < total; p += wstride) {
-    const long long b = p / npix;
-    const float d = dpred[b * dpred_bstride + (p - b * npix)];
-    const E* row = h + p * hc_pad;
+  for (int px = blockIdx.x * (blockDim.x >> 5) + warp; px < npix; px += wstride) {
+    const float d = dp[px];
+    const E* row = hb + static_cast<long long>(px) * hc_pad;
 #pragma unroll
     for (int k = 0; k < KMAX; ++k)
       if (k < nk) acc[k] = fmaf(d, from_elem(row[k * 32 + lane]), acc[k]);
@@ -363,7 +365,9 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const E* __restrict__ h, 
 cudaError_t launch_head_bwd(int dtype, const void* h, const float* dpred, long long dpred_bstride, float* dw, float* db,
                             long long npix, int B, int hc, int hc_pad, cudaStream_t s) {
   const int block = 256;
-  const int grid = 148 * 8;
+  int gx = (148 * 8 + B - 1) / B;
+  if (gx < 1) gx = 1;
+  const dim3 grid(gx, B);
   if (dtype == NINT_BF16)
     head_bwd_kernel<__nv_bfloat16><<<grid, block, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(h), dpred, dpred_bstride,
                                                          dw, db, npix, B, hc, hc_pad);
