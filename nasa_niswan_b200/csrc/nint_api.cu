@@ -106,6 +106,7 @@ struct nint_plan {
   int final_slot_h = 0, final_slot_c = 0;
   int cluster = 2;        // 2: CTA pairs (tcgen05 cta_group::2) where the layer geometry allows, 1: single CTAs
   int debug_flags = 0;
+  int ones_lane = -1;     // padding channel of X that holds 1.0 (bias gradient through the wgrad GEMM), -1: no spare channel
   int plan_g = 0, plan_ns = 0;   // NINT_PLAN_G / NINT_PLAN_NS: experiment knobs of the backward kernel's shared-memory plan
   Profile prof;
 };
@@ -447,6 +448,9 @@ int nint_plan_create(const nint_config* cfg, nint_plan** out) {
     if (l > 0 && cin > 256) { delete p; return fail("layer %d input channels %d > 256", l, cin); }
     y.cx_pad = (y.cin + 31) / 32 * 32; y.chx = y.cx_pad / p->ce;   // channels padded to 32 in both dtypes
     y.hc_pad = (y.hc + 31) / 32 * 32;  y.chh = y.hc_pad / p->ce;
+    // a spare padding channel of X carries 1.0: the packed forward weights are zero there (no effect on the cell),
+    // and the weight-gradient GEMM then produces the bias gradient in that column for free
+    if (l == 0 && y.cx_pad > y.cin && !(p->debug_flags & 128)) p->ones_lane = y.cin;
     // forward N slice (n-block) = hcb hidden channels x 4 gates.  If the whole weight slice of an n-block
     // fits in shared memory next to the halo buffers and epilogue stages (<= 112 KiB per CTA of a pair), the
     // conv kernel keeps it resident and only activations stream: weight re-reads were ~55 % of the L2 -> SM
@@ -632,7 +636,7 @@ int nint_forward(nint_plan* p, const float* x, float* pred, float* seq, void* st
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool tr = p->cfg.training != 0;
   const long long HW = static_cast<long long>(p->H) * p->W;
-  LAUNCH(p, K_OTHER, st, launch_pack_input(p->dtype, x, p->X, p->B, p->T, p->cfg.in_channels, p->H, p->W, p->layer[0].cx_pad, st));
+  LAUNCH(p, K_OTHER, st, launch_pack_input(p->dtype, x, p->X, p->B, p->T, p->cfg.in_channels, p->H, p->W, p->layer[0].cx_pad, p->ones_lane, st));
   const Layer& top = p->layer[p->L - 1];
   for (int t = 0; t < p->T; ++t) {          // model.py:265
     for (int l = 0; l < p->L; ++l)          // model.py:267
@@ -701,7 +705,7 @@ int nint_debug_raw_gates(nint_plan* p, const float* x, float* out, void* stream)
   if (check_ready(p)) return 1;
   if (!x || !out) return fail("nint_debug_raw_gates: null argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  LAUNCH(p, K_OTHER, st, launch_pack_input(p->dtype, x, p->X, p->B, p->T, p->cfg.in_channels, p->H, p->W, p->layer[0].cx_pad, st));
+  LAUNCH(p, K_OTHER, st, launch_pack_input(p->dtype, x, p->X, p->B, p->T, p->cfg.in_channels, p->H, p->W, p->layer[0].cx_pad, p->ones_lane, st));
   return cell_step(p, 0, 0, EPI_RAW, out, st);
 }
 
@@ -811,30 +815,61 @@ int nint_backward(nint_plan* p, const float* dpred, const float* dseq, float* co
     }
     w.m_blocks = w.pair ? w.hc4 / 256 : (w.hc4 + 127) / 128;
     w.ncols = y.ncols;
-    // tap groups: a CTA keeps (taps in group) x ncols accumulator columns in TMEM (512 available); the 32 bias
-    // columns go to whichever group is lightest (the last one when it has room, else the first)
+    // tap groups: a CTA keeps (taps in group) x ncols accumulator columns in TMEM (512 available).  The bias
+    // gradient is either free (layer 0: x carries 1.0 in padding channel `ones_lane`, so db is that column of the
+    // centre tap) or costs 32 more columns and one N=32 MMA per K step in the lightest group (the last one when it
+    // has room, else the first).
+    const int bias_col = (l == 0) ? p->ones_lane : -1;
+    const int bias_cols = bias_col >= 0 ? 0 : 32;
     const int tpg = 512 / y.ncols;                      // taps per group
     if (tpg < 1) return fail("wgrad: ncols %d exceeds the accumulator", y.ncols);
     int ng = 0, tap = 0;
     w.group_tap0[0] = 0;
-    const int full_groups = y.taps / tpg, rest = y.taps % tpg;
-    const bool bias_last = rest > 0 && rest * y.ncols + 32 <= 512;   // a partial last group with room for the bias
-    const int g0 = bias_last ? tpg : ((512 - 32) / y.ncols < tpg ? (512 - 32) / y.ncols : tpg);
+    const int rest = y.taps % tpg;
+    const bool bias_last = rest > 0 && rest * y.ncols + bias_cols <= 512;   // a partial last group with room for the bias
+    const int g0 = bias_last ? tpg : ((512 - bias_cols) / y.ncols < tpg ? (512 - bias_cols) / y.ncols : tpg);
     if (g0 < 1) return fail("wgrad: ncols %d leaves no room for the bias columns", y.ncols);
-    (void)full_groups;
     while (tap < y.taps) {
       const int n = ng == 0 ? g0 : tpg;
       tap = tap + n > y.taps ? y.taps : tap + n;
       if (ng + 1 > kMaxWgradGroups) return fail("wgrad: too many tap groups");
       w.group_tap0[++ng] = tap;
     }
-    w.bias_group = bias_last ? ng - 1 : 0;
+    w.bias_group = bias_col >= 0 ? -1 : (bias_last ? ng - 1 : 0);
     w.n_groups = ng;
+    // split-K over pixel tiles: every group gets a share of the SMs in proportion to its MMA cycles per K step
+    // (pair MMA: ~N/2 cycles with a ~40-cycle floor; 1-CTA MMA: ~N*0.67 with a ~88-cycle floor -- DESIGN.md 4)
     const long long total_tiles = static_cast<long long>(T) * p->B * p->tiles_x * p->tiles_y;
-    int splits = (w.pair ? p->num_sms / 2 : p->num_sms) / (w.m_blocks * ng);
-    if (splits < 1) splits = 1;
-    if (splits > total_tiles) splits = static_cast<int>(total_tiles);
-    w.splits = splits;
+    {
+      const int units = (w.pair ? p->num_sms / 2 : p->num_sms) / w.m_blocks;   // (group, split) slots
+      auto mma_cost = [&](int n) { return w.pair ? (n / 2 > 40 ? n / 2 : 40) : (n * 2 / 3 > 88 ? n * 2 / 3 : 88); };
+      int cost[kMaxWgradGroups], tot = 0;
+      for (int g = 0; g < ng; ++g) {
+        cost[g] = (w.group_tap0[g + 1] - w.group_tap0[g]) * mma_cost(y.ncols) + (g == w.bias_group ? mma_cost(32) : 0);
+        tot += cost[g];
+      }
+      const bool even = (p->debug_flags & 64) != 0;     // experiment: the same split count for every group
+      int used = 0;
+      for (int g = 0; g < ng; ++g) {
+        int sp = even ? units / ng : static_cast<int>(static_cast<long long>(units) * cost[g] / tot);
+        if (sp < 1) sp = 1;
+        w.group_splits[g] = sp;
+        used += sp;
+      }
+      // hand the remaining slots to whichever group has the most work per split
+      while (!even && used < units) {
+        int best = 0;
+        for (int g = 1; g < ng; ++g)
+          if (static_cast<long long>(cost[g]) * w.group_splits[best] > static_cast<long long>(cost[best]) * w.group_splits[g]) best = g;
+        ++w.group_splits[best];
+        ++used;
+      }
+      w.group_unit0[0] = 0;
+      for (int g = 0; g < ng; ++g) {
+        if (w.group_splits[g] > total_tiles) w.group_splits[g] = static_cast<int>(total_tiles);
+        w.group_unit0[g + 1] = w.group_unit0[g] + w.m_blocks * w.group_splits[g];
+      }
+    }
     wgrad_pick_buffers(p->dtype, y.ncols / 32, w.b_panel_bytes, &w.a_bufs, &w.b_stages);
     if (w.b_stages < 1) return fail("wgrad: operand panels do not fit in shared memory");
     w.idesc = idesc_of(p->dtype, w.pair ? 256 : 128, y.ncols, 1, 1);
@@ -843,7 +878,7 @@ int nint_backward(nint_plan* p, const float* dpred, const float* dseq, float* co
     w.db_acc = y.db_acc;
     LAUNCH(p, K_WGRAD, st, launch_wgrad(p->dtype, w, st));
     if (grad_weight[l])
-      LAUNCH(p, K_OTHER, st, launch_unpack_wgrad(y.dw_acc, y.db_acc, grad_weight[l], grad_bias[l], y.cin, y.hc, y.k, y.ncols, y.cx_pad, 0, st));
+      LAUNCH(p, K_OTHER, st, launch_unpack_wgrad(y.dw_acc, y.db_acc, grad_weight[l], grad_bias[l], y.cin, y.hc, y.k, y.ncols, y.cx_pad, bias_col, 0, st));
   }
   return 0;
 }

@@ -92,8 +92,10 @@ struct alignas(64) WgradParams {
   int m_blocks;           // ceil(4*hc / 128)
   int n_groups;
   int group_tap0[kMaxWgradGroups + 1];  // taps [group_tap0[g], group_tap0[g+1]) belong to group g
-  int bias_group;         // tap group whose CTAs also accumulate the bias gradient
-  int splits;             // split-K factor over pixel tiles
+  int bias_group;         // tap group whose CTAs also accumulate the bias gradient with a ones-panel MMA (-1: none --
+                          // the x tensor carries a constant 1.0 in a padding channel and db falls out of the centre tap)
+  int group_splits[kMaxWgradGroups];    // split-K factor over pixel tiles, per tap group (in proportion to its MMA cost)
+  int group_unit0[kMaxWgradGroups + 1]; // first CTA (cluster, for the pair kernel) of each group; [n_groups] = grid units
   int ncols;              // accumulator columns per tap = (sum nchunks_b) * 32
   int a_bufs, b_stages;
   int halo;               // 1: 8x16 tiles, B panels hold the tile + k//2 halo and every tap re-reads them in place
@@ -114,8 +116,9 @@ cudaError_t launch_wgrad(int dtype, const WgradParams& p, cudaStream_t stream);
 
 // ---- pointwise / layout kernels (nint_pointwise.cu)
 // x [B,T,C,H,W] fp32 (model.py:255) -> X [T][B][H][W][c_pad] E (pad channels zero)
+// ones_lane >= C: that padding channel is set to 1.0 (bias gradient through the wgrad GEMM), -1: none
 cudaError_t launch_pack_input(int dtype, const float* x, void* X, int B, int T, int C, int H, int W, int c_pad,
-                              cudaStream_t s);
+                              int ones_lane, cudaStream_t s);
 // NCHW fp32 <-> NHWC E (state import / export for the cell API)
 cudaError_t launch_pack_state(int dtype, const float* src_nchw, void* dst_nhwc, int B, int C, int H, int W,
                               int c_pad, cudaStream_t s);
@@ -133,9 +136,10 @@ cudaError_t launch_head_fwd(int dtype, const void* h, const float* w, const floa
                             int B, int hc, int hc_pad, long long out_bstride, cudaStream_t s);
 cudaError_t launch_head_bwd(int dtype, const void* h, const float* dpred, long long dpred_bstride, float* dw, float* db,
                             long long npix_per_img, int B, int hc, int hc_pad, cudaStream_t s);
-// dw_acc [taps][4hc (q)][ncols] -> grad weight OIHW [4hc][cin+hc][k][k]; db_acc (q) -> grad bias
+// dw_acc [taps][4hc (q)][ncols] -> grad weight OIHW [4hc][cin+hc][k][k]; grad bias from db_acc (q), or from column
+// bias_col of the centre tap of dw_acc when bias_col >= 0
 cudaError_t launch_unpack_wgrad(const float* dw_acc, const float* db_acc, float* gw, float* gb, int cin, int hc,
-                                int k, int ncols, int cx_pad, int accumulate, cudaStream_t s);
+                                int k, int ncols, int cx_pad, int bias_col, int accumulate, cudaStream_t s);
 
 // preprocessing fusion: stack levels + emission, z-score, cyclic-longitude / reflect-latitude halo
 cudaError_t launch_fuse_inputs(const float* lev, const float* emis, const float* mean, const float* stdv, float* out,

@@ -31,7 +31,7 @@ __device__ __forceinline__ float from_elem(float v) { return v; }
 template <typename E, int CP>
 __global__ void pack_cl_kernel(const float* __restrict__ src, E* __restrict__ dst, int C, long long HW,
                                int n_outer, int n_inner, long long src_outer_stride, long long src_inner_stride,
-                               long long dst_outer_stride, long long dst_inner_stride) {
+                               long long dst_outer_stride, long long dst_inner_stride, int ones_lane) {
   // image (o, i): src + o*src_outer_stride + i*src_inner_stride, [C][HW];  dst + o*dst_outer + i*dst_inner, [HW][CP]
   const long long total = static_cast<long long>(n_outer) * n_inner * HW;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
@@ -44,24 +44,24 @@ __global__ void pack_cl_kernel(const float* __restrict__ src, E* __restrict__ ds
     E* d = dst + o * dst_outer_stride + i * dst_inner_stride + pix * CP;
     float v[CP];
 #pragma unroll
-    for (int c = 0; c < CP; ++c) v[c] = (c < C) ? round_for(__ldg(s + c * HW), (E*)nullptr) : 0.f;
+    for (int c = 0; c < CP; ++c) v[c] = (c < C) ? round_for(__ldg(s + c * HW), (E*)nullptr) : (c == ones_lane ? 1.f : 0.f);
     store_elems<E, CP>(d, v);
   }
 }
 
 template <typename E>
 static cudaError_t pack_cl(const float* src, E* dst, int C, int c_pad, long long HW, int n_outer, int n_inner,
-                           long long so, long long si, long long dso, long long dsi, cudaStream_t s) {
+                           long long so, long long si, long long dso, long long dsi, int ones_lane, cudaStream_t s) {
   const long long total = static_cast<long long>(n_outer) * n_inner * HW;
   const int threads = 256;
   long long blocks = (total + threads - 1) / threads;
   if (blocks > 148 * 16) blocks = 148 * 16;
   if (blocks <= 0) return cudaSuccess;
   switch (c_pad) {
-    case 16: pack_cl_kernel<E, 16><<<blocks, threads, 0, s>>>(src, dst, C, HW, n_outer, n_inner, so, si, dso, dsi); break;
-    case 32: pack_cl_kernel<E, 32><<<blocks, threads, 0, s>>>(src, dst, C, HW, n_outer, n_inner, so, si, dso, dsi); break;
-    case 48: pack_cl_kernel<E, 48><<<blocks, threads, 0, s>>>(src, dst, C, HW, n_outer, n_inner, so, si, dso, dsi); break;
-    case 64: pack_cl_kernel<E, 64><<<blocks, threads, 0, s>>>(src, dst, C, HW, n_outer, n_inner, so, si, dso, dsi); break;
+    case 16: pack_cl_kernel<E, 16><<<blocks, threads, 0, s>>>(src, dst, C, HW, n_outer, n_inner, so, si, dso, dsi, ones_lane); break;
+    case 32: pack_cl_kernel<E, 32><<<blocks, threads, 0, s>>>(src, dst, C, HW, n_outer, n_inner, so, si, dso, dsi, ones_lane); break;
+    case 48: pack_cl_kernel<E, 48><<<blocks, threads, 0, s>>>(src, dst, C, HW, n_outer, n_inner, so, si, dso, dsi, ones_lane); break;
+    case 64: pack_cl_kernel<E, 64><<<blocks, threads, 0, s>>>(src, dst, C, HW, n_outer, n_inner, so, si, dso, dsi, ones_lane); break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();
@@ -71,7 +71,7 @@ static cudaError_t pack_cl(const float* src, E* dst, int C, int c_pad, long long
 template <typename E>
 __global__ void pack_cl_wide_kernel(const float* __restrict__ src, E* __restrict__ dst, int C, int c_pad,
                                     long long HW, int n_outer, int n_inner, long long so, long long si,
-                                    long long dso, long long dsi) {
+                                    long long dso, long long dsi, int ones_lane) {
   const int groups = c_pad / 16;
   const long long total = static_cast<long long>(n_outer) * n_inner * groups * HW;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
@@ -88,7 +88,7 @@ __global__ void pack_cl_wide_kernel(const float* __restrict__ src, E* __restrict
 #pragma unroll
     for (int c = 0; c < 16; ++c) {
       const int ch = g * 16 + c;
-      v[c] = (ch < C) ? round_for(__ldg(s + ch * HW), (E*)nullptr) : 0.f;
+      v[c] = (ch < C) ? round_for(__ldg(s + ch * HW), (E*)nullptr) : (ch == ones_lane ? 1.f : 0.f);
     }
     store_elems<E, 16>(d, v);
   }
@@ -96,26 +96,26 @@ __global__ void pack_cl_wide_kernel(const float* __restrict__ src, E* __restrict
 
 template <typename E>
 static cudaError_t pack_any(const float* src, E* dst, int C, int c_pad, long long HW, int n_outer, int n_inner,
-                            long long so, long long si, long long dso, long long dsi, cudaStream_t s) {
+                            long long so, long long si, long long dso, long long dsi, cudaStream_t s, int ones_lane = -1) {
   if (c_pad % 16) return cudaErrorInvalidValue;
-  if (c_pad <= 64) return pack_cl<E>(src, dst, C, c_pad, HW, n_outer, n_inner, so, si, dso, dsi, s);
+  if (c_pad <= 64) return pack_cl<E>(src, dst, C, c_pad, HW, n_outer, n_inner, so, si, dso, dsi, ones_lane, s);
   const long long total = static_cast<long long>(n_outer) * n_inner * (c_pad / 16) * HW;
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   if (blocks <= 0) return cudaSuccess;
-  pack_cl_wide_kernel<E><<<blocks, 256, 0, s>>>(src, dst, C, c_pad, HW, n_outer, n_inner, so, si, dso, dsi);
+  pack_cl_wide_kernel<E><<<blocks, 256, 0, s>>>(src, dst, C, c_pad, HW, n_outer, n_inner, so, si, dso, dsi, ones_lane);
   return cudaGetLastError();
 }
 
 cudaError_t launch_pack_input(int dtype, const float* x, void* X, int B, int T, int C, int H, int W, int c_pad,
-                              cudaStream_t s) {
+                              int ones_lane, cudaStream_t s) {
   // x[b][t] (model.py:266) -> X[t][b]: outer = b, inner = t
   const long long HW = static_cast<long long>(H) * W;
   const long long so = static_cast<long long>(T) * C * HW, si = C * HW;
   const long long dso = HW * c_pad, dsi = static_cast<long long>(B) * HW * c_pad;
   if (dtype == NINT_BF16)
-    return pack_any<__nv_bfloat16>(x, reinterpret_cast<__nv_bfloat16*>(X), C, c_pad, HW, B, T, so, si, dso, dsi, s);
-  return pack_any<float>(x, reinterpret_cast<float*>(X), C, c_pad, HW, B, T, so, si, dso, dsi, s);
+    return pack_any<__nv_bfloat16>(x, reinterpret_cast<__nv_bfloat16*>(X), C, c_pad, HW, B, T, so, si, dso, dsi, s, ones_lane);
+  return pack_any<float>(x, reinterpret_cast<float*>(X), C, c_pad, HW, B, T, so, si, dso, dsi, s, ones_lane);
 }
 
 cudaError_t launch_pack_state(int dtype, const float* src, void* dst, int B, int C, int H, int W, int c_pad,
@@ -380,7 +380,7 @@ cudaError_t launch_head_bwd(int dtype, const void* h, const float* dpred, long l
 // dw_acc [taps][4hc (q)][ncols] -> grad W[n][c][dy][dx];  col(c) = c (x part) or cx_pad + (c - cin) (h part)
 __global__ void unpack_wgrad_kernel(const float* __restrict__ dw_acc, const float* __restrict__ db_acc,
                                     float* __restrict__ gw, float* __restrict__ gb, int cin, int hc, int k, int ncols,
-                                    int cx_pad, int accumulate) {
+                                    int cx_pad, int bias_col, int accumulate) {
   const int taps = k * k, ctot = cin + hc, hc4 = 4 * hc;
   const long long total = static_cast<long long>(hc4) * ctot * taps;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
@@ -398,13 +398,15 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ dw_acc, const floa
   if (gb) {
     for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < hc4; q += gridDim.x * blockDim.x) {
       float* dst = gb + q_to_n(q, hc);
-      *dst = accumulate ? *dst + db_acc[q] : db_acc[q];
+      // bias_col: x carried 1.0 in that channel, so the centre tap's column is sum_pixels dgates = db
+      const float v = bias_col >= 0 ? dw_acc[(static_cast<long long>(taps / 2) * hc4 + q) * ncols + bias_col] : db_acc[q];
+      *dst = accumulate ? *dst + v : v;
     }
   }
 }
 cudaError_t launch_unpack_wgrad(const float* dw_acc, const float* db_acc, float* gw, float* gb, int cin, int hc, int k,
-                                int ncols, int cx_pad, int accumulate, cudaStream_t s) {
-  unpack_wgrad_kernel<<<296, 256, 0, s>>>(dw_acc, db_acc, gw, gb, cin, hc, k, ncols, cx_pad, accumulate);
+                                int ncols, int cx_pad, int bias_col, int accumulate, cudaStream_t s) {
+  unpack_wgrad_kernel<<<296, 256, 0, s>>>(dw_acc, db_acc, gw, gb, cin, hc, k, ncols, cx_pad, bias_col, accumulate);
   return cudaGetLastError();
 }
 

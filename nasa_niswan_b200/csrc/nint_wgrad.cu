@@ -84,15 +84,18 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ctrl + kWgCtrlBytes - 16);
 
   // blockIdx -> (split, group, m-block); CTAs of one split share their pixel tiles through L2
-  const int mb = blockIdx.x % p.m_blocks;
-  const int grp = (blockIdx.x / p.m_blocks) % p.n_groups;
-  const int split = blockIdx.x / (p.m_blocks * p.n_groups);
+  int grp = 0;
+  while (grp + 1 < p.n_groups && static_cast<int>(blockIdx.x) >= p.group_unit0[grp + 1]) ++grp;
+  const int unit = static_cast<int>(blockIdx.x) - p.group_unit0[grp];
+  const int mb = unit % p.m_blocks;
+  const int split = unit / p.m_blocks;
+  const int nsplits = p.group_splits[grp];
   const int tap_begin = p.group_tap0[grp];
   const int ntaps = p.group_tap0[grp + 1] - tap_begin;
   const bool do_bias = (grp == p.bias_group) && (p.db_acc != nullptr);
   const int tiles_per_img = p.tiles_x * p.tiles_y;
   const int total_tiles = p.T * p.B * tiles_per_img;
-  const int my_tiles = (total_tiles - split + p.splits - 1) / p.splits;  // split < splits <= total or 0 tiles
+  const int my_tiles = (total_tiles - split + nsplits - 1) / nsplits;  // split < splits <= total or 0 tiles
   const uint32_t panel_tx = static_cast<uint32_t>(p.tile_w * p.tile_h * ROWB);
   const int pad = p.ksize >> 1;
 
@@ -139,7 +142,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
       int ab = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
       for (int i = 0; i < my_tiles; ++i) {
-        int r = split + i * p.splits;
+        int r = split + i * nsplits;
         const int tx = r % p.tiles_x;
         r /= p.tiles_x;
         const int ty = r % p.tiles_y;
@@ -369,15 +372,18 @@ wgrad_pair_kernel(const __grid_constant__ WgradParams p) {
 
   // cluster -> (split, tap group, m-block of 256 q)
   const int cid = blockIdx.x >> 1;
-  const int mb = cid % p.m_blocks;
-  const int grp = (cid / p.m_blocks) % p.n_groups;
-  const int split = cid / (p.m_blocks * p.n_groups);
+  int grp = 0;
+  while (grp + 1 < p.n_groups && cid >= p.group_unit0[grp + 1]) ++grp;
+  const int unit = cid - p.group_unit0[grp];
+  const int mb = unit % p.m_blocks;
+  const int split = unit / p.m_blocks;
+  const int nsplits = p.group_splits[grp];
   const int tap_begin = p.group_tap0[grp];
   const int ntaps = p.group_tap0[grp + 1] - tap_begin;
   const bool do_bias = (grp == p.bias_group) && (p.db_acc != nullptr);
   const int tiles_per_img = p.tiles_x * p.tiles_y;
   const int total_tiles = p.T * p.B * tiles_per_img;
-  const int my_tiles = (total_tiles - split + p.splits - 1) / p.splits;
+  const int my_tiles = (total_tiles - split + nsplits - 1) / nsplits;
   const int pad = p.ksize >> 1;
 
   {
@@ -411,7 +417,7 @@ wgrad_pair_kernel(const __grid_constant__ WgradParams p) {
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   auto tile_coords = [&](int i, int& x0, int& y0, int& b, int& t) {
-    int r = split + i * p.splits;
+    int r = split + i * nsplits;
     const int tx = r % p.tiles_x;
     r /= p.tiles_x;
     const int ty = r % p.tiles_y;
@@ -611,7 +617,7 @@ static cudaError_t launch_wg_pair(const WgradParams& p, cudaStream_t stream) {
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  const int grid = 2 * p.m_blocks * p.n_groups * p.splits;
+  const int grid = 2 * p.group_unit0[p.n_groups];
   if (grid <= 0) return cudaSuccess;
   wgrad_pair_kernel<<<grid, kWgPairThreads, smem, stream>>>(p);
   return cudaGetLastError();
@@ -627,7 +633,7 @@ static cudaError_t launch_wg(const WgradParams& p, cudaStream_t stream) {
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  const int grid = p.m_blocks * p.n_groups * p.splits;
+  const int grid = p.group_unit0[p.n_groups];
   if (grid <= 0) return cudaSuccess;
   wgrad_kernel<E><<<grid, kWgThreads, smem, stream>>>(p);
   return cudaGetLastError();
