@@ -236,10 +236,13 @@ def main():
                                  "frac": round(flops[name] * K_ / (ms * 1e-3) / 1e12 / peak_tf, 4)}
         dominant = max(kernels, key=lambda n_: kernels[n_]["ms_per_step"])
         conv_ms = sum(v["ms_per_step"] for v in kernels.values())
-        # the fused dgrad + gate-backward kernel is HBM-bound: 2048 algorithmic bytes per pixel-step
-        # (gates r 512 + dgates w 512 + c_t 256 + c_{t-1} 256 + dc r/w 512, bf16 gates / fp32 state)
+        # the fused dgrad + gate-backward kernel is HBM-bound.  Algorithmic bytes per pixel of one launch
+        # (bf16 gates / fp32 state, hidden 64): gates_t r 512 + dgates_t w 512 + dc w 256 in every launch; the dgrad
+        # operand dgates_{t+1} r 512, c_{t-1} r 256 and dc r 256 in T-1 of the T launches (nothing flows into the last
+        # step, nothing precedes the first); c_t is recomputed, not read.  Average over the T launches of a step.
         esz = 2 if args.precision == "bf16" else 4
-        bwd_bytes = B * H * W * (2 * 4 * HIDDEN * esz + 4 * HIDDEN * 4)
+        gates_b, state_b = 4 * HIDDEN * esz, HIDDEN * 4
+        bwd_bytes = int(B * H * W * (2 * gates_b + state_b + (gates_b + 2 * state_b) * (T - 1) / T))
         hbm_peak = peaks.get("hbm_gbs", 6550.0)
         if "dgrad_gate_bwd" in kernels:
             kb = kernels["dgrad_gate_bwd"]

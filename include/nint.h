@@ -80,14 +80,16 @@ int nint_backward(nint_plan* plan, const float* dpred, const float* dseq, float*
 
 /* ---- preprocessing fusion (north-star item 4).  Stacks the first `levels` model
  * levels of a 3-D forcing levels3d [frames,levels,H,W] with the 2-D emission field emis2d [frames,H,W] as the last
- * channel (dataset.py:526), z-scores every channel with mean/std [levels+1] (dataset.py:520-529) and adds the
- * geophysical halo -- cyclic in longitude, reflected in latitude (dataset.py:67-98, 535-536) -- giving
- * out [frames,levels+1,padded_height,padded_width] fp32, the model's input layout.  mode 0: true reflect
+ * channel (dataset.py:526), z-scores every channel with mean/std [levels+1] (dataset.py:520-529), appends the
+ * n_static already z-scored static attribute fields statics [n_static,H,W] to every frame (dataset.py:100-122,
+ * 532-533; NULL / 0 for none) and adds the geophysical halo -- cyclic in longitude, reflected in latitude
+ * (dataset.py:67-98, 535-536) -- giving out [frames,levels+1+n_static,padded_height,padded_width] fp32, the
+ * model's input layout.  mode 0: true reflect
  * (dataset.py:38-53); mode 1: bug-compatible with the shipped RNN dataset (np.fliplr flips channels, dataset.py:96).
  * Same error conditions as dataset.py:80,98.  PARITY UNPINNED upstream for levels > 1 (no shipped code). */
-int nint_fuse_inputs(const float* levels3d, const float* emis2d, const float* mean, const float* std, long long frames,
-                     int levels, int height, int width, int padded_height, int padded_width, int mode, float* out,
-                     void* stream);
+int nint_fuse_inputs(const float* levels3d, const float* emis2d, const float* mean, const float* std,
+                     const float* statics, int n_static, long long frames, int levels, int height, int width,
+                     int padded_height, int padded_width, int mode, float* out, void* stream);
 
 /* ---- the rest of the training step (train.py:101-110), SURVEY.md section 8f rank 1.
  * nint_loss_mse_l1: loss = MSELoss(y, p) + L1Loss(y, p) (train.py:74-75,105) with p = pred[:, 0, y0:y1, x0:x1]

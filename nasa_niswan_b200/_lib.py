@@ -57,7 +57,7 @@ def load():
     L.nint_debug_read_trace.argtypes = [ctypes.POINTER(ctypes.c_longlong), ci, ci]
     L.nint_loss_mse_l1.argtypes = [fp, fp, ci, ci, ci, ci, ci, ci, ci, fp, fp, fp, vp]
     cf, cll = ctypes.c_float, ctypes.c_longlong
-    L.nint_fuse_inputs.argtypes = [fp, fp, fp, fp, cll, ci, ci, ci, ci, ci, ci, fp, vp]
+    L.nint_fuse_inputs.argtypes = [fp, fp, fp, fp, fp, ci, cll, ci, ci, ci, ci, ci, ci, fp, vp]
     L.nint_adam_step.argtypes = [fp, fp, fp, fp, cll, cf, cf, cf, cf, ci, cf, vp]
     L.nint_pick_tile.argtypes = [ci, ci, ctypes.POINTER(ci), ctypes.POINTER(ci)]
     for name in EXPORTS:

@@ -655,10 +655,11 @@ int nint_forward(nint_plan* p, const float* x, float* pred, float* seq, void* st
   return 0;
 }
 
-int nint_fuse_inputs(const float* levels3d, const float* emis2d, const float* mean, const float* std, long long frames,
-                     int levels, int height, int width, int padded_height, int padded_width, int mode, float* out,
-                     void* stream) {
+int nint_fuse_inputs(const float* levels3d, const float* emis2d, const float* mean, const float* std,
+                     const float* statics, int n_static, long long frames, int levels, int height, int width,
+                     int padded_height, int padded_width, int mode, float* out, void* stream) {
   if ((!levels3d && levels > 0) || !emis2d || !mean || !std || !out) return fail("nint_fuse_inputs: null argument");
+  if (n_static < 0 || (n_static > 0 && !statics)) return fail("nint_fuse_inputs: %d static fields but no data", n_static);
   if (frames < 1 || levels < 0 || height < 1 || width < 1) return fail("nint_fuse_inputs: bad shape");
   if (mode != 0 && mode != 1) return fail("nint_fuse_inputs: mode must be 0 (reflect) or 1 (reference RNN dataset)");
   const int left = (padded_width - width) / 2, right = padded_width - width - left;
@@ -669,7 +670,7 @@ int nint_fuse_inputs(const float* levels3d, const float* emis2d, const float* me
   if (top + 1 > height || bot + 1 > height)   // dataset.py:98
     return fail("The requested padding size is larger than height size of the input image.");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  LAUNCH(nullptr, K_OTHER, st, launch_fuse_inputs(levels3d, emis2d, mean, std, out, frames, levels, height, width, padded_height, padded_width, mode, st));
+  LAUNCH(nullptr, K_OTHER, st, launch_fuse_inputs(levels3d, emis2d, mean, std, statics, n_static, out, frames, levels, height, width, padded_height, padded_width, mode, st));
   return 0;
 }
 
@@ -762,7 +763,6 @@ int nint_backward(nint_plan* p, const float* dpred, const float* dseq, float* co
       // epilogue I/O: gates_t -> dgates_t in place, c_t, c_{t-1}, running dc in place
       g.tm_c = y.tme_C; g.tm_h = y.tme_H; g.tm_g = y.tme_G; g.tm_dc = y.tme_dC;
       g.slot_g = t;
-      g.slot_c_cur = t + 1;
       g.slot_c_prev = (t == 0 && p->zero_init) ? -1 : t;
       g.has_dc_in = (t == T - 1) ? 0 : 1;
       g.slot_c_in = g.slot_c_out = g.slot_h_out = -1;

@@ -569,7 +569,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
 // shared-memory plan: epilogue I/O stages, tiles per group, taps per weight stage, stage / halo-buffer counts
 int conv_halo_plan(int epi, int dtype, ConvGemmParams& p) {
   const int esize = dtype == NINT_BF16 ? 2 : 4;
-  // ---- epilogue stage layout (nint_epilogue.cuh): [gates][c / c_t][c_{t-1}][dc] or [gates][c][h]
+  // ---- epilogue stage layout (nint_epilogue.cuh): backward [gates][c_{t-1}][dc], forward [gates][h] + c ring
   const int gate_bytes = kTilePixels * 64 * esize;
   p.c_ring = 0;
   if (epi == EPI_FWD) {
@@ -580,8 +580,7 @@ int conv_halo_plan(int epi, int dtype, ConvGemmParams& p) {
     p.e_stage_bytes = (g + kTilePixels * 16 * esize + 1023) & ~1023;
     p.c_ring = 3;
   } else if (epi == EPI_BWD) {
-    p.e_off_c = gate_bytes;
-    p.e_off_c2 = p.e_off_c + kEpiBoxBytes16;
+    p.e_off_c = p.e_off_c2 = gate_bytes;
     p.e_off_dc = p.e_off_c2 + kEpiBoxBytes16;
     p.e_off_h = 0;
     p.e_stage_bytes = p.e_off_dc + kEpiBoxBytes16;

@@ -418,13 +418,13 @@ __device__ __forceinline__ void epi_loader(const ConvGemmParams& p, uint8_t* sE,
               mbar_arrive(bar);   // zero state: nothing to read, the stage is only an output buffer
             }
           } else {
-            const uint32_t bytes = GE::kGateBytes + kEpiBoxBytes16 * (1 + (p.slot_c_prev >= 0) + (p.has_dc_in != 0));
+            const uint32_t bytes = GE::kGateBytes + kEpiBoxBytes16 * ((p.slot_c_prev >= 0) + (p.has_dc_in != 0));
             mbar_arrive_expect_tx(bar, bytes);
             const int q0 = group_q0(grp * 16);
 #pragma unroll
             for (int bx = 0; bx < GE::kGateBoxes; ++bx)
               tma_load_5d(st + bx * GE::kGateBoxBytes, &p.tm_g, bar, q0 + bx * GE::kGateBoxCols, c.x0, c.y0, c.b, p.slot_g);
-            tma_load_5d(st + p.e_off_c, &p.tm_c, bar, grp * 16, c.x0, c.y0, c.b, p.slot_c_cur);
+            // c_t is not read back: it is c_{t-1} f + i g of the values loaded here (model.py:228)
             if (p.slot_c_prev >= 0)
               tma_load_5d(st + p.e_off_c2, &p.tm_c, bar, grp * 16, c.x0, c.y0, c.b, p.slot_c_prev);
             if (p.has_dc_in) tma_load_5d(st + p.e_off_dc, &p.tm_dc, bar, grp * 16, c.x0, c.y0, c.b, 0);
@@ -591,7 +591,7 @@ __device__ __forceinline__ void epi_math(const ConvGemmParams& p, int warp, int 
           }
         } else {
           // gate backward; accumulator column c = dh_t[c] from the dgrad conv
-          float gi_[8], gf[8], gg[8], go[8], ct[8], cp[8], dc[8], dh[8];
+          float gi_[8], gf[8], gg[8], go[8], cp[8], dc[8], dh[8];
           const int c0 = grp * 16 + half * 8;
           if (p.nseg > 0) {
             tmem_ld8(taddr + c0, dh);
@@ -604,7 +604,6 @@ __device__ __forceinline__ void epi_math(const ConvGemmParams& p, int warp, int 
             lds_gate<E>(st, row, 1, half, gf);
             lds_gate<E>(st, row, 2, half, gg);
             lds_gate<E>(st, row, 3, half, go);
-            lds8<float, 64>(st + p.e_off_c, row, half, ct);
             if (p.slot_c_prev >= 0) {
               lds8<float, 64>(st + p.e_off_c2, row, half, cp);
             } else {
@@ -631,7 +630,7 @@ __device__ __forceinline__ void epi_math(const ConvGemmParams& p, int warp, int 
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const float dhv = fmaf(dpred, hw[j], dh[j]);
-              const float tc = act_tanh<FAST>(ct[j]);
+              const float tc = act_tanh<FAST>(fmaf(cp[j], gf[j], gi_[j] * gg[j]));   // tanh(c_t), the forward's expression
               const float d_o = dhv * tc;
               const float dcv = fmaf(dhv * go[j], 1.f - tc * tc, dc[j]);
               const float d_i = dcv * gg[j];

@@ -52,7 +52,7 @@ struct alignas(64) ConvGemmParams {
   // c history (fp32), h history (E), saved gates (E, q-order) and running dc (fp32); slot < 0 = absent
   CUtensorMap tm_c, tm_h, tm_g, tm_dc;
   int slot_c_in, slot_c_out, slot_h_out, slot_g;   // FWD: c_{t-1}, c_t, h_t, gates_t;  BWD: slot_g = gates_t / dgates_t
-  int slot_c_cur, slot_c_prev, has_dc_in;          // BWD: c_t, c_{t-1}, dc_t present
+  int slot_c_prev, has_dc_in;                      // BWD: c_{t-1}, dc_t present (c_t is recomputed from c_{t-1} and the gates)
   int e_stages, e_stage_bytes, e_off_c, e_off_c2, e_off_dc, e_off_h;
   int c_ring;               // forward: slots of the separate c_{t-1} -> c_t ring (0 for the backward kernel)
   uint32_t idesc;
@@ -142,8 +142,9 @@ cudaError_t launch_unpack_wgrad(const float* dw_acc, const float* db_acc, float*
                                 int k, int ncols, int cx_pad, int bias_col, int accumulate, cudaStream_t s);
 
 // preprocessing fusion: stack levels + emission, z-score, cyclic-longitude / reflect-latitude halo
-cudaError_t launch_fuse_inputs(const float* lev, const float* emis, const float* mean, const float* stdv, float* out,
-                               long long N, int L, int H, int W, int Hp, int Wp, int mode, cudaStream_t s);
+cudaError_t launch_fuse_inputs(const float* lev, const float* emis, const float* mean, const float* stdv,
+                               const float* statics, int S, float* out, long long N, int L, int H, int W, int Hp, int Wp,
+                               int mode, cudaStream_t s);
 // fused training loss MSE + L1 on the cropped prediction (value + gradient); stats = 5 floats of scratch
 cudaError_t launch_loss_mse_l1(const float* pred, const float* y, float* dpred, float* stats, float* loss, int B, int H,
                                int W, int y0, int y1, int x0, int x1, cudaStream_t s);

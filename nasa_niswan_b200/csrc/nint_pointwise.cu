@@ -413,15 +413,17 @@ cudaError_t launch_unpack_wgrad(const float* dw_acc, const float* db_acc, float*
 // ------------------------------------------------------------------------------------------
 // preprocessing fusion (north-star item 4; dataset.py:520-537 stack + z-score, dataset.py:67-98 halo): stack the
 // first L levels of a 3-D forcing [N,L,H,W] with a 2-D emission field [N,H,W] as channel L, z-score per channel,
-// cyclic halo in longitude, reflect halo in latitude -> [N,L+1,Hp,Wp] fp32.  mode 1 reproduces the shipped RNN
+// append S pre-normalised static attribute fields [S,H,W] (dataset.py:100-122,532-533: the same for every frame),
+// cyclic halo in longitude, reflect halo in latitude -> [N,L+1+S,Hp,Wp] fp32.  mode 1 reproduces the shipped RNN
 // dataset's quirk (np.fliplr on a (T,C,rows,W) slab flips CHANNELS: halo rows keep their order, channel order is
 // reversed; dataset.py:96).  One thread per output element, coalesced along longitude; HBM-bound.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) fuse_inputs_kernel(const float* __restrict__ lev, const float* __restrict__ emis,
                                                           const float* __restrict__ mean, const float* __restrict__ stdv,
+                                                          const float* __restrict__ statics, int S,
                                                           float* __restrict__ out, long long N, int L, int H, int W, int Hp,
                                                           int Wp, int mode) {
-  const int C = L + 1;
+  const int C = L + 1 + S;
   const int left = (Wp - W) / 2, top = (Hp - H) / 2, bot = Hp - H - top;
   const long long total = N * C * Hp * Wp;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -442,13 +444,18 @@ __global__ void __launch_bounds__(256) fuse_inputs_kernel(const float* __restric
       const int j = ys - H;
       if (mode == 0) ys = H - 2 - j; else { ys = H - bot - 1 + j; cs = C - 1 - c; }
     }
+    if (cs > L) {                             // static attributes: already z-scored, the same for every frame
+      out[i] = statics[(static_cast<long long>(cs - L - 1) * H + ys) * W + xs];
+      continue;
+    }
     const float v = cs < L ? lev[((n * L + cs) * H + ys) * W + xs] : emis[(n * H + ys) * W + xs];
     out[i] = (v - mean[cs]) / stdv[cs];       // IEEE subtract / divide: bit-identical to the numpy float32 pipeline
   }
 }
-cudaError_t launch_fuse_inputs(const float* lev, const float* emis, const float* mean, const float* stdv, float* out,
-                               long long N, int L, int H, int W, int Hp, int Wp, int mode, cudaStream_t s) {
-  fuse_inputs_kernel<<<148 * 8, 256, 0, s>>>(lev, emis, mean, stdv, out, N, L, H, W, Hp, Wp, mode);
+cudaError_t launch_fuse_inputs(const float* lev, const float* emis, const float* mean, const float* stdv,
+                               const float* statics, int S, float* out, long long N, int L, int H, int W, int Hp, int Wp,
+                               int mode, cudaStream_t s) {
+  fuse_inputs_kernel<<<148 * 8, 256, 0, s>>>(lev, emis, mean, stdv, statics, S, out, N, L, H, W, Hp, Wp, mode);
   return cudaGetLastError();
 }
 

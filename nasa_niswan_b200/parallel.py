@@ -161,13 +161,46 @@ class NativeAdam:
         self.betas, self.eps = (float(g["betas"][0]), float(g["betas"][1])), float(g["eps"])
 
 
+class StepLR:
+    """torch.optim.lr_scheduler.StepLR(optimizer, step_size, gamma) (train.py:72) for any optimizer that exposes
+    `param_groups` -- torch's own class insists on a torch.optim.Optimizer, which NativeAdam is not.  Stepped once per
+    epoch (train.py:120): lr = initial_lr * gamma ** (epoch // step_size)."""
+
+    def __init__(self, optimizer, step_size, gamma=0.1):
+        self.optimizer, self.step_size, self.gamma = optimizer, int(step_size), float(gamma)
+        if self.step_size < 1:
+            raise ValueError("step_size must be a positive integer")
+        self.base_lrs = [float(g.setdefault("initial_lr", g["lr"])) for g in optimizer.param_groups]
+        self.last_epoch = 0
+        self._last_lr = [float(g["lr"]) for g in optimizer.param_groups]
+
+    def step(self):
+        self.last_epoch += 1
+        for g, base in zip(self.optimizer.param_groups, self.base_lrs):
+            g["lr"] = base * self.gamma ** (self.last_epoch // self.step_size)
+        self._last_lr = [float(g["lr"]) for g in self.optimizer.param_groups]
+
+    def get_last_lr(self):
+        return list(self._last_lr)
+
+    def state_dict(self):
+        return {"step_size": self.step_size, "gamma": self.gamma, "base_lrs": list(self.base_lrs),
+                "last_epoch": self.last_epoch, "_last_lr": list(self._last_lr)}
+
+    def load_state_dict(self, sd):
+        self.step_size, self.gamma = int(sd["step_size"]), float(sd["gamma"])
+        self.base_lrs, self.last_epoch = [float(v) for v in sd["base_lrs"]], int(sd["last_epoch"])
+        self._last_lr = [float(v) for v in sd["_last_lr"]]
+
+
 class Trainer:
     """`native=True` (default on CUDA): the whole step stays in libnint kernels -- forward, fused MSE+L1 loss with its
     gradient (nint_loss_mse_l1), BPTT writing straight into the flat all-reduce buffer, one Adam kernel -- with no
     autograd graph and ~25 fewer small launches per step.  `native=False` keeps torch's loss / autograd / fused Adam
     around the same ConvLSTM kernels (identical numerics up to summation order)."""
 
-    def __init__(self, model, lr: float = 1e-3, betas=(0.5, 0.999), crop=None, process_group=None, native=None):
+    def __init__(self, model, lr: float = 1e-3, betas=(0.5, 0.999), crop=None, process_group=None, native=None,
+                 scheduler_config=None):
         self.model, self.crop, self.group = model, crop, process_group
         self.grads = FlatGradients(model.parameters(), process_group)
         on_cuda = next(model.parameters()).is_cuda
@@ -178,7 +211,17 @@ class Trainer:
             self._stats = torch.zeros(8, dtype=torch.float32, device=self.grads.flat.device)
         else:
             self.optimizer = torch.optim.Adam(self.grads.params, lr=lr, betas=betas, fused=on_cuda)   # train.py:71
+        # train.py:72 / launcher.sh:27: `--scheduler-config STEP GAMMA`, stepped once per epoch by `end_epoch`
+        self.scheduler = None if scheduler_config is None else StepLR(self.optimizer, int(scheduler_config[0]),
+                                                                      float(scheduler_config[1]))
         self.broadcast_parameters(process_group)
+
+    def end_epoch(self):
+        """train.py:120: `scheduler.step()` after the last batch of an epoch; returns the learning rate(s) now in force."""
+        if self.scheduler is not None:
+            self.scheduler.step()
+            return self.scheduler.get_last_lr()
+        return [float(g["lr"]) for g in self.optimizer.param_groups]
 
     def broadcast_parameters(self, group=None):
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:

@@ -75,3 +75,28 @@ def val_loop(dataloader, model, crop: Optional[Tuple[int, int, int, int]] = (5, 
             r2 += r2_score_device(pred, y, crop)
             n += 1
     return r2 / max(n, 1)
+
+
+def sensitivity_sweep(dataloader, model, num_features: int, perturbation: float = 0.05,
+                      crop: Optional[Tuple[int, int, int, int]] = (5, 95, 5, 149), y_mean: float = 0.0,
+                      y_std: float = 1.0) -> torch.Tensor:
+    """One-at-a-time input sensitivity (test.ipynb:2430-2462): for every feature i, predictions with channel i of the
+    whole window scaled by (1 + perturbation), cropped and de-normalised -> [num_features, N, Hc, Wc] on the host.
+
+    The notebook walks the dataloader once per feature and uploads every batch again each time; here a batch is
+    uploaded once, the perturbation is applied and undone on the device, and only the cropped predictions come back."""
+    model.eval()
+    chunks = [[] for _ in range(num_features)]
+    with torch.no_grad():
+        for X, _ in dataloader:
+            X = X.cuda(non_blocking=True)
+            for i in range(num_features):
+                saved = X[:, :, i].clone()
+                X[:, :, i] *= (1 + perturbation)
+                out = model(X)
+                pred = out[0] if isinstance(out, tuple) else out
+                if crop is not None:
+                    pred = pred[:, :, crop[0]:crop[1], crop[2]:crop[3]]
+                chunks[i].append((pred[:, 0] * y_std + y_mean).cpu())
+                X[:, :, i] = saved
+    return torch.stack([torch.cat(c, dim=0) for c in chunks], dim=0)

@@ -253,8 +253,15 @@ def halo_pad(data: np.ndarray, target_hw: Tuple[int, int], mode: str = "reflect"
     return reflect_pad_lat(cyclic_pad_lon(data, target_hw[1]), target_hw[0], mode)
 
 
+def normalise_static_attributes(fields: np.ndarray) -> np.ndarray:
+    """dataset.py:109-116: per-field spatial z-score of the static attributes [S,H,W]."""
+    S = np.asarray(fields)
+    return (S - S.mean(axis=(1, 2)).reshape(-1, 1, 1)) / S.std(axis=(1, 2)).reshape(-1, 1, 1)
+
+
 def fuse_inputs(levels3d: np.ndarray, emis2d: np.ndarray, mean: np.ndarray, std: np.ndarray,
-                target_hw: Optional[Tuple[int, int]] = None, mode: str = "reflect") -> np.ndarray:
+                target_hw: Optional[Tuple[int, int]] = None, mode: str = "reflect",
+                statics: Optional[np.ndarray] = None) -> np.ndarray:
     """Preprocessing fusion: stack ``levels3d`` [T,L,H,W] (first L model levels of
     the 3-D forcings) with the 2-D emission field ``emis2d`` [T,H,W] as channel L,
     z-score per channel, then halo-pad.  Follows the shipped single-level code
@@ -263,6 +270,9 @@ def fuse_inputs(levels3d: np.ndarray, emis2d: np.ndarray, mean: np.ndarray, std:
     (discrepancy 2)."""
     X = np.concatenate([levels3d, emis2d[:, None]], axis=1).astype(np.float32)
     X = (X - mean.reshape(1, -1, 1, 1).astype(np.float32)) / std.reshape(1, -1, 1, 1).astype(np.float32)
+    if statics is not None:   # dataset.py:118-122, 532-533: normalised static fields repeated over the sequence
+        rep = np.repeat(np.expand_dims(statics.astype(np.float32), 0), repeats=X.shape[0], axis=0)
+        X = np.concatenate((X, rep), axis=1)
     if target_hw is not None:
         X = halo_pad(X, target_hw, mode)
     return X.astype(np.float32)

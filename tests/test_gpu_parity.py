@@ -307,6 +307,28 @@ def test_fuse_inputs_matches_oracle(shape, mode):
     assert np.array_equal(got.cpu().numpy(), ref)
 
 
+@pytest.mark.parametrize("mode", ["reflect", "reference_rnn"])
+def test_fuse_inputs_with_static_attributes(mode):
+    """dataset.py:100-122, 532-533: z-scored static fields appended to every frame before the halo (so the shipped
+    dataset's channel flip in the latitude halo runs over dynamic AND static channels): bit-exact"""
+    from nasa_niswan_b200.preprocess import fuse_inputs, normalise_static_attributes
+    T, L, S, H, W, Hp, Wp = 3, 4, 3, 18, 24, 24, 32
+    rng = np.random.default_rng(19)
+    lev = rng.standard_normal((T, L, H, W)).astype(np.float32)
+    em = np.abs(rng.standard_normal((T, H, W))).astype(np.float32)
+    mean = rng.standard_normal(L + 1).astype(np.float32)
+    std = (np.abs(rng.standard_normal(L + 1)) + 0.5).astype(np.float32)
+    raw = (rng.standard_normal((S, H, W)) * 40 + 100).astype(np.float32)
+    st = O.normalise_static_attributes(raw).astype(np.float32)
+    ref = O.fuse_inputs(lev, em, mean, std, (Hp, Wp), mode, statics=st)
+    got = fuse_inputs(*(torch.from_numpy(a).cuda() for a in (lev, em, mean, std)), (Hp, Wp), mode,
+                      statics=torch.from_numpy(st).cuda())
+    assert got.shape == ref.shape == (T, L + 1 + S, Hp, Wp)
+    assert np.array_equal(got.cpu().numpy(), ref)
+    dev = normalise_static_attributes(torch.from_numpy(raw).cuda()).cpu().numpy()
+    assert np.allclose(dev, st, rtol=1e-5, atol=1e-5)
+
+
 def test_fuse_inputs_rejects_oversized_halo():
     from nasa_niswan_b200.preprocess import fuse_inputs
     z = torch.zeros(1, 1, 4, 4, device="cuda")
@@ -329,6 +351,50 @@ def test_val_loop_r2_matches_sklearn():
             pred = net(X.cuda())[:, :, 5:95, 5:149].squeeze()
             ref += r2_score(y.numpy().flatten(), pred.cpu().numpy().flatten())
     assert abs(got - ref / len(data)) < 1e-4
+
+
+def test_sensitivity_sweep_matches_notebook_loop():
+    """test.ipynb:2430-2462: one-at-a-time +5 % perturbation of every input feature, cropped, de-normalised"""
+    from nasa_niswan_b200 import ConvLSTM
+    from nasa_niswan_b200.utils import sensitivity_sweep
+    torch.manual_seed(12)
+    net = ConvLSTM(5, [16], [3], 1, precision="tf32").cuda()
+    data = [(torch.randn(2, 3, 5, 100, 154), torch.randn(2, 90, 144)) for _ in range(2)]
+    got = sensitivity_sweep(data, net, num_features=5, perturbation=0.05, y_mean=2.0, y_std=3.0)
+    assert got.shape == (5, 4, 90, 144)
+    net.eval()
+    with torch.no_grad():
+        for i in range(5):
+            k = 0
+            for X, _ in data:
+                Xp = X.clone()
+                Xp[:, :, i] *= 1.05
+                p = net(Xp.cuda())[:, :, 5:95, 5:149].squeeze(1).cpu() * 3.0 + 2.0
+                assert torch.allclose(got[i, k:k + 2], p, rtol=1e-5, atol=1e-5)
+                k += 2
+    for X, _ in data:          # borrowed inputs are left as they were
+        assert X.is_cpu
+
+
+def test_trainer_step_lr_schedule():
+    """train.py:72,120: StepLR stepped per epoch changes the learning rate the native Adam kernel uses"""
+    from nasa_niswan_b200 import ConvLSTM
+    from nasa_niswan_b200.parallel import Trainer
+    torch.manual_seed(13)
+    x, y = torch.randn(2, 2, 5, 20, 24, device="cuda"), torch.randn(2, 20, 24, device="cuda")
+    net = ConvLSTM(5, [16], [3], 1, precision="tf32").cuda()
+    ref = ConvLSTM(5, [16], [3], 1, precision="tf32").cuda()
+    ref.load_state_dict(net.state_dict())
+    tr = Trainer(net, lr=1e-2, betas=(0.5, 0.999), native=True, scheduler_config=(1, 0.5))
+    tr_ref = Trainer(ref, lr=1e-2, betas=(0.5, 0.999), native=False)
+    sched = torch.optim.lr_scheduler.StepLR(tr_ref.optimizer, step_size=1, gamma=0.5)
+    for epoch in range(3):
+        tr.step(x, y)
+        tr_ref.step(x, y)
+        sched.step()
+        assert abs(tr.end_epoch()[0] - sched.get_last_lr()[0]) < 1e-12
+    for (n, a), (_, b) in zip(net.state_dict().items(), ref.state_dict().items()):
+        assert torch.allclose(a, b, rtol=2e-3, atol=2e-5), n
 
 
 def test_checkpoint_moves_between_native_and_torch_adam(tmp_path):

@@ -81,3 +81,31 @@ def test_flat_gradients_are_views():
     assert all(p.grad.data_ptr() >= fg.flat.data_ptr() for p in m.parameters())
     fg.zero()
     assert all(float(p.grad.abs().sum()) == 0 for p in m.parameters())
+
+
+def test_step_lr_matches_torch_scheduler():
+    """parallel.StepLR follows torch.optim.lr_scheduler.StepLR (train.py:72,120; launcher.sh:27 `10 0.9`) epoch by epoch"""
+    import torch
+    from nasa_niswan_b200.parallel import StepLR
+
+    class Opt:   # the only thing a scheduler touches
+        def __init__(self, lr):
+            self.param_groups = [{"lr": lr}]
+
+    w = torch.nn.Parameter(torch.zeros(1))
+    ref_opt = torch.optim.Adam([w], lr=1e-3)
+    ref = torch.optim.lr_scheduler.StepLR(ref_opt, step_size=10, gamma=0.9)
+    mine_opt = Opt(1e-3)
+    mine = StepLR(mine_opt, 10, 0.9)
+    assert mine.get_last_lr() == ref.get_last_lr()
+    for _ in range(35):
+        ref_opt.step()
+        ref.step()
+        mine.step()
+        assert abs(mine.get_last_lr()[0] - ref.get_last_lr()[0]) < 1e-15
+        assert mine_opt.param_groups[0]["lr"] == mine.get_last_lr()[0]
+    resumed = StepLR(Opt(1e-3), 10, 0.9)
+    resumed.load_state_dict(mine.state_dict())
+    resumed.step()
+    mine.step()
+    assert resumed.get_last_lr() == mine.get_last_lr()
