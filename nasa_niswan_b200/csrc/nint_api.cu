@@ -478,6 +478,17 @@ int nint_plan_create(const nint_config* cfg, nint_plan** out) {
       delete p;
       return fail("layer %d: padded input+hidden channels %d > 256 not supported by wgrad", l, y.ncols);
     }
+    if (cfg->training && !(p->cluster == 2 && wgrad_pair_supported(p->dtype, 4 * y.hc, y.ncols, y.k))) {
+      // single-CTA wgrad kernel: one stage holds a halo panel per 32 input+hidden channels next to the dgates panels
+      int a_bufs = 0, b_stages = 0;
+      wgrad_pick_buffers(p->dtype, y.ncols / 32, wgrad_b_panel_bytes(p->dtype, 1, y.k), &a_bufs, &b_stages);
+      if (b_stages < 1) {
+        const int hc = y.hc, k = y.k, nc = y.ncols;
+        delete p;
+        return fail("layer %d: training with hidden %d, kernel %d in this precision needs %d-channel wgrad operand panels "
+                    "that do not fit in shared memory", l, hc, k, nc);
+      }
+    }
     cin = y.hc;
   }
   // (layer l >= 1 reads the h tensor of layer l-1 as its x segment: ceil(hc_{l-1}/ce) chunks on both sides)

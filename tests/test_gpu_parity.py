@@ -151,6 +151,42 @@ def test_plans_against_oracle(cfg, precision):
         assert O.max_abs_normalised(p.grad.cpu(), leaf[k].grad) < TOL[precision], k
 
 
+@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+@pytest.mark.parametrize("cfg", [
+    (1, 1, 32, 8, 16, [64], [3]),            # one sample, one step, one exact tile; cin = 32: no spare channel -> ones-panel bias MMA at layer 0
+    (2, 2, 40, 9, 17, [64], [3]),            # cin = 40 -> two x chunks, ones channel 40 in the second; grid one pixel past the tile in x and y
+    (1, 2, 3, 12, 20, [192], [3]),           # widest hidden size whose padded input+hidden channels fit one wgrad MMA (N <= 256)
+    (1, 2, 4, 10, 12, [16], [7]),            # 7x7 taps on a grid barely larger than the kernel
+    (5, 2, 21, 8, 16, [64], [1]),            # 1x1 "convolution": no halo at all
+], ids=["b1_t1_c32", "c40_ragged", "h192", "k7", "k1"])
+def test_edge_geometries_against_oracle(cfg, precision):
+    """forward + BPTT against the CPU oracle at the edges of the supported geometry.  tf32 tolerance here is 2e-3:
+    dgates are rounded to tf32 (2^-11) before the wgrad MMAs, and with only 128..400 pixel-steps a gradient is a
+    short sum of signed terms, so that rounding is not averaged away as in the 12-step rollout (1e-3 there)."""
+    from nasa_niswan_b200 import ConvLSTM
+    B, T, C, H, W, hidden, ks = cfg
+    tol = {"tf32": 2e-3, "bf16": TOL["bf16"]}[precision]
+    torch.manual_seed(5)
+    net = ConvLSTM(C, hidden, ks, len(hidden), precision=precision)
+    if precision == "tf32" and hidden == [192]:
+        # fp32 operand panels for 32+192 channels do not fit in shared memory: refused when the plan is made
+        with pytest.raises(RuntimeError, match="do not fit in shared memory"):
+            net.cuda()(torch.randn(B, T, C, H, W, device="cuda"))
+        return
+    params = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    net = net.cuda()
+    x, y = torch.randn(B, T, C, H, W), torch.randn(B, H, W)
+    leaf = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    ref_pred = O.convlstm_forward(x, leaf, len(hidden))
+    dpred = torch.autograd.grad(O.training_loss(ref_pred, y), ref_pred, retain_graph=True)[0]
+    ref_pred.backward(dpred)
+    pred = net(x.cuda())
+    assert O.max_abs_normalised(pred.detach().cpu(), ref_pred.detach()) < tol
+    pred.backward(dpred.cuda())
+    for k, p in net.named_parameters():
+        assert O.max_abs_normalised(p.grad.cpu(), leaf[k].grad) < tol, k
+
+
 def test_long_inference_rollout_keeps_state_resident():
     """BASELINE cfg 4 in miniature: forward-only T = 40 rollout (2-slot h ring, c updated in place) vs the oracle"""
     from nasa_niswan_b200 import ConvLSTM
