@@ -83,6 +83,7 @@ struct Layer {
   CUtensorMap tmw_H_up;      // Hs[l] as the x part of layer l+1's wgrad (halo of k_{l+1})
   CUtensorMap tmp_G, tmp_H, tmp_H_up;        // CTA-pair wgrad views: 64-q dgates boxes (SWIZZLE_128B), 16-channel halo boxes (SWIZZLE_32B)
   bool wgrad_pair = false;
+  int wg_pw = 16;            // pair wgrad: channels per B panel
   CUtensorMap tme_C, tme_H, tme_G, tme_dC;  // epilogue I/O boxes (16 | 64 channels x 8 x 16 pixels; nint_epilogue.cuh)
   bool weights_set = false;
 };
@@ -478,7 +479,7 @@ int nint_plan_create(const nint_config* cfg, nint_plan** out) {
       delete p;
       return fail("layer %d: padded input+hidden channels %d > 256 not supported by wgrad", l, y.ncols);
     }
-    if (cfg->training && !(p->cluster == 2 && wgrad_pair_supported(p->dtype, 4 * y.hc, y.ncols, y.k))) {
+    if (cfg->training && !(p->cluster == 2 && wgrad_pair_supported(p->dtype, 4 * y.hc, y.cx_pad, y.ncols, y.k))) {
       // single-CTA wgrad kernel: one stage holds a halo panel per 32 input+hidden channels next to the dgates panels
       int a_bufs = 0, b_stages = 0;
       wgrad_pick_buffers(p->dtype, y.ncols / 32, wgrad_b_panel_bytes(p->dtype, 1, y.k), &a_bufs, &b_stages);
@@ -549,15 +550,18 @@ int nint_plan_bind(nint_plan* p, void* workspace, size_t bytes, void* stream) {
   if (p->cfg.training) {
     for (int l = 0; l < p->L; ++l) {
       Layer& y = p->layer[l];
-      y.wgrad_pair = p->cluster == 2 && wgrad_pair_supported(p->dtype, 4 * y.hc, y.ncols, y.k) != 0;
+      y.wgrad_pair = p->cluster == 2 && wgrad_pair_supported(p->dtype, 4 * y.hc, y.cx_pad, y.ncols, y.k) != 0;
       if (!y.wgrad_pair) continue;
+      y.wg_pw = wgrad_pair_panel_width(y.cx_pad, y.ncols);
+      const CUtensorMapSwizzle sw = y.wg_pw == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                                  : (y.wg_pw == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
       if (encode_act_box(&y.tmp_G, p->dtype, y.G, 4 * y.hc, p->W, p->H, p->B, p->T, 64, tw, th, 0, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
-      if (encode_act_box(&y.tmp_H, p->dtype, y.Hs, y.hc_pad, p->W, p->H, p->B, y.nslots_h, 16, tw, th, pad_of(l), CU_TENSOR_MAP_SWIZZLE_32B)) return 1;
+      if (encode_act_box(&y.tmp_H, p->dtype, y.Hs, y.hc_pad, p->W, p->H, p->B, y.nslots_h, y.wg_pw, tw, th, pad_of(l), sw)) return 1;
       if (l == 0) {
-        if (encode_act_box(&p->tmp_X, p->dtype, p->X, y.cx_pad, p->W, p->H, p->B, p->T, 16, tw, th, pad_of(0), CU_TENSOR_MAP_SWIZZLE_32B)) return 1;
+        if (encode_act_box(&p->tmp_X, p->dtype, p->X, y.cx_pad, p->W, p->H, p->B, p->T, y.wg_pw, tw, th, pad_of(0), sw)) return 1;
       } else {
         Layer& dn = p->layer[l - 1];
-        if (encode_act_box(&dn.tmp_H_up, p->dtype, dn.Hs, dn.hc_pad, p->W, p->H, p->B, dn.nslots_h, 16, tw, th, pad_of(l), CU_TENSOR_MAP_SWIZZLE_32B)) return 1;
+        if (encode_act_box(&dn.tmp_H_up, p->dtype, dn.Hs, dn.hc_pad, p->W, p->H, p->B, dn.nslots_h, y.wg_pw, tw, th, pad_of(l), sw)) return 1;
       }
     }
   }
@@ -881,7 +885,13 @@ int nint_backward(nint_plan* p, const float* dpred, const float* dseq, float* co
         w.group_unit0[g + 1] = w.group_unit0[g] + w.m_blocks * w.group_splits[g];
       }
     }
-    wgrad_pick_buffers(p->dtype, y.ncols / 32, w.b_panel_bytes, &w.a_bufs, &w.b_stages);
+    if (w.pair) {
+      w.b_pw = y.wg_pw;
+      w.a_bufs = 3;
+      w.b_stages = wgrad_pair_b_stages(y.cx_pad, y.ncols, y.k);
+    } else {
+      wgrad_pick_buffers(p->dtype, y.ncols / 32, w.b_panel_bytes, &w.a_bufs, &w.b_stages);
+    }
     if (w.b_stages < 1) return fail("wgrad: operand panels do not fit in shared memory");
     w.idesc = idesc_of(p->dtype, w.pair ? 256 : 128, y.ncols, 1, 1);
     w.idesc_bias = idesc_of(p->dtype, w.pair ? 256 : 128, 32, 1, 1);

@@ -102,7 +102,8 @@ struct alignas(64) WgradParams {
   int b_panel_bytes;      // bytes between consecutive B panels of a stage
   int debug_flags;        // experiments: 2 = no MMA issue, 4 = issue every MMA twice
   int pair;               // 1: CTA-pair kernel (bf16, 4*hc % 256 == 0): m_blocks counts 256-q blocks, tmap_dg has 64-q
-                          // boxes (SWIZZLE_128B) and tmap_b 16-channel halo boxes (SWIZZLE_32B)
+                          // boxes (SWIZZLE_128B) and tmap_b b_pw-channel halo boxes (SWIZZLE_32B / 64B / 128B)
+  int b_pw;               // pair kernel: channels per B panel (16 / 32 / 64)
   uint32_t idesc, idesc_bias;
   int hc4;                // 4*hc
   float* dw_acc;          // [taps][4*hc][ncols] fp32, atomically accumulated (pre-zeroed)
@@ -111,7 +112,9 @@ struct alignas(64) WgradParams {
 int wgrad_b_panel_bytes(int dtype, int halo, int ksize);
 int wgrad_smem_bytes(int dtype, int bpanels, int a_bufs, int b_stages, int b_panel_bytes);
 void wgrad_pick_buffers(int dtype, int bpanels, int b_panel_bytes, int* a_bufs, int* b_stages);
-int wgrad_pair_supported(int dtype, int hc4, int ncols, int ksize);
+int wgrad_pair_supported(int dtype, int hc4, int cx_pad, int ncols, int ksize);
+int wgrad_pair_panel_width(int cx_pad, int ncols);          // channels per B panel of the pair kernel: 16 / 32 / 64
+int wgrad_pair_b_stages(int cx_pad, int ncols, int ksize);  // B stages that fit (0: pair kernel not possible)
 cudaError_t launch_wgrad(int dtype, const WgradParams& p, cudaStream_t stream);
 
 // ---- pointwise / layout kernels (nint_pointwise.cu)

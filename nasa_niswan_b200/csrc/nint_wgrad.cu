@@ -324,22 +324,37 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
 // (128 per CTA) at the tensor pipe's nominal rate; the single-CTA M=128 MMA above needs ~100 cycles for the
 // N=96 shape whose floor is 48 (tools/micro/mma_rate.cu).  Operands per pixel tile and CTA:
 //   A  dgates  [128 px][128 q]  as 2 panels of 64 q   (128-byte rows, SWIZZLE_128B, MN-major)
-//   B  comb    [halo px][N/2 channels] as 16-channel panels (32-byte rows, SWIZZLE_32B, MN-major): the pair MMA
-//      splits N between the CTAs, and N/2 = 48 is not a multiple of the 32-channel panel of the 64B swizzle
+//   B  comb    [halo px][N/2 channels] as panels of `b_pw` = 16 / 32 / 64 channels (32 / 64 / 128-byte rows with the
+//      matching swizzle, MN-major): the pair MMA splits N between the CTAs, so the panel width is the largest that
+//      divides N/2 and the x / h boundary (N/2 = 48 at hidden 64 -> 16; 128 + 128 channels -> 64).  Wide panels
+//      matter: a TMA box row is one L2 request, and 16-channel rows are 32-byte requests.
 // Warps: 0 A producer, 3 / 2 B producers (every bulk-async instruction occupies its issuing warp for ~450-750
 // cycles; 2 also allocates TMEM), 1 / 8 MMA issuers (leader CTA, alternate tiles), 4-7 flush the accumulators with
 // fp32 atomics.
-constexpr int kWgPairBStages = 4;
+constexpr int kWgPairMaxBStages = 4;
 constexpr int kWgPairABufs = 3;   // the issuer awaits tile i+1 before issuing tile i: needs i-1, i, i+1 resident
 constexpr int kWgPairAPanel = kTilePixels * 128;   // 64 q x 128 px bf16 = 16 KiB
 constexpr int kWgPairThreads = 288;                // 9 warps: warp 8 is the second MMA issuer
 
-__host__ __device__ static inline int wgp_b_panel_bytes(int ksize) {
+__host__ __device__ static inline int wgp_b_panel_bytes(int ksize, int pw) {
   const int rows = (8 + (ksize & ~1)) * (16 + (ksize & ~1));
-  return (rows * 32 + 1023) & ~1023;
+  return (rows * pw * 2 + 1023) & ~1023;
 }
-static inline int wgp_smem_bytes(int bp_cta, int ksize) {
-  return 1024 + kWgPairABufs * 2 * kWgPairAPanel + kWgPairBStages * bp_cta * wgp_b_panel_bytes(ksize) + 1024 + kWgCtrlBytes;
+static inline int wgp_smem_bytes(int half_cols, int ksize, int pw, int b_stages) {
+  return 1024 + kWgPairABufs * 2 * kWgPairAPanel + b_stages * (half_cols / pw) * wgp_b_panel_bytes(ksize, pw) + 1024 + kWgCtrlBytes;
+}
+// widest B panel (channels) that tiles both CTAs' halves of N and does not straddle the x / h boundary
+int wgrad_pair_panel_width(int cx_pad, int ncols) {
+  for (int pw = 64; pw > 16; pw >>= 1)
+    if ((ncols / 2) % pw == 0 && cx_pad % pw == 0) return pw;
+  return 16;
+}
+// B stages that fit next to the three A buffers (0: the pair kernel cannot run this layer)
+int wgrad_pair_b_stages(int cx_pad, int ncols, int ksize) {
+  const int pw = wgrad_pair_panel_width(cx_pad, ncols);
+  for (int st = kWgPairMaxBStages; st >= 2; --st)
+    if (wgp_smem_bytes(ncols / 2, ksize, pw, st) <= 227 * 1024) return st;
+  return 0;
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kWgPairThreads, 1)
@@ -350,17 +365,20 @@ wgrad_pair_kernel(const __grid_constant__ WgradParams p) {
   const int lane = threadIdx.x & 31;
   const uint32_t crank = __shfl_sync(0xffffffffu, cluster_ctarank(), 0);
   const bool lead_cta = crank == 0;
-  const int bp_all = (p.nchunks_b[0] + p.nchunks_b[1]) * 2;   // 16-channel panels of the concatenated input
+  const int pw = p.b_pw;                                      // channels per B panel (16 / 32 / 64)
+  const int rowb = pw * 2;                                    // bytes per pixel row of a B panel
+  const int bp_all = (p.nchunks_b[0] + p.nchunks_b[1]) * 32 / pw;   // panels of the concatenated input
   const int bp_cta = bp_all / 2;                              // this CTA's half of N
-  const int bx16 = p.nchunks_b[0] * 2;                        // panels that come from the x tensor
-  const int b_panel = wgp_b_panel_bytes(p.ksize);
+  const int bx16 = p.nchunks_b[0] * 32 / pw;                  // panels that come from the x tensor
+  const int b_panel = wgp_b_panel_bytes(p.ksize, pw);
+  const int nbs = p.b_stages;
   const int a_buf_bytes = 2 * kWgPairAPanel;
   const int b_stage_bytes = bp_cta * b_panel;
   const int hpitch = 8 + (p.ksize & ~1);
   const int hrows = hpitch * (16 + (p.ksize & ~1));
   uint8_t* sA = smem;
   uint8_t* sB = sA + kWgPairABufs * a_buf_bytes;
-  uint8_t* sOnes = sB + kWgPairBStages * b_stage_bytes;
+  uint8_t* sOnes = sB + nbs * b_stage_bytes;
   uint8_t* ctrl = sOnes + 1024;
   uint64_t* a_full = reinterpret_cast<uint64_t*>(ctrl);
   uint64_t* a_empty = a_full + kWgMaxBufs;
@@ -461,18 +479,18 @@ wgrad_pair_kernel(const __grid_constant__ WgradParams p) {
       tile_coords(i, x0, y0, b, t);
       mbar_wait(&b_empty[bs], bph ^ 1);
       if (leader) {
-        if (lead_cta && jpar == 0) mbar_arrive_expect_tx(&b_full[bs], static_cast<uint32_t>(2 * bp_cta * hrows * 32));
+        if (lead_cta && jpar == 0) mbar_arrive_expect_tx(&b_full[bs], static_cast<uint32_t>(2 * bp_cta * hrows * rowb));
         const uint32_t bar = mapa_rank(smem_u32(&b_full[bs]), 0);
         uint8_t* dst = sB + bs * b_stage_bytes + jpar * b_panel;
         for (int j = jpar; j < bp_cta; j += 2, dst += 2 * b_panel) {
           const int pj = static_cast<int>(crank) * bp_cta + j;   // 16-channel panel of the concatenated input
           if (pj < bx16)
-            tma_load_5d_pair(dst, &p.tmap_b[0], bar, pj * 16, x0 - pad, y0 - pad, b, p.slot_b0[0] + t);
+            tma_load_5d_pair(dst, &p.tmap_b[0], bar, pj * pw, x0 - pad, y0 - pad, b, p.slot_b0[0] + t);
           else
-            tma_load_5d_pair(dst, &p.tmap_b[1], bar, (pj - bx16) * 16, x0 - pad, y0 - pad, b, p.slot_b0[1] + t);
+            tma_load_5d_pair(dst, &p.tmap_b[1], bar, (pj - bx16) * pw, x0 - pad, y0 - pad, b, p.slot_b0[1] + t);
         }
       }
-      if (++bs == kWgPairBStages) {
+      if (++bs == nbs) {
         bs = 0;
         bph ^= 1;
       }
@@ -490,25 +508,26 @@ wgrad_pair_kernel(const __grid_constant__ WgradParams p) {
       const int ksize = p.ksize;
       const bool issue_any = !(p.debug_flags & 2);
       // MN-major descriptors.  A: 64-q atoms (128-byte rows, SWIZZLE_128B) one panel apart, 8-pixel groups 1 KiB apart.
-      // B: 16-channel atoms (32-byte rows, SWIZZLE_32B) one panel apart, 8-pixel groups one halo row apart.
+      // B: pw-channel atoms (32 / 64 / 128-byte rows, matching swizzle) one panel apart, 8-pixel groups one halo row apart.
       const uint64_t adesc_base = make_smem_desc(0, kWgPairAPanel, 1024, 2);
-      const uint64_t bdesc_base = make_smem_desc(0, static_cast<uint32_t>(b_panel), static_cast<uint32_t>(hpitch * 32), 6);
+      const uint64_t bdesc_base = make_smem_desc(0, static_cast<uint32_t>(b_panel), static_cast<uint32_t>(hpitch * rowb),
+                                                 pw == 16 ? 6u : (pw == 32 ? 4u : 2u));
       const uint64_t odesc = make_smem_desc(smem_u32(sOnes), 512, 256, 6);
       const uint32_t ahi = static_cast<uint32_t>(adesc_base >> 32), bhi = static_cast<uint32_t>(bdesc_base >> 32);
       const uint32_t alo_base = static_cast<uint32_t>(adesc_base), blo_base = static_cast<uint32_t>(bdesc_base);
       const uint32_t sA16 = smem_u32(sA) >> 4, sB16 = smem_u32(sB) >> 4;
       const int dy0 = tap_begin / ksize, dx0 = tap_begin % ksize;
-      const uint32_t krow16 = static_cast<uint32_t>((2 * hpitch * 32) >> 4);   // one K step = two halo rows
+      const uint32_t krow16 = static_cast<uint32_t>((2 * hpitch * rowb) >> 4);   // one K step = two halo rows
       uint32_t tap_off[5];
 #pragma unroll
       for (int ti = 0; ti < 5; ++ti) {
         const int tp = tap_begin + (ti < ntaps ? ti : 0);
-        tap_off[ti] = static_cast<uint32_t>((((tp / ksize) * hpitch + tp % ksize) * 32) >> 4);
+        tap_off[ti] = static_cast<uint32_t>((((tp / ksize) * hpitch + tp % ksize) * rowb) >> 4);
       }
       int last_mine = -1;
       for (int i = which; i < my_tiles; i += 2) {
-        const int ab = i % kWgPairABufs, bs = i % kWgPairBStages;
-        const uint32_t aph = static_cast<uint32_t>(i / kWgPairABufs) & 1u, bph = static_cast<uint32_t>(i / kWgPairBStages) & 1u;
+        const int ab = i % kWgPairABufs, bs = i % nbs;
+        const uint32_t aph = static_cast<uint32_t>(i / kWgPairABufs) & 1u, bph = static_cast<uint32_t>(i / nbs) & 1u;
         mbar_wait(&a_full[ab], aph);
         mbar_wait(&b_full[bs], bph);
         spin_until_at_least(mma_issued, static_cast<uint32_t>(i));   // the other warp has issued all of tile i-1
@@ -541,16 +560,16 @@ wgrad_pair_kernel(const __grid_constant__ WgradParams p) {
 #pragma unroll 1
             for (int ks = 0; ks < 8; ++ks) {
               const uint32_t alo = a0 + static_cast<uint32_t>(ks * 128);
-              uint32_t blo = b0 + static_cast<uint32_t>((((2 * ks + dy0) * hpitch + dx0) * 32) >> 4);
+              uint32_t blo = b0 + static_cast<uint32_t>((((2 * ks + dy0) * hpitch + dx0) * rowb) >> 4);
               uint32_t d = tmem_base;
               int dx = dx0;
               for (int ti = 0; ti < ntaps; ++ti) {
                 umma_lohi<NINT_BF16, true>(d, alo, ahi, blo, bhi, idesc, acc);
                 d += ncols;
-                blo += 2;
+                blo += static_cast<uint32_t>(rowb >> 4);
                 if (++dx == ksize) {
                   dx = 0;
-                  blo += static_cast<uint32_t>(((hpitch - ksize) * 32) >> 4);
+                  blo += static_cast<uint32_t>(((hpitch - ksize) * rowb) >> 4);
                 }
               }
               if (do_bias)
@@ -604,13 +623,13 @@ wgrad_pair_kernel(const __grid_constant__ WgradParams p) {
   }
 }
 
-int wgrad_pair_supported(int dtype, int hc4, int ncols, int ksize) {
+int wgrad_pair_supported(int dtype, int hc4, int cx_pad, int ncols, int ksize) {
   if (dtype != NINT_BF16 || (hc4 % 256) != 0 || (ncols % 32) != 0) return 0;
-  return wgp_smem_bytes(ncols / 32, ksize) <= 227 * 1024;
+  return wgrad_pair_b_stages(cx_pad, ncols, ksize) >= 2;
 }
 
 static cudaError_t launch_wg_pair(const WgradParams& p, cudaStream_t stream) {
-  const int smem = wgp_smem_bytes(p.nchunks_b[0] + p.nchunks_b[1], p.ksize);
+  const int smem = wgp_smem_bytes((p.nchunks_b[0] + p.nchunks_b[1]) * 16, p.ksize, p.b_pw, p.b_stages);
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(wgrad_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

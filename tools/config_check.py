@@ -33,7 +33,13 @@ def train_cfg(name, B, T, C, H, W, hidden, ks, crop=None, n=3):
     y = torch.randn(B, yh, yw, device="cuda")
     l0 = float(tr.step(x, y))
     ms = timed(lambda: tr.step(x, y), n)
+    plan = net.plan_for(x, True)
+    plan.profile(True)
+    tr.step(x, y)
+    prof = plan.profile_read()
+    plan.profile(False)
     l1 = float(tr.step(x, y))
+    print("   per kernel class (ms, launches): " + ", ".join(f"{k} {v[0]:.2f}/{v[1]}" for k, v in prof.items()), flush=True)
     print(f"{name}: {ms:.2f} ms/step, {B / ms * 1e3:.0f} samples/s, loss {l0:.4f} -> {l1:.4f}, "
           f"peak mem {torch.cuda.max_memory_allocated() / 2**30:.1f} GiB", flush=True)
     del net, tr, x, y
