@@ -77,6 +77,13 @@ int nint_forward(nint_plan* plan, const float* x, float* pred, float* seq, void*
  * device pointers with the parameters' shapes; gradients are WRITTEN (not accumulated). */
 int nint_backward(nint_plan* plan, const float* dpred, const float* dseq, float* const* grad_weight,
                   float* const* grad_bias, float* grad_head_weight, float* grad_head_bias, void* stream);
+/* The same in two stages, so a data-parallel caller can all-reduce one layer's gradient bucket while the next
+ * layer's weight gradient is still being computed (train.py has no DDP):
+ * nint_backward_bptt = head gradients + the reverse-time loop (leaves dgates of every step in the workspace),
+ * nint_backward_wgrad = weight / bias gradient of ONE layer over all T steps; any layer order, each layer once. */
+int nint_backward_bptt(nint_plan* plan, const float* dpred, const float* dseq, float* grad_head_weight,
+                       float* grad_head_bias, void* stream);
+int nint_backward_wgrad(nint_plan* plan, int layer, float* grad_weight, float* grad_bias, void* stream);
 
 /* ---- preprocessing fusion (north-star item 4).  Stacks the first `levels` model
  * levels of a 3-D forcing levels3d [frames,levels,H,W] with the 2-D emission field emis2d [frames,H,W] as the last

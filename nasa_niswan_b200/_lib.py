@@ -10,7 +10,7 @@ DTYPE_BF16, DTYPE_TF32 = 0, 1
 EXPORTS = ["nint_version", "nint_last_error", "nint_plan_create", "nint_plan_destroy", "nint_plan_workspace_bytes",
            "nint_plan_bind", "nint_plan_set_weights", "nint_plan_set_head", "nint_plan_reset_state",
            "nint_plan_set_state", "nint_plan_get_state", "nint_forward", "nint_backward", "nint_debug_raw_gates",
-           "nint_gate_column", "nint_debug_read_trace", "nint_loss_mse_l1", "nint_adam_step", "nint_fuse_inputs", "nint_pick_tile", "nint_launch_count", "nint_plan_profile",
+           "nint_gate_column", "nint_debug_read_trace", "nint_backward_bptt", "nint_backward_wgrad", "nint_loss_mse_l1", "nint_adam_step", "nint_fuse_inputs", "nint_pick_tile", "nint_launch_count", "nint_plan_profile",
            "nint_plan_profile_read"]
 
 
@@ -48,6 +48,8 @@ def load():
     L.nint_plan_get_state.argtypes = [vp, ci, fp, fp, vp]
     L.nint_forward.argtypes = [vp, fp, fp, fp, vp]
     L.nint_backward.argtypes = [vp, fp, fp, ctypes.POINTER(vp), ctypes.POINTER(vp), fp, fp, vp]
+    L.nint_backward_bptt.argtypes = [vp, fp, fp, fp, fp, vp]
+    L.nint_backward_wgrad.argtypes = [vp, ci, fp, fp, vp]
     L.nint_debug_raw_gates.argtypes = [vp, fp, fp, vp]
     L.nint_launch_count.argtypes = [ci]
     L.nint_launch_count.restype = ctypes.c_longlong

@@ -104,6 +104,7 @@ struct nint_plan {
   bool head_set = false;
   bool zero_init = true;
   bool fwd_done = false;
+  bool bptt_done = false;   // dgates of the last forward are in place: nint_backward_wgrad may run
   int final_slot_h = 0, final_slot_c = 0;
   int cluster = 2;        // 2: CTA pairs (tcgen05 cta_group::2) where the layer geometry allows, 1: single CTAs
   int debug_flags = 0;
@@ -567,6 +568,7 @@ int nint_plan_bind(nint_plan* p, void* workspace, size_t bytes, void* stream) {
   }
   p->zero_init = true;
   p->fwd_done = false;
+  p->bptt_done = false;
   return 0;
 }
 
@@ -667,6 +669,7 @@ int nint_forward(nint_plan* p, const float* x, float* pred, float* seq, void* st
   LAUNCH(p, K_OTHER, st, launch_head_fwd(p->dtype, slot_ptr(p, top.Hs, p->final_slot_h, top.hc_pad), p->head_w, p->head_b, pred, HW, p->B,
                      top.hc, top.hc_pad, HW, st));  // model.py:274
   p->fwd_done = true;
+  p->bptt_done = false;
   return 0;
 }
 
@@ -725,15 +728,15 @@ int nint_debug_raw_gates(nint_plan* p, const float* x, float* out, void* stream)
   return cell_step(p, 0, 0, EPI_RAW, out, st);
 }
 
-int nint_backward(nint_plan* p, const float* dpred, const float* dseq, float* const* grad_weight,
-                  float* const* grad_bias, float* grad_head_weight, float* grad_head_bias, void* stream) {
+int nint_backward_bptt(nint_plan* p, const float* dpred, const float* dseq, float* grad_head_weight,
+                       float* grad_head_bias, void* stream) {
   if (check_ready(p)) return 1;
   if (!p->cfg.training) return fail("nint_backward needs a training plan");
   if (!p->fwd_done) return fail("nint_backward before nint_forward");
   if (!dpred && !dseq) return fail("nint_backward: no upstream gradient");
   if (dseq && !p->cfg.return_sequence) return fail("dseq requires return_sequence in the plan");
   if (dseq && dpred) return fail("pass either dpred or dseq (fold dpred into dseq[:, T-1])");
-  if (!grad_weight || !grad_bias) return fail("nint_backward: null gradient tables");
+  p->bptt_done = false;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long HW = static_cast<long long>(p->H) * p->W;
   const int L = p->L, T = p->T;
@@ -801,8 +804,19 @@ int nint_backward(nint_plan* p, const float* dpred, const float* dseq, float* co
       LAUNCH(p, K_BWD, st, launch_conv_halo(EPI_BWD, p->dtype, g, p->num_sms, st));
     }
   }
-  // ---- weight / bias gradients, batched over all T steps
-  for (int l = 0; l < L; ++l) {
+  p->bptt_done = true;
+  return 0;
+}
+
+// ---- weight / bias gradient of one layer, batched over all T steps (needs the dgates nint_backward_bptt left)
+int nint_backward_wgrad(nint_plan* p, int l, float* grad_weight_l, float* grad_bias_l, void* stream) {
+  if (check_ready(p)) return 1;
+  if (!p->cfg.training) return fail("nint_backward_wgrad needs a training plan");
+  if (!p->bptt_done) return fail("nint_backward_wgrad before nint_backward_bptt");
+  if (l < 0 || l >= p->L) return fail("layer %d out of range", l);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int T = p->T;
+  {
     Layer& y = p->layer[l];
     CK(cudaMemsetAsync(y.dw_acc, 0, y.dw_acc_bytes, st));
     CK(cudaMemsetAsync(y.db_acc, 0, 4 * y.hc * 4, st));
@@ -898,9 +912,18 @@ int nint_backward(nint_plan* p, const float* dpred, const float* dseq, float* co
     w.dw_acc = y.dw_acc;
     w.db_acc = y.db_acc;
     LAUNCH(p, K_WGRAD, st, launch_wgrad(p->dtype, w, st));
-    if (grad_weight[l])
-      LAUNCH(p, K_OTHER, st, launch_unpack_wgrad(y.dw_acc, y.db_acc, grad_weight[l], grad_bias[l], y.cin, y.hc, y.k, y.ncols, y.cx_pad, bias_col, 0, st));
+    if (grad_weight_l)
+      LAUNCH(p, K_OTHER, st, launch_unpack_wgrad(y.dw_acc, y.db_acc, grad_weight_l, grad_bias_l, y.cin, y.hc, y.k, y.ncols, y.cx_pad, bias_col, 0, st));
   }
+  return 0;
+}
+
+int nint_backward(nint_plan* p, const float* dpred, const float* dseq, float* const* grad_weight,
+                  float* const* grad_bias, float* grad_head_weight, float* grad_head_bias, void* stream) {
+  if (!grad_weight || !grad_bias) return fail("nint_backward: null gradient tables");
+  if (nint_backward_bptt(p, dpred, dseq, grad_head_weight, grad_head_bias, stream)) return 1;
+  for (int l = 0; l < p->L; ++l)
+    if (nint_backward_wgrad(p, l, grad_weight[l], grad_bias[l], stream)) return 1;
   return 0;
 }
 

@@ -123,10 +123,11 @@ class Plan:
         self.generation += 1
         return pred, seq
 
-    def backward(self, dpred: Optional[torch.Tensor], dseq: Optional[torch.Tensor] = None, out=None):
+    def backward(self, dpred: Optional[torch.Tensor], dseq: Optional[torch.Tensor] = None, out=None, on_ready=None):
         """Returns ([grad_weight_l], [grad_bias_l], grad_head_weight, grad_head_bias).  `out`: optional
         (gw list, gb list, ghw, ghb) of preallocated contiguous fp32 tensors the gradients are written into
-        (e.g. views of one flat all-reduce buffer)."""
+        (e.g. views of one flat all-reduce buffer).  `on_ready(i)`: called as soon as the kernels producing a
+        gradient bucket are queued on the current stream -- i = L for the head, then i = L-1 .. 0 for the layers."""
         if dseq is not None:
             dseq = dseq.detach().contiguous().clone() if dpred is not None else dseq.detach().contiguous()
             _check_dev(dseq, "dseq", (self.B, self.T, self.H, self.W))
@@ -157,10 +158,21 @@ class Plan:
                 cin = hc
             ghw = torch.empty((1, self.hidden[-1], 1, 1), dtype=torch.float32, device=self.device)
             ghb = torch.empty((1,), dtype=torch.float32, device=self.device)
-        arr_w = (ctypes.c_void_p * self.L)(*[t.data_ptr() for t in gw])
-        arr_b = (ctypes.c_void_p * self.L)(*[t.data_ptr() for t in gb])
-        _lib.check(self.lib.nint_backward(self._h, _ptr(dpred), _ptr(dseq), arr_w, arr_b, _ptr(ghw), _ptr(ghb),
-                                          _stream()), "nint_backward")
+        if on_ready is None:
+            arr_w = (ctypes.c_void_p * self.L)(*[t.data_ptr() for t in gw])
+            arr_b = (ctypes.c_void_p * self.L)(*[t.data_ptr() for t in gb])
+            _lib.check(self.lib.nint_backward(self._h, _ptr(dpred), _ptr(dseq), arr_w, arr_b, _ptr(ghw), _ptr(ghb),
+                                              _stream()), "nint_backward")
+            return gw, gb, ghw, ghb
+        # staged: the caller hears about every finished gradient bucket (the head's after BPTT, then one layer at a
+        # time, top layer first) while the following wgrad kernels are still queued -- nint.h nint_backward_bptt/_wgrad
+        _lib.check(self.lib.nint_backward_bptt(self._h, _ptr(dpred), _ptr(dseq), _ptr(ghw), _ptr(ghb), _stream()),
+                   "nint_backward_bptt")
+        on_ready(self.L)
+        for l in range(self.L - 1, -1, -1):
+            _lib.check(self.lib.nint_backward_wgrad(self._h, l, _ptr(gw[l]), _ptr(gb[l]), _stream()),
+                       "nint_backward_wgrad")
+            on_ready(l)
         return gw, gb, ghw, ghb
 
     # ---- measurement

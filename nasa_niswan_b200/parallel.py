@@ -7,6 +7,7 @@ section 8e): every rank runs the full T loop on its slice of the batch with repl
 the only exchange is one sum all-reduce of a flat fp32 gradient buffer (0.78 MB for the BASELINE
 geometry, latency-bound), issued on the current stream right after BPTT.
 """
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -35,8 +36,22 @@ class FlatGradients:
             p.grad = self.flat[off:off + p.numel()].view_as(p)
             off += p.numel()
 
+        # buckets for the overlapped all-reduce: one per ConvLSTM layer (weight + bias are adjacent in
+        # model.parameters() order) and one for the 1x1 head
+        self.buckets = []
+        off = 0
+        for i in range(0, len(self.params), 2):
+            n = sum(p.numel() for p in self.params[i:i + 2])
+            self.buckets.append(self.flat[off:off + n])
+            off += n
+
     def zero(self):
         self.flat.zero_()
+
+    def all_reduce_bucket_async(self, i: int):
+        """Start the sum all-reduce of bucket i (layer i; the last bucket is the head).  NCCL runs it on its own
+        stream after the work queued so far on the current one, so kernels launched next overlap with it."""
+        return dist.all_reduce(self.buckets[i], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
 
     def all_reduce_mean(self):
         if dist.is_available() and dist.is_initialized():
@@ -202,6 +217,11 @@ class Trainer:
     def __init__(self, model, lr: float = 1e-3, betas=(0.5, 0.999), crop=None, process_group=None, native=None,
                  scheduler_config=None):
         self.model, self.crop, self.group = model, crop, process_group
+        # one flat all-reduce after backward (default) or bucketed all-reduces overlapped with the wgrad kernels
+        # (NINT_DP_OVERLAP=1).  Measured at 2 x B200, cfg 2: overlapping is SLOWER (6.71-6.82 vs 6.64-6.67 ms/step, wgrad
+        # 2.02 vs 1.83 ms) -- the wgrad kernel is persistent with one CTA per SM, so NCCL's CTAs take SMs its static
+        # tile partition counts on, and a 0.78 MB all-reduce costs ~30 us when it runs alone.
+        self.overlap = os.environ.get("NINT_DP_OVERLAP", "0") == "1"
         self.grads = FlatGradients(model.parameters(), process_group)
         on_cuda = next(model.parameters()).is_cuda
         self.native = on_cuda if native is None else bool(native)
@@ -251,12 +271,21 @@ class Trainer:
         loss = torch.empty(1, dtype=torch.float32, device=pred.device)
         _lib.check(_lib.load().nint_loss_mse_l1(vp(pred), vp(y.contiguous()), B, H, W, y0, y1, x0, x1, vp(dpred), vp(loss),
                                                 vp(self._stats), st), "nint_loss_mse_l1")   # train.py:102,105
-        plan.backward(dpred, out=self._grad_views())                # train.py:109, written into the flat buffer
-        world = 1
-        if dist.is_available() and dist.is_initialized():
-            world = dist.get_world_size(self.group)
-            if world > 1:
-                dist.all_reduce(self.grads.flat, op=dist.ReduceOp.SUM, group=self.group)
+        world = dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
+        if world > 1 and not self.overlap:
+            plan.backward(dpred, out=self._grad_views())
+            dist.all_reduce(self.grads.flat, op=dist.ReduceOp.SUM, group=self.group)
+        elif world > 1:
+            # bucketed all-reduce overlapped with backward: the head bucket flies during the layers' wgrad kernels,
+            # layer l's bucket during the wgrad of layer l-1 (the weight gradients are batched over all T steps, so
+            # they only exist once BPTT is over: SURVEY.md section 8e)
+            pending = []
+            plan.backward(dpred, out=self._grad_views(),
+                          on_ready=lambda i: pending.append(self.grads.all_reduce_bucket_async(i)))
+            for work in pending:
+                work.wait()
+        else:
+            plan.backward(dpred, out=self._grad_views())            # train.py:109, written into the flat buffer
         self.optimizer.step(grad_scale=1.0 / world)                 # train.py:110 (mean over ranks folded in)
         return loss[0]
 

@@ -194,6 +194,42 @@ def test_edge_geometries_against_oracle(cfg, precision):
         assert O.max_abs_normalised(p.grad.cpu(), leaf[k].grad) < tol, k
 
 
+def test_staged_backward_matches_single_call():
+    """nint_backward_bptt + nint_backward_wgrad per layer (what the overlapped all-reduce drives) == nint_backward;
+    buckets are announced head first, then layers top-down; wgrad before BPTT is refused"""
+    from nasa_niswan_b200 import Plan
+    torch.manual_seed(6)
+    B, T, C, H, W, hidden, ks = 2, 3, 5, 12, 20, [64, 32], [3, 3]
+    plan = Plan(B, T, H, W, C, hidden, ks, precision="bf16", training=True)
+    cin = C
+    for l, (hc, k) in enumerate(zip(hidden, ks)):
+        plan.set_weights(l, torch.randn(4 * hc, cin + hc, k, k, device="cuda") * 0.1, torch.randn(4 * hc, device="cuda") * 0.1)
+        cin = hc
+    plan.set_head(torch.randn(1, hidden[-1], 1, 1, device="cuda"), torch.zeros(1, device="cuda"))
+    x = torch.randn(B, T, C, H, W, device="cuda")
+    pred, _ = plan.forward(x)
+    dpred = torch.randn_like(pred)
+    with pytest.raises(RuntimeError, match="before nint_backward_bptt"):
+        _lib_check_wgrad_first(plan)
+    ref = plan.backward(dpred)
+    pred2, _ = plan.forward(x)
+    assert torch.equal(pred, pred2)
+    order = []
+    got = plan.backward(dpred, on_ready=order.append)
+    assert order == [2, 1, 0]
+    for a, b in zip([*ref[0], *ref[1], ref[2], ref[3]], [*got[0], *got[1], got[2], got[3]]):
+        assert O.max_abs_normalised(b.cpu(), a.cpu()) < 1e-5      # fp32 atomics reorder sums only
+
+
+def _lib_check_wgrad_first(plan):
+    import ctypes
+    from nasa_niswan_b200 import _lib
+    g = torch.empty(4 * 64 * (5 + 64) * 9, device="cuda")
+    b = torch.empty(4 * 64, device="cuda")
+    _lib.check(plan.lib.nint_backward_wgrad(plan._h, 0, ctypes.c_void_p(g.data_ptr()), ctypes.c_void_p(b.data_ptr()),
+                                            ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "nint_backward_wgrad")
+
+
 def test_long_inference_rollout_keeps_state_resident():
     """BASELINE cfg 4 in miniature: forward-only T = 40 rollout (2-slot h ring, c updated in place) vs the oracle"""
     from nasa_niswan_b200 import ConvLSTM

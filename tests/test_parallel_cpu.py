@@ -109,3 +109,42 @@ def test_step_lr_matches_torch_scheduler():
     resumed.step()
     mine.step()
     assert resumed.get_last_lr() == mine.get_last_lr()
+
+
+class _TwoLayer(torch.nn.Module):     # parameter order of ConvLSTM: layers.0.w, layers.0.b, layers.1.w, layers.1.b, head w, b
+    def __init__(self):
+        super().__init__()
+        self.layers = torch.nn.ModuleList([torch.nn.Conv2d(3, 8, 3, padding=1), torch.nn.Conv2d(8, 4, 3, padding=1)])
+        self.conv = torch.nn.Conv2d(4, 1, 1)
+
+
+def _bucket_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    model = _TwoLayer()
+    grads = FlatGradients(model.parameters())
+    torch.manual_seed(7 + rank)
+    grads.flat.copy_(torch.randn_like(grads.flat))
+    mine = grads.flat.clone()
+    # the order Trainer uses: head first, then the layers top-down, all in flight together
+    pending = [grads.all_reduce_bucket_async(i) for i in (2, 1, 0)]
+    for w in pending:
+        w.wait()
+    total = mine.clone()
+    dist.all_reduce(total)
+    if rank == 0:
+        torch.save({"bucketed": grads.flat.clone(), "flat": total,
+                    "sizes": [b.numel() for b in grads.buckets],
+                    "views": all(p.grad.data_ptr() >= grads.flat.data_ptr() for p in model.parameters())}, out)
+    dist.destroy_process_group()
+
+
+def test_bucketed_async_all_reduce_equals_flat_all_reduce(tmp_path):
+    """one bucket per layer (weight + bias) plus the head, reduced asynchronously in the order backward
+    finishes them, gives exactly the single flat all-reduce"""
+    out = str(tmp_path / "buckets.pt")
+    mp.spawn(_bucket_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    r = torch.load(out)
+    assert r["sizes"] == [8 * 3 * 9 + 8, 4 * 8 * 9 + 4, 4 + 1]
+    assert r["views"]
+    assert torch.equal(r["bucketed"], r["flat"])
