@@ -12,6 +12,7 @@ from typing import Sequence
 import torch
 import torch.nn as nn
 
+from . import ops
 from .engine import Plan
 
 _MAX_CACHED_PLANS = 4
@@ -34,33 +35,6 @@ class _PlanCache:
 
     def clear(self):
         self._plans.clear()
-
-
-class _ConvLSTMFunction(torch.autograd.Function):
-    """forward = nint_forward (T x L fused cell steps + head); backward = nint_backward (BPTT)."""
-
-    @staticmethod
-    def forward(ctx, plan, x, *params):
-        pred, seq = plan.forward(x)
-        ctx.plan, ctx.generation = plan, plan.generation
-        if plan.return_sequence:
-            return pred, seq
-        return pred
-
-    @staticmethod
-    def backward(ctx, dpred, dseq=None):
-        plan = ctx.plan
-        if plan.generation != ctx.generation:
-            raise RuntimeError("the ConvLSTM workspace was overwritten by a later forward() with the same shape "
-                               "before backward() ran; run backward first (BPTT state lives in the plan workspace)")
-        if ctx.needs_input_grad[1]:
-            raise NotImplementedError("gradient w.r.t. the input x is not implemented (train.py never needs it)")
-        gw, gb, ghw, ghb = plan.backward(dpred, dseq)
-        grads = []
-        for l in range(plan.L):
-            grads += [gw[l], gb[l]]
-        grads += [ghw, ghb]
-        return (None, None, *grads)
 
 
 class ConvLSTMCell(nn.Module):
@@ -90,10 +64,7 @@ class ConvLSTMCell(nn.Module):
         B, _, H, W = x.shape
         key = (B, H, W, self.precision, x.device)
         plan = self._plans.get(key, lambda: self._make_plan(B, H, W, x.device))
-        plan.set_weights(0, self.conv.weight, self.conv.bias)
-        plan.set_state(0, h, c)
-        plan.forward(x.unsqueeze(1))
-        return plan.get_state(0)
+        return torch.ops.nint.cell_forward(x, h, c, self.conv.weight, self.conv.bias, ops.register_plan(plan))
 
     def _make_plan(self, B, H, W, device):
         plan = Plan(B, 1, H, W, self.input_channels, [self.hidden_channels], [self.kernel_size],
@@ -132,7 +103,7 @@ class ConvLSTM(nn.Module):
             ps += [cell.conv.weight, cell.conv.bias]
         return ps + [self.conv.weight, self.conv.bias]
 
-    def plan_for(self, x, training):
+    def plan_for(self, x, training, set_params=True):
         B, T, C, H, W = x.size()
         if C != self.input_channels:
             raise ValueError(f"expected {self.input_channels} input channels, got {C}")
@@ -142,9 +113,10 @@ class ConvLSTM(nn.Module):
         plan = self._plans.get(key, lambda: Plan(B, T, H, W, C, hidden, ks, precision=self.precision,
                                                  training=training, return_sequence=self.return_sequence,
                                                  device=x.device))
-        for l, cell in enumerate(self.layers):
-            plan.set_weights(l, cell.conv.weight, cell.conv.bias)
-        plan.set_head(self.conv.weight, self.conv.bias)
+        if set_params:
+            for l, cell in enumerate(self.layers):
+                plan.set_weights(l, cell.conv.weight, cell.conv.bias)
+            plan.set_head(self.conv.weight, self.conv.bias)
         return plan
 
     def forward(self, x):
@@ -153,10 +125,9 @@ class ConvLSTM(nn.Module):
                                "its input to the GPU")
         params = self._params()
         training = torch.is_grad_enabled() and any(p.requires_grad for p in params)
-        plan = self.plan_for(x, training)
-        if training:
-            return _ConvLSTMFunction.apply(plan, x, *params)
-        pred, seq = plan.forward(x)
+        plan = self.plan_for(x, training, set_params=False)   # the op repacks the weights it is handed
+        # torch.library op (ops.py): forward = nint_forward (T x L fused cell steps + head), autograd = nint_backward
+        pred, seq = torch.ops.nint.convlstm_forward(x, params, ops.register_plan(plan))
         return (pred, seq) if self.return_sequence else pred
 
     def release_workspaces(self):

@@ -91,7 +91,7 @@ def test_forward_backward_matches_golden(golden_dir, name, precision):
     assert torch.equal(pred_inf, pred.detach())
     loss = O.training_loss(pred, y, m["crop"])
     loss.backward()
-    assert abs(float(loss) - float(z["loss"])) < TOL[precision] * max(1.0, abs(float(z["loss"])))
+    assert abs(float(loss.detach()) - float(z["loss"])) < TOL[precision] * max(1.0, abs(float(z["loss"])))
     for k, p in net.named_parameters():
         assert p.grad is not None and p.grad.shape == p.shape
         assert O.max_abs_normalised(p.grad.cpu(), z["grad/" + k]) < TOL[precision], k
@@ -230,6 +230,27 @@ def _lib_check_wgrad_first(plan):
                                             ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "nint_backward_wgrad")
 
 
+def test_torch_library_op_contract():
+    """the dispatcher op behind ConvLSTM.forward: schema, fake-tensor shapes and autograd registration check out
+    (torch.library.opcheck), and calling it directly equals the module"""
+    from nasa_niswan_b200 import ConvLSTM, ops
+    torch.manual_seed(8)
+    net = ConvLSTM(5, [16, 16], [3, 3], 2, precision="tf32").cuda()
+    x = torch.randn(2, 3, 5, 12, 20, device="cuda")
+    plan = net.plan_for(x, True, set_params=False)
+    params = net._params()
+    pid = ops.register_plan(plan)
+    torch.library.opcheck(torch.ops.nint.convlstm_forward, (x, params, pid),
+                          test_utils=("test_schema", "test_faketensor", "test_autograd_registration"))
+    pred, seq = torch.ops.nint.convlstm_forward(x, params, pid)
+    assert seq.numel() == 0 and pred.requires_grad
+    assert torch.equal(pred.detach(), net(x).detach())
+    del plan
+    net.release_workspaces()
+    with pytest.raises(RuntimeError, match="no longer exists"):
+        torch.ops.nint.convlstm_forward(x, params, pid)
+
+
 def test_long_inference_rollout_keeps_state_resident():
     """BASELINE cfg 4 in miniature: forward-only T = 40 rollout (2-slot h ring, c updated in place) vs the oracle"""
     from nasa_niswan_b200 import ConvLSTM
@@ -311,7 +332,7 @@ def test_fused_loss_matches_torch(crop):
     st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
     _lib.check(_lib.load().nint_loss_mse_l1(vp(pred.detach()), vp(y), B, H, W, y0, y1, x0, x1, vp(dpred), vp(loss), vp(stats), st),
                "nint_loss_mse_l1")
-    assert abs(float(loss) - float(ref)) < 1e-5 * max(1.0, abs(float(ref)))
+    assert abs(float(loss.detach()) - float(ref.detach())) < 1e-5 * max(1.0, abs(float(ref.detach())))
     assert torch.allclose(dpred, pred.grad, rtol=1e-5, atol=1e-9)
     # the two extra sums give R^2 (train.py:114) without leaving the device
     r2 = 1.0 - float(stats[0]) / (float(stats[3]) - float(stats[2]) ** 2 / y.numel())

@@ -147,3 +147,15 @@ def test_checkpoint_format_matches_reference(tmp_path):
     assert opt2.param_groups[0]["lr"] == 5e-4            # utils.py:47-49: the stored learning rate wins
     load_checkpoint(str(f), net2, opt2, lr=1e-2)
     assert opt2.param_groups[0]["lr"] == 1e-2            # utils.py:43-45: an explicit lr overrides it
+
+
+def test_torch_library_ops_are_registered_cuda_only():
+    """the hot path is reachable as torch.library ops; they have no CPU kernel (no fallback)"""
+    import nasa_niswan_b200  # noqa: F401  (registers the ops)
+    assert str(torch.ops.nint.convlstm_forward.default._schema) == \
+        "nint::convlstm_forward(Tensor x, Tensor[] params, SymInt plan_id) -> (Tensor, Tensor)"
+    assert str(torch.ops.nint.convlstm_backward.default._schema) == \
+        "nint::convlstm_backward(Tensor dpred, Tensor? dseq, SymInt plan_id, SymInt generation) -> Tensor[]"
+    assert "nint::cell_forward" in str(torch.ops.nint.cell_forward.default._schema)
+    with pytest.raises(NotImplementedError, match="CPU"):
+        torch.ops.nint.convlstm_forward(torch.zeros(1, 1, 1, 8, 8), [torch.zeros(1)], 1)
