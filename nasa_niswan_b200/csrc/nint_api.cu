@@ -82,8 +82,16 @@ struct Layer {
   CUtensorMap tmw_H, tmw_G;  // wgrad views (32-channel boxes; differ from tm_* in tf32 mode only)
   CUtensorMap tmw_H_up;      // Hs[l] as the x part of layer l+1's wgrad (halo of k_{l+1})
   CUtensorMap tmp_G, tmp_H, tmp_H_up;        // CTA-pair wgrad views: 64-q dgates boxes (SWIZZLE_128B), 16-channel halo boxes (SWIZZLE_32B)
-  bool wgrad_pair = false;
-  int wg_pw = 16;            // pair wgrad: channels per B panel
+  // wgrad runs one launch per column block of dW (columns = padded input channels, then hidden channels): a block
+  // is what one CTA (pair) can hold as operand panels in shared memory and as an MMA N (<= 256)
+  struct WgBlock {
+    int col0 = 0, cols = 0;      // dw_acc columns [col0, col0 + cols)
+    int nch_x = 0, nch_h = 0;    // 32-channel panels taken from the x-part / h-part tensor
+    int chan0_x = 0, chan0_h = 0;
+    bool pair = false;
+    int pw = 16, a_bufs = 0, b_stages = 0;
+  };
+  std::vector<WgBlock> wg_blocks;
   CUtensorMap tme_C, tme_H, tme_G, tme_dC;  // epilogue I/O boxes (16 | 64 channels x 8 x 16 pixels; nint_epilogue.cuh)
   bool weights_set = false;
 };
@@ -370,6 +378,55 @@ int cell_step(nint_plan* p, int l, int t, int epi, float* raw_out, cudaStream_t 
 
 }  // namespace
 
+// Column blocks of a layer's weight gradient (Layer::WgBlock).  CTA-pair kernel (bf16, 4*hc % 256 == 0): the whole
+// row when it fits (N <= 256, >= 2 B stages), else the x part and the h part as two launches.  Otherwise the
+// single-CTA kernel with as few blocks of whole 32-channel panels as leave it two B stages.
+static int plan_wgrad_blocks(nint_plan* p, Layer& y) {
+  y.wg_blocks.clear();
+  const int px = y.cx_pad / 32, ph = y.hc_pad / 32;
+  auto pair_block = [&](int col0, int x_cols, int cols) {
+    Layer::WgBlock b;
+    b.col0 = col0; b.cols = cols;
+    b.nch_x = x_cols / 32; b.nch_h = (cols - x_cols) / 32;
+    b.pair = true;
+    b.pw = wgrad_pair_panel_width(x_cols, cols);
+    b.a_bufs = 3;
+    b.b_stages = wgrad_pair_b_stages(x_cols, cols, y.k);
+    return b;
+  };
+  if (p->cluster == 2 && p->dtype == BF16 && (4 * y.hc) % 256 == 0) {
+    if (wgrad_pair_supported(p->dtype, 4 * y.hc, y.cx_pad, y.ncols, y.k)) {
+      y.wg_blocks.push_back(pair_block(0, y.cx_pad, y.ncols));
+      return 0;
+    }
+    if (wgrad_pair_supported(p->dtype, 4 * y.hc, y.cx_pad, y.cx_pad, y.k) &&
+        wgrad_pair_supported(p->dtype, 4 * y.hc, 0, y.hc_pad, y.k)) {
+      y.wg_blocks.push_back(pair_block(0, y.cx_pad, y.cx_pad));
+      y.wg_blocks.push_back(pair_block(y.cx_pad, 0, y.hc_pad));
+      return 0;
+    }
+  }
+  const int panels = px + ph, bpb = wgrad_b_panel_bytes(p->dtype, 1, y.k);
+  int per = panels, a_bufs = 0, b_stages = 0;
+  for (; per >= 1; --per) {
+    wgrad_pick_buffers(p->dtype, per, bpb, &a_bufs, &b_stages);
+    if (per * 32 <= 256 && (b_stages >= 2 || (per == 1 && b_stages >= 1))) break;
+  }
+  if (per < 1) return 1;
+  for (int j0 = 0; j0 < panels; j0 += per) {
+    const int j1 = j0 + per < panels ? j0 + per : panels;
+    Layer::WgBlock b;
+    b.col0 = j0 * 32; b.cols = (j1 - j0) * 32;
+    b.nch_x = (j1 < px ? j1 : px) - (j0 < px ? j0 : px);
+    b.nch_h = (j1 - j0) - b.nch_x;
+    b.chan0_x = (j0 < px ? j0 : px) * 32;
+    b.chan0_h = (j0 > px ? j0 - px : 0) * 32;
+    wgrad_pick_buffers(p->dtype, j1 - j0, bpb, &b.a_bufs, &b.b_stages);
+    y.wg_blocks.push_back(b);
+  }
+  return 0;
+}
+
 extern "C" {
 
 int nint_version(void) { return 100; }
@@ -476,20 +533,11 @@ int nint_plan_create(const nint_config* cfg, nint_plan** out) {
     y.nslots_h = cfg->training ? p->T + 1 : 2;
     y.nslots_c = cfg->training ? p->T + 1 : 1;
     y.ncols = y.cx_pad + y.hc_pad;
-    if (cfg->training && y.ncols > 256) {
+    if (cfg->training && plan_wgrad_blocks(p, y)) {
+      const int hc = y.hc, k = y.k;
       delete p;
-      return fail("layer %d: padded input+hidden channels %d > 256 not supported by wgrad", l, y.ncols);
-    }
-    if (cfg->training && !(p->cluster == 2 && wgrad_pair_supported(p->dtype, 4 * y.hc, y.cx_pad, y.ncols, y.k))) {
-      // single-CTA wgrad kernel: one stage holds a halo panel per 32 input+hidden channels next to the dgates panels
-      int a_bufs = 0, b_stages = 0;
-      wgrad_pick_buffers(p->dtype, y.ncols / 32, wgrad_b_panel_bytes(p->dtype, 1, y.k), &a_bufs, &b_stages);
-      if (b_stages < 1) {
-        const int hc = y.hc, k = y.k, nc = y.ncols;
-        delete p;
-        return fail("layer %d: training with hidden %d, kernel %d in this precision needs %d-channel wgrad operand panels "
-                    "that do not fit in shared memory", l, hc, k, nc);
-      }
+      return fail("layer %d: training with hidden %d, kernel %d: not even one 32-channel wgrad operand panel fits in "
+                  "shared memory", l, hc, k);
     }
     cin = y.hc;
   }
@@ -551,19 +599,25 @@ int nint_plan_bind(nint_plan* p, void* workspace, size_t bytes, void* stream) {
   if (p->cfg.training) {
     for (int l = 0; l < p->L; ++l) {
       Layer& y = p->layer[l];
-      y.wgrad_pair = p->cluster == 2 && wgrad_pair_supported(p->dtype, 4 * y.hc, y.cx_pad, y.ncols, y.k) != 0;
-      if (!y.wgrad_pair) continue;
-      y.wg_pw = wgrad_pair_panel_width(y.cx_pad, y.ncols);
-      const CUtensorMapSwizzle sw = y.wg_pw == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
-                                                  : (y.wg_pw == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
-      if (encode_act_box(&y.tmp_G, p->dtype, y.G, 4 * y.hc, p->W, p->H, p->B, p->T, 64, tw, th, 0, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
-      if (encode_act_box(&y.tmp_H, p->dtype, y.Hs, y.hc_pad, p->W, p->H, p->B, y.nslots_h, y.wg_pw, tw, th, pad_of(l), sw)) return 1;
-      if (l == 0) {
-        if (encode_act_box(&p->tmp_X, p->dtype, p->X, y.cx_pad, p->W, p->H, p->B, p->T, y.wg_pw, tw, th, pad_of(0), sw)) return 1;
-      } else {
-        Layer& dn = p->layer[l - 1];
-        if (encode_act_box(&dn.tmp_H_up, p->dtype, dn.Hs, dn.hc_pad, p->W, p->H, p->B, dn.nslots_h, y.wg_pw, tw, th, pad_of(l), sw)) return 1;
+      auto sw_of = [](int pw) {
+        return pw == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (pw == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+      };
+      bool any_pair = false;
+      for (const Layer::WgBlock& b : y.wg_blocks) {
+        if (!b.pair) continue;
+        any_pair = true;
+        // a pair block covers whole tensors (the full row, or the x part / the h part), so one map per tensor
+        if (b.nch_h > 0 &&
+            encode_act_box(&y.tmp_H, p->dtype, y.Hs, y.hc_pad, p->W, p->H, p->B, y.nslots_h, b.pw, tw, th, pad_of(l), sw_of(b.pw))) return 1;
+        if (b.nch_x > 0 && l == 0 &&
+            encode_act_box(&p->tmp_X, p->dtype, p->X, y.cx_pad, p->W, p->H, p->B, p->T, b.pw, tw, th, pad_of(0), sw_of(b.pw))) return 1;
+        if (b.nch_x > 0 && l > 0) {
+          Layer& dn = p->layer[l - 1];
+          if (encode_act_box(&dn.tmp_H_up, p->dtype, dn.Hs, dn.hc_pad, p->W, p->H, p->B, dn.nslots_h, b.pw, tw, th, pad_of(l), sw_of(b.pw))) return 1;
+        }
       }
+      if (any_pair &&
+          encode_act_box(&y.tmp_G, p->dtype, y.G, 4 * y.hc, p->W, p->H, p->B, p->T, 64, tw, th, 0, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
     }
   }
   p->zero_init = true;
@@ -816,65 +870,75 @@ int nint_backward_wgrad(nint_plan* p, int l, float* grad_weight_l, float* grad_b
   if (l < 0 || l >= p->L) return fail("layer %d out of range", l);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int T = p->T;
-  {
-    Layer& y = p->layer[l];
-    CK(cudaMemsetAsync(y.dw_acc, 0, y.dw_acc_bytes, st));
-    CK(cudaMemsetAsync(y.db_acc, 0, 4 * y.hc * 4, st));
+  Layer& y = p->layer[l];
+  CK(cudaMemsetAsync(y.dw_acc, 0, y.dw_acc_bytes, st));
+  CK(cudaMemsetAsync(y.db_acc, 0, 4 * y.hc * 4, st));
+  // The bias gradient is either free (layer 0: x carries 1.0 in padding channel `ones_lane`, so db is that column
+  // of the centre tap) or costs 32 more accumulator columns and one N=32 MMA per K step against a panel of ones,
+  // in the first column block's lightest tap group (the last one when it has room, else the first).
+  const int bias_col = (l == 0) ? p->ones_lane : -1;
+  const long long total_tiles = static_cast<long long>(T) * p->B * p->tiles_x * p->tiles_y;
+  for (size_t bi = 0; bi < y.wg_blocks.size(); ++bi) {
+    const Layer::WgBlock& blk = y.wg_blocks[bi];
     WgradParams w;
     memset(&w, 0, sizeof(w));
-    w.tmap_dg = y.tmw_G;
-    w.tmap_b[0] = l == 0 ? p->tmw_X : p->layer[l - 1].tmw_H_up;
     w.halo = 1;
     w.debug_flags = p->debug_flags;
     w.b_panel_bytes = wgrad_b_panel_bytes(p->dtype, w.halo, y.k);
-    w.tmap_b[1] = y.tmw_H;
     w.slot_b0[0] = l == 0 ? 0 : 1;
     w.slot_b0[1] = 0;
-    w.nchunks_b[0] = y.cx_pad / 32;
-    w.nchunks_b[1] = y.hc_pad / 32;
+    w.nchunks_b[0] = blk.nch_x;
+    w.nchunks_b[1] = blk.nch_h;
+    w.chan0[0] = blk.chan0_x;
+    w.chan0[1] = blk.chan0_h;
     w.T = T; w.B = p->B; w.H = p->H; w.W = p->W;
     w.tile_w = p->tile_w; w.tile_h = p->tile_h; w.tiles_x = p->tiles_x; w.tiles_y = p->tiles_y;
     w.ksize = y.k;
     w.hc4 = 4 * y.hc;
-    w.pair = y.wgrad_pair ? 1 : 0;
+    w.pair = blk.pair ? 1 : 0;
     if (w.pair) {
       w.tmap_dg = y.tmp_G;
       w.tmap_b[0] = l == 0 ? p->tmp_X : p->layer[l - 1].tmp_H_up;
       w.tmap_b[1] = y.tmp_H;
+    } else {
+      w.tmap_dg = y.tmw_G;
+      w.tmap_b[0] = l == 0 ? p->tmw_X : p->layer[l - 1].tmw_H_up;
+      w.tmap_b[1] = y.tmw_H;
     }
+    // a block without x (or h) panels never dereferences that map, but kernel parameters must be valid maps
+    if (blk.nch_x == 0) w.tmap_b[0] = w.tmap_b[1];
+    if (blk.nch_h == 0) w.tmap_b[1] = w.tmap_b[0];
     w.m_blocks = w.pair ? w.hc4 / 256 : (w.hc4 + 127) / 128;
     w.ncols = y.ncols;
-    // tap groups: a CTA keeps (taps in group) x ncols accumulator columns in TMEM (512 available).  The bias
-    // gradient is either free (layer 0: x carries 1.0 in padding channel `ones_lane`, so db is that column of the
-    // centre tap) or costs 32 more columns and one N=32 MMA per K step in the lightest group (the last one when it
-    // has room, else the first).
-    const int bias_col = (l == 0) ? p->ones_lane : -1;
-    const int bias_cols = bias_col >= 0 ? 0 : 32;
-    const int tpg = 512 / y.ncols;                      // taps per group
-    if (tpg < 1) return fail("wgrad: ncols %d exceeds the accumulator", y.ncols);
+    w.acc_cols = blk.cols;
+    w.col0 = blk.col0;
+    // tap groups: a CTA keeps (taps in group) x acc_cols accumulator columns in TMEM (512 available)
+    const int bias_cols = (bias_col >= 0 || bi > 0) ? 0 : 32;
+    const int tpg = 512 / blk.cols;                      // taps per group
+    if (tpg < 1) return fail("wgrad: %d columns exceed the accumulator", blk.cols);
     int ng = 0, tap = 0;
     w.group_tap0[0] = 0;
     const int rest = y.taps % tpg;
-    const bool bias_last = rest > 0 && rest * y.ncols + bias_cols <= 512;   // a partial last group with room for the bias
-    const int g0 = bias_last ? tpg : ((512 - bias_cols) / y.ncols < tpg ? (512 - bias_cols) / y.ncols : tpg);
-    if (g0 < 1) return fail("wgrad: ncols %d leaves no room for the bias columns", y.ncols);
+    const bool bias_last = rest > 0 && rest * blk.cols + bias_cols <= 512;   // a partial last group with room for the bias
+    const int g0 = bias_last ? tpg : ((512 - bias_cols) / blk.cols < tpg ? (512 - bias_cols) / blk.cols : tpg);
+    if (g0 < 1) return fail("wgrad: %d columns leave no room for the bias columns", blk.cols);
     while (tap < y.taps) {
       const int n = ng == 0 ? g0 : tpg;
       tap = tap + n > y.taps ? y.taps : tap + n;
       if (ng + 1 > kMaxWgradGroups) return fail("wgrad: too many tap groups");
       w.group_tap0[++ng] = tap;
     }
-    w.bias_group = bias_col >= 0 ? -1 : (bias_last ? ng - 1 : 0);
+    w.bias_group = bias_cols == 0 ? -1 : (bias_last ? ng - 1 : 0);
     w.n_groups = ng;
     // split-K over pixel tiles: every group gets a share of the SMs in proportion to its MMA cycles per K step
     // (pair MMA: ~N/2 cycles with a ~40-cycle floor; 1-CTA MMA: ~N*0.67 with a ~88-cycle floor -- DESIGN.md 4)
-    const long long total_tiles = static_cast<long long>(T) * p->B * p->tiles_x * p->tiles_y;
     {
-      const int units = (w.pair ? p->num_sms / 2 : p->num_sms) / w.m_blocks;   // (group, split) slots
+      int units = (w.pair ? p->num_sms / 2 : p->num_sms) / w.m_blocks;   // (group, split) slots
+      if (units < ng) units = ng;
       auto mma_cost = [&](int n) { return w.pair ? (n / 2 > 40 ? n / 2 : 40) : (n * 2 / 3 > 88 ? n * 2 / 3 : 88); };
       int cost[kMaxWgradGroups], tot = 0;
       for (int g = 0; g < ng; ++g) {
-        cost[g] = (w.group_tap0[g + 1] - w.group_tap0[g]) * mma_cost(y.ncols) + (g == w.bias_group ? mma_cost(32) : 0);
+        cost[g] = (w.group_tap0[g + 1] - w.group_tap0[g]) * mma_cost(blk.cols) + (g == w.bias_group ? mma_cost(32) : 0);
         tot += cost[g];
       }
       const bool even = (p->debug_flags & 64) != 0;     // experiment: the same split count for every group
@@ -899,22 +963,18 @@ int nint_backward_wgrad(nint_plan* p, int l, float* grad_weight_l, float* grad_b
         w.group_unit0[g + 1] = w.group_unit0[g] + w.m_blocks * w.group_splits[g];
       }
     }
-    if (w.pair) {
-      w.b_pw = y.wg_pw;
-      w.a_bufs = 3;
-      w.b_stages = wgrad_pair_b_stages(y.cx_pad, y.ncols, y.k);
-    } else {
-      wgrad_pick_buffers(p->dtype, y.ncols / 32, w.b_panel_bytes, &w.a_bufs, &w.b_stages);
-    }
+    w.b_pw = blk.pw;
+    w.a_bufs = blk.a_bufs;
+    w.b_stages = blk.b_stages;
     if (w.b_stages < 1) return fail("wgrad: operand panels do not fit in shared memory");
-    w.idesc = idesc_of(p->dtype, w.pair ? 256 : 128, y.ncols, 1, 1);
+    w.idesc = idesc_of(p->dtype, w.pair ? 256 : 128, blk.cols, 1, 1);
     w.idesc_bias = idesc_of(p->dtype, w.pair ? 256 : 128, 32, 1, 1);
     w.dw_acc = y.dw_acc;
     w.db_acc = y.db_acc;
     LAUNCH(p, K_WGRAD, st, launch_wgrad(p->dtype, w, st));
-    if (grad_weight_l)
-      LAUNCH(p, K_OTHER, st, launch_unpack_wgrad(y.dw_acc, y.db_acc, grad_weight_l, grad_bias_l, y.cin, y.hc, y.k, y.ncols, y.cx_pad, bias_col, 0, st));
   }
+  if (grad_weight_l)
+    LAUNCH(p, K_OTHER, st, launch_unpack_wgrad(y.dw_acc, y.db_acc, grad_weight_l, grad_bias_l, y.cin, y.hc, y.k, y.ncols, y.cx_pad, bias_col, 0, st));
   return 0;
 }
 

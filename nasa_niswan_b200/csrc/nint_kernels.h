@@ -96,7 +96,10 @@ struct alignas(64) WgradParams {
                           // the x tensor carries a constant 1.0 in a padding channel and db falls out of the centre tap)
   int group_splits[kMaxWgradGroups];    // split-K factor over pixel tiles, per tap group (in proportion to its MMA cost)
   int group_unit0[kMaxWgradGroups + 1]; // first CTA (cluster, for the pair kernel) of each group; [n_groups] = grid units
-  int ncols;              // accumulator columns per tap = (sum nchunks_b) * 32
+  int ncols;              // row pitch of dw_acc = all padded input + hidden channels of the layer
+  int acc_cols;           // accumulator columns per tap of THIS launch = (sum nchunks_b) * 32 (one column block)
+  int col0;               // first dw_acc column of the block
+  int chan0[2];           // first channel of the block inside the x-part / h-part tensor
   int a_bufs, b_stages;
   int halo;               // 1: 8x16 tiles, B panels hold the tile + k//2 halo and every tap re-reads them in place
   int b_panel_bytes;      // bytes between consecutive B panels of a stage

@@ -166,9 +166,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
             mbar_arrive_expect_tx(&b_full[bs], static_cast<uint32_t>(hrows * ROWB * bpanels));
             uint8_t* dst = sB + bs * b_stage_bytes;
             for (int j = 0; j < p.nchunks_b[0]; ++j, dst += p.b_panel_bytes)
-              tma_load_5d(dst, &p.tmap_b[0], &b_full[bs], j * CE, x0 - pad, y0 - pad, b, p.slot_b0[0] + t);
+              tma_load_5d(dst, &p.tmap_b[0], &b_full[bs], p.chan0[0] + j * CE, x0 - pad, y0 - pad, b, p.slot_b0[0] + t);
             for (int j = 0; j < p.nchunks_b[1]; ++j, dst += p.b_panel_bytes)
-              tma_load_5d(dst, &p.tmap_b[1], &b_full[bs], j * CE, x0 - pad, y0 - pad, b, p.slot_b0[1] + t);
+              tma_load_5d(dst, &p.tmap_b[1], &b_full[bs], p.chan0[1] + j * CE, x0 - pad, y0 - pad, b, p.slot_b0[1] + t);
           }
           if (++bs == p.b_stages) {
             bs = 0;
@@ -183,9 +183,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
             mbar_arrive_expect_tx(&b_full[bs], panel_tx * bpanels);
             uint8_t* dst = sB + bs * b_stage_bytes;
             for (int j = 0; j < p.nchunks_b[0]; ++j, dst += PANEL)
-              tma_load_5d(dst, &p.tmap_b[0], &b_full[bs], j * CE, x0 + dx, y0 + dy, b, p.slot_b0[0] + t);
+              tma_load_5d(dst, &p.tmap_b[0], &b_full[bs], p.chan0[0] + j * CE, x0 + dx, y0 + dy, b, p.slot_b0[0] + t);
             for (int j = 0; j < p.nchunks_b[1]; ++j, dst += PANEL)
-              tma_load_5d(dst, &p.tmap_b[1], &b_full[bs], j * CE, x0 + dx, y0 + dy, b, p.slot_b0[1] + t);
+              tma_load_5d(dst, &p.tmap_b[1], &b_full[bs], p.chan0[1] + j * CE, x0 + dx, y0 + dy, b, p.slot_b0[1] + t);
           }
           if (++bs == p.b_stages) {
             bs = 0;
@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
               int dy = tap_begin / p.ksize, dx = tap_begin % p.ksize;
               for (int ti = 0; ti < ntaps; ++ti) {
                 const uint64_t boff = static_cast<uint64_t>((((row0 + dy) * hpitch + dx) * ROWB) >> 4);
-                umma<DT>(tmem_base + static_cast<uint32_t>(ti * p.ncols), adesc0 + aoff, bdesc0 + boff, p.idesc, acc);
+                umma<DT>(tmem_base + static_cast<uint32_t>(ti * p.acc_cols), adesc0 + aoff, bdesc0 + boff, p.idesc, acc);
                 if (++dx == p.ksize) {
                   dx = 0;
                   ++dy;
@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
               }
               if (do_bias) {
                 const uint64_t odesc0 = make_smem_desc(smem_u32(sOnes), PANEL, SBO, LAYOUT);
-                umma<DT>(tmem_base + static_cast<uint32_t>(ntaps * p.ncols), adesc0 + aoff, odesc0 + aoff, p.idesc_bias, acc);
+                umma<DT>(tmem_base + static_cast<uint32_t>(ntaps * p.acc_cols), adesc0 + aoff, odesc0 + aoff, p.idesc_bias, acc);
               }
             }
             umma_commit(&b_empty[bs]);
@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
           mbar_wait(&b_full[bs], bph);
           tc_fence_after();
           const uint64_t bdesc0 = make_smem_desc(smem_u32(sB + bs * b_stage_bytes), PANEL, SBO, LAYOUT);
-          const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(ti * p.ncols);
+          const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(ti * p.acc_cols);
           if (leader) {
 #pragma unroll
             for (int ks = 0; ks < KSTEPS; ++ks) {
@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
         }
         if (do_bias && leader) {
           const uint64_t odesc0 = make_smem_desc(smem_u32(sOnes), PANEL, SBO, LAYOUT);
-          const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(ntaps * p.ncols);
+          const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(ntaps * p.acc_cols);
 #pragma unroll
           for (int ks = 0; ks < KSTEPS; ++ks) {
             const uint64_t off = static_cast<uint64_t>((ks * ROWS_PER_MMA * ROWB) >> 4);
@@ -293,10 +293,10 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
     tc_fence_after();
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
     for (int ti = 0; ti < ntaps; ++ti) {
-      float* dst = p.dw_acc + (static_cast<long long>(tap_begin + ti) * p.hc4 + q) * p.ncols;
-      for (int c0 = 0; c0 < p.ncols; c0 += 16) {
+      float* dst = p.dw_acc + (static_cast<long long>(tap_begin + ti) * p.hc4 + q) * p.ncols + p.col0;
+      for (int c0 = 0; c0 < p.acc_cols; c0 += 16) {
         float v[16];
-        tmem_ld16(taddr + ti * p.ncols + c0, v);
+        tmem_ld16(taddr + ti * p.acc_cols + c0, v);
         tmem_ld_wait();
         if (valid) {
 #pragma unroll
@@ -306,7 +306,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
     }
     if (do_bias) {
       float v[16];
-      tmem_ld16(taddr + ntaps * p.ncols, v);
+      tmem_ld16(taddr + ntaps * p.acc_cols, v);
       tmem_ld_wait();
       if (valid) atomicAdd(p.db_acc + q, v[0]);
     }
@@ -485,9 +485,9 @@ wgrad_pair_kernel(const __grid_constant__ WgradParams p) {
         for (int j = jpar; j < bp_cta; j += 2, dst += 2 * b_panel) {
           const int pj = static_cast<int>(crank) * bp_cta + j;   // 16-channel panel of the concatenated input
           if (pj < bx16)
-            tma_load_5d_pair(dst, &p.tmap_b[0], bar, pj * pw, x0 - pad, y0 - pad, b, p.slot_b0[0] + t);
+            tma_load_5d_pair(dst, &p.tmap_b[0], bar, p.chan0[0] + pj * pw, x0 - pad, y0 - pad, b, p.slot_b0[0] + t);
           else
-            tma_load_5d_pair(dst, &p.tmap_b[1], bar, (pj - bx16) * pw, x0 - pad, y0 - pad, b, p.slot_b0[1] + t);
+            tma_load_5d_pair(dst, &p.tmap_b[1], bar, p.chan0[1] + (pj - bx16) * pw, x0 - pad, y0 - pad, b, p.slot_b0[1] + t);
         }
       }
       if (++bs == nbs) {
@@ -504,7 +504,7 @@ wgrad_pair_kernel(const __grid_constant__ WgradParams p) {
       const int which = warp == 1 ? 0 : 1;
       const bool leader = elect_one();
       const uint32_t idesc = p.idesc, idesc_bias = p.idesc_bias;
-      const uint32_t ncols = static_cast<uint32_t>(p.ncols);
+      const uint32_t ncols = static_cast<uint32_t>(p.acc_cols);
       const int ksize = p.ksize;
       const bool issue_any = !(p.debug_flags & 2);
       // MN-major descriptors.  A: 64-q atoms (128-byte rows, SWIZZLE_128B) one panel apart, 8-pixel groups 1 KiB apart.
@@ -598,10 +598,10 @@ wgrad_pair_kernel(const __grid_constant__ WgradParams p) {
     tc_fence_after();
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
     for (int ti = 0; ti < ntaps; ++ti) {
-      float* dst = p.dw_acc + (static_cast<long long>(tap_begin + ti) * p.hc4 + q) * p.ncols;
-      for (int c0 = 0; c0 < p.ncols; c0 += 16) {
+      float* dst = p.dw_acc + (static_cast<long long>(tap_begin + ti) * p.hc4 + q) * p.ncols + p.col0;
+      for (int c0 = 0; c0 < p.acc_cols; c0 += 16) {
         float v[16];
-        tmem_ld16(taddr + ti * p.ncols + c0, v);
+        tmem_ld16(taddr + ti * p.acc_cols + c0, v);
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 16; ++j) atomicAdd(dst + c0 + j, v[j]);
@@ -609,7 +609,7 @@ wgrad_pair_kernel(const __grid_constant__ WgradParams p) {
     }
     if (do_bias) {
       float v[16];
-      tmem_ld16(taddr + ntaps * p.ncols, v);
+      tmem_ld16(taddr + ntaps * p.acc_cols, v);
       tmem_ld_wait();
       atomicAdd(p.db_acc + q, v[0]);
     }
@@ -624,7 +624,7 @@ wgrad_pair_kernel(const __grid_constant__ WgradParams p) {
 }
 
 int wgrad_pair_supported(int dtype, int hc4, int cx_pad, int ncols, int ksize) {
-  if (dtype != NINT_BF16 || (hc4 % 256) != 0 || (ncols % 32) != 0) return 0;
+  if (dtype != NINT_BF16 || (hc4 % 256) != 0 || (ncols % 32) != 0 || ncols > 256) return 0;
   return wgrad_pair_b_stages(cx_pad, ncols, ksize) >= 2;
 }
 

@@ -1,0 +1,91 @@
+"""Randomised geometry sweep on the GPU box: forward + BPTT of random small ConvLSTM configurations against the CPU
+oracle (the same check as tests/test_gpu_parity.py::test_plans_against_oracle).  Prints one line per case and a
+summary; exit code 1 if any case is outside its tolerance or raises.
+
+    python tools/fuzz_parity.py [n_cases] [seed]
+"""
+import os
+import random
+import sys
+import time
+import traceback
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+from nasa_niswan_b200 import ConvLSTM  # noqa: E402
+from oracle import convlstm_oracle as O  # noqa: E402
+
+# short sums of signed tf32-rounded terms: see tests/test_gpu_parity.py::test_edge_geometries_against_oracle
+TOL = {"bf16": 2e-2, "tf32": 2e-3}
+HIDDEN = [16, 32, 48, 64, 128, 192, 256]
+
+
+def random_case(rng):
+    L = rng.choice([1, 1, 2, 3])
+    hidden = [rng.choice(HIDDEN) for l in range(L)]
+    ks = [rng.choice([1, 3, 3, 5, 7]) for _ in range(L)]
+    C = rng.choice([1, 3, 5, 16, 21, 32, 33, 40, 64])
+    return dict(B=rng.randint(1, 3), T=rng.randint(1, 4), C=C, H=rng.randint(2, 40), W=rng.randint(2, 40),
+                hidden=hidden, ks=ks, precision=rng.choice(["bf16", "tf32"]), seq=rng.random() < 0.25)
+
+
+def run_case(c, seed):
+    torch.manual_seed(seed)
+    L = len(c["hidden"])
+    net = ConvLSTM(c["C"], c["hidden"], c["ks"], L, precision=c["precision"], return_sequence=c["seq"])
+    params = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    net = net.cuda()
+    x = torch.randn(c["B"], c["T"], c["C"], c["H"], c["W"])
+    leaf = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    if c["seq"]:
+        rp, rs = O.convlstm_forward(x, leaf, L, return_sequence=True)
+        wts = torch.linspace(0.5, 1.5, c["T"]).view(1, -1, 1, 1)
+        ((rs * wts).sum() / rs.numel() + rp.mean()).backward()
+        pred, seq = net(x.cuda())
+        ((seq * wts.cuda()).sum() / seq.numel() + pred.mean()).backward()
+        err = max(O.max_abs_normalised(pred.detach().cpu(), rp.detach()), O.max_abs_normalised(seq.detach().cpu(), rs.detach()))
+    else:
+        rp = O.convlstm_forward(x, leaf, L)
+        y = torch.randn(c["B"], c["H"], c["W"])
+        dpred = torch.autograd.grad(O.training_loss(rp, y), rp, retain_graph=True)[0]
+        rp.backward(dpred)
+        pred = net(x.cuda())
+        pred.backward(dpred.cuda())
+        err = O.max_abs_normalised(pred.detach().cpu(), rp.detach())
+    gerr = max(O.max_abs_normalised(p.grad.cpu(), leaf[k].grad) for k, p in net.named_parameters())
+    return err, gerr
+
+
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 60
+    seed = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+    rng = random.Random(seed)
+    bad = refused = 0
+    t0 = time.time()
+    for i in range(n):
+        c = random_case(rng)
+        tag = (f"B{c['B']} T{c['T']} C{c['C']} {c['H']}x{c['W']} h{c['hidden']} k{c['ks']} {c['precision']}"
+               f"{' seq' if c['seq'] else ''}")
+        try:
+            err, gerr = run_case(c, seed * 1000 + i)
+            ok = err < TOL[c["precision"]] and gerr < TOL[c["precision"]]
+            bad += not ok
+            print(f"[{i:3d}] {'ok  ' if ok else 'FAIL'} pred {err:.2e} grad {gerr:.2e}  {tag}", flush=True)
+        except RuntimeError as e:
+            msg = str(e)
+            # geometry limits are refused when the plan is made: that is the specified behaviour
+            if "nint_plan_create" in msg and ("not supported" in msg or "do not fit" in msg or "unsupported" in msg):
+                refused += 1
+                print(f"[{i:3d}] refused ({msg.split(':', 1)[1].strip()[:90]})  {tag}", flush=True)
+            else:
+                bad += 1
+                print(f"[{i:3d}] ERROR {msg[:300]}  {tag}", flush=True)
+                traceback.print_exc()
+        torch.cuda.empty_cache()
+    print(f"{n} cases, {bad} bad, {refused} refused by plan validation, {time.time() - t0:.0f} s")
+    sys.exit(1 if bad else 0)
+
+
+if __name__ == "__main__":
+    main()
