@@ -29,8 +29,10 @@ print("pred", O.max_abs_normalised(pred.detach().cpu(), rp.detach()))
 for k, p in net.named_parameters():
     g, r = p.grad.cpu(), leaf[k].grad
     print(k, tuple(g.shape), "err %.3e" % O.max_abs_normalised(g, r), "max|ref| %.3e" % r.abs().max().item())
-    if g.dim() == 4:
-        cin = g.shape[1] - hidden[0] if k.startswith("layers.0") else None
-        if cin is not None:
-            print("   x-part err %.3e  h-part err %.3e" % (O.max_abs_normalised(g[:, :cin], r[:, :cin]),
-                                                           O.max_abs_normalised(g[:, cin:], r[:, cin:])))
+    if g.dim() == 4 and k.startswith("layers."):
+        l = int(k.split(".")[1])
+        cin = C if l == 0 else hidden[l - 1]
+        den = r.abs().max()
+        print("   x-part %.3e  h-part %.3e (both / max|ref| of the tensor);  max|ref| x %.2e h %.2e" % (
+            (g[:, :cin] - r[:, :cin]).abs().max() / den, (g[:, cin:] - r[:, cin:]).abs().max() / den,
+            r[:, :cin].abs().max(), r[:, cin:].abs().max()))
