@@ -86,6 +86,7 @@ struct Layer {
   // is what one CTA (pair) can hold as operand panels in shared memory and as an MMA N (<= 256)
   struct WgBlock {
     int col0 = 0, cols = 0;      // dw_acc columns [col0, col0 + cols)
+    int n_mma = 0;               // MMA N / accumulator columns per tap (>= cols: the tf32 pair kernel pads to whole panels)
     int nch_x = 0, nch_h = 0;    // 32-channel panels taken from the x-part / h-part tensor
     int chan0_x = 0, chan0_h = 0;
     bool pair = false;
@@ -392,8 +393,24 @@ static int plan_wgrad_blocks(nint_plan* p, Layer& y) {
     b.pw = wgrad_pair_panel_width(x_cols, cols);
     b.a_bufs = 3;
     b.b_stages = wgrad_pair_b_stages(x_cols, cols, y.k);
+    b.n_mma = cols;
     return b;
   };
+  // tf32 CTA-pair kernel: 32-channel fp32 panels, each CTA takes whole panels, so N is rounded up to an even panel
+  // count (the extra panel lies outside the h tensor: TMA zero-fills it); it has no ones-panel bias MMA, so it
+  // needs the constant-1 channel of layer 0
+  if (p->cluster == 2 && p->dtype == TF32 && (4 * y.hc) % 256 == 0 && &y == &p->layer[0] && p->ones_lane >= 0) {
+    const int n_mma = (y.ncols / 32 + 1) / 2 * 64;
+    const int st = n_mma <= 256 ? wgrad_pair_b_stages_tf32(n_mma, y.k) : 0;
+    if (st >= 2) {
+      Layer::WgBlock b;
+      b.col0 = 0; b.cols = y.ncols; b.n_mma = n_mma;
+      b.nch_x = y.cx_pad / 32; b.nch_h = y.hc_pad / 32;
+      b.pair = true; b.pw = 32; b.a_bufs = 2; b.b_stages = st;
+      y.wg_blocks.push_back(b);
+      return 0;
+    }
+  }
   if (p->cluster == 2 && p->dtype == BF16 && (4 * y.hc) % 256 == 0) {
     if (wgrad_pair_supported(p->dtype, 4 * y.hc, y.cx_pad, y.ncols, y.k)) {
       y.wg_blocks.push_back(pair_block(0, y.cx_pad, y.ncols));
@@ -416,7 +433,7 @@ static int plan_wgrad_blocks(nint_plan* p, Layer& y) {
   for (int j0 = 0; j0 < panels; j0 += per) {
     const int j1 = j0 + per < panels ? j0 + per : panels;
     Layer::WgBlock b;
-    b.col0 = j0 * 32; b.cols = (j1 - j0) * 32;
+    b.col0 = j0 * 32; b.cols = b.n_mma = (j1 - j0) * 32;
     b.nch_x = (j1 < px ? j1 : px) - (j0 < px ? j0 : px);
     b.nch_h = (j1 - j0) - b.nch_x;
     b.chan0_x = (j0 < px ? j0 : px) * 32;
@@ -604,7 +621,7 @@ int nint_plan_bind(nint_plan* p, void* workspace, size_t bytes, void* stream) {
       };
       bool any_pair = false;
       for (const Layer::WgBlock& b : y.wg_blocks) {
-        if (!b.pair) continue;
+        if (!b.pair || p->dtype != BF16) continue;   // the tf32 pair kernel reads the 32-channel tmw_* maps
         any_pair = true;
         // a pair block covers whole tensors (the full row, or the x part / the h part), so one map per tensor
         if (b.nch_h > 0 &&
@@ -896,11 +913,11 @@ int nint_backward_wgrad(nint_plan* p, int l, float* grad_weight_l, float* grad_b
     w.ksize = y.k;
     w.hc4 = 4 * y.hc;
     w.pair = blk.pair ? 1 : 0;
-    if (w.pair) {
+    if (w.pair && p->dtype == BF16) {
       w.tmap_dg = y.tmp_G;
       w.tmap_b[0] = l == 0 ? p->tmp_X : p->layer[l - 1].tmp_H_up;
       w.tmap_b[1] = y.tmp_H;
-    } else {
+    } else {   // single-CTA kernel, and the tf32 pair kernel: 32-channel boxes (bf16 SWIZZLE_64B / tf32 128B_ATOM_32B)
       w.tmap_dg = y.tmw_G;
       w.tmap_b[0] = l == 0 ? p->tmw_X : p->layer[l - 1].tmw_H_up;
       w.tmap_b[1] = y.tmw_H;
@@ -910,18 +927,19 @@ int nint_backward_wgrad(nint_plan* p, int l, float* grad_weight_l, float* grad_b
     if (blk.nch_h == 0) w.tmap_b[1] = w.tmap_b[0];
     w.m_blocks = w.pair ? w.hc4 / 256 : (w.hc4 + 127) / 128;
     w.ncols = y.ncols;
-    w.acc_cols = blk.cols;
+    w.acc_cols = blk.n_mma;
+    w.real_cols = blk.cols;
     w.col0 = blk.col0;
     // tap groups: a CTA keeps (taps in group) x acc_cols accumulator columns in TMEM (512 available)
     const int bias_cols = (bias_col >= 0 || bi > 0) ? 0 : 32;
-    const int tpg = 512 / blk.cols;                      // taps per group
-    if (tpg < 1) return fail("wgrad: %d columns exceed the accumulator", blk.cols);
+    const int tpg = 512 / blk.n_mma;                     // taps per group
+    if (tpg < 1) return fail("wgrad: %d columns exceed the accumulator", blk.n_mma);
     int ng = 0, tap = 0;
     w.group_tap0[0] = 0;
     const int rest = y.taps % tpg;
-    const bool bias_last = rest > 0 && rest * blk.cols + bias_cols <= 512;   // a partial last group with room for the bias
-    const int g0 = bias_last ? tpg : ((512 - bias_cols) / blk.cols < tpg ? (512 - bias_cols) / blk.cols : tpg);
-    if (g0 < 1) return fail("wgrad: %d columns leave no room for the bias columns", blk.cols);
+    const bool bias_last = rest > 0 && rest * blk.n_mma + bias_cols <= 512;   // a partial last group with room for the bias
+    const int g0 = bias_last ? tpg : ((512 - bias_cols) / blk.n_mma < tpg ? (512 - bias_cols) / blk.n_mma : tpg);
+    if (g0 < 1) return fail("wgrad: %d columns leave no room for the bias columns", blk.n_mma);
     while (tap < y.taps) {
       const int n = ng == 0 ? g0 : tpg;
       tap = tap + n > y.taps ? y.taps : tap + n;
@@ -938,7 +956,7 @@ int nint_backward_wgrad(nint_plan* p, int l, float* grad_weight_l, float* grad_b
       auto mma_cost = [&](int n) { return w.pair ? (n / 2 > 40 ? n / 2 : 40) : (n * 2 / 3 > 88 ? n * 2 / 3 : 88); };
       int cost[kMaxWgradGroups], tot = 0;
       for (int g = 0; g < ng; ++g) {
-        cost[g] = (w.group_tap0[g + 1] - w.group_tap0[g]) * mma_cost(blk.cols) + (g == w.bias_group ? mma_cost(32) : 0);
+        cost[g] = (w.group_tap0[g + 1] - w.group_tap0[g]) * mma_cost(blk.n_mma) + (g == w.bias_group ? mma_cost(32) : 0);
         tot += cost[g];
       }
       const bool even = (p->debug_flags & 64) != 0;     // experiment: the same split count for every group
@@ -967,7 +985,7 @@ int nint_backward_wgrad(nint_plan* p, int l, float* grad_weight_l, float* grad_b
     w.a_bufs = blk.a_bufs;
     w.b_stages = blk.b_stages;
     if (w.b_stages < 1) return fail("wgrad: operand panels do not fit in shared memory");
-    w.idesc = idesc_of(p->dtype, w.pair ? 256 : 128, blk.cols, 1, 1);
+    w.idesc = idesc_of(p->dtype, w.pair ? 256 : 128, blk.n_mma, 1, 1);
     w.idesc_bias = idesc_of(p->dtype, w.pair ? 256 : 128, 32, 1, 1);
     w.dw_acc = y.dw_acc;
     w.db_acc = y.db_acc;

@@ -99,6 +99,7 @@ struct alignas(64) WgradParams {
   int ncols;              // row pitch of dw_acc = all padded input + hidden channels of the layer
   int acc_cols;           // accumulator columns per tap of THIS launch = (sum nchunks_b) * 32 (one column block)
   int col0;               // first dw_acc column of the block
+  int real_cols;          // columns of the block that exist in dw_acc (<= acc_cols; the rest is MMA padding)
   int chan0[2];           // first channel of the block inside the x-part / h-part tensor
   int a_bufs, b_stages;
   int halo;               // 1: 8x16 tiles, B panels hold the tile + k//2 halo and every tap re-reads them in place
@@ -118,6 +119,7 @@ void wgrad_pick_buffers(int dtype, int bpanels, int b_panel_bytes, int* a_bufs, 
 int wgrad_pair_supported(int dtype, int hc4, int cx_pad, int ncols, int ksize);
 int wgrad_pair_panel_width(int cx_pad, int ncols);          // channels per B panel of the pair kernel: 16 / 32 / 64
 int wgrad_pair_b_stages(int cx_pad, int ncols, int ksize);  // B stages that fit (0: pair kernel not possible)
+int wgrad_pair_b_stages_tf32(int n_mma, int ksize);         // same for the tf32 variant (32-channel fp32 panels)
 cudaError_t launch_wgrad(int dtype, const WgradParams& p, cudaStream_t stream);
 
 // ---- pointwise / layout kernels (nint_pointwise.cu)

@@ -336,12 +336,14 @@ constexpr int kWgPairABufs = 3;   // the issuer awaits tile i+1 before issuing t
 constexpr int kWgPairAPanel = kTilePixels * 128;   // 64 q x 128 px bf16 = 16 KiB
 constexpr int kWgPairThreads = 288;                // 9 warps: warp 8 is the second MMA issuer
 
-__host__ __device__ static inline int wgp_b_panel_bytes(int ksize, int pw) {
+__host__ __device__ static inline int wgp_b_panel_bytes(int ksize, int pw, int esize = 2) {
   const int rows = (8 + (ksize & ~1)) * (16 + (ksize & ~1));
-  return (rows * pw * 2 + 1023) & ~1023;
+  return (rows * pw * esize + 1023) & ~1023;
 }
-static inline int wgp_smem_bytes(int half_cols, int ksize, int pw, int b_stages) {
-  return 1024 + kWgPairABufs * 2 * kWgPairAPanel + b_stages * (half_cols / pw) * wgp_b_panel_bytes(ksize, pw) + 1024 + kWgCtrlBytes;
+// bf16: three A buffers of 2 x 16 KiB panels; tf32: two A buffers of 4 x 16 KiB panels (32 q x 4 B rows)
+static inline int wgp_smem_bytes(int half_cols, int ksize, int pw, int b_stages, int esize = 2) {
+  const int a_bytes = esize == 2 ? kWgPairABufs * 2 * kWgPairAPanel : 2 * 4 * kWgPairAPanel;
+  return 1024 + a_bytes + b_stages * (half_cols / pw) * wgp_b_panel_bytes(ksize, pw, esize) + 1024 + kWgCtrlBytes;
 }
 // widest B panel (channels) that tiles both CTAs' halves of N and does not straddle the x / h boundary
 int wgrad_pair_panel_width(int cx_pad, int ncols) {
@@ -356,9 +358,25 @@ int wgrad_pair_b_stages(int cx_pad, int ncols, int ksize) {
     if (wgp_smem_bytes(ncols / 2, ksize, pw, st) <= 227 * 1024) return st;
   return 0;
 }
+// tf32 variant: 32-channel fp32 panels (SWIZZLE_128B_ATOM_32B), N rounded up to two whole panels per CTA
+int wgrad_pair_b_stages_tf32(int n_mma, int ksize) {
+  for (int st = kWgPairMaxBStages; st >= 2; --st)
+    if (wgp_smem_bytes(n_mma / 2, ksize, 32, st, 4) <= 227 * 1024) return st;
+  return 0;
+}
 
+template <int DT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kWgPairThreads, 1)
 wgrad_pair_kernel(const __grid_constant__ WgradParams p) {
+  // bf16: A = 2 panels of 64 q (SWIZZLE_128B), K step = 16 pixels = two tile rows.  tf32: A = 4 panels of 32 q and
+  // B = 32-channel panels, both SWIZZLE_128B_ATOM_32B with 4-pixel groups 512 B apart (as the single-CTA kernel),
+  // K step = 8 pixels = one tile row, twice as many MMAs at the same cycles each.
+  constexpr bool BF = DT == NINT_BF16;
+  constexpr int A_PANELS = BF ? 2 : 4;
+  constexpr int A_PANEL_COLS = BF ? 64 : 32;
+  constexpr int KSTEPS = BF ? 8 : 16;
+  constexpr uint32_t A_KSTEP16 = BF ? 128u : 64u;      // A advance per K step in 16-byte units
+  constexpr int ESIZE = BF ? 2 : 4;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
@@ -366,18 +384,19 @@ wgrad_pair_kernel(const __grid_constant__ WgradParams p) {
   const uint32_t crank = __shfl_sync(0xffffffffu, cluster_ctarank(), 0);
   const bool lead_cta = crank == 0;
   const int pw = p.b_pw;                                      // channels per B panel (16 / 32 / 64)
-  const int rowb = pw * 2;                                    // bytes per pixel row of a B panel
-  const int bp_all = (p.nchunks_b[0] + p.nchunks_b[1]) * 32 / pw;   // panels of the concatenated input
+  const int rowb = pw * ESIZE;                                // bytes per pixel row of a B panel
+  const int bp_all = p.acc_cols / pw;                         // panels of the concatenated input (tf32: + a zero panel)
   const int bp_cta = bp_all / 2;                              // this CTA's half of N
   const int bx16 = p.nchunks_b[0] * 32 / pw;                  // panels that come from the x tensor
-  const int b_panel = wgp_b_panel_bytes(p.ksize, pw);
+  const int b_panel = wgp_b_panel_bytes(p.ksize, pw, ESIZE);
   const int nbs = p.b_stages;
-  const int a_buf_bytes = 2 * kWgPairAPanel;
+  const int nab = p.a_bufs;
+  constexpr int a_buf_bytes = A_PANELS * kWgPairAPanel;
   const int b_stage_bytes = bp_cta * b_panel;
   const int hpitch = 8 + (p.ksize & ~1);
   const int hrows = hpitch * (16 + (p.ksize & ~1));
   uint8_t* sA = smem;
-  uint8_t* sB = sA + kWgPairABufs * a_buf_bytes;
+  uint8_t* sB = sA + nab * a_buf_bytes;
   uint8_t* sOnes = sB + nbs * b_stage_bytes;
   uint8_t* ctrl = sOnes + 1024;
   uint64_t* a_full = reinterpret_cast<uint64_t*>(ctrl);
@@ -459,10 +478,11 @@ wgrad_pair_kernel(const __grid_constant__ WgradParams p) {
         if (lead_cta) mbar_arrive_expect_tx(&a_full[ab], static_cast<uint32_t>(2 * a_buf_bytes));
         const uint32_t bar = mapa_rank(smem_u32(&a_full[ab]), 0);
         const int q0 = mb * 256 + static_cast<int>(crank) * 128;
-        tma_load_5d_pair(sA + ab * a_buf_bytes, &p.tmap_dg, bar, q0, x0, y0, b, t);
-        tma_load_5d_pair(sA + ab * a_buf_bytes + kWgPairAPanel, &p.tmap_dg, bar, q0 + 64, x0, y0, b, t);
+#pragma unroll
+        for (int j = 0; j < A_PANELS; ++j)
+          tma_load_5d_pair(sA + ab * a_buf_bytes + j * kWgPairAPanel, &p.tmap_dg, bar, q0 + j * A_PANEL_COLS, x0, y0, b, t);
       }
-      if (++ab == kWgPairABufs) {
+      if (++ab == nab) {
         ab = 0;
         aph ^= 1;
       }
@@ -509,15 +529,16 @@ wgrad_pair_kernel(const __grid_constant__ WgradParams p) {
       const bool issue_any = !(p.debug_flags & 2);
       // MN-major descriptors.  A: 64-q atoms (128-byte rows, SWIZZLE_128B) one panel apart, 8-pixel groups 1 KiB apart.
       // B: pw-channel atoms (32 / 64 / 128-byte rows, matching swizzle) one panel apart, 8-pixel groups one halo row apart.
-      const uint64_t adesc_base = make_smem_desc(0, kWgPairAPanel, 1024, 2);
-      const uint64_t bdesc_base = make_smem_desc(0, static_cast<uint32_t>(b_panel), static_cast<uint32_t>(hpitch * rowb),
-                                                 pw == 16 ? 6u : (pw == 32 ? 4u : 2u));
+      const uint64_t adesc_base = make_smem_desc(0, kWgPairAPanel, BF ? 1024u : 512u, BF ? 2u : kLayoutSw128Base32);
+      const uint64_t bdesc_base = make_smem_desc(0, static_cast<uint32_t>(b_panel),
+                                                 BF ? static_cast<uint32_t>(hpitch * rowb) : 512u,
+                                                 BF ? (pw == 16 ? 6u : (pw == 32 ? 4u : 2u)) : kLayoutSw128Base32);
       const uint64_t odesc = make_smem_desc(smem_u32(sOnes), 512, 256, 6);
       const uint32_t ahi = static_cast<uint32_t>(adesc_base >> 32), bhi = static_cast<uint32_t>(bdesc_base >> 32);
       const uint32_t alo_base = static_cast<uint32_t>(adesc_base), blo_base = static_cast<uint32_t>(bdesc_base);
       const uint32_t sA16 = smem_u32(sA) >> 4, sB16 = smem_u32(sB) >> 4;
       const int dy0 = tap_begin / ksize, dx0 = tap_begin % ksize;
-      const uint32_t krow16 = static_cast<uint32_t>((2 * hpitch * rowb) >> 4);   // one K step = two halo rows
+      const uint32_t krow16 = static_cast<uint32_t>(((BF ? 2 : 1) * hpitch * rowb) >> 4);   // one K step = two (bf16) / one (tf32) halo rows
       uint32_t tap_off[5];
 #pragma unroll
       for (int ti = 0; ti < 5; ++ti) {
@@ -526,8 +547,8 @@ wgrad_pair_kernel(const __grid_constant__ WgradParams p) {
       }
       int last_mine = -1;
       for (int i = which; i < my_tiles; i += 2) {
-        const int ab = i % kWgPairABufs, bs = i % nbs;
-        const uint32_t aph = static_cast<uint32_t>(i / kWgPairABufs) & 1u, bph = static_cast<uint32_t>(i / nbs) & 1u;
+        const int ab = i % nab, bs = i % nbs;
+        const uint32_t aph = static_cast<uint32_t>(i / nab) & 1u, bph = static_cast<uint32_t>(i / nbs) & 1u;
         mbar_wait(&a_full[ab], aph);
         mbar_wait(&b_full[bs], bph);
         spin_until_at_least(mma_issued, static_cast<uint32_t>(i));   // the other warp has issued all of tile i-1
@@ -541,30 +562,30 @@ wgrad_pair_kernel(const __grid_constant__ WgradParams p) {
           if (ntaps <= 5) {
             // per-tap B offsets are loop invariants: the MMA stream is adds + tcgen05.mma only
 #pragma unroll 2
-            for (int ks = 0; ks < 8; ++ks) {
-              // K step = 16 pixels = 2 tile rows: A advances 16 x 128 B, B two halo rows
-              const uint32_t alo = a0 + static_cast<uint32_t>(ks * 128);
+            for (int ks = 0; ks < KSTEPS; ++ks) {
+              // K step = 16 pixels = 2 tile rows: A advances 16 x 128 B, B two halo rows (tf32: 8 pixels, one row)
+              const uint32_t alo = a0 + static_cast<uint32_t>(ks) * A_KSTEP16;
               const uint32_t bk = b0 + static_cast<uint32_t>(ks) * krow16;
               uint32_t d = tmem_base;
 #pragma unroll
               for (int ti = 0; ti < 5; ++ti) {
-                if (ti < ntaps) umma_lohi<NINT_BF16, true>(d, alo, ahi, bk + tap_off[ti], bhi, idesc, acc);
+                if (ti < ntaps) umma_lohi<DT, true>(d, alo, ahi, bk + tap_off[ti], bhi, idesc, acc);
                 d += ncols;
               }
-              if (do_bias)
-                umma_lohi<NINT_BF16, true>(tmem_base + static_cast<uint32_t>(ntaps) * ncols, alo, ahi,
+              if (BF && do_bias)
+                umma_lohi<DT, true>(tmem_base + static_cast<uint32_t>(ntaps) * ncols, alo, ahi,
                                            static_cast<uint32_t>(odesc), static_cast<uint32_t>(odesc >> 32), idesc_bias, acc);
               acc = 1;
             }
           } else {
 #pragma unroll 1
-            for (int ks = 0; ks < 8; ++ks) {
-              const uint32_t alo = a0 + static_cast<uint32_t>(ks * 128);
-              uint32_t blo = b0 + static_cast<uint32_t>((((2 * ks + dy0) * hpitch + dx0) * rowb) >> 4);
+            for (int ks = 0; ks < KSTEPS; ++ks) {
+              const uint32_t alo = a0 + static_cast<uint32_t>(ks) * A_KSTEP16;
+              uint32_t blo = b0 + static_cast<uint32_t>(((((BF ? 2 : 1) * ks + dy0) * hpitch + dx0) * rowb) >> 4);
               uint32_t d = tmem_base;
               int dx = dx0;
               for (int ti = 0; ti < ntaps; ++ti) {
-                umma_lohi<NINT_BF16, true>(d, alo, ahi, blo, bhi, idesc, acc);
+                umma_lohi<DT, true>(d, alo, ahi, blo, bhi, idesc, acc);
                 d += ncols;
                 blo += static_cast<uint32_t>(rowb >> 4);
                 if (++dx == ksize) {
@@ -572,8 +593,8 @@ wgrad_pair_kernel(const __grid_constant__ WgradParams p) {
                   blo += static_cast<uint32_t>(((hpitch - ksize) * rowb) >> 4);
                 }
               }
-              if (do_bias)
-                umma_lohi<NINT_BF16, true>(d, alo, ahi, static_cast<uint32_t>(odesc), static_cast<uint32_t>(odesc >> 32),
+              if (BF && do_bias)
+                umma_lohi<DT, true>(d, alo, ahi, static_cast<uint32_t>(odesc), static_cast<uint32_t>(odesc >> 32),
                                            idesc_bias, acc);
               acc = 1;
             }
@@ -599,7 +620,7 @@ wgrad_pair_kernel(const __grid_constant__ WgradParams p) {
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
     for (int ti = 0; ti < ntaps; ++ti) {
       float* dst = p.dw_acc + (static_cast<long long>(tap_begin + ti) * p.hc4 + q) * p.ncols + p.col0;
-      for (int c0 = 0; c0 < p.acc_cols; c0 += 16) {
+      for (int c0 = 0; c0 < p.real_cols; c0 += 16) {   // columns beyond real_cols are the tf32 variant's zero panel
         float v[16];
         tmem_ld16(taddr + ti * p.acc_cols + c0, v);
         tmem_ld_wait();
@@ -628,17 +649,18 @@ int wgrad_pair_supported(int dtype, int hc4, int cx_pad, int ncols, int ksize) {
   return wgrad_pair_b_stages(cx_pad, ncols, ksize) >= 2;
 }
 
+template <int DT>
 static cudaError_t launch_wg_pair(const WgradParams& p, cudaStream_t stream) {
-  const int smem = wgp_smem_bytes((p.nchunks_b[0] + p.nchunks_b[1]) * 16, p.ksize, p.b_pw, p.b_stages);
+  const int smem = wgp_smem_bytes(p.acc_cols / 2, p.ksize, p.b_pw, p.b_stages, DT == NINT_BF16 ? 2 : 4);
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(wgrad_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(wgrad_pair_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     configured = true;
   }
   const int grid = 2 * p.group_unit0[p.n_groups];
   if (grid <= 0) return cudaSuccess;
-  wgrad_pair_kernel<<<grid, kWgPairThreads, smem, stream>>>(p);
+  wgrad_pair_kernel<DT><<<grid, kWgPairThreads, smem, stream>>>(p);
   return cudaGetLastError();
 }
 
@@ -659,7 +681,7 @@ static cudaError_t launch_wg(const WgradParams& p, cudaStream_t stream) {
 }
 
 cudaError_t launch_wgrad(int dtype, const WgradParams& p, cudaStream_t stream) {
-  if (p.pair) return launch_wg_pair(p, stream);
+  if (p.pair) return dtype == NINT_BF16 ? launch_wg_pair<NINT_BF16>(p, stream) : launch_wg_pair<NINT_TF32>(p, stream);
   if (dtype == NINT_BF16) return launch_wg<__nv_bfloat16>(p, stream);
   return launch_wg<float>(p, stream);
 }
