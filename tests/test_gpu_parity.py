@@ -104,7 +104,7 @@ def test_twelve_step_rollout_against_oracle(precision, ksize):
     Forward: pred vs the oracle.  Backward: BPTT of the SAME upstream gradient -- d(MSE+L1)/dpred taken
     at the oracle's prediction -- because L1Loss's sign(pred - y) is discontinuous: a 1e-4 difference in
     pred flips the sign at a pixel or two and moves a weight gradient by ~2/sqrt(#pixels) ~ 1e-2, which
-    says nothing about the kernels (measured: tools/parity_report.py)."""
+    says nothing about the kernels (measured: tests/tools/parity_report.py)."""
     from nasa_niswan_b200 import ConvLSTM
     torch.manual_seed(0)
     B, T, C, H, W, hc = 2, 12, 21, 90, 144, 64

@@ -1,4 +1,4 @@
-"""Re-run one fuzz case with per-parameter errors: python tools/fuzz_one.py B T C H W "h1,h2" "k1,k2" precision seed"""
+"""Re-run one fuzz case with per-parameter errors: python tests/tools/fuzz_one.py B T C H W "h1,h2" "k1,k2" precision seed"""
 import os
 import sys
 

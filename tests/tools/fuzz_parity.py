@@ -6,9 +6,9 @@ This is a bug finder, not the parity gate: the bars (2e-2 bf16, 1e-3 tf32) are d
 the 90x144 grid, where gradients are long, coherent sums.  Tiny random cases have ill-conditioned gradients (a bias
 gradient is a plain sum of a few hundred signed terms that nearly cancel, so the 2^-9 rounding of the stored gates
 shows up amplified: 2e-2..8e-2 in bf16); such cases are listed as "marginal" and reproduce bit-for-bit the same
-error in the CTA-pair and the single-CTA kernels (tools/fuzz_one.py), while an indexing bug gives errors of O(1).
+error in the CTA-pair and the single-CTA kernels (tests/tools/fuzz_one.py), while an indexing bug gives errors of O(1).
 
-    python tools/fuzz_parity.py [n_cases] [seed]
+    python tests/tools/fuzz_parity.py [n_cases] [seed]
 """
 import os
 import random

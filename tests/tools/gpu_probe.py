@@ -1,8 +1,8 @@
 """Stage-by-stage diagnostic of the CUDA path against torch fp32 references (run on the GPU box).
 
-    python tools/gpu_probe.py            # runs every stage in its own process (a CUDA fault in one
+    python tests/tools/gpu_probe.py            # runs every stage in its own process (a CUDA fault in one
                                          # stage must not poison the others)
-    python tools/gpu_probe.py STAGE ...  # run the named stage(s) in-process
+    python tests/tools/gpu_probe.py STAGE ...  # run the named stage(s) in-process
 """
 import os
 import subprocess
