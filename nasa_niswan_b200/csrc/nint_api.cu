@@ -372,7 +372,7 @@ int cell_step(nint_plan* p, int l, int t, int epi, float* raw_out, cudaStream_t 
   g.raw_out = raw_out;
   if (conv_halo_plan(epi, p->dtype, g)) return fail("layer %d: the conv kernel's shared-memory plan does not fit (hidden %d, k %d)", l, y.hc, y.k);
   for (int i = 0; i < g.nseg; ++i)
-    if (get_w_map(p, y, g.seg[i].wsel, g.n_tile, g.n_tile / g.cluster, g.taps_per_stage, &g.seg[i].tmap_w)) return 1;
+    if (get_w_map(p, y, g.seg[i].wsel, g.n_tile, g.n_tile / g.cluster, g.seg[i].ts, &g.seg[i].tmap_w)) return 1;
   LAUNCH(p, (epi == EPI_FWD ? K_FWD : K_OTHER), st, launch_conv_halo(epi, p->dtype, g, p->num_sms, st));
   return 0;
 }
@@ -870,7 +870,7 @@ int nint_backward_bptt(nint_plan* p, const float* dpred, const float* dseq, floa
           if (conv_halo_plan(EPI_BWD, p->dtype, g)) return fail("layer %d: the dgrad kernel's shared-memory plan does not fit (hidden %d, k %d)", l, y.hc, y.k);
       for (int i = 0; i < g.nseg; ++i) {
         Layer& owner = g.seg[i].wsel == 2 ? p->layer[l + 1] : y;   // wdx belongs to the layer above
-        if (get_w_map(p, owner, g.seg[i].wsel, g.n_tile, g.n_tile / g.cluster, g.taps_per_stage, &g.seg[i].tmap_w)) return 1;
+        if (get_w_map(p, owner, g.seg[i].wsel, g.n_tile, g.n_tile / g.cluster, g.seg[i].ts, &g.seg[i].tmap_w)) return 1;
       }
       LAUNCH(p, K_BWD, st, launch_conv_halo(EPI_BWD, p->dtype, g, p->num_sms, st));
     }

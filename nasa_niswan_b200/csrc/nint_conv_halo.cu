@@ -212,10 +212,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
             pa ^= 1;
           }
           if (!do_w || (resident && !first)) continue;   // resident weights are loaded once
-          for (int tap0 = 0; tap0 < taps; tap0 += TS) {   // TS divides taps (conv_halo_plan)
+          for (int tap0 = 0; tap0 < taps; tap0 += sg.ts) {   // sg.ts divides taps (conv_halo_plan)
             if (!resident) mbar_wait(&w_empty[iw], pw ^ 1);
             if (leader) {
-              if (lead_cta) mbar_arrive_expect_tx(&w_full[iw], static_cast<uint32_t>(stage_bytes * S));
+              if (lead_cta) mbar_arrive_expect_tx(&w_full[iw], static_cast<uint32_t>(sg.ts * w_bytes * S));
               uint8_t* dst = sW + iw * stage_bytes;   // a weight stage is ONE box (all TS taps)
               if constexpr (pair)
                 tma_load_3d_pair(dst, &sg.tmap_w, mapa_rank(smem_u32(&w_full[iw]), 0), 0, static_cast<int>(crank) * w_rows, wtap + tap0);
@@ -331,7 +331,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
       const bool lookahead = NA >= 3;
       // streaming weights with one stage per chunk: the next chunk's stage is awaited ahead as well
       bool single_stage = true;
-      for (int s = 0; s < nseg; ++s) single_stage = single_stage && (TS == p.seg[s].ksize * p.seg[s].ksize);
+      for (int s = 0; s < nseg; ++s) single_stage = single_stage && (p.seg[s].ts == p.seg[s].ksize * p.seg[s].ksize);
       const bool w_ahead = lookahead && !resident && NW >= 3 && single_stage;
       if (valid && lookahead) {
         mbar_wait(&tempty_bar[abuf], aphase ^ 1);
@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
         // 3x3 single-stage chunks take these waits BETWEEN the tap rows of the MMA stream (fast path below): the
         // issuing thread only runs a few MMAs ahead of the tensor pipe, so a 300-cycle block of waits between two
         // chunks idles the pipe, while three ~100-cycle pieces hide behind the rows already issued
-        const bool fast = lookahead && issue_any && p.seg[cs].ksize == 3 && TS == 9 && G == 2 && (resident || w_ahead);
+        const bool fast = lookahead && issue_any && p.seg[cs].ksize == 3 && p.seg[cs].ts == 9 && G == 2 && (resident || w_ahead);
         tr.stamp();
         if (lookahead && !fast) {
           if (nvalid) {
@@ -446,7 +446,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
             pw ^= 1;
           }
         } else
-        for (int tap0 = 0; tap0 < taps; tap0 += TS) {
+        for (int tap0 = 0, tsc = p.seg[cs].ts; tap0 < taps; tap0 += tsc) {   // tsc: taps per weight stage of this segment
           if ((!resident || first) && !w_ahead) {
             mbar_wait(&w_full[iw], pw);
             tc_fence_after();
@@ -460,7 +460,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
             int dxl = dx;
             if (G == 1) {
 #pragma unroll 3
-              for (int j = 0; j < TS; ++j) {
+              for (int j = 0; j < tsc; ++j) {
                 umma_lohi<DT, pair>(d_tmem, alo, ahi, blo, bhi, idesc, accumulate);
                 umma_lohi<DT, pair>(d_tmem, alo + 2, ahi, blo + 2, bhi, idesc, 1u);
                 accumulate = 1;
@@ -475,7 +475,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
               const uint32_t halo16l = static_cast<uint32_t>(a_halo16);
               const uint32_t d1 = d_tmem + n_tile;
 #pragma unroll 3
-              for (int j = 0; j < TS; ++j) {
+              for (int j = 0; j < tsc; ++j) {
                 umma_lohi<DT, pair>(d_tmem, alo, ahi, blo, bhi, idesc, accumulate);
                 umma_lohi<DT, pair>(d1, alo + halo16l, ahi, blo, bhi, idesc, accumulate);
                 umma_lohi<DT, pair>(d_tmem, alo + 2, ahi, blo + 2, bhi, idesc, 1u);
@@ -490,7 +490,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
               }
             } else {
               const uint32_t halo16l = static_cast<uint32_t>(a_halo16);
-              for (int j = 0; j < TS; ++j) {
+              for (int j = 0; j < tsc; ++j) {
                 uint32_t a2 = alo;
                 uint32_t d = d_tmem;
                 for (int g = 0; g < G; ++g, a2 += halo16l, d += n_tile) {
@@ -515,8 +515,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
             pw ^= 1;
           }
           // advance the warp-uniform descriptor past this stage's TS taps
-          const int adv = dx + TS;
-          adesc += static_cast<uint64_t>(TS * (kChunkBytes >> 4)) + static_cast<uint64_t>(adv / ks) * row_skip;
+          const int adv = dx + tsc;
+          adesc += static_cast<uint64_t>(tsc * (kChunkBytes >> 4)) + static_cast<uint64_t>(adv / ks) * row_skip;
           dx = adv % ks;
         }
         umma_commit_elect<pair>(&a_empty[ia]);
@@ -614,6 +614,7 @@ int conv_halo_plan(int epi, int dtype, ConvGemmParams& p) {
         p.a_buf_bytes = p.a_halo_bytes;
         p.na_bufs = static_cast<int>(rem / p.a_halo_bytes) > 6 ? 6 : static_cast<int>(rem / p.a_halo_bytes);
         p.taps_per_stage = ts;
+        for (int s = 0; s < p.nseg; ++s) p.seg[s].ts = ts;
         p.num_stages = n_st;
         p.acc_cols = p.n_tile;
         p.n_acc = 512 / p.acc_cols > kMaxAcc ? kMaxAcc : 512 / p.acc_cols;
@@ -632,9 +633,19 @@ int conv_halo_plan(int epi, int dtype, ConvGemmParams& p) {
   // ~450-750 cycles of its producer warp, so a stage should carry all taps of a chunk when it fits
   int want = (1536 + p.n_tile - 1) / p.n_tile;
   if (want > max_k * max_k) want = max_k * max_k;
-  auto divides_all = [&](int cand) {
-    for (int s = 0; s < p.nseg; ++s) if ((p.seg[s].ksize * p.seg[s].ksize) % cand) return false;
-    return true;
+  // per segment: the largest divisor of its tap count that is <= cand (segments of one launch can have different
+  // kernel sizes -- the dgrad of a layer reads its own dgates through k_l and the layer above's through k_{l+1});
+  // a stage is sized for the largest of them
+  auto seg_ts = [&](int s, int cand) {
+    const int taps = p.seg[s].ksize * p.seg[s].ksize;
+    int t = cand < taps ? cand : taps;
+    while (taps % t) --t;
+    return t;
+  };
+  auto stage_ts = [&](int cand) {
+    int m = 1;
+    for (int s = 0; s < p.nseg; ++s) if (seg_ts(s, cand) > m) m = seg_ts(s, cand);
+    return m;
   };
   // preference order: >= 3 halo buffers (the MMA issuer waits one chunk ahead) with 3 weight stages of `want` taps,
   // first with three epilogue stages then two; after that relax the tap count, then the group size, then the buffers
@@ -643,13 +654,14 @@ int conv_halo_plan(int epi, int dtype, ConvGemmParams& p) {
   const int ns_hi = (p.plan_ns >= ns_min && p.plan_ns <= ns_max) ? p.plan_ns : ns_max;
   for (int pass = 0; pass < 2 && NS < 0; ++pass, min_na = 2)
     for (int cand = want; cand >= 1 && NS < 0; --cand) {
-      if (!divides_all(cand)) continue;
+      if (cand < want && stage_ts(cand) == stage_ts(cand + 1)) continue;   // same plan as the previous candidate
       for (int g = gmax; g >= 1 && NS < 0; --g)
         for (int ns = ns_hi; ns >= ns_min; --ns)
-          if (total - ns * p.e_stage_bytes >= min_na * g * p.a_halo_bytes + 3 * cand * w_bytes) {
+          if (total - ns * p.e_stage_bytes >= min_na * g * p.a_halo_bytes + 3 * stage_ts(cand) * w_bytes) {
             NS = ns;
             G = g;
-            ts = cand;
+            ts = stage_ts(cand);
+            for (int s = 0; s < p.nseg; ++s) p.seg[s].ts = seg_ts(s, cand);
             break;
           }
     }

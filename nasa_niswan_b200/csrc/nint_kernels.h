@@ -30,6 +30,7 @@ struct alignas(64) ConvSegment {
   int ksize;
   int nchunks;
   int wsel;   // host only: which packed weight tensor of the layer (nint_api.cu get_w_map)
+  int ts;     // taps per weight stage of THIS segment (divides ksize^2; conv_halo_plan); taps_per_stage is the largest
 };
 
 struct alignas(64) ConvGemmParams {
