@@ -63,7 +63,7 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.25)
         self.proc.terminate()
-        sm, smax, reasons = [], None, set()
+        sm, smax, reasons, watts = [], None, set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             try:
@@ -71,12 +71,17 @@ class ClockSampler:
                 smax = float(r[1])
             except (ValueError, IndexError):
                 continue
+            try:
+                watts.append(float(r[2]))
+            except (ValueError, IndexError):
+                pass
             for n, v in zip(names, r[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
         sm.sort()
+        watts.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "power_w": watts[len(watts) // 2] if watts else None}
 
 
 def cpu_oracle_run(batch, T, k, steps, warmup, threads):
