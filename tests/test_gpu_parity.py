@@ -511,3 +511,44 @@ def test_checkpoint_moves_between_native_and_torch_adam(tmp_path):
     assert tr2.optimizer.step_count == 1
     l1, l2 = float(tr.step(x, y)), float(tr2.step(x, y))
     assert l1 == pytest.approx(l2, rel=1e-5)
+
+
+def _ddp_worker(rank, world, port, out):
+    import torch.distributed as dist
+    from torch.nn.parallel import DistributedDataParallel as DDP
+    from nasa_niswan_b200 import ConvLSTM
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)   # both ranks share cuda:0 here; gloo moves CUDA tensors
+    torch.manual_seed(21)
+    net = ConvLSTM(5, [16, 16], [3, 3], 2, precision="tf32").cuda()
+    ddp = DDP(net)
+    torch.manual_seed(22)
+    X, Y = torch.randn(4, 3, 5, 12, 20), torch.randn(4, 12, 20)
+    a, b = rank * 2, rank * 2 + 2
+    pred = ddp(X[a:b].cuda())
+    F.mse_loss(pred.squeeze(1), Y[a:b].cuda()).backward()
+    if rank == 0:
+        torch.save({k: p.grad.cpu() for k, p in net.named_parameters()}, out)
+    dist.destroy_process_group()
+
+
+def test_distributed_data_parallel_wrapper(tmp_path):
+    """the dispatcher op is an ordinary autograd node, so torch's DistributedDataParallel (gradient
+    hooks, bucketed all-reduce) works on the module unchanged: 2 ranks x 2 samples == the 4-sample gradient"""
+    import socket
+    import torch.multiprocessing as mp
+    from nasa_niswan_b200 import ConvLSTM
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    out = str(tmp_path / "ddp.pt")
+    mp.spawn(_ddp_worker, args=(2, port, out), nprocs=2, join=True)
+    got = torch.load(out)
+    torch.manual_seed(21)
+    net = ConvLSTM(5, [16, 16], [3, 3], 2, precision="tf32").cuda()
+    torch.manual_seed(22)
+    X, Y = torch.randn(4, 3, 5, 12, 20), torch.randn(4, 12, 20)
+    F.mse_loss(net(X.cuda()).squeeze(1), Y.cuda()).backward()
+    for k, p in net.named_parameters():
+        assert O.max_abs_normalised(got[k], p.grad.cpu()) < 1e-4, k
