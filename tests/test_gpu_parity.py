@@ -513,6 +513,30 @@ def test_checkpoint_moves_between_native_and_torch_adam(tmp_path):
     assert l1 == pytest.approx(l2, rel=1e-5)
 
 
+def test_cuda_graph_capture_of_the_forward():
+    """everything the op does is stream-ordered (kernels, memsets, TMA descriptors built on the host), so an
+    inference rollout can be captured in a CUDA graph and replayed on new input"""
+    from nasa_niswan_b200 import ConvLSTM
+    torch.manual_seed(14)
+    net = ConvLSTM(5, [32], [3], 1, precision="bf16").cuda().eval()
+    x = torch.randn(2, 4, 5, 24, 32, device="cuda")
+    with torch.no_grad():
+        first = net(x).clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            net(x)
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = net(x)
+        x.copy_(torch.randn_like(x))
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(out, net(x))
+        assert not torch.equal(out, first)
+
+
 def _ddp_worker(rank, world, port, out):
     import torch.distributed as dist
     from torch.nn.parallel import DistributedDataParallel as DDP
