@@ -36,12 +36,23 @@ typedef struct nint_config {
   int32_t batch, seq_len, height, width; /* B, T, H, W of x (model.py:255) */
   int32_t in_channels;                   /* C */
   int32_t num_layers;                    /* L <= NINT_MAX_LAYERS */
-  int32_t hidden[NINT_MAX_LAYERS];       /* Hc_l: multiple of 16; multiple of 64 when > 64; <= 256 */
+  int32_t hidden[NINT_MAX_LAYERS];       /* Hc_l: any size in [1, 256] (model.py:207 takes any int); run internally padded
+                                            to a multiple of 16 (64 above 64) with zero weights: results unchanged */
   int32_t ksize[NINT_MAX_LAYERS];        /* odd (model.py:204: padding = k // 2) */
   int32_t dtype;                         /* NINT_DTYPE_* */
   int32_t training;                      /* 1: keep gates/c/h of every step for BPTT */
   int32_t return_sequence;               /* 1: also apply the head at every t (model.py:264,272) */
+  int32_t flags;                         /* NINT_FLAG_* */
 } nint_config;
+
+/* NINT_FLAG_DETERMINISTIC: gradients are bit-reproducible run to run (utils.py:77-88 asks cuDNN for the same): split-K
+ * partial sums go to per-split buffers and are reduced in a fixed order instead of fp32 atomics.
+ * NINT_FLAG_INPUT_GRAD: training plans also keep what nint_backward_input / nint_cell_backward need (the reference's
+ * autograd yields x.grad and the gradient w.r.t. an explicit initial state, model.py:216-231). */
+#define NINT_FLAG_DETERMINISTIC 1
+#define NINT_FLAG_INPUT_GRAD 2
+#define NINT_X_FP32 0
+#define NINT_X_BF16 1
 
 int nint_version(void);
 const char* nint_last_error(void);
@@ -71,6 +82,24 @@ int nint_plan_get_state(nint_plan* plan, int layer, float* h, float* c, void* st
 /* ---- ConvLSTM.forward (model.py:253-274): T x L fused cell steps + head.
  * pred [B,1,H,W]; seq [B,T,H,W] or NULL (requires return_sequence). */
 int nint_forward(nint_plan* plan, const float* x, float* pred, float* seq, void* stream);
+/* The same with x [B,T,C,H,W] given as bf16 (x_dtype = NINT_X_BF16; bf16 plans only): a host loader that stages its
+ * windows in bf16 halves the host-to-device bytes of train.py:92, and the values the tensor cores see are identical
+ * (the fp32 path rounds x to bf16 as it packs it). */
+int nint_forward_ex(nint_plan* plan, const void* x, int x_dtype, float* pred, float* seq, void* stream);
+
+/* ---- frame bank: the B200 form of dataset.py:551-637 (E33OMA90D_CRNN keeps the whole record in RAM and makes its
+ * windows with sliding_window_view, consecutive windows sharing T-1 frames).  Here the record lives once in HBM in the
+ * model's own operand layout -- bank [n_frames][H][W][c_pad] of bf16 (bf16 plans) or tf32-rounded fp32, channels-last,
+ * padding lanes zero except lane `ones_lane` = 1.0 (nint_plan_input_layout) -- and a batch is B window start indices:
+ * sample b reads frames win_start[b] .. win_start[b] + T - 1 straight through the TMA descriptors (no per-step copy or
+ * packing pass).  win_start: device int32 [B]; it and the bank must stay valid until the backward of the step is
+ * queued.  nint_pack_frames builds a bank from frames [n_frames,C,H,W] (fp32 or bf16); nint_fuse_inputs_bank builds it
+ * from the raw fields (below). */
+int nint_plan_input_layout(const nint_plan* plan, int* c_pad, int* ones_lane, int* elem_bytes);
+int nint_pack_frames(int dtype, const void* frames, int x_dtype, long long n_frames, int channels, int height, int width,
+                     int c_pad, int ones_lane, void* bank, void* stream);
+int nint_forward_bank(nint_plan* plan, const void* bank, long long n_frames, const int* win_start, float* pred,
+                      float* seq, void* stream);
 
 /* ---- BPTT of the last nint_forward (replaces autograd over model.py:216-274, train.py:109).
  * dpred [B,1,H,W], dseq [B,T,H,W] or NULL.  grad_weight[l] / grad_bias[l] are host arrays of
@@ -84,6 +113,18 @@ int nint_backward(nint_plan* plan, const float* dpred, const float* dseq, float*
 int nint_backward_bptt(nint_plan* plan, const float* dpred, const float* dseq, float* grad_head_weight,
                        float* grad_head_bias, void* stream);
 int nint_backward_wgrad(nint_plan* plan, int layer, float* grad_weight, float* grad_bias, void* stream);
+/* Gradient w.r.t. the input, dx [B,T,C,H,W] fp32 (x.grad of the reference's autograd through model.py:219-220); after
+ * nint_backward_bptt, plans created with NINT_FLAG_INPUT_GRAD. */
+int nint_backward_input(nint_plan* plan, float* dx, void* stream);
+
+/* ---- ConvLSTMCell as a differentiable unit (model.py:216-231): one step from an explicit state, and its backward.
+ * Plans with seq_len = 1, num_layers = 1, training = 1, NINT_FLAG_INPUT_GRAD.  nint_cell_forward = set_state + one
+ * fused step + get_state; nint_cell_backward takes dL/dh', dL/dc' [B,Hc,H,W] (either may be NULL = zero) and writes
+ * dx [B,C,H,W], dh, dc [B,Hc,H,W], grad_weight, grad_bias (any output may be NULL). */
+int nint_cell_forward(nint_plan* plan, const float* x, const float* h, const float* c, float* h_out, float* c_out,
+                      void* stream);
+int nint_cell_backward(nint_plan* plan, const float* dh_out, const float* dc_out, float* dx, float* dh, float* dc,
+                       float* grad_weight, float* grad_bias, void* stream);
 
 /* ---- preprocessing fusion (north-star item 4).  Stacks the first `levels` model
  * levels of a 3-D forcing levels3d [frames,levels,H,W] with the 2-D emission field emis2d [frames,H,W] as the last
@@ -97,6 +138,12 @@ int nint_backward_wgrad(nint_plan* plan, int layer, float* grad_weight, float* g
 int nint_fuse_inputs(const float* levels3d, const float* emis2d, const float* mean, const float* std,
                      const float* statics, int n_static, long long frames, int levels, int height, int width,
                      int padded_height, int padded_width, int mode, float* out, void* stream);
+/* The same fusion written straight into the frame-bank layout (dtype = NINT_DTYPE_*): bank
+ * [frames][padded_height][padded_width][c_pad], no fp32 NCHW intermediate, no second packing pass. */
+int nint_fuse_inputs_bank(const float* levels3d, const float* emis2d, const float* mean, const float* std,
+                          const float* statics, int n_static, long long frames, int levels, int height, int width,
+                          int padded_height, int padded_width, int mode, int dtype, int c_pad, int ones_lane,
+                          void* bank, void* stream);
 
 /* ---- the rest of the training step (train.py:101-110), SURVEY.md section 8f rank 1.
  * nint_loss_mse_l1: loss = MSELoss(y, p) + L1Loss(y, p) (train.py:74-75,105) with p = pred[:, 0, y0:y1, x0:x1]
@@ -109,6 +156,16 @@ int nint_loss_mse_l1(const float* pred, const float* y, int batch, int height, i
                      int crop_x0, int crop_x1, float* dpred, float* loss, float* stats, void* stream);
 int nint_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr,
                    float beta1, float beta2, float eps, int step, float grad_scale, void* stream);
+/* nint_loss_mse_l1 with the targets in a bank y [n_frames, y1-y0, x1-x0]: sample b's target is frame
+ * win_start[b] + y_offset (dataset.py:600-601: y[seq_len - 1:] pairs window i with frame i + T - 1). */
+int nint_loss_mse_l1_bank(const float* pred, const float* ybank, const int* win_start, int y_offset, int batch,
+                          int height, int width, int crop_y0, int crop_y1, int crop_x0, int crop_x1, float* dpred,
+                          float* loss, float* stats, void* stream);
+/* nint_adam_step with the step count and learning rate in DEVICE memory: state = 4 floats {step, lr, -, -}; the call
+ * increments state[0] itself.  Nothing in the launch depends on host values that change between steps, so a CUDA graph
+ * of the whole training step can be replayed. */
+int nint_adam_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float* state,
+                       float beta1, float beta2, float eps, float grad_scale, void* stream);
 
 /* ---- measurement.  Kernel classes: 0 = fused gate-conv forward, 1 = dgrad + gate backward,
  * 2 = wgrad, 3 = everything else (layout packing, head, gradient unpacking); -1 = all.

@@ -1,38 +1,55 @@
 """Builds libnint.so (hand-written sm_100a kernels + C ABI) in-tree with nvcc.
 
-    python -m nasa_niswan_b200.build
+    python -m nasa_niswan_b200.build [--force] [-v]
 
 nvcc cross-compiles for sm_100a without a GPU.  The library ships next to this file so the
-snapshot taken by gpurun carries it to the GPU box.
+snapshot taken by gpurun carries it to the GPU box.  Every translation unit is compiled to an
+object file (in parallel, only when it or a header is newer) and the objects are linked into the
+shared library.
 """
 import os
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "build")
 SOURCES = ["nint_api.cu", "nint_conv_halo.cu", "nint_wgrad.cu", "nint_pointwise.cu"]
 HEADERS = ["nint_common.cuh", "nint_kernels.h", "nint_epilogue.cuh", "nint_pair.cuh", os.path.join("..", "..", "include", "nint.h")]
 LIB = os.path.join(HERE, "libnint.so")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+
+
+def _mtime(path):
+    return os.path.getmtime(path) if os.path.exists(path) else 0.0
 
 
 def _stale() -> bool:
-    if not os.path.exists(LIB):
-        return True
-    t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
+    t = _mtime(LIB)
+    return t == 0.0 or any(_mtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-           "-shared", "-Xcompiler", "-fPIC", "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    os.makedirs(OBJ, exist_ok=True)
+    hdr_time = max(_mtime(os.path.join(CSRC, h)) for h in HEADERS)
+    flags = ARCH + ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
     if verbose:
-        cmd.insert(1, "-Xptxas")
-        cmd.insert(2, "-v")
-    subprocess.run(cmd, check=True)
+        flags += ["-Xptxas", "-v"]
+
+    def compile_one(src):
+        obj = os.path.join(OBJ, src.replace(".cu", ".o"))
+        path = os.path.join(CSRC, src)
+        if force or _mtime(obj) < max(_mtime(path), hdr_time):
+            subprocess.run([nvcc] + flags + ["-c", path, "-o", obj], check=True)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as pool:
+        objs = list(pool.map(compile_one, SOURCES))
+    subprocess.run([nvcc] + ARCH + ["-shared", "-o", LIB] + objs, check=True)
     return LIB
 
 

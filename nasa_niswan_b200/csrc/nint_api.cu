@@ -61,7 +61,9 @@ struct Profile {
 };
 
 struct Layer {
-  int cin, hc, k, taps;
+  int cin, hc_real, hc, k, taps;   // cin / hc_real: the reference's channel counts (model.py:207); hc: hc_real padded to the
+                                   // kernels' granularity (16; 64 above 64) with zero weights -- results are unchanged
+  int cin_rows;                    // rows (N) of the dx dgrad operand: padded width of the tensor dx flows into
   int cx_pad, hc_pad, chx, chh;  // padded channels / 64-byte chunks of the x and h segments
   int hcb, n_blocks, n_tile;
   int nslots_h, nslots_c;
@@ -72,11 +74,12 @@ struct Layer {
   float* dC = nullptr;     // [B][H][W][hc]         (training)
   uint8_t *wx = nullptr, *wh = nullptr, *wdx = nullptr, *wdh = nullptr;
   float *bias_q = nullptr, *dw_acc = nullptr, *db_acc = nullptr;
-  size_t dw_acc_bytes = 0;
+  size_t dw_acc_bytes = 0;   // one slice [taps][4hc][ncols]; deterministic mode keeps det_splits slices
+  int det_splits = 0;
   int ncols = 0;
   CUtensorMap tm_H, tm_G;
   // weight maps depend on the launch's shared-memory plan (taps per stage): encoded on first use, cached
-  struct WMap { int ts = 0, rows = 0; CUtensorMap map; };
+  struct WMap { int ts = 0, rows = 0, n_tile = 0; CUtensorMap map; };
   std::vector<WMap> wmaps[4];   // 0: wx, 1: wh, 2: wdx, 3: wdh
   CUtensorMap tm_H_up;       // Hs[l] read as the x segment of layer l+1 (halo of k_{l+1})
   CUtensorMap tmw_H, tmw_G;  // wgrad views (32-channel boxes; differ from tm_* in tf32 mode only)
@@ -95,6 +98,10 @@ struct Layer {
   std::vector<WgBlock> wg_blocks;
   CUtensorMap tme_C, tme_H, tme_G, tme_dC;  // epilogue I/O boxes (16 | 64 channels x 8 x 16 pixels; nint_epilogue.cuh)
   bool weights_set = false;
+  // launch parameters that do not change from step to step (shared-memory plan, tensor maps, descriptors): built on
+  // first use, then only the slot indices are patched per launch.  fwd[have_state][bank], bwd[has dgates_{t+1} segment]
+  struct CachedConv { bool valid = false; ConvGemmParams g; };
+  CachedConv fwd_cache[2][2], bwd_cache[2];
 };
 
 }  // namespace
@@ -109,11 +116,25 @@ struct nint_plan {
   uint8_t* ws = nullptr;
   uint8_t* X = nullptr;  // [T][B][H][W][cx_pad0] E
   CUtensorMap tm_X, tmw_X, tmp_X;
+  // frame-bank input (nint_forward_bank): maps over the caller's [n_frames][H][W][cx_pad0] tensor, re-encoded when the
+  // bank pointer or length changes
+  bool x_bank = false;
+  const void* bank_ptr = nullptr;
+  long long bank_frames = 0;
+  const int* win_start = nullptr;
+  CUtensorMap tmb_X, tmbw_X, tmbp_X;
   float *head_w = nullptr, *head_b = nullptr;
+  float* raw = nullptr;      // NINT_FLAG_INPUT_GRAD: [B][H][W][max(cx_pad0, hc0)] fp32 dgrad dump
+  float* dh_ext = nullptr;   // NINT_FLAG_INPUT_GRAD, cell plans: upstream dL/dh' as [B][H][W][hc] fp32
+  float* head_part = nullptr;  // deterministic mode: per-block partial sums of the head gradient
   bool head_set = false;
   bool zero_init = true;
   bool fwd_done = false;
+  bool gates_valid = false; // the saved activated gates of the last forward are intact (BPTT overwrites them in place)
   bool bptt_done = false;   // dgates of the last forward are in place: nint_backward_wgrad may run
+  bool deterministic = false, input_grad = false;
+  int sub_batch = 0;        // > 0: sub-batch-major schedule (images [b0, b0 + sub_batch) run all T steps before the next
+                            // slice, so a step's recurrent operands are still in L2 when the next step reads them)
   int final_slot_h = 0, final_slot_c = 0;
   int cluster = 2;        // 2: CTA pairs (tcgen05 cta_group::2) where the layer geometry allows, 1: single CTAs
   int debug_flags = 0;
@@ -276,15 +297,25 @@ size_t carve(nint_plan* p, uint8_t* base) {
     y.bias_q = reinterpret_cast<float*>(take(4 * y.hc * 4));
     if (tr) {
       const int nch = 4 * y.hc / p->ce;
-      y.wdx = l > 0 ? take(static_cast<size_t>(y.taps) * nch * y.cin * wrow) : nullptr;
+      y.wdx = (l > 0 || p->input_grad) ? take(static_cast<size_t>(y.taps) * nch * y.cin_rows * wrow) : nullptr;
       y.wdh = take(static_cast<size_t>(y.taps) * nch * y.hc * wrow);
       y.dw_acc_bytes = static_cast<size_t>(y.taps) * 4 * y.hc * y.ncols * 4;
-      y.dw_acc = reinterpret_cast<float*>(take(y.dw_acc_bytes));
-      y.db_acc = reinterpret_cast<float*>(take(4 * y.hc * 4));
+      const size_t slices = p->deterministic ? static_cast<size_t>(y.det_splits) : 1;
+      y.dw_acc = reinterpret_cast<float*>(take(y.dw_acc_bytes * slices));
+      y.db_acc = reinterpret_cast<float*>(take(4 * y.hc * 4 * slices));
     }
   }
-  p->head_w = reinterpret_cast<float*>(take(p->layer[p->L - 1].hc * 4));
+  const Layer& top = p->layer[p->L - 1];
+  p->head_w = reinterpret_cast<float*>(take(top.hc * 4));
   p->head_b = reinterpret_cast<float*>(take(16));
+  if (tr && p->deterministic)
+    p->head_part = reinterpret_cast<float*>(take(static_cast<size_t>(head_bwd_blocks(p->B)) * (top.hc_real + 1) * 4));
+  if (tr && p->input_grad) {
+    const Layer& y0 = p->layer[0];
+    const size_t cols = y0.cin_rows > y0.hc ? y0.cin_rows : y0.hc;
+    p->raw = reinterpret_cast<float*>(take(npix * cols * 4));
+    p->dh_ext = reinterpret_cast<float*>(take(npix * y0.hc * 4));
+  }
   return off;
 }
 
@@ -299,7 +330,7 @@ void fill_common(const nint_plan* p, const Layer& y, ConvGemmParams& g) {
   memset(&g, 0, sizeof(g));
   g.debug_flags = p->debug_flags;
   g.plan_g = p->plan_g; g.plan_ns = p->plan_ns;
-  g.B = p->B; g.H = p->H; g.W = p->W;
+  g.B = p->B; g.b0 = 0; g.H = p->H; g.W = p->W;
   g.tile_w = p->tile_w; g.tile_h = p->tile_h; g.tiles_x = p->tiles_x; g.tiles_y = p->tiles_y;
   g.hc = y.hc; g.hc_pad = y.hc_pad; g.hcb = y.hcb;
 }
@@ -318,62 +349,103 @@ int bwd_cluster(const nint_plan* p, int l) {
 // (dgrad, N = n_tile input channels); `rows` = N rows per CTA, `ts` = taps per weight stage
 int get_w_map(nint_plan* p, Layer& y, int which, int n_tile, int rows, int ts, CUtensorMap* out) {
   for (const Layer::WMap& w : y.wmaps[which])
-    if (w.ts == ts && w.rows == rows) { *out = w.map; return 0; }
+    if (w.ts == ts && w.rows == rows && w.n_tile == n_tile) { *out = w.map; return 0; }
   void* base = which == 0 ? y.wx : which == 1 ? y.wh : which == 2 ? y.wdx : y.wdh;
+  if (!base) return fail("internal: packed weight tensor %d of this layer was not allocated", which);
   long long chunk_taps;
   if (which == 0) chunk_taps = (long long)y.n_blocks * y.chx * y.taps;
   else if (which == 1) chunk_taps = (long long)y.n_blocks * y.chh * y.taps;
   else chunk_taps = (long long)(4 * y.hc / p->ce) * y.taps;
   Layer::WMap w;
-  w.ts = ts; w.rows = rows;
+  w.ts = ts; w.rows = rows; w.n_tile = n_tile;
   if (encode_w_map(&w.map, p->dtype, base, chunk_taps, p->ce, n_tile, rows, ts)) return 1;
   y.wmaps[which].push_back(w);
   *out = w.map;
   return 0;
 }
 
-// one fused cell step of layer l at time t (model.py:216-231)
-int cell_step(nint_plan* p, int l, int t, int epi, float* raw_out, cudaStream_t st) {
+// images [b0, b0 + nb) of a launch (nb <= 0: the whole batch)
+inline void set_batch_range(const nint_plan* p, ConvGemmParams& g, int b0, int nb) {
+  g.b0 = nb > 0 ? b0 : 0;
+  g.B = nb > 0 ? nb : p->B;
+}
+
+// one fused cell step of layer l at time t (model.py:216-231) for images [b0, b0 + nb)
+int cell_step(nint_plan* p, int l, int t, int epi, float* raw_out, cudaStream_t st, int b0 = 0, int nb = 0) {
   Layer& y = p->layer[l];
   const bool tr = p->cfg.training != 0;
+  const bool have_state = !(t == 0 && p->zero_init);
+  const bool bank = l == 0 && p->x_bank;
+  Layer::CachedConv* cache = epi == EPI_FWD ? &y.fwd_cache[have_state ? 1 : 0][bank ? 1 : 0] : nullptr;
   ConvGemmParams g;
-  fill_common(p, y, g);
-  g.n_tile = y.n_tile;
-  g.n_blocks = y.n_blocks;
-  g.cluster = fwd_cluster(p, l);
-  g.idesc = idesc_of(p->dtype, 128 * g.cluster, y.n_tile, 0, 0);
+  if (cache && cache->valid) {
+    g = cache->g;
+  } else {
+    fill_common(p, y, g);
+    g.n_tile = y.n_tile;
+    g.n_blocks = y.n_blocks;
+    g.cluster = fwd_cluster(p, l);
+    g.idesc = idesc_of(p->dtype, 128 * g.cluster, y.n_tile, 0, 0);
+    // segment 0: x_t (layer 0) or the h_t of the layer below (model.py:266,271)
+    int s = 0;
+    g.seg[s].tmap_act = l == 0 ? (bank ? p->tmb_X : p->tm_X) : p->layer[l - 1].tm_H_up;
+    g.seg[s].wsel = 0;
+    g.seg[s].ksize = y.k;
+    g.seg[s].nchunks = y.chx;
+    ++s;
+    if (have_state) {  // h_{t-1} == 0 contributes nothing: skip its K-segment
+      g.seg[s].tmap_act = y.tm_H;
+      g.seg[s].wsel = 1;
+      g.seg[s].ksize = y.k;
+      g.seg[s].nchunks = y.chh;
+      ++s;
+    }
+    g.nseg = s;
+    g.bias_q = y.bias_q;
+    // epilogue I/O (TMA boxes): c_{t-1} -> c_t (in place at inference), h_t, activated gates (training)
+    g.tm_c = y.tme_C; g.tm_h = y.tme_H; g.tm_g = y.tme_G; g.tm_dc = y.tme_dC;
+    g.slot_g = (tr && epi == EPI_FWD) ? 0 : -1;   // only its sign enters the shared-memory plan
+    if (conv_halo_plan(epi, p->dtype, g)) return fail("layer %d: the conv kernel's shared-memory plan does not fit (hidden %d, k %d)", l, y.hc, y.k);
+    for (int i = 0; i < g.nseg; ++i)
+      if (get_w_map(p, y, g.seg[i].wsel, g.n_tile, g.n_tile / g.cluster, g.seg[i].ts, &g.seg[i].tmap_w)) return 1;
+    if (cache) { cache->g = g; cache->valid = true; }
+  }
+  // ---- what changes from step to step: slots, batch range, bank indices
   const int in_slot_h = tr ? t : (t & 1);
   const int out_slot_h = tr ? t + 1 : ((t + 1) & 1);
-  // segment 0: x_t (layer 0) or the h_t of the layer below (model.py:266,271)
-  int s = 0;
-  g.seg[s].tmap_act = l == 0 ? p->tm_X : p->layer[l - 1].tm_H_up;
-  g.seg[s].wsel = 0;
-  g.seg[s].slot = l == 0 ? t : (tr ? t + 1 : ((t + 1) & 1));
-  g.seg[s].ksize = y.k;
-  g.seg[s].nchunks = y.chx;
-  ++s;
-  const bool have_state = !(t == 0 && p->zero_init);
-  if (have_state) {  // h_{t-1} == 0 contributes nothing: skip its K-segment
-    g.seg[s].tmap_act = y.tm_H;
-    g.seg[s].wsel = 1;
-    g.seg[s].slot = in_slot_h;
-    g.seg[s].ksize = y.k;
-    g.seg[s].nchunks = y.chh;
-    ++s;
-  }
-  g.nseg = s;
-  g.bias_q = y.bias_q;
-  // epilogue I/O (TMA boxes): c_{t-1} -> c_t (in place at inference), h_t, activated gates (training)
-  g.tm_c = y.tme_C; g.tm_h = y.tme_H; g.tm_g = y.tme_G; g.tm_dc = y.tme_dC;
+  g.seg[0].slot = l == 0 ? t : (tr ? t + 1 : ((t + 1) & 1));
+  g.seg[0].win_start = bank ? p->win_start : nullptr;
+  g.seg[0].bank_frames = bank ? static_cast<int>(p->bank_frames) : 0;
+  if (have_state) g.seg[1].slot = in_slot_h;
   g.slot_c_in = have_state ? (tr ? t : 0) : -1;
   g.slot_c_out = tr ? t + 1 : 0;
   g.slot_h_out = out_slot_h;
   g.slot_g = (tr && epi == EPI_FWD) ? t : -1;
   g.raw_out = raw_out;
-  if (conv_halo_plan(epi, p->dtype, g)) return fail("layer %d: the conv kernel's shared-memory plan does not fit (hidden %d, k %d)", l, y.hc, y.k);
-  for (int i = 0; i < g.nseg; ++i)
-    if (get_w_map(p, y, g.seg[i].wsel, g.n_tile, g.n_tile / g.cluster, g.seg[i].ts, &g.seg[i].tmap_w)) return 1;
+  set_batch_range(p, g, b0, nb);
   LAUNCH(p, (epi == EPI_FWD ? K_FWD : K_OTHER), st, launch_conv_halo(epi, p->dtype, g, p->num_sms, st));
+  return 0;
+}
+
+// dgrad convolution without the gate epilogue: raw[b][y][x][n] = sum dgates_t (*) flip(W) for the N = `n_rows` input
+// channels of packed operand `wsel` (2: x part, 3: h part) of layer l; fp32 dump through the EPI_RAW epilogue
+int dgrad_raw(nint_plan* p, int l, int t, int wsel, int n_rows, float* raw_out, cudaStream_t st) {
+  Layer& y = p->layer[l];
+  ConvGemmParams g;
+  fill_common(p, y, g);
+  g.n_tile = n_rows;
+  g.n_blocks = 1;
+  g.cluster = (n_rows % 32 == 0) ? p->cluster : 1;
+  g.idesc = idesc_of(p->dtype, 128 * g.cluster, n_rows, 0, 0);
+  g.seg[0].tmap_act = y.tm_G; g.seg[0].wsel = wsel; g.seg[0].slot = t;
+  g.seg[0].ksize = y.k; g.seg[0].nchunks = 4 * y.hc / p->ce;
+  g.nseg = 1;
+  g.tm_c = y.tme_C; g.tm_h = y.tme_H; g.tm_g = y.tme_G; g.tm_dc = y.tme_dC;
+  g.slot_g = g.slot_c_in = g.slot_c_out = g.slot_h_out = g.slot_c_prev = -1;
+  g.raw_out = raw_out;
+  if (conv_halo_plan(EPI_RAW, p->dtype, g)) return fail("layer %d: the dgrad kernel's shared-memory plan does not fit (N %d, k %d)", l, n_rows, y.k);
+  if (get_w_map(p, y, wsel, g.n_tile, g.n_tile / g.cluster, g.seg[0].ts, &g.seg[0].tmap_w)) return 1;
+  LAUNCH(p, K_OTHER, st, launch_conv_halo(EPI_RAW, p->dtype, g, p->num_sms, st));
   return 0;
 }
 
@@ -444,6 +516,120 @@ static int plan_wgrad_blocks(nint_plan* p, Layer& y) {
   return 0;
 }
 
+// Launch parameters of column block `bi` of layer l's weight gradient: operand maps, tap groups, split-K shares.
+// Also used (with the nominal 148 SMs, before any device is known) to size the deterministic mode's partial buffers.
+static int wgrad_params(nint_plan* p, int l, size_t bi, int num_sms, WgradParams& w) {
+  Layer& y = p->layer[l];
+  const int T = p->T;
+  const Layer::WgBlock& blk = y.wg_blocks[bi];
+  const int bias_col = (l == 0) ? p->ones_lane : -1;
+  const long long total_tiles = static_cast<long long>(T) * p->B * p->tiles_x * p->tiles_y;
+  memset(&w, 0, sizeof(w));
+  w.halo = 1;
+  w.debug_flags = p->debug_flags;
+  w.b_panel_bytes = wgrad_b_panel_bytes(p->dtype, w.halo, y.k);
+  w.slot_b0[0] = l == 0 ? 0 : 1;
+  w.slot_b0[1] = 0;
+  w.nchunks_b[0] = blk.nch_x;
+  w.nchunks_b[1] = blk.nch_h;
+  w.chan0[0] = blk.chan0_x;
+  w.chan0[1] = blk.chan0_h;
+  w.T = T; w.B = p->B; w.H = p->H; w.W = p->W;
+  w.tile_w = p->tile_w; w.tile_h = p->tile_h; w.tiles_x = p->tiles_x; w.tiles_y = p->tiles_y;
+  w.ksize = y.k;
+  w.hc4 = 4 * y.hc;
+  w.pair = blk.pair ? 1 : 0;
+  const bool bank = l == 0 && p->x_bank;
+  w.win_start = bank ? p->win_start : nullptr;
+  if (w.pair && p->dtype == BF16) {
+    w.tmap_dg = y.tmp_G;
+    w.tmap_b[0] = l == 0 ? (bank ? p->tmbp_X : p->tmp_X) : p->layer[l - 1].tmp_H_up;
+    w.tmap_b[1] = y.tmp_H;
+  } else {   // single-CTA kernel, and the tf32 pair kernel: 32-channel boxes (bf16 SWIZZLE_64B / tf32 128B_ATOM_32B)
+    w.tmap_dg = y.tmw_G;
+    w.tmap_b[0] = l == 0 ? (bank ? p->tmbw_X : p->tmw_X) : p->layer[l - 1].tmw_H_up;
+    w.tmap_b[1] = y.tmw_H;
+  }
+  // a block without x (or h) panels never dereferences that map, but kernel parameters must be valid maps
+  if (blk.nch_x == 0) { w.tmap_b[0] = w.tmap_b[1]; w.win_start = nullptr; }
+  if (blk.nch_h == 0) w.tmap_b[1] = w.tmap_b[0];
+  w.m_blocks = w.pair ? w.hc4 / 256 : (w.hc4 + 127) / 128;
+  w.ncols = y.ncols;
+  w.acc_cols = blk.n_mma;
+  w.real_cols = blk.cols;
+  w.col0 = blk.col0;
+  // The bias gradient is either free (layer 0: x carries 1.0 in padding channel `ones_lane`, so db is that column
+  // of the centre tap) or costs 32 more accumulator columns and one N=32 MMA per K step against a panel of ones,
+  // in the first column block's lightest tap group (the last one when it has room, else the first).
+  // tap groups: a CTA keeps (taps in group) x acc_cols accumulator columns in TMEM (512 available)
+  const int bias_cols = (bias_col >= 0 || bi > 0) ? 0 : 32;
+  const int tpg = 512 / blk.n_mma;                     // taps per group
+  if (tpg < 1) return fail("wgrad: %d columns exceed the accumulator", blk.n_mma);
+  int ng = 0, tap = 0;
+  w.group_tap0[0] = 0;
+  const int rest = y.taps % tpg;
+  const bool bias_last = rest > 0 && rest * blk.n_mma + bias_cols <= 512;   // a partial last group with room for the bias
+  const int g0 = bias_last ? tpg : ((512 - bias_cols) / blk.n_mma < tpg ? (512 - bias_cols) / blk.n_mma : tpg);
+  if (g0 < 1) return fail("wgrad: %d columns leave no room for the bias columns", blk.n_mma);
+  while (tap < y.taps) {
+    const int n = ng == 0 ? g0 : tpg;
+    tap = tap + n > y.taps ? y.taps : tap + n;
+    if (ng + 1 > kMaxWgradGroups) return fail("wgrad: too many tap groups");
+    w.group_tap0[++ng] = tap;
+  }
+  w.bias_group = bias_cols == 0 ? -1 : (bias_last ? ng - 1 : 0);
+  w.n_groups = ng;
+  // split-K over pixel tiles: every group gets a share of the SMs in proportion to its MMA cycles per K step
+  // (pair MMA: ~N/2 cycles with a ~40-cycle floor; 1-CTA MMA: ~N*0.67 with a ~88-cycle floor -- DESIGN.md 4)
+  {
+    int units = (w.pair ? num_sms / 2 : num_sms) / w.m_blocks;   // (group, split) slots
+    if (units < ng) units = ng;
+    auto mma_cost = [&](int n) { return w.pair ? (n / 2 > 40 ? n / 2 : 40) : (n * 2 / 3 > 88 ? n * 2 / 3 : 88); };
+    int cost[kMaxWgradGroups], tot = 0;
+    for (int g = 0; g < ng; ++g) {
+      cost[g] = (w.group_tap0[g + 1] - w.group_tap0[g]) * mma_cost(blk.n_mma) + (g == w.bias_group ? mma_cost(32) : 0);
+      tot += cost[g];
+    }
+    const bool even = (p->debug_flags & 64) != 0;     // experiment: the same split count for every group
+    int used = 0;
+    for (int g = 0; g < ng; ++g) {
+      int sp = even ? units / ng : static_cast<int>(static_cast<long long>(units) * cost[g] / tot);
+      if (sp < 1) sp = 1;
+      w.group_splits[g] = sp;
+      used += sp;
+    }
+    // hand the remaining slots to whichever group has the most work per split
+    while (!even && used < units) {
+      int best = 0;
+      for (int g = 1; g < ng; ++g)
+        if (static_cast<long long>(cost[g]) * w.group_splits[best] > static_cast<long long>(cost[best]) * w.group_splits[g]) best = g;
+      ++w.group_splits[best];
+      ++used;
+    }
+    w.group_unit0[0] = 0;
+    for (int g = 0; g < ng; ++g) {
+      if (w.group_splits[g] > total_tiles) w.group_splits[g] = static_cast<int>(total_tiles);
+      w.group_unit0[g + 1] = w.group_unit0[g] + w.m_blocks * w.group_splits[g];
+    }
+  }
+  w.b_pw = blk.pw;
+  w.a_bufs = blk.a_bufs;
+  w.b_stages = blk.b_stages;
+  if (w.b_stages < 1) return fail("wgrad: operand panels do not fit in shared memory");
+  w.idesc = idesc_of(p->dtype, w.pair ? 256 : 128, blk.n_mma, 1, 1);
+  w.idesc_bias = idesc_of(p->dtype, w.pair ? 256 : 128, 32, 1, 1);
+  w.dw_acc = y.dw_acc;
+  w.db_acc = y.db_acc;
+  w.dw_part = p->deterministic ? y.dw_acc : nullptr;
+  w.db_part = p->deterministic ? y.db_acc : nullptr;
+  return 0;
+}
+static int wgrad_max_splits(const WgradParams& w) {
+  int m = 1;
+  for (int g = 0; g < w.n_groups; ++g) if (w.group_splits[g] > m) m = w.group_splits[g];
+  return m;
+}
+
 extern "C" {
 
 int nint_version(void) { return 100; }
@@ -495,6 +681,8 @@ int nint_plan_create(const nint_config* cfg, nint_plan** out) {
   p->dtype = cfg->dtype;
   p->esize = cfg->dtype == BF16 ? 2 : 4;
   p->ce = 64 / p->esize;
+  p->deterministic = (cfg->flags & NINT_FLAG_DETERMINISTIC) != 0;
+  p->input_grad = (cfg->flags & NINT_FLAG_INPUT_GRAD) != 0;
   {  // debug / A-B knobs (documented in DESIGN.md): CTA pairs on/off, experiment flags
     const char* c = getenv("NINT_CLUSTER");
     p->cluster = c ? atoi(c) : 2;
@@ -505,25 +693,35 @@ int nint_plan_create(const nint_config* cfg, nint_plan** out) {
     p->plan_g = pg ? atoi(pg) : 0;
     const char* pn = getenv("NINT_PLAN_NS");
     p->plan_ns = pn ? atoi(pn) : 0;
+    if (const char* e = getenv("NINT_DETERMINISTIC")) p->deterministic = p->deterministic || atoi(e) != 0;
+    const char* sb = getenv("NINT_SUB_BATCH");
+    p->sub_batch = sb ? atoi(sb) : 0;
+    if (p->sub_batch < 0 || p->sub_batch >= p->B) p->sub_batch = 0;
   }
   pick_tile(p->H, p->W, &p->tile_w, &p->tile_h);
   p->tiles_x = (p->W + p->tile_w - 1) / p->tile_w;
   p->tiles_y = (p->H + p->tile_h - 1) / p->tile_h;
-  int cin = cfg->in_channels;
+  int cin = cfg->in_channels, below_hc = 0;
   for (int l = 0; l < p->L; ++l) {
     Layer& y = p->layer[l];
-    y.cin = cin; y.hc = cfg->hidden[l]; y.k = cfg->ksize[l]; y.taps = y.k * y.k;
-    if (y.hc < 16 || y.hc % 16 || y.hc > 256 || (y.hc > 64 && y.hc % 64)) {
+    y.cin = cin; y.hc_real = cfg->hidden[l]; y.k = cfg->ksize[l]; y.taps = y.k * y.k;
+    if (y.hc_real < 1 || y.hc_real > 256) {
       delete p;
-      return fail("hidden_channels[%d] = %d unsupported (multiple of 16; multiple of 64 above 64; <= 256)", l, y.hc);
+      return fail("hidden_channels[%d] = %d unsupported (1 .. 256)", l, cfg->hidden[l]);
     }
+    // any hidden size runs padded to the kernels' granularity (a multiple of 16, of 64 above 64): the padding channels
+    // get zero weights and biases, so their c and h stay exactly zero and nothing downstream sees them (model.py:207)
+    y.hc = y.hc_real <= 64 ? (y.hc_real + 15) / 16 * 16 : (y.hc_real + 63) / 64 * 64;
     if (y.k < 1 || y.k % 2 == 0 || y.k > 15) {
       delete p;
       return fail("kernel_size[%d] = %d unsupported (odd, <= 15)", l, y.k);
     }
     if (l > 0 && cin > 256) { delete p; return fail("layer %d input channels %d > 256", l, cin); }
-    y.cx_pad = (y.cin + 31) / 32 * 32; y.chx = y.cx_pad / p->ce;   // channels padded to 32 in both dtypes
+    // x segment: layer 0 reads X (cin channels padded to 32); layer l > 0 reads the whole padded h tensor of the layer below
+    y.cx_pad = l == 0 ? (y.cin + 31) / 32 * 32 : (below_hc + 31) / 32 * 32;
+    y.chx = y.cx_pad / p->ce;
     y.hc_pad = (y.hc + 31) / 32 * 32;  y.chh = y.hc_pad / p->ce;
+    y.cin_rows = l == 0 ? y.cx_pad : below_hc;
     // a spare padding channel of X carries 1.0: the packed forward weights are zero there (no effect on the cell),
     // and the weight-gradient GEMM then produces the bias gradient in that column for free
     if (l == 0 && y.cx_pad > y.cin && !(p->debug_flags & 128)) p->ones_lane = y.cin;
@@ -535,7 +733,7 @@ int nint_plan_create(const nint_config* cfg, nint_plan** out) {
     if (cfg->dtype == BF16) {
       bool fits = false;
       for (int cand = y.hcb; cand >= 32 && !fits; cand >>= 1) {
-        const long long w_cta = static_cast<long long>((y.cin + 31) / 32 + (y.hc + 31) / 32) * y.taps * (4 * cand / p->cluster) * 64;
+        const long long w_cta = static_cast<long long>(y.cx_pad / 32 + y.hc_pad / 32) * y.taps * (4 * cand / p->cluster) * 64;
         if (y.hc % cand == 0 && w_cta <= 112 * 1024) { y.hcb = cand; fits = true; }
       }
       // weights that have to stream (5x5 taps, wide layers): N = 128 with two pixel tiles sharing every weight stage
@@ -556,7 +754,22 @@ int nint_plan_create(const nint_config* cfg, nint_plan** out) {
       return fail("layer %d: training with hidden %d, kernel %d: not even one 32-channel wgrad operand panel fits in "
                   "shared memory", l, hc, k);
     }
-    cin = y.hc;
+    if (cfg->training && p->deterministic) {
+      // partial-sum slices of the deterministic weight gradient: as many as the widest split-K of any column block
+      // on a 148-SM part (checked again at launch against the real device)
+      y.det_splits = 1;
+      for (size_t bi = 0; bi < y.wg_blocks.size(); ++bi) {
+        WgradParams w;
+        if (wgrad_params(p, l, bi, 148, w)) { delete p; return 1; }
+        if (wgrad_max_splits(w) > y.det_splits) y.det_splits = wgrad_max_splits(w);
+      }
+    }
+    cin = y.hc_real;
+    below_hc = y.hc;
+  }
+  if (p->input_grad && cfg->training && p->layer[0].cin_rows > 256) {
+    delete p;
+    return fail("input gradient: %d input channels exceed one MMA N (256)", cfg->in_channels);
   }
   // (layer l >= 1 reads the h tensor of layer l-1 as its x segment: ceil(hc_{l-1}/ce) chunks on both sides)
   p->ws_bytes = carve(p, nullptr);
@@ -571,6 +784,32 @@ void nint_plan_destroy(nint_plan* plan) {
 }
 
 size_t nint_plan_workspace_bytes(const nint_plan* plan) { return plan ? plan->ws_bytes : 0; }
+
+int nint_plan_input_layout(const nint_plan* plan, int* c_pad, int* ones_lane, int* elem_bytes) {
+  if (!plan) return fail("null plan");
+  if (c_pad) *c_pad = plan->layer[0].cx_pad;
+  if (ones_lane) *ones_lane = plan->ones_lane;
+  if (elem_bytes) *elem_bytes = plan->esize;
+  return 0;
+}
+
+// tensor maps over an input tensor [images][H][W][cx_pad0] x `slots`: conv view, wgrad view, CTA-pair wgrad view
+static int encode_input_maps(nint_plan* p, void* base, long long images, int slots, CUtensorMap* conv, CUtensorMap* wg,
+                             CUtensorMap* wg_pair) {
+  const int tw = p->tile_w, th = p->tile_h, ce = p->ce, pad0 = p->layer[0].k / 2;
+  Layer& y = p->layer[0];
+  if (images > 0x7fffffffLL) return fail("too many frames (%lld)", images);
+  const int n = static_cast<int>(images);
+  if (encode_act_map(conv, p->dtype, base, y.cx_pad, p->W, p->H, n, slots, ce, tw, th, false, pad0)) return 1;
+  if (encode_act_map(wg, p->dtype, base, y.cx_pad, p->W, p->H, n, slots, ce, tw, th, true, pad0)) return 1;
+  if (p->cfg.training && p->dtype == BF16)
+    for (const Layer::WgBlock& b : y.wg_blocks) {
+      if (!b.pair || b.nch_x == 0) continue;
+      const CUtensorMapSwizzle sw = b.pw == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (b.pw == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+      if (encode_act_box(wg_pair, p->dtype, base, y.cx_pad, p->W, p->H, n, slots, b.pw, tw, th, pad0, sw)) return 1;
+    }
+  return 0;
+}
 
 int nint_plan_bind(nint_plan* p, void* workspace, size_t bytes, void* stream) {
   if (!p || !workspace) return fail("nint_plan_bind: null argument");
@@ -588,10 +827,12 @@ int nint_plan_bind(nint_plan* p, void* workspace, size_t bytes, void* stream) {
   CK(cudaMemsetAsync(p->ws, 0, p->ws_bytes, st));
   const int tw = p->tile_w, th = p->tile_h, ce = p->ce;
   auto pad_of = [&](int l) { return p->layer[l].k / 2; };
-  if (encode_act_map(&p->tm_X, p->dtype, p->X, p->layer[0].cx_pad, p->W, p->H, p->B, p->T, ce, tw, th, false, pad_of(0))) return 1;
-  if (encode_act_map(&p->tmw_X, p->dtype, p->X, p->layer[0].cx_pad, p->W, p->H, p->B, p->T, ce, tw, th, true, pad_of(0))) return 1;
+  if (encode_input_maps(p, p->X, p->B, p->T, &p->tm_X, &p->tmw_X, &p->tmp_X)) return 1;
+  p->x_bank = false; p->bank_ptr = nullptr; p->bank_frames = 0; p->win_start = nullptr;
   for (int l = 0; l < p->L; ++l) {
     Layer& y = p->layer[l];
+    for (auto& a : y.fwd_cache) for (auto& c : a) c.valid = false;
+    for (auto& c : y.bwd_cache) c.valid = false;
     if (encode_act_map(&y.tm_H, p->dtype, y.Hs, y.hc_pad, p->W, p->H, p->B, y.nslots_h, ce, tw, th, false, pad_of(l))) return 1;
     if (l + 1 < p->L &&
         encode_act_map(&y.tm_H_up, p->dtype, y.Hs, y.hc_pad, p->W, p->H, p->B, y.nslots_h, ce, tw, th, false, pad_of(l + 1))) return 1;
@@ -626,8 +867,6 @@ int nint_plan_bind(nint_plan* p, void* workspace, size_t bytes, void* stream) {
         // a pair block covers whole tensors (the full row, or the x part / the h part), so one map per tensor
         if (b.nch_h > 0 &&
             encode_act_box(&y.tmp_H, p->dtype, y.Hs, y.hc_pad, p->W, p->H, p->B, y.nslots_h, b.pw, tw, th, pad_of(l), sw_of(b.pw))) return 1;
-        if (b.nch_x > 0 && l == 0 &&
-            encode_act_box(&p->tmp_X, p->dtype, p->X, y.cx_pad, p->W, p->H, p->B, p->T, b.pw, tw, th, pad_of(0), sw_of(b.pw))) return 1;
         if (b.nch_x > 0 && l > 0) {
           Layer& dn = p->layer[l - 1];
           if (encode_act_box(&dn.tmp_H_up, p->dtype, dn.Hs, dn.hc_pad, p->W, p->H, p->B, dn.nslots_h, b.pw, tw, th, pad_of(l), sw_of(b.pw))) return 1;
@@ -639,6 +878,7 @@ int nint_plan_bind(nint_plan* p, void* workspace, size_t bytes, void* stream) {
   }
   p->zero_init = true;
   p->fwd_done = false;
+  p->gates_valid = false;
   p->bptt_done = false;
   return 0;
 }
@@ -649,8 +889,8 @@ int nint_plan_set_weights(nint_plan* p, int l, const float* weight, const float*
   if (!weight) return fail("null weight");
   Layer& y = p->layer[l];
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  LAUNCH(p, K_OTHER, st, launch_pack_weights_fwd(p->dtype, weight, bias, y.wx, y.wh, y.bias_q, y.cin, y.hc, y.hcb, y.k, y.cx_pad, y.hc_pad, st));
-  if (p->cfg.training) LAUNCH(p, K_OTHER, st, launch_pack_weights_bwd(p->dtype, weight, y.wdx, y.wdh, y.cin, y.hc, y.k, st));
+  LAUNCH(p, K_OTHER, st, launch_pack_weights_fwd(p->dtype, weight, bias, y.wx, y.wh, y.bias_q, y.cin, y.hc_real, y.hc, y.hcb, y.k, y.cx_pad, y.hc_pad, st));
+  if (p->cfg.training) LAUNCH(p, K_OTHER, st, launch_pack_weights_bwd(p->dtype, weight, y.wdx, y.wdh, y.cin, y.cin_rows, y.hc_real, y.hc, y.k, st));
   y.weights_set = true;
   return 0;
 }
@@ -659,7 +899,7 @@ int nint_plan_set_head(nint_plan* p, const float* weight, const float* bias, voi
   if (!p || !p->ws) return fail("plan not bound");
   if (!weight || !bias) return fail("null head parameter");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  CK(cudaMemcpyAsync(p->head_w, weight, p->layer[p->L - 1].hc * 4, cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemcpyAsync(p->head_w, weight, p->layer[p->L - 1].hc_real * 4, cudaMemcpyDeviceToDevice, st));
   CK(cudaMemcpyAsync(p->head_b, bias, 4, cudaMemcpyDeviceToDevice, st));
   p->head_set = true;
   return 0;
@@ -692,8 +932,8 @@ int nint_plan_set_state(nint_plan* p, int l, const float* h, const float* c, voi
       CK(cudaMemsetAsync(z.Cs, 0, static_cast<size_t>(p->B) * p->H * p->W * z.hc * 4, st));
     }
   }
-  LAUNCH(p, K_OTHER, st, launch_pack_state(p->dtype, h, y.Hs, p->B, y.hc, p->H, p->W, y.hc_pad, st));
-  LAUNCH(p, K_OTHER, st, launch_nchw_to_nhwc_f32(c, y.Cs, p->B, y.hc, p->H, p->W, st));
+  LAUNCH(p, K_OTHER, st, launch_pack_state(p->dtype, h, y.Hs, p->B, y.hc_real, p->H, p->W, y.hc_pad, st));
+  LAUNCH(p, K_OTHER, st, launch_nchw_to_nhwc_f32(c, y.Cs, p->B, y.hc_real, p->H, p->W, y.hc, st));
   p->zero_init = false;
   return 0;
 }
@@ -704,8 +944,8 @@ int nint_plan_get_state(nint_plan* p, int l, float* h, float* c, void* stream) {
   if (!p->fwd_done) return fail("nint_plan_get_state before nint_forward");
   Layer& y = p->layer[l];
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (h) LAUNCH(p, K_OTHER, st, launch_unpack_state(p->dtype, slot_ptr(p, y.Hs, p->final_slot_h, y.hc_pad), h, p->B, y.hc, p->H, p->W, y.hc_pad, st));
-  if (c) LAUNCH(p, K_OTHER, st, launch_nhwc_to_nchw_f32(cslot_ptr(p, y, p->final_slot_c), c, p->B, y.hc, p->H, p->W, st));
+  if (h) LAUNCH(p, K_OTHER, st, launch_unpack_state(p->dtype, slot_ptr(p, y.Hs, p->final_slot_h, y.hc_pad), h, p->B, y.hc_real, p->H, p->W, y.hc_pad, st));
+  if (c) LAUNCH(p, K_OTHER, st, launch_nhwc_to_nchw_f32(cslot_ptr(p, y, p->final_slot_c), c, p->B, y.hc_real, p->H, p->W, y.hc, st));
   return 0;
 }
 
@@ -717,36 +957,86 @@ static int check_ready(nint_plan* p) {
   return 0;
 }
 
-int nint_forward(nint_plan* p, const float* x, float* pred, float* seq, void* stream) {
-  if (check_ready(p)) return 1;
-  if (!x || !pred) return fail("nint_forward: null x / pred");
-  if (seq && !p->cfg.return_sequence) return fail("seq output requires return_sequence in the plan");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
+// the T x L fused cell steps + head of ConvLSTM.forward once the input is in place (X packed, or the bank attached)
+static int forward_steps(nint_plan* p, float* pred, float* seq, cudaStream_t st) {
   const bool tr = p->cfg.training != 0;
   const long long HW = static_cast<long long>(p->H) * p->W;
-  LAUNCH(p, K_OTHER, st, launch_pack_input(p->dtype, x, p->X, p->B, p->T, p->cfg.in_channels, p->H, p->W, p->layer[0].cx_pad, p->ones_lane, st));
   const Layer& top = p->layer[p->L - 1];
-  for (int t = 0; t < p->T; ++t) {          // model.py:265
-    for (int l = 0; l < p->L; ++l)          // model.py:267
-      if (cell_step(p, l, t, EPI_FWD, nullptr, st)) return 1;
-    if (seq) {                              // model.py:272 (commented variant)
-      const int slot = tr ? t + 1 : ((t + 1) & 1);
-      LAUNCH(p, K_OTHER, st, launch_head_fwd(p->dtype, slot_ptr(p, top.Hs, slot, top.hc_pad), p->head_w, p->head_b, seq + t * HW, HW,
-                         p->B, top.hc, top.hc_pad, p->T * HW, st));
+  const size_t top_img = static_cast<size_t>(HW) * top.hc_pad * p->esize;   // bytes of one image of the top layer's h
+  const int SB = p->sub_batch > 0 ? p->sub_batch : p->B;
+  for (int b0 = 0; b0 < p->B; b0 += SB) {     // sub-batch-major: every slice runs all its steps while its state is in L2
+    const int nb = b0 + SB <= p->B ? SB : p->B - b0;
+    for (int t = 0; t < p->T; ++t) {          // model.py:265
+      for (int l = 0; l < p->L; ++l)          // model.py:267
+        if (cell_step(p, l, t, EPI_FWD, nullptr, st, b0, SB < p->B ? nb : 0)) return 1;
+      if (seq) {                              // model.py:272 (commented variant)
+        const int slot = tr ? t + 1 : ((t + 1) & 1);
+        LAUNCH(p, K_OTHER, st, launch_head_fwd(p->dtype, slot_ptr(p, top.Hs, slot, top.hc_pad) + b0 * top_img, p->head_w, p->head_b,
+                           seq + b0 * p->T * HW + t * HW, HW, nb, top.hc_real, top.hc_pad, p->T * HW, st));
+      }
     }
   }
   p->final_slot_h = tr ? p->T : (p->T & 1);
   p->final_slot_c = tr ? p->T : 0;
   LAUNCH(p, K_OTHER, st, launch_head_fwd(p->dtype, slot_ptr(p, top.Hs, p->final_slot_h, top.hc_pad), p->head_w, p->head_b, pred, HW, p->B,
-                     top.hc, top.hc_pad, HW, st));  // model.py:274
+                     top.hc_real, top.hc_pad, HW, st));  // model.py:274
   p->fwd_done = true;
+  p->gates_valid = tr;
   p->bptt_done = false;
   return 0;
 }
 
-int nint_fuse_inputs(const float* levels3d, const float* emis2d, const float* mean, const float* std,
-                     const float* statics, int n_static, long long frames, int levels, int height, int width,
-                     int padded_height, int padded_width, int mode, float* out, void* stream) {
+int nint_forward_ex(nint_plan* p, const void* x, int x_dtype, float* pred, float* seq, void* stream) {
+  if (check_ready(p)) return 1;
+  if (!x || !pred) return fail("nint_forward: null x / pred");
+  if (seq && !p->cfg.return_sequence) return fail("seq output requires return_sequence in the plan");
+  if (x_dtype != NINT_X_FP32 && x_dtype != NINT_X_BF16) return fail("unknown x dtype %d", x_dtype);
+  if (x_dtype == NINT_X_BF16 && p->dtype != BF16) return fail("bf16 inputs need a bf16 plan (a tf32 plan would lose input precision)");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  p->x_bank = false;
+  LAUNCH(p, K_OTHER, st, launch_pack_input(p->dtype, x, x_dtype == NINT_X_BF16, p->X, p->B, p->T, p->cfg.in_channels, p->H, p->W, p->layer[0].cx_pad, p->ones_lane, st));
+  return forward_steps(p, pred, seq, st);
+}
+
+int nint_forward(nint_plan* p, const float* x, float* pred, float* seq, void* stream) {
+  return nint_forward_ex(p, x, NINT_X_FP32, pred, seq, stream);
+}
+
+int nint_forward_bank(nint_plan* p, const void* bank, long long n_frames, const int* win_start, float* pred, float* seq,
+                      void* stream) {
+  if (check_ready(p)) return 1;
+  if (!bank || !win_start || !pred) return fail("nint_forward_bank: null bank / win_start / pred");
+  if (n_frames < p->T) return fail("nint_forward_bank: %lld frames cannot hold a window of %d steps", n_frames, p->T);
+  if (reinterpret_cast<uintptr_t>(bank) % 128) return fail("the frame bank must be 128-byte aligned");
+  if (seq && !p->cfg.return_sequence) return fail("seq output requires return_sequence in the plan");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (bank != p->bank_ptr || n_frames != p->bank_frames) {
+    if (encode_input_maps(p, const_cast<void*>(bank), n_frames, 1, &p->tmb_X, &p->tmbw_X, &p->tmbp_X)) return 1;
+    p->bank_ptr = bank;
+    p->bank_frames = n_frames;
+    for (auto& a : p->layer[0].fwd_cache) a[1].valid = false;
+  }
+  p->x_bank = true;
+  p->win_start = win_start;
+  return forward_steps(p, pred, seq, st);
+}
+
+int nint_pack_frames(int dtype, const void* frames, int x_dtype, long long n_frames, int channels, int height, int width,
+                     int c_pad, int ones_lane, void* bank, void* stream) {
+  if (!frames || !bank) return fail("nint_pack_frames: null argument");
+  if (dtype != BF16 && dtype != TF32) return fail("unknown dtype %d", dtype);
+  if (x_dtype != NINT_X_FP32 && x_dtype != NINT_X_BF16) return fail("unknown x dtype %d", x_dtype);
+  if (n_frames < 1 || channels < 1 || height < 1 || width < 1) return fail("nint_pack_frames: bad shape");
+  if (c_pad < channels || c_pad % 16) return fail("nint_pack_frames: c_pad %d must be a multiple of 16 and >= %d", c_pad, channels);
+  if (ones_lane >= 0 && (ones_lane < channels || ones_lane >= c_pad)) return fail("nint_pack_frames: ones lane %d outside the padding lanes", ones_lane);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  LAUNCH(nullptr, K_OTHER, st, launch_pack_frames(dtype, frames, x_dtype == NINT_X_BF16, bank, n_frames, channels, height, width, c_pad, ones_lane, st));
+  return 0;
+}
+
+static int check_fuse_args(const float* levels3d, const float* emis2d, const float* mean, const float* std,
+                           const float* statics, int n_static, long long frames, int levels, int height, int width,
+                           int padded_height, int padded_width, int mode, const void* out) {
   if ((!levels3d && levels > 0) || !emis2d || !mean || !std || !out) return fail("nint_fuse_inputs: null argument");
   if (n_static < 0 || (n_static > 0 && !statics)) return fail("nint_fuse_inputs: %d static fields but no data", n_static);
   if (frames < 1 || levels < 0 || height < 1 || width < 1) return fail("nint_fuse_inputs: bad shape");
@@ -758,19 +1048,56 @@ int nint_fuse_inputs(const float* levels3d, const float* emis2d, const float* me
     return fail("The requested padding size is larger than width size of the input image.");
   if (top + 1 > height || bot + 1 > height)   // dataset.py:98
     return fail("The requested padding size is larger than height size of the input image.");
+  return 0;
+}
+
+int nint_fuse_inputs(const float* levels3d, const float* emis2d, const float* mean, const float* std,
+                     const float* statics, int n_static, long long frames, int levels, int height, int width,
+                     int padded_height, int padded_width, int mode, float* out, void* stream) {
+  if (check_fuse_args(levels3d, emis2d, mean, std, statics, n_static, frames, levels, height, width, padded_height, padded_width, mode, out)) return 1;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   LAUNCH(nullptr, K_OTHER, st, launch_fuse_inputs(levels3d, emis2d, mean, std, statics, n_static, out, frames, levels, height, width, padded_height, padded_width, mode, st));
   return 0;
 }
 
-int nint_loss_mse_l1(const float* pred, const float* y, int batch, int height, int width, int crop_y0, int crop_y1,
-                     int crop_x0, int crop_x1, float* dpred, float* loss, float* stats, void* stream) {
+int nint_fuse_inputs_bank(const float* levels3d, const float* emis2d, const float* mean, const float* std,
+                          const float* statics, int n_static, long long frames, int levels, int height, int width,
+                          int padded_height, int padded_width, int mode, int dtype, int c_pad, int ones_lane,
+                          void* bank, void* stream) {
+  if (check_fuse_args(levels3d, emis2d, mean, std, statics, n_static, frames, levels, height, width, padded_height, padded_width, mode, bank)) return 1;
+  if (dtype != BF16 && dtype != TF32) return fail("unknown dtype %d", dtype);
+  const int C = levels + 1 + n_static;
+  if (c_pad < C || c_pad % 16 || c_pad > 64) return fail("nint_fuse_inputs_bank: c_pad %d must be a multiple of 16 in [%d, 64]", c_pad, C);
+  if (ones_lane >= 0 && (ones_lane < C || ones_lane >= c_pad)) return fail("nint_fuse_inputs_bank: ones lane %d outside the padding lanes", ones_lane);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  LAUNCH(nullptr, K_OTHER, st, launch_fuse_inputs_bank(dtype, levels3d, emis2d, mean, std, statics, n_static, bank, frames, levels, height, width, padded_height, padded_width, mode, c_pad, ones_lane, st));
+  return 0;
+}
+
+static int check_loss_args(const float* pred, const float* y, const float* loss, const float* stats, int batch, int height,
+                           int width, int crop_y0, int crop_y1, int crop_x0, int crop_x1) {
   if (!pred || !y || !loss || !stats) return fail("nint_loss_mse_l1: null argument");
   if (batch < 1 || height < 1 || width < 1) return fail("nint_loss_mse_l1: bad shape");
   if (crop_y0 < 0 || crop_y1 > height || crop_y0 >= crop_y1 || crop_x0 < 0 || crop_x1 > width || crop_x0 >= crop_x1)
     return fail("nint_loss_mse_l1: crop [%d:%d, %d:%d] outside %dx%d", crop_y0, crop_y1, crop_x0, crop_x1, height, width);
+  return 0;
+}
+
+int nint_loss_mse_l1(const float* pred, const float* y, int batch, int height, int width, int crop_y0, int crop_y1,
+                     int crop_x0, int crop_x1, float* dpred, float* loss, float* stats, void* stream) {
+  if (check_loss_args(pred, y, loss, stats, batch, height, width, crop_y0, crop_y1, crop_x0, crop_x1)) return 1;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  LAUNCH(nullptr, K_OTHER, st, launch_loss_mse_l1(pred, y, dpred, stats, loss, batch, height, width, crop_y0, crop_y1, crop_x0, crop_x1, st));
+  LAUNCH(nullptr, K_OTHER, st, launch_loss_mse_l1(pred, y, dpred, stats, loss, batch, height, width, crop_y0, crop_y1, crop_x0, crop_x1, nullptr, 0, st));
+  return 0;
+}
+
+int nint_loss_mse_l1_bank(const float* pred, const float* ybank, const int* win_start, int y_offset, int batch,
+                          int height, int width, int crop_y0, int crop_y1, int crop_x0, int crop_x1, float* dpred,
+                          float* loss, float* stats, void* stream) {
+  if (check_loss_args(pred, ybank, loss, stats, batch, height, width, crop_y0, crop_y1, crop_x0, crop_x1)) return 1;
+  if (!win_start) return fail("nint_loss_mse_l1_bank: null win_start");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  LAUNCH(nullptr, K_OTHER, st, launch_loss_mse_l1(pred, ybank, dpred, stats, loss, batch, height, width, crop_y0, crop_y1, crop_x0, crop_x1, win_start, y_offset, st));
   return 0;
 }
 
@@ -780,6 +1107,16 @@ int nint_adam_step(float* params, const float* grads, float* exp_avg, float* exp
   if (n < 0 || step < 1) return fail("nint_adam_step: n >= 0 and step >= 1 required");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   LAUNCH(nullptr, K_OTHER, st, launch_adam(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step, grad_scale, st));
+  return 0;
+}
+
+int nint_adam_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float* state,
+                       float beta1, float beta2, float eps, float grad_scale, void* stream) {
+  if (!params || !grads || !exp_avg || !exp_avg_sq || !state) return fail("nint_adam_step_dev: null argument");
+  if (n < 0) return fail("nint_adam_step_dev: n >= 0 required");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  LAUNCH(nullptr, K_OTHER, st, launch_adam_dev(params, grads, exp_avg, exp_avg_sq, n, state, beta1, beta2, eps, grad_scale, st));
+  ++g_launches[K_OTHER];   // two kernels: the step tick and the update
   return 0;
 }
 
@@ -795,8 +1132,91 @@ int nint_debug_raw_gates(nint_plan* p, const float* x, float* out, void* stream)
   if (check_ready(p)) return 1;
   if (!x || !out) return fail("nint_debug_raw_gates: null argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  LAUNCH(p, K_OTHER, st, launch_pack_input(p->dtype, x, p->X, p->B, p->T, p->cfg.in_channels, p->H, p->W, p->layer[0].cx_pad, p->ones_lane, st));
+  p->x_bank = false;
+  LAUNCH(p, K_OTHER, st, launch_pack_input(p->dtype, x, 0, p->X, p->B, p->T, p->cfg.in_channels, p->H, p->W, p->layer[0].cx_pad, p->ones_lane, st));
   return cell_step(p, 0, 0, EPI_RAW, out, st);
+}
+
+// one fused dgrad + gate-backward launch of layer l at step t for images [b0, b0 + nb) (nb = 0: all)
+static int bwd_step(nint_plan* p, int l, int t, const float* dpred, const float* dseq, const float* dh_ext, bool dc_given,
+                    cudaStream_t st, int b0, int nb) {
+  const long long HW = static_cast<long long>(p->H) * p->W;
+  const int L = p->L, T = p->T;
+  Layer& y = p->layer[l];
+  const bool has_next = t < T - 1;
+  Layer::CachedConv& cache = y.bwd_cache[has_next ? 1 : 0];
+  ConvGemmParams g;
+  if (cache.valid) {
+    g = cache.g;
+  } else {
+    fill_common(p, y, g);
+    g.n_tile = y.hc;
+    g.n_blocks = 1;
+    g.cluster = bwd_cluster(p, l);
+    g.idesc = idesc_of(p->dtype, 128 * g.cluster, y.hc, 0, 0);
+    int s = 0;
+    if (has_next) {  // dh_t += dgates_{t+1} (*) flip(W_h)
+      g.seg[s].tmap_act = y.tm_G; g.seg[s].wsel = 3;
+      g.seg[s].ksize = y.k; g.seg[s].nchunks = 4 * y.hc / p->ce;
+      ++s;
+    }
+    if (l < L - 1) {  // dh_t += dx of the layer above at the same t
+      Layer& up = p->layer[l + 1];
+      g.seg[s].tmap_act = up.tm_G; g.seg[s].wsel = 2;
+      g.seg[s].ksize = up.k; g.seg[s].nchunks = 4 * up.hc / p->ce;
+      ++s;
+    }
+    g.nseg = s;
+    // epilogue I/O: gates_t -> dgates_t in place, c_{t-1}, running dc in place (c_t is recomputed)
+    g.tm_c = y.tme_C; g.tm_h = y.tme_H; g.tm_g = y.tme_G; g.tm_dc = y.tme_dC;
+    g.slot_c_in = g.slot_c_out = g.slot_h_out = -1;
+    if (conv_halo_plan(EPI_BWD, p->dtype, g)) return fail("layer %d: the dgrad kernel's shared-memory plan does not fit (hidden %d, k %d)", l, y.hc, y.k);
+    for (int i = 0; i < g.nseg; ++i) {
+      Layer& owner = g.seg[i].wsel == 2 ? p->layer[l + 1] : y;   // wdx belongs to the layer above
+      if (get_w_map(p, owner, g.seg[i].wsel, g.n_tile, g.n_tile / g.cluster, g.seg[i].ts, &g.seg[i].tmap_w)) return 1;
+    }
+    cache.g = g;
+    cache.valid = true;
+  }
+  int s = 0;
+  if (has_next) g.seg[s++].slot = t + 1;
+  if (l < L - 1) g.seg[s++].slot = t;
+  g.slot_g = t;
+  g.slot_c_prev = (t == 0 && p->zero_init) ? -1 : t;
+  g.has_dc_in = (t == T - 1) ? (dc_given ? 1 : 0) : 1;
+  g.head_dpred = nullptr; g.head_w = nullptr; g.head_dpred_bstride = 0;
+  if (l == L - 1) {
+    if (dseq) {
+      // per-step head gradient; dpred (last step) is folded in by the caller adding it to dseq[:, T-1]
+      g.head_dpred = dseq + t * HW;
+      g.head_dpred_bstride = T * HW;
+      g.head_w = p->head_w;
+    } else if (t == T - 1 && dpred) {
+      g.head_dpred = dpred;
+      g.head_dpred_bstride = HW;
+      g.head_w = p->head_w;
+    }
+  }
+  g.dh_ext = (l == L - 1 && t == T - 1) ? dh_ext : nullptr;
+  set_batch_range(p, g, b0, nb);
+  LAUNCH(p, K_BWD, st, launch_conv_halo(EPI_BWD, p->dtype, g, p->num_sms, st));
+  return 0;
+}
+
+static int bptt_loop(nint_plan* p, const float* dpred, const float* dseq, const float* dh_ext, bool dc_given, cudaStream_t st) {
+  // ---- BPTT: reverse time, top layer first.  The dgrad conv of step t+1 (and of the layer
+  // above at step t) accumulates dh_t in TMEM; its epilogue is the gate backward of step t and
+  // overwrites the saved gates with dgates in place.
+  const int SB = p->sub_batch > 0 ? p->sub_batch : p->B;
+  for (int b0 = 0; b0 < p->B; b0 += SB) {
+    const int nb = b0 + SB <= p->B ? SB : p->B - b0;
+    for (int t = p->T - 1; t >= 0; --t)
+      for (int l = p->L - 1; l >= 0; --l)
+        if (bwd_step(p, l, t, dpred, dseq, dh_ext, dc_given, st, b0, SB < p->B ? nb : 0)) return 1;
+  }
+  p->gates_valid = false;
+  p->bptt_done = true;
+  return 0;
 }
 
 int nint_backward_bptt(nint_plan* p, const float* dpred, const float* dseq, float* grad_head_weight,
@@ -804,6 +1224,9 @@ int nint_backward_bptt(nint_plan* p, const float* dpred, const float* dseq, floa
   if (check_ready(p)) return 1;
   if (!p->cfg.training) return fail("nint_backward needs a training plan");
   if (!p->fwd_done) return fail("nint_backward before nint_forward");
+  if (!p->gates_valid)
+    return fail("nint_backward: the activations saved by the last forward were already consumed by a backward (BPTT "
+                "turns the saved gates into their gradients in place); run the forward again");
   if (!dpred && !dseq) return fail("nint_backward: no upstream gradient");
   if (dseq && !p->cfg.return_sequence) return fail("dseq requires return_sequence in the plan");
   if (dseq && dpred) return fail("pass either dpred or dseq (fold dpred into dseq[:, T-1])");
@@ -814,69 +1237,17 @@ int nint_backward_bptt(nint_plan* p, const float* dpred, const float* dseq, floa
   const Layer& top = p->layer[L - 1];
   // ---- head gradients (model.py:274): dw = sum dpred * h_T, db = sum dpred
   if (grad_head_weight && grad_head_bias) {
-    CK(cudaMemsetAsync(grad_head_weight, 0, top.hc * 4, st));
+    CK(cudaMemsetAsync(grad_head_weight, 0, top.hc_real * 4, st));
     CK(cudaMemsetAsync(grad_head_bias, 0, 4, st));
     if (dpred)
       LAUNCH(p, K_OTHER, st, launch_head_bwd(p->dtype, slot_ptr(p, top.Hs, T, top.hc_pad), dpred, HW, grad_head_weight, grad_head_bias, HW,
-                         p->B, top.hc, top.hc_pad, st));
+                         p->B, top.hc_real, top.hc_pad, p->head_part, st));
     if (dseq)
       for (int t = 0; t < T; ++t)
         LAUNCH(p, K_OTHER, st, launch_head_bwd(p->dtype, slot_ptr(p, top.Hs, t + 1, top.hc_pad), dseq + t * HW, T * HW, grad_head_weight,
-                           grad_head_bias, HW, p->B, top.hc, top.hc_pad, st));
+                           grad_head_bias, HW, p->B, top.hc_real, top.hc_pad, p->head_part, st));
   }
-  // ---- BPTT: reverse time, top layer first.  The dgrad conv of step t+1 (and of the layer
-  // above at step t) accumulates dh_t in TMEM; its epilogue is the gate backward of step t and
-  // overwrites the saved gates with dgates in place.
-  for (int t = T - 1; t >= 0; --t) {
-    for (int l = L - 1; l >= 0; --l) {
-      Layer& y = p->layer[l];
-      ConvGemmParams g;
-      fill_common(p, y, g);
-      g.n_tile = y.hc;
-      g.n_blocks = 1;
-      g.cluster = bwd_cluster(p, l);
-      g.idesc = idesc_of(p->dtype, 128 * g.cluster, y.hc, 0, 0);
-      int s = 0;
-      if (t < T - 1) {  // dh_t += dgates_{t+1} (*) flip(W_h)
-        g.seg[s].tmap_act = y.tm_G; g.seg[s].wsel = 3; g.seg[s].slot = t + 1;
-        g.seg[s].ksize = y.k; g.seg[s].nchunks = 4 * y.hc / p->ce;
-        ++s;
-      }
-      if (l < L - 1) {  // dh_t += dx of the layer above at the same t
-        Layer& up = p->layer[l + 1];
-        g.seg[s].tmap_act = up.tm_G; g.seg[s].wsel = 2; g.seg[s].slot = t;
-        g.seg[s].ksize = up.k; g.seg[s].nchunks = 4 * up.hc / p->ce;
-        ++s;
-      }
-      g.nseg = s;
-      // epilogue I/O: gates_t -> dgates_t in place, c_t, c_{t-1}, running dc in place
-      g.tm_c = y.tme_C; g.tm_h = y.tme_H; g.tm_g = y.tme_G; g.tm_dc = y.tme_dC;
-      g.slot_g = t;
-      g.slot_c_prev = (t == 0 && p->zero_init) ? -1 : t;
-      g.has_dc_in = (t == T - 1) ? 0 : 1;
-      g.slot_c_in = g.slot_c_out = g.slot_h_out = -1;
-      if (l == L - 1) {
-        if (dseq) {
-          // per-step head gradient; dpred (last step) is folded in by the caller adding it to dseq[:, T-1]
-          g.head_dpred = dseq + t * HW;
-          g.head_dpred_bstride = T * HW;
-          g.head_w = p->head_w;
-        } else if (t == T - 1) {
-          g.head_dpred = dpred;
-          g.head_dpred_bstride = HW;
-          g.head_w = p->head_w;
-        }
-      }
-          if (conv_halo_plan(EPI_BWD, p->dtype, g)) return fail("layer %d: the dgrad kernel's shared-memory plan does not fit (hidden %d, k %d)", l, y.hc, y.k);
-      for (int i = 0; i < g.nseg; ++i) {
-        Layer& owner = g.seg[i].wsel == 2 ? p->layer[l + 1] : y;   // wdx belongs to the layer above
-        if (get_w_map(p, owner, g.seg[i].wsel, g.n_tile, g.n_tile / g.cluster, g.seg[i].ts, &g.seg[i].tmap_w)) return 1;
-      }
-      LAUNCH(p, K_BWD, st, launch_conv_halo(EPI_BWD, p->dtype, g, p->num_sms, st));
-    }
-  }
-  p->bptt_done = true;
-  return 0;
+  return bptt_loop(p, dpred, dseq, nullptr, false, st);
 }
 
 // ---- weight / bias gradient of one layer, batched over all T steps (needs the dgates nint_backward_bptt left)
@@ -886,113 +1257,21 @@ int nint_backward_wgrad(nint_plan* p, int l, float* grad_weight_l, float* grad_b
   if (!p->bptt_done) return fail("nint_backward_wgrad before nint_backward_bptt");
   if (l < 0 || l >= p->L) return fail("layer %d out of range", l);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int T = p->T;
   Layer& y = p->layer[l];
-  CK(cudaMemsetAsync(y.dw_acc, 0, y.dw_acc_bytes, st));
-  CK(cudaMemsetAsync(y.db_acc, 0, 4 * y.hc * 4, st));
-  // The bias gradient is either free (layer 0: x carries 1.0 in padding channel `ones_lane`, so db is that column
-  // of the centre tap) or costs 32 more accumulator columns and one N=32 MMA per K step against a panel of ones,
-  // in the first column block's lightest tap group (the last one when it has room, else the first).
+  const size_t slices = p->deterministic ? static_cast<size_t>(y.det_splits) : 1;
+  CK(cudaMemsetAsync(y.dw_acc, 0, y.dw_acc_bytes * slices, st));
+  CK(cudaMemsetAsync(y.db_acc, 0, 4 * y.hc * 4 * slices, st));
   const int bias_col = (l == 0) ? p->ones_lane : -1;
-  const long long total_tiles = static_cast<long long>(T) * p->B * p->tiles_x * p->tiles_y;
   for (size_t bi = 0; bi < y.wg_blocks.size(); ++bi) {
-    const Layer::WgBlock& blk = y.wg_blocks[bi];
     WgradParams w;
-    memset(&w, 0, sizeof(w));
-    w.halo = 1;
-    w.debug_flags = p->debug_flags;
-    w.b_panel_bytes = wgrad_b_panel_bytes(p->dtype, w.halo, y.k);
-    w.slot_b0[0] = l == 0 ? 0 : 1;
-    w.slot_b0[1] = 0;
-    w.nchunks_b[0] = blk.nch_x;
-    w.nchunks_b[1] = blk.nch_h;
-    w.chan0[0] = blk.chan0_x;
-    w.chan0[1] = blk.chan0_h;
-    w.T = T; w.B = p->B; w.H = p->H; w.W = p->W;
-    w.tile_w = p->tile_w; w.tile_h = p->tile_h; w.tiles_x = p->tiles_x; w.tiles_y = p->tiles_y;
-    w.ksize = y.k;
-    w.hc4 = 4 * y.hc;
-    w.pair = blk.pair ? 1 : 0;
-    if (w.pair && p->dtype == BF16) {
-      w.tmap_dg = y.tmp_G;
-      w.tmap_b[0] = l == 0 ? p->tmp_X : p->layer[l - 1].tmp_H_up;
-      w.tmap_b[1] = y.tmp_H;
-    } else {   // single-CTA kernel, and the tf32 pair kernel: 32-channel boxes (bf16 SWIZZLE_64B / tf32 128B_ATOM_32B)
-      w.tmap_dg = y.tmw_G;
-      w.tmap_b[0] = l == 0 ? p->tmw_X : p->layer[l - 1].tmw_H_up;
-      w.tmap_b[1] = y.tmw_H;
-    }
-    // a block without x (or h) panels never dereferences that map, but kernel parameters must be valid maps
-    if (blk.nch_x == 0) w.tmap_b[0] = w.tmap_b[1];
-    if (blk.nch_h == 0) w.tmap_b[1] = w.tmap_b[0];
-    w.m_blocks = w.pair ? w.hc4 / 256 : (w.hc4 + 127) / 128;
-    w.ncols = y.ncols;
-    w.acc_cols = blk.n_mma;
-    w.real_cols = blk.cols;
-    w.col0 = blk.col0;
-    // tap groups: a CTA keeps (taps in group) x acc_cols accumulator columns in TMEM (512 available)
-    const int bias_cols = (bias_col >= 0 || bi > 0) ? 0 : 32;
-    const int tpg = 512 / blk.n_mma;                     // taps per group
-    if (tpg < 1) return fail("wgrad: %d columns exceed the accumulator", blk.n_mma);
-    int ng = 0, tap = 0;
-    w.group_tap0[0] = 0;
-    const int rest = y.taps % tpg;
-    const bool bias_last = rest > 0 && rest * blk.n_mma + bias_cols <= 512;   // a partial last group with room for the bias
-    const int g0 = bias_last ? tpg : ((512 - bias_cols) / blk.n_mma < tpg ? (512 - bias_cols) / blk.n_mma : tpg);
-    if (g0 < 1) return fail("wgrad: %d columns leave no room for the bias columns", blk.n_mma);
-    while (tap < y.taps) {
-      const int n = ng == 0 ? g0 : tpg;
-      tap = tap + n > y.taps ? y.taps : tap + n;
-      if (ng + 1 > kMaxWgradGroups) return fail("wgrad: too many tap groups");
-      w.group_tap0[++ng] = tap;
-    }
-    w.bias_group = bias_cols == 0 ? -1 : (bias_last ? ng - 1 : 0);
-    w.n_groups = ng;
-    // split-K over pixel tiles: every group gets a share of the SMs in proportion to its MMA cycles per K step
-    // (pair MMA: ~N/2 cycles with a ~40-cycle floor; 1-CTA MMA: ~N*0.67 with a ~88-cycle floor -- DESIGN.md 4)
-    {
-      int units = (w.pair ? p->num_sms / 2 : p->num_sms) / w.m_blocks;   // (group, split) slots
-      if (units < ng) units = ng;
-      auto mma_cost = [&](int n) { return w.pair ? (n / 2 > 40 ? n / 2 : 40) : (n * 2 / 3 > 88 ? n * 2 / 3 : 88); };
-      int cost[kMaxWgradGroups], tot = 0;
-      for (int g = 0; g < ng; ++g) {
-        cost[g] = (w.group_tap0[g + 1] - w.group_tap0[g]) * mma_cost(blk.n_mma) + (g == w.bias_group ? mma_cost(32) : 0);
-        tot += cost[g];
-      }
-      const bool even = (p->debug_flags & 64) != 0;     // experiment: the same split count for every group
-      int used = 0;
-      for (int g = 0; g < ng; ++g) {
-        int sp = even ? units / ng : static_cast<int>(static_cast<long long>(units) * cost[g] / tot);
-        if (sp < 1) sp = 1;
-        w.group_splits[g] = sp;
-        used += sp;
-      }
-      // hand the remaining slots to whichever group has the most work per split
-      while (!even && used < units) {
-        int best = 0;
-        for (int g = 1; g < ng; ++g)
-          if (static_cast<long long>(cost[g]) * w.group_splits[best] > static_cast<long long>(cost[best]) * w.group_splits[g]) best = g;
-        ++w.group_splits[best];
-        ++used;
-      }
-      w.group_unit0[0] = 0;
-      for (int g = 0; g < ng; ++g) {
-        if (w.group_splits[g] > total_tiles) w.group_splits[g] = static_cast<int>(total_tiles);
-        w.group_unit0[g + 1] = w.group_unit0[g] + w.m_blocks * w.group_splits[g];
-      }
-    }
-    w.b_pw = blk.pw;
-    w.a_bufs = blk.a_bufs;
-    w.b_stages = blk.b_stages;
-    if (w.b_stages < 1) return fail("wgrad: operand panels do not fit in shared memory");
-    w.idesc = idesc_of(p->dtype, w.pair ? 256 : 128, blk.n_mma, 1, 1);
-    w.idesc_bias = idesc_of(p->dtype, w.pair ? 256 : 128, 32, 1, 1);
-    w.dw_acc = y.dw_acc;
-    w.db_acc = y.db_acc;
+    if (wgrad_params(p, l, bi, p->num_sms, w)) return 1;
+    if (p->deterministic && wgrad_max_splits(w) > y.det_splits)
+      return fail("deterministic wgrad: this device splits the reduction %d ways, the plan reserved %d slices", wgrad_max_splits(w), y.det_splits);
     LAUNCH(p, K_WGRAD, st, launch_wgrad(p->dtype, w, st));
   }
   if (grad_weight_l)
-    LAUNCH(p, K_OTHER, st, launch_unpack_wgrad(y.dw_acc, y.db_acc, grad_weight_l, grad_bias_l, y.cin, y.hc, y.k, y.ncols, y.cx_pad, bias_col, 0, st));
+    LAUNCH(p, K_OTHER, st, launch_unpack_wgrad(y.dw_acc, y.db_acc, grad_weight_l, grad_bias_l, y.cin, y.hc_real, y.hc, y.k, y.ncols, y.cx_pad,
+                                               bias_col, 0, p->deterministic ? y.det_splits : 0, st));
   return 0;
 }
 
@@ -1002,6 +1281,74 @@ int nint_backward(nint_plan* p, const float* dpred, const float* dseq, float* co
   if (nint_backward_bptt(p, dpred, dseq, grad_head_weight, grad_head_bias, stream)) return 1;
   for (int l = 0; l < p->L; ++l)
     if (nint_backward_wgrad(p, l, grad_weight[l], grad_bias[l], stream)) return 1;
+  return 0;
+}
+
+// dx_t = dgates_t (of layer 0) (*) flip(W_x), all t: x.grad of the reference's autograd
+int nint_backward_input(nint_plan* p, float* dx, void* stream) {
+  if (check_ready(p)) return 1;
+  if (!p->cfg.training || !p->input_grad) return fail("nint_backward_input needs a training plan created with NINT_FLAG_INPUT_GRAD");
+  if (!p->bptt_done) return fail("nint_backward_input before nint_backward_bptt");
+  if (!dx) return fail("nint_backward_input: null dx");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const Layer& y = p->layer[0];
+  const long long HW = static_cast<long long>(p->H) * p->W;
+  const int C = p->cfg.in_channels;
+  for (int t = 0; t < p->T; ++t) {
+    if (dgrad_raw(p, 0, t, 2, y.cin_rows, p->raw, st)) return 1;
+    LAUNCH(p, K_OTHER, st, launch_unpack_raw(p->raw, dx + t * C * HW, p->B, C, p->H, p->W, y.cin_rows, static_cast<long long>(p->T) * C * HW, st));
+  }
+  return 0;
+}
+
+int nint_cell_forward(nint_plan* p, const float* x, const float* h, const float* c, float* h_out, float* c_out,
+                      void* stream) {
+  if (check_ready(p)) return 1;
+  if (p->L != 1 || p->T != 1) return fail("nint_cell_forward needs a plan with one layer and seq_len 1");
+  if (!x || !h || !c) return fail("nint_cell_forward: null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (nint_plan_set_state(p, 0, h, c, stream)) return 1;
+  p->x_bank = false;
+  LAUNCH(p, K_OTHER, st, launch_pack_input(p->dtype, x, 0, p->X, p->B, 1, p->cfg.in_channels, p->H, p->W, p->layer[0].cx_pad, p->ones_lane, st));
+  if (cell_step(p, 0, 0, EPI_FWD, nullptr, st)) return 1;
+  const bool tr = p->cfg.training != 0;
+  p->final_slot_h = tr ? 1 : 1;
+  p->final_slot_c = tr ? 1 : 0;
+  p->fwd_done = true;
+  p->gates_valid = tr;
+  p->bptt_done = false;
+  return nint_plan_get_state(p, 0, h_out, c_out, stream);
+}
+
+int nint_cell_backward(nint_plan* p, const float* dh_out, const float* dc_out, float* dx, float* dh, float* dc,
+                       float* grad_weight, float* grad_bias, void* stream) {
+  if (check_ready(p)) return 1;
+  if (p->L != 1 || p->T != 1 || !p->cfg.training || !p->input_grad)
+    return fail("nint_cell_backward needs a one-layer, seq_len 1 training plan created with NINT_FLAG_INPUT_GRAD");
+  if (!p->fwd_done || !p->gates_valid) return fail("nint_cell_backward: no forward to differentiate (or already consumed)");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Layer& y = p->layer[0];
+  const size_t npix = static_cast<size_t>(p->B) * p->H * p->W;
+  if (dh_out) LAUNCH(p, K_OTHER, st, launch_nchw_to_nhwc_f32(dh_out, p->dh_ext, p->B, y.hc_real, p->H, p->W, y.hc, st));
+  if (dc_out) {
+    CK(cudaMemsetAsync(y.dC, 0, npix * y.hc * 4, st));
+    LAUNCH(p, K_OTHER, st, launch_nchw_to_nhwc_f32(dc_out, y.dC, p->B, y.hc_real, p->H, p->W, y.hc, st));
+  }
+  if (bptt_loop(p, nullptr, nullptr, dh_out ? p->dh_ext : nullptr, dc_out != nullptr, st)) return 1;
+  if (dc) LAUNCH(p, K_OTHER, st, launch_nhwc_to_nchw_f32(y.dC, dc, p->B, y.hc_real, p->H, p->W, y.hc, st));
+  if (dh) {
+    if (dgrad_raw(p, 0, 0, 3, y.hc, p->raw, st)) return 1;
+    LAUNCH(p, K_OTHER, st, launch_unpack_raw(p->raw, dh, p->B, y.hc_real, p->H, p->W, y.hc, static_cast<long long>(y.hc_real) * p->H * p->W, st));
+  }
+  if (dx) {
+    const int C = p->cfg.in_channels;
+    if (dgrad_raw(p, 0, 0, 2, y.cin_rows, p->raw, st)) return 1;
+    LAUNCH(p, K_OTHER, st, launch_unpack_raw(p->raw, dx, p->B, C, p->H, p->W, y.cin_rows, static_cast<long long>(C) * p->H * p->W, st));
+  }
+  if (grad_weight || grad_bias) {
+    if (!grad_weight) return fail("nint_cell_backward: grad_bias without grad_weight");
+    if (nint_backward_wgrad(p, 0, grad_weight, grad_bias, stream)) return 1;
+  }
   return 0;
 }
 

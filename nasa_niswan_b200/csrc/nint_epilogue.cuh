@@ -46,7 +46,7 @@ __device__ __forceinline__ ItemCoord decode_tile(const ConvGemmParams& p, int ti
   const int tx = tile % p.tiles_x;
   int r = tile / p.tiles_x;
   const int ty = r % p.tiles_y;
-  c.b = r / p.tiles_y;   // >= B for the padding tiles of the last group: TMA zero-fills / clips them
+  c.b = p.b0 + r / p.tiles_y;   // padding tiles of the last group: operand loads only (their epilogue I/O is skipped)
   c.x0 = tx * p.tile_w;
   c.y0 = ty * p.tile_h;
   return c;
@@ -626,6 +626,15 @@ __device__ __forceinline__ void epi_math(const ConvGemmParams& p, int warp, int 
             for (int j = 0; j < 8; ++j) hw[j] = 0.f;
           }
           if (p.nseg > 0) tmem_ld_wait();
+          if (p.dh_ext) {   // explicit upstream dh (cell API): one 32-byte read per thread, not a hot path
+            const int y = c.y0 + (row >> 3), x = c.x0 + (row & 7);
+            if (y < p.H && x < p.W) {
+              float e[8];
+              load_elems<float, 8>(p.dh_ext + ((static_cast<long long>(c.b) * p.H + y) * p.W + x) * p.hc + c0, e);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) dh[j] += e[j];
+            }
+          }
           if (!skip) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {

@@ -31,12 +31,17 @@ struct alignas(64) ConvSegment {
   int nchunks;
   int wsel;   // host only: which packed weight tensor of the layer (nint_api.cu get_w_map)
   int ts;     // taps per weight stage of THIS segment (divides ksize^2; conv_halo_plan); taps_per_stage is the largest
+  // frame-bank input (nint_forward_bank): tmap_act is [n_frames][H][W][C] and image b of the launch reads frame
+  // win_start[b] + slot (slot = time step); null = the plan's own [slot][B][H][W][C] tensor
+  const int* win_start;
+  int bank_frames;
 };
 
 struct alignas(64) ConvGemmParams {
   ConvSegment seg[2];
   int nseg;
-  int B, H, W;
+  int B, H, W;   // B = images of THIS launch: images [b0, b0 + B) of the plan's batch (sub-batch-major schedules)
+  int b0;
   int tile_w, tile_h;
   int tiles_x, tiles_y;
   int n_tile;    // UMMA N (accumulator columns per tile)
@@ -66,6 +71,7 @@ struct alignas(64) ConvGemmParams {
   const float* head_dpred;  // optional [B,H,W] (+ stride): dh += head_dpred * head_w[c]
   long long head_dpred_bstride;  // elements between images of head_dpred
   const float* head_w;      // [hc]
+  const float* dh_ext;      // optional [B,H,W,hc] fp32 channels-last: dh += dh_ext (standalone cell backward, model.py:216-231)
   // ---- EPI_RAW: dump fp32 accumulators [B,H,W,n_blocks*n_tile] (debug / generic conv)
   float* raw_out;
 };
@@ -111,6 +117,9 @@ struct alignas(64) WgradParams {
   int b_pw;               // pair kernel: channels per B panel (16 / 32 / 64)
   uint32_t idesc, idesc_bias;
   int hc4;                // 4*hc
+  const int* win_start;   // frame-bank input: tmap_b[0] is [n_frames][H][W][C]; image b at step t reads frame win_start[b] + t
+  float* dw_part;         // deterministic mode: per-split partial sums [max splits][taps][4*hc][ncols] (plain stores) or null
+  float* db_part;         // deterministic mode: [max splits][4*hc] or null
   float* dw_acc;          // [taps][4*hc][ncols] fp32, atomically accumulated (pre-zeroed)
   float* db_acc;          // [4*hc] fp32 (q-order) or null
 };
@@ -124,42 +133,62 @@ int wgrad_pair_b_stages_tf32(int n_mma, int ksize);         // same for the tf32
 cudaError_t launch_wgrad(int dtype, const WgradParams& p, cudaStream_t stream);
 
 // ---- pointwise / layout kernels (nint_pointwise.cu)
-// x [B,T,C,H,W] fp32 (model.py:255) -> X [T][B][H][W][c_pad] E (pad channels zero)
+// x [B,T,C,H,W] fp32 or bf16 (model.py:255) -> X [T][B][H][W][c_pad] E (pad channels zero)
 // ones_lane >= C: that padding channel is set to 1.0 (bias gradient through the wgrad GEMM), -1: none
-cudaError_t launch_pack_input(int dtype, const float* x, void* X, int B, int T, int C, int H, int W, int c_pad,
+cudaError_t launch_pack_input(int dtype, const void* x, int x_bf16, void* X, int B, int T, int C, int H, int W, int c_pad,
                               int ones_lane, cudaStream_t s);
+// frames [N][C][H][W] fp32 or bf16 -> frame bank [N][H][W][c_pad] E (nint_forward_bank)
+cudaError_t launch_pack_frames(int dtype, const void* src, int src_bf16, void* bank, long long N, int C, int H, int W,
+                               int c_pad, int ones_lane, cudaStream_t s);
 // NCHW fp32 <-> NHWC E (state import / export for the cell API)
 cudaError_t launch_pack_state(int dtype, const float* src_nchw, void* dst_nhwc, int B, int C, int H, int W,
                               int c_pad, cudaStream_t s);
 cudaError_t launch_unpack_state(int dtype, const void* src_nhwc, float* dst_nchw, int B, int C, int H, int W,
                                 int c_pad, cudaStream_t s);
-cudaError_t launch_nchw_to_nhwc_f32(const float* src, float* dst, int B, int C, int H, int W, cudaStream_t s);
-cudaError_t launch_nhwc_to_nchw_f32(const float* src, float* dst, int B, int C, int H, int W, cudaStream_t s);
-// OIHW fp32 master weights -> packed operand panels
+cudaError_t launch_nchw_to_nhwc_f32(const float* src, float* dst, int B, int C, int H, int W, int c_pad, cudaStream_t s);
+cudaError_t launch_nhwc_to_nchw_f32(const float* src, float* dst, int B, int C, int H, int W, int c_pad, cudaStream_t s);
+// OIHW fp32 master weights [4*hc_real][cin + hc_real][k][k] -> packed operand panels of a layer whose hidden size is
+// padded to hc >= hc_real (padding channels: zero weights, zero bias -> their h and c stay exactly zero)
 cudaError_t launch_pack_weights_fwd(int dtype, const float* w, const float* bias, void* wpack_x, void* wpack_h,
-                                    float* bias_q, int cin, int hc, int hcb, int k, int cx_pad, int hc_pad, cudaStream_t s);
-cudaError_t launch_pack_weights_bwd(int dtype, const float* w, void* wpack_dx, void* wpack_dh, int cin, int hc,
-                                    int k, cudaStream_t s);
+                                    float* bias_q, int cin, int hc_real, int hc, int hcb, int k, int cx_pad, int hc_pad,
+                                    cudaStream_t s);
+cudaError_t launch_pack_weights_bwd(int dtype, const float* w, void* wpack_dx, void* wpack_dh, int cin, int cin_rows,
+                                    int hc_real, int hc, int k, cudaStream_t s);
 // 1x1 head (model.py:251,274)
 cudaError_t launch_head_fwd(int dtype, const void* h, const float* w, const float* b, float* out, long long npix_per_img,
                             int B, int hc, int hc_pad, long long out_bstride, cudaStream_t s);
+// part: null (fp32 atomics) or head_bwd_blocks(B) * (hc + 1) floats of scratch (deterministic fixed-order sum)
+int head_bwd_blocks(int B);
 cudaError_t launch_head_bwd(int dtype, const void* h, const float* dpred, long long dpred_bstride, float* dw, float* db,
-                            long long npix_per_img, int B, int hc, int hc_pad, cudaStream_t s);
-// dw_acc [taps][4hc (q)][ncols] -> grad weight OIHW [4hc][cin+hc][k][k]; grad bias from db_acc (q), or from column
-// bias_col of the centre tap of dw_acc when bias_col >= 0
-cudaError_t launch_unpack_wgrad(const float* dw_acc, const float* db_acc, float* gw, float* gb, int cin, int hc,
-                                int k, int ncols, int cx_pad, int bias_col, int accumulate, cudaStream_t s);
+                            long long npix_per_img, int B, int hc, int hc_pad, float* part, cudaStream_t s);
+// dw_acc [taps][4hc (q)][ncols] -> grad weight OIHW [4hc_real][cin+hc_real][k][k]; grad bias from db_acc (q), or from
+// column bias_col of the centre tap of dw_acc when bias_col >= 0; nparts > 0: dw_acc / db_acc are `nparts` partial
+// slices summed in order (deterministic mode)
+cudaError_t launch_unpack_wgrad(const float* dw_acc, const float* db_acc, float* gw, float* gb, int cin, int hc_real,
+                                int hc, int k, int ncols, int cx_pad, int bias_col, int accumulate, int nparts,
+                                cudaStream_t s);
+// fp32 accumulator dump [B][H][W][ncols] (EPI_RAW) -> gradient tensor [B][(T)][C][H][W] fp32 (dx / dh of the cell API)
+cudaError_t launch_unpack_raw(const float* raw, float* dst, int B, int C, int H, int W, int ncols, long long dst_bstride,
+                              cudaStream_t s);
 
 // preprocessing fusion: stack levels + emission, z-score, cyclic-longitude / reflect-latitude halo
 cudaError_t launch_fuse_inputs(const float* lev, const float* emis, const float* mean, const float* stdv,
                                const float* statics, int S, float* out, long long N, int L, int H, int W, int Hp, int Wp,
                                int mode, cudaStream_t s);
-// fused training loss MSE + L1 on the cropped prediction (value + gradient); stats = 5 floats of scratch
+// the same, written as the frame bank [N][Hp][Wp][c_pad] E (channels-last operand layout, ones lane)
+cudaError_t launch_fuse_inputs_bank(int dtype, const float* lev, const float* emis, const float* mean, const float* stdv,
+                                    const float* statics, int S, void* out, long long N, int L, int H, int W, int Hp, int Wp,
+                                    int mode, int c_pad, int ones_lane, cudaStream_t s);
+// fused training loss MSE + L1 on the cropped prediction (value + gradient); stats = 5 floats of scratch;
+// y_index != null: the target of sample b is image y_index[b] + y_offset of y (frame bank)
 cudaError_t launch_loss_mse_l1(const float* pred, const float* y, float* dpred, float* stats, float* loss, int B, int H,
-                               int W, int y0, int y1, int x0, int x1, cudaStream_t s);
+                               int W, int y0, int y1, int x0, int x1, const int* y_index, int y_offset, cudaStream_t s);
 // Adam step over a flat fp32 parameter buffer
 cudaError_t launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                         float eps, int step, float grad_scale, cudaStream_t s);
+// the same with {step, lr, bc1, sqrt(bc2)} in device memory (`state`, 4 floats): capturable in a CUDA graph
+cudaError_t launch_adam_dev(float* p, const float* g, float* m, float* v, long long n, float* state, float beta1,
+                            float beta2, float eps, float grad_scale, cudaStream_t s);
 
 // q-order helper (host + device)
 __host__ __device__ inline int q_to_n(int q, int hc) { return ((q >> 4) & 3) * hc + (q >> 6) * 16 + (q & 15); }

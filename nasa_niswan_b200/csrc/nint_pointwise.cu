@@ -28,8 +28,14 @@ __device__ __forceinline__ float from_elem(float v) { return v; }
 // per thread, i.e. a warp writes one contiguous span.  src image stride / dst image index are
 // given by the caller through (src_img_stride, dst slot mapping).
 // ------------------------------------------------------------------------------------------
-template <typename E, int CP>
-__global__ void pack_cl_kernel(const float* __restrict__ src, E* __restrict__ dst, int C, long long HW,
+__device__ __forceinline__ float ldg_f(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float ldg_f(const __nv_bfloat16* p) {
+  return __uint_as_float(static_cast<uint32_t>(__ldg(reinterpret_cast<const unsigned short*>(p))) << 16);
+}
+
+// S = source element type: fp32 (the reference's tensors) or bf16 (host-staged windows: half the PCIe bytes)
+template <typename S, typename E, int CP>
+__global__ void pack_cl_kernel(const S* __restrict__ src, E* __restrict__ dst, int C, long long HW,
                                int n_outer, int n_inner, long long src_outer_stride, long long src_inner_stride,
                                long long dst_outer_stride, long long dst_inner_stride, int ones_lane) {
   // image (o, i): src + o*src_outer_stride + i*src_inner_stride, [C][HW];  dst + o*dst_outer + i*dst_inner, [HW][CP]
@@ -40,17 +46,17 @@ __global__ void pack_cl_kernel(const float* __restrict__ src, E* __restrict__ ds
     const long long img = idx / HW;
     const int i = static_cast<int>(img % n_inner);
     const int o = static_cast<int>(img / n_inner);
-    const float* s = src + o * src_outer_stride + i * src_inner_stride + pix;
+    const S* s = src + o * src_outer_stride + i * src_inner_stride + pix;
     E* d = dst + o * dst_outer_stride + i * dst_inner_stride + pix * CP;
     float v[CP];
 #pragma unroll
-    for (int c = 0; c < CP; ++c) v[c] = (c < C) ? round_for(__ldg(s + c * HW), (E*)nullptr) : (c == ones_lane ? 1.f : 0.f);
+    for (int c = 0; c < CP; ++c) v[c] = (c < C) ? round_for(ldg_f(s + c * HW), (E*)nullptr) : (c == ones_lane ? 1.f : 0.f);
     store_elems<E, CP>(d, v);
   }
 }
 
-template <typename E>
-static cudaError_t pack_cl(const float* src, E* dst, int C, int c_pad, long long HW, int n_outer, int n_inner,
+template <typename S, typename E>
+static cudaError_t pack_cl(const S* src, E* dst, int C, int c_pad, long long HW, int n_outer, int n_inner,
                            long long so, long long si, long long dso, long long dsi, int ones_lane, cudaStream_t s) {
   const long long total = static_cast<long long>(n_outer) * n_inner * HW;
   const int threads = 256;
@@ -58,18 +64,18 @@ static cudaError_t pack_cl(const float* src, E* dst, int C, int c_pad, long long
   if (blocks > 148 * 16) blocks = 148 * 16;
   if (blocks <= 0) return cudaSuccess;
   switch (c_pad) {
-    case 16: pack_cl_kernel<E, 16><<<blocks, threads, 0, s>>>(src, dst, C, HW, n_outer, n_inner, so, si, dso, dsi, ones_lane); break;
-    case 32: pack_cl_kernel<E, 32><<<blocks, threads, 0, s>>>(src, dst, C, HW, n_outer, n_inner, so, si, dso, dsi, ones_lane); break;
-    case 48: pack_cl_kernel<E, 48><<<blocks, threads, 0, s>>>(src, dst, C, HW, n_outer, n_inner, so, si, dso, dsi, ones_lane); break;
-    case 64: pack_cl_kernel<E, 64><<<blocks, threads, 0, s>>>(src, dst, C, HW, n_outer, n_inner, so, si, dso, dsi, ones_lane); break;
+    case 16: pack_cl_kernel<S, E, 16><<<blocks, threads, 0, s>>>(src, dst, C, HW, n_outer, n_inner, so, si, dso, dsi, ones_lane); break;
+    case 32: pack_cl_kernel<S, E, 32><<<blocks, threads, 0, s>>>(src, dst, C, HW, n_outer, n_inner, so, si, dso, dsi, ones_lane); break;
+    case 48: pack_cl_kernel<S, E, 48><<<blocks, threads, 0, s>>>(src, dst, C, HW, n_outer, n_inner, so, si, dso, dsi, ones_lane); break;
+    case 64: pack_cl_kernel<S, E, 64><<<blocks, threads, 0, s>>>(src, dst, C, HW, n_outer, n_inner, so, si, dso, dsi, ones_lane); break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();
 }
 
 // generic (any channel count) variant: one thread per (pixel, 16-channel group)
-template <typename E>
-__global__ void pack_cl_wide_kernel(const float* __restrict__ src, E* __restrict__ dst, int C, int c_pad,
+template <typename S, typename E>
+__global__ void pack_cl_wide_kernel(const S* __restrict__ src, E* __restrict__ dst, int C, int c_pad,
                                     long long HW, int n_outer, int n_inner, long long so, long long si,
                                     long long dso, long long dsi, int ones_lane) {
   const int groups = c_pad / 16;
@@ -82,60 +88,74 @@ __global__ void pack_cl_wide_kernel(const float* __restrict__ src, E* __restrict
     r /= groups;
     const int i = static_cast<int>(r % n_inner);
     const int o = static_cast<int>(r / n_inner);
-    const float* s = src + o * so + i * si + pix;
+    const S* s = src + o * so + i * si + pix;
     E* d = dst + o * dso + i * dsi + pix * c_pad + g * 16;
     float v[16];
 #pragma unroll
     for (int c = 0; c < 16; ++c) {
       const int ch = g * 16 + c;
-      v[c] = (ch < C) ? round_for(__ldg(s + ch * HW), (E*)nullptr) : (ch == ones_lane ? 1.f : 0.f);
+      v[c] = (ch < C) ? round_for(ldg_f(s + ch * HW), (E*)nullptr) : (ch == ones_lane ? 1.f : 0.f);
     }
     store_elems<E, 16>(d, v);
   }
 }
 
-template <typename E>
-static cudaError_t pack_any(const float* src, E* dst, int C, int c_pad, long long HW, int n_outer, int n_inner,
+template <typename S, typename E>
+static cudaError_t pack_any(const S* src, E* dst, int C, int c_pad, long long HW, int n_outer, int n_inner,
                             long long so, long long si, long long dso, long long dsi, cudaStream_t s, int ones_lane = -1) {
   if (c_pad % 16) return cudaErrorInvalidValue;
-  if (c_pad <= 64) return pack_cl<E>(src, dst, C, c_pad, HW, n_outer, n_inner, so, si, dso, dsi, ones_lane, s);
+  if (c_pad <= 64) return pack_cl<S, E>(src, dst, C, c_pad, HW, n_outer, n_inner, so, si, dso, dsi, ones_lane, s);
   const long long total = static_cast<long long>(n_outer) * n_inner * (c_pad / 16) * HW;
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   if (blocks <= 0) return cudaSuccess;
-  pack_cl_wide_kernel<E><<<blocks, 256, 0, s>>>(src, dst, C, c_pad, HW, n_outer, n_inner, so, si, dso, dsi, ones_lane);
+  pack_cl_wide_kernel<S, E><<<blocks, 256, 0, s>>>(src, dst, C, c_pad, HW, n_outer, n_inner, so, si, dso, dsi, ones_lane);
   return cudaGetLastError();
 }
 
-cudaError_t launch_pack_input(int dtype, const float* x, void* X, int B, int T, int C, int H, int W, int c_pad,
+template <typename S>
+static cudaError_t pack_dispatch(int dtype, const S* src, void* dst, int C, int c_pad, long long HW, int n_outer, int n_inner,
+                                 long long so, long long si, long long dso, long long dsi, int ones_lane, cudaStream_t s) {
+  if (dtype == NINT_BF16)
+    return pack_any<S, __nv_bfloat16>(src, reinterpret_cast<__nv_bfloat16*>(dst), C, c_pad, HW, n_outer, n_inner, so, si, dso, dsi, s, ones_lane);
+  return pack_any<S, float>(src, reinterpret_cast<float*>(dst), C, c_pad, HW, n_outer, n_inner, so, si, dso, dsi, s, ones_lane);
+}
+
+cudaError_t launch_pack_input(int dtype, const void* x, int x_bf16, void* X, int B, int T, int C, int H, int W, int c_pad,
                               int ones_lane, cudaStream_t s) {
   // x[b][t] (model.py:266) -> X[t][b]: outer = b, inner = t
   const long long HW = static_cast<long long>(H) * W;
   const long long so = static_cast<long long>(T) * C * HW, si = C * HW;
   const long long dso = HW * c_pad, dsi = static_cast<long long>(B) * HW * c_pad;
-  if (dtype == NINT_BF16)
-    return pack_any<__nv_bfloat16>(x, reinterpret_cast<__nv_bfloat16*>(X), C, c_pad, HW, B, T, so, si, dso, dsi, s, ones_lane);
-  return pack_any<float>(x, reinterpret_cast<float*>(X), C, c_pad, HW, B, T, so, si, dso, dsi, s, ones_lane);
+  if (x_bf16) return pack_dispatch(dtype, reinterpret_cast<const __nv_bfloat16*>(x), X, C, c_pad, HW, B, T, so, si, dso, dsi, ones_lane, s);
+  return pack_dispatch(dtype, reinterpret_cast<const float*>(x), X, C, c_pad, HW, B, T, so, si, dso, dsi, ones_lane, s);
+}
+
+// frames [N][C][H][W] (fp32 or bf16) -> bank [N][H][W][c_pad] E: the HBM-resident frame bank of nint_forward_bank
+cudaError_t launch_pack_frames(int dtype, const void* src, int src_bf16, void* bank, long long N, int C, int H, int W,
+                               int c_pad, int ones_lane, cudaStream_t s) {
+  const long long HW = static_cast<long long>(H) * W;
+  if (N > 0x7fffffffLL) return cudaErrorInvalidValue;
+  if (src_bf16) return pack_dispatch(dtype, reinterpret_cast<const __nv_bfloat16*>(src), bank, C, c_pad, HW, static_cast<int>(N), 1, C * HW, 0, HW * c_pad, 0, ones_lane, s);
+  return pack_dispatch(dtype, reinterpret_cast<const float*>(src), bank, C, c_pad, HW, static_cast<int>(N), 1, C * HW, 0, HW * c_pad, 0, ones_lane, s);
 }
 
 cudaError_t launch_pack_state(int dtype, const float* src, void* dst, int B, int C, int H, int W, int c_pad,
                               cudaStream_t s) {
   const long long HW = static_cast<long long>(H) * W;
-  if (dtype == NINT_BF16)
-    return pack_any<__nv_bfloat16>(src, reinterpret_cast<__nv_bfloat16*>(dst), C, c_pad, HW, B, 1, C * HW, 0,
-                                   HW * c_pad, 0, s);
-  return pack_any<float>(src, reinterpret_cast<float*>(dst), C, c_pad, HW, B, 1, C * HW, 0, HW * c_pad, 0, s);
+  return pack_dispatch(dtype, src, dst, C, c_pad, HW, B, 1, C * HW, 0, HW * c_pad, 0, -1, s);
 }
 
 // channels-last E / fp32 -> NCHW fp32: tile transpose through shared memory (32 pixels x 32 channels)
 template <typename E>
-__global__ void unpack_cl_kernel(const E* __restrict__ src, float* __restrict__ dst, int C, int c_pad, long long HW) {
+__global__ void unpack_cl_kernel(const E* __restrict__ src, float* __restrict__ dst, int C, int c_pad, long long HW,
+                                 long long dst_bstride) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const long long p0 = static_cast<long long>(blockIdx.x) * 32;
   const int c0 = blockIdx.y * 32;
   const E* s = src + static_cast<long long>(b) * HW * c_pad;
-  float* d = dst + static_cast<long long>(b) * C * HW;
+  float* d = dst + static_cast<long long>(b) * dst_bstride;
   for (int r = threadIdx.y; r < 32; r += blockDim.y) {
     const long long p = p0 + r;
     const int c = c0 + threadIdx.x;
@@ -154,19 +174,26 @@ cudaError_t launch_unpack_state(int dtype, const void* src, float* dst, int B, i
   const long long HW = static_cast<long long>(H) * W;
   dim3 grid(static_cast<unsigned>((HW + 31) / 32), (C + 31) / 32, B), block(32, 8);
   if (dtype == NINT_BF16)
-    unpack_cl_kernel<__nv_bfloat16><<<grid, block, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(src), dst, C, c_pad, HW);
+    unpack_cl_kernel<__nv_bfloat16><<<grid, block, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(src), dst, C, c_pad, HW, C * HW);
   else
-    unpack_cl_kernel<float><<<grid, block, 0, s>>>(reinterpret_cast<const float*>(src), dst, C, c_pad, HW);
+    unpack_cl_kernel<float><<<grid, block, 0, s>>>(reinterpret_cast<const float*>(src), dst, C, c_pad, HW, C * HW);
+  return cudaGetLastError();
+}
+cudaError_t launch_unpack_raw(const float* raw, float* dst, int B, int C, int H, int W, int ncols, long long dst_bstride,
+                              cudaStream_t s) {
+  const long long HW = static_cast<long long>(H) * W;
+  dim3 grid(static_cast<unsigned>((HW + 31) / 32), (C + 31) / 32, B), block(32, 8);
+  unpack_cl_kernel<float><<<grid, block, 0, s>>>(raw, dst, C, ncols, HW, dst_bstride);
   return cudaGetLastError();
 }
 
-__global__ void nchw_to_nhwc_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, long long HW) {
+__global__ void nchw_to_nhwc_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int c_pad, long long HW) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const long long p0 = static_cast<long long>(blockIdx.x) * 32;
   const int c0 = blockIdx.y * 32;
   const float* s = src + static_cast<long long>(b) * C * HW;
-  float* d = dst + static_cast<long long>(b) * C * HW;
+  float* d = dst + static_cast<long long>(b) * c_pad * HW;
   for (int r = threadIdx.y; r < 32; r += blockDim.y) {
     const int c = c0 + r;
     const long long p = p0 + threadIdx.x;
@@ -176,17 +203,18 @@ __global__ void nchw_to_nhwc_f32_kernel(const float* __restrict__ src, float* __
   for (int r = threadIdx.y; r < 32; r += blockDim.y) {
     const long long p = p0 + r;
     const int c = c0 + threadIdx.x;
-    if (p < HW && c < C) d[p * C + c] = tile[threadIdx.x][r];
+    if (p < HW && c < C) d[p * c_pad + c] = tile[threadIdx.x][r];
   }
 }
-cudaError_t launch_nchw_to_nhwc_f32(const float* src, float* dst, int B, int C, int H, int W, cudaStream_t s) {
+// c_pad >= C channels per pixel in the NHWC tensor (padding lanes are left untouched)
+cudaError_t launch_nchw_to_nhwc_f32(const float* src, float* dst, int B, int C, int H, int W, int c_pad, cudaStream_t s) {
   const long long HW = static_cast<long long>(H) * W;
   dim3 grid(static_cast<unsigned>((HW + 31) / 32), (C + 31) / 32, B), block(32, 8);
-  nchw_to_nhwc_f32_kernel<<<grid, block, 0, s>>>(src, dst, C, HW);
+  nchw_to_nhwc_f32_kernel<<<grid, block, 0, s>>>(src, dst, C, c_pad, HW);
   return cudaGetLastError();
 }
-cudaError_t launch_nhwc_to_nchw_f32(const float* src, float* dst, int B, int C, int H, int W, cudaStream_t s) {
-  return launch_unpack_state(NINT_TF32, src, dst, B, C, H, W, C, s);
+cudaError_t launch_nhwc_to_nchw_f32(const float* src, float* dst, int B, int C, int H, int W, int c_pad, cudaStream_t s) {
+  return launch_unpack_state(NINT_TF32, src, dst, B, C, H, W, c_pad, s);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -194,13 +222,19 @@ cudaError_t launch_nhwc_to_nchw_f32(const float* src, float* dst, int B, int C, 
 // (model.py:207-211,219).  Packed panel row index = ((nb*nchunks + chunk)*taps + tap)*n_tile + col,
 // each row holds one chunk (CE elements) of K.
 // ------------------------------------------------------------------------------------------
+// gate / hidden channel of kernel column q (q-order, nint_kernels.h)
+__device__ __forceinline__ int q_gate(int q) { return (q >> 4) & 3; }
+__device__ __forceinline__ int q_chan(int q) { return (q >> 6) * 16 + (q & 15); }
+
+// hc = the layer's (padded) hidden size the kernels run with, hc_real <= hc the reference's: weights and biases of the
+// padding channels are zero, so their gates are (0.5, 0.5, 0, 0.5) and their c and h stay exactly 0 (model.py:223-229)
 template <typename E>
 __global__ void pack_w_fwd_kernel(const float* __restrict__ w, const float* __restrict__ bias, E* __restrict__ wx,
-                                  E* __restrict__ wh, float* __restrict__ bias_q, int cin, int hc, int hcb, int k,
-                                  int cx_pad, int hc_pad) {
+                                  E* __restrict__ wh, float* __restrict__ bias_q, int cin, int hc_real, int hc, int hcb,
+                                  int k, int cx_pad, int hc_pad) {
   constexpr int CE = ElemTraits<E>::kPerChunk;
   const int n_blocks = hc / hcb, n_tile = 4 * hcb, taps = k * k;
-  const int ctot = cin + hc;
+  const int ctot = cin + hc_real;
   const int chx = cx_pad / CE, chh = hc_pad / CE;
   const long long nx = static_cast<long long>(n_blocks) * taps * chx * n_tile * CE;
   const long long nh = static_cast<long long>(n_blocks) * taps * chh * n_tile * CE;
@@ -214,175 +248,251 @@ __global__ void pack_w_fwd_kernel(const float* __restrict__ w, const float* __re
     const int tap = static_cast<int>(r % taps); r /= taps;
     const int ch = static_cast<int>(r % nch);
     const int nb = static_cast<int>(r / nch);
-    const int n = q_to_n(nb * n_tile + col, hc);
+    const int q = nb * n_tile + col;
+    const int oc = q_chan(q);
     const int cl = ch * CE + e;
-    const int climit = is_h ? hc : cin;
+    const int climit = is_h ? hc_real : cin;
     float v = 0.f;
-    if (cl < climit) v = w[(static_cast<long long>(n) * ctot + (is_h ? cin + cl : cl)) * taps + tap];
+    if (cl < climit && oc < hc_real)
+      v = w[(static_cast<long long>(q_gate(q) * hc_real + oc) * ctot + (is_h ? cin + cl : cl)) * taps + tap];
     (is_h ? wh : wx)[is_h ? idx - nx : idx] = to_elem<E>(v);
   }
   for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < 4 * hc; q += gridDim.x * blockDim.x)
-    bias_q[q] = bias ? bias[q_to_n(q, hc)] : 0.f;
+    bias_q[q] = (bias && q_chan(q) < hc_real) ? bias[q_gate(q) * hc_real + q_chan(q)] : 0.f;
 }
 
 // dgrad operands: K = q (4*hc), N = input channel, taps flipped (transposed convolution):
 //   wd[chunk][tap'][col][e] = W[n(q = chunk*CE + e)][c(col)][k-1-dy'][k-1-dx']
+// wdx has cin_rows >= cin rows of N (rows >= cin are zero: the padded width of the tensor the gradient flows into),
+// wdh has hc rows (rows >= hc_real zero)
 template <typename E>
 __global__ void pack_w_bwd_kernel(const float* __restrict__ w, E* __restrict__ wdx, E* __restrict__ wdh, int cin,
-                                  int hc, int k) {
+                                  int cin_rows, int hc_real, int hc, int k) {
   constexpr int CE = ElemTraits<E>::kPerChunk;
-  const int taps = k * k, ctot = cin + hc, nch = 4 * hc / CE;
-  const long long nx = wdx ? static_cast<long long>(taps) * nch * cin * CE : 0;
+  const int taps = k * k, ctot = cin + hc_real, nch = 4 * hc / CE;
+  const long long nx = wdx ? static_cast<long long>(taps) * nch * cin_rows * CE : 0;
   const long long nh = static_cast<long long>(taps) * nch * hc * CE;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < nx + nh;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
     const bool is_h = idx >= nx;
     long long r = is_h ? idx - nx : idx;
-    const int ncol = is_h ? hc : cin;
+    const int ncol = is_h ? hc : cin_rows;
     const int e = static_cast<int>(r % CE); r /= CE;
     const int col = static_cast<int>(r % ncol); r /= ncol;
     const int tap = static_cast<int>(r % taps);
     const int ch = static_cast<int>(r / taps);
-    const int n = q_to_n(ch * CE + e, hc);
-    const int c = is_h ? cin + col : col;
-    const float v = w[(static_cast<long long>(n) * ctot + c) * taps + (taps - 1 - tap)];
+    const int q = ch * CE + e;
+    const int oc = q_chan(q);
+    float v = 0.f;
+    if (oc < hc_real && col < (is_h ? hc_real : cin)) {
+      const int c = is_h ? cin + col : col;
+      v = w[(static_cast<long long>(q_gate(q) * hc_real + oc) * ctot + c) * taps + (taps - 1 - tap)];
+    }
     (is_h ? wdh : wdx)[is_h ? idx - nx : idx] = to_elem<E>(v);
   }
 }
 
 cudaError_t launch_pack_weights_fwd(int dtype, const float* w, const float* bias, void* wx, void* wh, float* bias_q,
-                                    int cin, int hc, int hcb, int k, int cx_pad, int hc_pad, cudaStream_t s) {
+                                    int cin, int hc_real, int hc, int hcb, int k, int cx_pad, int hc_pad, cudaStream_t s) {
   if (dtype == NINT_BF16)
     pack_w_fwd_kernel<__nv_bfloat16><<<296, 256, 0, s>>>(w, bias, reinterpret_cast<__nv_bfloat16*>(wx),
-                                                         reinterpret_cast<__nv_bfloat16*>(wh), bias_q, cin, hc, hcb, k,
-                                                         cx_pad, hc_pad);
+                                                         reinterpret_cast<__nv_bfloat16*>(wh), bias_q, cin, hc_real, hc, hcb,
+                                                         k, cx_pad, hc_pad);
   else
     pack_w_fwd_kernel<float><<<296, 256, 0, s>>>(w, bias, reinterpret_cast<float*>(wx), reinterpret_cast<float*>(wh),
-                                                 bias_q, cin, hc, hcb, k, cx_pad, hc_pad);
+                                                 bias_q, cin, hc_real, hc, hcb, k, cx_pad, hc_pad);
   return cudaGetLastError();
 }
-cudaError_t launch_pack_weights_bwd(int dtype, const float* w, void* wdx, void* wdh, int cin, int hc, int k,
-                                    cudaStream_t s) {
+cudaError_t launch_pack_weights_bwd(int dtype, const float* w, void* wdx, void* wdh, int cin, int cin_rows, int hc_real,
+                                    int hc, int k, cudaStream_t s) {
   if (dtype == NINT_BF16)
     pack_w_bwd_kernel<__nv_bfloat16><<<296, 256, 0, s>>>(w, reinterpret_cast<__nv_bfloat16*>(wdx),
-                                                         reinterpret_cast<__nv_bfloat16*>(wdh), cin, hc, k);
+                                                         reinterpret_cast<__nv_bfloat16*>(wdh), cin, cin_rows, hc_real, hc, k);
   else
     pack_w_bwd_kernel<float><<<296, 256, 0, s>>>(w, reinterpret_cast<float*>(wdx), reinterpret_cast<float*>(wdh), cin,
-                                                 hc, k);
+                                                 cin_rows, hc_real, hc, k);
   return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------
 // 1x1 head: pred[b][pix] = bias + sum_c h[b][pix][c] * w[c]    (model.py:274)
-// One thread per pixel, 16-byte loads; a pixel's channel vector (<= 512 B) stays in L1 between
-// the thread's consecutive loads, so DRAM traffic is the algorithmic hc_pad*sizeof(E) per pixel.
+// A pixel's channel vector is CPP = hc_pad*sizeof(E)/16 chunks of 16 bytes; LP = min(CPP, 32) lanes share a pixel,
+// so one warp-wide 16-byte load covers 32/LP whole pixels = 512 contiguous bytes (the one-thread-per-pixel version
+// touched 32 different lines per request and sat at ~40 % of HBM).  Partial dot products meet through shuffles.
 // ------------------------------------------------------------------------------------------
 template <typename E>
-__global__ void head_fwd_kernel(const E* __restrict__ h, const float* __restrict__ w, const float* __restrict__ bias,
-                                float* __restrict__ out, long long npix, int B, int hc, int hc_pad,
-                                long long out_bstride) {
+__global__ void __launch_bounds__(256) head_fwd_kernel(const E* __restrict__ h, const float* __restrict__ w,
+                                                       const float* __restrict__ bias, float* __restrict__ out,
+                                                       long long npix, long long total, int hc, int hc_pad,
+                                                       long long out_bstride, int lp) {
   extern __shared__ float s_w[];
   for (int i = threadIdx.x; i < hc_pad; i += blockDim.x) s_w[i] = i < hc ? w[i] : 0.f;
   __syncthreads();
-  constexpr int V = 16 / sizeof(E);
-  const long long total = static_cast<long long>(B) * npix;
+  constexpr int V = 16 / sizeof(E);             // channels per 16-byte chunk
+  const int cpp = hc_pad / V;                   // chunks per pixel
+  const int lane = threadIdx.x & 31;
+  const int sub = lane & (lp - 1);              // this lane's chunk slot inside its pixel
+  const int ppw = 32 / lp;                      // pixels per warp-wide load
+  const long long warp0 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
   const float b0 = bias[0];
-  for (long long gp = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; gp < total;
-       gp += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const E* hp = h + gp * hc_pad;
-    float acc = b0;
-    for (int c0 = 0; c0 < hc_pad; c0 += V) {
-      float f[V];
-      load_elems<E, V>(hp + c0, f);
+  for (long long p0 = warp0 * ppw; p0 < total; p0 += nwarps * ppw) {
+    const long long gp = p0 + lane / lp;
+    float acc = 0.f;
+    if (gp < total) {
+      const E* hp = h + gp * hc_pad;
+      for (int ck = sub; ck < cpp; ck += lp) {
+        float f[V];
+        load_elems<E, V>(hp + ck * V, f);
 #pragma unroll
-      for (int j = 0; j < V; ++j) acc = fmaf(f[j], s_w[c0 + j], acc);
+        for (int j = 0; j < V; ++j) acc = fmaf(f[j], s_w[ck * V + j], acc);
+      }
     }
-    const long long b = gp / npix;
-    out[b * out_bstride + (gp - b * npix)] = acc;
+    for (int o = lp >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (sub == 0 && gp < total) {
+      const long long b = gp / npix;
+      out[b * out_bstride + (gp - b * npix)] = acc + b0;
+    }
   }
+}
+
+static int head_lanes_per_pixel(int dtype, int hc_pad) {
+  const int cpp = hc_pad / (dtype == NINT_BF16 ? 8 : 4);
+  int lp = 1;
+  while (lp * 2 <= cpp && lp < 32) lp *= 2;     // largest power of two <= min(cpp, 32) (cpp is 4 * k: lp >= 4)
+  return lp;
 }
 
 cudaError_t launch_head_fwd(int dtype, const void* h, const float* w, const float* b, float* out, long long npix,
                             int B, int hc, int hc_pad, long long out_bstride, cudaStream_t s) {
   const long long total = static_cast<long long>(B) * npix;
-  long long blocks = (total + 255) / 256;
+  if (total <= 0) return cudaSuccess;
+  const int lp = head_lanes_per_pixel(dtype, hc_pad);
+  long long blocks = (total * lp + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  if (blocks <= 0) return cudaSuccess;
   if (dtype == NINT_BF16)
     head_fwd_kernel<__nv_bfloat16><<<blocks, 256, hc_pad * 4, s>>>(reinterpret_cast<const __nv_bfloat16*>(h), w, b, out,
-                                                                  npix, B, hc, hc_pad, out_bstride);
+                                                                  npix, total, hc, hc_pad, out_bstride, lp);
   else
-    head_fwd_kernel<float><<<blocks, 256, hc_pad * 4, s>>>(reinterpret_cast<const float*>(h), w, b, out, npix, B, hc,
-                                                          hc_pad, out_bstride);
+    head_fwd_kernel<float><<<blocks, 256, hc_pad * 4, s>>>(reinterpret_cast<const float*>(h), w, b, out, npix, total, hc,
+                                                          hc_pad, out_bstride, lp);
   return cudaGetLastError();
 }
 
-// head backward: dw[c] = sum_pix dpred[pix] * h[pix][c], db = sum dpred   (dh is fused into the
-// gate-backward epilogue).
+// head backward: dw[c] = sum_pix dpred[pix] * h[pix][c], db = sum dpred   (dh is fused into the gate-backward
+// epilogue).  Same access pattern as the forward: LP lanes share a pixel and each lane keeps the partial sums of its
+// own 16-byte channel slices in registers across all its pixels; one shuffle + shared-memory reduction per block at
+// the end, then either fp32 atomics (default) or a per-block partial row reduced in a fixed order by the caller's
+// second launch (deterministic mode: `part` != null, [gridDim.x * gridDim.y][hc_pad + 1]).
 template <typename E>
 __global__ void __launch_bounds__(256) head_bwd_kernel(const E* __restrict__ h, const float* __restrict__ dpred,
                                                        long long dpred_bstride, float* __restrict__ dw,
-                                                       float* __restrict__ db, long long npix, int B, int hc, int hc_pad) {
-  // one warp per pixel: lane l owns channels l, l+32, ... (a warp reads one contiguous row of h per pixel);
-  // partial sums stay in registers across the warp's pixels, then one block reduction + atomics
-  constexpr int KMAX = 8;   // hc_pad <= 256
+                                                       float* __restrict__ db, long long npix, int hc, int hc_pad, int lp,
+                                                       float* __restrict__ part) {
+  constexpr int V = 16 / sizeof(E);
+  constexpr int KMAX = 2;                       // chunk slots per lane: cpp / lp <= 2 (hc_pad <= 256)
+  const int cpp = hc_pad / V;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int nk = hc_pad >> 5;
-  // blockIdx.y = image, blockIdx.x strides over that image's pixels: no division in the loop
+  const int sub = lane & (lp - 1), ppw = 32 / lp;
   const int b = blockIdx.y;
   const float* dp = dpred + b * dpred_bstride;
   const E* hb = h + static_cast<long long>(b) * npix * hc_pad;
-  const int wstride = gridDim.x * (blockDim.x >> 5);
-  float acc[KMAX];
+  float acc[KMAX][V];
 #pragma unroll
-  for (int k = 0; k < KMAX; ++k) acc[k] = 0.f;
+  for (int k = 0; k < KMAX; ++k)
+#pragma unroll
+    for (int j = 0; j < V; ++j) acc[k][j] = 0.f;
   float accb = 0.f;
-  for (int px = blockIdx.x * (blockDim.x >> 5) + warp; px < npix; px += wstride) {
-    const float d = dp[px];
-    const E* row = hb + static_cast<long long>(px) * hc_pad;
+  const long long wstride = static_cast<long long>(gridDim.x) * (blockDim.x >> 5) * ppw;
+  for (long long p0 = (static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + warp) * ppw; p0 < npix; p0 += wstride) {
+    const long long px = p0 + lane / lp;
+    if (px < npix) {
+      const float d = __ldg(dp + px);
+      const E* row = hb + px * hc_pad;
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) {
+        const int ck = sub + k * lp;
+        if (ck < cpp) {
+          float f[V];
+          load_elems<E, V>(row + ck * V, f);
+#pragma unroll
+          for (int j = 0; j < V; ++j) acc[k][j] = fmaf(d, f[j], acc[k][j]);
+        }
+      }
+      if (sub == 0) accb += d;
+    }
+  }
+  // lanes with the same `sub` hold partial sums of the same channels: fold them (offsets lp, 2*lp, ...)
+  for (int o = lp; o < 32; o <<= 1) {
 #pragma unroll
     for (int k = 0; k < KMAX; ++k)
-      if (k < nk) acc[k] = fmaf(d, from_elem(row[k * 32 + lane]), acc[k]);
-    accb += d;
-  }
-  __shared__ float red[8][KMAX * 32 + 1];
 #pragma unroll
-  for (int k = 0; k < KMAX; ++k) red[warp][k * 32 + lane] = acc[k];
-  if (lane == 0) red[warp][KMAX * 32] = accb;
-  __syncthreads();
-  for (int c = threadIdx.x; c < hc; c += blockDim.x) {
-    float s = 0.f;
-    for (int w = 0; w < 8; ++w) s += red[w][c];
-    atomicAdd(dw + c, s);
+      for (int j = 0; j < V; ++j) acc[k][j] += __shfl_xor_sync(0xffffffffu, acc[k][j], o);
+    accb += __shfl_xor_sync(0xffffffffu, accb, o);
   }
-  if (threadIdx.x == 0) {
-    float s = 0.f;
-    for (int w = 0; w < 8; ++w) s += red[w][KMAX * 32];
-    atomicAdd(db, s);
+  __shared__ float red[8][256 + 1];
+  if (lane < lp) {
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+      const int ck = sub + k * lp;
+      if (ck < cpp) {
+#pragma unroll
+        for (int j = 0; j < V; ++j) red[warp][ck * V + j] = acc[k][j];
+      }
+    }
+    if (lane == 0) red[warp][256] = accb;
+  }
+  __syncthreads();
+  const int blk = blockIdx.y * gridDim.x + blockIdx.x;
+  for (int c = threadIdx.x; c <= hc; c += blockDim.x) {
+    const int col = c < hc ? c : 256;            // c == hc: the bias column
+    float sum = 0.f;
+    for (int wv = 0; wv < 8; ++wv) sum += red[wv][col];
+    if (part) part[static_cast<long long>(blk) * (hc + 1) + c] = sum;
+    else atomicAdd(c < hc ? dw + c : db, sum);
+  }
+}
+// deterministic mode: fixed-order sum of the per-block partial rows; accumulates into dw / db
+__global__ void head_bwd_reduce_kernel(const float* __restrict__ part, int nblocks, int hc, float* __restrict__ dw,
+                                       float* __restrict__ db) {
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c <= hc; c += gridDim.x * blockDim.x) {
+    float sum = 0.f;
+    for (int i = 0; i < nblocks; ++i) sum += part[static_cast<long long>(i) * (hc + 1) + c];
+    if (c < hc) dw[c] += sum; else db[0] += sum;
   }
 }
 
+int head_bwd_blocks(int B) {
+  int gx = (148 * 4 + B - 1) / B;
+  return (gx < 1 ? 1 : gx) * B;
+}
 cudaError_t launch_head_bwd(int dtype, const void* h, const float* dpred, long long dpred_bstride, float* dw, float* db,
-                            long long npix, int B, int hc, int hc_pad, cudaStream_t s) {
-  const int block = 256;
-  int gx = (148 * 8 + B - 1) / B;
-  if (gx < 1) gx = 1;
-  const dim3 grid(gx, B);
+                            long long npix, int B, int hc, int hc_pad, float* part, cudaStream_t s) {
+  if (hc_pad > 256) return cudaErrorInvalidValue;
+  const int lp = head_lanes_per_pixel(dtype, hc_pad);
+  const dim3 grid(head_bwd_blocks(B) / B, B);
   if (dtype == NINT_BF16)
-    head_bwd_kernel<__nv_bfloat16><<<grid, block, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(h), dpred, dpred_bstride,
-                                                         dw, db, npix, B, hc, hc_pad);
+    head_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(h), dpred, dpred_bstride,
+                                                       dw, db, npix, hc, hc_pad, lp, part);
   else
-    head_bwd_kernel<float><<<grid, block, 0, s>>>(reinterpret_cast<const float*>(h), dpred, dpred_bstride, dw, db, npix,
-                                                 B, hc, hc_pad);
+    head_bwd_kernel<float><<<grid, 256, 0, s>>>(reinterpret_cast<const float*>(h), dpred, dpred_bstride, dw, db, npix,
+                                               hc, hc_pad, lp, part);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess || !part) return e;
+  head_bwd_reduce_kernel<<<1, 256, 0, s>>>(part, grid.x * grid.y, hc, dw, db);
   return cudaGetLastError();
 }
 
-// dw_acc [taps][4hc (q)][ncols] -> grad W[n][c][dy][dx];  col(c) = c (x part) or cx_pad + (c - cin) (h part)
+// dw_acc [taps][4hc (q)][ncols] -> grad W[n][c][dy][dx];  col(c) = c (x part) or cx_pad + (c - cin) (h part).
+// nparts > 0 (deterministic mode): dw_acc / db_acc hold `nparts` partial-sum slices one after the other, summed here in a
+// fixed order.
 __global__ void unpack_wgrad_kernel(const float* __restrict__ dw_acc, const float* __restrict__ db_acc,
-                                    float* __restrict__ gw, float* __restrict__ gb, int cin, int hc, int k, int ncols,
-                                    int cx_pad, int bias_col, int accumulate) {
-  const int taps = k * k, ctot = cin + hc, hc4 = 4 * hc;
+                                    float* __restrict__ gw, float* __restrict__ gb, int cin, int hc_real, int hc, int k,
+                                    int ncols, int cx_pad, int bias_col, int accumulate, int nparts) {
+  const int taps = k * k, ctot = cin + hc_real, hc4 = 4 * hc;
   const long long total = static_cast<long long>(hc4) * ctot * taps;
+  const long long slice = static_cast<long long>(taps) * hc4 * ncols;
+  const int np = nparts > 0 ? nparts : 1;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
     // read-coalesced order: (tap, q, c)
@@ -390,23 +500,32 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ dw_acc, const floa
     long long r = idx / ctot;
     const int q = static_cast<int>(r % hc4);
     const int tap = static_cast<int>(r / hc4);
+    if (q_chan(q) >= hc_real) continue;   // padding channel of the hidden size: no such row in the reference's weight
     const int col = c < cin ? c : cx_pad + (c - cin);
-    const float v = dw_acc[(static_cast<long long>(tap) * hc4 + q) * ncols + col];
-    float* dst = gw + (static_cast<long long>(q_to_n(q, hc)) * ctot + c) * taps + tap;
+    const float* src = dw_acc + (static_cast<long long>(tap) * hc4 + q) * ncols + col;
+    float v = 0.f;
+    for (int s = 0; s < np; ++s) v += src[s * slice];
+    float* dst = gw + (static_cast<long long>(q_gate(q) * hc_real + q_chan(q)) * ctot + c) * taps + tap;
     *dst = accumulate ? *dst + v : v;
   }
   if (gb) {
     for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < hc4; q += gridDim.x * blockDim.x) {
-      float* dst = gb + q_to_n(q, hc);
+      if (q_chan(q) >= hc_real) continue;
+      float* dst = gb + q_gate(q) * hc_real + q_chan(q);
       // bias_col: x carried 1.0 in that channel, so the centre tap's column is sum_pixels dgates = db
-      const float v = bias_col >= 0 ? dw_acc[(static_cast<long long>(taps / 2) * hc4 + q) * ncols + bias_col] : db_acc[q];
+      float v = 0.f;
+      for (int s = 0; s < np; ++s)
+        v += bias_col >= 0 ? dw_acc[s * slice + (static_cast<long long>(taps / 2) * hc4 + q) * ncols + bias_col]
+                           : db_acc[static_cast<long long>(s) * hc4 + q];
       *dst = accumulate ? *dst + v : v;
     }
   }
 }
-cudaError_t launch_unpack_wgrad(const float* dw_acc, const float* db_acc, float* gw, float* gb, int cin, int hc, int k,
-                                int ncols, int cx_pad, int bias_col, int accumulate, cudaStream_t s) {
-  unpack_wgrad_kernel<<<296, 256, 0, s>>>(dw_acc, db_acc, gw, gb, cin, hc, k, ncols, cx_pad, bias_col, accumulate);
+cudaError_t launch_unpack_wgrad(const float* dw_acc, const float* db_acc, float* gw, float* gb, int cin, int hc_real,
+                                int hc, int k, int ncols, int cx_pad, int bias_col, int accumulate, int nparts,
+                                cudaStream_t s) {
+  unpack_wgrad_kernel<<<296, 256, 0, s>>>(dw_acc, db_acc, gw, gb, cin, hc_real, hc, k, ncols, cx_pad, bias_col, accumulate,
+                                          nparts);
   return cudaGetLastError();
 }
 
@@ -459,6 +578,80 @@ cudaError_t launch_fuse_inputs(const float* lev, const float* emis, const float*
   return cudaGetLastError();
 }
 
+// The same fusion written straight into the model's operand layout: the frame bank
+// [N][Hp][Wp][CP] of E (bf16, or fp32 holding tf32-rounded values), channels-last with zero padding lanes and the
+// constant-1 lane the bias gradient rides on -- what nint_forward_bank's TMA descriptors read, so no fp32 NCHW
+// intermediate and no second packing pass exist.  One thread per output pixel: for a fixed channel the warp's loads are
+// 32 consecutive longitudes of one source row (coalesced; the cyclic wrap splits at most one request), and a thread
+// writes its pixel's CP channels as CP*sizeof(E)/32 256-bit stores (a warp covers one contiguous span).
+template <typename E, int CP>
+__global__ void __launch_bounds__(256) fuse_bank_kernel(const float* __restrict__ lev, const float* __restrict__ emis,
+                                                        const float* __restrict__ mean, const float* __restrict__ stdv,
+                                                        const float* __restrict__ statics, int S, E* __restrict__ out,
+                                                        long long N, int L, int H, int W, int Hp, int Wp, int mode,
+                                                        int ones_lane) {
+  const int C = L + 1 + S;
+  const int left = (Wp - W) / 2, top = (Hp - H) / 2, bot = Hp - H - top;
+  const long long HWp = static_cast<long long>(Hp) * Wp, HW = static_cast<long long>(H) * W;
+  const long long total = N * HWp;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long n = i / HWp;
+    const int rem = static_cast<int>(i - n * HWp);
+    const int yp = rem / Wp, xp = rem - yp * Wp;
+    int xs = xp - left;                       // cyclic longitude (dataset.py:67-80)
+    if (xs < 0) xs += W;
+    if (xs >= W) xs -= W;
+    int ys = yp - top;
+    bool flip = false;                        // mode 1: halo rows carry the channels in reverse order (dataset.py:96)
+    if (ys < 0) {                             // upper halo: rows 1..top (dataset.py:82-98)
+      if (mode == 0) ys = top - yp; else { ys = 1 + yp; flip = true; }
+    } else if (ys >= H) {                     // lower halo: rows H-bot-1..H-2
+      const int j = ys - H;
+      if (mode == 0) ys = H - 2 - j; else { ys = H - bot - 1 + j; flip = true; }
+    }
+    const long long pix = static_cast<long long>(ys) * W + xs;
+    const float* lev_n = lev + n * L * HW + pix;
+    const float* emis_n = emis + n * HW + pix;
+    float v[CP];
+#pragma unroll
+    for (int c = 0; c < CP; ++c) {
+      float r = (c == ones_lane) ? 1.f : 0.f;
+      if (c < C) {
+        const int cs = flip ? C - 1 - c : c;
+        if (cs > L) r = __ldg(statics + (cs - L - 1) * HW + pix);        // static attributes: already z-scored
+        else r = ((cs < L ? __ldg(lev_n + cs * HW) : __ldg(emis_n)) - __ldg(mean + cs)) / __ldg(stdv + cs);
+        r = round_for(r, (E*)nullptr);
+      }
+      v[c] = r;
+    }
+    store_elems<E, CP>(out + i * CP, v);
+  }
+}
+template <typename E>
+static cudaError_t fuse_bank(const float* lev, const float* emis, const float* mean, const float* stdv, const float* statics,
+                             int S, E* out, long long N, int L, int H, int W, int Hp, int Wp, int mode, int c_pad,
+                             int ones_lane, cudaStream_t s) {
+  long long blocks = (N * Hp * Wp + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks <= 0) return cudaSuccess;
+  switch (c_pad) {
+    case 16: fuse_bank_kernel<E, 16><<<blocks, 256, 0, s>>>(lev, emis, mean, stdv, statics, S, out, N, L, H, W, Hp, Wp, mode, ones_lane); break;
+    case 32: fuse_bank_kernel<E, 32><<<blocks, 256, 0, s>>>(lev, emis, mean, stdv, statics, S, out, N, L, H, W, Hp, Wp, mode, ones_lane); break;
+    case 48: fuse_bank_kernel<E, 48><<<blocks, 256, 0, s>>>(lev, emis, mean, stdv, statics, S, out, N, L, H, W, Hp, Wp, mode, ones_lane); break;
+    case 64: fuse_bank_kernel<E, 64><<<blocks, 256, 0, s>>>(lev, emis, mean, stdv, statics, S, out, N, L, H, W, Hp, Wp, mode, ones_lane); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+cudaError_t launch_fuse_inputs_bank(int dtype, const float* lev, const float* emis, const float* mean, const float* stdv,
+                                    const float* statics, int S, void* out, long long N, int L, int H, int W, int Hp, int Wp,
+                                    int mode, int c_pad, int ones_lane, cudaStream_t s) {
+  if (dtype == NINT_BF16)
+    return fuse_bank<__nv_bfloat16>(lev, emis, mean, stdv, statics, S, reinterpret_cast<__nv_bfloat16*>(out), N, L, H, W, Hp, Wp, mode, c_pad, ones_lane, s);
+  return fuse_bank<float>(lev, emis, mean, stdv, statics, S, reinterpret_cast<float*>(out), N, L, H, W, Hp, Wp, mode, c_pad, ones_lane, s);
+}
+
 // ------------------------------------------------------------------------------------------
 // training loss (train.py:74-75,102,105): MSELoss(y, p) + L1Loss(y, p), both 'mean', on the cropped prediction
 // pred[:, 0, y0:y1, x0:x1]; forward value and d loss / d pred in one pass.  stats = {sum (p-y)^2, sum |p-y|,
@@ -468,7 +661,7 @@ cudaError_t launch_fuse_inputs(const float* lev, const float* emis, const float*
 __global__ void __launch_bounds__(256) loss_mse_l1_kernel(const float* __restrict__ pred, const float* __restrict__ y,
                                                           float* __restrict__ dpred, float* __restrict__ stats,
                                                           float* __restrict__ loss, int B, int H, int W, int y0, int y1,
-                                                          int x0, int x1) {
+                                                          int x0, int x1, const int* __restrict__ y_index, int y_offset) {
   const int hc = y1 - y0, wc = x1 - x0;
   const long long total = static_cast<long long>(B) * H * W;
   const float inv_n = 1.0f / (static_cast<float>(B) * hc * wc);
@@ -481,7 +674,9 @@ __global__ void __launch_bounds__(256) loss_mse_l1_kernel(const float* __restric
     const long long b = r / H;
     float g = 0.f;
     if (yy >= y0 && yy < y1 && x >= x0 && x < x1) {
-      const float t = y[(b * hc + (yy - y0)) * wc + (x - x0)];
+      // frame bank: the target of sample b is image y_index[b] + y_offset of y (dataset.py:600: y[i + seq_len - 1])
+      const long long yb = y_index ? static_cast<long long>(__ldg(y_index + b)) + y_offset : b;
+      const float t = y[(yb * hc + (yy - y0)) * wc + (x - x0)];
       const float d = pred[i] - t;
       s2 = fmaf(d, d, s2);
       s1 += fabsf(d);
@@ -519,10 +714,10 @@ __global__ void __launch_bounds__(256) loss_mse_l1_kernel(const float* __restric
   }
 }
 cudaError_t launch_loss_mse_l1(const float* pred, const float* y, float* dpred, float* stats, float* loss, int B, int H,
-                               int W, int y0, int y1, int x0, int x1, cudaStream_t s) {
+                               int W, int y0, int y1, int x0, int x1, const int* y_index, int y_offset, cudaStream_t s) {
   cudaError_t e = cudaMemsetAsync(stats, 0, 5 * sizeof(float), s);
   if (e != cudaSuccess) return e;
-  loss_mse_l1_kernel<<<148, 256, 0, s>>>(pred, y, dpred, stats, loss, B, H, W, y0, y1, x0, x1);
+  loss_mse_l1_kernel<<<148, 256, 0, s>>>(pred, y, dpred, stats, loss, B, H, W, y0, y1, x0, x1, y_index, y_offset);
   return cudaGetLastError();
 }
 
@@ -552,6 +747,41 @@ cudaError_t launch_adam(float* p, const float* g, float* m, float* v, long long 
   if (grid > 148 * 8) grid = 148 * 8;
   if (grid < 1) grid = 1;
   adam_kernel<<<grid, 256, 0, s>>>(p, g, m, v, n, lr, beta1, beta2, eps, bc1, bc2_sqrt, grad_scale);
+  return cudaGetLastError();
+}
+
+
+// The same update with the step count and learning rate read from DEVICE memory, so a captured CUDA graph of the
+// training step stays valid as both change: state = {step (as float), lr}.  adam_tick_kernel advances the step and
+// derives the bias corrections once; the update kernel reads them.
+__global__ void adam_tick_kernel(float* __restrict__ state, float beta1, float beta2) {
+  const float step = state[0] + 1.f;
+  state[0] = step;
+  state[2] = 1.f - powf(beta1, step);            // bc1
+  state[3] = sqrtf(1.f - powf(beta2, step));     // sqrt(bc2)
+}
+__global__ void __launch_bounds__(256) adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                       float* __restrict__ v, long long n, const float* __restrict__ state,
+                                                       float beta1, float beta2, float eps, float grad_scale) {
+  const float lr = state[1], bc1 = state[2], bc2_sqrt = state[3];
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float gi = g[i] * grad_scale;
+    const float mi = fmaf(beta1, m[i], (1.f - beta1) * gi);
+    const float vi = fmaf(beta2, v[i], (1.f - beta2) * gi * gi);
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] -= (lr / bc1) * (mi / denom);
+  }
+}
+cudaError_t launch_adam_dev(float* p, const float* g, float* m, float* v, long long n, float* state, float beta1,
+                            float beta2, float eps, float grad_scale, cudaStream_t s) {
+  adam_tick_kernel<<<1, 1, 0, s>>>(state, beta1, beta2);
+  int grid = static_cast<int>((n + 255) / 256);
+  if (grid > 148 * 8) grid = 148 * 8;
+  if (grid < 1) grid = 1;
+  adam_dev_kernel<<<grid, 256, 0, s>>>(p, g, m, v, n, state, beta1, beta2, eps, grad_scale);
   return cudaGetLastError();
 }
 

@@ -165,8 +165,10 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
           if (leader) {
             mbar_arrive_expect_tx(&b_full[bs], static_cast<uint32_t>(hrows * ROWB * bpanels));
             uint8_t* dst = sB + bs * b_stage_bytes;
+            // frame bank: the x tensor is [n_frames][H][W][C] and image b of step t is frame win_start[b] + t
+            const int xb = p.win_start ? __ldg(p.win_start + b) + t : b, xs = p.win_start ? 0 : p.slot_b0[0] + t;
             for (int j = 0; j < p.nchunks_b[0]; ++j, dst += p.b_panel_bytes)
-              tma_load_5d(dst, &p.tmap_b[0], &b_full[bs], p.chan0[0] + j * CE, x0 - pad, y0 - pad, b, p.slot_b0[0] + t);
+              tma_load_5d(dst, &p.tmap_b[0], &b_full[bs], p.chan0[0] + j * CE, x0 - pad, y0 - pad, xb, xs);
             for (int j = 0; j < p.nchunks_b[1]; ++j, dst += p.b_panel_bytes)
               tma_load_5d(dst, &p.tmap_b[1], &b_full[bs], p.chan0[1] + j * CE, x0 - pad, y0 - pad, b, p.slot_b0[1] + t);
           }
@@ -182,8 +184,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
           if (leader) {
             mbar_arrive_expect_tx(&b_full[bs], panel_tx * bpanels);
             uint8_t* dst = sB + bs * b_stage_bytes;
+            const int xb = p.win_start ? __ldg(p.win_start + b) + t : b, xs = p.win_start ? 0 : p.slot_b0[0] + t;
             for (int j = 0; j < p.nchunks_b[0]; ++j, dst += PANEL)
-              tma_load_5d(dst, &p.tmap_b[0], &b_full[bs], p.chan0[0] + j * CE, x0 + dx, y0 + dy, b, p.slot_b0[0] + t);
+              tma_load_5d(dst, &p.tmap_b[0], &b_full[bs], p.chan0[0] + j * CE, x0 + dx, y0 + dy, xb, xs);
             for (int j = 0; j < p.nchunks_b[1]; ++j, dst += PANEL)
               tma_load_5d(dst, &p.tmap_b[1], &b_full[bs], p.chan0[1] + j * CE, x0 + dx, y0 + dy, b, p.slot_b0[1] + t);
           }
@@ -292,15 +295,23 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
     mbar_wait(acc_full, 0);
     tc_fence_after();
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    // deterministic mode (dw_part): every split stores its partial sums into its own slice and a fixed-order
+    // reduction follows (unpack_wgrad_kernel); default: fp32 atomics into dw_acc (summation order varies run to run)
+    const long long part = static_cast<long long>(p.ksize) * p.ksize * p.hc4 * p.ncols * split;
     for (int ti = 0; ti < ntaps; ++ti) {
-      float* dst = p.dw_acc + (static_cast<long long>(tap_begin + ti) * p.hc4 + q) * p.ncols + p.col0;
+      const long long off = (static_cast<long long>(tap_begin + ti) * p.hc4 + q) * p.ncols + p.col0;
+      float* dst = p.dw_part ? p.dw_part + part + off : p.dw_acc + off;
       for (int c0 = 0; c0 < p.acc_cols; c0 += 16) {
         float v[16];
         tmem_ld16(taddr + ti * p.acc_cols + c0, v);
         tmem_ld_wait();
         if (valid) {
+          if (p.dw_part) {
+            store_elems<float, 16>(dst + c0, v);
+          } else {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) atomicAdd(dst + c0 + j, v[j]);
+            for (int j = 0; j < 16; ++j) atomicAdd(dst + c0 + j, v[j]);
+          }
         }
       }
     }
@@ -308,7 +319,10 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
       float v[16];
       tmem_ld16(taddr + ntaps * p.acc_cols, v);
       tmem_ld_wait();
-      if (valid) atomicAdd(p.db_acc + q, v[0]);
+      if (valid) {
+        if (p.db_part) p.db_part[static_cast<long long>(split) * p.hc4 + q] = v[0];
+        else atomicAdd(p.db_acc + q, v[0]);
+      }
     }
   }
   tc_fence_before();
@@ -502,10 +516,11 @@ wgrad_pair_kernel(const __grid_constant__ WgradParams p) {
         if (lead_cta && jpar == 0) mbar_arrive_expect_tx(&b_full[bs], static_cast<uint32_t>(2 * bp_cta * hrows * rowb));
         const uint32_t bar = mapa_rank(smem_u32(&b_full[bs]), 0);
         uint8_t* dst = sB + bs * b_stage_bytes + jpar * b_panel;
+        const int xb = p.win_start ? __ldg(p.win_start + b) + t : b, xs = p.win_start ? 0 : p.slot_b0[0] + t;   // frame bank
         for (int j = jpar; j < bp_cta; j += 2, dst += 2 * b_panel) {
           const int pj = static_cast<int>(crank) * bp_cta + j;   // 16-channel panel of the concatenated input
           if (pj < bx16)
-            tma_load_5d_pair(dst, &p.tmap_b[0], bar, p.chan0[0] + pj * pw, x0 - pad, y0 - pad, b, p.slot_b0[0] + t);
+            tma_load_5d_pair(dst, &p.tmap_b[0], bar, p.chan0[0] + pj * pw, x0 - pad, y0 - pad, xb, xs);
           else
             tma_load_5d_pair(dst, &p.tmap_b[1], bar, p.chan0[1] + (pj - bx16) * pw, x0 - pad, y0 - pad, b, p.slot_b0[1] + t);
         }
@@ -618,21 +633,28 @@ wgrad_pair_kernel(const __grid_constant__ WgradParams p) {
     mbar_wait(acc_full, 0);
     tc_fence_after();
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    const long long part = static_cast<long long>(p.ksize) * p.ksize * p.hc4 * p.ncols * split;   // deterministic mode
     for (int ti = 0; ti < ntaps; ++ti) {
-      float* dst = p.dw_acc + (static_cast<long long>(tap_begin + ti) * p.hc4 + q) * p.ncols + p.col0;
+      const long long off = (static_cast<long long>(tap_begin + ti) * p.hc4 + q) * p.ncols + p.col0;
+      float* dst = p.dw_part ? p.dw_part + part + off : p.dw_acc + off;
       for (int c0 = 0; c0 < p.real_cols; c0 += 16) {   // columns beyond real_cols are the tf32 variant's zero panel
         float v[16];
         tmem_ld16(taddr + ti * p.acc_cols + c0, v);
         tmem_ld_wait();
+        if (p.dw_part) {
+          store_elems<float, 16>(dst + c0, v);
+        } else {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) atomicAdd(dst + c0 + j, v[j]);
+          for (int j = 0; j < 16; ++j) atomicAdd(dst + c0 + j, v[j]);
+        }
       }
     }
     if (do_bias) {
       float v[16];
       tmem_ld16(taddr + ntaps * p.acc_cols, v);
       tmem_ld_wait();
-      atomicAdd(p.db_acc + q, v[0]);
+      if (p.db_part) p.db_part[static_cast<long long>(split) * p.hc4 + q] = v[0];
+      else atomicAdd(p.db_acc + q, v[0]);
     }
   }
   tc_fence_before();

@@ -70,10 +70,41 @@ def training_loss(pred: torch.Tensor, y: torch.Tensor, crop: Optional[Tuple[int,
     return F.mse_loss(p, y) + F.l1_loss(p, y)
 
 
+def bind_to_gpu_numa_node(device) -> Optional[int]:
+    """Pins this process (and therefore the first-touch placement of the pinned staging buffers it allocates next) to
+    the CPUs of the NUMA node the GPU hangs off.  With 8 ranks per box all staging from node 0, host-to-device copies
+    share one socket's memory controllers and inter-socket links; bound, every rank streams from local DRAM through its
+    own PCIe root.  Returns the node, or None when the topology cannot be read (nothing is changed then)."""
+    try:
+        dev = torch.device(device)
+        idx = dev.index if dev.index is not None else torch.cuda.current_device()
+        props = torch.cuda.get_device_properties(idx)
+        bus, dom, devid = getattr(props, "pci_bus_id", None), getattr(props, "pci_domain_id", 0), getattr(props, "pci_device_id", 0)
+        if bus is None:
+            return None
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{devid:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except (OSError, ValueError, AttributeError, RuntimeError):
+        return None
+
+
 class HostFeeder:
     """Double-buffered host -> device input path: the pinned-memory copy of batch i+1 (train.py:92-93) runs on a
-    side stream while batch i trains.  `put` starts the copy and returns a handle, `get` makes the current stream
-    wait for it, `release` marks the device buffers reusable once the step that read them has been enqueued."""
+    side stream while batch i trains.  `put` starts the copies of any number of host tensors and returns a handle, `get`
+    makes the current stream wait for them and returns the device tensors, `release` marks the device buffers reusable
+    once the step that read them has been enqueued.  Host tensors keep their dtype: windows staged as bf16 cross PCIe
+    at half the bytes of fp32 and give identical results (the model rounds fp32 inputs to bf16 anyway)."""
 
     def __init__(self, device, depth: int = 2):
         self.device = torch.device(device)
@@ -81,39 +112,38 @@ class HostFeeder:
         self.slots = [None] * depth
         self.i = 0
 
-    def put(self, xh: torch.Tensor, yh: torch.Tensor):
+    def put(self, *host_tensors):
         k = self.i % len(self.slots)
         self.i += 1
         slot = self.slots[k]
-        if slot is None or slot["x"].shape != xh.shape or slot["y"].shape != yh.shape:
-            slot = {"x": torch.empty(xh.shape, dtype=xh.dtype, device=self.device),
-                    "y": torch.empty(yh.shape, dtype=yh.dtype, device=self.device),
+        if slot is None or [(t.shape, t.dtype) for t in slot["dev"]] != [(t.shape, t.dtype) for t in host_tensors]:
+            slot = {"dev": [torch.empty(t.shape, dtype=t.dtype, device=self.device) for t in host_tensors],
                     "ready": torch.cuda.Event(), "free": None}
             self.slots[k] = slot
         with torch.cuda.stream(self.stream):
             if slot["free"] is not None:
                 self.stream.wait_event(slot["free"])      # the step that last read this slot has finished
-            slot["x"].copy_(xh, non_blocking=True)
-            slot["y"].copy_(yh, non_blocking=True)
+            for d, h in zip(slot["dev"], host_tensors):
+                d.copy_(h, non_blocking=True)
             slot["ready"].record(self.stream)
         return slot
 
-    @staticmethod
-    def get(slot):
-        torch.cuda.current_stream().wait_event(slot["ready"])
-        return slot["x"], slot["y"]
+    def get(self, slot):
+        torch.cuda.current_stream(self.device).wait_event(slot["ready"])
+        return tuple(slot["dev"])
 
-    @staticmethod
-    def release(slot):
+    def release(self, slot):
         ev = torch.cuda.Event()
-        ev.record(torch.cuda.current_stream())
+        ev.record(torch.cuda.current_stream(self.device))
         slot["free"] = ev
 
 
 class NativeAdam:
-    """torch.optim.Adam(lr, betas) (train.py:71) as ONE kernel over flat buffers (nint_adam_step).  The parameters
+    """torch.optim.Adam(lr, betas) (train.py:71) as ONE kernel over flat buffers (nint_adam_step_dev).  The parameters
     are re-pointed at views of one flat fp32 buffer (names, shapes and values unchanged: `state_dict` is untouched);
-    `state_dict` / `load_state_dict` speak torch.optim.Adam's format so utils.py:23-50 checkpoints interoperate."""
+    `state_dict` / `load_state_dict` speak torch.optim.Adam's format so utils.py:23-50 checkpoints interoperate.
+    The step count and the learning rate live in device memory (`self.state` = {step, lr, ...}): no launch argument
+    changes from step to step, so a CUDA graph of the whole training step can be replayed."""
 
     def __init__(self, params, flat_grads: torch.Tensor, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
         from . import _lib
@@ -123,6 +153,7 @@ class NativeAdam:
         self.step_count = 0
         n = sum(p.numel() for p in self.params)
         dev = self.params[0].device
+        self.device = dev
         self.flat_params = torch.empty(n, dtype=torch.float32, device=dev)
         off = 0
         with torch.no_grad():
@@ -135,25 +166,35 @@ class NativeAdam:
         self.exp_avg = torch.zeros_like(self.flat_params)
         self.exp_avg_sq = torch.zeros_like(self.flat_params)
         self.param_groups = [{"lr": self.lr, "betas": self.betas, "eps": self.eps}]   # what LR schedulers touch
+        self.state = torch.zeros(4, dtype=torch.float32, device=dev)                  # {step, lr, bc1, sqrt(bc2)}
+        self._lr_on_device = None
+        self._sync_lr()
+
+    def _sync_lr(self):
+        lr = float(self.param_groups[0]["lr"])
+        if lr != self._lr_on_device:        # schedulers change it once per epoch: a 4-byte upload then, nothing per step
+            self.state[1:2].copy_(torch.tensor([lr], dtype=torch.float32), non_blocking=False)
+            self._lr_on_device = lr
 
     def step(self, grad_scale: float = 1.0):
-        import ctypes
         from . import _lib
         self.step_count += 1
-        lr = float(self.param_groups[0]["lr"])
-        vp = lambda t: ctypes.c_void_p(t.data_ptr())
-        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-        _lib.check(self.lib.nint_adam_step(vp(self.flat_params), vp(self.flat_grads), vp(self.exp_avg), vp(self.exp_avg_sq),
-                                           self.flat_params.numel(), lr, self.betas[0], self.betas[1], self.eps,
-                                           self.step_count, float(grad_scale), st), "nint_adam_step")
+        self._sync_lr()
+        vp = _lib.ptr
+        with _lib.on_device(self.device):
+            _lib.check(self.lib.nint_adam_step_dev(vp(self.flat_params), vp(self.flat_grads), vp(self.exp_avg),
+                                                   vp(self.exp_avg_sq), self.flat_params.numel(), vp(self.state),
+                                                   self.betas[0], self.betas[1], self.eps, float(grad_scale),
+                                                   _lib.stream_ptr(self.device)), "nint_adam_step_dev")
         for p in self.params:      # modified in place behind torch's back: keep the version counters honest
             torch.autograd.graph.increment_version(p)
 
     def state_dict(self):
         state, off = {}, 0
+        step = int(round(float(self.state[0])))     # the device counter is the truth (graph replays advance it)
         for i, p in enumerate(self.params):
             n = p.numel()
-            state[i] = {"step": torch.tensor(float(self.step_count)),
+            state[i] = {"step": torch.tensor(float(step)),
                         "exp_avg": self.exp_avg[off:off + n].view_as(p).clone(),
                         "exp_avg_sq": self.exp_avg_sq[off:off + n].view_as(p).clone()}
             off += n
@@ -171,15 +212,19 @@ class NativeAdam:
                 self.exp_avg_sq[off:off + n].copy_(st["exp_avg_sq"].reshape(-1))
                 self.step_count = int(float(st["step"]))
             off += n
+        self.state[0:1].copy_(torch.tensor([float(self.step_count)], dtype=torch.float32))
         g = sd["param_groups"][0]
         self.param_groups[0]["lr"] = float(g["lr"])
         self.betas, self.eps = (float(g["betas"][0]), float(g["betas"][1])), float(g["eps"])
+        self._sync_lr()
 
 
 class StepLR:
     """torch.optim.lr_scheduler.StepLR(optimizer, step_size, gamma) (train.py:72) for any optimizer that exposes
     `param_groups` -- torch's own class insists on a torch.optim.Optimizer, which NativeAdam is not.  Stepped once per
-    epoch (train.py:120): lr = initial_lr * gamma ** (epoch // step_size)."""
+    epoch (train.py:120).  Same chainable rule as torch: every `step_size`-th epoch the CURRENT learning rate of each
+    group is multiplied by gamma, so a rate written into `param_groups` by utils.load_checkpoint (its `lr` argument or
+    the checkpoint's `learning_rate`, utils.py:42-48) is kept, exactly as with torch's scheduler."""
 
     def __init__(self, optimizer, step_size, gamma=0.1):
         self.optimizer, self.step_size, self.gamma = optimizer, int(step_size), float(gamma)
@@ -191,8 +236,9 @@ class StepLR:
 
     def step(self):
         self.last_epoch += 1
-        for g, base in zip(self.optimizer.param_groups, self.base_lrs):
-            g["lr"] = base * self.gamma ** (self.last_epoch // self.step_size)
+        if self.last_epoch % self.step_size == 0:
+            for g in self.optimizer.param_groups:
+                g["lr"] = float(g["lr"]) * self.gamma
         self._last_lr = [float(g["lr"]) for g in self.optimizer.param_groups]
 
     def get_last_lr(self):
@@ -212,7 +258,12 @@ class Trainer:
     """`native=True` (default on CUDA): the whole step stays in libnint kernels -- forward, fused MSE+L1 loss with its
     gradient (nint_loss_mse_l1), BPTT writing straight into the flat all-reduce buffer, one Adam kernel -- with no
     autograd graph and ~25 fewer small launches per step.  `native=False` keeps torch's loss / autograd / fused Adam
-    around the same ConvLSTM kernels (identical numerics up to summation order)."""
+    around the same ConvLSTM kernels (identical numerics up to summation order).
+
+    Three ways to feed a step (all the same arithmetic):
+      step(x, y)                      x [B,T,C,H,W] fp32 or bf16 on the device (train.py:92-96)
+      step_windows(bank, win_start)   window start indices into an HBM-resident preprocess.FrameBank (dataset.py:551-637)
+      capture(...) / replay()         the native step as ONE CUDA graph over static input buffers"""
 
     def __init__(self, model, lr: float = 1e-3, betas=(0.5, 0.999), crop=None, process_group=None, native=None,
                  scheduler_config=None):
@@ -224,22 +275,25 @@ class Trainer:
         self.overlap = os.environ.get("NINT_DP_OVERLAP", "0") == "1"
         self.grads = FlatGradients(model.parameters(), process_group)
         on_cuda = next(model.parameters()).is_cuda
+        self.device = next(model.parameters()).device
         self.native = on_cuda if native is None else bool(native)
         if self.native:
             self.optimizer = NativeAdam(self.grads.params, self.grads.flat, lr=lr, betas=betas)
-            self._loss = torch.zeros(1, dtype=torch.float32, device=self.grads.flat.device)
             self._stats = torch.zeros(8, dtype=torch.float32, device=self.grads.flat.device)
         else:
             self.optimizer = torch.optim.Adam(self.grads.params, lr=lr, betas=betas, fused=on_cuda)   # train.py:71
         # train.py:72 / launcher.sh:27: `--scheduler-config STEP GAMMA`, stepped once per epoch by `end_epoch`
         self.scheduler = None if scheduler_config is None else StepLR(self.optimizer, int(scheduler_config[0]),
                                                                       float(scheduler_config[1]))
+        self._graph = None
         self.broadcast_parameters(process_group)
 
     def end_epoch(self):
         """train.py:120: `scheduler.step()` after the last batch of an epoch; returns the learning rate(s) now in force."""
         if self.scheduler is not None:
             self.scheduler.step()
+            if self.native:
+                self.optimizer._sync_lr()      # outside any graph replay: the device copy of lr follows the schedule
             return self.scheduler.get_last_lr()
         return [float(g["lr"]) for g in self.optimizer.param_groups]
 
@@ -248,30 +302,38 @@ class Trainer:
             for p in self.model.parameters():
                 dist.broadcast(p.data, src=0, group=group)
 
+    def _world(self):
+        return dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
+
     def _grad_views(self):
         ps = self.grads.params            # layers.{l}.conv.weight, .bias, ..., conv.weight, conv.bias (model.parameters() order)
         L = (len(ps) - 2) // 2
         return [ps[2 * l].grad for l in range(L)], [ps[2 * l + 1].grad for l in range(L)], ps[-2].grad, ps[-1].grad
 
-    def _step_native(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
-        import ctypes
+    def _loss_and_update(self, plan, pred, y, y_index, y_offset):
+        """train.py:102-110 after the forward: fused loss + its gradient, BPTT into the flat buffer, all-reduce, Adam."""
         from . import _lib
-        model = self.model
-        if getattr(model, "return_sequence", False):
-            raise NotImplementedError("the native step trains on the last-step prediction (train.py:96-105)")
-        plan = model.plan_for(x, True)
-        pred, _ = plan.forward(x)                                   # train.py:96
         B, _, H, W = pred.shape
         y0, y1, x0, x1 = self.crop if self.crop is not None else (0, H, 0, W)
-        if tuple(y.shape) != (B, y1 - y0, x1 - x0):
-            raise ValueError(f"y has shape {tuple(y.shape)}, expected {(B, y1 - y0, x1 - x0)}")
+        want = (y1 - y0, x1 - x0)
+        if y_index is None and tuple(y.shape) != (B,) + want:
+            raise ValueError(f"y has shape {tuple(y.shape)}, expected {(B,) + want}")
+        if y_index is not None and tuple(y.shape[1:]) != want:
+            raise ValueError(f"target bank has frames of shape {tuple(y.shape[1:])}, expected {want}")
+        if y.dtype != torch.float32 or y.device != pred.device:
+            raise TypeError("targets must be float32 on the model's device")
         dpred = torch.empty_like(pred)
-        vp = lambda t: ctypes.c_void_p(t.data_ptr())
-        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
         loss = torch.empty(1, dtype=torch.float32, device=pred.device)
-        _lib.check(_lib.load().nint_loss_mse_l1(vp(pred), vp(y.contiguous()), B, H, W, y0, y1, x0, x1, vp(dpred), vp(loss),
+        vp, lib = _lib.ptr, _lib.load()
+        with _lib.on_device(pred.device):
+            st = _lib.stream_ptr(pred.device)
+            if y_index is None:
+                _lib.check(lib.nint_loss_mse_l1(vp(pred), vp(y.contiguous()), B, H, W, y0, y1, x0, x1, vp(dpred), vp(loss),
                                                 vp(self._stats), st), "nint_loss_mse_l1")   # train.py:102,105
-        world = dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
+            else:
+                _lib.check(lib.nint_loss_mse_l1_bank(vp(pred), vp(y), vp(y_index), int(y_offset), B, H, W, y0, y1, x0, x1,
+                                                     vp(dpred), vp(loss), vp(self._stats), st), "nint_loss_mse_l1_bank")
+        world = self._world()
         if world > 1 and not self.overlap:
             plan.backward(dpred, out=self._grad_views())
             dist.all_reduce(self.grads.flat, op=dist.ReduceOp.SUM, group=self.group)
@@ -289,14 +351,87 @@ class Trainer:
         self.optimizer.step(grad_scale=1.0 / world)                 # train.py:110 (mean over ranks folded in)
         return loss[0]
 
+    def _step_native(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        model = self.model
+        if getattr(model, "return_sequence", False):
+            raise NotImplementedError("the native step trains on the last-step prediction (train.py:96-105)")
+        plan = model.plan_for(x, True)
+        pred, _ = plan.forward(x)                                   # train.py:96
+        return self._loss_and_update(plan, pred, y, None, 0)
+
     def step(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
         """One optimizer step on this rank's shard; returns the (un-synchronised) local loss tensor."""
         if self.native:
             return self._step_native(x, y)
         self.grads.zero()                                   # train.py:108
-        pred = self.model(x)                                # train.py:96
+        pred = self.model(x.float() if x.dtype != torch.float32 and self.model.precision != "bf16" else x)   # train.py:96
         loss = training_loss(pred, y, self.crop)            # train.py:102,105
         loss.backward()                                     # train.py:109
         self.grads.all_reduce_mean()
         self.optimizer.step()                               # train.py:110
         return loss.detach()
+
+    def step_windows(self, bank, win_start: torch.Tensor, seq_len: int) -> torch.Tensor:
+        """One optimizer step on windows of a frame bank: sample b = bank.frames[i_b : i_b + T] with target
+        bank.targets[i_b + T - 1] (dataset.py:600-601).  `win_start`: int32 [B] on the device (what HostFeeder delivers
+        from the loader's index batch) or on the host."""
+        if bank.targets is None:
+            raise ValueError("step_windows needs a FrameBank with targets")
+        model = self.model
+        starts = win_start if (win_start.is_cuda and win_start.dtype == torch.int32) else \
+            win_start.to(device=bank.frames.device, dtype=torch.int32)
+        bank.check_windows(win_start, seq_len)
+        if not self.native:
+            self.grads.zero()
+            pred = model.forward_windows(bank, starts, seq_len)
+            y = bank.targets.index_select(0, starts.long() + (seq_len - 1))
+            loss = training_loss(pred, y, self.crop)
+            loss.backward()
+            self.grads.all_reduce_mean()
+            self.optimizer.step()
+            return loss.detach()
+        if getattr(model, "return_sequence", False):
+            raise NotImplementedError("the native step trains on the last-step prediction (train.py:96-105)")
+        _, H, W, _ = bank.frames.shape
+        plan = model.plan_for_shape(starts.shape[0], int(seq_len), H, W, bank.frames.device, True)
+        bank.check_plan(plan)
+        pred, _ = plan.forward_bank(bank.frames, starts.contiguous())
+        return self._loss_and_update(plan, pred, bank.targets, starts, seq_len - 1)
+
+    # ---- the native step as one CUDA graph
+    def capture(self, x: torch.Tensor = None, y: torch.Tensor = None, bank=None, win_start: torch.Tensor = None,
+                seq_len: int = None, warmup: int = 2):
+        """Records one native training step into a CUDA graph over STATIC input buffers (`self.static_inputs`): either
+        (x, y) device tensors or (bank, win_start).  Afterwards `replay()` runs the step with whatever the caller
+        copied into those buffers; nothing on the host changes between replays (Adam's step count and learning rate
+        live in device memory).  Single-process only: NCCL collectives are left out of the graph."""
+        if not self.native:
+            raise RuntimeError("graph capture is for the native step")
+        if self._world() > 1:
+            raise RuntimeError("capture() is single-process; with several ranks run step() (the all-reduce stays eager)")
+        if bank is not None:
+            static = (win_start.to(device=bank.frames.device, dtype=torch.int32).clone(),)
+            run = lambda: self.step_windows(bank, static[0], seq_len)
+        else:
+            static = (x.clone(), y.clone())
+            run = lambda: self.step(static[0], static[1])
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):       # plans, tensor maps and kernel attributes are set up outside the capture
+                run()
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            loss = run()
+        self._graph, self._graph_loss, self.static_inputs = graph, loss, static
+        return self.static_inputs
+
+    def replay(self) -> torch.Tensor:
+        """Runs the captured step on the current contents of `static_inputs`; returns the (static) loss tensor."""
+        if self._graph is None:
+            raise RuntimeError("replay() before capture()")
+        self._graph.replay()
+        self.optimizer.step_count += 1
+        return self._graph_loss

@@ -56,25 +56,51 @@ def r2_score_device(pred: torch.Tensor, y: torch.Tensor, crop: Optional[Tuple[in
     y0, y1, x0, x1 = crop if crop is not None else (0, H, 0, W)
     stats = torch.zeros(8, dtype=torch.float32, device=pred.device)
     loss = torch.empty(1, dtype=torch.float32, device=pred.device)
-    vp = lambda t: ctypes.c_void_p(t.data_ptr())
-    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-    _lib.check(_lib.load().nint_loss_mse_l1(vp(pred.detach().contiguous().float()), vp(y.contiguous().float()), B, H, W,
-                                            y0, y1, x0, x1, None, vp(loss), vp(stats), st), "nint_loss_mse_l1")
+    vp = _lib.ptr
+    with _lib.on_device(pred.device):
+        _lib.check(_lib.load().nint_loss_mse_l1(vp(pred.detach().contiguous().float()), vp(y.contiguous().float()), B, H, W,
+                                                y0, y1, x0, x1, None, vp(loss), vp(stats), _lib.stream_ptr(pred.device)),
+                   "nint_loss_mse_l1")
     return r2_from_stats(stats, B * (y1 - y0) * (x1 - x0))
 
 
-def val_loop(dataloader, model, crop: Optional[Tuple[int, int, int, int]] = (5, 95, 5, 149)) -> float:
-    """utils.py:52-75 for the LSTM branch: mean over batches of R^2 on the cropped prediction."""
+_CROPS = {"LSTM": (5, 95, 5, 149), "PIX2PIX": (83, 173, 56, 200), "UNet": (83, 173, 56, 200)}   # utils.py:67-71
+
+
+def val_loop(args, dataloader, model, crop="auto") -> float:
+    """utils.py:52-75, same signature and call (`val_loop(args, val_dataloader, generator)`, train.py:122): mean over
+    batches of R^2 on the cropped prediction, with the crop chosen by the `args.model` prefix like the reference.
+    `args` may be None (or anything without `.model`): the LSTM crop is used.  `crop=None` disables cropping, a
+    4-tuple (y0, y1, x0, x1) overrides it.  R^2 is reduced on the GPU; only five floats per batch cross to the host."""
+    if crop == "auto":
+        kind = str(getattr(args, "model", "LSTM")).split("-")[0]
+        crop = _CROPS.get(kind, _CROPS["LSTM"])
     model.eval()
     r2, n = 0.0, 0
+    device = next(model.parameters()).device
     with torch.no_grad():
         for X, y in dataloader:
-            X, y = X.cuda(non_blocking=True), y.cuda(non_blocking=True)
+            X, y = X.to(device, non_blocking=True), y.to(device, non_blocking=True)
             out = model(X)
             pred = out[0] if isinstance(out, tuple) else out
             r2 += r2_score_device(pred, y, crop)
             n += 1
     return r2 / max(n, 1)
+
+
+def seed(seed=0):
+    """utils.py:77-88: seeds python / numpy / torch and asks for deterministic kernels.  Here `cudnn.deterministic`
+    also selects the fixed-order gradient reductions of the ConvLSTM kernels (model._deterministic_default)."""
+    import random
+    import numpy as np
+    random.seed(seed)
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    if torch.cuda.is_available():
+        torch.cuda.manual_seed(seed)
+        torch.cuda.manual_seed_all(seed)
+    torch.backends.cudnn.deterministic = True
+    torch.backends.cudnn.benchmark = False
 
 
 def sensitivity_sweep(dataloader, model, num_features: int, perturbation: float = 0.05,
@@ -89,7 +115,7 @@ def sensitivity_sweep(dataloader, model, num_features: int, perturbation: float 
     chunks = [[] for _ in range(num_features)]
     with torch.no_grad():
         for X, _ in dataloader:
-            X = X.cuda(non_blocking=True)
+            X = X.to(next(model.parameters()).device, non_blocking=True)
             for i in range(num_features):
                 saved = X[:, :, i].clone()
                 X[:, :, i] *= (1 + perturbation)

@@ -79,10 +79,42 @@ def test_plan_validation_and_workspace_accounting():
     assert train_bytes > infer_bytes
     assert train_bytes >= 3 * npix * 32 * 2 + 4 * npix * 32 * 2 + 4 * npix * 32 * 4 + 3 * npix * 128 * 2
     assert infer_bytes >= 3 * npix * 32 * 2 + 2 * npix * 32 * 2 + npix * 32 * 4
-    for bad in [dict(hidden=[24]), dict(hidden=[96]), dict(ksize=[4]), dict(num_layers=0), dict(batch=0),
-                dict(dtype=7), dict(hidden=[512])]:
+    for bad in [dict(hidden=[0]), dict(hidden=[257]), dict(ksize=[4]), dict(num_layers=0), dict(batch=0),
+                dict(dtype=7), dict(hidden=[512]), dict(ksize=[17])]:
         rc, h, lib = _create(_cfg(**bad))
         assert rc != 0 and lib.nint_last_error(), bad
+
+
+def test_any_hidden_size_is_accepted_by_padding():
+    # model.py:207 takes any int (the notebooks use ConvLSTM(5, 10, 3, 2)-style sizes): hidden sizes run padded to the
+    # kernels' granularity (16; 64 above 64), so the workspace of hidden 10 equals that of hidden 16, 70 that of 128
+    def ws(hidden):
+        rc, h, lib = _create(_cfg(hidden=hidden, ksize=[3] * len(hidden), num_layers=len(hidden)))
+        assert rc == 0, lib.nint_last_error()
+        n = lib.nint_plan_workspace_bytes(h)
+        lib.nint_plan_destroy(h)
+        return n
+    assert ws([10]) == ws([16]) and ws([24]) == ws([32]) and ws([70]) == ws([128]) and ws([96]) == ws([128])
+    assert ws([10, 3]) == ws([16, 16])
+    assert ws([16]) < ws([32]) < ws([64]) < ws([128])
+
+
+def test_deterministic_and_input_grad_plans_reserve_their_buffers():
+    base = _cfg(hidden=[64], batch=4, seq_len=5, height=90, width=144)
+    det = _cfg(hidden=[64], batch=4, seq_len=5, height=90, width=144, flags=_lib.FLAG_DETERMINISTIC)
+    dx = _cfg(hidden=[64], batch=4, seq_len=5, height=90, width=144, flags=_lib.FLAG_INPUT_GRAD)
+    sizes = []
+    for cfg in (base, det, dx):
+        rc, h, lib = _create(cfg)
+        assert rc == 0, lib.nint_last_error()
+        sizes.append(lib.nint_plan_workspace_bytes(h))
+        c_pad, ones, eb = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        assert lib.nint_plan_input_layout(h, ctypes.byref(c_pad), ctypes.byref(ones), ctypes.byref(eb)) == 0
+        assert (c_pad.value, ones.value, eb.value) == (32, 21, 2)      # 21 channels -> 32 lanes, lane 21 carries 1.0
+        lib.nint_plan_destroy(h)
+    slice_bytes = 9 * 256 * 96 * 4                                     # [taps][4hc][x 32 + h 64 columns] fp32
+    assert sizes[1] - sizes[0] >= 30 * slice_bytes                     # one partial-sum slice per split-K share
+    assert sizes[2] - sizes[0] >= 4 * 90 * 144 * (64 + 64) * 4         # dgrad dump + upstream dh staging
 
 
 def test_compute_without_binding_fails_loudly():
@@ -155,7 +187,60 @@ def test_torch_library_ops_are_registered_cuda_only():
     assert str(torch.ops.nint.convlstm_forward.default._schema) == \
         "nint::convlstm_forward(Tensor x, Tensor[] params, SymInt plan_id) -> (Tensor, Tensor)"
     assert str(torch.ops.nint.convlstm_backward.default._schema) == \
-        "nint::convlstm_backward(Tensor dpred, Tensor? dseq, SymInt plan_id, SymInt generation) -> Tensor[]"
+        "nint::convlstm_backward(Tensor dpred, Tensor? dseq, SymInt plan_id, SymInt generation, bool need_dx) -> Tensor[]"
+    assert str(torch.ops.nint.convlstm_forward_bank.default._schema) == \
+        "nint::convlstm_forward_bank(Tensor frames, Tensor win_start, Tensor[] params, SymInt plan_id) -> (Tensor, Tensor)"
     assert "nint::cell_forward" in str(torch.ops.nint.cell_forward.default._schema)
+    assert "nint::cell_backward" in str(torch.ops.nint.cell_backward.default._schema)
     with pytest.raises(NotImplementedError, match="CPU"):
         torch.ops.nint.convlstm_forward(torch.zeros(1, 1, 1, 8, 8), [torch.zeros(1)], 1)
+
+
+def test_module_survives_deepcopy_and_pickle():
+    """plans (ctypes handles + workspaces) are derived state; copying / pickling the module must work and
+    yield an empty plan cache (copy.deepcopy, torch.save(model), swa_utils.AveragedModel all do this)."""
+    import copy
+    import io
+    net = ConvLSTM(5, [16], [3], 1)
+    net._plans._plans["fake"] = ctypes.c_void_p(1)            # what a live plan holds: deepcopy of this raises
+    net.layers[0]._plans._all.append(ctypes.c_void_p(2))
+    twin = copy.deepcopy(net)
+    assert len(twin._plans._plans) == 0 and len(twin.layers[0]._plans._all) == 0
+    assert all(torch.equal(a, b) for a, b in zip(net.state_dict().values(), twin.state_dict().values()))
+    buf = io.BytesIO()
+    torch.save(net, buf)
+    buf.seek(0)
+    back = torch.load(buf, weights_only=False)
+    assert len(back._plans._plans) == 0 and back.layers[0].hidden_channels == 16
+    torch.optim.swa_utils.AveragedModel(net)
+
+
+def test_model_shim_reexports_upstream_names(tmp_path, monkeypatch):
+    """a replacement model.py keeps `from model import Generator, UNet, ConvLSTM, initialize_weights`
+    (train.py:19) resolving -- ConvLSTM from here, the rest from upstream's renamed file."""
+    import importlib.util
+    import sys
+    (tmp_path / "model_reference.py").write_text(
+        "class Generator: pass\nclass UNet: pass\nclass Discriminator: pass\ndef initialize_weights(m): return 'init'\n")
+    monkeypatch.syspath_prepend(str(tmp_path))
+    sys.modules.pop("model_reference", None)
+    spec = importlib.util.spec_from_file_location("model_shim", os.path.join(ROOT, "integration", "model.py"))
+    shim = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(shim)
+    assert shim.ConvLSTM is ConvLSTM and shim.ConvLSTMCell is ConvLSTMCell
+    assert shim.Generator.__name__ == "Generator" and shim.initialize_weights(None) == "init"
+    with pytest.raises(ImportError, match="reference"):
+        shim.Encoder()                                        # not in the fake upstream: importable, raises when used
+    sys.modules.pop("model_reference", None)
+
+
+def test_val_loop_keeps_the_reference_signature():
+    import inspect
+    from nasa_niswan_b200.utils import val_loop, seed
+    assert list(inspect.signature(val_loop).parameters)[:3] == ["args", "dataloader", "model"]   # utils.py:52
+    prev = torch.backends.cudnn.deterministic
+    seed(0)                                                   # utils.py:77-88
+    assert torch.backends.cudnn.deterministic and not torch.backends.cudnn.benchmark
+    from nasa_niswan_b200.model import _deterministic_default
+    assert _deterministic_default()
+    torch.backends.cudnn.deterministic = prev

@@ -104,11 +104,40 @@ def test_step_lr_matches_torch_scheduler():
         mine.step()
         assert abs(mine.get_last_lr()[0] - ref.get_last_lr()[0]) < 1e-15
         assert mine_opt.param_groups[0]["lr"] == mine.get_last_lr()[0]
-    resumed = StepLR(Opt(1e-3), 10, 0.9)
+    # resume: like torch, the optimizer's state dict carries the current lr, the scheduler's the epoch counter
+    resumed = StepLR(Opt(mine_opt.param_groups[0]["lr"]), 10, 0.9)
     resumed.load_state_dict(mine.state_dict())
     resumed.step()
     mine.step()
     assert resumed.get_last_lr() == mine.get_last_lr()
+
+
+def test_step_lr_keeps_an_overridden_learning_rate_like_torch():
+    """utils.load_checkpoint writes an lr into param_groups (its `lr` argument or the checkpoint's
+    `learning_rate`, utils.py:42-48).  torch's StepLR is chainable -- it multiplies the CURRENT lr -- so the override
+    survives; a closed-form `base_lr * gamma ** (epoch // step)` would silently go back to the constructor's lr."""
+    import torch
+    from nasa_niswan_b200.parallel import StepLR
+
+    class Opt:
+        def __init__(self, lr):
+            self.param_groups = [{"lr": lr}]
+
+    w = torch.nn.Parameter(torch.zeros(1))
+    ref_opt = torch.optim.Adam([w], lr=1e-3)
+    ref = torch.optim.lr_scheduler.StepLR(ref_opt, step_size=2, gamma=0.5)
+    mine_opt = Opt(1e-3)
+    mine = StepLR(mine_opt, 2, 0.5)
+    ref_opt.param_groups[0]["lr"] = 5e-4          # what load_checkpoint(..., lr=5e-4) does after the scheduler exists
+    mine_opt.param_groups[0]["lr"] = 5e-4
+    seen = []
+    for _ in range(6):
+        ref_opt.step()
+        ref.step()
+        mine.step()
+        assert abs(mine_opt.param_groups[0]["lr"] - ref_opt.param_groups[0]["lr"]) < 1e-15
+        seen.append(mine_opt.param_groups[0]["lr"])
+    assert seen[0] == 5e-4 and abs(seen[1] - 2.5e-4) < 1e-15 and abs(seen[-1] - 6.25e-5) < 1e-15
 
 
 class _TwoLayer(torch.nn.Module):     # parameter order of ConvLSTM: layers.0.w, layers.0.b, layers.1.w, layers.1.b, head w, b
