@@ -435,7 +435,9 @@ def test_val_loop_r2_matches_sklearn():
     torch.manual_seed(10)
     net = ConvLSTM(5, [16], [3], 1, precision="tf32").cuda()
     data = [(torch.randn(2, 3, 5, 100, 154), torch.randn(2, 90, 144)) for _ in range(2)]
-    got = val_loop(data, net)
+    import argparse
+    got = val_loop(argparse.Namespace(model="LSTM-E33OMA"), data, net)     # utils.py:52 signature, train.py:122 call
+    assert got == val_loop(None, data, net)
     ref = 0.0
     with torch.no_grad():
         for X, y in data:
