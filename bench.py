@@ -405,6 +405,7 @@ def main():
                                         "d2h_bytes_per_step": 4, "steps": e2e_steps,
                                         "how": "the reference's staging dtype (train.py:92: fp32 X.cuda())"}
     headline = "host_window_bf16" if xh16 is not None else "host_window_fp32"
+    bank_resident = None
     if not args.no_extras:
         # frame bank: the record lives in HBM once (dataset.py:551-637 keeps it in RAM), a step uploads B window indices
         n_frames = 512
@@ -413,7 +414,21 @@ def main():
                                      targets=torch.randn(n_frames, H, W, device=dev))
         gen = torch.Generator().manual_seed(rank)
         idx_batches = [torch.randint(0, n_frames - T + 1, (B,), generator=gen, dtype=torch.int32).pin_memory() for _ in range(8)]
+        idx_dev = [t.to(dev) for t in idx_batches]
         it = iter(range(10 ** 9))
+        for i in range(3):
+            trainer.step_windows(bank, idx_dev[i], T)
+        barrier()
+        e0.record()
+        for i in range(K_):
+            trainer.step_windows(bank, idx_dev[i % 8], T)
+        e1.record()
+        barrier()
+        ms_bank = max_over_ranks(e0.elapsed_time(e1)) / K_
+        bank_resident = {"value": round(global_batch / (ms_bank * 1e-3), 2), "unit": "samples/s", "steps": K_,
+                         "ms_per_step": round(ms_bank, 3),
+                         "how": "as `value`, with the batch given as window indices into the HBM-resident frame bank: no "
+                                "per-step input packing pass (the TMA descriptors read the bank)"}
         v = e2e_run(lambda: feeder.put(idx_batches[next(it) % 8]), lambda a: trainer.step_windows(bank, a[0], T), e2e_steps)
         variants["frame_bank"] = {"value": round(v, 2), "h2d_bytes_per_step": B * 4, "d2h_bytes_per_step": 4, "steps": e2e_steps,
                                   "resident_bytes": bank.frames.numel() * bank.frames.element_size() + bank.targets.numel() * 4,
@@ -485,10 +500,12 @@ def main():
                                    f"= 21 ch, hidden 64, k{k}, T={T}, batch {B}/GPU (global {global_batch})",
                        "parallelism": f"dp{world}", "l2_policy": "inputs (418 MB/step at B=32) larger than the 126 MB L2",
                        "loss_at_end": round(float(loss), 5), "numa_node": numa,
-                       "sub_batch": int(os.environ.get("NINT_SUB_BATCH", "0") or 0)},
+                       "sub_batch": int(os.environ.get("NINT_SUB_BATCH", "0") or 0),
+                       "pdl": int(os.environ.get("NINT_PDL", "0") or 0)},
             "e2e": e2e,
             "e2e_variants": variants,
             "sustained": sustained,
+            "frame_bank_resident": bank_resident,
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roof,

@@ -133,6 +133,7 @@ struct nint_plan {
   bool gates_valid = false; // the saved activated gates of the last forward are intact (BPTT overwrites them in place)
   bool bptt_done = false;   // dgates of the last forward are in place: nint_backward_wgrad may run
   bool deterministic = false, input_grad = false;
+  int pdl = 0;              // programmatic dependent launch of the conv kernels (NINT_PDL)
   int sub_batch = 0;        // > 0: sub-batch-major schedule (images [b0, b0 + sub_batch) run all T steps before the next
                             // slice, so a step's recurrent operands are still in L2 when the next step reads them)
   int final_slot_h = 0, final_slot_c = 0;
@@ -329,6 +330,7 @@ inline float* cslot_ptr(const nint_plan* p, const Layer& y, int slot) {
 void fill_common(const nint_plan* p, const Layer& y, ConvGemmParams& g) {
   memset(&g, 0, sizeof(g));
   g.debug_flags = p->debug_flags;
+  g.pdl = p->pdl;
   g.plan_g = p->plan_g; g.plan_ns = p->plan_ns;
   g.B = p->B; g.b0 = 0; g.H = p->H; g.W = p->W;
   g.tile_w = p->tile_w; g.tile_h = p->tile_h; g.tiles_x = p->tiles_x; g.tiles_y = p->tiles_y;
@@ -694,6 +696,8 @@ int nint_plan_create(const nint_config* cfg, nint_plan** out) {
     const char* pn = getenv("NINT_PLAN_NS");
     p->plan_ns = pn ? atoi(pn) : 0;
     if (const char* e = getenv("NINT_DETERMINISTIC")) p->deterministic = p->deterministic || atoi(e) != 0;
+    const char* pd = getenv("NINT_PDL");
+    p->pdl = pd ? (atoi(pd) != 0) : 0;
     const char* sb = getenv("NINT_SUB_BATCH");
     p->sub_batch = sb ? atoi(sb) : 0;
     if (p->sub_batch < 0 || p->sub_batch >= p->B) p->sub_batch = 0;

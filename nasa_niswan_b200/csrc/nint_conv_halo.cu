@@ -151,6 +151,14 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
       tmem_relinquish();
     }
   }
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) touches no
+  // global data, so a CTA of this launch may run it on an SM the previous conv launch of the stream has already left
+  // while that launch's last tiles are still in flight elsewhere.  launch_dependents lets the NEXT launch do the same
+  // with us; wait blocks until the previous launch has completed and its writes are visible.
+  if (p.pdl) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+  }
   if (EPI == EPI_FWD) {
     for (int i = threadIdx.x; i < 4 * p.hc; i += kConvThreads) s_bias[i] = p.bias_q ? p.bias_q[i] : 0.f;
   }
@@ -711,13 +719,22 @@ static cudaError_t launch_h(const ConvGemmParams& p, int num_sms, cudaStream_t s
   cfg.blockDim = dim3(kConvThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = S;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (PAIR) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = S;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (p.pdl) {   // may start while the previous kernel of the stream drains (the kernel calls griddepcontrol.wait)
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = PAIR ? 1 : 0;
+  cfg.numAttrs = na;
   return cudaLaunchKernelEx(&cfg, conv_halo_kernel<E, EPI, PAIR>, p);
 }
 

@@ -54,6 +54,7 @@ struct alignas(64) ConvGemmParams {
   int plan_g, plan_ns;      // experiment knobs for conv_halo_plan: cap on tiles per group / epilogue stages (0 = auto)
   int w_resident;           // 1: num_stages covers a tile's whole K walk; weights are loaded once per CTA
   int debug_flags;          // experiments: 1 = epilogue does no memory ops / math, 2 = no MMA issue
+  int pdl;                  // 1: programmatic dependent launch (prologue overlaps the previous launch's tail)
   // ---- TMA-staged epilogue I/O (nint_epilogue.cuh): 5-D maps (channel, x, y, image, slot) of the layer's
   // c history (fp32), h history (E), saved gates (E, q-order) and running dc (fp32); slot < 0 = absent
   CUtensorMap tm_c, tm_h, tm_g, tm_dc;

@@ -302,7 +302,7 @@ def test_stale_workspace_is_detected(golden_dir):
     x = torch.from_numpy(z["x"]).cuda()
     p1 = net(x)
     net(x)
-    with pytest.raises(RuntimeError, match="overwritten"):
+    with pytest.raises(RuntimeError, match="overwrote the ConvLSTM workspace"):
         p1.sum().backward()
 
 
