@@ -437,7 +437,7 @@ def test_val_loop_r2_matches_sklearn():
     data = [(torch.randn(2, 3, 5, 100, 154), torch.randn(2, 90, 144)) for _ in range(2)]
     import argparse
     got = val_loop(argparse.Namespace(model="LSTM-E33OMA"), data, net)     # utils.py:52 signature, train.py:122 call
-    assert got == val_loop(None, data, net)
+    assert abs(got - val_loop(None, data, net)) < 1e-5          # (the R^2 sums are reduced with fp32 atomics)
     ref = 0.0
     with torch.no_grad():
         for X, y in data:
