@@ -561,45 +561,47 @@ __global__ void __launch_bounds__(256) fuse_inputs_kernel(const float* __restric
                                                           const float* __restrict__ statics, int S,
                                                           float* __restrict__ out, long long N, int L, int H, int W, int Hp,
                                                           int Wp, int mode) {
-  // one block iteration = one output row (n, c, yp): the source row, its channel and the z-score constants are block-
-  // uniform, a thread only wraps its longitude -- loads and stores are both coalesced along x
+  // one block iteration = one output row yp of one frame, all channels: warps take channels, lanes walk the longitudes,
+  // so loads and stores are coalesced and there is no per-element index arithmetic beyond the cyclic wrap
   const int C = L + 1 + S;
   const int left = (Wp - W) / 2, top = (Hp - H) / 2, bot = Hp - H - top;
-  const long long rows = N * C * Hp;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const long long rows = N * Hp;
   for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
     const int yp = static_cast<int>(r % Hp);
-    const long long nc = r / Hp;
-    const int c = static_cast<int>(nc % C);
-    const long long n = nc / C;
-    int ys = yp - top, cs = c;
+    const long long n = r / Hp;
+    int ys = yp - top;
+    bool flip = false;
     if (ys < 0) {                             // upper halo: rows 1..top (dataset.py:82-98)
-      if (mode == 0) ys = top - yp; else { ys = 1 + yp; cs = C - 1 - c; }
+      if (mode == 0) ys = top - yp; else { ys = 1 + yp; flip = true; }
     } else if (ys >= H) {                     // lower halo: rows H-bot-1..H-2
       const int j = ys - H;
-      if (mode == 0) ys = H - 2 - j; else { ys = H - bot - 1 + j; cs = C - 1 - c; }
+      if (mode == 0) ys = H - 2 - j; else { ys = H - bot - 1 + j; flip = true; }
     }
-    const float* src = cs > L ? statics + (static_cast<long long>(cs - L - 1) * H + ys) * W
-                              : (cs < L ? lev + ((n * L + cs) * H + ys) * W : emis + (n * H + ys) * W);
-    const bool zs = cs <= L;                  // static attributes arrive already z-scored
-    const float m = zs ? mean[cs] : 0.f, sd = zs ? stdv[cs] : 1.f;
-    float* dst = out + r * Wp;
-    for (int xp = threadIdx.x; xp < Wp; xp += blockDim.x) {
-      int xs = xp - left;                     // cyclic longitude (dataset.py:67-80)
-      if (xs < 0) xs += W;
-      if (xs >= W) xs -= W;
-      const float v = __ldg(src + xs);
-      dst[xp] = zs ? (v - m) / sd : v;        // IEEE subtract / divide: bit-identical to the numpy float32 pipeline
+    for (int c = warp; c < C; c += nwarps) {
+      const int cs = flip ? C - 1 - c : c;    // mode 1: halo rows carry the channels in reverse order (dataset.py:96)
+      const float* src = cs > L ? statics + (static_cast<long long>(cs - L - 1) * H + ys) * W
+                                : (cs < L ? lev + ((n * L + cs) * H + ys) * W : emis + (n * H + ys) * W);
+      const bool zs = cs <= L;                // static attributes arrive already z-scored
+      const float m = zs ? mean[cs] : 0.f, sd = zs ? stdv[cs] : 1.f;
+      float* dst = out + ((n * C + c) * Hp + yp) * Wp;
+      for (int xp = lane; xp < Wp; xp += 32) {
+        int xs = xp - left;                   // cyclic longitude (dataset.py:67-80)
+        if (xs < 0) xs += W;
+        if (xs >= W) xs -= W;
+        const float v = __ldg(src + xs);
+        dst[xp] = zs ? (v - m) / sd : v;      // IEEE subtract / divide: bit-identical to the numpy float32 pipeline
+      }
     }
   }
 }
 cudaError_t launch_fuse_inputs(const float* lev, const float* emis, const float* mean, const float* stdv,
                                const float* statics, int S, float* out, long long N, int L, int H, int W, int Hp, int Wp,
                                int mode, cudaStream_t s) {
-  const long long rows = N * (L + 1 + S) * Hp;
-  const int threads = Wp >= 192 ? 256 : (Wp >= 96 ? 128 : 64);
-  const long long blocks = rows < 148LL * 64 ? rows : 148LL * 64;
+  const long long rows = N * Hp;
+  const long long blocks = rows < 148LL * 32 ? rows : 148LL * 32;
   if (blocks <= 0) return cudaSuccess;
-  fuse_inputs_kernel<<<static_cast<unsigned>(blocks), threads, 0, s>>>(lev, emis, mean, stdv, statics, S, out, N, L, H, W, Hp, Wp, mode);
+  fuse_inputs_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(lev, emis, mean, stdv, statics, S, out, N, L, H, W, Hp, Wp, mode);
   return cudaGetLastError();
 }
 
@@ -609,82 +611,107 @@ cudaError_t launch_fuse_inputs(const float* lev, const float* emis, const float*
 // intermediate and no second packing pass exist.  One thread per output pixel: for a fixed channel the warp's loads are
 // 32 consecutive longitudes of one source row (coalesced; the cyclic wrap splits at most one request), and a thread
 // writes its pixel's CP channels as CP*sizeof(E)/32 256-bit stores (a warp covers one contiguous span).
-template <typename E, int CP>
+// One block iteration = one strip of SW <= 160 consecutive longitudes of one output row of one frame, all channels:
+//   load phase   warps walk (channel, 32-pixel run) pairs: a warp-wide load is 32 consecutive longitudes of ONE source
+//                row (128 contiguous bytes; the cyclic wrap splits at most one request), z-scored on the way into a
+//                [channel][pixel] fp32 tile in shared memory (row pitch SW + 1 words: both phases are conflict free);
+//   store phase  each thread packs one 16-byte piece (8 bf16 / 4 tf32 channels of one pixel) and consecutive lanes
+//                write consecutive pieces: a warp-wide store is 512 contiguous bytes of the bank.
+// The source row, the channel flip of mode 1 and the z-score constants are block- or warp-uniform; a thread does no
+// index arithmetic beyond the longitude wrap.  (The first version -- one thread per pixel looping over the channels --
+// ran at 1.1-2.3 TB/s: 32 IEEE divisions and 64 address computations per thread.)
+template <typename E>
 __global__ void __launch_bounds__(256) fuse_bank_kernel(const float* __restrict__ lev, const float* __restrict__ emis,
                                                         const float* __restrict__ mean, const float* __restrict__ stdv,
                                                         const float* __restrict__ statics, int S, E* __restrict__ out,
                                                         long long N, int L, int H, int W, int Hp, int Wp, int mode,
-                                                        int ones_lane) {
+                                                        int c_pad, int ones_lane, int SW) {
+  extern __shared__ float s_tile[];            // [c_pad][SW + 1]
   const int C = L + 1 + S;
-  __shared__ float s_mean[CP], s_std[CP];
-  for (int c = threadIdx.x; c < CP; c += blockDim.x) {
-    s_mean[c] = c <= L ? mean[c] : 0.f;
-    s_std[c] = c <= L ? stdv[c] : 1.f;
-  }
-  __syncthreads();
+  const int pitch = SW + 1;
   const int left = (Wp - W) / 2, top = (Hp - H) / 2, bot = Hp - H - top;
-  const long long HWp = static_cast<long long>(Hp) * Wp, HW = static_cast<long long>(H) * W;
-  const long long total = N * HWp;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long n = i / HWp;
-    const int rem = static_cast<int>(i - n * HWp);
-    const int yp = rem / Wp, xp = rem - yp * Wp;
-    int xs = xp - left;                       // cyclic longitude (dataset.py:67-80)
-    if (xs < 0) xs += W;
-    if (xs >= W) xs -= W;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int strips = (Wp + SW - 1) / SW;
+  const int runs = SW >> 5;                    // 32-pixel runs per strip
+  constexpr int V = 16 / sizeof(E);            // channels per 16-byte piece
+  const int ppp = c_pad / V;                   // pieces per pixel
+  // padding lanes never change: zero (or one) once
+  for (int i = threadIdx.x; i < (c_pad - C) * SW; i += blockDim.x) {
+    const int c = C + i / SW;
+    s_tile[c * pitch + i % SW] = (c == ones_lane) ? 1.f : 0.f;
+  }
+  const long long items = N * Hp * strips;
+  for (long long it = blockIdx.x; it < items; it += gridDim.x) {
+    const int strip = static_cast<int>(it % strips);
+    const long long row = it / strips;
+    const int yp = static_cast<int>(row % Hp);
+    const long long n = row / Hp;
+    const int x0 = strip * SW;
+    const int npx = Wp - x0 < SW ? Wp - x0 : SW;
     int ys = yp - top;
-    bool flip = false;                        // mode 1: halo rows carry the channels in reverse order (dataset.py:96)
-    if (ys < 0) {                             // upper halo: rows 1..top (dataset.py:82-98)
+    bool flip = false;                         // mode 1: halo rows carry the channels in reverse order (dataset.py:96)
+    if (ys < 0) {                              // upper halo: rows 1..top (dataset.py:82-98)
       if (mode == 0) ys = top - yp; else { ys = 1 + yp; flip = true; }
-    } else if (ys >= H) {                     // lower halo: rows H-bot-1..H-2
+    } else if (ys >= H) {                      // lower halo: rows H-bot-1..H-2
       const int j = ys - H;
       if (mode == 0) ys = H - 2 - j; else { ys = H - bot - 1 + j; flip = true; }
     }
-    const long long pix = static_cast<long long>(ys) * W + xs;
-    const float* lev_n = lev + n * L * HW + pix;
-    const float* emis_n = emis + n * HW + pix;
-    const float* stat_n = statics + pix;      // (never dereferenced without static fields: cs <= L then)
-    // pass 1: every load of the pixel, each into its own register, all in flight together.  The loads are
-    // unconditional (padding lanes re-read channel C-1: an L1 hit) so that no per-channel branch splits the basic
-    // block: with branches the compiler put each division right behind its load and the loads serialised (1.1 TB/s).
-    float v[CP];
+    __syncthreads();                           // the previous strip's store phase is done with the tile
+    // four (channel, run) items per warp iteration, every load issued before the first division: with one load in
+    // flight per warp the kernel is latency bound
+    for (int w0 = warp; w0 < C * runs; w0 += 4 * nwarps) {
+      float v[4];
+      int cs4[4], at[4];
 #pragma unroll
-    for (int c = 0; c < CP; ++c) {
-      const int cc = c < C ? c : C - 1;
-      const int cs = flip ? C - 1 - cc : cc;
-      // branch-free source select: levels [0, L), the emission field (L), static attributes (> L)
-      const float* base = cs < L ? lev_n : (cs == L ? emis_n : stat_n);
-      const int k = cs < L ? cs : (cs == L ? 0 : cs - L - 1);
-      v[c] = __ldg(base + k * HW);
-    }
-    // pass 2: z-score (IEEE subtract / divide: bit-identical to the numpy float32 pipeline; static attributes arrive
-    // already z-scored) and rounding to the operand type
+      for (int u = 0; u < 4; ++u) {
+        const int w = w0 + u * nwarps;
+        const int c = w / runs, px = (w - c * runs) * 32 + lane;
+        at[u] = -1;
+        v[u] = 0.f;
+        cs4[u] = 0;
+        if (w < C * runs && px < npx) {
+          const int cs = flip ? C - 1 - c : c;
+          const float* src = cs > L ? statics + (static_cast<long long>(cs - L - 1) * H + ys) * W
+                                    : (cs < L ? lev + ((n * L + cs) * H + ys) * W : emis + (n * H + ys) * W);
+          int xs = x0 + px - left;             // cyclic longitude (dataset.py:67-80)
+          if (xs < 0) xs += W;
+          if (xs >= W) xs -= W;
+          v[u] = __ldg(src + xs);
+          cs4[u] = cs;
+          at[u] = c * pitch + px;
+        }
+      }
 #pragma unroll
-    for (int c = 0; c < CP; ++c) {
-      const int cc = c < C ? c : C - 1;
-      const int cs = flip ? C - 1 - cc : cc;
-      const float z = (v[c] - s_mean[cs]) / s_std[cs];
-      const float r = round_for(cs <= L ? z : v[c], (E*)nullptr);
-      v[c] = c < C ? r : ((c == ones_lane) ? 1.f : 0.f);
+      for (int u = 0; u < 4; ++u) {
+        if (at[u] >= 0) {
+          // IEEE subtract / divide: bit-identical to the numpy float32 pipeline; static attributes arrive z-scored
+          s_tile[at[u]] = cs4[u] <= L ? (v[u] - __ldg(mean + cs4[u])) / __ldg(stdv + cs4[u]) : v[u];
+        }
+      }
     }
-    store_elems<E, CP>(out + i * CP, v);
+    __syncthreads();
+    E* dst = out + (row * Wp + x0) * c_pad;
+    for (int i = threadIdx.x; i < npx * ppp; i += blockDim.x) {
+      const int px = i / ppp, piece = i - px * ppp;
+      float v[V];
+#pragma unroll
+      for (int j = 0; j < V; ++j) v[j] = round_for(s_tile[(piece * V + j) * pitch + px], (E*)nullptr);
+      store_elems<E, V>(dst + static_cast<long long>(i) * V, v);
+    }
   }
 }
 template <typename E>
 static cudaError_t fuse_bank(const float* lev, const float* emis, const float* mean, const float* stdv, const float* statics,
                              int S, E* out, long long N, int L, int H, int W, int Hp, int Wp, int mode, int c_pad,
                              int ones_lane, cudaStream_t s) {
-  long long blocks = (N * Hp * Wp + 255) / 256;
-  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (c_pad % 16 || c_pad > 64) return cudaErrorInvalidValue;
+  const int SW = Wp <= 160 ? (Wp + 31) / 32 * 32 : 128;
+  const int smem = c_pad * (SW + 1) * 4;                     // <= 64 * 161 * 4 = 41 KB
+  const long long items = N * Hp * ((Wp + SW - 1) / SW);
+  long long blocks = items < 148LL * 8 ? items : 148LL * 8;
   if (blocks <= 0) return cudaSuccess;
-  switch (c_pad) {
-    case 16: fuse_bank_kernel<E, 16><<<blocks, 256, 0, s>>>(lev, emis, mean, stdv, statics, S, out, N, L, H, W, Hp, Wp, mode, ones_lane); break;
-    case 32: fuse_bank_kernel<E, 32><<<blocks, 256, 0, s>>>(lev, emis, mean, stdv, statics, S, out, N, L, H, W, Hp, Wp, mode, ones_lane); break;
-    case 48: fuse_bank_kernel<E, 48><<<blocks, 256, 0, s>>>(lev, emis, mean, stdv, statics, S, out, N, L, H, W, Hp, Wp, mode, ones_lane); break;
-    case 64: fuse_bank_kernel<E, 64><<<blocks, 256, 0, s>>>(lev, emis, mean, stdv, statics, S, out, N, L, H, W, Hp, Wp, mode, ones_lane); break;
-    default: return cudaErrorInvalidValue;
-  }
+  fuse_bank_kernel<E><<<static_cast<unsigned>(blocks), 256, smem, s>>>(lev, emis, mean, stdv, statics, S, out, N, L, H, W, Hp, Wp,
+                                                                       mode, c_pad, ones_lane, SW);
   return cudaGetLastError();
 }
 cudaError_t launch_fuse_inputs_bank(int dtype, const float* lev, const float* emis, const float* mean, const float* stdv,

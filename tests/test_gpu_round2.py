@@ -153,15 +153,20 @@ def test_trainer_step_windows_matches_step_on_explicit_windows():
     net_b, _ = _fresh(C, [32], [3], "bf16", seed=9)
     ta, tb = Trainer(net_a, lr=1e-3), Trainer(net_b, lr=1e-3)
     gen = torch.Generator().manual_seed(0)
-    for _ in range(3):
-        starts = torch.randint(0, N - T + 1, (B,), generator=gen)
-        x = torch.stack([record[s:s + T] for s in starts.tolist()])
-        y = targets[starts + T - 1]
-        la = ta.step(x, y)
-        lb = tb.step_windows(bank, starts.to(torch.int32).cuda(), T)
-        assert abs(float(la) - float(lb)) <= 1e-6 * max(1.0, abs(float(la)))
+    prev = torch.backends.cudnn.deterministic
+    torch.backends.cudnn.deterministic = True      # fixed-order gradient sums: the two input paths agree bit for bit, and
+    try:                                           # Adam cannot amplify a last-bit difference of a near-zero gradient
+        for _ in range(3):
+            starts = torch.randint(0, N - T + 1, (B,), generator=gen)
+            x = torch.stack([record[s:s + T] for s in starts.tolist()])
+            y = targets[starts + T - 1]
+            la = ta.step(x, y)
+            lb = tb.step_windows(bank, starts.to(torch.int32).cuda(), T)
+            assert abs(float(la) - float(lb)) <= 1e-6 * max(1.0, abs(float(la)))
+    finally:
+        torch.backends.cudnn.deterministic = prev
     for pa, pb in zip(net_a.parameters(), net_b.parameters()):
-        assert O.max_abs_normalised(pb.detach().cpu(), pa.detach().cpu()) < 1e-5
+        assert torch.equal(pa, pb)
 
 
 def test_host_feeder_carries_bf16_windows_and_index_batches():
@@ -354,6 +359,7 @@ def test_training_step_replays_as_one_cuda_graph():
     """the native step (forward, fused loss, BPTT, wgrad, Adam with its step count and lr in device memory) captured
     once and replayed: same parameters as the eager steps, including across a learning-rate change"""
     from nasa_niswan_b200.parallel import Trainer
+    torch.backends.cudnn.deterministic = True     # fixed-order sums: eager and replayed steps see identical gradients
     C, H, W, T, B = 21, 20, 24, 4, 4
     torch.manual_seed(6)
     xs = [torch.randn(B, T, C, H, W, device="cuda") for _ in range(4)]
@@ -377,6 +383,7 @@ def test_training_step_replays_as_one_cuda_graph():
     for pa, pb in zip(net_a.parameters(), net_b.parameters()):
         assert O.max_abs_normalised(pb.detach().cpu(), pa.detach().cpu()) < 1e-4
     assert int(float(tb.optimizer.state[0])) == int(float(ta.optimizer.state[0]))
+    torch.backends.cudnn.deterministic = False
 
 
 # ------------------------------------------------------------------------------------------------ parity at size
