@@ -167,6 +167,19 @@ int nint_loss_mse_l1_bank(const float* pred, const float* ybank, const int* win_
 int nint_adam_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float* state,
                        float beta1, float beta2, float eps, float grad_scale, void* stream);
 
+/* ---- data-parallel step tail over NVLink peer memory (the reference has no multi-GPU code).
+ * Replaces ncclAllReduce + nint_adam_step_dev by ONE kernel: cross-rank barrier, sum of every rank's gradients read
+ * straight from the peers' memory in rank order (bit-identical on all ranks), Adam on this rank's parameters.
+ * peer_buffers: HOST array of `world` device pointers -- the same symmetric allocation as mapped for each rank
+ * ([rank] is this GPU's own).  Layout of the allocation: two gradient slots of n fp32 used alternately (the caller
+ * writes step s's gradients to the slot at slot_offset_bytes, alternating by step parity) and a zero-initialised flag
+ * block of 32 uint32 at flags_offset_bytes.  seq: step number, increasing from 1 on every rank.  state as in
+ * nint_adam_step_dev.  Every rank must make the call for a step; a rank that never arrives traps the waiters after
+ * ~20 s instead of hanging them. */
+int nint_dp_allreduce_adam(const void* const* peer_buffers, long long slot_offset_bytes, long long flags_offset_bytes,
+                           int rank, int world, unsigned seq, float* params, float* exp_avg, float* exp_avg_sq,
+                           long long n, float* state, float beta1, float beta2, float eps, float grad_scale, void* stream);
+
 /* ---- measurement.  Kernel classes: 0 = fused gate-conv forward, 1 = dgrad + gate backward,
  * 2 = wgrad, 3 = everything else (layout packing, head, gradient unpacking); -1 = all.
  * nint_launch_count: kernels launched by this library in the calling process so far.

@@ -16,7 +16,7 @@ EXPORTS = ["nint_version", "nint_last_error", "nint_plan_create", "nint_plan_des
            "nint_plan_input_layout", "nint_pack_frames", "nint_backward", "nint_debug_raw_gates",
            "nint_gate_column", "nint_debug_read_trace", "nint_backward_bptt", "nint_backward_wgrad",
            "nint_backward_input", "nint_cell_forward", "nint_cell_backward", "nint_loss_mse_l1",
-           "nint_loss_mse_l1_bank", "nint_adam_step", "nint_adam_step_dev", "nint_fuse_inputs", "nint_fuse_inputs_bank",
+           "nint_loss_mse_l1_bank", "nint_adam_step", "nint_adam_step_dev", "nint_dp_allreduce_adam", "nint_fuse_inputs", "nint_fuse_inputs_bank",
            "nint_pick_tile", "nint_launch_count", "nint_plan_profile", "nint_plan_profile_read"]
 
 
@@ -76,6 +76,7 @@ def load():
     L.nint_fuse_inputs.argtypes = [fp, fp, fp, fp, fp, ci, cll, ci, ci, ci, ci, ci, ci, fp, vp]
     L.nint_adam_step.argtypes = [fp, fp, fp, fp, cll, cf, cf, cf, cf, ci, cf, vp]
     L.nint_adam_step_dev.argtypes = [fp, fp, fp, fp, cll, fp, cf, cf, cf, cf, vp]
+    L.nint_dp_allreduce_adam.argtypes = [ctypes.POINTER(vp), cll, cll, ci, ci, ctypes.c_uint, fp, fp, fp, cll, fp, cf, cf, cf, cf, vp]
     L.nint_fuse_inputs_bank.argtypes = [fp, fp, fp, fp, fp, ci, cll, ci, ci, ci, ci, ci, ci, ci, ci, ci, fp, vp]
     L.nint_loss_mse_l1_bank.argtypes = [fp, fp, fp, ci, ci, ci, ci, ci, ci, ci, ci, fp, fp, fp, vp]
     L.nint_pick_tile.argtypes = [ci, ci, ctypes.POINTER(ci), ctypes.POINTER(ci)]

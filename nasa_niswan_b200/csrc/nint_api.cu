@@ -1124,6 +1124,21 @@ int nint_adam_step_dev(float* params, const float* grads, float* exp_avg, float*
   return 0;
 }
 
+int nint_dp_allreduce_adam(const void* const* peer_buffers, long long slot_offset_bytes, long long flags_offset_bytes,
+                           int rank, int world, unsigned seq, float* params, float* exp_avg, float* exp_avg_sq,
+                           long long n, float* state, float beta1, float beta2, float eps, float grad_scale, void* stream) {
+  if (!peer_buffers || !params || !exp_avg || !exp_avg_sq || !state) return fail("nint_dp_allreduce_adam: null argument");
+  if (world < 1 || world > 16 || rank < 0 || rank >= world) return fail("nint_dp_allreduce_adam: rank %d of %d (at most 16 ranks)", rank, world);
+  if (n < 0 || seq == 0) return fail("nint_dp_allreduce_adam: n >= 0 and seq >= 1 required");
+  if (slot_offset_bytes % 16 || flags_offset_bytes % 16) return fail("nint_dp_allreduce_adam: offsets must be 16-byte aligned");
+  for (int r = 0; r < world; ++r)
+    if (!peer_buffers[r]) return fail("nint_dp_allreduce_adam: no mapping of rank %d's buffer", r);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  LAUNCH(nullptr, K_OTHER, st, launch_dp_allreduce_adam(peer_buffers, slot_offset_bytes, flags_offset_bytes, rank, world, seq, params,
+                                                        exp_avg, exp_avg_sq, n, state, beta1, beta2, eps, grad_scale, st));
+  return 0;
+}
+
 int nint_debug_read_trace(long long* host, int n, int clear) {
   if (!host || n < 0) return fail("nint_debug_read_trace: bad arguments");
   CK(cudaDeviceSynchronize());

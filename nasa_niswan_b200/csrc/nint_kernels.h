@@ -191,6 +191,11 @@ cudaError_t launch_adam(float* p, const float* g, float* m, float* v, long long 
 cudaError_t launch_adam_dev(float* p, const float* g, float* m, float* v, long long n, float* state, float beta1,
                             float beta2, float eps, float grad_scale, cudaStream_t s);
 
+// fused cross-rank barrier + gradient all-reduce over NVLink peer memory + Adam (nint_dp.cu)
+cudaError_t launch_dp_allreduce_adam(const void* const* peer_bases, long long slot_offset_bytes, long long flags_offset_bytes,
+                                     int rank, int world, unsigned seq, float* params, float* m, float* v, long long n,
+                                     float* state, float beta1, float beta2, float eps, float grad_scale, cudaStream_t s);
+
 // q-order helper (host + device)
 __host__ __device__ inline int q_to_n(int q, int hc) { return ((q >> 4) & 3) * hc + (q >> 6) * 16 + (q & 15); }
 

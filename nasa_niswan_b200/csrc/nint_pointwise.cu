@@ -2,6 +2,8 @@
 // repacking between the reference's NCHW fp32 tensors and the channels-last operand layout,
 // weight packing into UMMA panels, the 1x1 output head (model.py:251,274) and its backward,
 // and the unpacking of the wgrad accumulators into OIHW gradients.
+#include <type_traits>
+
 #include "nint_common.cuh"
 #include "nint_kernels.h"
 
@@ -552,167 +554,178 @@ cudaError_t launch_unpack_wgrad(const float* dw_acc, const float* db_acc, float*
 // preprocessing fusion (north-star item 4; dataset.py:520-537 stack + z-score, dataset.py:67-98 halo): stack the
 // first L levels of a 3-D forcing [N,L,H,W] with a 2-D emission field [N,H,W] as channel L, z-score per channel,
 // append S pre-normalised static attribute fields [S,H,W] (dataset.py:100-122,532-533: the same for every frame),
-// cyclic halo in longitude, reflect halo in latitude -> [N,L+1+S,Hp,Wp] fp32.  mode 1 reproduces the shipped RNN
-// dataset's quirk (np.fliplr on a (T,C,rows,W) slab flips CHANNELS: halo rows keep their order, channel order is
-// reversed; dataset.py:96).  One thread per output element, coalesced along longitude; HBM-bound.
+// cyclic halo in longitude, reflect halo in latitude.  mode 1 reproduces the shipped RNN dataset's quirk (np.fliplr on
+// a (T,C,rows,W) slab flips CHANNELS: halo rows keep their order, channel order is reversed; dataset.py:96).
+//
+// One kernel, two output layouts:
+//   PLANAR = false  the frame bank [N][Hp][Wp][CP] of E (bf16, or fp32 holding tf32-rounded values): the model's own
+//                   operand layout -- channels-last, zero padding lanes, the constant-1 lane the bias gradient rides on
+//                   -- that nint_forward_bank's TMA descriptors read.  No fp32 NCHW intermediate, no second packing pass.
+//   PLANAR = true   [N][C][Hp][Wp] fp32: the reference dataset's tensor layout (nint_fuse_inputs).
+// One thread per output pixel.  For a fixed channel the warp's loads are 32 consecutive longitudes of one source row
+// (coalesced; the cyclic wrap splits at most one request).  What it took to get off the instruction-issue limit
+// (measured on B200, 797 MB per call: 698 us -> see profiles/): every load of the pixel is issued before the first
+// use, unconditionally (padding lanes re-read channel C-1, an L1 hit: no per-channel branch splits the basic block), and
+// the z-score's IEEE division by the per-channel constant is Markstein's sequence on a precomputed RN(1/std) -- q0 =
+// RN(a*r), e = a - std*q0 (exact, fma), q = RN(q0 + e*r), the correctly rounded quotient whenever no intermediate leaves
+// the normal range -- three dependent FMA-class instructions instead of the ~10 of a general division; out-of-range
+// operands take the true division.  Results stay bit-identical to the numpy float32 pipeline.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) fuse_inputs_kernel(const float* __restrict__ lev, const float* __restrict__ emis,
-                                                          const float* __restrict__ mean, const float* __restrict__ stdv,
-                                                          const float* __restrict__ statics, int S,
-                                                          float* __restrict__ out, long long N, int L, int H, int W, int Hp,
-                                                          int Wp, int mode) {
-  // one block iteration = one output row yp of one frame, all channels: warps take channels, lanes walk the longitudes,
-  // so loads and stores are coalesced and there is no per-element index arithmetic beyond the cyclic wrap
+// z-score with the exact quotient: q0 = a*r; two Newton corrections on the exact (fma) residual.  The first makes q1
+// a faithful approximation of a/sd, Markstein's theorem then makes RN(q1 + e1*r) THE correctly rounded quotient.
+__device__ __forceinline__ float zscore_exact(float a, float sd, float rcp) {
+  const float q0 = a * rcp;
+  const float q1 = fmaf(fmaf(-sd, q0, a), rcp, q0);
+  return fmaf(fmaf(-sd, q1, a), rcp, q1);
+}
+
+struct FuseChan {            // per source channel, built once per block in shared memory
+  const float* src;          // frame 0, pixel 0 of the channel's field
+  long long frame_stride;    // elements between frames (0 for the static attributes)
+};
+
+template <typename E, int CP, bool PLANAR>
+__global__ void __launch_bounds__(256) fuse_kernel(const float* __restrict__ lev, const float* __restrict__ emis,
+                                                   const float* __restrict__ mean, const float* __restrict__ stdv,
+                                                   const float* __restrict__ statics, int S, E* __restrict__ out,
+                                                   long long N, int L, int H, int W, int Hp, int Wp, int mode,
+                                                   int ones_lane) {
   const int C = L + 1 + S;
+  const int HWp = Hp * Wp;
+  const long long HW = static_cast<long long>(H) * W;
+  __shared__ FuseChan s_ch[CP];
+  __shared__ float4 s_k[CP];                  // {mean, std, RN(1/std), range-check poison}; static attributes: {0, 1, 1, 0}
+  __shared__ const float* s_base[CP];         // s_ch[c].src advanced to the block's current frame
+  for (int c = threadIdx.x; c < CP; c += blockDim.x) {
+    FuseChan k;
+    const int cc = c < C ? c : C - 1;         // padding lanes alias the last channel (their loads are discarded)
+    if (cc < L) { k.src = lev + cc * HW; k.frame_stride = L * HW; }
+    else if (cc == L) { k.src = emis; k.frame_stride = HW; }
+    else { k.src = statics + (cc - L - 1) * HW; k.frame_stride = 0; }
+    s_ch[c] = k;
+    const bool zs = cc <= L;
+    const float sd = zs ? stdv[cc] : 1.f, rcp = 1.0f / sd;
+    // constants whose reciprocal leaves [2^-40, 2^40] (or is not finite) poison the range check: general division
+    const bool usual = fabsf(rcp) > 9.1e-13f && fabsf(rcp) < 1.1e12f;
+    s_k[c] = make_float4(zs ? mean[cc] : 0.f, sd, rcp, usual ? 0.f : -INFINITY);
+  }
   const int left = (Wp - W) / 2, top = (Hp - H) / 2, bot = Hp - H - top;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  const long long rows = N * Hp;
-  for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
-    const int yp = static_cast<int>(r % Hp);
-    const long long n = r / Hp;
+  const int chunks = (HWp + 255) / 256;       // 256-pixel chunks of one output frame
+  const long long items = N * chunks;
+  for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+    const long long n = item / chunks;        // block-uniform: the frame's base pointers are computed once per chunk
+    const int chunk = static_cast<int>(item - n * chunks);
+    __syncthreads();
+    if (threadIdx.x < CP) s_base[threadIdx.x] = s_ch[threadIdx.x].src + n * s_ch[threadIdx.x].frame_stride;
+    __syncthreads();
+    const int p = chunk * 256 + static_cast<int>(threadIdx.x);
+    if (p >= HWp) continue;
+    const int yp = p / Wp, xp = p - yp * Wp;
+    int xs = xp - left;                       // cyclic longitude (dataset.py:67-80)
+    if (xs < 0) xs += W;
+    if (xs >= W) xs -= W;
     int ys = yp - top;
-    bool flip = false;
+    bool flip = false;                        // mode 1: halo rows carry the channels in reverse order (dataset.py:96)
     if (ys < 0) {                             // upper halo: rows 1..top (dataset.py:82-98)
       if (mode == 0) ys = top - yp; else { ys = 1 + yp; flip = true; }
     } else if (ys >= H) {                     // lower halo: rows H-bot-1..H-2
       const int j = ys - H;
       if (mode == 0) ys = H - 2 - j; else { ys = H - bot - 1 + j; flip = true; }
     }
-    for (int c = warp; c < C; c += nwarps) {
-      const int cs = flip ? C - 1 - c : c;    // mode 1: halo rows carry the channels in reverse order (dataset.py:96)
-      const float* src = cs > L ? statics + (static_cast<long long>(cs - L - 1) * H + ys) * W
-                                : (cs < L ? lev + ((n * L + cs) * H + ys) * W : emis + (n * H + ys) * W);
-      const bool zs = cs <= L;                // static attributes arrive already z-scored
-      const float m = zs ? mean[cs] : 0.f, sd = zs ? stdv[cs] : 1.f;
-      float* dst = out + ((n * C + c) * Hp + yp) * Wp;
-      for (int xp = lane; xp < Wp; xp += 32) {
-        int xs = xp - left;                   // cyclic longitude (dataset.py:67-80)
-        if (xs < 0) xs += W;
-        if (xs >= W) xs -= W;
-        const float v = __ldg(src + xs);
-        dst[xp] = zs ? (v - m) / sd : v;      // IEEE subtract / divide: bit-identical to the numpy float32 pipeline
+    const int pix = ys * W + xs;
+    // pass 1: loads only, in groups of eight channels (a group past the last channel is skipped; inside a group the
+    // padding lanes re-read channel 0 or C-1, an L1 hit): nothing here depends on a loaded value.  pass 2: z-score.
+    // Static attributes carry the constants {0, 1, 1}: the same arithmetic returns them unchanged.
+    // The exactness argument (Markstein) needs a = v - mean and every intermediate in the normal range: with the
+    // per-channel constants vetted once per block (s_k.w) that holds whenever 2^-60 <= |a| <= 2^60, so the only
+    // per-element bookkeeping is min / max of |a|; a pixel that fails (zeros included) is redone with the division.
+    float v[CP];
+    float lo = 3.0e38f, hi = 0.f;
+    auto body = [&](auto flip_tag) {
+      constexpr bool FLIP = decltype(flip_tag)::value;
+#pragma unroll
+      for (int c0 = 0; c0 < CP; c0 += 8) {
+        if (c0 < C) {
+#pragma unroll
+          for (int c = c0; c < c0 + 8; ++c) {
+            const int cs = FLIP ? (c < C ? C - 1 - c : 0) : c;
+            v[c] = __ldg(s_base[cs] + pix);
+          }
+        } else {
+#pragma unroll
+          for (int c = c0; c < c0 + 8; ++c) v[c] = 0.f;
+        }
       }
+#pragma unroll
+      for (int c = 0; c < CP; ++c) {
+        if (c < C) {
+          const float4 k = s_k[FLIP ? C - 1 - c : c];
+          const float a = v[c] - k.x;           // IEEE subtract as in numpy
+          lo = fminf(lo, fabsf(a) + k.w);       // k.w = 0, or -inf (poison) when the channel's constants are unusual
+          hi = fmaxf(hi, fabsf(a));
+          v[c] = zscore_exact(a, k.y, k.z);
+        } else {
+          v[c] = (c == ones_lane) ? 1.f : 0.f;
+        }
+      }
+    };
+    if (flip) body(std::true_type{}); else body(std::false_type{});
+    if (!(lo > 8.7e-19f && hi < 1.1e18f)) {     // 2^-60 .. 2^60
+#pragma unroll
+      for (int c = 0; c < CP; ++c) {
+        if (c < C) {
+          const int cs = flip ? C - 1 - c : c;
+          const float4 k = s_k[cs];
+          v[c] = (__ldg(s_base[cs] + pix) - k.x) / k.y;
+        }
+      }
+    }
+    if constexpr (PLANAR) {
+      float* o = reinterpret_cast<float*>(out) + (n * C * Hp + yp) * Wp + xp;
+#pragma unroll
+      for (int c = 0; c < CP; ++c)
+        if (c < C) o[static_cast<long long>(c) * HWp] = v[c];
+    } else {
+      float r[CP];
+#pragma unroll
+      for (int c = 0; c < CP; ++c) r[c] = round_for(v[c], (E*)nullptr);
+      store_elems<E, CP>(out + (n * HWp + p) * CP, r);
     }
   }
 }
-cudaError_t launch_fuse_inputs(const float* lev, const float* emis, const float* mean, const float* stdv,
-                               const float* statics, int S, float* out, long long N, int L, int H, int W, int Hp, int Wp,
-                               int mode, cudaStream_t s) {
-  const long long rows = N * Hp;
-  const long long blocks = rows < 148LL * 32 ? rows : 148LL * 32;
+
+template <typename E, bool PLANAR>
+static cudaError_t fuse_launch(const float* lev, const float* emis, const float* mean, const float* stdv, const float* statics,
+                               int S, E* out, long long N, int L, int H, int W, int Hp, int Wp, int mode, int c_pad,
+                               int ones_lane, cudaStream_t s) {
+  if (static_cast<long long>(Hp) * Wp > 0x7fffff00LL || static_cast<long long>(H) * W > 0x7fffff00LL) return cudaErrorInvalidValue;
+  long long blocks = N * ((static_cast<long long>(Hp) * Wp + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
   if (blocks <= 0) return cudaSuccess;
-  fuse_inputs_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(lev, emis, mean, stdv, statics, S, out, N, L, H, W, Hp, Wp, mode);
+  switch (c_pad) {
+    case 16: fuse_kernel<E, 16, PLANAR><<<blocks, 256, 0, s>>>(lev, emis, mean, stdv, statics, S, out, N, L, H, W, Hp, Wp, mode, ones_lane); break;
+    case 32: fuse_kernel<E, 32, PLANAR><<<blocks, 256, 0, s>>>(lev, emis, mean, stdv, statics, S, out, N, L, H, W, Hp, Wp, mode, ones_lane); break;
+    case 48: fuse_kernel<E, 48, PLANAR><<<blocks, 256, 0, s>>>(lev, emis, mean, stdv, statics, S, out, N, L, H, W, Hp, Wp, mode, ones_lane); break;
+    case 64: fuse_kernel<E, 64, PLANAR><<<blocks, 256, 0, s>>>(lev, emis, mean, stdv, statics, S, out, N, L, H, W, Hp, Wp, mode, ones_lane); break;
+    default: return cudaErrorInvalidValue;
+  }
   return cudaGetLastError();
 }
 
-// The same fusion written straight into the model's operand layout: the frame bank
-// [N][Hp][Wp][CP] of E (bf16, or fp32 holding tf32-rounded values), channels-last with zero padding lanes and the
-// constant-1 lane the bias gradient rides on -- what nint_forward_bank's TMA descriptors read, so no fp32 NCHW
-// intermediate and no second packing pass exist.  One thread per output pixel: for a fixed channel the warp's loads are
-// 32 consecutive longitudes of one source row (coalesced; the cyclic wrap splits at most one request), and a thread
-// writes its pixel's CP channels as CP*sizeof(E)/32 256-bit stores (a warp covers one contiguous span).
-// One block iteration = one strip of SW <= 160 consecutive longitudes of one output row of one frame, all channels:
-//   load phase   warps walk (channel, 32-pixel run) pairs: a warp-wide load is 32 consecutive longitudes of ONE source
-//                row (128 contiguous bytes; the cyclic wrap splits at most one request), z-scored on the way into a
-//                [channel][pixel] fp32 tile in shared memory (row pitch SW + 1 words: both phases are conflict free);
-//   store phase  each thread packs one 16-byte piece (8 bf16 / 4 tf32 channels of one pixel) and consecutive lanes
-//                write consecutive pieces: a warp-wide store is 512 contiguous bytes of the bank.
-// The source row, the channel flip of mode 1 and the z-score constants are block- or warp-uniform; a thread does no
-// index arithmetic beyond the longitude wrap.  (The first version -- one thread per pixel looping over the channels --
-// ran at 1.1-2.3 TB/s: 32 IEEE divisions and 64 address computations per thread.)
-template <typename E>
-__global__ void __launch_bounds__(256) fuse_bank_kernel(const float* __restrict__ lev, const float* __restrict__ emis,
-                                                        const float* __restrict__ mean, const float* __restrict__ stdv,
-                                                        const float* __restrict__ statics, int S, E* __restrict__ out,
-                                                        long long N, int L, int H, int W, int Hp, int Wp, int mode,
-                                                        int c_pad, int ones_lane, int SW) {
-  extern __shared__ float s_tile[];            // [c_pad][SW + 1]
+// planar fp32 output for up to 64 channels; more channels (never the case for this model) take 64 at a time
+cudaError_t launch_fuse_inputs(const float* lev, const float* emis, const float* mean, const float* stdv,
+                               const float* statics, int S, float* out, long long N, int L, int H, int W, int Hp, int Wp,
+                               int mode, cudaStream_t s) {
   const int C = L + 1 + S;
-  const int pitch = SW + 1;
-  const int left = (Wp - W) / 2, top = (Hp - H) / 2, bot = Hp - H - top;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  const int strips = (Wp + SW - 1) / SW;
-  const int runs = SW >> 5;                    // 32-pixel runs per strip
-  constexpr int V = 16 / sizeof(E);            // channels per 16-byte piece
-  const int ppp = c_pad / V;                   // pieces per pixel
-  // padding lanes never change: zero (or one) once
-  for (int i = threadIdx.x; i < (c_pad - C) * SW; i += blockDim.x) {
-    const int c = C + i / SW;
-    s_tile[c * pitch + i % SW] = (c == ones_lane) ? 1.f : 0.f;
-  }
-  const long long items = N * Hp * strips;
-  for (long long it = blockIdx.x; it < items; it += gridDim.x) {
-    const int strip = static_cast<int>(it % strips);
-    const long long row = it / strips;
-    const int yp = static_cast<int>(row % Hp);
-    const long long n = row / Hp;
-    const int x0 = strip * SW;
-    const int npx = Wp - x0 < SW ? Wp - x0 : SW;
-    int ys = yp - top;
-    bool flip = false;                         // mode 1: halo rows carry the channels in reverse order (dataset.py:96)
-    if (ys < 0) {                              // upper halo: rows 1..top (dataset.py:82-98)
-      if (mode == 0) ys = top - yp; else { ys = 1 + yp; flip = true; }
-    } else if (ys >= H) {                      // lower halo: rows H-bot-1..H-2
-      const int j = ys - H;
-      if (mode == 0) ys = H - 2 - j; else { ys = H - bot - 1 + j; flip = true; }
-    }
-    __syncthreads();                           // the previous strip's store phase is done with the tile
-    // four (channel, run) items per warp iteration, every load issued before the first division: with one load in
-    // flight per warp the kernel is latency bound
-    for (int w0 = warp; w0 < C * runs; w0 += 4 * nwarps) {
-      float v[4];
-      int cs4[4], at[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int w = w0 + u * nwarps;
-        const int c = w / runs, px = (w - c * runs) * 32 + lane;
-        at[u] = -1;
-        v[u] = 0.f;
-        cs4[u] = 0;
-        if (w < C * runs && px < npx) {
-          const int cs = flip ? C - 1 - c : c;
-          const float* src = cs > L ? statics + (static_cast<long long>(cs - L - 1) * H + ys) * W
-                                    : (cs < L ? lev + ((n * L + cs) * H + ys) * W : emis + (n * H + ys) * W);
-          int xs = x0 + px - left;             // cyclic longitude (dataset.py:67-80)
-          if (xs < 0) xs += W;
-          if (xs >= W) xs -= W;
-          v[u] = __ldg(src + xs);
-          cs4[u] = cs;
-          at[u] = c * pitch + px;
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (at[u] >= 0) {
-          // IEEE subtract / divide: bit-identical to the numpy float32 pipeline; static attributes arrive z-scored
-          s_tile[at[u]] = cs4[u] <= L ? (v[u] - __ldg(mean + cs4[u])) / __ldg(stdv + cs4[u]) : v[u];
-        }
-      }
-    }
-    __syncthreads();
-    E* dst = out + (row * Wp + x0) * c_pad;
-    for (int i = threadIdx.x; i < npx * ppp; i += blockDim.x) {
-      const int px = i / ppp, piece = i - px * ppp;
-      float v[V];
-#pragma unroll
-      for (int j = 0; j < V; ++j) v[j] = round_for(s_tile[(piece * V + j) * pitch + px], (E*)nullptr);
-      store_elems<E, V>(dst + static_cast<long long>(i) * V, v);
-    }
-  }
+  if (C > 64) return cudaErrorInvalidValue;
+  return fuse_launch<float, true>(lev, emis, mean, stdv, statics, S, out, N, L, H, W, Hp, Wp, mode, (C + 15) / 16 * 16, -1, s);
 }
+
 template <typename E>
 static cudaError_t fuse_bank(const float* lev, const float* emis, const float* mean, const float* stdv, const float* statics,
                              int S, E* out, long long N, int L, int H, int W, int Hp, int Wp, int mode, int c_pad,
                              int ones_lane, cudaStream_t s) {
-  if (c_pad % 16 || c_pad > 64) return cudaErrorInvalidValue;
-  const int SW = Wp <= 160 ? (Wp + 31) / 32 * 32 : 128;
-  const int smem = c_pad * (SW + 1) * 4;                     // <= 64 * 161 * 4 = 41 KB
-  const long long items = N * Hp * ((Wp + SW - 1) / SW);
-  long long blocks = items < 148LL * 8 ? items : 148LL * 8;
-  if (blocks <= 0) return cudaSuccess;
-  fuse_bank_kernel<E><<<static_cast<unsigned>(blocks), 256, smem, s>>>(lev, emis, mean, stdv, statics, S, out, N, L, H, W, Hp, Wp,
-                                                                       mode, c_pad, ones_lane, SW);
-  return cudaGetLastError();
+  return fuse_launch<E, false>(lev, emis, mean, stdv, statics, S, out, N, L, H, W, Hp, Wp, mode, c_pad, ones_lane, s);
 }
 cudaError_t launch_fuse_inputs_bank(int dtype, const float* lev, const float* emis, const float* mean, const float* stdv,
                                     const float* statics, int S, void* out, long long N, int L, int H, int W, int Hp, int Wp,

@@ -70,6 +70,34 @@ def training_loss(pred: torch.Tensor, y: torch.Tensor, crop: Optional[Tuple[int,
     return F.mse_loss(p, y) + F.l1_loss(p, y)
 
 
+class SymmetricGradients:
+    """The flat gradient buffer as a SYMMETRIC allocation (torch.distributed._symmetric_memory: same layout on every
+    rank, mapped into every peer's address space over NVLink / NVSwitch): two gradient slots used alternately by step
+    parity plus a flag block.  `nint_dp_allreduce_adam` then does the cross-rank barrier, the sum of all ranks' slots in
+    rank order and the Adam update in ONE kernel that reads the peers' gradients directly -- no NCCL call, no second pass
+    over the gradients, bit-identical sums on every rank."""
+
+    def __init__(self, n: int, device, group=None):
+        import ctypes
+        import torch.distributed._symmetric_memory as symm
+        self.n = n
+        self.n_pad = (n + 63) // 64 * 64                 # slot size in floats: slots stay 256-byte aligned
+        self.buf = symm.empty(2 * self.n_pad + 64, dtype=torch.float32, device=device)
+        self.buf.zero_()
+        self.hdl = symm.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+        self.rank, self.world = self.hdl.rank, self.hdl.world_size
+        if self.world > 16:
+            raise RuntimeError("the fused NVLink step tail handles up to 16 ranks")
+        self.peer_ptrs = (ctypes.c_void_p * self.world)(*[int(ptr) for ptr in self.hdl.buffer_ptrs])
+        self.flags_offset_bytes = 2 * self.n_pad * 4
+        self.seq = 0
+        torch.cuda.synchronize(device)
+        dist.barrier(group)                              # every rank's zeroed flags are in place before the first signal
+
+    def slot(self, parity: int) -> torch.Tensor:
+        return self.buf[parity * self.n_pad: parity * self.n_pad + self.n]
+
+
 def bind_to_gpu_numa_node(device) -> Optional[int]:
     """Pins this process (and therefore the first-touch placement of the pinned staging buffers it allocates next) to
     the CPUs of the NUMA node the GPU hangs off.  With 8 ranks per box all staging from node 0, host-to-device copies
@@ -287,6 +315,17 @@ class Trainer:
                                                                       float(scheduler_config[1]))
         self._graph = None
         self.broadcast_parameters(process_group)
+        # multi-GPU step tail: one fused kernel over NVLink peer memory (barrier + all-reduce + Adam) instead of
+        # ncclAllReduce + the Adam kernel; NINT_DP_FUSED=0, or a box without peer mappings, keeps NCCL
+        self.sym = None
+        if self.native and self._world() > 1 and not self.overlap and os.environ.get("NINT_DP_FUSED", "1") == "1":
+            try:
+                self.sym = SymmetricGradients(self.grads.flat.numel(), self.device, process_group)
+                self._sym_views = [self._views_into(self.sym.slot(0)), self._views_into(self.sym.slot(1))]
+            except Exception as exc:     # noqa: BLE001  (no symmetric-memory support here: say so once, use NCCL)
+                import warnings
+                warnings.warn(f"fused NVLink step tail unavailable ({type(exc).__name__}: {exc}); using NCCL all-reduce")
+                self.sym = None
 
     def end_epoch(self):
         """train.py:120: `scheduler.step()` after the last batch of an epoch; returns the learning rate(s) now in force."""
@@ -309,6 +348,15 @@ class Trainer:
         ps = self.grads.params            # layers.{l}.conv.weight, .bias, ..., conv.weight, conv.bias (model.parameters() order)
         L = (len(ps) - 2) // 2
         return [ps[2 * l].grad for l in range(L)], [ps[2 * l + 1].grad for l in range(L)], ps[-2].grad, ps[-1].grad
+
+    def _views_into(self, flat: torch.Tensor):
+        """the same (weights, biases, head weight, head bias) views laid over another flat buffer"""
+        views, off = [], 0
+        for p in self.grads.params:
+            views.append(flat[off:off + p.numel()].view_as(p))
+            off += p.numel()
+        L = (len(views) - 2) // 2
+        return [views[2 * l] for l in range(L)], [views[2 * l + 1] for l in range(L)], views[-2], views[-1]
 
     def _loss_and_update(self, plan, pred, y, y_index, y_offset):
         """train.py:102-110 after the forward: fused loss + its gradient, BPTT into the flat buffer, all-reduce, Adam."""
@@ -334,6 +382,26 @@ class Trainer:
                 _lib.check(lib.nint_loss_mse_l1_bank(vp(pred), vp(y), vp(y_index), int(y_offset), B, H, W, y0, y1, x0, x1,
                                                      vp(dpred), vp(loss), vp(self._stats), st), "nint_loss_mse_l1_bank")
         world = self._world()
+        if self.sym is not None:
+            # fused tail: BPTT writes this step's slot of the symmetric buffer; one kernel then signals the peers, waits
+            # for theirs, sums all ranks' slots over NVLink in rank order and applies Adam
+            sym, opt = self.sym, self.optimizer
+            sym.seq += 1
+            parity = sym.seq & 1
+            plan.backward(dpred, out=self._sym_views[parity])
+            opt.step_count += 1
+            opt._sync_lr()
+            with _lib.on_device(pred.device):
+                _lib.check(lib.nint_dp_allreduce_adam(sym.peer_ptrs, parity * sym.n_pad * 4, sym.flags_offset_bytes, sym.rank,
+                                                      sym.world, sym.seq, vp(opt.flat_params), vp(opt.exp_avg),
+                                                      vp(opt.exp_avg_sq), opt.flat_params.numel(), vp(opt.state),
+                                                      opt.betas[0], opt.betas[1], opt.eps, 1.0 / world,
+                                                      _lib.stream_ptr(pred.device)), "nint_dp_allreduce_adam")
+            flat_views = self._sym_views[parity]
+            for q, g in zip(opt.params, [t for pair in zip(flat_views[0], flat_views[1]) for t in pair] + [flat_views[2], flat_views[3]]):
+                q.grad = g                 # this rank's (un-reduced) gradients of the step; the sum lives only in registers
+                torch.autograd.graph.increment_version(q)
+            return loss[0]
         if world > 1 and not self.overlap:
             plan.backward(dpred, out=self._grad_views())
             dist.all_reduce(self.grads.flat, op=dist.ReduceOp.SUM, group=self.group)

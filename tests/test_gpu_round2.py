@@ -220,6 +220,60 @@ def test_model_on_a_non_current_device():
         net.plan_for(x.to("cuda:1"), False).forward(x.to("cuda:0"))
 
 
+def _fused_tail_worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    from nasa_niswan_b200 import ConvLSTM
+    from nasa_niswan_b200.parallel import Trainer
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    torch.backends.cudnn.deterministic = True          # fixed-order local gradients: the two tails see the same inputs
+    C, H, W, T, B = 21, 20, 24, 4, 4
+    results = {}
+    for fused in ("1", "0"):
+        os.environ["NINT_DP_FUSED"] = fused
+        torch.manual_seed(5)
+        net = ConvLSTM(C, [32], [3], 1, precision="bf16").to(dev)
+        tr = Trainer(net, lr=1e-3, scheduler_config=(2, 0.5))
+        assert (tr.sym is not None) == (fused == "1"), "fused NVLink tail did not come up"
+        gen = torch.Generator().manual_seed(100 + rank)          # every rank trains on its own shard
+        losses = []
+        for step in range(5):
+            x = torch.randn(B, T, C, H, W, generator=gen).to(dev)
+            y = torch.randn(B, H, W, generator=gen).to(dev)
+            losses.append(float(tr.step(x, y)))
+            if step % 2 == 1:
+                tr.end_epoch()
+        results[fused] = ([p.detach().cpu() for p in net.parameters()], losses)
+    torch.save(results, os.path.join(out_dir, f"rank{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs with NVLink peer access")
+def test_fused_nvlink_step_tail_matches_nccl(tmp_path):
+    """nint_dp_allreduce_adam (cross-rank barrier + gradient sum over NVLink peer memory + Adam in one kernel) against
+    ncclAllReduce + the Adam kernel: same parameters on every rank after five steps on rank-specific shards, and the
+    replicas stay bit-identical to each other"""
+    import socket
+    import torch.multiprocessing as mp
+    with socket.socket() as s_:
+        s_.bind(("127.0.0.1", 0))
+        port = s_.getsockname()[1]
+    world = 2
+    mp.spawn(_fused_tail_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    res = [torch.load(os.path.join(tmp_path, f"rank{r}.pt")) for r in range(world)]
+    for fused in ("1", "0"):
+        for a, b in zip(res[0][fused][0], res[1][fused][0]):
+            assert torch.equal(a, b), "replicas diverged"
+    for a, b in zip(res[0]["1"][0], res[0]["0"][0]):
+        assert O.max_abs_normalised(a, b) < 1e-6
+    assert res[0]["1"][1] != res[1]["1"][1]                       # different shards -> different local losses
+    for la, lb in zip(res[0]["1"][1], res[0]["0"][1]):
+        assert abs(la - lb) < 1e-5 * max(1.0, abs(la))
+
+
 # ------------------------------------------------------------------------------------------------ API completeness
 @pytest.mark.parametrize("cfg", [("tf32", 5, 32, 3), ("bf16", 21, 64, 5), ("tf32", 3, 10, 3)], ids=["tf32_h32", "bf16_h64_k5", "tf32_h10"])
 def test_cell_is_differentiable_like_the_reference_module(cfg):
