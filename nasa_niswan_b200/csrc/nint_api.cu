@@ -1217,9 +1217,6 @@ static int bwd_step(nint_plan* p, int l, int t, const float* dpred, const float*
     }
   }
   g.dh_ext = (l == L - 1 && t == T - 1) ? dh_ext : nullptr;
-  g.direct_store = (p->debug_flags & 256) ? 1 : 0;   // experiment: epilogue outputs written straight to global memory
-  g.direct_g = slot_ptr(p, y.G, t, 4 * y.hc);
-  g.direct_dc = y.dC;
   set_batch_range(p, g, b0, nb);
   LAUNCH(p, K_BWD, st, launch_conv_halo(EPI_BWD, p->dtype, g, p->num_sms, st));
   return 0;

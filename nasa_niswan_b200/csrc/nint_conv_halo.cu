@@ -546,15 +546,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
   } else if (warp == 2 || warp == 3) {
     // ------------------------------------------------------------------ epilogue TMA stores
     // backward: the two warps alternate channel groups; forward: warp 3 stores c, warp 2 stores h + gates
-    if constexpr (EPI == EPI_BWD) {
-      if (!p.direct_store) epi_storer<E, EPI>(p, sE, st_ready, e_empty, walk, warp - 2, 2);
-    }
+    if constexpr (EPI == EPI_BWD) epi_storer<E, EPI>(p, sE, st_ready, e_empty, walk, warp - 2, 2);
     if constexpr (EPI == EPI_FWD) fwd_storer<E>(p, sE, FwdEpiBars{e_full, e_empty, st_ready, hg_ready, hg_empty}, walk, warp == 3 ? 0 : 1);
   } else if (warp == 4 || warp == 5) {
     // ------------------------------------------------------------------ epilogue TMA loads
     // backward: 4 boxes per channel group, two loaders alternate groups; forward: one box per group, warp 4 only
-    // (direct-store mode has no storer: the math warps free a stage themselves, through st_ready)
-    if constexpr (EPI == EPI_BWD) epi_loader<E, EPI>(p, sE, e_full, p.direct_store ? st_ready : e_empty, walk, warp - 4, 2);
+    if constexpr (EPI == EPI_BWD) epi_loader<E, EPI>(p, sE, e_full, e_empty, walk, warp - 4, 2);
     if constexpr (EPI == EPI_FWD) {
       if (warp == 4) fwd_c_loader<E>(p, sE, FwdEpiBars{e_full, e_empty, st_ready, hg_ready, hg_empty}, walk);
       if (warp == 5 && p.nseg > 0 && lead_cta && dual) issue_dual(1);   // second MMA issuer

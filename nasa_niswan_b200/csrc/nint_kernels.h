@@ -72,11 +72,6 @@ struct alignas(64) ConvGemmParams {
   const float* head_dpred;  // optional [B,H,W] (+ stride): dh += head_dpred * head_w[c]
   long long head_dpred_bstride;  // elements between images of head_dpred
   const float* head_w;      // [hc]
-  // direct_store (experiment -> BWD epilogue): the math warps write dgates / dc straight to global memory instead of
-  // staging them in shared memory for TMA stores: direct_g = dgates_t [B][H][W][4hc] of E, direct_dc [B][H][W][hc] fp32
-  int direct_store;
-  void* direct_g;
-  float* direct_dc;
   const float* dh_ext;      // optional [B,H,W,hc] fp32 channels-last: dh += dh_ext (standalone cell backward, model.py:216-231)
   // ---- EPI_RAW: dump fp32 accumulators [B,H,W,n_blocks*n_tile] (debug / generic conv)
   float* raw_out;
