@@ -24,7 +24,7 @@ from oracle import convlstm_oracle as O  # noqa: E402
 
 BAR = {"bf16": 2e-2, "tf32": 1e-3}      # north-star parity bars
 FAIL_FACTOR = 5.0
-HIDDEN = [16, 32, 48, 64, 128, 192, 256]
+HIDDEN = [10, 16, 24, 32, 48, 64, 70, 128, 192, 256]      # incl. sizes that run padded (model.py:207 takes any int)
 
 
 def random_case(rng):
