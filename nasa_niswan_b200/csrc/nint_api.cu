@@ -51,6 +51,7 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // kernel classes for the launch counter / CUDA-event profile
 enum : int { K_FWD = 0, K_BWD = 1, K_WGRAD = 2, K_OTHER = 3, K_NCLS = 4 };
+constexpr int kResidCtas = 160;   // upper bound on the CTAs of one conv launch (one per SM)
 long long g_launches[K_NCLS] = {0, 0, 0, 0};
 
 struct Profile {
@@ -74,6 +75,7 @@ struct Layer {
   float* dC = nullptr;     // [B][H][W][hc]         (training)
   uint8_t *wx = nullptr, *wh = nullptr, *wdx = nullptr, *wdh = nullptr;
   float *bias_q = nullptr, *dw_acc = nullptr, *db_acc = nullptr;
+  float* db_resid = nullptr;   // tf32 training plans: [kResidCtas][4][4hc] sums of the dgates rounding residuals (nint_kernels.h)
   size_t dw_acc_bytes = 0;   // one slice [taps][4hc][ncols]; deterministic mode keeps det_splits slices
   int det_splits = 0;
   int ncols = 0;
@@ -304,6 +306,7 @@ size_t carve(nint_plan* p, uint8_t* base) {
       const size_t slices = p->deterministic ? static_cast<size_t>(y.det_splits) : 1;
       y.dw_acc = reinterpret_cast<float*>(take(y.dw_acc_bytes * slices));
       y.db_acc = reinterpret_cast<float*>(take(4 * y.hc * 4 * slices));
+      y.db_resid = p->dtype == TF32 ? reinterpret_cast<float*>(take(static_cast<size_t>(kResidCtas) * 4 * 4 * y.hc * 4)) : nullptr;
     }
   }
   const Layer& top = p->layer[p->L - 1];
@@ -1217,6 +1220,7 @@ static int bwd_step(nint_plan* p, int l, int t, const float* dpred, const float*
     }
   }
   g.dh_ext = (l == L - 1 && t == T - 1) ? dh_ext : nullptr;
+  g.db_resid = p->num_sms <= kResidCtas ? y.db_resid : nullptr;
   set_batch_range(p, g, b0, nb);
   LAUNCH(p, K_BWD, st, launch_conv_halo(EPI_BWD, p->dtype, g, p->num_sms, st));
   return 0;
@@ -1227,6 +1231,8 @@ static int bptt_loop(nint_plan* p, const float* dpred, const float* dseq, const 
   // above at step t) accumulates dh_t in TMEM; its epilogue is the gate backward of step t and
   // overwrites the saved gates with dgates in place.
   const int SB = p->sub_batch > 0 ? p->sub_batch : p->B;
+  for (int l = 0; l < p->L; ++l)
+    if (p->layer[l].db_resid) CK(cudaMemsetAsync(p->layer[l].db_resid, 0, static_cast<size_t>(kResidCtas) * 4 * 4 * p->layer[l].hc * 4, st));
   for (int b0 = 0; b0 < p->B; b0 += SB) {
     const int nb = b0 + SB <= p->B ? SB : p->B - b0;
     for (int t = p->T - 1; t >= 0; --t)
@@ -1290,7 +1296,8 @@ int nint_backward_wgrad(nint_plan* p, int l, float* grad_weight_l, float* grad_b
   }
   if (grad_weight_l)
     LAUNCH(p, K_OTHER, st, launch_unpack_wgrad(y.dw_acc, y.db_acc, grad_weight_l, grad_bias_l, y.cin, y.hc_real, y.hc, y.k, y.ncols, y.cx_pad,
-                                               bias_col, 0, p->deterministic ? y.det_splits : 0, st));
+                                               bias_col, 0, p->deterministic ? y.det_splits : 0,
+                                               p->num_sms <= kResidCtas ? y.db_resid : nullptr, kResidCtas * 4, st));
   return 0;
 }
 

@@ -520,6 +520,11 @@ __device__ __forceinline__ void epi_math(const ConvGemmParams& p, int warp, int 
   uint32_t ph = 0;
   int abuf = 0;
   uint32_t aphase = 0;
+  // tf32 backward: per-lane sums of the dgates rounding residuals, one column per channel group (see db_resid)
+  constexpr int kResidGroups = (EPI == EPI_BWD && DT == NINT_TF32) ? 16 : 1;
+  float racc[kResidGroups];
+#pragma unroll
+  for (int k = 0; k < kResidGroups; ++k) racc[k] = 0.f;
   for (int base = w.first_tile; base < w.tiles_padded; base += w.tile_stride) {
     bool waited = (p.nseg == 0);
     for (int gi = 0; gi < G; ++gi) {
@@ -651,10 +656,35 @@ __device__ __forceinline__ void epi_math(const ConvGemmParams& p, int warp, int 
               gf[j] = d_f * f_ * (1.f - f_);
               gg[j] = d_g * (1.f - g_ * g_);
               go[j] = d_o * o_ * (1.f - o_);
-              if constexpr (DT == NINT_TF32) {
-                // dgates are MMA operands of dgrad and wgrad: round to nearest tf32 (the MMA truncates)
-                gi_[j] = round_tf32(gi_[j]); gf[j] = round_tf32(gf[j]);
-                gg[j] = round_tf32(gg[j]); go[j] = round_tf32(go[j]);
+            }
+            if constexpr (DT == NINT_TF32) {
+              // dgates are MMA operands of dgrad and wgrad: round to nearest tf32 (the MMA truncates).  The residuals
+              // would be lost to the bias gradient (a plain, often nearly cancelling sum of dgates): reduce them over
+              // the warp's 32 pixels with a butterfly that halves the values per lane at every step (31 shuffles for
+              // 32 columns; lane l ends with column l = gate * 8 + channel) and keep them per channel group.
+              float res[32];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float r;
+                r = round_tf32(gi_[j]); res[j] = gi_[j] - r; gi_[j] = r;
+                r = round_tf32(gf[j]); res[8 + j] = gf[j] - r; gf[j] = r;
+                r = round_tf32(gg[j]); res[16 + j] = gg[j] - r; gg[j] = r;
+                r = round_tf32(go[j]); res[24 + j] = go[j] - r; go[j] = r;
+              }
+              if (p.db_resid) {
+#pragma unroll
+                for (int st_ = 16; st_ >= 1; st_ >>= 1) {
+                  const bool upper = (lane & st_) != 0;
+#pragma unroll
+                  for (int i = 0; i < st_; ++i) {
+                    const float send = upper ? res[i] : res[i + st_];
+                    const float keep = upper ? res[i + st_] : res[i];
+                    res[i] = keep + __shfl_xor_sync(0xffffffffu, send, st_);
+                  }
+                }
+#pragma unroll
+                for (int k = 0; k < kResidGroups; ++k)
+                  if (k == grp) racc[k] += res[0];
               }
             }
             sts8<float, 64>(st + p.e_off_dc, row, half, dc);
@@ -690,6 +720,16 @@ __device__ __forceinline__ void epi_math(const ConvGemmParams& p, int warp, int 
         abuf = 0;
         aphase ^= 1;
       }
+    }
+  }
+  if constexpr (EPI == EPI_BWD && DT == NINT_TF32) {
+    if (p.db_resid) {
+      // lane l owns column (gate = l >> 3, channel = half * 8 + (l & 7)) of every channel group; slots are private to
+      // (CTA, pixel quadrant), so the read-modify-write needs no atomics and the sum order is fixed
+      float* slot = p.db_resid + (static_cast<long long>(blockIdx.x) * 4 + quad) * (4 * p.hc);
+#pragma unroll
+      for (int k = 0; k < kResidGroups; ++k)
+        if (k < ngroups) slot[k * 64 + (lane >> 3) * 16 + half * 8 + (lane & 7)] += racc[k];
     }
   }
 }

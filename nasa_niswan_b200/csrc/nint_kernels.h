@@ -72,6 +72,10 @@ struct alignas(64) ConvGemmParams {
   const float* head_dpred;  // optional [B,H,W] (+ stride): dh += head_dpred * head_w[c]
   long long head_dpred_bstride;  // elements between images of head_dpred
   const float* head_w;      // [hc]
+  // tf32 mode: dgates are rounded to tf32 (the MMA operand format) when stored; the bias gradient -- a plain sum of
+  // dgates that can nearly cancel -- also gets the sum of the rounding residuals: [gridDim.x][4 quadrants][4*hc] fp32,
+  // every (CTA, pixel quadrant) adds into its own slots (deterministic), reduced by unpack_wgrad_kernel
+  float* db_resid;
   const float* dh_ext;      // optional [B,H,W,hc] fp32 channels-last: dh += dh_ext (standalone cell backward, model.py:216-231)
   // ---- EPI_RAW: dump fp32 accumulators [B,H,W,n_blocks*n_tile] (debug / generic conv)
   float* raw_out;
@@ -167,7 +171,7 @@ cudaError_t launch_head_bwd(int dtype, const void* h, const float* dpred, long l
 // slices summed in order (deterministic mode)
 cudaError_t launch_unpack_wgrad(const float* dw_acc, const float* db_acc, float* gw, float* gb, int cin, int hc_real,
                                 int hc, int k, int ncols, int cx_pad, int bias_col, int accumulate, int nparts,
-                                cudaStream_t s);
+                                const float* db_resid, int resid_slots, cudaStream_t s);
 // fp32 accumulator dump [B][H][W][ncols] (EPI_RAW) -> gradient tensor [B][(T)][C][H][W] fp32 (dx / dh of the cell API)
 cudaError_t launch_unpack_raw(const float* raw, float* dst, int B, int C, int H, int W, int ncols, long long dst_bstride,
                               cudaStream_t s);

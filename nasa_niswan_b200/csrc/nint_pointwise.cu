@@ -536,7 +536,8 @@ cudaError_t launch_head_bwd(int dtype, const void* h, const float* dpred, long l
 // fixed order.
 __global__ void unpack_wgrad_kernel(const float* __restrict__ dw_acc, const float* __restrict__ db_acc,
                                     float* __restrict__ gw, float* __restrict__ gb, int cin, int hc_real, int hc, int k,
-                                    int ncols, int cx_pad, int bias_col, int accumulate, int nparts) {
+                                    int ncols, int cx_pad, int bias_col, int accumulate, int nparts,
+                                    const float* __restrict__ db_resid, int resid_slots) {
   const int taps = k * k, ctot = cin + hc_real, hc4 = 4 * hc;
   const long long total = static_cast<long long>(hc4) * ctot * taps;
   const long long slice = static_cast<long long>(taps) * hc4 * ncols;
@@ -565,15 +566,19 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ dw_acc, const floa
       for (int s = 0; s < np; ++s)
         v += bias_col >= 0 ? dw_acc[s * slice + (static_cast<long long>(taps / 2) * hc4 + q) * ncols + bias_col]
                            : db_acc[static_cast<long long>(s) * hc4 + q];
+      // tf32 mode: plus what rounding the stored dgates to tf32 took away from the sum (fixed-order over the slots)
+      float r = 0.f;
+      for (int i = 0; i < resid_slots; ++i) r += db_resid[static_cast<long long>(i) * hc4 + q];
+      v += r;
       *dst = accumulate ? *dst + v : v;
     }
   }
 }
 cudaError_t launch_unpack_wgrad(const float* dw_acc, const float* db_acc, float* gw, float* gb, int cin, int hc_real,
                                 int hc, int k, int ncols, int cx_pad, int bias_col, int accumulate, int nparts,
-                                cudaStream_t s) {
+                                const float* db_resid, int resid_slots, cudaStream_t s) {
   unpack_wgrad_kernel<<<296, 256, 0, s>>>(dw_acc, db_acc, gw, gb, cin, hc_real, hc, k, ncols, cx_pad, bias_col, accumulate,
-                                          nparts);
+                                          nparts, db_resid, db_resid ? resid_slots : 0);
   return cudaGetLastError();
 }
 

@@ -163,12 +163,13 @@ def test_plans_against_oracle(cfg, precision):
     (5, 2, 21, 8, 16, [64], [1]),            # 1x1 "convolution": no halo at all
 ], ids=["b1_t1_c32", "c40_ragged", "h192", "h256", "k7", "k1"])
 def test_edge_geometries_against_oracle(cfg, precision):
-    """forward + BPTT against the CPU oracle at the edges of the supported geometry.  tf32 tolerance here is 2e-3:
-    dgates are rounded to tf32 (2^-11) before the wgrad MMAs, and with only 128..400 pixel-steps a gradient is a
-    short sum of signed terms, so that rounding is not averaged away as in the 12-step rollout (1e-3 there)."""
+    """forward + BPTT against the CPU oracle at the edges of the supported geometry, at the north-star bars (1e-3 tf32,
+    2e-2 bf16) even though a gradient here is a short sum of 128..400 signed pixel-steps: in tf32 mode the bias gradient
+    also receives the sum of the residuals that rounding the stored dgates to tf32 takes away (nint_kernels.h db_resid);
+    until round 2 that rounding left the nearly cancelling bias sums at 1.4e-3..2.5e-3 and this test allowed 2e-3."""
     from nasa_niswan_b200 import ConvLSTM
     B, T, C, H, W, hidden, ks = cfg
-    tol = {"tf32": 2e-3, "bf16": TOL["bf16"]}[precision]
+    tol = TOL[precision]
     torch.manual_seed(5)
     net = ConvLSTM(C, hidden, ks, len(hidden), precision=precision)
     params = {k: v.detach().clone() for k, v in net.state_dict().items()}

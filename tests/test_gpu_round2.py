@@ -334,7 +334,7 @@ def test_input_gradient_matches_autograd(precision):
     # parameters still get their gradients on this path
     leaf = {k: v.clone().requires_grad_(True) for k, v in params.items()}
     O.convlstm_forward(x, leaf, 2).backward(g)
-    _check_grads(net, {k: v.grad for k, v in leaf.items()}, 2e-3 if precision == "tf32" else TOL[precision])
+    _check_grads(net, {k: v.grad for k, v in leaf.items()}, TOL[precision])
 
 
 @pytest.mark.parametrize("cfg", [(5, [10], [3]), (21, [70], [3]), (5, [24, 5], [3, 5]), (8, [100, 48], [3, 3])],
@@ -351,7 +351,7 @@ def test_arbitrary_hidden_sizes(cfg, precision):
     pred = net(x.cuda())
     assert O.max_abs_normalised(pred.detach().cpu(), ref_pred) < TOL[precision]
     pred.backward(dpred.cuda())
-    _check_grads(net, ref_grads, 2e-3 if precision == "tf32" else TOL[precision])
+    _check_grads(net, ref_grads, TOL[precision])
     assert [tuple(p.shape) for p in net.parameters()] == [tuple(v.shape) for v in params.values()]
 
 
