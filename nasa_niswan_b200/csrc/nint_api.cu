@@ -52,6 +52,11 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 // kernel classes for the launch counter / CUDA-event profile
 enum : int { K_FWD = 0, K_BWD = 1, K_WGRAD = 2, K_OTHER = 3, K_NCLS = 4 };
 constexpr int kResidCtas = 160;   // upper bound on the CTAs of one conv launch (one per SM)
+// tf32 rounding residuals of the bias gradient are tracked for SHORT sums only (up to 2^20 pixel-steps per bias
+// element): there the rounding does not average out (tiny cases sat at 1.4e-3..2.5e-3 of the 1e-3 bar); on long sums
+// (cfg 2 at B=32: 5 M pixel-steps, bias gradients at 1e-4..7e-4) the warp reductions would cost the tf32 backward
+// kernel 40 % (306 -> 430 us per launch, measured) for nothing.
+constexpr long long kResidMaxPixelSteps = 1LL << 20;
 long long g_launches[K_NCLS] = {0, 0, 0, 0};
 
 struct Profile {
@@ -1159,6 +1164,10 @@ int nint_debug_raw_gates(nint_plan* p, const float* x, float* out, void* stream)
   return cell_step(p, 0, 0, EPI_RAW, out, st);
 }
 
+static bool resid_on(const nint_plan* p) {
+  return p->num_sms <= kResidCtas && static_cast<long long>(p->B) * p->T * p->H * p->W <= kResidMaxPixelSteps;
+}
+
 // one fused dgrad + gate-backward launch of layer l at step t for images [b0, b0 + nb) (nb = 0: all)
 static int bwd_step(nint_plan* p, int l, int t, const float* dpred, const float* dseq, const float* dh_ext, bool dc_given,
                     cudaStream_t st, int b0, int nb) {
@@ -1220,7 +1229,7 @@ static int bwd_step(nint_plan* p, int l, int t, const float* dpred, const float*
     }
   }
   g.dh_ext = (l == L - 1 && t == T - 1) ? dh_ext : nullptr;
-  g.db_resid = p->num_sms <= kResidCtas ? y.db_resid : nullptr;
+  g.db_resid = resid_on(p) ? y.db_resid : nullptr;
   set_batch_range(p, g, b0, nb);
   LAUNCH(p, K_BWD, st, launch_conv_halo(EPI_BWD, p->dtype, g, p->num_sms, st));
   return 0;
@@ -1297,7 +1306,7 @@ int nint_backward_wgrad(nint_plan* p, int l, float* grad_weight_l, float* grad_b
   if (grad_weight_l)
     LAUNCH(p, K_OTHER, st, launch_unpack_wgrad(y.dw_acc, y.db_acc, grad_weight_l, grad_bias_l, y.cin, y.hc_real, y.hc, y.k, y.ncols, y.cx_pad,
                                                bias_col, 0, p->deterministic ? y.det_splits : 0,
-                                               p->num_sms <= kResidCtas ? y.db_resid : nullptr, kResidCtas * 4, st));
+                                               resid_on(p) ? y.db_resid : nullptr, kResidCtas * 4, st));
   return 0;
 }
 
