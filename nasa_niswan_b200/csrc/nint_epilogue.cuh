@@ -520,11 +520,6 @@ __device__ __forceinline__ void epi_math(const ConvGemmParams& p, int warp, int 
   uint32_t ph = 0;
   int abuf = 0;
   uint32_t aphase = 0;
-  // tf32 backward: per-lane sums of the dgates rounding residuals, one column per channel group (see db_resid)
-  constexpr int kResidGroups = (EPI == EPI_BWD && DT == NINT_TF32) ? 16 : 1;
-  float racc[kResidGroups];
-#pragma unroll
-  for (int k = 0; k < kResidGroups; ++k) racc[k] = 0.f;
   for (int base = w.first_tile; base < w.tiles_padded; base += w.tile_stride) {
     bool waited = (p.nseg == 0);
     for (int gi = 0; gi < G; ++gi) {
@@ -682,9 +677,10 @@ __device__ __forceinline__ void epi_math(const ConvGemmParams& p, int warp, int 
                     res[i] = keep + __shfl_xor_sync(0xffffffffu, send, st_);
                   }
                 }
-#pragma unroll
-                for (int k = 0; k < kResidGroups; ++k)
-                  if (k == grp) racc[k] += res[0];
+                // lane l owns column (gate = l >> 3, channel = half * 8 + (l & 7)) of this channel group; the slots are
+                // private to (CTA, pixel quadrant): the read-modify-write needs no atomics and the sum order is fixed
+                float* slot = p.db_resid + (static_cast<long long>(blockIdx.x) * 4 + quad) * (4 * p.hc);
+                slot[grp * 64 + (lane >> 3) * 16 + half * 8 + (lane & 7)] += res[0];
               }
             }
             sts8<float, 64>(st + p.e_off_dc, row, half, dc);
@@ -720,16 +716,6 @@ __device__ __forceinline__ void epi_math(const ConvGemmParams& p, int warp, int 
         abuf = 0;
         aphase ^= 1;
       }
-    }
-  }
-  if constexpr (EPI == EPI_BWD && DT == NINT_TF32) {
-    if (p.db_resid) {
-      // lane l owns column (gate = l >> 3, channel = half * 8 + (l & 7)) of every channel group; slots are private to
-      // (CTA, pixel quadrant), so the read-modify-write needs no atomics and the sum order is fixed
-      float* slot = p.db_resid + (static_cast<long long>(blockIdx.x) * 4 + quad) * (4 * p.hc);
-#pragma unroll
-      for (int k = 0; k < kResidGroups; ++k)
-        if (k < ngroups) slot[k * 64 + (lane >> 3) * 16 + half * 8 + (lane & 7)] += racc[k];
     }
   }
 }
