@@ -22,14 +22,20 @@ def main():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--seq-len", type=int, default=12)
     ap.add_argument("--ksize", type=int, default=3)
+    ap.add_argument("--shipped", action="store_true", help="the reference's recipe: 5 -> 64/32/16, k 5/3/3, 100x154, T=48, B=8, crop")
     ap.add_argument("--bank", action="store_true")
     ap.add_argument("--graph", action="store_true")
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     B, T, C, H, W = a.batch, a.seq_len, 21, 90, 144
     torch.manual_seed(0)
-    net = ConvLSTM(C, [64], [a.ksize], 1, precision="bf16").to(dev)
-    tr = Trainer(net, lr=1e-3, betas=(0.5, 0.999))
+    crop = None
+    if a.shipped:
+        B, T, C, H, W, crop = 8, 48, 5, 100, 154, (5, 95, 5, 149)
+        net = ConvLSTM(C, [64, 32, 16], [5, 3, 3], 3, precision="bf16").to(dev)
+    else:
+        net = ConvLSTM(C, [64], [a.ksize], 1, precision="bf16").to(dev)
+    tr = Trainer(net, lr=1e-3, betas=(0.5, 0.999), crop=crop)
     if a.bank:
         bank = FrameBank.from_frames(torch.randn(512, C, H, W, device=dev), "bf16", targets=torch.randn(512, H, W, device=dev))
         idx = torch.randint(0, 512 - T + 1, (B,), dtype=torch.int32).to(dev)
@@ -38,7 +44,8 @@ def main():
             tr.capture(bank=bank, win_start=idx, seq_len=T)
             step = tr.replay
     else:
-        x, y = torch.randn(B, T, C, H, W, device=dev), torch.randn(B, H, W, device=dev)
+        x = torch.randn(B, T, C, H, W, device=dev)
+        y = torch.randn(B, crop[1] - crop[0], crop[3] - crop[2], device=dev) if crop else torch.randn(B, H, W, device=dev)
         step = lambda: tr.step(x, y)
         if a.graph:
             tr.capture(x, y)
@@ -53,7 +60,7 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / a.steps
-    print(f"pdl={os.environ.get('NINT_PDL', '0')} bank={int(a.bank)} graph={int(a.graph)} B={B} T={T} k{a.ksize}: "
+    print(f"pdl={os.environ.get('NINT_PDL', '0')} bank={int(a.bank)} graph={int(a.graph)} shipped={int(a.shipped)} B={B} T={T} k{a.ksize}: "
           f"{ms:.3f} ms/step, {B / ms * 1e3:.0f} samples/s over {a.steps} steps, loss {float(loss):.4f}", flush=True)
 
 
