@@ -244,3 +244,28 @@ def test_val_loop_keeps_the_reference_signature():
     from nasa_niswan_b200.model import _deterministic_default
     assert _deterministic_default()
     torch.backends.cudnn.deterministic = prev
+
+
+def test_frame_bank_layout_rule_matches_the_library():
+    """preprocess.input_layout (what FrameBank builds) and nint_plan_input_layout (what the TMA descriptors expect) are
+    the same rule: channels padded to 32 lanes, first padding lane = the ones lane, none when C is a multiple of 32"""
+    from nasa_niswan_b200.preprocess import input_layout
+    for C in (1, 5, 8, 21, 31, 32, 33, 40, 64):
+        rc, h, lib = _create(_cfg(in_channels=C, training=0))
+        assert rc == 0, lib.nint_last_error()
+        c_pad, ones, eb = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        assert lib.nint_plan_input_layout(h, ctypes.byref(c_pad), ctypes.byref(ones), ctypes.byref(eb)) == 0
+        lib.nint_plan_destroy(h)
+        assert (c_pad.value, ones.value) == input_layout(C), C
+    rc, h, lib = _create(_cfg(dtype=1, training=0))
+    lib.nint_plan_input_layout(h, None, None, ctypes.byref(eb))
+    lib.nint_plan_destroy(h)
+    assert eb.value == 4                                            # tf32 plans keep fp32 storage
+
+
+def test_host_side_helpers_degrade_without_a_gpu():
+    from nasa_niswan_b200.parallel import bind_to_gpu_numa_node, shard_batch
+    if not torch.cuda.is_available():
+        assert bind_to_gpu_numa_node("cuda:0") is None              # topology unreadable: nothing is changed
+    assert [shard_batch(256, r, 8) for r in (0, 7)] == [(0, 32), (224, 256)]     # BASELINE cfg 3 at 8 ranks
+    assert [shard_batch(256, r, 2)[1] - shard_batch(256, r, 2)[0] for r in (0, 1)] == [128, 128]
