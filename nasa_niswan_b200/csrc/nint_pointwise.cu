@@ -339,7 +339,8 @@ cudaError_t launch_pack_weights_bwd(int dtype, const float* w, void* wdx, void* 
 // 1x1 head: pred[b][pix] = bias + sum_c h[b][pix][c] * w[c]    (model.py:274)
 // A pixel's channel vector is CPP = hc_pad*sizeof(E)/16 chunks of 16 bytes; LP = min(CPP, 32) lanes share a pixel,
 // so one warp-wide 16-byte load covers 32/LP whole pixels = 512 contiguous bytes (the one-thread-per-pixel version
-// touched 32 different lines per request and sat at ~40 % of HBM).  Partial dot products meet through shuffles.
+// touched 32 different lines per request).  One 16-byte load per lane and iteration, many warps: a variant with four
+// pixel groups in flight per warp measured SLOWER (49 vs 26 us under ncu: 95 registers, a third of the warps).  Partial dot products meet through shuffles.
 // ------------------------------------------------------------------------------------------
 template <typename E>
 __global__ void __launch_bounds__(256) head_fwd_kernel(const E* __restrict__ h, const float* __restrict__ w,
@@ -350,7 +351,6 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const E* __restrict__ h, 
   for (int i = threadIdx.x; i < hc_pad; i += blockDim.x) s_w[i] = i < hc ? w[i] : 0.f;
   __syncthreads();
   constexpr int V = 16 / sizeof(E);             // channels per 16-byte chunk
-  constexpr int KCH = 2;                        // chunk slots per lane: cpp / lp <= 2 (hc_pad <= 256)
   const int cpp = hc_pad / V;                   // chunks per pixel
   const int lane = threadIdx.x & 31;
   const int sub = lane & (lp - 1);              // this lane's chunk slot inside its pixel
@@ -358,35 +358,22 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const E* __restrict__ h, 
   const long long warp0 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
   const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
   const float b0 = bias[0];
-  constexpr int U = 4;                          // pixel groups in flight per warp: one 16-byte load per lane each
-  for (long long p0 = warp0 * ppw * U; p0 < total; p0 += nwarps * ppw * U) {
-    float f[U][KCH][V];
+  for (long long p0 = warp0 * ppw; p0 < total; p0 += nwarps * ppw) {
+    const long long gp = p0 + lane / lp;
+    float acc = 0.f;
+    if (gp < total) {
+      const E* hp = h + gp * hc_pad;
+      for (int ck = sub; ck < cpp; ck += lp) {
+        float f[V];
+        load_elems<E, V>(hp + ck * V, f);
 #pragma unroll
-    for (int u = 0; u < U; ++u) {               // all loads first (ncu: with one load in flight per lane the kernel sat at 0.31 of HBM)
-      const long long gp = p0 + u * ppw + lane / lp;
-#pragma unroll
-      for (int k = 0; k < KCH; ++k) {
-        const int ck = sub + k * lp;
-        if (gp < total && ck < cpp) load_elems<E, V>(h + gp * hc_pad + ck * V, f[u][k]);
+        for (int j = 0; j < V; ++j) acc = fmaf(f[j], s_w[ck * V + j], acc);
       }
     }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const long long gp = p0 + u * ppw + lane / lp;
-      float acc = 0.f;
-#pragma unroll
-      for (int k = 0; k < KCH; ++k) {
-        const int ck = sub + k * lp;
-        if (gp < total && ck < cpp) {
-#pragma unroll
-          for (int j = 0; j < V; ++j) acc = fmaf(f[u][k][j], s_w[ck * V + j], acc);
-        }
-      }
-      for (int o = lp >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      if (sub == 0 && gp < total) {
-        const long long b = gp / npix;
-        out[b * out_bstride + (gp - b * npix)] = acc + b0;
-      }
+    for (int o = lp >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (sub == 0 && gp < total) {
+      const long long b = gp / npix;
+      out[b * out_bstride + (gp - b * npix)] = acc + b0;
     }
   }
 }
@@ -402,11 +389,9 @@ cudaError_t launch_head_fwd(int dtype, const void* h, const float* w, const floa
                             int B, int hc, int hc_pad, long long out_bstride, cudaStream_t s) {
   const long long total = static_cast<long long>(B) * npix;
   if (total <= 0) return cudaSuccess;
-  if (hc_pad > 256) return cudaErrorInvalidValue;
   const int lp = head_lanes_per_pixel(dtype, hc_pad);
-  long long blocks = (total * lp / 4 + 255) / 256;
+  long long blocks = (total * lp + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  if (blocks < 1) blocks = 1;
   if (dtype == NINT_BF16)
     head_fwd_kernel<__nv_bfloat16><<<blocks, 256, hc_pad * 4, s>>>(reinterpret_cast<const __nv_bfloat16*>(h), w, b, out,
                                                                   npix, total, hc, hc_pad, out_bstride, lp);
@@ -440,34 +425,23 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const E* __restrict__ h, 
 #pragma unroll
     for (int j = 0; j < V; ++j) acc[k][j] = 0.f;
   float accb = 0.f;
-  constexpr int U = 4;                          // pixel groups in flight per warp
-  const long long wstride = static_cast<long long>(gridDim.x) * (blockDim.x >> 5) * ppw * U;
-  for (long long p0 = (static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + warp) * ppw * U; p0 < npix; p0 += wstride) {
-    float f[U][KMAX][V], d[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {               // all loads first
-      const long long px = p0 + u * ppw + lane / lp;
-      d[u] = px < npix ? __ldg(dp + px) : 0.f;
+  const long long wstride = static_cast<long long>(gridDim.x) * (blockDim.x >> 5) * ppw;
+  for (long long p0 = (static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + warp) * ppw; p0 < npix; p0 += wstride) {
+    const long long px = p0 + lane / lp;
+    if (px < npix) {
+      const float d = __ldg(dp + px);
+      const E* row = hb + px * hc_pad;
 #pragma unroll
       for (int k = 0; k < KMAX; ++k) {
         const int ck = sub + k * lp;
-        if (px < npix && ck < cpp) load_elems<E, V>(hb + px * hc_pad + ck * V, f[u][k]);
-      }
-    }
+        if (ck < cpp) {
+          float f[V];
+          load_elems<E, V>(row + ck * V, f);
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const long long px = p0 + u * ppw + lane / lp;
-      if (px < npix) {
-#pragma unroll
-        for (int k = 0; k < KMAX; ++k) {
-          const int ck = sub + k * lp;
-          if (ck < cpp) {
-#pragma unroll
-            for (int j = 0; j < V; ++j) acc[k][j] = fmaf(d[u], f[u][k][j], acc[k][j]);
-          }
+          for (int j = 0; j < V; ++j) acc[k][j] = fmaf(d, f[j], acc[k][j]);
         }
-        if (sub == 0) accb += d[u];
       }
+      if (sub == 0) accb += d;
     }
   }
   // lanes with the same `sub` hold partial sums of the same channels: fold them (offsets lp, 2*lp, ...)
