@@ -105,6 +105,7 @@ struct Layer {
   std::vector<WgBlock> wg_blocks;
   CUtensorMap tme_C, tme_H, tme_G, tme_dC;  // epilogue I/O boxes (16 | 64 channels x 8 x 16 pixels; nint_epilogue.cuh)
   bool weights_set = false;
+  bool bias_folded = false;   // the forward bias rides in the GEMM through the input's constant-1 lane
   // launch parameters that do not change from step to step (shared-memory plan, tensor maps, descriptors): built on
   // first use, then only the slot indices are patched per launch.  fwd[have_state][bank], bwd[has dgates_{t+1} segment]
   struct CachedConv { bool valid = false; ConvGemmParams g; };
@@ -411,7 +412,6 @@ int cell_step(nint_plan* p, int l, int t, int epi, float* raw_out, cudaStream_t 
       ++s;
     }
     g.nseg = s;
-    g.bias_q = y.bias_q;
     // epilogue I/O (TMA boxes): c_{t-1} -> c_t (in place at inference), h_t, activated gates (training)
     g.tm_c = y.tme_C; g.tm_h = y.tme_H; g.tm_g = y.tme_G; g.tm_dc = y.tme_dC;
     g.slot_g = (tr && epi == EPI_FWD) ? 0 : -1;   // only its sign enters the shared-memory plan
@@ -431,6 +431,7 @@ int cell_step(nint_plan* p, int l, int t, int epi, float* raw_out, cudaStream_t 
   g.slot_c_out = tr ? t + 1 : 0;
   g.slot_h_out = out_slot_h;
   g.slot_g = (tr && epi == EPI_FWD) ? t : -1;
+  g.bias_q = (y.bias_folded && epi == EPI_FWD) ? nullptr : y.bias_q;   // folded: the GEMM adds it (set_weights decides)
   g.raw_out = raw_out;
   set_batch_range(p, g, b0, nb);
   LAUNCH(p, (epi == EPI_FWD ? K_FWD : K_OTHER), st, launch_conv_halo(epi, p->dtype, g, p->num_sms, st));
@@ -901,7 +902,10 @@ int nint_plan_set_weights(nint_plan* p, int l, const float* weight, const float*
   if (!weight) return fail("null weight");
   Layer& y = p->layer[l];
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  LAUNCH(p, K_OTHER, st, launch_pack_weights_fwd(p->dtype, weight, bias, y.wx, y.wh, y.bias_q, y.cin, y.hc_real, y.hc, y.hcb, y.k, y.cx_pad, y.hc_pad, st));
+  // layer 0 with a constant-1 input lane: the bias becomes that lane's centre-tap weight and the epilogue adds nothing
+  y.bias_folded = l == 0 && p->ones_lane >= 0 && bias != nullptr && !(p->debug_flags & 512);
+  LAUNCH(p, K_OTHER, st, launch_pack_weights_fwd(p->dtype, weight, bias, y.wx, y.wh, y.bias_q, y.cin, y.hc_real, y.hc, y.hcb, y.k, y.cx_pad, y.hc_pad,
+                                                 y.bias_folded ? p->ones_lane : -1, st));
   if (p->cfg.training) LAUNCH(p, K_OTHER, st, launch_pack_weights_bwd(p->dtype, weight, y.wdx, y.wdh, y.cin, y.cin_rows, y.hc_real, y.hc, y.k, st));
   y.weights_set = true;
   return 0;

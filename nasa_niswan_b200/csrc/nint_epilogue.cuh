@@ -323,13 +323,15 @@ __device__ __forceinline__ void fwd_math(const ConvGemmParams& p, int warp, int 
         const uint32_t bq = smem_u32(s_bias + w.nb * p.n_tile + grp * 64 + half * 8);
         tmem_ld_wait();
         if (!skip) {
+          if (p.bias_q) {   // null: the bias rides in the GEMM (weight row of the input's constant-1 lane, centre tap)
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            float bias[8];
-            lds128(bq + g * 64, bias);
-            lds128(bq + g * 64 + 16, bias + 4);
+            for (int g = 0; g < 4; ++g) {
+              float bias[8];
+              lds128(bq + g * 64, bias);
+              lds128(bq + g * 64 + 16, bias + 4);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) a[g][j] += bias[j];
+              for (int j = 0; j < 8; ++j) a[g][j] += bias[j];
+            }
           }
 #pragma unroll
           for (int j = 0; j < 8; ++j) {

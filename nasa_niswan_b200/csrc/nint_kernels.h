@@ -66,7 +66,7 @@ struct alignas(64) ConvGemmParams {
   int hc, hc_pad;  // hidden channels of this layer / padded channel count of its h tensor
   int hcb;         // hidden channels per n-block (n_tile / 4)
   // ---- EPI_FWD: LSTM cell update (model.py:221-229)
-  const float* bias_q;  // [4*hc], q-order
+  const float* bias_q;  // [4*hc], q-order; null = the bias is folded into the GEMM (layer 0 with the constant-1 input lane)
   // ---- EPI_BWD: gate backward; accumulator = dh (absent when nseg == 0); dgates overwrite
   // the saved gates in place
   const float* head_dpred;  // optional [B,H,W] (+ stride): dh += head_dpred * head_w[c]
@@ -156,7 +156,7 @@ cudaError_t launch_nhwc_to_nchw_f32(const float* src, float* dst, int B, int C, 
 // padded to hc >= hc_real (padding channels: zero weights, zero bias -> their h and c stay exactly zero)
 cudaError_t launch_pack_weights_fwd(int dtype, const float* w, const float* bias, void* wpack_x, void* wpack_h,
                                     float* bias_q, int cin, int hc_real, int hc, int hcb, int k, int cx_pad, int hc_pad,
-                                    cudaStream_t s);
+                                    int bias_lane, cudaStream_t s);
 cudaError_t launch_pack_weights_bwd(int dtype, const float* w, void* wpack_dx, void* wpack_dh, int cin, int cin_rows,
                                     int hc_real, int hc, int k, cudaStream_t s);
 // 1x1 head (model.py:251,274)

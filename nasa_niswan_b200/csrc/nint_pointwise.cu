@@ -252,7 +252,7 @@ __device__ __forceinline__ int q_chan(int q) { return (q >> 6) * 16 + (q & 15); 
 template <typename E>
 __global__ void pack_w_fwd_kernel(const float* __restrict__ w, const float* __restrict__ bias, E* __restrict__ wx,
                                   E* __restrict__ wh, float* __restrict__ bias_q, int cin, int hc_real, int hc, int hcb,
-                                  int k, int cx_pad, int hc_pad) {
+                                  int k, int cx_pad, int hc_pad, int bias_lane) {
   constexpr int CE = ElemTraits<E>::kPerChunk;
   const int n_blocks = hc / hcb, n_tile = 4 * hcb, taps = k * k;
   const int ctot = cin + hc_real;
@@ -276,6 +276,9 @@ __global__ void pack_w_fwd_kernel(const float* __restrict__ w, const float* __re
     float v = 0.f;
     if (cl < climit && oc < hc_real)
       v = w[(static_cast<long long>(q_gate(q) * hc_real + oc) * ctot + (is_h ? cin + cl : cl)) * taps + tap];
+    // bias folded into the GEMM: the input carries 1.0 in padding lane `bias_lane`, so the centre tap's weight for that
+    // lane IS the bias (the epilogue then adds nothing); off the centre the lane keeps a zero weight
+    if (!is_h && cl == bias_lane && tap == taps / 2 && oc < hc_real && bias) v = bias[q_gate(q) * hc_real + oc];
     (is_h ? wh : wx)[is_h ? idx - nx : idx] = to_elem<E>(v);
   }
   for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < 4 * hc; q += gridDim.x * blockDim.x)
@@ -314,14 +317,15 @@ __global__ void pack_w_bwd_kernel(const float* __restrict__ w, E* __restrict__ w
 }
 
 cudaError_t launch_pack_weights_fwd(int dtype, const float* w, const float* bias, void* wx, void* wh, float* bias_q,
-                                    int cin, int hc_real, int hc, int hcb, int k, int cx_pad, int hc_pad, cudaStream_t s) {
+                                    int cin, int hc_real, int hc, int hcb, int k, int cx_pad, int hc_pad, int bias_lane,
+                                    cudaStream_t s) {
   if (dtype == NINT_BF16)
     pack_w_fwd_kernel<__nv_bfloat16><<<296, 256, 0, s>>>(w, bias, reinterpret_cast<__nv_bfloat16*>(wx),
                                                          reinterpret_cast<__nv_bfloat16*>(wh), bias_q, cin, hc_real, hc, hcb,
-                                                         k, cx_pad, hc_pad);
+                                                         k, cx_pad, hc_pad, bias_lane);
   else
     pack_w_fwd_kernel<float><<<296, 256, 0, s>>>(w, bias, reinterpret_cast<float*>(wx), reinterpret_cast<float*>(wh),
-                                                 bias_q, cin, hc_real, hc, hcb, k, cx_pad, hc_pad);
+                                                 bias_q, cin, hc_real, hc, hcb, k, cx_pad, hc_pad, bias_lane);
   return cudaGetLastError();
 }
 cudaError_t launch_pack_weights_bwd(int dtype, const float* w, void* wdx, void* wdh, int cin, int cin_rows, int hc_real,
