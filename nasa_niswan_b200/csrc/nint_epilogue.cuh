@@ -335,10 +335,11 @@ __device__ __forceinline__ void fwd_math(const ConvGemmParams& p, int warp, int 
           }
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float gi_ = act_sigmoid<FAST>(a[0][j]);
-            const float gf = act_sigmoid<FAST>(a[1][j]);
+            // (the i, f, o pre-activations come out of the GEMM already halved: nint_pointwise.cu pack_w_fwd_kernel)
+            const float gi_ = act_sigmoid_halved<FAST>(a[0][j]);
+            const float gf = act_sigmoid_halved<FAST>(a[1][j]);
             const float gg = act_tanh<FAST>(a[2][j]);
-            const float go = act_sigmoid<FAST>(a[3][j]);
+            const float go = act_sigmoid_halved<FAST>(a[3][j]);
             const float cv = fmaf(cn[j], gf, gi_ * gg);
             cn[j] = cv;
             float hv = go * act_tanh<FAST>(cv);
@@ -573,10 +574,10 @@ __device__ __forceinline__ void epi_math(const ConvGemmParams& p, int warp, int 
             }
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const float gi_ = act_sigmoid<FAST>(a[0][j]);
-              const float gf = act_sigmoid<FAST>(a[1][j]);
+              const float gi_ = act_sigmoid_halved<FAST>(a[0][j]);
+              const float gf = act_sigmoid_halved<FAST>(a[1][j]);
               const float gg = act_tanh<FAST>(a[2][j]);
-              const float go = act_sigmoid<FAST>(a[3][j]);
+              const float go = act_sigmoid_halved<FAST>(a[3][j]);
               const float cv = fmaf(cn[j], gf, gi_ * gg);
               cn[j] = cv;
               float hv = go * act_tanh<FAST>(cv);

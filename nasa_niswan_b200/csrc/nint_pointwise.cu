@@ -279,10 +279,12 @@ __global__ void pack_w_fwd_kernel(const float* __restrict__ w, const float* __re
     // bias folded into the GEMM: the input carries 1.0 in padding lane `bias_lane`, so the centre tap's weight for that
     // lane IS the bias (the epilogue then adds nothing); off the centre the lane keeps a zero weight
     if (!is_h && cl == bias_lane && tap == taps / 2 && oc < hc_real && bias) v = bias[q_gate(q) * hc_real + oc];
+    // sigmoid gates (i, f, o) are fed HALVED pre-activations (act_sigmoid_halved): exact, 0.5 is a power of two
+    if (q_gate(q) != 2) v *= 0.5f;
     (is_h ? wh : wx)[is_h ? idx - nx : idx] = to_elem<E>(v);
   }
   for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < 4 * hc; q += gridDim.x * blockDim.x)
-    bias_q[q] = (bias && q_chan(q) < hc_real) ? bias[q_gate(q) * hc_real + q_chan(q)] : 0.f;
+    bias_q[q] = (bias && q_chan(q) < hc_real) ? bias[q_gate(q) * hc_real + q_chan(q)] * (q_gate(q) != 2 ? 0.5f : 1.f) : 0.f;
 }
 
 // dgrad operands: K = q (4*hc), N = input channel, taps flipped (transposed convolution):

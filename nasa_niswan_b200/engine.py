@@ -298,4 +298,9 @@ class Plan:
         perm = torch.tensor([self.lib.nint_gate_column(q, hc) for q in range(4 * hc)], device=self.device)
         nat = torch.empty_like(out)
         nat[..., perm] = out
-        return nat.permute(0, 3, 1, 2).contiguous()
+        nat = nat.permute(0, 3, 1, 2).contiguous()
+        # the packed forward weights of the sigmoid gates (i, f, o) carry a factor 0.5 (the epilogue's sigmoid expects
+        # halved pre-activations: exact, a power of two); undo it for the comparison with a plain convolution
+        for gate in (0, 1, 3):
+            nat[:, gate * hc:(gate + 1) * hc] *= 2.0
+        return nat
