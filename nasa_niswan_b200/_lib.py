@@ -4,7 +4,7 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libnint.so")
+LIB_PATH = os.environ.get("NINT_LIB") or os.path.join(HERE, "libnint.so")   # NINT_LIB: A/B runs against another build
 MAX_LAYERS = 8
 DTYPE_BF16, DTYPE_TF32 = 0, 1
 DTYPE_BYTES = {DTYPE_BF16: 2, DTYPE_TF32: 4}

@@ -650,10 +650,10 @@ __device__ __forceinline__ void epi_math(const ConvGemmParams& p, int warp, int 
               const float d_f = dcv * cp[j];
               dc[j] = dcv * gf[j];
               const float i_ = gi_[j], f_ = gf[j], g_ = gg[j], o_ = go[j];
-              gi_[j] = d_i * i_ * (1.f - i_);
-              gf[j] = d_f * f_ * (1.f - f_);
-              gg[j] = d_g * (1.f - g_ * g_);
-              go[j] = d_o * o_ * (1.f - o_);
+              gi_[j] = d_i * fmaf(-i_, i_, i_);      // sigma' = s (1 - s) = s - s^2: one FFMA
+              gf[j] = d_f * fmaf(-f_, f_, f_);
+              gg[j] = d_g * fmaf(-g_, g_, 1.f);      // tanh' = 1 - g^2
+              go[j] = d_o * fmaf(-o_, o_, o_);
             }
             if constexpr (DT == NINT_TF32) {
               // dgates are MMA operands of dgrad and wgrad: round to nearest tf32 (the MMA truncates).  The residuals
