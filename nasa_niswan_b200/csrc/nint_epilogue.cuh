@@ -413,25 +413,16 @@ __device__ __forceinline__ void epi_loader(const ConvGemmParams& p, uint8_t* sE,
         if (mine && leader) {
           uint8_t* st = sE + s * p.e_stage_bytes;
           uint64_t* bar = &e_full[s];
-          if constexpr (EPI == EPI_FWD) {
-            if (p.slot_c_in >= 0) {
-              mbar_arrive_expect_tx(bar, kEpiBoxBytes16);
-              tma_load_5d(st + p.e_off_c, &p.tm_c, bar, w.nb * p.hcb + grp * 16, c.x0, c.y0, c.b, p.slot_c_in);
-            } else {
-              mbar_arrive(bar);   // zero state: nothing to read, the stage is only an output buffer
-            }
-          } else {
-            const uint32_t bytes = GE::kGateBytes + kEpiBoxBytes16 * ((p.slot_c_prev >= 0) + (p.has_dc_in != 0));
-            mbar_arrive_expect_tx(bar, bytes);
-            const int q0 = group_q0(grp * 16);
+          const uint32_t bytes = GE::kGateBytes + kEpiBoxBytes16 * ((p.slot_c_prev >= 0) + (p.has_dc_in != 0));
+          mbar_arrive_expect_tx(bar, bytes);
+          const int q0 = group_q0(grp * 16);
 #pragma unroll
-            for (int bx = 0; bx < GE::kGateBoxes; ++bx)
-              tma_load_5d(st + bx * GE::kGateBoxBytes, &p.tm_g, bar, q0 + bx * GE::kGateBoxCols, c.x0, c.y0, c.b, p.slot_g);
-            // c_t is not read back: it is c_{t-1} f + i g of the values loaded here (model.py:228)
-            if (p.slot_c_prev >= 0)
-              tma_load_5d(st + p.e_off_c2, &p.tm_c, bar, grp * 16, c.x0, c.y0, c.b, p.slot_c_prev);
-            if (p.has_dc_in) tma_load_5d(st + p.e_off_dc, &p.tm_dc, bar, grp * 16, c.x0, c.y0, c.b, 0);
-          }
+          for (int bx = 0; bx < GE::kGateBoxes; ++bx)
+            tma_load_5d(st + bx * GE::kGateBoxBytes, &p.tm_g, bar, q0 + bx * GE::kGateBoxCols, c.x0, c.y0, c.b, p.slot_g);
+          // c_t is not read back: it is c_{t-1} f + i g of the values loaded here (model.py:228)
+          if (p.slot_c_prev >= 0)
+            tma_load_5d(st + p.e_off_c2, &p.tm_c, bar, grp * 16, c.x0, c.y0, c.b, p.slot_c_prev);
+          if (p.has_dc_in) tma_load_5d(st + p.e_off_dc, &p.tm_dc, bar, grp * 16, c.x0, c.y0, c.b, 0);
         }
         if (mine) tr.stamp();
         if (++s == p.e_stages) {
@@ -468,23 +459,11 @@ __device__ __forceinline__ void epi_storer(const ConvGemmParams& p, uint8_t* sE,
         if (mine && leader) {
           const uint8_t* st = sE + s * p.e_stage_bytes;
           if (!(p.debug_flags & 1)) {
-            if constexpr (EPI == EPI_FWD) {
-              const int ch = w.nb * p.hcb + grp * 16;
-              tma_store_5d(&p.tm_c, st + p.e_off_c, ch, c.x0, c.y0, c.b, p.slot_c_out);
-              tma_store_5d(&p.tm_h, st + p.e_off_h, ch, c.x0, c.y0, c.b, p.slot_h_out);
-              if (p.slot_g >= 0) {
-                const int q0 = group_q0(ch);
+            const int q0 = group_q0(grp * 16);
 #pragma unroll
-                for (int bx = 0; bx < GE::kGateBoxes; ++bx)
-                  tma_store_5d(&p.tm_g, st + bx * GE::kGateBoxBytes, q0 + bx * GE::kGateBoxCols, c.x0, c.y0, c.b, p.slot_g);
-              }
-            } else {
-              const int q0 = group_q0(grp * 16);
-#pragma unroll
-              for (int bx = 0; bx < GE::kGateBoxes; ++bx)
-                tma_store_5d(&p.tm_g, st + bx * GE::kGateBoxBytes, q0 + bx * GE::kGateBoxCols, c.x0, c.y0, c.b, p.slot_g);
-              tma_store_5d(&p.tm_dc, st + p.e_off_dc, grp * 16, c.x0, c.y0, c.b, 0);
-            }
+            for (int bx = 0; bx < GE::kGateBoxes; ++bx)
+              tma_store_5d(&p.tm_g, st + bx * GE::kGateBoxBytes, q0 + bx * GE::kGateBoxCols, c.x0, c.y0, c.b, p.slot_g);
+            tma_store_5d(&p.tm_dc, st + p.e_off_dc, grp * 16, c.x0, c.y0, c.b, 0);
             tma_store_commit();
             tma_store_wait_read();   // the stage may be overwritten once TMA has read it
           }
@@ -550,148 +529,107 @@ __device__ __forceinline__ void epi_math(const ConvGemmParams& p, int warp, int 
           waited = true;
         }
         tr.stamp();
-        if constexpr (EPI == EPI_FWD) {
-          // model.py:221-229.  accumulator columns of this group: grp*64 + gate*16 + channel
-          float a[4][8], cn[8], hn[8];
-#pragma unroll
-          for (int g = 0; g < 4; ++g) tmem_ld8(taddr + grp * 64 + g * 16 + half * 8, a[g]);
-          if (p.slot_c_in >= 0 && !skip) {
-            lds8<float, 64>(st + p.e_off_c, row, half, cn);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) cn[j] = 0.f;
-          }
-          const uint32_t bq = smem_u32(s_bias + w.nb * p.n_tile + grp * 64 + half * 8);
-          tmem_ld_wait();
-          if (!skip) {
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              float bias[8];
-              lds128(bq + g * 64, bias);
-              lds128(bq + g * 64 + 16, bias + 4);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) a[g][j] += bias[j];
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float gi_ = act_sigmoid_halved<FAST>(a[0][j]);
-              const float gf = act_sigmoid_halved<FAST>(a[1][j]);
-              const float gg = act_tanh<FAST>(a[2][j]);
-              const float go = act_sigmoid_halved<FAST>(a[3][j]);
-              const float cv = fmaf(cn[j], gf, gi_ * gg);
-              cn[j] = cv;
-              float hv = go * act_tanh<FAST>(cv);
-              if constexpr (DT == NINT_TF32) hv = round_tf32(hv);  // h feeds the next step's tf32 MMA
-              hn[j] = hv;
-              a[0][j] = gi_; a[1][j] = gf; a[2][j] = gg; a[3][j] = go;
-            }
-            sts8<float, 64>(st + p.e_off_c, row, half, cn);
-            sts8<E, GE::kHRowB>(st + p.e_off_h, row, half, hn);
-            if (p.slot_g >= 0) {
-#pragma unroll
-              for (int g = 0; g < 4; ++g) sts_gate<E>(st, row, g, half, a[g]);
-            }
-          }
+        {
+        // gate backward; accumulator column c = dh_t[c] from the dgrad conv
+        float gi_[8], gf[8], gg[8], go[8], cp[8], dc[8], dh[8];
+        const int c0 = grp * 16 + half * 8;
+        if (p.nseg > 0) {
+          tmem_ld8(taddr + c0, dh);
         } else {
-          // gate backward; accumulator column c = dh_t[c] from the dgrad conv
-          float gi_[8], gf[8], gg[8], go[8], cp[8], dc[8], dh[8];
-          const int c0 = grp * 16 + half * 8;
-          if (p.nseg > 0) {
-            tmem_ld8(taddr + c0, dh);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dh[j] = 0.f;
+        }
+        if (!skip) {
+          lds_gate<E>(st, row, 0, half, gi_);
+          lds_gate<E>(st, row, 1, half, gf);
+          lds_gate<E>(st, row, 2, half, gg);
+          lds_gate<E>(st, row, 3, half, go);
+          if (p.slot_c_prev >= 0) {
+            lds8<float, 64>(st + p.e_off_c2, row, half, cp);
           } else {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) dh[j] = 0.f;
+            for (int j = 0; j < 8; ++j) cp[j] = 0.f;
           }
-          if (!skip) {
-            lds_gate<E>(st, row, 0, half, gi_);
-            lds_gate<E>(st, row, 1, half, gf);
-            lds_gate<E>(st, row, 2, half, gg);
-            lds_gate<E>(st, row, 3, half, go);
-            if (p.slot_c_prev >= 0) {
-              lds8<float, 64>(st + p.e_off_c2, row, half, cp);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) cp[j] = 0.f;
-            }
-            if (p.has_dc_in) {
-              lds8<float, 64>(st + p.e_off_dc, row, half, dc);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) dc[j] = 0.f;
-            }
-          }
-          float hw[8];
-          if (p.head_dpred) {
-            lds128(smem_u32(s_headw + c0), hw);
-            lds128(smem_u32(s_headw + c0 + 4), hw + 4);
+          if (p.has_dc_in) {
+            lds8<float, 64>(st + p.e_off_dc, row, half, dc);
           } else {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) hw[j] = 0.f;
+            for (int j = 0; j < 8; ++j) dc[j] = 0.f;
           }
-          if (p.nseg > 0) tmem_ld_wait();
-          if (p.dh_ext) {   // explicit upstream dh (cell API): one 32-byte read per thread, not a hot path
-            const int y = c.y0 + (row >> 3), x = c.x0 + (row & 7);
-            if (y < p.H && x < p.W) {
-              float e[8];
-              load_elems<float, 8>(p.dh_ext + ((static_cast<long long>(c.b) * p.H + y) * p.W + x) * p.hc + c0, e);
+        }
+        float hw[8];
+        if (p.head_dpred) {
+          lds128(smem_u32(s_headw + c0), hw);
+          lds128(smem_u32(s_headw + c0 + 4), hw + 4);
+        } else {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) dh[j] += e[j];
-            }
+          for (int j = 0; j < 8; ++j) hw[j] = 0.f;
+        }
+        if (p.nseg > 0) tmem_ld_wait();
+        if (p.dh_ext) {   // explicit upstream dh (cell API): one 32-byte read per thread, not a hot path
+          const int y = c.y0 + (row >> 3), x = c.x0 + (row & 7);
+          if (y < p.H && x < p.W) {
+            float e[8];
+            load_elems<float, 8>(p.dh_ext + ((static_cast<long long>(c.b) * p.H + y) * p.W + x) * p.hc + c0, e);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dh[j] += e[j];
           }
-          if (!skip) {
+        }
+        if (!skip) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float dhv = fmaf(dpred, hw[j], dh[j]);
+            const float tc = act_tanh<FAST>(fmaf(cp[j], gf[j], gi_[j] * gg[j]));   // tanh(c_t), the forward's expression
+            const float d_o = dhv * tc;
+            const float dcv = fmaf(dhv * go[j], 1.f - tc * tc, dc[j]);
+            const float d_i = dcv * gg[j];
+            const float d_g = dcv * gi_[j];
+            const float d_f = dcv * cp[j];
+            dc[j] = dcv * gf[j];
+            const float i_ = gi_[j], f_ = gf[j], g_ = gg[j], o_ = go[j];
+            gi_[j] = d_i * fmaf(-i_, i_, i_);      // sigma' = s (1 - s) = s - s^2: one FFMA
+            gf[j] = d_f * fmaf(-f_, f_, f_);
+            gg[j] = d_g * fmaf(-g_, g_, 1.f);      // tanh' = 1 - g^2
+            go[j] = d_o * fmaf(-o_, o_, o_);
+          }
+          if constexpr (DT == NINT_TF32) {
+            // dgates are MMA operands of dgrad and wgrad: round to nearest tf32 (the MMA truncates).  The residuals
+            // would be lost to the bias gradient (a plain, often nearly cancelling sum of dgates): reduce them over
+            // the warp's 32 pixels with a butterfly that halves the values per lane at every step (31 shuffles for
+            // 32 columns; lane l ends with column l = gate * 8 + channel) and keep them per channel group.
+            float res[32];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const float dhv = fmaf(dpred, hw[j], dh[j]);
-              const float tc = act_tanh<FAST>(fmaf(cp[j], gf[j], gi_[j] * gg[j]));   // tanh(c_t), the forward's expression
-              const float d_o = dhv * tc;
-              const float dcv = fmaf(dhv * go[j], 1.f - tc * tc, dc[j]);
-              const float d_i = dcv * gg[j];
-              const float d_g = dcv * gi_[j];
-              const float d_f = dcv * cp[j];
-              dc[j] = dcv * gf[j];
-              const float i_ = gi_[j], f_ = gf[j], g_ = gg[j], o_ = go[j];
-              gi_[j] = d_i * fmaf(-i_, i_, i_);      // sigma' = s (1 - s) = s - s^2: one FFMA
-              gf[j] = d_f * fmaf(-f_, f_, f_);
-              gg[j] = d_g * fmaf(-g_, g_, 1.f);      // tanh' = 1 - g^2
-              go[j] = d_o * fmaf(-o_, o_, o_);
+              float r;
+              r = round_tf32(gi_[j]); res[j] = gi_[j] - r; gi_[j] = r;
+              r = round_tf32(gf[j]); res[8 + j] = gf[j] - r; gf[j] = r;
+              r = round_tf32(gg[j]); res[16 + j] = gg[j] - r; gg[j] = r;
+              r = round_tf32(go[j]); res[24 + j] = go[j] - r; go[j] = r;
             }
-            if constexpr (DT == NINT_TF32) {
-              // dgates are MMA operands of dgrad and wgrad: round to nearest tf32 (the MMA truncates).  The residuals
-              // would be lost to the bias gradient (a plain, often nearly cancelling sum of dgates): reduce them over
-              // the warp's 32 pixels with a butterfly that halves the values per lane at every step (31 shuffles for
-              // 32 columns; lane l ends with column l = gate * 8 + channel) and keep them per channel group.
-              float res[32];
+            if (p.db_resid) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                float r;
-                r = round_tf32(gi_[j]); res[j] = gi_[j] - r; gi_[j] = r;
-                r = round_tf32(gf[j]); res[8 + j] = gf[j] - r; gf[j] = r;
-                r = round_tf32(gg[j]); res[16 + j] = gg[j] - r; gg[j] = r;
-                r = round_tf32(go[j]); res[24 + j] = go[j] - r; go[j] = r;
-              }
-              if (p.db_resid) {
+              for (int st_ = 16; st_ >= 1; st_ >>= 1) {
+                const bool upper = (lane & st_) != 0;
 #pragma unroll
-                for (int st_ = 16; st_ >= 1; st_ >>= 1) {
-                  const bool upper = (lane & st_) != 0;
-#pragma unroll
-                  for (int i = 0; i < st_; ++i) {
-                    const float send = upper ? res[i] : res[i + st_];
-                    const float keep = upper ? res[i + st_] : res[i];
-                    res[i] = keep + __shfl_xor_sync(0xffffffffu, send, st_);
-                  }
+                for (int i = 0; i < st_; ++i) {
+                  const float send = upper ? res[i] : res[i + st_];
+                  const float keep = upper ? res[i + st_] : res[i];
+                  res[i] = keep + __shfl_xor_sync(0xffffffffu, send, st_);
                 }
-                // lane l owns column (gate = l >> 3, channel = half * 8 + (l & 7)) of this channel group; the slots are
-                // private to (CTA, pixel quadrant): the read-modify-write needs no atomics and the sum order is fixed
-                float* slot = p.db_resid + (static_cast<long long>(blockIdx.x) * 4 + quad) * (4 * p.hc);
-                slot[grp * 64 + (lane >> 3) * 16 + half * 8 + (lane & 7)] += res[0];
               }
+              // lane l owns column (gate = l >> 3, channel = half * 8 + (l & 7)) of this channel group; the slots are
+              // private to (CTA, pixel quadrant): the read-modify-write needs no atomics and the sum order is fixed
+              float* slot = p.db_resid + (static_cast<long long>(blockIdx.x) * 4 + quad) * (4 * p.hc);
+              slot[grp * 64 + (lane >> 3) * 16 + half * 8 + (lane & 7)] += res[0];
             }
-            sts8<float, 64>(st + p.e_off_dc, row, half, dc);
-            sts_gate<E>(st, row, 0, half, gi_);
-            sts_gate<E>(st, row, 1, half, gf);
-            sts_gate<E>(st, row, 2, half, gg);
-            sts_gate<E>(st, row, 3, half, go);
           }
+          sts8<float, 64>(st + p.e_off_dc, row, half, dc);
+          sts_gate<E>(st, row, 0, half, gi_);
+          sts_gate<E>(st, row, 1, half, gf);
+          sts_gate<E>(st, row, 2, half, gg);
+          sts_gate<E>(st, row, 3, half, go);
+        }
+      
         }
         // results visible to the async proxy (TMA store), then hand the stage to the storer
         fence_proxy_async_smem();
