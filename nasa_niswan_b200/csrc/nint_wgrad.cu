@@ -542,7 +542,9 @@ wgrad_pair_kernel(const __grid_constant__ WgradParams p) {
       const uint32_t ncols = static_cast<uint32_t>(p.acc_cols);
       const int ksize = p.ksize;
       const bool issue_any = !(p.debug_flags & 2);
-      const bool keep_a = ntaps >= 2 && !(p.debug_flags & 1024);   // A-collector reuse across the taps of a K step
+      // A-collector reuse across the taps of a K step: measured SLOWER (wgrad 2.08 -> 2.30 ms on the same box: the
+      // MMAs of a K step serialise on the collector), so it is an experiment knob only (NINT_DEBUG_FLAGS bit 10)
+      const bool keep_a = ntaps >= 2 && (p.debug_flags & 1024);
       // MN-major descriptors.  A: 64-q atoms (128-byte rows, SWIZZLE_128B) one panel apart, 8-pixel groups 1 KiB apart.
       // B: pw-channel atoms (32 / 64 / 128-byte rows, matching swizzle) one panel apart, 8-pixel groups one halo row apart.
       const uint64_t adesc_base = make_smem_desc(0, kWgPairAPanel, BF ? 1024u : 512u, BF ? 2u : kLayoutSw128Base32);
