@@ -157,8 +157,9 @@ int nint_loss_mse_l1(const float* pred, const float* y, int batch, int height, i
 int nint_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr,
                    float beta1, float beta2, float eps, int step, float grad_scale, void* stream);
 /* nint_loss_mse_l1 with the targets in a bank y [n_frames, y1-y0, x1-x0]: sample b's target is frame
- * win_start[b] + y_offset (dataset.py:600-601: y[seq_len - 1:] pairs window i with frame i + T - 1). */
-int nint_loss_mse_l1_bank(const float* pred, const float* ybank, const int* win_start, int y_offset, int batch,
+ * win_start[b] + y_offset (dataset.py:600-601: y[seq_len - 1:] pairs window i with frame i + T - 1); an index outside
+ * [0, n_frames) reads as a zero target (the input side reads zeros through TMA) instead of faulting. */
+int nint_loss_mse_l1_bank(const float* pred, const float* ybank, long long n_frames, const int* win_start, int y_offset, int batch,
                           int height, int width, int crop_y0, int crop_y1, int crop_x0, int crop_x1, float* dpred,
                           float* loss, float* stats, void* stream);
 /* nint_adam_step with the step count and learning rate in DEVICE memory: state = 4 floats {step, lr, -, -}; the call

@@ -78,7 +78,7 @@ def load():
     L.nint_adam_step_dev.argtypes = [fp, fp, fp, fp, cll, fp, cf, cf, cf, cf, vp]
     L.nint_dp_allreduce_adam.argtypes = [ctypes.POINTER(vp), cll, cll, ci, ci, ctypes.c_uint, fp, fp, fp, cll, fp, cf, cf, cf, cf, vp]
     L.nint_fuse_inputs_bank.argtypes = [fp, fp, fp, fp, fp, ci, cll, ci, ci, ci, ci, ci, ci, ci, ci, ci, fp, vp]
-    L.nint_loss_mse_l1_bank.argtypes = [fp, fp, fp, ci, ci, ci, ci, ci, ci, ci, ci, fp, fp, fp, vp]
+    L.nint_loss_mse_l1_bank.argtypes = [fp, fp, cll, fp, ci, ci, ci, ci, ci, ci, ci, ci, fp, fp, fp, vp]
     L.nint_pick_tile.argtypes = [ci, ci, ctypes.POINTER(ci), ctypes.POINTER(ci)]
     for name in EXPORTS:
         getattr(L, name)  # raises AttributeError if the library does not export what nint.h declares

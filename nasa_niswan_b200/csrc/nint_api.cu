@@ -1103,17 +1103,17 @@ int nint_loss_mse_l1(const float* pred, const float* y, int batch, int height, i
                      int crop_x0, int crop_x1, float* dpred, float* loss, float* stats, void* stream) {
   if (check_loss_args(pred, y, loss, stats, batch, height, width, crop_y0, crop_y1, crop_x0, crop_x1)) return 1;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  LAUNCH(nullptr, K_OTHER, st, launch_loss_mse_l1(pred, y, dpred, stats, loss, batch, height, width, crop_y0, crop_y1, crop_x0, crop_x1, nullptr, 0, st));
+  LAUNCH(nullptr, K_OTHER, st, launch_loss_mse_l1(pred, y, dpred, stats, loss, batch, height, width, crop_y0, crop_y1, crop_x0, crop_x1, nullptr, 0, 0, st));
   return 0;
 }
 
-int nint_loss_mse_l1_bank(const float* pred, const float* ybank, const int* win_start, int y_offset, int batch,
+int nint_loss_mse_l1_bank(const float* pred, const float* ybank, long long n_frames, const int* win_start, int y_offset, int batch,
                           int height, int width, int crop_y0, int crop_y1, int crop_x0, int crop_x1, float* dpred,
                           float* loss, float* stats, void* stream) {
   if (check_loss_args(pred, ybank, loss, stats, batch, height, width, crop_y0, crop_y1, crop_x0, crop_x1)) return 1;
-  if (!win_start) return fail("nint_loss_mse_l1_bank: null win_start");
+  if (!win_start || n_frames < 1) return fail("nint_loss_mse_l1_bank: null win_start / empty target bank");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  LAUNCH(nullptr, K_OTHER, st, launch_loss_mse_l1(pred, ybank, dpred, stats, loss, batch, height, width, crop_y0, crop_y1, crop_x0, crop_x1, win_start, y_offset, st));
+  LAUNCH(nullptr, K_OTHER, st, launch_loss_mse_l1(pred, ybank, dpred, stats, loss, batch, height, width, crop_y0, crop_y1, crop_x0, crop_x1, win_start, y_offset, n_frames, st));
   return 0;
 }
 

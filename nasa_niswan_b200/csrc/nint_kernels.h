@@ -187,7 +187,8 @@ cudaError_t launch_fuse_inputs_bank(int dtype, const float* lev, const float* em
 // fused training loss MSE + L1 on the cropped prediction (value + gradient); stats = 5 floats of scratch;
 // y_index != null: the target of sample b is image y_index[b] + y_offset of y (frame bank)
 cudaError_t launch_loss_mse_l1(const float* pred, const float* y, float* dpred, float* stats, float* loss, int B, int H,
-                               int W, int y0, int y1, int x0, int x1, const int* y_index, int y_offset, cudaStream_t s);
+                               int W, int y0, int y1, int x0, int x1, const int* y_index, int y_offset, long long y_frames,
+                               cudaStream_t s);
 // Adam step over a flat fp32 parameter buffer
 cudaError_t launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                         float eps, int step, float grad_scale, cudaStream_t s);

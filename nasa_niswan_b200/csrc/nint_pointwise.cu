@@ -744,7 +744,8 @@ cudaError_t launch_fuse_inputs_bank(int dtype, const float* lev, const float* em
 __global__ void __launch_bounds__(256) loss_mse_l1_kernel(const float* __restrict__ pred, const float* __restrict__ y,
                                                           float* __restrict__ dpred, float* __restrict__ stats,
                                                           float* __restrict__ loss, int B, int H, int W, int y0, int y1,
-                                                          int x0, int x1, const int* __restrict__ y_index, int y_offset) {
+                                                          int x0, int x1, const int* __restrict__ y_index, int y_offset,
+                                                          long long y_frames) {
   const int hc = y1 - y0, wc = x1 - x0;
   const long long total = static_cast<long long>(B) * H * W;
   const float inv_n = 1.0f / (static_cast<float>(B) * hc * wc);
@@ -759,7 +760,8 @@ __global__ void __launch_bounds__(256) loss_mse_l1_kernel(const float* __restric
     if (yy >= y0 && yy < y1 && x >= x0 && x < x1) {
       // frame bank: the target of sample b is image y_index[b] + y_offset of y (dataset.py:600: y[i + seq_len - 1])
       const long long yb = y_index ? static_cast<long long>(__ldg(y_index + b)) + y_offset : b;
-      const float t = y[(yb * hc + (yy - y0)) * wc + (x - x0)];
+      // an out-of-range window index reads as a zero target instead of faulting (the input side reads zeros through TMA)
+      const float t = (y_index && (yb < 0 || yb >= y_frames)) ? 0.f : y[(yb * hc + (yy - y0)) * wc + (x - x0)];
       const float d = pred[i] - t;
       s2 = fmaf(d, d, s2);
       s1 += fabsf(d);
@@ -797,10 +799,11 @@ __global__ void __launch_bounds__(256) loss_mse_l1_kernel(const float* __restric
   }
 }
 cudaError_t launch_loss_mse_l1(const float* pred, const float* y, float* dpred, float* stats, float* loss, int B, int H,
-                               int W, int y0, int y1, int x0, int x1, const int* y_index, int y_offset, cudaStream_t s) {
+                               int W, int y0, int y1, int x0, int x1, const int* y_index, int y_offset, long long y_frames,
+                               cudaStream_t s) {
   cudaError_t e = cudaMemsetAsync(stats, 0, 5 * sizeof(float), s);
   if (e != cudaSuccess) return e;
-  loss_mse_l1_kernel<<<148, 256, 0, s>>>(pred, y, dpred, stats, loss, B, H, W, y0, y1, x0, x1, y_index, y_offset);
+  loss_mse_l1_kernel<<<148, 256, 0, s>>>(pred, y, dpred, stats, loss, B, H, W, y0, y1, x0, x1, y_index, y_offset, y_frames);
   return cudaGetLastError();
 }
 

@@ -379,7 +379,7 @@ class Trainer:
                 _lib.check(lib.nint_loss_mse_l1(vp(pred), vp(y.contiguous()), B, H, W, y0, y1, x0, x1, vp(dpred), vp(loss),
                                                 vp(self._stats), st), "nint_loss_mse_l1")   # train.py:102,105
             else:
-                _lib.check(lib.nint_loss_mse_l1_bank(vp(pred), vp(y), vp(y_index), int(y_offset), B, H, W, y0, y1, x0, x1,
+                _lib.check(lib.nint_loss_mse_l1_bank(vp(pred), vp(y), y.shape[0], vp(y_index), int(y_offset), B, H, W, y0, y1, x0, x1,
                                                      vp(dpred), vp(loss), vp(self._stats), st), "nint_loss_mse_l1_bank")
         world = self._world()
         if self.sym is not None:

@@ -106,6 +106,12 @@ def test_frame_bank_windows_match_explicit_windows(cfg):
         assert torch.equal(a, p.grad)
     with pytest.raises(IndexError):
         net.forward_windows(bank, torch.tensor([N - T + 1]), T)
+    # indices that only exist on the device are not checked on the host: frames outside the bank read as zeros through
+    # TMA (inputs) and as zero targets (loss) -- never a fault
+    with torch.no_grad():
+        wild = net.forward_windows(bank, torch.tensor([N + 5, -3, 0, 1, 2], dtype=torch.int32, device="cuda"), T)
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(wild).all()) and torch.equal(wild[2:], pred_b[[1, 1, 1]].detach()) is False
 
 
 @pytest.mark.parametrize("precision", ["bf16", "tf32"])
