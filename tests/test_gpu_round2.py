@@ -111,7 +111,8 @@ def test_frame_bank_windows_match_explicit_windows(cfg):
     with torch.no_grad():
         wild = net.forward_windows(bank, torch.tensor([N + 5, -3, 0, 1, 2], dtype=torch.int32, device="cuda"), T)
     torch.cuda.synchronize()
-    assert bool(torch.isfinite(wild).all()) and torch.equal(wild[2:], pred_b[[1, 1, 1]].detach()) is False
+    assert bool(torch.isfinite(wild).all())
+    assert torch.equal(wild[2], pred_b[1].detach())          # window start 0 again: per-sample arithmetic, bit for bit
 
 
 @pytest.mark.parametrize("precision", ["bf16", "tf32"])
