@@ -32,8 +32,11 @@ def random_case(rng):
     hidden = [rng.choice(HIDDEN) for l in range(L)]
     ks = [rng.choice([1, 3, 3, 5, 7]) for _ in range(L)]
     C = rng.choice([1, 3, 5, 16, 21, 32, 33, 40, 64])
+    seq = rng.random() < 0.25
     return dict(B=rng.randint(1, 3), T=rng.randint(1, 4), C=C, H=rng.randint(2, 40), W=rng.randint(2, 40),
-                hidden=hidden, ks=ks, precision=rng.choice(["bf16", "tf32"]), seq=rng.random() < 0.25)
+                hidden=hidden, ks=ks, precision=rng.choice(["bf16", "tf32"]), seq=seq,
+                # round 2: windows cut out of an HBM-resident frame bank instead of an explicit tensor; gradient w.r.t. x
+                bank=(not seq) and rng.random() < 0.3, dx=(not seq) and rng.random() < 0.3)
 
 
 def run_case(c, seed):
@@ -43,6 +46,11 @@ def run_case(c, seed):
     params = {k: v.detach().clone() for k, v in net.state_dict().items()}
     net = net.cuda()
     x = torch.randn(c["B"], c["T"], c["C"], c["H"], c["W"])
+    starts = None
+    if c.get("bank"):
+        record = torch.randn(c["T"] + 3, c["C"], c["H"], c["W"])
+        starts = torch.randint(0, 4, (c["B"],))
+        x = torch.stack([record[s:s + c["T"]] for s in starts.tolist()])
     leaf = {k: v.clone().requires_grad_(True) for k, v in params.items()}
     if c["seq"]:
         rp, rs = O.convlstm_forward(x, leaf, L, return_sequence=True)
@@ -52,14 +60,23 @@ def run_case(c, seed):
         ((seq * wts.cuda()).sum() / seq.numel() + pred.mean()).backward()
         err = max(O.max_abs_normalised(pred.detach().cpu(), rp.detach()), O.max_abs_normalised(seq.detach().cpu(), rs.detach()))
     else:
-        rp = O.convlstm_forward(x, leaf, L)
+        xr = x.clone().requires_grad_(bool(c.get("dx")))
+        rp = O.convlstm_forward(xr, leaf, L)
         y = torch.randn(c["B"], c["H"], c["W"])
         dpred = torch.autograd.grad(O.training_loss(rp, y), rp, retain_graph=True)[0]
         rp.backward(dpred)
-        pred = net(x.cuda())
+        if starts is not None:
+            from nasa_niswan_b200.preprocess import FrameBank
+            pred = net.forward_windows(FrameBank.from_frames(record.cuda(), c["precision"]), starts, c["T"])
+            xd = None
+        else:
+            xd = x.clone().cuda().requires_grad_(bool(c.get("dx")))
+            pred = net(xd)
         pred.backward(dpred.cuda())
         err = O.max_abs_normalised(pred.detach().cpu(), rp.detach())
     gerr = max(O.max_abs_normalised(p.grad.cpu(), leaf[k].grad) for k, p in net.named_parameters())
+    if not c["seq"] and c.get("dx") and xd is not None and xr.grad.abs().max() > 0:
+        gerr = max(gerr, O.max_abs_normalised(xd.grad.cpu(), xr.grad))
     return err, gerr
 
 
@@ -72,7 +89,7 @@ def main():
     for i in range(n):
         c = random_case(rng)
         tag = (f"B{c['B']} T{c['T']} C{c['C']} {c['H']}x{c['W']} h{c['hidden']} k{c['ks']} {c['precision']}"
-               f"{' seq' if c['seq'] else ''}")
+               f"{' seq' if c['seq'] else ''}{' bank' if c.get('bank') else ''}{' dx' if c.get('dx') else ''}")
         try:
             err, gerr = run_case(c, seed * 1000 + i)
             bar = BAR[c["precision"]]
