@@ -335,6 +335,7 @@ def main():
         sampler.start()
     plan.profile(True)
     n0 = lib.nint_launch_count(-1)
+    cls0 = [lib.nint_launch_count(c) for c in range(4)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(K_):
@@ -342,6 +343,8 @@ def main():
     e1.record()
     barrier()
     launches = lib.nint_launch_count(-1) - n0
+    cls_launches = dict(zip(("gate_conv_fwd", "dgrad_gate_bwd", "wgrad", "other"),
+                            [lib.nint_launch_count(c) - v for c, v in enumerate(cls0)]))
     prof = plan.profile_read()
     plan.profile(False)
     clocks = sampler.stop() if rank == 0 else None
@@ -450,11 +453,16 @@ def main():
             peak_sus, peak_burst, peak_src = peak_sus / 2, peak_burst / 2, peak_src + " / 2 (tf32 nominal half rate)"
         flops = conv_flops(B, T, k)
         kernels = {}
+        # n counts TIME STEPS: a time-fused conv launch (all steps of a layer but the first as one persistent launch,
+        # DESIGN.md 5.1) counts once per step it covers, so "launches_per_step" / "avg_launch_us" keep meaning "per
+        # (layer, time step)" = per launch of the one-launch-per-step schedule; "kernel_launches_per_step" is the
+        # number of kernels actually launched
         for name in ("gate_conv_fwd", "dgrad_gate_bwd", "wgrad"):
             ms, n = prof[name]
             if n:
                 tf = flops[name] * K_ / (ms * 1e-3) / 1e12
-                kernels[name] = {"launches_per_step": n / K_, "ms_per_step": round(ms / K_, 4),
+                kernels[name] = {"launches_per_step": n / K_, "kernel_launches_per_step": cls_launches[name] / K_,
+                                 "ms_per_step": round(ms / K_, 4),
                                  "avg_launch_us": round(ms / n * 1e3, 2), "tflops": round(tf, 1),
                                  "frac": round(tf / peak_sus, 4), "frac_burst": round(tf / peak_burst, 4)}
         ms_o, n_o = prof["other"]
@@ -501,7 +509,8 @@ def main():
                        "parallelism": f"dp{world}", "l2_policy": "inputs (418 MB/step at B=32) larger than the 126 MB L2",
                        "loss_at_end": round(float(loss), 5), "numa_node": numa,
                        "sub_batch": int(os.environ.get("NINT_SUB_BATCH", "0") or 0),
-                       "pdl": int(os.environ.get("NINT_PDL", "1") or 0)},
+                       "pdl": int(os.environ.get("NINT_PDL", "1") or 0),
+                       "time_fused_launches": int(os.environ.get("NINT_FUSE_STEPS", "2") or 0)},
             "e2e": e2e,
             "e2e_variants": variants,
             "sustained": sustained,

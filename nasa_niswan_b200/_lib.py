@@ -14,7 +14,7 @@ EXPORTS = ["nint_version", "nint_last_error", "nint_plan_create", "nint_plan_des
            "nint_plan_bind", "nint_plan_set_weights", "nint_plan_set_head", "nint_plan_reset_state",
            "nint_plan_set_state", "nint_plan_get_state", "nint_forward", "nint_forward_ex", "nint_forward_bank",
            "nint_plan_input_layout", "nint_pack_frames", "nint_backward", "nint_debug_raw_gates",
-           "nint_gate_column", "nint_debug_read_trace", "nint_backward_bptt", "nint_backward_wgrad",
+           "nint_gate_column", "nint_debug_read_trace", "nint_debug_fail_record", "nint_backward_bptt", "nint_backward_wgrad",
            "nint_backward_input", "nint_cell_forward", "nint_cell_backward", "nint_loss_mse_l1",
            "nint_loss_mse_l1_bank", "nint_adam_step", "nint_adam_step_dev", "nint_dp_allreduce_adam", "nint_fuse_inputs", "nint_fuse_inputs_bank",
            "nint_pick_tile", "nint_launch_count", "nint_plan_profile", "nint_plan_profile_read"]
@@ -71,6 +71,7 @@ def load():
     L.nint_plan_profile_read.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_longlong)]
     L.nint_gate_column.argtypes = [ci, ci]
     L.nint_debug_read_trace.argtypes = [ctypes.POINTER(ctypes.c_longlong), ci, ci]
+    L.nint_debug_fail_record.argtypes = [ctypes.POINTER(ctypes.c_ulonglong)]
     L.nint_loss_mse_l1.argtypes = [fp, fp, ci, ci, ci, ci, ci, ci, ci, fp, fp, fp, vp]
     cf, cll = ctypes.c_float, ctypes.c_longlong
     L.nint_fuse_inputs.argtypes = [fp, fp, fp, fp, fp, ci, cll, ci, ci, ci, ci, ci, ci, fp, vp]

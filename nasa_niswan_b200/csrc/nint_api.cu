@@ -63,6 +63,7 @@ struct Profile {
   bool on = false;
   std::vector<cudaEvent_t> pool;
   std::vector<int> cls;  // class of pair i (events 2i, 2i+1)
+  std::vector<int> weight;  // time steps the launch of pair i covers (1; n for a time-fused conv launch)
   size_t used = 0;       // pairs in flight
 };
 
@@ -135,6 +136,12 @@ struct nint_plan {
   float* raw = nullptr;      // NINT_FLAG_INPUT_GRAD: [B][H][W][max(cx_pad0, hc0)] fp32 dgrad dump
   float* dh_ext = nullptr;   // NINT_FLAG_INPUT_GRAD, cell plans: upstream dL/dh' as [B][H][W][hc] fp32
   float* head_part = nullptr;  // deterministic mode: per-block partial sums of the head gradient
+  unsigned* step_done = nullptr;   // [T][B] tile counters of a time-fused conv launch (ConvGemmParams::step_done)
+  // consecutive time steps of a layer as ONE persistent launch whose tiles wait on the previous step's tiles of the same
+  // image (ConvGemmParams::n_steps).  Bit 0: forward, bit 1: BPTT (NINT_FUSE_STEPS).  Measured on B200 at cfg 2: the
+  // backward launch -6 % per step; the forward kernel runs at its steady-state rate from start to end already (PDL hides
+  // its prologue) and the storer's wait for write completion costs it +8 %, so only the backward is fused by default.
+  int fuse_steps = 2;
   bool head_set = false;
   bool zero_init = true;
   bool fwd_done = false;
@@ -168,8 +175,9 @@ int launch(nint_plan* p, int cls, cudaStream_t st, const char* what, F&& f) {
       pr.pool.push_back(b);
     }
     e1 = pr.pool[2 * pr.used + 1];
-    if (pr.cls.size() <= pr.used) pr.cls.resize(pr.used + 1);
+    if (pr.cls.size() <= pr.used) pr.cls.resize(pr.used + 1), pr.weight.resize(pr.used + 1);
     pr.cls[pr.used] = cls;
+    pr.weight[pr.used] = 1;
     cudaEventRecord(pr.pool[2 * pr.used], st);
     ++pr.used;
   }
@@ -320,6 +328,7 @@ size_t carve(nint_plan* p, uint8_t* base) {
   p->head_b = reinterpret_cast<float*>(take(16));
   if (tr && p->deterministic)
     p->head_part = reinterpret_cast<float*>(take(static_cast<size_t>(head_bwd_blocks(p->B)) * (top.hc_real + 1) * 4));
+  p->step_done = reinterpret_cast<unsigned*>(take(static_cast<size_t>(p->T) * p->B * 4));
   if (tr && p->input_grad) {
     const Layer& y0 = p->layer[0];
     const size_t cols = y0.cin_rows > y0.hc ? y0.cin_rows : y0.hc;
@@ -344,6 +353,20 @@ void fill_common(const nint_plan* p, const Layer& y, ConvGemmParams& g) {
   g.B = p->B; g.b0 = 0; g.H = p->H; g.W = p->W;
   g.tile_w = p->tile_w; g.tile_h = p->tile_h; g.tiles_x = p->tiles_x; g.tiles_y = p->tiles_y;
   g.hc = y.hc; g.hc_pad = y.hc_pad; g.hcb = y.hcb;
+  g.n_steps = 1;
+  g.c_prev_none_step = -1;
+}
+
+// turn g (set up for its first step) into a time-fused launch of n_steps consecutive steps: zero the tile counters
+int arm_fused(nint_plan* p, ConvGemmParams& g, int n_steps, int storer_warps, cudaStream_t st) {
+  g.n_steps = n_steps;
+  g.step_done = p->step_done;
+  g.step_target = static_cast<unsigned>(p->tiles_x * p->tiles_y * g.n_blocks * storer_warps);
+  if (reinterpret_cast<uint8_t*>(p->step_done) < p->ws ||
+      reinterpret_cast<uint8_t*>(p->step_done + static_cast<size_t>(n_steps) * p->B) > p->ws + p->ws_bytes)
+    return fail("internal: step counters outside the workspace (%p, ws %p + %zu)", (void*)p->step_done, (void*)p->ws, p->ws_bytes);
+  CK(cudaMemsetAsync(p->step_done, 0, static_cast<size_t>(n_steps) * p->B * 4, st));
+  return 0;
 }
 
 // CTA-pair mode (cluster of 2, tcgen05 cta_group::2; halo variant only): every CTA holds half of the N rows
@@ -381,8 +404,9 @@ inline void set_batch_range(const nint_plan* p, ConvGemmParams& g, int b0, int n
   g.B = nb > 0 ? nb : p->B;
 }
 
-// one fused cell step of layer l at time t (model.py:216-231) for images [b0, b0 + nb)
-int cell_step(nint_plan* p, int l, int t, int epi, float* raw_out, cudaStream_t st, int b0 = 0, int nb = 0) {
+// one fused cell step of layer l at time t (model.py:216-231) for images [b0, b0 + nb); n_steps > 1: steps t .. t+n_steps-1
+// as ONE time-fused launch (all of them must have a recurrent state: t >= 1, or an explicit initial state)
+int cell_step(nint_plan* p, int l, int t, int epi, float* raw_out, cudaStream_t st, int b0 = 0, int nb = 0, int n_steps = 1) {
   Layer& y = p->layer[l];
   const bool tr = p->cfg.training != 0;
   const bool have_state = !(t == 0 && p->zero_init);
@@ -434,7 +458,16 @@ int cell_step(nint_plan* p, int l, int t, int epi, float* raw_out, cudaStream_t 
   g.bias_q = (y.bias_folded && epi == EPI_FWD) ? nullptr : y.bias_q;   // folded: the GEMM adds it (set_weights decides)
   g.raw_out = raw_out;
   set_batch_range(p, g, b0, nb);
+  g.n_steps = 1;
+  if (n_steps > 1) {
+    if (!have_state || epi != EPI_FWD || nb > 0) return fail("internal: time-fused forward launch without a recurrent state");
+    g.d_seg[0] = g.d_seg[1] = g.d_h_out = g.d_g = 1;
+    g.d_c_in = g.d_c_out = tr ? 1 : 0;
+    g.ring_bits = tr ? 0 : ((l > 0 ? 1 : 0) | 2 | 16);   // inference: the h history is a 2-slot ring
+    if (arm_fused(p, g, n_steps, 2, st)) return 1;
+  }
   LAUNCH(p, (epi == EPI_FWD ? K_FWD : K_OTHER), st, launch_conv_halo(epi, p->dtype, g, p->num_sms, st));
+  if (p->prof.on && p->prof.used > 0) p->prof.weight[p->prof.used - 1] = n_steps;
   return 0;
 }
 
@@ -672,7 +705,7 @@ int nint_plan_profile_read(nint_plan* p, double* ms, long long* count) {
     float t = 0.f;
     CK(cudaEventElapsedTime(&t, pr.pool[2 * i], pr.pool[2 * i + 1]));
     ms[pr.cls[i]] += t;
-    ++count[pr.cls[i]];
+    count[pr.cls[i]] += pr.weight[i];
   }
   pr.used = 0;
   return 0;
@@ -707,6 +740,7 @@ int nint_plan_create(const nint_config* cfg, nint_plan** out) {
     if (const char* e = getenv("NINT_DETERMINISTIC")) p->deterministic = p->deterministic || atoi(e) != 0;
     const char* pd = getenv("NINT_PDL");
     p->pdl = pd ? (atoi(pd) != 0) : 1;   // on by default: -0.4..0.6 % step time at cfg 2, -3 % at cfg 1, -1 % on the shipped model
+    if (const char* e = getenv("NINT_FUSE_STEPS")) p->fuse_steps = atoi(e);   // bit 0: forward, bit 1: backward
     const char* sb = getenv("NINT_SUB_BATCH");
     p->sub_batch = sb ? atoi(sb) : 0;
     if (p->sub_batch < 0 || p->sub_batch >= p->B) p->sub_batch = 0;
@@ -980,6 +1014,25 @@ static int forward_steps(nint_plan* p, float* pred, float* seq, cudaStream_t st)
   const Layer& top = p->layer[p->L - 1];
   const size_t top_img = static_cast<size_t>(HW) * top.hc_pad * p->esize;   // bytes of one image of the top layer's h
   const int SB = p->sub_batch > 0 ? p->sub_batch : p->B;
+  // time-fused schedule: layer by layer, all steps of a layer in ONE persistent launch (after the step that starts
+  // from the zero state, whose GEMM has no h segment).  Layer-major order needs the whole h history of the layer
+  // below, which a training plan keeps; an inference plan keeps two slots, so only a single layer fuses there
+  if ((p->fuse_steps & 1) && SB >= p->B && p->T > 1 && (tr || (p->L == 1 && !seq))) {
+    for (int l = 0; l < p->L; ++l) {          // model.py:267
+      int t = 0;
+      if (p->zero_init) {
+        if (cell_step(p, l, 0, EPI_FWD, nullptr, st)) return 1;
+        t = 1;
+      }
+      if (p->T - t == 1) {
+        if (cell_step(p, l, t, EPI_FWD, nullptr, st)) return 1;
+      } else if (cell_step(p, l, t, EPI_FWD, nullptr, st, 0, 0, p->T - t)) return 1;   // model.py:265
+    }
+    if (seq)
+      for (int t = 0; t < p->T; ++t)          // model.py:272 (commented variant)
+        LAUNCH(p, K_OTHER, st, launch_head_fwd(p->dtype, slot_ptr(p, top.Hs, t + 1, top.hc_pad), p->head_w, p->head_b,
+                           seq + t * HW, HW, p->B, top.hc_real, top.hc_pad, p->T * HW, st));
+  } else
   for (int b0 = 0; b0 < p->B; b0 += SB) {     // sub-batch-major: every slice runs all its steps while its state is in L2
     const int nb = b0 + SB <= p->B ? SB : p->B - b0;
     for (int t = 0; t < p->T; ++t) {          // model.py:265
@@ -1159,6 +1212,13 @@ int nint_debug_read_trace(long long* host, int n, int clear) {
   return 0;
 }
 
+int nint_debug_fail_record(unsigned long long* out5) {
+  if (!out5) return fail("nint_debug_fail_record: null argument");
+  cudaError_t e = fail_record(out5);
+  if (e != cudaSuccess) return fail("nint_debug_fail_record: %s", cudaGetErrorString(e));
+  return 0;
+}
+
 int nint_debug_raw_gates(nint_plan* p, const float* x, float* out, void* stream) {
   if (check_ready(p)) return 1;
   if (!x || !out) return fail("nint_debug_raw_gates: null argument");
@@ -1172,9 +1232,10 @@ static bool resid_on(const nint_plan* p) {
   return p->num_sms <= kResidCtas && static_cast<long long>(p->B) * p->T * p->H * p->W <= kResidMaxPixelSteps;
 }
 
-// one fused dgrad + gate-backward launch of layer l at step t for images [b0, b0 + nb) (nb = 0: all)
+// one fused dgrad + gate-backward launch of layer l at step t for images [b0, b0 + nb) (nb = 0: all); n_steps > 1: steps
+// t, t-1, .. t-n_steps+1 as ONE time-fused launch (t < T-1: all of them have a dgates_{t+1} segment and a running dc)
 static int bwd_step(nint_plan* p, int l, int t, const float* dpred, const float* dseq, const float* dh_ext, bool dc_given,
-                    cudaStream_t st, int b0, int nb) {
+                    cudaStream_t st, int b0, int nb, int n_steps = 1) {
   const long long HW = static_cast<long long>(p->H) * p->W;
   const int L = p->L, T = p->T;
   Layer& y = p->layer[l];
@@ -1235,7 +1296,19 @@ static int bwd_step(nint_plan* p, int l, int t, const float* dpred, const float*
   g.dh_ext = (l == L - 1 && t == T - 1) ? dh_ext : nullptr;
   g.db_resid = resid_on(p) ? y.db_resid : nullptr;
   set_batch_range(p, g, b0, nb);
+  g.n_steps = 1;
+  g.c_prev_none_step = -1;
+  if (n_steps > 1) {
+    if (!has_next || nb > 0 || t - n_steps + 1 < 0) return fail("internal: bad time-fused backward launch");
+    g.d_seg[0] = g.d_seg[1] = g.d_g = g.d_c_prev = -1;
+    g.ring_bits = 0;
+    g.slot_c_prev = t;                                   // the zero initial state is a per-step property here
+    g.c_prev_none_step = (p->zero_init && t - n_steps + 1 == 0) ? n_steps - 1 : -1;
+    g.head_dpred_sstride = -HW;                          // dseq + (t - s) * HW
+    if (arm_fused(p, g, n_steps, 2, st)) return 1;
+  }
   LAUNCH(p, K_BWD, st, launch_conv_halo(EPI_BWD, p->dtype, g, p->num_sms, st));
+  if (p->prof.on && p->prof.used > 0) p->prof.weight[p->prof.used - 1] = n_steps;
   return 0;
 }
 
@@ -1246,6 +1319,14 @@ static int bptt_loop(nint_plan* p, const float* dpred, const float* dseq, const 
   const int SB = p->sub_batch > 0 ? p->sub_batch : p->B;
   for (int l = 0; l < p->L; ++l)
     if (p->layer[l].db_resid) CK(cudaMemsetAsync(p->layer[l].db_resid, 0, static_cast<size_t>(kResidCtas) * 4 * 4 * p->layer[l].hc * 4, st));
+  if ((p->fuse_steps & 2) && SB >= p->B && p->T > 2) {
+    // time-fused schedule: top layer first, each layer's steps T-2 .. 0 as ONE persistent launch after its step T-1
+    // (which has no dgates_{t+1} segment); layer l reads the dgates of layer l+1 at the same t, all in place by then
+    for (int l = p->L - 1; l >= 0; --l) {
+      if (bwd_step(p, l, p->T - 1, dpred, dseq, dh_ext, dc_given, st, 0, 0)) return 1;
+      if (bwd_step(p, l, p->T - 2, dpred, dseq, dh_ext, dc_given, st, 0, 0, p->T - 1)) return 1;
+    }
+  } else
   for (int b0 = 0; b0 < p->B; b0 += SB) {
     const int nb = b0 + SB <= p->B ? SB : p->B - b0;
     for (int t = p->T - 1; t >= 0; --t)

@@ -57,6 +57,7 @@ __device__ __forceinline__ ItemCoord decode_tile(const ConvGemmParams& p, int ti
 // groups; the CTAs of a pair take adjacent groups of G tiles.
 struct TileWalk {
   int nb, first_tile, tile_stride, tiles_padded, num_tiles;
+  int tiles_step;   // padded tiles of ONE time step; tiles_padded = n_steps * tiles_step (time-fused launch: step-major walk)
 };
 __device__ __forceinline__ TileWalk make_walk(const ConvGemmParams& p, int S, int crank) {
   TileWalk w;
@@ -68,8 +69,124 @@ __device__ __forceinline__ TileWalk make_walk(const ConvGemmParams& p, int S, in
   w.nb = cid % p.n_blocks;
   w.first_tile = ((cid / p.n_blocks) * S + crank) * G;
   w.tile_stride = cpn * S * G;
-  w.tiles_padded = groups * S * G;
+  w.tiles_step = groups * S * G;
+  w.tiles_padded = w.tiles_step * p.n_steps;
   return w;
+}
+
+// ---- time-fused launch (ConvGemmParams::n_steps > 1): position of a tile group inside the step-major walk, the slot a
+// field has in that step, and the per-image hand-off between consecutive steps
+struct GroupPos {
+  int step, tile0;   // time step of the launch, first tile of the group inside that step
+};
+__device__ __forceinline__ GroupPos group_pos(const ConvGemmParams& p, const TileWalk& w, int base) {
+  GroupPos g;
+  g.step = 0;
+  g.tile0 = base;
+  if (p.n_steps > 1) {
+    g.step = base / w.tiles_step;
+    g.tile0 = base - g.step * w.tiles_step;
+  }
+  return g;
+}
+__device__ __forceinline__ int step_slot(const ConvGemmParams& p, int slot, int d, int ring_bit, int step) {
+  if (slot < 0 || p.n_steps == 1) return slot;
+  const int v = slot + d * step;
+  return (p.ring_bits >> ring_bit) & 1 ? (v & 1) : v;
+}
+// one lane: block until every tile of image b of the previous step has been stored (no-op in step 0 / single-step launches).
+// A wait that lasts ~2 s means a peer CTA is not resident or died: trap instead of hanging the GPU.  With debug flag 2048
+// the limit is ~0.1 s and the wait is then abandoned after leaving a record (block, warp, step, image, count) in the
+// trace buffer's last row (nint_debug_read_trace), so a dependency bug can be read back instead of killing the context.
+__device__ __forceinline__ void wait_prev_step(const ConvGemmParams& p, int step, int b) {
+  if (step == 0) return;
+  const unsigned* ctr = p.step_done + static_cast<long long>(step - 1) * p.B + (b - p.b0);
+  unsigned v;
+  long long t0 = 0;
+  unsigned spins = 0;
+  const bool diag = (p.debug_flags & 2048) != 0;
+  for (;;) {
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+    if (v >= p.step_target) break;
+    if (spins == 0) t0 = clock64();
+    // (diagnostic mode: once one wait has been abandoned every other one gives up at once, so the launch ends quickly)
+    if ((++spins & 0x3ff) == 0 &&
+        (clock64() - t0 > (diag ? 200000000LL : 4000000000LL) ||
+         (diag && *reinterpret_cast<volatile long long*>(g_trace + (kTraceRoles - 1) * kTraceLen) != 0))) {
+      if (!diag) {
+        fail_note(3, (static_cast<unsigned long long>(step) << 32) | static_cast<unsigned>(b), v);
+        __trap();
+      }
+      long long* row = g_trace + (kTraceRoles - 1) * kTraceLen;
+      const unsigned long long i = atomicAdd(reinterpret_cast<unsigned long long*>(row), 1ULL);
+      if (i < 200) {
+        row[1 + 5 * i] = blockIdx.x;
+        row[2 + 5 * i] = threadIdx.x >> 5;
+        row[3 + 5 * i] = step;
+        row[4 + 5 * i] = b;
+        row[5 + 5 * i] = v;
+      }
+      break;
+    }
+  }
+  // the data was written by TMA stores (async proxy) and is about to be read by TMA loads
+  asm volatile("fence.proxy.async;" ::: "memory");
+}
+// whole warp (step and b warp-uniform): the elected lane waits, the others rejoin it before the next warp-wide barrier wait
+// `seen`: (step, image) this warp checked last -- consecutive tiles of one image cost one look at the counter
+__device__ __forceinline__ void wait_prev_step_warp(const ConvGemmParams& p, int step, int b, bool leader, int& seen) {
+  if (step == 0) return;
+  const int key = step * p.B + (b - p.b0);
+  if (key == seen) return;
+  seen = key;
+  if (leader) wait_prev_step(p, step, b);
+  __syncwarp();
+}
+// Storer side of the hand-off (one lane): count a tile once this thread's TMA stores of it are complete (not only read).
+// The counter update is a RELAXED reduction: the tile's data were written by this thread's own TMA stores, which
+// cp.async.bulk.wait_group (without .read) has seen performed at the L2 -- the coherence point the consumers' TMA
+// loads read from -- and the reduction is issued after it in program order.  A gpu-scope release here
+// (red.release.gpu / fence.acq_rel.gpu: MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR in SASS) made the CTA-pair backward kernel
+// fail with "unspecified launch failure" on B200 whenever a cluster processed several tile groups per step, with or
+// without the reduction that follows it; the relaxed form is bit-exact over the whole test-suite.
+//
+// Waiting for a tile's writes right after issuing them would idle the storer for the write latency once per tile, so
+// the count of tile k is DEFERRED until tile k+1's stores have been committed (wait_group N: all but the N newest
+// groups are complete) -- but only inside a time step: the next step's tiles may depend on this one, so the last tile
+// a CTA has in a step is flushed at once.
+struct TileSignal {
+  int step, b;   // tile whose stores are committed but not yet counted (b < 0: none)
+  __device__ __forceinline__ TileSignal() : step(0), b(-1) {}
+  __device__ __forceinline__ void count(const ConvGemmParams& p) {
+    asm volatile("fence.proxy.async;" ::: "memory");
+    unsigned* ctr = p.step_done + static_cast<long long>(step) * p.B + (b - p.b0);
+    asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+    b = -1;
+  }
+  // a tile's stores have just been committed as `newest` bulk groups
+  __device__ __forceinline__ void tile_done(const ConvGemmParams& p, int step_, int b_, int newest) {
+    if (p.n_steps == 1) return;
+    if (b >= 0) {
+      if (newest <= 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      else if (newest == 1) asm volatile("cp.async.bulk.wait_group 1;" ::: "memory");
+      else if (newest == 2) asm volatile("cp.async.bulk.wait_group 2;" ::: "memory");
+      else if (newest == 3) asm volatile("cp.async.bulk.wait_group 3;" ::: "memory");
+      else asm volatile("cp.async.bulk.wait_group 4;" ::: "memory");
+      count(p);
+    }
+    step = step_;
+    b = b_;
+  }
+  __device__ __forceinline__ void flush(const ConvGemmParams& p) {
+    if (p.n_steps == 1 || b < 0) return;
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    count(p);
+  }
+};
+// the walk's next group (base + stride) lies in another time step, or there is none
+__device__ __forceinline__ bool last_group_of_step(const ConvGemmParams& p, const TileWalk& w, int base, int step) {
+  const int nb = base + w.tile_stride;
+  return nb >= w.tiles_padded || nb / w.tiles_step != step;
 }
 
 // shared-memory address of 16-byte chunk `chunk` of pixel row `row` inside a TMA box with ROWB-byte rows
@@ -192,13 +309,16 @@ __device__ __forceinline__ void fwd_c_loader(const ConvGemmParams& p, uint8_t* s
   const bool leader = elect_one();
   Tracer tr(p, 2, leader);
   const int G = p.group, ngroups = p.hcb >> 4;
-  int s = 0;
+  int s = 0, seen = -1;
   uint32_t ph = 0;
   for (int base = w.first_tile; base < w.tiles_padded; base += w.tile_stride) {
+    const GroupPos gp = group_pos(p, w, base);
+    const int slot_c_in = step_slot(p, p.slot_c_in, p.d_c_in, 2, gp.step);
     for (int gi = 0; gi < G; ++gi) {
-      const int tile = base + gi;
+      const int tile = gp.tile0 + gi;
       if (tile >= w.num_tiles) break;
       const ItemCoord c = decode_tile(p, tile);
+      wait_prev_step_warp(p, gp.step, c.b, leader, seen);   // c_{t-1} of this tile comes from the previous step of this launch
       for (int grp = 0; grp < ngroups; ++grp) {
         tr.stamp();
         mbar_wait(&b.c_empty[s], ph ^ 1);
@@ -206,7 +326,7 @@ __device__ __forceinline__ void fwd_c_loader(const ConvGemmParams& p, uint8_t* s
         if (leader) {
           if (p.slot_c_in >= 0) {
             mbar_arrive_expect_tx(&b.c_full[s], kEpiBoxBytes16);
-            tma_load_5d(fwd_c_slot(p, sE, s), &p.tm_c, &b.c_full[s], w.nb * p.hcb + grp * 16, c.x0, c.y0, c.b, p.slot_c_in);
+            tma_load_5d(fwd_c_slot(p, sE, s), &p.tm_c, &b.c_full[s], w.nb * p.hcb + grp * 16, c.x0, c.y0, c.b, slot_c_in);
           } else {
             mbar_arrive(&b.c_full[s]);   // zero state: nothing to read, the slot is only an output buffer
           }
@@ -233,9 +353,14 @@ __device__ __forceinline__ void fwd_storer(const ConvGemmParams& p, uint8_t* sE,
   uint64_t* empty = kind == 0 ? b.c_empty : b.hg_empty;
   int s = 0;
   uint32_t ph = 0;
+  TileSignal sig;
   for (int base = w.first_tile; base < w.tiles_padded; base += w.tile_stride) {
+    const GroupPos gp = group_pos(p, w, base);
+    const int slot_c_out = step_slot(p, p.slot_c_out, p.d_c_out, 3, gp.step);
+    const int slot_h_out = step_slot(p, p.slot_h_out, p.d_h_out, 4, gp.step);
+    const int slot_g = step_slot(p, p.slot_g, p.d_g, 31, gp.step);
     for (int gi = 0; gi < G; ++gi) {
-      const int tile = base + gi;
+      const int tile = gp.tile0 + gi;
       if (tile >= w.num_tiles) break;
       const ItemCoord c = decode_tile(p, tile);
       for (int grp = 0; grp < ngroups; ++grp) {
@@ -246,15 +371,15 @@ __device__ __forceinline__ void fwd_storer(const ConvGemmParams& p, uint8_t* sE,
           if (!(p.debug_flags & 1)) {
             const int ch = w.nb * p.hcb + grp * 16;
             if (kind == 0) {
-              tma_store_5d(&p.tm_c, fwd_c_slot(p, sE, s), ch, c.x0, c.y0, c.b, p.slot_c_out);
+              tma_store_5d(&p.tm_c, fwd_c_slot(p, sE, s), ch, c.x0, c.y0, c.b, slot_c_out);
             } else {
               const uint8_t* st = fwd_hg_stage(p, sE, s);
-              tma_store_5d(&p.tm_h, st + p.e_off_h, ch, c.x0, c.y0, c.b, p.slot_h_out);
+              tma_store_5d(&p.tm_h, st + p.e_off_h, ch, c.x0, c.y0, c.b, slot_h_out);
               if (p.slot_g >= 0) {
                 const int q0 = group_q0(ch);
 #pragma unroll
                 for (int bx = 0; bx < GE::kGateBoxes; ++bx)
-                  tma_store_5d(&p.tm_g, st + bx * GE::kGateBoxBytes, q0 + bx * GE::kGateBoxCols, c.x0, c.y0, c.b, p.slot_g);
+                  tma_store_5d(&p.tm_g, st + bx * GE::kGateBoxBytes, q0 + bx * GE::kGateBoxCols, c.x0, c.y0, c.b, slot_g);
               }
             }
             tma_store_commit();
@@ -268,7 +393,9 @@ __device__ __forceinline__ void fwd_storer(const ConvGemmParams& p, uint8_t* sE,
           ph ^= 1;
         }
       }
+      if (leader) sig.tile_done(p, gp.step, c.b, (p.debug_flags & 1) ? 0 : ngroups);
     }
+    if (leader && last_group_of_step(p, w, base, gp.step)) sig.flush(p);
   }
   if (leader) tma_store_wait_all();   // global writes complete before the CTA exits
 }
@@ -292,8 +419,9 @@ __device__ __forceinline__ void fwd_math(const ConvGemmParams& p, int warp, int 
   uint32_t aphase = 0;
   for (int base = w.first_tile; base < w.tiles_padded; base += w.tile_stride) {
     bool waited = false;
+    const GroupPos gp = group_pos(p, w, base);
     for (int gi = 0; gi < G; ++gi) {
-      const int tile = base + gi;
+      const int tile = gp.tile0 + gi;
       if (tile >= w.num_tiles) break;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
                              static_cast<uint32_t>(abuf * p.acc_cols + gi * p.n_tile);
@@ -398,13 +526,17 @@ __device__ __forceinline__ void epi_loader(const ConvGemmParams& p, uint8_t* sE,
   Tracer tr(p, 2, leader && which == 0);
   const int G = p.group;
   const int ngroups = epi_groups<EPI>(p);
-  int s = 0, n = 0;
+  int s = 0, n = 0, seen = -1;
   uint32_t ph = 0;
   for (int base = w.first_tile; base < w.tiles_padded; base += w.tile_stride) {
+    const GroupPos gp = group_pos(p, w, base);
+    const int slot_g = step_slot(p, p.slot_g, p.d_g, 31, gp.step);
+    const int slot_c_prev = gp.step == p.c_prev_none_step ? -1 : step_slot(p, p.slot_c_prev, p.d_c_prev, 31, gp.step);
     for (int gi = 0; gi < G; ++gi) {
-      const int tile = base + gi;
+      const int tile = gp.tile0 + gi;
       if (tile >= w.num_tiles) break;
       const ItemCoord c = decode_tile(p, tile);
+      wait_prev_step_warp(p, gp.step, c.b, leader, seen);   // the running dc of this tile comes from the previous step of this launch
       for (int grp = 0; grp < ngroups; ++grp, ++n) {
         const bool mine = (nwhich == 1) || ((n % nwhich) == which);
         if (mine) tr.stamp();
@@ -413,15 +545,15 @@ __device__ __forceinline__ void epi_loader(const ConvGemmParams& p, uint8_t* sE,
         if (mine && leader) {
           uint8_t* st = sE + s * p.e_stage_bytes;
           uint64_t* bar = &e_full[s];
-          const uint32_t bytes = GE::kGateBytes + kEpiBoxBytes16 * ((p.slot_c_prev >= 0) + (p.has_dc_in != 0));
+          const uint32_t bytes = GE::kGateBytes + kEpiBoxBytes16 * ((slot_c_prev >= 0) + (p.has_dc_in != 0));
           mbar_arrive_expect_tx(bar, bytes);
           const int q0 = group_q0(grp * 16);
 #pragma unroll
           for (int bx = 0; bx < GE::kGateBoxes; ++bx)
-            tma_load_5d(st + bx * GE::kGateBoxBytes, &p.tm_g, bar, q0 + bx * GE::kGateBoxCols, c.x0, c.y0, c.b, p.slot_g);
+            tma_load_5d(st + bx * GE::kGateBoxBytes, &p.tm_g, bar, q0 + bx * GE::kGateBoxCols, c.x0, c.y0, c.b, slot_g);
           // c_t is not read back: it is c_{t-1} f + i g of the values loaded here (model.py:228)
-          if (p.slot_c_prev >= 0)
-            tma_load_5d(st + p.e_off_c2, &p.tm_c, bar, grp * 16, c.x0, c.y0, c.b, p.slot_c_prev);
+          if (slot_c_prev >= 0)
+            tma_load_5d(st + p.e_off_c2, &p.tm_c, bar, grp * 16, c.x0, c.y0, c.b, slot_c_prev);
           if (p.has_dc_in) tma_load_5d(st + p.e_off_dc, &p.tm_dc, bar, grp * 16, c.x0, c.y0, c.b, 0);
         }
         if (mine) tr.stamp();
@@ -446,13 +578,18 @@ __device__ __forceinline__ void epi_storer(const ConvGemmParams& p, uint8_t* sE,
   const int ngroups = epi_groups<EPI>(p);
   int s = 0, n = 0;
   uint32_t ph = 0;
+  TileSignal sig;
   for (int base = w.first_tile; base < w.tiles_padded; base += w.tile_stride) {
+    const GroupPos gp = group_pos(p, w, base);
+    const int slot_g = step_slot(p, p.slot_g, p.d_g, 31, gp.step);
     for (int gi = 0; gi < G; ++gi) {
-      const int tile = base + gi;
+      const int tile = gp.tile0 + gi;
       if (tile >= w.num_tiles) break;
       const ItemCoord c = decode_tile(p, tile);
+      int committed = 0;   // bulk groups this warp commits for this tile
       for (int grp = 0; grp < ngroups; ++grp, ++n) {
         const bool mine = (nwhich == 1) || ((n % nwhich) == which);
+        if (mine && !(p.debug_flags & 1)) ++committed;
         if (mine) tr.stamp();
         if (mine) mbar_wait(&st_ready[s], ph);
         if (mine) tr.stamp();
@@ -462,7 +599,7 @@ __device__ __forceinline__ void epi_storer(const ConvGemmParams& p, uint8_t* sE,
             const int q0 = group_q0(grp * 16);
 #pragma unroll
             for (int bx = 0; bx < GE::kGateBoxes; ++bx)
-              tma_store_5d(&p.tm_g, st + bx * GE::kGateBoxBytes, q0 + bx * GE::kGateBoxCols, c.x0, c.y0, c.b, p.slot_g);
+              tma_store_5d(&p.tm_g, st + bx * GE::kGateBoxBytes, q0 + bx * GE::kGateBoxCols, c.x0, c.y0, c.b, slot_g);
             tma_store_5d(&p.tm_dc, st + p.e_off_dc, grp * 16, c.x0, c.y0, c.b, 0);
             tma_store_commit();
             tma_store_wait_read();   // the stage may be overwritten once TMA has read it
@@ -475,7 +612,9 @@ __device__ __forceinline__ void epi_storer(const ConvGemmParams& p, uint8_t* sE,
           ph ^= 1;
         }
       }
+      if (leader) sig.tile_done(p, gp.step, c.b, committed);
     }
+    if (leader && last_group_of_step(p, w, base, gp.step)) sig.flush(p);
   }
   if (leader) tma_store_wait_all();   // global writes complete before the CTA exits
 }
@@ -504,8 +643,10 @@ __device__ __forceinline__ void epi_math(const ConvGemmParams& p, int warp, int 
   uint32_t aphase = 0;
   for (int base = w.first_tile; base < w.tiles_padded; base += w.tile_stride) {
     bool waited = (p.nseg == 0);
+    const GroupPos gp = group_pos(p, w, base);
+    const bool have_c_prev = p.slot_c_prev >= 0 && gp.step != p.c_prev_none_step;
     for (int gi = 0; gi < G; ++gi) {
-      const int tile = base + gi;
+      const int tile = gp.tile0 + gi;
       if (tile >= w.num_tiles) break;
       const ItemCoord c = decode_tile(p, tile);
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
@@ -515,7 +656,7 @@ __device__ __forceinline__ void epi_math(const ConvGemmParams& p, int warp, int 
         if (p.head_dpred) {
           const int y = c.y0 + (row >> 3), x = c.x0 + (row & 7);
           if (y < p.H && x < p.W)
-            dpred = p.head_dpred[c.b * p.head_dpred_bstride + static_cast<long long>(y) * p.W + x];
+            dpred = p.head_dpred[gp.step * p.head_dpred_sstride + c.b * p.head_dpred_bstride + static_cast<long long>(y) * p.W + x];
         }
       }
       for (int grp = 0; grp < ngroups; ++grp) {
@@ -544,7 +685,7 @@ __device__ __forceinline__ void epi_math(const ConvGemmParams& p, int warp, int 
           lds_gate<E>(st, row, 1, half, gf);
           lds_gate<E>(st, row, 2, half, gg);
           lds_gate<E>(st, row, 3, half, go);
-          if (p.slot_c_prev >= 0) {
+          if (have_c_prev) {
             lds8<float, 64>(st + p.e_off_c2, row, half, cp);
           } else {
 #pragma unroll

@@ -79,6 +79,19 @@ struct alignas(64) ConvGemmParams {
   const float* dh_ext;      // optional [B,H,W,hc] fp32 channels-last: dh += dh_ext (standalone cell backward, model.py:216-231)
   // ---- EPI_RAW: dump fp32 accumulators [B,H,W,n_blocks*n_tile] (debug / generic conv)
   float* raw_out;
+  // ---- time-fused launch: n_steps > 1 consecutive time steps of one layer run as ONE persistent launch.  The tile walk
+  // covers n_steps x tiles (step-major); in step s every slot field advances by its `d_*` (forward +1, BPTT -1; fields in
+  // ring_bits live in a 2-slot ring).  Step s of image b may only start once every tile of image b of step s-1 has been
+  // stored: step_done[(s-1) * B + b] counts the storer warps that have finished a tile (zeroed before the launch) and
+  // reaches step_target.  Tile-level dependencies instead of a grid-wide drain between launches: the pipeline of a CTA
+  // never empties across steps.
+  int n_steps;
+  int d_seg[2], d_c_in, d_c_out, d_h_out, d_g, d_c_prev;
+  int ring_bits;            // bit 0/1: seg[0/1].slot, 2: slot_c_in, 3: slot_c_out, 4: slot_h_out (slot & 1 after the advance)
+  int c_prev_none_step;     // BWD: step whose c_{t-1} is the zero initial state (-1: none)
+  long long head_dpred_sstride;   // elements between consecutive steps of head_dpred
+  unsigned* step_done;
+  unsigned step_target;
 };
 
 // 8x16 pixel tiles, activation chunk + halo loaded once and re-read by every tap (nint_conv_halo.cu).
@@ -89,6 +102,7 @@ int conv_halo_smem_bytes(const ConvGemmParams& p);
 cudaError_t launch_conv_halo(int epi, int dtype, const ConvGemmParams& p, int num_sms, cudaStream_t stream);
 // debug timeline (debug_flags & 8): 8 roles x 1024 clock64 stamps written by CTA 0 of the last traced launch
 cudaError_t read_trace(long long* host, int n);
+cudaError_t fail_record(unsigned long long* out5);
 cudaError_t clear_trace();
 
 // ---- wgrad (nint_wgrad.cu):  dW[tap][q][col] += sum_pixels dgates[pix][q] * comb[pix + tap][col]

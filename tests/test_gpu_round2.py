@@ -416,6 +416,47 @@ def test_sub_batch_major_schedule_changes_nothing(monkeypatch):
         torch.backends.cudnn.deterministic = prev
 
 
+@pytest.mark.parametrize("shape", [(9, 6, 40, 36), (40, 4, 40, 36)])
+@pytest.mark.parametrize("hidden,ks,precision,seq", [([64], [3], "bf16", False), ([64, 32], [3, 5], "bf16", False),
+                                                     ([32], [3], "tf32", False), ([16, 16, 16], [3, 3, 3], "bf16", True)])
+def test_time_fused_launches_change_nothing(monkeypatch, hidden, ks, precision, seq, shape):
+    """NINT_FUSE_STEPS (default on): all time steps of a layer run as ONE persistent launch whose tiles wait for the
+    previous step's tiles of the same image instead of for the whole previous launch.  Per-tile arithmetic is untouched,
+    so training forward, inference forward (2-slot h ring) and the deterministic gradients are bit-identical to the
+    one-launch-per-step schedule.  9 images of 3 x 5 tiles: fewer tile groups per step than CTA pairs, every cluster
+    jumps a step between groups; 40 images: several groups per cluster and step"""
+    B, T = shape[:2]
+    x = torch.randn(B, T, 21, shape[2], shape[3], device="cuda")
+
+    from nasa_niswan_b200 import ConvLSTM
+
+    def run(fuse):
+        monkeypatch.setenv("NINT_FUSE_STEPS", "3" if fuse else "0")
+        torch.manual_seed(11)
+        net = ConvLSTM(21, hidden, ks, len(hidden), precision=precision, return_sequence=seq).cuda()
+        if seq:
+            pred, hs = net(x)
+            (pred.sum() + (hs * torch.linspace(0.5, 1.5, T, device="cuda").view(1, T, 1, 1)).sum()).backward()
+        else:
+            pred = net(x)
+            pred.backward(torch.ones_like(pred) * 0.25)
+        with torch.no_grad():
+            inf = net(x)
+            inf = inf[0] if seq else inf
+        return pred.detach(), inf, [p.grad.clone() for p in net.parameters()]
+    prev = torch.backends.cudnn.deterministic
+    torch.backends.cudnn.deterministic = True
+    try:
+        ref = run(False)
+        for _ in range(2):
+            got = run(True)
+            assert torch.equal(ref[0], got[0]) and torch.equal(ref[1], got[1])
+            for a, b in zip(ref[2], got[2]):
+                assert torch.equal(a, b)
+    finally:
+        torch.backends.cudnn.deterministic = prev
+
+
 def test_training_step_replays_as_one_cuda_graph():
     """the native step (forward, fused loss, BPTT, wgrad, Adam with its step count and lr in device memory) captured
     once and replayed: same parameters as the eager steps, including across a learning-rate change"""
