@@ -129,8 +129,9 @@ __device__ __forceinline__ void wait_prev_step(const ConvGemmParams& p, int step
       break;
     }
   }
-  // the data was written by TMA stores (async proxy) and is about to be read by TMA loads
-  asm volatile("fence.proxy.async;" ::: "memory");
+  // No proxy fence: the data was written by TMA stores and is about to be read by TMA loads -- async proxy on both
+  // sides, through the L2 -- and only the counter goes through the generic proxy.  (fence.proxy.async compiles to
+  // MEMBAR.ALL.GPU + FENCE.VIEW.ASYNC; see TileSignal for what gpu-scope membars did to this kernel.)
 }
 // whole warp (step and b warp-uniform): the elected lane waits, the others rejoin it before the next warp-wide barrier wait
 // `seen`: (step, image) this warp checked last -- consecutive tiles of one image cost one look at the counter
@@ -145,10 +146,14 @@ __device__ __forceinline__ void wait_prev_step_warp(const ConvGemmParams& p, int
 // Storer side of the hand-off (one lane): count a tile once this thread's TMA stores of it are complete (not only read).
 // The counter update is a RELAXED reduction: the tile's data were written by this thread's own TMA stores, which
 // cp.async.bulk.wait_group (without .read) has seen performed at the L2 -- the coherence point the consumers' TMA
-// loads read from -- and the reduction is issued after it in program order.  A gpu-scope release here
-// (red.release.gpu / fence.acq_rel.gpu: MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR in SASS) made the CTA-pair backward kernel
+// loads read from -- and the reduction is issued after it in program order.  No gpu-scope fence on either side:
+// red.release.gpu / fence.acq_rel.gpu (SASS: MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR) made the CTA-pair backward kernel
 // fail with "unspecified launch failure" on B200 whenever a cluster processed several tile groups per step, with or
-// without the reduction that follows it; the relaxed form is bit-exact over the whole test-suite.
+// without the reduction after it, and fence.proxy.async (MEMBAR.ALL.GPU + FENCE.VIEW.ASYNC) still did so once in a few
+// hundred training steps.  None of the kernel's bounded waits had fired (nint_debug_fail_record); compute-sanitizer
+// and GPU core dumps are closed on this pool, so the cause is unknown.  The fence-free form has run 7 000 training
+// steps at the BASELINE geometry without a failure and leaves bit-identical parameters after 400 deterministic
+// steps (tools/fused_stress.py --det, NINT_FUSE_STEPS=0 / 2 / 3).
 //
 // Waiting for a tile's writes right after issuing them would idle the storer for the write latency once per tile, so
 // the count of tile k is DEFERRED until tile k+1's stores have been committed (wait_group N: all but the N newest
@@ -158,7 +163,6 @@ struct TileSignal {
   int step, b;   // tile whose stores are committed but not yet counted (b < 0: none)
   __device__ __forceinline__ TileSignal() : step(0), b(-1) {}
   __device__ __forceinline__ void count(const ConvGemmParams& p) {
-    asm volatile("fence.proxy.async;" ::: "memory");
     unsigned* ctr = p.step_done + static_cast<long long>(step) * p.B + (b - p.b0);
     asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
     b = -1;
