@@ -510,7 +510,7 @@ def main():
                        "loss_at_end": round(float(loss), 5), "numa_node": numa,
                        "sub_batch": int(os.environ.get("NINT_SUB_BATCH", "0") or 0),
                        "pdl": int(os.environ.get("NINT_PDL", "1") or 0),
-                       "time_fused_launches": int(os.environ.get("NINT_FUSE_STEPS", "2") or 0)},
+                       "time_fused_launches": os.environ.get("NINT_FUSE_STEPS", "auto (BPTT launches fused when short)")},
             "e2e": e2e,
             "e2e_variants": variants,
             "sustained": sustained,

@@ -197,9 +197,9 @@ int nint_debug_raw_gates(nint_plan* plan, const float* x, float* out, void* stre
 /* debug timeline: with NINT_DEBUG_FLAGS & 8, CTA 0 of every conv launch records clock64() stamps per warp role
  * (8 roles x 1024 stamps; later launches overwrite earlier ones).  Copies them to `host`, optionally clears. */
 int nint_debug_read_trace(long long* host, int n, int clear);
-/* Post-mortem of the conv kernels' bounded waits (a protocol bug traps instead of hanging the GPU, and a trap destroys
- * the context): the first call arms a host-mapped record, later calls -- also after a failed launch -- return
- * {code (0 = none, 1 mbarrier, 2 progress counter, 3 time-fused step hand-off), block, thread, a, b}. */
+/* Post-mortem of a time-fused conv launch's step hand-off (a wait that lasts ~2 s traps instead of hanging the GPU, and
+ * a trap destroys the context): the first call arms a host-mapped record, later calls -- also after a failed launch --
+ * return {code (0 = none, 3 = hand-off timed out), block, thread, (step << 32) | image, counter value}. */
 int nint_debug_fail_record(unsigned long long* out5);
 /* reference gate channel n = gate*Hc + c for kernel column q of a layer with Hc hidden channels */
 int nint_gate_column(int q, int hidden);

@@ -138,10 +138,11 @@ struct nint_plan {
   float* head_part = nullptr;  // deterministic mode: per-block partial sums of the head gradient
   unsigned* step_done = nullptr;   // [T][B] tile counters of a time-fused conv launch (ConvGemmParams::step_done)
   // consecutive time steps of a layer as ONE persistent launch whose tiles wait on the previous step's tiles of the same
-  // image (ConvGemmParams::n_steps).  Bit 0: forward, bit 1: BPTT (NINT_FUSE_STEPS).  Measured on B200 at cfg 2: the
-  // backward launch -6 % per step; the forward kernel runs at its steady-state rate from start to end already (PDL hides
-  // its prologue) and the storer's wait for write completion costs it +8 %, so only the backward is fused by default.
-  int fuse_steps = 2;
+  // image (ConvGemmParams::n_steps).  -1: automatic -- BPTT launches are fused while they are short (bwd_should_fuse),
+  // forward launches never (with PDL the forward kernel runs at its steady-state rate from start to end, and the
+  // storers' wait for write completion costs it more than the drain it saves: DESIGN.md section 6).  NINT_FUSE_STEPS=
+  // 0 / 1 / 2 / 3 forces nothing / forward / BPTT / both.
+  int fuse_steps = -1;
   bool head_set = false;
   bool zero_init = true;
   bool fwd_done = false;
@@ -1017,7 +1018,7 @@ static int forward_steps(nint_plan* p, float* pred, float* seq, cudaStream_t st)
   // time-fused schedule: layer by layer, all steps of a layer in ONE persistent launch (after the step that starts
   // from the zero state, whose GEMM has no h segment).  Layer-major order needs the whole h history of the layer
   // below, which a training plan keeps; an inference plan keeps two slots, so only a single layer fuses there
-  if ((p->fuse_steps & 1) && SB >= p->B && p->T > 1 && (tr || (p->L == 1 && !seq))) {
+  if (p->fuse_steps > 0 && (p->fuse_steps & 1) && SB >= p->B && p->T > 1 && (tr || (p->L == 1 && !seq))) {
     for (int l = 0; l < p->L; ++l) {          // model.py:267
       int t = 0;
       if (p->zero_init) {
@@ -1232,16 +1233,11 @@ static bool resid_on(const nint_plan* p) {
   return p->num_sms <= kResidCtas && static_cast<long long>(p->B) * p->T * p->H * p->W <= kResidMaxPixelSteps;
 }
 
-// one fused dgrad + gate-backward launch of layer l at step t for images [b0, b0 + nb) (nb = 0: all); n_steps > 1: steps
-// t, t-1, .. t-n_steps+1 as ONE time-fused launch (t < T-1: all of them have a dgates_{t+1} segment and a running dc)
-static int bwd_step(nint_plan* p, int l, int t, const float* dpred, const float* dseq, const float* dh_ext, bool dc_given,
-                    cudaStream_t st, int b0, int nb, int n_steps = 1) {
-  const long long HW = static_cast<long long>(p->H) * p->W;
-  const int L = p->L, T = p->T;
+// step-independent launch parameters of layer l's dgrad + gate-backward kernel (has_next: with a dgates_{t+1} segment)
+static int bwd_conv_params(nint_plan* p, int l, bool has_next, ConvGemmParams& g) {
+  const int L = p->L;
   Layer& y = p->layer[l];
-  const bool has_next = t < T - 1;
   Layer::CachedConv& cache = y.bwd_cache[has_next ? 1 : 0];
-  ConvGemmParams g;
   if (cache.valid) {
     g = cache.g;
   } else {
@@ -1274,6 +1270,41 @@ static int bwd_step(nint_plan* p, int l, int t, const float* dpred, const float*
     cache.g = g;
     cache.valid = true;
   }
+  return 0;
+}
+
+// Time-fused BPTT launch (ConvGemmParams::n_steps) or one launch per step?  Fusing removes the pipeline drain and the
+// tail imbalance of every launch but makes the kernel's steady state ~5 % slower (hand-off polling, storers waiting for
+// write completion): measured on B200 it pays while a launch is short -- a CTA pair walks few tile groups per step
+// (reference recipe, 3.8 rounds: -2.6 %; cfg 2 at B=8, 2.9 rounds: -2.9 %) -- is neutral at 5.8 rounds (B=16) and costs
+// +0.5 % at 11.7 (B=32).  NINT_FUSE_STEPS bit 1 forces it, 0 forbids it.
+static int bwd_should_fuse(nint_plan* p, int l, bool* fuse) {
+  *fuse = false;
+  const int SB = p->sub_batch > 0 ? p->sub_batch : p->B;
+  if (SB < p->B || p->T <= 2 || p->fuse_steps == 0) return 0;
+  if (p->fuse_steps > 0) {
+    *fuse = (p->fuse_steps & 2) != 0;
+    return 0;
+  }
+  ConvGemmParams g;
+  if (bwd_conv_params(p, l, true, g)) return 1;
+  const int per_group = g.cluster * g.group;
+  const double groups = (static_cast<double>(p->B) * p->tiles_x * p->tiles_y + per_group - 1) / per_group;
+  const int clusters = p->num_sms / g.cluster;
+  *fuse = clusters > 0 && groups / clusters <= 5.0;
+  return 0;
+}
+
+// one fused dgrad + gate-backward launch of layer l at step t for images [b0, b0 + nb) (nb = 0: all); n_steps > 1: steps
+// t, t-1, .. t-n_steps+1 as ONE time-fused launch (t < T-1: all of them have a dgates_{t+1} segment and a running dc)
+static int bwd_step(nint_plan* p, int l, int t, const float* dpred, const float* dseq, const float* dh_ext, bool dc_given,
+                    cudaStream_t st, int b0, int nb, int n_steps = 1) {
+  const long long HW = static_cast<long long>(p->H) * p->W;
+  const int L = p->L, T = p->T;
+  Layer& y = p->layer[l];
+  const bool has_next = t < T - 1;
+  ConvGemmParams g;
+  if (bwd_conv_params(p, l, has_next, g)) return 1;
   int s = 0;
   if (has_next) g.seg[s++].slot = t + 1;
   if (l < L - 1) g.seg[s++].slot = t;
@@ -1319,12 +1350,24 @@ static int bptt_loop(nint_plan* p, const float* dpred, const float* dseq, const 
   const int SB = p->sub_batch > 0 ? p->sub_batch : p->B;
   for (int l = 0; l < p->L; ++l)
     if (p->layer[l].db_resid) CK(cudaMemsetAsync(p->layer[l].db_resid, 0, static_cast<size_t>(kResidCtas) * 4 * 4 * p->layer[l].hc * 4, st));
-  if ((p->fuse_steps & 2) && SB >= p->B && p->T > 2) {
-    // time-fused schedule: top layer first, each layer's steps T-2 .. 0 as ONE persistent launch after its step T-1
-    // (which has no dgates_{t+1} segment); layer l reads the dgates of layer l+1 at the same t, all in place by then
+  bool any_fused = false;
+  bool fuse_l[NINT_MAX_LAYERS];
+  for (int l = 0; l < p->L; ++l) {
+    if (bwd_should_fuse(p, l, &fuse_l[l])) return 1;
+    any_fused = any_fused || fuse_l[l];
+  }
+  if (any_fused) {
+    // layer-major schedule: top layer first; layer l reads the dgates of layer l+1 at the same t, all in place by then.
+    // A fused layer runs its steps T-2 .. 0 as ONE persistent launch after its step T-1 (which has no dgates_{t+1}
+    // segment); the others one launch per step
     for (int l = p->L - 1; l >= 0; --l) {
       if (bwd_step(p, l, p->T - 1, dpred, dseq, dh_ext, dc_given, st, 0, 0)) return 1;
-      if (bwd_step(p, l, p->T - 2, dpred, dseq, dh_ext, dc_given, st, 0, 0, p->T - 1)) return 1;
+      if (fuse_l[l]) {
+        if (bwd_step(p, l, p->T - 2, dpred, dseq, dh_ext, dc_given, st, 0, 0, p->T - 1)) return 1;
+      } else {
+        for (int t = p->T - 2; t >= 0; --t)
+          if (bwd_step(p, l, t, dpred, dseq, dh_ext, dc_given, st, 0, 0)) return 1;
+      }
     }
   } else
   for (int b0 = 0; b0 < p->B; b0 += SB) {

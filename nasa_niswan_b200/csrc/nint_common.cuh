@@ -70,23 +70,6 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Post-mortem record of a timed-out wait: a trap kills the context (device memory and the printf buffer with it), so
-// the first failing thread also leaves {code, block, thread, a, b} in host-mapped memory when a debug session armed it
-// (nint_debug_fail_record); one copy of the pointer per translation unit.
-static __device__ unsigned long long* g_fail_host = nullptr;
-static __device__ __noinline__ void fail_note(unsigned long long code, unsigned long long a, unsigned long long b) {
-  unsigned long long* h = g_fail_host;
-  if (!h) return;
-  if (*reinterpret_cast<volatile unsigned long long*>(h) == 0ULL) {   // (plain stores: no PCIe atomics needed; first writers may race)
-    h[1] = blockIdx.x;
-    h[2] = threadIdx.x;
-    h[3] = a;
-    h[4] = b;
-    __threadfence_system();
-    *reinterpret_cast<volatile unsigned long long*>(h) = code;
-    __threadfence_system();
-  }
-}
 // Bounded wait: a protocol bug must trap (error returned to the host), never hang the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
@@ -94,7 +77,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if ((++spins & 0x3ff) == 0 && clock64() - t0 > 4000000000LL) {
-      fail_note(1, smem_u32(bar), parity);
       printf("nint: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", (int)blockIdx.x,
              (int)threadIdx.x, smem_u32(bar), parity);
       __trap();
@@ -110,7 +92,6 @@ __device__ __forceinline__ void spin_until_at_least(volatile uint32_t* counter, 
   uint32_t spins = 0;
   while (*counter < value) {
     if ((++spins & 0x3ff) == 0 && clock64() - t0 > 4000000000LL) {
-      fail_note(2, value, *counter);
       printf("nint: progress counter wait timed out (block %d thread %d want %u have %u)\n", (int)blockIdx.x,
              (int)threadIdx.x, value, *counter);
       __trap();

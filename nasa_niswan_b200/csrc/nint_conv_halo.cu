@@ -54,7 +54,9 @@ __device__ __forceinline__ int halo_operand_bytes_dev(int a_buf_bytes, int na, i
   return (na * a_buf_bytes + nw * stage_bytes + 1023) & ~1023;
 }
 
-template <typename E, int EPI, bool PAIR>
+// FUSED: time-fused launch (ConvGemmParams::n_steps > 1).  A template parameter, not a run-time test: the hand-off code
+// in every role loop cost the one-launch-per-step forward kernel 19 % when it was merely branched around.
+template <typename E, int EPI, bool PAIR, bool FUSED>
 __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid_constant__ ConvGemmParams p) {
   constexpr int DT = ElemTraits<E>::kDtype;
   constexpr int CE = ElemTraits<E>::kPerChunk;
@@ -185,18 +187,19 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
     int ia = 0, iw = 0, cc = 0, seen = -1;
     uint32_t pa = 0, pw = 0;
     bool first = true;
+    StepCursor<FUSED> cur;
     for (int base = walk.first_tile; base < walk.tiles_padded; base += walk.tile_stride) {
-      const GroupPos gp = group_pos(p, walk, base);
-      if (do_a && gp.step > 0) {
+      const GroupPos gp = cur.at(walk, base);
+      if (FUSED && do_a && gp.step > 0) {
         // time-fused launch: the recurrent operand (h_{t-1} / dgates_{t+1}, with its halo) of these tiles was written by
         // the previous step of THIS launch
         const int g_begin = by_tile ? a_par : 0, g_end = by_tile ? a_par + 1 : G;
         for (int g = g_begin; g < g_end; ++g)
-          if (gp.tile0 + g < walk.num_tiles) wait_prev_step_warp(p, gp.step, decode_tile(p, gp.tile0 + g).b, leader, seen);
+          if (gp.tile0 + g < walk.num_tiles) wait_prev_step_warp<FUSED>(p, gp.step, decode_tile(p, gp.tile0 + g).b, seen);
       }
       for (int s = 0; s < p.nseg; ++s) {
         const ConvSegment& sg = p.seg[s];
-        const int seg_slot = step_slot(p, sg.slot, p.d_seg[s], s, gp.step);
+        const int seg_slot = step_slot<FUSED>(p, sg.slot, p.d_seg[s], s, gp.step);
         const int pad = sg.ksize >> 1;
         const int taps = sg.ksize * sg.ksize;
         const uint32_t a_bytes = static_cast<uint32_t>(halo_rows(sg.ksize) * kChunkBytes);
@@ -357,6 +360,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
       const bool w_ahead = lookahead && !resident && NW >= 3 && single_stage;
       // cur_ready: the current chunk's barriers were already awaited (by the previous iteration's look-ahead)
       bool cur_ready = false;
+      int step_hi = walk.tiles_step;
       if (valid && lookahead) {
         mbar_wait(&tempty_bar[abuf], aphase ^ 1);
         mbar_wait(&a_full[ia], pa);
@@ -391,8 +395,13 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
         // time-fused launch: the first tile group of the NEXT time step is loaded only after other CTAs have finished
         // tiles of this step -- possibly tiles that wait, symmetrically, on this CTA's current one.  Its barriers must
         // not be awaited before the current chunk (the last of this step here) has been issued.
-        const bool cross = p.n_steps > 1 && nvalid && last_of_tile &&
-                           ((nbase / walk.tiles_step != cbase / walk.tiles_step) || (p.debug_flags & 4096));
+        bool cross = false;
+        if constexpr (FUSED) {
+          if (last_of_tile) {
+            while (cbase >= step_hi) step_hi += walk.tiles_step;   // step_hi: end of the step cbase lies in
+            cross = nvalid && (nbase >= step_hi || (p.debug_flags & 4096));
+          }
+        }
         const bool look = lookahead && !cross;
         tr.stamp();
         if (!cur_ready) {
@@ -565,14 +574,14 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
   } else if (warp == 2 || warp == 3) {
     // ------------------------------------------------------------------ epilogue TMA stores
     // backward: the two warps alternate channel groups; forward: warp 3 stores c, warp 2 stores h + gates
-    if constexpr (EPI == EPI_BWD) epi_storer<E, EPI>(p, sE, st_ready, e_empty, walk, warp - 2, 2);
-    if constexpr (EPI == EPI_FWD) fwd_storer<E>(p, sE, FwdEpiBars{e_full, e_empty, st_ready, hg_ready, hg_empty}, walk, warp == 3 ? 0 : 1);
+    if constexpr (EPI == EPI_BWD) epi_storer<E, EPI, FUSED>(p, sE, st_ready, e_empty, walk, warp - 2, 2);
+    if constexpr (EPI == EPI_FWD) fwd_storer<E, FUSED>(p, sE, FwdEpiBars{e_full, e_empty, st_ready, hg_ready, hg_empty}, walk, warp == 3 ? 0 : 1);
   } else if (warp == 4 || warp == 5) {
     // ------------------------------------------------------------------ epilogue TMA loads
     // backward: 4 boxes per channel group, two loaders alternate groups; forward: one box per group, warp 4 only
-    if constexpr (EPI == EPI_BWD) epi_loader<E, EPI>(p, sE, e_full, e_empty, walk, warp - 4, 2);
+    if constexpr (EPI == EPI_BWD) epi_loader<E, EPI, FUSED>(p, sE, e_full, e_empty, walk, warp - 4, 2);
     if constexpr (EPI == EPI_FWD) {
-      if (warp == 4) fwd_c_loader<E>(p, sE, FwdEpiBars{e_full, e_empty, st_ready, hg_ready, hg_empty}, walk);
+      if (warp == 4) fwd_c_loader<E, FUSED>(p, sE, FwdEpiBars{e_full, e_empty, st_ready, hg_ready, hg_empty}, walk);
       if (warp == 5 && p.nseg > 0 && lead_cta && dual) issue_dual(1);   // second MMA issuer
     }
   } else if (warp >= kConvIoWarps) {
@@ -583,10 +592,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
     if constexpr (EPI == EPI_RAW)
       epi_raw(p, warp, lane, tmem_base, tfull_bar, tempty_bar, walk, tempty_remote);
     else if constexpr (EPI == EPI_FWD)
-      fwd_math<E>(p, warp, lane, tmem_base, sE, FwdEpiBars{e_full, e_empty, st_ready, hg_ready, hg_empty}, tfull_bar,
+      fwd_math<E, FUSED>(p, warp, lane, tmem_base, sE, FwdEpiBars{e_full, e_empty, st_ready, hg_ready, hg_empty}, tfull_bar,
                   tempty_bar, s_bias, walk, tempty_remote);
     else
-      epi_math<E, EPI>(p, warp, lane, tmem_base, sE, e_full, st_ready, tfull_bar, tempty_bar, s_bias, s_headw, walk,
+      epi_math<E, EPI, FUSED>(p, warp, lane, tmem_base, sE, e_full, st_ready, tfull_bar, tempty_bar, s_bias, s_headw, walk,
                        tempty_remote);
   }
   tc_fence_before();
@@ -717,13 +726,13 @@ int conv_halo_plan(int epi, int dtype, ConvGemmParams& p) {
   return 0;
 }
 
-template <typename E, int EPI, bool PAIR>
+template <typename E, int EPI, bool PAIR, bool FUSED>
 static cudaError_t launch_h(const ConvGemmParams& p, int num_sms, cudaStream_t stream) {
   const int smem = conv_halo_smem_bytes(p);
   if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<E, EPI, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<E, EPI, PAIR, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     configured = true;
   }
@@ -747,7 +756,7 @@ static cudaError_t launch_h(const ConvGemmParams& p, int num_sms, cudaStream_t s
     attr[na].val.clusterDim.z = 1;
     ++na;
   }
-  if (p.n_steps > 1) {
+  if (FUSED) {
     // CTAs of a time-fused launch wait for each other's tiles: every one of them must be resident at once
     static int max_units = -1;   // co-resident CTAs (single) / clusters (pair) of this instantiation at this smem size
     static int max_units_smem = -1;
@@ -757,10 +766,10 @@ static cudaError_t launch_h(const ConvGemmParams& p, int num_sms, cudaStream_t s
       if (PAIR) {
         cfg.attrs = attr;
         cfg.numAttrs = na;
-        e = cudaOccupancyMaxActiveClusters(&n, conv_halo_kernel<E, EPI, PAIR>, &cfg);
+        e = cudaOccupancyMaxActiveClusters(&n, conv_halo_kernel<E, EPI, PAIR, FUSED>, &cfg);
       } else {
         int per_sm = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, conv_halo_kernel<E, EPI, PAIR>, kConvThreads, smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, conv_halo_kernel<E, EPI, PAIR, FUSED>, kConvThreads, smem);
         n = per_sm * num_sms;
       }
       if (e != cudaSuccess) return e;
@@ -778,14 +787,16 @@ static cudaError_t launch_h(const ConvGemmParams& p, int num_sms, cudaStream_t s
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  return cudaLaunchKernelEx(&cfg, conv_halo_kernel<E, EPI, PAIR>, p);
+  return cudaLaunchKernelEx(&cfg, conv_halo_kernel<E, EPI, PAIR, FUSED>, p);
 }
 
 template <typename E, bool PAIR>
 static cudaError_t launch_e(int epi, const ConvGemmParams& p, int num_sms, cudaStream_t stream) {
-  if (epi == EPI_FWD) return launch_h<E, EPI_FWD, PAIR>(p, num_sms, stream);
-  if (epi == EPI_BWD) return launch_h<E, EPI_BWD, PAIR>(p, num_sms, stream);
-  return launch_h<E, EPI_RAW, PAIR>(p, num_sms, stream);
+  const bool fused = p.n_steps > 1;
+  if (epi == EPI_FWD) return fused ? launch_h<E, EPI_FWD, PAIR, true>(p, num_sms, stream) : launch_h<E, EPI_FWD, PAIR, false>(p, num_sms, stream);
+  if (epi == EPI_BWD) return fused ? launch_h<E, EPI_BWD, PAIR, true>(p, num_sms, stream) : launch_h<E, EPI_BWD, PAIR, false>(p, num_sms, stream);
+  if (fused) return cudaErrorInvalidValue;
+  return launch_h<E, EPI_RAW, PAIR, false>(p, num_sms, stream);
 }
 
 cudaError_t launch_conv_halo(int epi, int dtype, const ConvGemmParams& p, int num_sms, cudaStream_t stream) {
@@ -800,7 +811,7 @@ cudaError_t launch_conv_halo(int epi, int dtype, const ConvGemmParams& p, int nu
   return p.cluster == 2 ? launch_e<float, true>(epi, p, num_sms, stream) : launch_e<float, false>(epi, p, num_sms, stream);
 }
 
-// debug: arm (first call) and read the host-mapped post-mortem record of the conv kernels' bounded waits (fail_note);
+// debug: arm (first call) and read the host-mapped post-mortem record of the time-fused step hand-off (wait_prev_step);
 // readable after a trap has destroyed the context
 cudaError_t fail_record(unsigned long long* out5) {
   static unsigned long long* host = nullptr;

@@ -22,6 +22,9 @@ constexpr int kConvThreads = 512;   // warps 8-15: epilogue math
 constexpr int kEpiMaxStages = 4;    // ring depth limit (epilogue stages / forward c slots)
 constexpr int kEpiBoxBytes16 = kTilePixels * 16 * 4;   // 16 fp32 channels x 128 pixels = 8 KiB
 
+// host-mapped post-mortem record of a timed-out step hand-off (armed by nint_debug_fail_record; null otherwise)
+static __device__ unsigned long long* g_fail_host = nullptr;
+
 // ---- timeline trace (debug_flags & 8): CTA 0 records clock64() stamps per role into a global buffer that
 // tools/trace_report.py reads back through nint_debug_read_trace
 constexpr int kTraceRoles = 8, kTraceLen = 1024;
@@ -79,22 +82,41 @@ __device__ __forceinline__ TileWalk make_walk(const ConvGemmParams& p, int S, in
 struct GroupPos {
   int step, tile0;   // time step of the launch, first tile of the group inside that step
 };
-__device__ __forceinline__ GroupPos group_pos(const ConvGemmParams& p, const TileWalk& w, int base) {
-  GroupPos g;
-  g.step = 0;
-  g.tile0 = base;
-  if (p.n_steps > 1) {
-    g.step = base / w.tiles_step;
-    g.tile0 = base - g.step * w.tiles_step;
+// walks the step-major tile sequence without divisions: bases only grow, so the step is advanced by comparison
+template <bool FUSED>
+struct StepCursor {
+  int step, lo;   // current time step, first (padded) tile index of that step
+  __device__ __forceinline__ StepCursor() : step(0), lo(0) {}
+  __device__ __forceinline__ GroupPos at(const TileWalk& w, int base) {
+    GroupPos g;
+    if constexpr (FUSED) {
+      while (base >= lo + w.tiles_step) {
+        ++step;
+        lo += w.tiles_step;
+      }
+      g.step = step;
+      g.tile0 = base - lo;
+    } else {
+      g.step = 0;
+      g.tile0 = base;
+    }
+    return g;
   }
-  return g;
-}
+  // (after at(base)) the walk's next group, base + stride, lies in another time step, or there is none
+  __device__ __forceinline__ bool last_in_step(const TileWalk& w, int base) const {
+    if constexpr (!FUSED) return false;
+    const int nb = base + w.tile_stride;
+    return nb >= w.tiles_padded || nb >= lo + w.tiles_step;
+  }
+};
+template <bool FUSED>
 __device__ __forceinline__ int step_slot(const ConvGemmParams& p, int slot, int d, int ring_bit, int step) {
-  if (slot < 0 || p.n_steps == 1) return slot;
+  if constexpr (!FUSED) return slot;
+  if (slot < 0) return slot;
   const int v = slot + d * step;
   return (p.ring_bits >> ring_bit) & 1 ? (v & 1) : v;
 }
-// one lane: block until every tile of image b of the previous step has been stored (no-op in step 0 / single-step launches).
+// whole warp (all lanes poll the same word): block until every tile of image b of the previous step has been stored.
 // A wait that lasts ~2 s means a peer CTA is not resident or died: trap instead of hanging the GPU.  With debug flag 2048
 // the limit is ~0.1 s and the wait is then abandoned after leaving a record (block, warp, step, image, count) in the
 // trace buffer's last row (nint_debug_read_trace), so a dependency bug can be read back instead of killing the context.
@@ -114,9 +136,22 @@ __device__ __forceinline__ void wait_prev_step(const ConvGemmParams& p, int step
         (clock64() - t0 > (diag ? 200000000LL : 4000000000LL) ||
          (diag && *reinterpret_cast<volatile long long*>(g_trace + (kTraceRoles - 1) * kTraceLen) != 0))) {
       if (!diag) {
-        fail_note(3, (static_cast<unsigned long long>(step) << 32) | static_cast<unsigned>(b), v);
+        // post-mortem in host-mapped memory (a trap destroys the context): plain stores, no function call -- a CALL in
+        // a wait that is inlined into every role loop costs the hot loops their uniform registers (measured: forward
+        // +22 %, wgrad +17 % when mbar_wait carried one)
+        unsigned long long* h = g_fail_host;
+        if (h && (threadIdx.x & 31) == 0) {
+          h[1] = blockIdx.x;
+          h[2] = threadIdx.x;
+          h[3] = (static_cast<unsigned long long>(step) << 32) | static_cast<unsigned>(b);
+          h[4] = v;
+          h[0] = 3;
+          __threadfence_system();
+        }
+        __syncwarp();
         __trap();
       }
+      if ((threadIdx.x & 31) != 0) break;
       long long* row = g_trace + (kTraceRoles - 1) * kTraceLen;
       const unsigned long long i = atomicAdd(reinterpret_cast<unsigned long long*>(row), 1ULL);
       if (i < 200) {
@@ -133,15 +168,16 @@ __device__ __forceinline__ void wait_prev_step(const ConvGemmParams& p, int step
   // sides, through the L2 -- and only the counter goes through the generic proxy.  (fence.proxy.async compiles to
   // MEMBAR.ALL.GPU + FENCE.VIEW.ASYNC; see TileSignal for what gpu-scope membars did to this kernel.)
 }
-// whole warp (step and b warp-uniform): the elected lane waits, the others rejoin it before the next warp-wide barrier wait
+// whole warp (step and b are warp-uniform; every lane polls the same word: one request, no divergence).
 // `seen`: (step, image) this warp checked last -- consecutive tiles of one image cost one look at the counter
-__device__ __forceinline__ void wait_prev_step_warp(const ConvGemmParams& p, int step, int b, bool leader, int& seen) {
+template <bool FUSED>
+__device__ __forceinline__ void wait_prev_step_warp(const ConvGemmParams& p, int step, int b, int& seen) {
+  if constexpr (!FUSED) return;
   if (step == 0) return;
   const int key = step * p.B + (b - p.b0);
   if (key == seen) return;
   seen = key;
-  if (leader) wait_prev_step(p, step, b);
-  __syncwarp();
+  wait_prev_step(p, step, b);
 }
 // Storer side of the hand-off (one lane): count a tile once this thread's TMA stores of it are complete (not only read).
 // The counter update is a RELAXED reduction: the tile's data were written by this thread's own TMA stores, which
@@ -159,6 +195,7 @@ __device__ __forceinline__ void wait_prev_step_warp(const ConvGemmParams& p, int
 // the count of tile k is DEFERRED until tile k+1's stores have been committed (wait_group N: all but the N newest
 // groups are complete) -- but only inside a time step: the next step's tiles may depend on this one, so the last tile
 // a CTA has in a step is flushed at once.
+template <bool FUSED>
 struct TileSignal {
   int step, b;   // tile whose stores are committed but not yet counted (b < 0: none)
   __device__ __forceinline__ TileSignal() : step(0), b(-1) {}
@@ -169,7 +206,7 @@ struct TileSignal {
   }
   // a tile's stores have just been committed as `newest` bulk groups
   __device__ __forceinline__ void tile_done(const ConvGemmParams& p, int step_, int b_, int newest) {
-    if (p.n_steps == 1) return;
+    if constexpr (!FUSED) return;
     if (b >= 0) {
       if (newest <= 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
       else if (newest == 1) asm volatile("cp.async.bulk.wait_group 1;" ::: "memory");
@@ -182,16 +219,12 @@ struct TileSignal {
     b = b_;
   }
   __device__ __forceinline__ void flush(const ConvGemmParams& p) {
-    if (p.n_steps == 1 || b < 0) return;
+    if constexpr (!FUSED) return;
+    if (b < 0) return;
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     count(p);
   }
 };
-// the walk's next group (base + stride) lies in another time step, or there is none
-__device__ __forceinline__ bool last_group_of_step(const ConvGemmParams& p, const TileWalk& w, int base, int step) {
-  const int nb = base + w.tile_stride;
-  return nb >= w.tiles_padded || nb / w.tiles_step != step;
-}
 
 // shared-memory address of 16-byte chunk `chunk` of pixel row `row` inside a TMA box with ROWB-byte rows
 // (ROWB = 32 / 64 / 128 <-> SWIZZLE_32B / 64B / 128B: address bits [4,4+n) ^= bits [7,7+n)); base 1024-aligned
@@ -308,21 +341,22 @@ __device__ __forceinline__ uint8_t* fwd_hg_stage(const ConvGemmParams& p, uint8_
   return sE + p.c_ring * kEpiBoxBytes16 + s * p.e_stage_bytes;
 }
 
-template <typename E>
+template <typename E, bool FUSED>
 __device__ __forceinline__ void fwd_c_loader(const ConvGemmParams& p, uint8_t* sE, const FwdEpiBars& b, const TileWalk& w) {
   const bool leader = elect_one();
   Tracer tr(p, 2, leader);
   const int G = p.group, ngroups = p.hcb >> 4;
   int s = 0, seen = -1;
   uint32_t ph = 0;
+  StepCursor<FUSED> cur;
   for (int base = w.first_tile; base < w.tiles_padded; base += w.tile_stride) {
-    const GroupPos gp = group_pos(p, w, base);
-    const int slot_c_in = step_slot(p, p.slot_c_in, p.d_c_in, 2, gp.step);
+    const GroupPos gp = cur.at(w, base);
+    const int slot_c_in = step_slot<FUSED>(p, p.slot_c_in, p.d_c_in, 2, gp.step);
     for (int gi = 0; gi < G; ++gi) {
       const int tile = gp.tile0 + gi;
       if (tile >= w.num_tiles) break;
       const ItemCoord c = decode_tile(p, tile);
-      wait_prev_step_warp(p, gp.step, c.b, leader, seen);   // c_{t-1} of this tile comes from the previous step of this launch
+      wait_prev_step_warp<FUSED>(p, gp.step, c.b, seen);   // c_{t-1} of this tile comes from the previous step of this launch
       for (int grp = 0; grp < ngroups; ++grp) {
         tr.stamp();
         mbar_wait(&b.c_empty[s], ph ^ 1);
@@ -346,7 +380,7 @@ __device__ __forceinline__ void fwd_c_loader(const ConvGemmParams& p, uint8_t* s
 }
 
 // kind 0: c slots (warp 3), kind 1: h + gates stages (warp 2)
-template <typename E>
+template <typename E, bool FUSED>
 __device__ __forceinline__ void fwd_storer(const ConvGemmParams& p, uint8_t* sE, const FwdEpiBars& b, const TileWalk& w, int kind) {
   using GE = EpiGeom<E>;
   const bool leader = elect_one();
@@ -357,12 +391,13 @@ __device__ __forceinline__ void fwd_storer(const ConvGemmParams& p, uint8_t* sE,
   uint64_t* empty = kind == 0 ? b.c_empty : b.hg_empty;
   int s = 0;
   uint32_t ph = 0;
-  TileSignal sig;
+  TileSignal<FUSED> sig;
+  StepCursor<FUSED> cur;
   for (int base = w.first_tile; base < w.tiles_padded; base += w.tile_stride) {
-    const GroupPos gp = group_pos(p, w, base);
-    const int slot_c_out = step_slot(p, p.slot_c_out, p.d_c_out, 3, gp.step);
-    const int slot_h_out = step_slot(p, p.slot_h_out, p.d_h_out, 4, gp.step);
-    const int slot_g = step_slot(p, p.slot_g, p.d_g, 31, gp.step);
+    const GroupPos gp = cur.at(w, base);
+    const int slot_c_out = step_slot<FUSED>(p, p.slot_c_out, p.d_c_out, 3, gp.step);
+    const int slot_h_out = step_slot<FUSED>(p, p.slot_h_out, p.d_h_out, 4, gp.step);
+    const int slot_g = step_slot<FUSED>(p, p.slot_g, p.d_g, 31, gp.step);
     for (int gi = 0; gi < G; ++gi) {
       const int tile = gp.tile0 + gi;
       if (tile >= w.num_tiles) break;
@@ -399,12 +434,12 @@ __device__ __forceinline__ void fwd_storer(const ConvGemmParams& p, uint8_t* sE,
       }
       if (leader) sig.tile_done(p, gp.step, c.b, (p.debug_flags & 1) ? 0 : ngroups);
     }
-    if (leader && last_group_of_step(p, w, base, gp.step)) sig.flush(p);
+    if (leader && cur.last_in_step(w, base)) sig.flush(p);
   }
   if (leader) tma_store_wait_all();   // global writes complete before the CTA exits
 }
 
-template <typename E>
+template <typename E, bool FUSED>
 __device__ __forceinline__ void fwd_math(const ConvGemmParams& p, int warp, int lane, uint32_t tmem_base, uint8_t* sE,
                                          const FwdEpiBars& b, uint64_t* tfull_bar, uint64_t* tempty_bar,
                                          const float* s_bias, const TileWalk& w, uint32_t tempty_remote) {
@@ -421,9 +456,10 @@ __device__ __forceinline__ void fwd_math(const ConvGemmParams& p, int warp, int 
   uint32_t cph = 0, hph = 0;
   int abuf = 0;
   uint32_t aphase = 0;
+  StepCursor<FUSED> cur;
   for (int base = w.first_tile; base < w.tiles_padded; base += w.tile_stride) {
     bool waited = false;
-    const GroupPos gp = group_pos(p, w, base);
+    const GroupPos gp = cur.at(w, base);
     for (int gi = 0; gi < G; ++gi) {
       const int tile = gp.tile0 + gi;
       if (tile >= w.num_tiles) break;
@@ -522,7 +558,7 @@ __device__ __forceinline__ void fwd_math(const ConvGemmParams& p, int warp, int 
 
 // ------------------------------------------------------------------------------------ loader
 // handles the channel groups whose running index n satisfies n % nwhich == which
-template <typename E, int EPI>
+template <typename E, int EPI, bool FUSED>
 __device__ __forceinline__ void epi_loader(const ConvGemmParams& p, uint8_t* sE, uint64_t* e_full, uint64_t* e_empty,
                                            const TileWalk& w, int which, int nwhich) {
   using GE = EpiGeom<E>;
@@ -532,15 +568,16 @@ __device__ __forceinline__ void epi_loader(const ConvGemmParams& p, uint8_t* sE,
   const int ngroups = epi_groups<EPI>(p);
   int s = 0, n = 0, seen = -1;
   uint32_t ph = 0;
+  StepCursor<FUSED> cur;
   for (int base = w.first_tile; base < w.tiles_padded; base += w.tile_stride) {
-    const GroupPos gp = group_pos(p, w, base);
-    const int slot_g = step_slot(p, p.slot_g, p.d_g, 31, gp.step);
-    const int slot_c_prev = gp.step == p.c_prev_none_step ? -1 : step_slot(p, p.slot_c_prev, p.d_c_prev, 31, gp.step);
+    const GroupPos gp = cur.at(w, base);
+    const int slot_g = step_slot<FUSED>(p, p.slot_g, p.d_g, 31, gp.step);
+    const int slot_c_prev = (FUSED && gp.step == p.c_prev_none_step) ? -1 : step_slot<FUSED>(p, p.slot_c_prev, p.d_c_prev, 31, gp.step);
     for (int gi = 0; gi < G; ++gi) {
       const int tile = gp.tile0 + gi;
       if (tile >= w.num_tiles) break;
       const ItemCoord c = decode_tile(p, tile);
-      wait_prev_step_warp(p, gp.step, c.b, leader, seen);   // the running dc of this tile comes from the previous step of this launch
+      wait_prev_step_warp<FUSED>(p, gp.step, c.b, seen);   // the running dc of this tile comes from the previous step of this launch
       for (int grp = 0; grp < ngroups; ++grp, ++n) {
         const bool mine = (nwhich == 1) || ((n % nwhich) == which);
         if (mine) tr.stamp();
@@ -572,7 +609,7 @@ __device__ __forceinline__ void epi_loader(const ConvGemmParams& p, uint8_t* sE,
 
 // ------------------------------------------------------------------------------------ storer
 // handles the channel groups whose running index n satisfies n % nwhich == which
-template <typename E, int EPI>
+template <typename E, int EPI, bool FUSED>
 __device__ __forceinline__ void epi_storer(const ConvGemmParams& p, uint8_t* sE, uint64_t* st_ready, uint64_t* e_empty,
                                            const TileWalk& w, int which, int nwhich) {
   using GE = EpiGeom<E>;
@@ -582,10 +619,11 @@ __device__ __forceinline__ void epi_storer(const ConvGemmParams& p, uint8_t* sE,
   const int ngroups = epi_groups<EPI>(p);
   int s = 0, n = 0;
   uint32_t ph = 0;
-  TileSignal sig;
+  TileSignal<FUSED> sig;
+  StepCursor<FUSED> cur;
   for (int base = w.first_tile; base < w.tiles_padded; base += w.tile_stride) {
-    const GroupPos gp = group_pos(p, w, base);
-    const int slot_g = step_slot(p, p.slot_g, p.d_g, 31, gp.step);
+    const GroupPos gp = cur.at(w, base);
+    const int slot_g = step_slot<FUSED>(p, p.slot_g, p.d_g, 31, gp.step);
     for (int gi = 0; gi < G; ++gi) {
       const int tile = gp.tile0 + gi;
       if (tile >= w.num_tiles) break;
@@ -618,7 +656,7 @@ __device__ __forceinline__ void epi_storer(const ConvGemmParams& p, uint8_t* sE,
       }
       if (leader) sig.tile_done(p, gp.step, c.b, committed);
     }
-    if (leader && last_group_of_step(p, w, base, gp.step)) sig.flush(p);
+    if (leader && cur.last_in_step(w, base)) sig.flush(p);
   }
   if (leader) tma_store_wait_all();   // global writes complete before the CTA exits
 }
@@ -626,7 +664,7 @@ __device__ __forceinline__ void epi_storer(const ConvGemmParams& p, uint8_t* sE,
 // ------------------------------------------------------------------------------------ math (warps 8..15)
 // TMEM lane quadrant = warp % 4 (hardware rule); the two warps of a quadrant take the two 8-channel halves
 // of the 16-channel group.  `tempty_remote`: CTA-pair mode, shared::cluster address of the leader's tempty_bar[0].
-template <typename E, int EPI>
+template <typename E, int EPI, bool FUSED>
 __device__ __forceinline__ void epi_math(const ConvGemmParams& p, int warp, int lane, uint32_t tmem_base, uint8_t* sE,
                                          uint64_t* e_full, uint64_t* st_ready, uint64_t* tfull_bar, uint64_t* tempty_bar,
                                          const float* s_bias, const float* s_headw, const TileWalk& w,
@@ -645,10 +683,11 @@ __device__ __forceinline__ void epi_math(const ConvGemmParams& p, int warp, int 
   uint32_t ph = 0;
   int abuf = 0;
   uint32_t aphase = 0;
+  StepCursor<FUSED> cur;
   for (int base = w.first_tile; base < w.tiles_padded; base += w.tile_stride) {
     bool waited = (p.nseg == 0);
-    const GroupPos gp = group_pos(p, w, base);
-    const bool have_c_prev = p.slot_c_prev >= 0 && gp.step != p.c_prev_none_step;
+    const GroupPos gp = cur.at(w, base);
+    const bool have_c_prev = p.slot_c_prev >= 0 && !(FUSED && gp.step == p.c_prev_none_step);
     for (int gi = 0; gi < G; ++gi) {
       const int tile = gp.tile0 + gi;
       if (tile >= w.num_tiles) break;
@@ -660,7 +699,7 @@ __device__ __forceinline__ void epi_math(const ConvGemmParams& p, int warp, int 
         if (p.head_dpred) {
           const int y = c.y0 + (row >> 3), x = c.x0 + (row & 7);
           if (y < p.H && x < p.W)
-            dpred = p.head_dpred[gp.step * p.head_dpred_sstride + c.b * p.head_dpred_bstride + static_cast<long long>(y) * p.W + x];
+            dpred = p.head_dpred[(FUSED ? gp.step * p.head_dpred_sstride : 0) + c.b * p.head_dpred_bstride + static_cast<long long>(y) * p.W + x];
         }
       }
       for (int grp = 0; grp < ngroups; ++grp) {
