@@ -405,15 +405,12 @@ inline void set_batch_range(const nint_plan* p, ConvGemmParams& g, int b0, int n
   g.B = nb > 0 ? nb : p->B;
 }
 
-// one fused cell step of layer l at time t (model.py:216-231) for images [b0, b0 + nb); n_steps > 1: steps t .. t+n_steps-1
-// as ONE time-fused launch (all of them must have a recurrent state: t >= 1, or an explicit initial state)
-int cell_step(nint_plan* p, int l, int t, int epi, float* raw_out, cudaStream_t st, int b0 = 0, int nb = 0, int n_steps = 1) {
+// step-independent launch parameters of layer l's gate convolution (have_state: with the h_{t-1} K segment)
+int fwd_conv_params(nint_plan* p, int l, bool have_state, int epi, ConvGemmParams& g) {
   Layer& y = p->layer[l];
   const bool tr = p->cfg.training != 0;
-  const bool have_state = !(t == 0 && p->zero_init);
   const bool bank = l == 0 && p->x_bank;
   Layer::CachedConv* cache = epi == EPI_FWD ? &y.fwd_cache[have_state ? 1 : 0][bank ? 1 : 0] : nullptr;
-  ConvGemmParams g;
   if (cache && cache->valid) {
     g = cache->g;
   } else {
@@ -445,6 +442,18 @@ int cell_step(nint_plan* p, int l, int t, int epi, float* raw_out, cudaStream_t 
       if (get_w_map(p, y, g.seg[i].wsel, g.n_tile, g.n_tile / g.cluster, g.seg[i].ts, &g.seg[i].tmap_w)) return 1;
     if (cache) { cache->g = g; cache->valid = true; }
   }
+  return 0;
+}
+
+// one fused cell step of layer l at time t (model.py:216-231) for images [b0, b0 + nb); n_steps > 1: steps t .. t+n_steps-1
+// as ONE time-fused launch (all of them must have a recurrent state: t >= 1, or an explicit initial state)
+int cell_step(nint_plan* p, int l, int t, int epi, float* raw_out, cudaStream_t st, int b0 = 0, int nb = 0, int n_steps = 1) {
+  Layer& y = p->layer[l];
+  const bool tr = p->cfg.training != 0;
+  const bool have_state = !(t == 0 && p->zero_init);
+  const bool bank = l == 0 && p->x_bank;
+  ConvGemmParams g;
+  if (fwd_conv_params(p, l, have_state, epi, g)) return 1;
   // ---- what changes from step to step: slots, batch range, bank indices
   const int in_slot_h = tr ? t : (t & 1);
   const int out_slot_h = tr ? t + 1 : ((t + 1) & 1);
@@ -1008,6 +1017,25 @@ static int check_ready(nint_plan* p) {
   return 0;
 }
 
+// Time-fused forward launch of layer l?  NINT_FUSE_STEPS bit 0 forces it, 0 forbids it.  Automatic: only for short
+// launches -- at most 8 rounds of tile groups per cluster and step (the narrow upper layers of the reference's recipe:
+// 7.6 rounds, ~30 us launches); at 11.7 rounds (cfg 2, B=8) the fused forward already loses to one launch per step.
+static int fwd_should_fuse(nint_plan* p, int l, bool* fuse) {
+  *fuse = false;
+  if (p->fuse_steps == 0) return 0;
+  if (p->fuse_steps > 0) {
+    *fuse = (p->fuse_steps & 1) != 0;
+    return 0;
+  }
+  ConvGemmParams g;
+  if (fwd_conv_params(p, l, true, EPI_FWD, g)) return 1;
+  const int per_group = g.cluster * g.group;
+  const double groups = (static_cast<double>(p->B) * p->tiles_x * p->tiles_y + per_group - 1) / per_group;
+  const int clusters = p->num_sms / (g.cluster * g.n_blocks);
+  *fuse = clusters > 0 && groups / clusters <= 8.0;
+  return 0;
+}
+
 // the T x L fused cell steps + head of ConvLSTM.forward once the input is in place (X packed, or the bank attached)
 static int forward_steps(nint_plan* p, float* pred, float* seq, cudaStream_t st) {
   const bool tr = p->cfg.training != 0;
@@ -1015,19 +1043,27 @@ static int forward_steps(nint_plan* p, float* pred, float* seq, cudaStream_t st)
   const Layer& top = p->layer[p->L - 1];
   const size_t top_img = static_cast<size_t>(HW) * top.hc_pad * p->esize;   // bytes of one image of the top layer's h
   const int SB = p->sub_batch > 0 ? p->sub_batch : p->B;
-  // time-fused schedule: layer by layer, all steps of a layer in ONE persistent launch (after the step that starts
+  // time-fused schedule: layer by layer, all steps of a fused layer in ONE persistent launch (after the step that starts
   // from the zero state, whose GEMM has no h segment).  Layer-major order needs the whole h history of the layer
   // below, which a training plan keeps; an inference plan keeps two slots, so only a single layer fuses there
-  if (p->fuse_steps > 0 && (p->fuse_steps & 1) && SB >= p->B && p->T > 1 && (tr || (p->L == 1 && !seq))) {
+  bool fuse_l[NINT_MAX_LAYERS];
+  bool any_fused = false;
+  for (int l = 0; l < p->L; ++l) {
+    fuse_l[l] = false;
+    if (SB >= p->B && p->T > 1 && (tr || (p->L == 1 && !seq)) && fwd_should_fuse(p, l, &fuse_l[l])) return 1;
+    any_fused = any_fused || fuse_l[l];
+  }
+  if (any_fused) {
     for (int l = 0; l < p->L; ++l) {          // model.py:267
       int t = 0;
-      if (p->zero_init) {
+      if (p->zero_init || !fuse_l[l]) {
         if (cell_step(p, l, 0, EPI_FWD, nullptr, st)) return 1;
         t = 1;
       }
-      if (p->T - t == 1) {
-        if (cell_step(p, l, t, EPI_FWD, nullptr, st)) return 1;
-      } else if (cell_step(p, l, t, EPI_FWD, nullptr, st, 0, 0, p->T - t)) return 1;   // model.py:265
+      if (!fuse_l[l] || p->T - t == 1) {
+        for (; t < p->T; ++t)                 // model.py:265
+          if (cell_step(p, l, t, EPI_FWD, nullptr, st)) return 1;
+      } else if (cell_step(p, l, t, EPI_FWD, nullptr, st, 0, 0, p->T - t)) return 1;
     }
     if (seq)
       for (int t = 0; t < p->T; ++t)          // model.py:272 (commented variant)
