@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--shipped", action="store_true", help="the reference's recipe: 5 -> 64/32/16, k 5/3/3, 100x154, T=48, B=8, crop")
     ap.add_argument("--bank", action="store_true")
     ap.add_argument("--graph", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="afterwards: 5 more steps with per-launch events, time per kernel class")
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     B, T, C, H, W = a.batch, a.seq_len, 21, 90, 144
@@ -62,6 +63,15 @@ def main():
     ms = e0.elapsed_time(e1) / a.steps
     print(f"pdl={os.environ.get('NINT_PDL', '1')} bank={int(a.bank)} graph={int(a.graph)} shipped={int(a.shipped)} B={B} T={T} k{a.ksize}: "
           f"{ms:.3f} ms/step, {B / ms * 1e3:.0f} samples/s over {a.steps} steps, loss {float(loss):.4f}", flush=True)
+    if a.profile and not a.bank:
+        plan = net.plan_for(x, True)
+        plan.profile(True)
+        for _ in range(5):
+            step()
+        torch.cuda.synchronize()
+        prof = plan.profile_read()
+        plan.profile(False)
+        print("   per step: " + ", ".join(f"{k} {v[0] / 5:.3f} ms ({v[1] // 5} steps/launches)" for k, v in prof.items()), flush=True)
 
 
 if __name__ == "__main__":
