@@ -759,8 +759,10 @@ static cudaError_t launch_h(const ConvGemmParams& p, int num_sms, cudaStream_t s
   if (FUSED) {
     // CTAs of a time-fused launch wait for each other's tiles: every one of them must be resident at once
     static int max_units = -1;   // co-resident CTAs (single) / clusters (pair) of this instantiation at this smem size
-    static int max_units_smem = -1;
-    if (max_units < 0 || max_units_smem != smem) {
+    static int max_units_smem = -1, max_units_dev = -1;   // ... on this device
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess) return cudaErrorInvalidDevice;
+    if (max_units < 0 || max_units_smem != smem || max_units_dev != dev) {
       int n = 0;
       cudaError_t e;
       if (PAIR) {
@@ -775,6 +777,7 @@ static cudaError_t launch_h(const ConvGemmParams& p, int num_sms, cudaStream_t s
       if (e != cudaSuccess) return e;
       max_units = n;
       max_units_smem = smem;
+      max_units_dev = dev;
     }
     if (cpn * p.n_blocks > max_units) cpn = max_units / p.n_blocks;
     if (cpn <= 0) return cudaErrorInvalidConfiguration;
