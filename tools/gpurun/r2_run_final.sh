@@ -1,6 +1,6 @@
 #!/bin/bash
 # last check of the committed tree: smoke(), the whole GPU suite, the default bench line
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
 timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -2
