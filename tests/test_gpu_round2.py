@@ -457,6 +457,31 @@ def test_time_fused_launches_change_nothing(monkeypatch, hidden, ks, precision, 
         torch.backends.cudnn.deterministic = prev
 
 
+def test_time_fused_rule_follows_the_launch_length(monkeypatch):
+    """default schedule: a layer's BPTT steps are ONE launch (after the step without a dgates_{t+1} operand) while a
+    CTA pair walks at most 5 tile groups per step, one launch per step for long launches such as BASELINE cfg 2 at
+    B=32; NINT_FUSE_STEPS=0 forbids fusing (counted through nint_launch_count, class 1 = dgrad + gate backward)"""
+    from nasa_niswan_b200 import ConvLSTM, _lib
+    lib = _lib.load()
+
+    def bwd_launches(B, T, H, W, env):
+        if env is None:
+            monkeypatch.delenv("NINT_FUSE_STEPS", raising=False)
+        else:
+            monkeypatch.setenv("NINT_FUSE_STEPS", env)
+        torch.manual_seed(0)
+        net = ConvLSTM(21, [64], [3], 1, precision="bf16").cuda()
+        pred = net(torch.randn(B, T, 21, H, W, device="cuda"))
+        n0 = lib.nint_launch_count(1)
+        pred.sum().backward()
+        torch.cuda.synchronize()
+        return lib.nint_launch_count(1) - n0
+    assert bwd_launches(2, 6, 24, 24, None) == 2          # 2 images of 2 x 3 tiles: short launches, fused
+    assert bwd_launches(2, 6, 24, 24, "0") == 6
+    assert bwd_launches(32, 3, 90, 144, None) == 3        # 11.7 rounds of tile groups per CTA pair: one launch per step
+    assert bwd_launches(32, 3, 90, 144, "2") == 2
+
+
 def test_training_step_replays_as_one_cuda_graph():
     """the native step (forward, fused loss, BPTT, wgrad, Adam with its step count and lr in device memory) captured
     once and replayed: same parameters as the eager steps, including across a learning-rate change"""
