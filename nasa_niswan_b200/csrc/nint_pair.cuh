@@ -111,31 +111,6 @@ __device__ __forceinline__ void umma_lohi(uint32_t d_tmem, uint32_t alo, uint32_
 #undef NINT_UMMA_LOHI
 }
 
-// The same with a collector hint for the A operand: MODE 1 = fill (keep A in the tensor core's collector buffer after
-// this MMA), 2 = use (take A from the collector, keep it), 3 = lastuse (take it, then release it).  Consecutive MMAs that
-// share their A descriptor -- wgrad's tap loop: one dgates panel against every tap's shifted view of the input -- then
-// read the 4 KB A tile from shared memory once instead of once per tap.  CTA-pair form only.
-template <int DTYPE, int MODE>
-__device__ __forceinline__ void umma_lohi_keep_a(uint32_t d_tmem, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi,
-                                                 uint32_t idesc, uint32_t accumulate) {
-#define NINT_UMMA_COLL(KIND, COLL)                                                                          \
-  asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 ad, bd;\n\tsetp.ne.b32 p, %6, 0;\n\t"                       \
-               "mov.b64 ad, {%1, %2};\n\tmov.b64 bd, {%3, %4};\n\t"                                        \
-               "tcgen05.mma.cta_group::2.kind::" KIND ".collector::a::" COLL " [%0], ad, bd, %5, p;\n\t}" ::"r"(d_tmem), \
-               "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(accumulate)                          \
-               : "memory")
-  if constexpr (DTYPE == NINT_BF16) {
-    if constexpr (MODE == 1) NINT_UMMA_COLL("f16", "fill");
-    else if constexpr (MODE == 2) NINT_UMMA_COLL("f16", "use");
-    else NINT_UMMA_COLL("f16", "lastuse");
-  } else {
-    if constexpr (MODE == 1) NINT_UMMA_COLL("tf32", "fill");
-    else if constexpr (MODE == 2) NINT_UMMA_COLL("tf32", "use");
-    else NINT_UMMA_COLL("tf32", "lastuse");
-  }
-#undef NINT_UMMA_COLL
-}
-
 // ---- "elected" variants: every lane of the (converged) warp executes the call, the instruction itself is
 // predicated on elect.sync inside the asm block.  The surrounding C++ then has no divergent branch, which lets
 // ptxas keep descriptors / addresses in uniform registers (a lane-predicated branch around tcgen05.mma cost ~8

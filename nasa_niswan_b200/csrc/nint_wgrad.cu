@@ -542,9 +542,9 @@ wgrad_pair_kernel(const __grid_constant__ WgradParams p) {
       const uint32_t ncols = static_cast<uint32_t>(p.acc_cols);
       const int ksize = p.ksize;
       const bool issue_any = !(p.debug_flags & 2);
-      // A-collector reuse across the taps of a K step: measured SLOWER (wgrad 2.08 -> 2.30 ms on the same box: the
-      // MMAs of a K step serialise on the collector), so it is an experiment knob only (NINT_DEBUG_FLAGS bit 10)
-      const bool keep_a = ntaps >= 2 && (p.debug_flags & 1024);
+      // (A-collector reuse across the taps of a K step -- tcgen05.mma .collector::a::fill / use / lastuse -- was tried and
+      // is slower: the MMAs of a K step serialise on the collector.  Even as a run-time knob it cost this loop ~10 %,
+      // so the code is gone: DESIGN.md section 6.)
       // MN-major descriptors.  A: 64-q atoms (128-byte rows, SWIZZLE_128B) one panel apart, 8-pixel groups 1 KiB apart.
       // B: pw-channel atoms (32 / 64 / 128-byte rows, matching swizzle) one panel apart, 8-pixel groups one halo row apart.
       const uint64_t adesc_base = make_smem_desc(0, kWgPairAPanel, BF ? 1024u : 512u, BF ? 2u : kLayoutSw128Base32);
@@ -585,32 +585,14 @@ wgrad_pair_kernel(const __grid_constant__ WgradParams p) {
               const uint32_t alo = a0 + static_cast<uint32_t>(ks) * A_KSTEP16;
               const uint32_t bk = b0 + static_cast<uint32_t>(ks) * krow16;
               uint32_t d = tmem_base;
-              if (keep_a) {
-                // every tap of this K step multiplies the SAME dgates panel: keep it in the A collector (one 4 KB
-                // shared-memory read per K step instead of one per tap)
-                const bool bias_mma = BF && do_bias;
 #pragma unroll
-                for (int ti = 0; ti < 5; ++ti) {
-                  if (ti < ntaps) {
-                    if (ti == 0) umma_lohi_keep_a<DT, 1>(d, alo, ahi, bk + tap_off[ti], bhi, idesc, acc);
-                    else if (ti == ntaps - 1 && !bias_mma) umma_lohi_keep_a<DT, 3>(d, alo, ahi, bk + tap_off[ti], bhi, idesc, acc);
-                    else umma_lohi_keep_a<DT, 2>(d, alo, ahi, bk + tap_off[ti], bhi, idesc, acc);
-                  }
-                  d += ncols;
-                }
-                if (bias_mma)
-                  umma_lohi_keep_a<DT, 3>(tmem_base + static_cast<uint32_t>(ntaps) * ncols, alo, ahi,
-                                          static_cast<uint32_t>(odesc), static_cast<uint32_t>(odesc >> 32), idesc_bias, acc);
-              } else {
-#pragma unroll
-                for (int ti = 0; ti < 5; ++ti) {
-                  if (ti < ntaps) umma_lohi<DT, true>(d, alo, ahi, bk + tap_off[ti], bhi, idesc, acc);
-                  d += ncols;
-                }
-                if (BF && do_bias)
-                  umma_lohi<DT, true>(tmem_base + static_cast<uint32_t>(ntaps) * ncols, alo, ahi,
-                                             static_cast<uint32_t>(odesc), static_cast<uint32_t>(odesc >> 32), idesc_bias, acc);
+              for (int ti = 0; ti < 5; ++ti) {
+                if (ti < ntaps) umma_lohi<DT, true>(d, alo, ahi, bk + tap_off[ti], bhi, idesc, acc);
+                d += ncols;
               }
+              if (BF && do_bias)
+                umma_lohi<DT, true>(tmem_base + static_cast<uint32_t>(ntaps) * ncols, alo, ahi,
+                                           static_cast<uint32_t>(odesc), static_cast<uint32_t>(odesc >> 32), idesc_bias, acc);
               acc = 1;
             }
           } else {
