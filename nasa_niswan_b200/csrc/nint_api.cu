@@ -743,6 +743,13 @@ int nint_plan_create(const nint_config* cfg, nint_plan** out) {
     if (p->cluster != 1 && p->cluster != 2) p->cluster = 1;
     const char* d = getenv("NINT_DEBUG_FLAGS");
     p->debug_flags = d ? atoi(d) : 0;
+    // bits other than 512 (host side: no bias folding) are kernel experiment knobs, compiled in only with -DNINT_KNOBS=1
+    if (!NINT_KNOBS && (p->debug_flags & ~512)) {
+      const int flags = p->debug_flags;
+      delete p;
+      return fail("NINT_DEBUG_FLAGS=%d needs the experiment build of the library (python -m nasa_niswan_b200.build --knobs, "
+                  "then NINT_LIB=<...>/libnint_knobs.so): the product build compiles the kernel knobs out", flags);
+    }
     const char* pg = getenv("NINT_PLAN_G");
     p->plan_g = pg ? atoi(pg) : 0;
     const char* pn = getenv("NINT_PLAN_NS");

@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
     chunks_per_tile += p.seg[s].nchunks;
     all_k3 = all_k3 && p.seg[s].ksize == 3;
   }
-  const bool dual = EPI == EPI_FWD && resident && G == 1 && all_k3 && TS == 9 && NA >= 4 && !(p.debug_flags & 32);
+  const bool dual = EPI == EPI_FWD && resident && G == 1 && all_k3 && TS == 9 && NA >= 4 && !(NINT_DBG(p) & 32);
   volatile uint32_t* mma_started = reinterpret_cast<volatile uint32_t*>(ctrl + kHaloCtrlBytes - 32);
 
   if (warp == 0 && lane == 0) {
@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
   auto issue_dual = [&](int which) {
     const bool leader = elect_one();
     Tracer tr(p, 1, leader && which == 0);
-    const bool issue_any = !(p.debug_flags & 2);
+    const bool issue_any = !(NINT_DBG(p) & 2);
     const int n_acc = p.n_acc, acc_cols = p.acc_cols, a_buf_bytes = p.a_buf_bytes;
     const uint32_t idesc = p.idesc;
     const uint32_t w16l = static_cast<uint32_t>(w_bytes >> 4);
@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
     } else if (p.nseg > 0 && lead_cta) {
       const bool leader = elect_one();
       Tracer tr(p, 1, leader);
-      const bool issue_any = !(p.debug_flags & 2);
+      const bool issue_any = !(NINT_DBG(p) & 2);
       const int n_acc = p.n_acc, acc_cols = p.acc_cols, nseg = p.nseg, a_buf_bytes = p.a_buf_bytes;
       const uint32_t idesc = p.idesc;
       const uint32_t n_tile = static_cast<uint32_t>(p.n_tile);
@@ -399,7 +399,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
         if constexpr (FUSED) {
           if (last_of_tile) {
             while (cbase >= step_hi) step_hi += walk.tiles_step;   // step_hi: end of the step cbase lies in
-            cross = nvalid && (nbase >= step_hi || (p.debug_flags & 4096));
+            cross = nvalid && (nbase >= step_hi || (NINT_DBG(p) & 4096));
           }
         }
         const bool look = lookahead && !cross;

@@ -33,7 +33,7 @@ struct Tracer {
   long long* dst;
   int n;
   __device__ __forceinline__ Tracer(const ConvGemmParams& p, int role, bool on) {
-    dst = (on && (p.debug_flags & 8) && blockIdx.x == 0) ? g_trace + role * kTraceLen : nullptr;
+    dst = (on && (NINT_DBG(p) & 8) && blockIdx.x == 0) ? g_trace + role * kTraceLen : nullptr;
     n = 0;
   }
   __device__ __forceinline__ void stamp() {
@@ -126,7 +126,7 @@ __device__ __forceinline__ void wait_prev_step(const ConvGemmParams& p, int step
   unsigned v;
   long long t0 = 0;
   unsigned spins = 0;
-  const bool diag = (p.debug_flags & 2048) != 0;
+  const bool diag = (NINT_DBG(p) & 2048) != 0;
   for (;;) {
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
     if (v >= p.step_target) break;
@@ -407,7 +407,7 @@ __device__ __forceinline__ void fwd_storer(const ConvGemmParams& p, uint8_t* sE,
         mbar_wait(&ready[s], ph);
         tr.stamp();
         if (leader) {
-          if (!(p.debug_flags & 1)) {
+          if (!(NINT_DBG(p) & 1)) {
             const int ch = w.nb * p.hcb + grp * 16;
             if (kind == 0) {
               tma_store_5d(&p.tm_c, fwd_c_slot(p, sE, s), ch, c.x0, c.y0, c.b, slot_c_out);
@@ -432,7 +432,7 @@ __device__ __forceinline__ void fwd_storer(const ConvGemmParams& p, uint8_t* sE,
           ph ^= 1;
         }
       }
-      if (leader) sig.tile_done(p, gp.step, c.b, (p.debug_flags & 1) ? 0 : ngroups);
+      if (leader) sig.tile_done(p, gp.step, c.b, (NINT_DBG(p) & 1) ? 0 : ngroups);
     }
     if (leader && cur.last_in_step(w, base)) sig.flush(p);
   }
@@ -450,7 +450,7 @@ __device__ __forceinline__ void fwd_math(const ConvGemmParams& p, int warp, int 
   const int quad = warp & 3;
   const int half = (warp - kConvIoWarps) >> 2;
   const int row = quad * 32 + lane;
-  const bool skip = (p.debug_flags & 1) != 0;
+  const bool skip = (NINT_DBG(p) & 1) != 0;
   Tracer tr(p, 4, warp == kConvIoWarps && lane == 0);
   int cs = 0, hs = 0;
   uint32_t cph = 0, hph = 0;
@@ -631,13 +631,13 @@ __device__ __forceinline__ void epi_storer(const ConvGemmParams& p, uint8_t* sE,
       int committed = 0;   // bulk groups this warp commits for this tile
       for (int grp = 0; grp < ngroups; ++grp, ++n) {
         const bool mine = (nwhich == 1) || ((n % nwhich) == which);
-        if (mine && !(p.debug_flags & 1)) ++committed;
+        if (mine && !(NINT_DBG(p) & 1)) ++committed;
         if (mine) tr.stamp();
         if (mine) mbar_wait(&st_ready[s], ph);
         if (mine) tr.stamp();
         if (mine && leader) {
           const uint8_t* st = sE + s * p.e_stage_bytes;
-          if (!(p.debug_flags & 1)) {
+          if (!(NINT_DBG(p) & 1)) {
             const int q0 = group_q0(grp * 16);
 #pragma unroll
             for (int bx = 0; bx < GE::kGateBoxes; ++bx)
@@ -677,7 +677,7 @@ __device__ __forceinline__ void epi_math(const ConvGemmParams& p, int warp, int 
   const int quad = warp & 3;
   const int half = (warp - kConvIoWarps) >> 2;
   const int row = quad * 32 + lane;
-  const bool skip = (p.debug_flags & 1) != 0;
+  const bool skip = (NINT_DBG(p) & 1) != 0;
   Tracer tr(p, 4, warp == kConvIoWarps && lane == 0);
   int s = 0;
   uint32_t ph = 0;

@@ -15,6 +15,15 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// Experiment knobs (ConvGemmParams / WgradParams::debug_flags: skip the epilogue's memory work, issue no MMAs, issue them
+// twice, timeline stamps, ...) are compiled in only with -DNINT_KNOBS=1 (`python -m nasa_niswan_b200.build --knobs` ->
+// libnint_knobs.so, selected with NINT_LIB).  In the product build the flags read as 0 at compile time: a run-time
+// branch inside the single-thread MMA loops costs the default path dearly (-12 % for one).
+#ifndef NINT_KNOBS
+#define NINT_KNOBS 0
+#endif
+#define NINT_DBG(p) (NINT_KNOBS ? (p).debug_flags : 0)
+
 namespace nint {
 
 enum : int { EPI_FWD = 0, EPI_BWD = 1, EPI_RAW = 2 };

@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
           const uint32_t sbo_b = (DT == NINT_BF16) ? static_cast<uint32_t>(hpitch * ROWB) : 512u;
           const uint64_t bdesc0 = make_smem_desc(smem_u32(sB + bs * b_stage_bytes), p.b_panel_bytes, sbo_b, LAYOUT);
           if (leader) {
-            const int reps = (p.debug_flags & 2) ? 0 : ((p.debug_flags & 4) ? 2 : 1);
+            const int reps = (NINT_DBG(p) & 2) ? 0 : ((NINT_DBG(p) & 4) ? 2 : 1);
             for (int rep = 0; rep < reps; ++rep)
 #pragma unroll 1
             for (int ks = 0; ks < KSTEPS; ++ks) {
@@ -541,7 +541,7 @@ wgrad_pair_kernel(const __grid_constant__ WgradParams p) {
       const uint32_t idesc = p.idesc, idesc_bias = p.idesc_bias;
       const uint32_t ncols = static_cast<uint32_t>(p.acc_cols);
       const int ksize = p.ksize;
-      const bool issue_any = !(p.debug_flags & 2);
+      const bool issue_any = !(NINT_DBG(p) & 2);
       // (A-collector reuse across the taps of a K step -- tcgen05.mma .collector::a::fill / use / lastuse -- was tried and
       // is slower: the MMAs of a K step serialise on the collector.  Even as a run-time knob it cost this loop ~10 %,
       // so the code is gone: DESIGN.md section 6.)
@@ -575,7 +575,7 @@ wgrad_pair_kernel(const __grid_constant__ WgradParams p) {
           const uint32_t a0 = alo_base + sA16 + static_cast<uint32_t>((ab * a_buf_bytes) >> 4);
           const uint32_t b0 = blo_base + sB16 + static_cast<uint32_t>((bs * b_stage_bytes) >> 4);
           uint32_t acc = i != 0 ? 1u : 0u;
-          const int reps = (p.debug_flags & 4) ? 2 : 1;   // experiment: issue every tile's MMA stream twice
+          const int reps = (NINT_DBG(p) & 4) ? 2 : 1;   // experiment: issue every tile's MMA stream twice
           for (int rep = 0; rep < reps; ++rep)
           if (ntaps <= 5) {
             // per-tap B offsets are loop invariants: the MMA stream is adds + tcgen05.mma only

@@ -1,5 +1,5 @@
 #!/bin/bash
-# same-box A/B of two builds of the library (NINT_LIB): libnint_prev.so (wgrad with the collector knob compiled in) vs libnint.so
+# same-box A/B of two builds of the library (NINT_LIB): libnint_prev.so vs libnint.so
 cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 show() { python - "$1" "$2" <<'PY'
@@ -13,4 +13,6 @@ for rep in 1 2 3; do
   NINT_LIB=$PWD/nasa_niswan_b200/libnint_prev.so timeout 300 python bench.py --no-extras --steps 20 --warmup 5 > gpurun_out/wg_prev.json 2> gpurun_out/wg_prev.err; show prev gpurun_out/wg_prev.json
   timeout 300 python bench.py --no-extras --steps 20 --warmup 5 > gpurun_out/wg_new.json 2> gpurun_out/wg_new.err; show new gpurun_out/wg_new.json
 done
-timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -x 2>&1 | tail -2
+timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_round2.py -m gpu -q -x 2>&1 | tail -2
+NINT_DEBUG_FLAGS=8 timeout 200 python tools/trace_report.py bwd 2>&1 | grep "steady" | head -3
+NINT_DEBUG_FLAGS=2 timeout 100 python bench.py --no-extras --steps 3 --warmup 1 2>&1 | tail -1 | cut -c1-200
