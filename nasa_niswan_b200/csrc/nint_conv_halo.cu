@@ -190,12 +190,18 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
     StepCursor<FUSED> cur;
     for (int base = walk.first_tile; base < walk.tiles_padded; base += walk.tile_stride) {
       const GroupPos gp = cur.at(walk, base);
+      // tiles [g_begin, g_end) of the group are this warp's; the first one is decoded once per group (two divisions),
+      // the following ones by stepping the coordinates (next_tile): nothing but adds in front of the TMA issue
+      const int g_begin = by_tile ? a_par : 0, g_end = by_tile ? a_par + 1 : G;
+      ItemCoord c_first;
+      c_first.b = c_first.x0 = c_first.y0 = 0;
+      if (do_a) c_first = decode_tile(p, gp.tile0 + g_begin);
       if (FUSED && do_a && gp.step > 0) {
         // time-fused launch: the recurrent operand (h_{t-1} / dgates_{t+1}, with its halo) of these tiles was written by
         // the previous step of THIS launch
-        const int g_begin = by_tile ? a_par : 0, g_end = by_tile ? a_par + 1 : G;
-        for (int g = g_begin; g < g_end; ++g)
-          if (gp.tile0 + g < walk.num_tiles) wait_prev_step_warp<FUSED>(p, gp.step, decode_tile(p, gp.tile0 + g).b, seen);
+        ItemCoord cw = c_first;
+        for (int g = g_begin; g < g_end; ++g, next_tile(p, cw))
+          if (gp.tile0 + g < walk.num_tiles) wait_prev_step_warp<FUSED>(p, gp.step, cw.b, seen);
       }
       for (int s = 0; s < p.nseg; ++s) {
         const ConvSegment& sg = p.seg[s];
@@ -206,7 +212,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
         // weights: 3-D map (element, row of the N tile, chunk-tap index); one box = this CTA's rows of TS taps
         int wtap = (walk.nb * sg.nchunks) * taps;
         for (int ch = 0; ch < sg.nchunks; ++ch, ++cc, wtap += taps) {
-          if (do_a && (a_npar == 1 || by_tile || (cc % a_npar) == a_par)) {
+          if (do_a && (a_npar == 1 || by_tile || (cc & 1) == a_par)) {   // a_npar is 1 or 2
             tr.stamp();
             mbar_wait(&a_empty[ia], pa ^ 1);
             tr.stamp();
@@ -215,9 +221,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
               if (lead_cta && (!by_tile || a_par == 0)) mbar_arrive_expect_tx(&a_full[ia], a_bytes * G * S);
               uint32_t bar = 0;
               if constexpr (pair) bar = mapa_rank(smem_u32(&a_full[ia]), 0);
-              const int g_begin = by_tile ? a_par : 0, g_end = by_tile ? a_par + 1 : G;
-              for (int g = g_begin; g < g_end; ++g) {
-                const ItemCoord cg = decode_tile(p, gp.tile0 + g);
+              ItemCoord cg = c_first;
+              for (int g = g_begin; g < g_end; ++g, next_tile(p, cg)) {
                 uint8_t* dst = sA + ia * p.a_buf_bytes + g * p.a_halo_bytes;
                 int img = cg.b, slot = seg_slot;
                 if (sg.win_start) {   // frame bank: image b of step `slot` is frame win_start[b] + slot (OOB frame = zeros)
@@ -272,12 +277,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
     const uint64_t adesc0 = make_smem_desc_sw64(0, 16, 10 * kChunkBytes);   // 3x3: halo pitch 10 pixels
     const uint64_t bdesc0 = make_smem_desc_sw64(0, 16, 512);
     const uint32_t ahi = static_cast<uint32_t>(adesc0 >> 32), bhi = static_cast<uint32_t>(bdesc0 >> 32);
+    // running indices of chunk c (advanced by two chunks per iteration, no divisions in the loop): tile k of this CTA,
+    // chunk j inside the tile, halo buffer ia / phase pa, accumulator buffer abuf / phase aphase
+    int k = which / cpt, j = which % cpt, ia = which % NA, abuf = k % n_acc;
+    uint32_t pa = static_cast<uint32_t>(which / NA) & 1u, aphase = static_cast<uint32_t>(k / n_acc) & 1u;
     for (int c = which; c < total; c += 2) {
-      const int k = c / cpt, j = c - k * cpt;          // tile of this CTA, chunk inside the tile
-      const int ia = c % NA;
-      const uint32_t pa = static_cast<uint32_t>(c / NA) & 1u;
-      const int abuf = k % n_acc;
-      const uint32_t aphase = static_cast<uint32_t>(k / n_acc) & 1u;
       tr.stamp();
       if (j == 0) mbar_wait(&tempty_bar[abuf], aphase ^ 1);
       mbar_wait(&a_full[ia], pa);
@@ -309,8 +313,22 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_halo_kernel(const __grid
       }
       __syncwarp();
       umma_commit_elect<pair>(&a_empty[ia]);
-      if (c + 2 >= (k + 1) * cpt) umma_commit_elect<pair>(&tfull_bar[abuf]);   // this warp's last chunk of the tile
+      if (j + 2 >= cpt) umma_commit_elect<pair>(&tfull_bar[abuf]);   // this warp's last chunk of the tile
       tr.stamp();
+      j += 2;
+      while (j >= cpt) {
+        j -= cpt;
+        ++k;
+        if (++abuf == n_acc) {
+          abuf = 0;
+          aphase ^= 1;
+        }
+      }
+      ia += 2;
+      if (ia >= NA) {
+        ia -= NA;
+        pa ^= 1;
+      }
     }
   };
 

@@ -55,6 +55,19 @@ __device__ __forceinline__ ItemCoord decode_tile(const ConvGemmParams& p, int ti
   return c;
 }
 
+// the tile after c in walk order (x fastest, then y, then the image)
+__device__ __forceinline__ void next_tile(const ConvGemmParams& p, ItemCoord& c) {
+  c.x0 += p.tile_w;
+  if (c.x0 >= p.tiles_x * p.tile_w) {
+    c.x0 = 0;
+    c.y0 += p.tile_h;
+    if (c.y0 >= p.tiles_y * p.tile_h) {
+      c.y0 = 0;
+      ++c.b;
+    }
+  }
+}
+
 // Work distribution.  The grid is `cpn * n_blocks` clusters (S = 1 or 2 CTAs each).  A cluster owns ONE
 // n-block (N slice of the gate columns: its weights can stay resident in shared memory) and walks pixel-tile
 // groups; the CTAs of a pair take adjacent groups of G tiles.
