@@ -70,6 +70,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// The message of a timed-out wait is a device printf, i.e. a CALL inside a function that is inlined into every hot loop of
+// every kernel; it exists in the experiment build only (-DNINT_KNOBS=1), the product build just traps.
+#if defined(NINT_KNOBS) && NINT_KNOBS
+#define NINT_TIMEOUT_PRINTF(...) printf(__VA_ARGS__)
+#else
+#define NINT_TIMEOUT_PRINTF(...) ((void)0)
+#endif
 // Bounded wait: a protocol bug must trap (error returned to the host), never hang the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
@@ -77,8 +84,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if ((++spins & 0x3ff) == 0 && clock64() - t0 > 4000000000LL) {
-      printf("nint: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", (int)blockIdx.x,
-             (int)threadIdx.x, smem_u32(bar), parity);
+      NINT_TIMEOUT_PRINTF("nint: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", (int)blockIdx.x,
+                          (int)threadIdx.x, smem_u32(bar), parity);
       __trap();
     }
   }
@@ -92,8 +99,8 @@ __device__ __forceinline__ void spin_until_at_least(volatile uint32_t* counter, 
   uint32_t spins = 0;
   while (*counter < value) {
     if ((++spins & 0x3ff) == 0 && clock64() - t0 > 4000000000LL) {
-      printf("nint: progress counter wait timed out (block %d thread %d want %u have %u)\n", (int)blockIdx.x,
-             (int)threadIdx.x, value, *counter);
+      NINT_TIMEOUT_PRINTF("nint: progress counter wait timed out (block %d thread %d want %u have %u)\n", (int)blockIdx.x,
+                          (int)threadIdx.x, value, *counter);
       __trap();
     }
   }
