@@ -1024,9 +1024,10 @@ static int check_ready(nint_plan* p) {
   return 0;
 }
 
-// Time-fused forward launch of layer l?  NINT_FUSE_STEPS bit 0 forces it, 0 forbids it.  Automatic: only for short
-// launches -- at most 8 rounds of tile groups per cluster and step (the narrow upper layers of the reference's recipe:
-// 7.6 rounds, ~30 us launches); at 11.7 rounds (cfg 2, B=8) the fused forward already loses to one launch per step.
+// Time-fused forward launch of layer l?  NINT_FUSE_STEPS bit 0 forces it, 0 forbids it.  Automatic: for launches of at
+// most 16 rounds of tile groups per cluster and step -- all three layers of the reference's recipe (7.6 / 7.6 / 15
+// rounds: -1.3 % on top of the fused BPTT), cfg 2 at B=8 (11.7 rounds: -2 % on average, noisy); at 23 rounds (B=16) the
+// gain is ~2 % and at 47 (B=32) nil, and with PDL the forward runs at its steady-state rate from start to end there.
 static int fwd_should_fuse(nint_plan* p, int l, bool* fuse) {
   *fuse = false;
   if (p->fuse_steps == 0) return 0;
@@ -1039,7 +1040,7 @@ static int fwd_should_fuse(nint_plan* p, int l, bool* fuse) {
   const int per_group = g.cluster * g.group;
   const double groups = (static_cast<double>(p->B) * p->tiles_x * p->tiles_y + per_group - 1) / per_group;
   const int clusters = p->num_sms / (g.cluster * g.n_blocks);
-  *fuse = clusters > 0 && groups / clusters <= 8.0;
+  *fuse = clusters > 0 && groups / clusters <= 16.0;
   return 0;
 }
 
@@ -1317,10 +1318,11 @@ static int bwd_conv_params(nint_plan* p, int l, bool has_next, ConvGemmParams& g
 }
 
 // Time-fused BPTT launch (ConvGemmParams::n_steps) or one launch per step?  Fusing removes the pipeline drain and the
-// tail imbalance of every launch but makes the kernel's steady state ~5 % slower (hand-off polling, storers waiting for
-// write completion): measured on B200 it pays while a launch is short -- a CTA pair walks few tile groups per step
-// (reference recipe, 3.8 rounds: -2.6 %; cfg 2 at B=8, 2.9 rounds: -2.9 %) -- is neutral at 5.8 rounds (B=16) and costs
-// +0.5 % at 11.7 (B=32).  NINT_FUSE_STEPS bit 1 forces it, 0 forbids it.
+// tail imbalance of every launch; the fused kernel's steady state is a little slower (hand-off polling, storers waiting
+// for write completion).  Measured on B200 with the last build of round 2 (same box, alternating runs): it pays while a
+// launch is short -- a CTA pair walks few tile groups per step: reference recipe (3.8 rounds) -5 %, cfg 2 at B=8 (2.9
+// rounds) -5.7 %, B=16 (5.8) -2.6 %, B=24 (8.8) -1 % -- and is neutral at 11.7 rounds (B=32: +0.2 %).
+// NINT_FUSE_STEPS bit 1 forces it, 0 forbids it.
 static int bwd_should_fuse(nint_plan* p, int l, bool* fuse) {
   *fuse = false;
   const int SB = p->sub_batch > 0 ? p->sub_batch : p->B;
@@ -1334,7 +1336,7 @@ static int bwd_should_fuse(nint_plan* p, int l, bool* fuse) {
   const int per_group = g.cluster * g.group;
   const double groups = (static_cast<double>(p->B) * p->tiles_x * p->tiles_y + per_group - 1) / per_group;
   const int clusters = p->num_sms / g.cluster;
-  *fuse = clusters > 0 && groups / clusters <= 5.0;
+  *fuse = clusters > 0 && groups / clusters <= 10.0;
   return 0;
 }
 

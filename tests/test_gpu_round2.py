@@ -459,7 +459,7 @@ def test_time_fused_launches_change_nothing(monkeypatch, hidden, ks, precision, 
 
 def test_time_fused_rule_follows_the_launch_length(monkeypatch):
     """default schedule: a layer's BPTT steps are ONE launch (after the step without a dgates_{t+1} operand) while a
-    CTA pair walks at most 5 tile groups per step, one launch per step for long launches such as BASELINE cfg 2 at
+    CTA pair walks at most 10 tile groups per step, one launch per step for long launches such as BASELINE cfg 2 at
     B=32; NINT_FUSE_STEPS=0 forbids fusing (counted through nint_launch_count, class 1 = dgrad + gate backward)"""
     from nasa_niswan_b200 import ConvLSTM, _lib
     lib = _lib.load()
