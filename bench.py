@@ -509,7 +509,7 @@ def main():
                        "parallelism": f"dp{world}", "l2_policy": "inputs (418 MB/step at B=32) larger than the 126 MB L2",
                        "loss_at_end": round(float(loss), 5), "numa_node": numa,
                        "sub_batch": int(os.environ.get("NINT_SUB_BATCH", "0") or 0),
-                       "pdl": int(os.environ.get("NINT_PDL", "1") or 0),
+                       "pdl": int(os.environ.get("NINT_PDL", "0") or 0),
                        "time_fused_launches": os.environ.get("NINT_FUSE_STEPS", "auto (BPTT launches fused when short)")},
             "e2e": e2e,
             "e2e_variants": variants,

@@ -149,7 +149,11 @@ struct nint_plan {
   bool gates_valid = false; // the saved activated gates of the last forward are intact (BPTT overwrites them in place)
   bool bptt_done = false;   // dgates of the last forward are in place: nint_backward_wgrad may run
   bool deterministic = false, input_grad = false;
-  int pdl = 1;              // programmatic dependent launch of the conv kernels (NINT_PDL=0 switches it off)
+  // Programmatic dependent launch of the conv kernels (NINT_PDL=1 switches it on).  OFF by default: it buys 0.4-0.6 % at
+  // cfg 2, but with the last build of round 2 the one-launch-per-step schedule of the reference's three-layer recipe
+  // died with "unspecified launch failure" at a random step in 4 of 8 (and 5 of 12) 150-step runs with it and in 0 of
+  // 8 without it (same box, alternating: tools/gpurun/r2_run_fz.sh).  Cause unknown.
+  int pdl = 0;
   int sub_batch = 0;        // > 0: sub-batch-major schedule (images [b0, b0 + sub_batch) run all T steps before the next
                             // slice, so a step's recurrent operands are still in L2 when the next step reads them)
   int final_slot_h = 0, final_slot_c = 0;
@@ -756,7 +760,7 @@ int nint_plan_create(const nint_config* cfg, nint_plan** out) {
     p->plan_ns = pn ? atoi(pn) : 0;
     if (const char* e = getenv("NINT_DETERMINISTIC")) p->deterministic = p->deterministic || atoi(e) != 0;
     const char* pd = getenv("NINT_PDL");
-    p->pdl = pd ? (atoi(pd) != 0) : 1;   // on by default: -0.4..0.6 % step time at cfg 2, -3 % at cfg 1, -1 % on the shipped model
+    p->pdl = pd ? (atoi(pd) != 0) : 0;   // off by default (see nint_plan::pdl)
     if (const char* e = getenv("NINT_FUSE_STEPS")) p->fuse_steps = atoi(e);   // bit 0: forward, bit 1: backward
     const char* sb = getenv("NINT_SUB_BATCH");
     p->sub_batch = sb ? atoi(sb) : 0;

@@ -61,7 +61,7 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / a.steps
-    print(f"pdl={os.environ.get('NINT_PDL', '1')} bank={int(a.bank)} graph={int(a.graph)} shipped={int(a.shipped)} B={B} T={T} k{a.ksize}: "
+    print(f"pdl={os.environ.get('NINT_PDL', '0')} bank={int(a.bank)} graph={int(a.graph)} shipped={int(a.shipped)} B={B} T={T} k{a.ksize}: "
           f"{ms:.3f} ms/step, {B / ms * 1e3:.0f} samples/s over {a.steps} steps, loss {float(loss):.4f}", flush=True)
     if a.profile and not a.bank:
         plan = net.plan_for(x, True)
