@@ -85,6 +85,21 @@ def test_plan_validation_and_workspace_accounting():
         assert rc != 0 and lib.nint_last_error(), bad
 
 
+def test_product_build_refuses_the_kernel_experiment_knobs(monkeypatch):
+    # NINT_DEBUG_FLAGS (skip the epilogue's memory work, issue no MMAs, timeline stamps ...) are compiled into the
+    # experiment build only (build.py --knobs -> libnint_knobs.so); the product library says so instead of ignoring them.
+    # Bit 9 (512: no bias folding) is host-side and stays available
+    monkeypatch.setenv("NINT_DEBUG_FLAGS", "2")
+    rc, h, lib = _create(_cfg())
+    assert rc != 0 and b"experiment build" in lib.nint_last_error()
+    monkeypatch.setenv("NINT_DEBUG_FLAGS", "512")
+    rc, h, lib = _create(_cfg())
+    assert rc == 0
+    lib.nint_plan_destroy(h)
+    from nasa_niswan_b200 import build
+    assert build.LIB_KNOBS.endswith("libnint_knobs.so") and build.LIB != build.LIB_KNOBS
+
+
 def test_any_hidden_size_is_accepted_by_padding():
     # model.py:207 takes any int (the notebooks use ConvLSTM(5, 10, 3, 2)-style sizes): hidden sizes run padded to the
     # kernels' granularity (16; 64 above 64), so the workspace of hidden 10 equals that of hidden 16, 70 that of 128
